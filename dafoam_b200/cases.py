@@ -1,0 +1,476 @@
+"""Synthetic OpenFOAM cases for the adjoint hot path.
+
+The reference ships no mesh: every test `chdir`s into a case directory that is downloaded at test
+time (reference tests/Allrun:9-18).  This module generates cases of the same *shape* as the ones
+the reference's tests and BASELINE.json name -- a one-cell-thick NACA0012 O-grid with patches
+`wing` (wall), `inout` (farfield) and two `symmetry` planes (reference
+tests/runRegTests_AeroOpt.py:29-101), optionally extruded to a 3-D wing, and a convergent channel
+(reference tests/runRegTests_DASimpleFoamForward.py:32) -- and writes them in OpenFOAM `polyMesh`
+format (ASCII, or the `format binary` variant for million-cell meshes) together with `0/`,
+`constant/` and `system/` dictionaries that the C++ host reader of the engine parses.
+
+It is input synthesis only: nothing here is on the timed path.
+"""
+from __future__ import annotations
+
+import os
+import numpy as np
+
+# ----------------------------------------------------------------------------------------------
+# mesh container
+# ----------------------------------------------------------------------------------------------
+
+
+class PolyMesh:
+    """points (nP,3) f64; faces (nF,4) i32 (quads); owner (nF) i32; neighbour (nIF) i32;
+    patches: list of dict(name,type,start,size).  Internal faces come first, ordered by
+    (owner, neighbour); boundary faces are grouped patch by patch (OpenFOAM convention)."""
+
+    def __init__(self, points, faces, owner, neighbour, patches):
+        self.points = np.ascontiguousarray(points, dtype=np.float64)
+        self.faces = np.ascontiguousarray(faces, dtype=np.int32)
+        self.owner = np.ascontiguousarray(owner, dtype=np.int32)
+        self.neighbour = np.ascontiguousarray(neighbour, dtype=np.int32)
+        self.patches = patches
+
+    @property
+    def n_cells(self):
+        return int(self.owner.max()) + 1
+
+    @property
+    def n_faces(self):
+        return self.faces.shape[0]
+
+    @property
+    def n_internal_faces(self):
+        return self.neighbour.shape[0]
+
+    @property
+    def n_points(self):
+        return self.points.shape[0]
+
+
+def _naca0012_y(x):
+    # closed trailing edge variant (last coefficient -0.1036)
+    return 0.6 * (0.2969 * np.sqrt(np.maximum(x, 0.0)) - 0.1260 * x - 0.3516 * x**2 + 0.2843 * x**3 - 0.1036 * x**4)
+
+
+def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_centres):
+    """Orient faces (normal owner->neighbour / outward), sort, and build a PolyMesh.
+
+    quads: (n,4) point ids; cell_a: (n,) one adjacent cell; cell_b: (n,) other cell or -1;
+    patch_of_bface: (n,) patch index for boundary faces (ignored for internal)."""
+    quads = quads.copy()
+    internal = cell_b >= 0
+    own = np.where(internal, np.minimum(cell_a, cell_b), cell_a)
+    nei = np.where(internal, np.maximum(cell_a, cell_b), -1)
+    p = points[quads]  # (n,4,3)
+    fc = p.mean(axis=1)
+    # area vector of a quad by its diagonals
+    nrm = 0.5 * np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 1])
+    ref = np.where(internal[:, None], cell_centres[np.maximum(nei, 0)] - cell_centres[own], fc - cell_centres[own])
+    flip = np.einsum("ij,ij->i", nrm, ref) < 0
+    quads[flip] = quads[flip][:, ::-1]
+    # internal faces sorted by (owner, neighbour)
+    ii = np.nonzero(internal)[0]
+    order_i = ii[np.lexsort((nei[ii], own[ii]))]
+    bi = np.nonzero(~internal)[0]
+    order_b = bi[np.lexsort((np.arange(bi.size), patch_of_bface[bi]))]
+    order = np.concatenate([order_i, order_b])
+    faces = quads[order]
+    owner = own[order]
+    neighbour = nei[order_i]
+    patches = []
+    start = order_i.size
+    pb = patch_of_bface[order_b]
+    for k, (name, typ) in enumerate(patch_defs):
+        n = int(np.count_nonzero(pb == k))
+        patches.append(dict(name=name, type=typ, start=start, size=n))
+        start += n
+    return PolyMesh(points, faces, owner, neighbour, patches)
+
+
+def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3):
+    """NACA0012 O-grid: ni cells around the airfoil, nj cells radially (geometric stretching
+    from `first_dy` chord at the wall to the farfield circle of `radius` chords), nk cells in z.
+    Patches: wing (wall), inout (patch), sym1/sym2 (symmetry)."""
+    assert ni % 2 == 0
+    th = 2.0 * np.pi * np.arange(ni) / ni
+    xa = 0.5 * (1.0 + np.cos(th))
+    ya = np.where(th <= np.pi, 1.0, -1.0) * _naca0012_y(xa)
+    # farfield circle around mid-chord
+    xf = 0.5 + radius * np.cos(th)
+    yf = radius * np.sin(th)
+    # radial distribution s_j in [0,1], geometric growth
+    n = nj
+    lo, hi = 1.0 + 1e-9, 2.0
+    tot = radius
+
+    def total(r):
+        return first_dy * (r**n - 1.0) / (r - 1.0)
+
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        if total(mid) > tot:
+            hi = mid
+        else:
+            lo = mid
+    r = 0.5 * (lo + hi)
+    s = np.concatenate([[0.0], np.cumsum(first_dy * r ** np.arange(n))])
+    s = s / s[-1]
+    X = xa[None, :] + s[:, None] * (xf - xa)[None, :]  # (nj+1, ni)
+    Y = ya[None, :] + s[:, None] * (yf - ya)[None, :]
+    z = np.linspace(0.0, span, nk + 1)
+    npl = ni * (nj + 1)
+    points = np.empty(((nk + 1) * npl, 3))
+    for k in range(nk + 1):
+        points[k * npl:(k + 1) * npl, 0] = X.ravel()
+        points[k * npl:(k + 1) * npl, 1] = Y.ravel()
+        points[k * npl:(k + 1) * npl, 2] = z[k]
+
+    def pid(i, j, k):
+        return (i % ni) + ni * (j + (nj + 1) * k)
+
+    def cid(i, j, k):
+        return (i % ni) + ni * (j + nj * k)
+
+    I, J, K = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    # cell centres (mean of 8 corners) for orientation
+    corners = [pid(I + a, J + b, K + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+    cc = np.zeros((ni * nj * nk, 3))
+    cells = cid(I, J, K)
+    acc = sum(points[c] for c in corners) / 8.0
+    cc[cells] = acc
+
+    quads, ca, cb, pf = [], [], [], []
+
+    def add(q, a, b, patch):
+        quads.append(np.stack(q, axis=1))
+        ca.append(a)
+        cb.append(b)
+        pf.append(np.full(a.shape, patch, dtype=np.int64))
+
+    # i-faces (periodic in i): between (i,j,k) and (i+1,j,k)
+    add([pid(I + 1, J, K), pid(I + 1, J + 1, K), pid(I + 1, J + 1, K + 1), pid(I + 1, J, K + 1)],
+        cid(I, J, K), cid(I + 1, J, K), -1)
+    # j-faces
+    m = J >= 1
+    add([pid(I[m], J[m], K[m]), pid(I[m] + 1, J[m], K[m]), pid(I[m] + 1, J[m], K[m] + 1), pid(I[m], J[m], K[m] + 1)],
+        cid(I[m], J[m] - 1, K[m]), cid(I[m], J[m], K[m]), -1)
+    # k-faces
+    m = K >= 1
+    if m.any():
+        add([pid(I[m], J[m], K[m]), pid(I[m] + 1, J[m], K[m]), pid(I[m] + 1, J[m] + 1, K[m]), pid(I[m], J[m] + 1, K[m])],
+            cid(I[m], J[m], K[m] - 1), cid(I[m], J[m], K[m]), -1)
+    # boundary: wing (j=0), inout (j=nj), sym1 (k=0), sym2 (k=nk)
+    m = J == 0
+    add([pid(I[m], 0 * J[m], K[m]), pid(I[m] + 1, 0 * J[m], K[m]), pid(I[m] + 1, 0 * J[m], K[m] + 1), pid(I[m], 0 * J[m], K[m] + 1)],
+        cid(I[m], J[m], K[m]), np.full(m.sum(), -1), 0)
+    m = J == nj - 1
+    add([pid(I[m], J[m] + 1, K[m]), pid(I[m] + 1, J[m] + 1, K[m]), pid(I[m] + 1, J[m] + 1, K[m] + 1), pid(I[m], J[m] + 1, K[m] + 1)],
+        cid(I[m], J[m], K[m]), np.full(m.sum(), -1), 1)
+    m = K == 0
+    add([pid(I[m], J[m], K[m]), pid(I[m] + 1, J[m], K[m]), pid(I[m] + 1, J[m] + 1, K[m]), pid(I[m], J[m] + 1, K[m])],
+        cid(I[m], J[m], K[m]), np.full(m.sum(), -1), 2)
+    m = K == nk - 1
+    add([pid(I[m], J[m], K[m] + 1), pid(I[m] + 1, J[m], K[m] + 1), pid(I[m] + 1, J[m] + 1, K[m] + 1), pid(I[m], J[m] + 1, K[m] + 1)],
+        cid(I[m], J[m], K[m]), np.full(m.sum(), -1), 3)
+
+    quads = np.concatenate(quads).astype(np.int32)
+    ca = np.concatenate(ca).astype(np.int64)
+    cb = np.concatenate(cb).astype(np.int64)
+    pf = np.concatenate(pf)
+    defs = [("wing", "wall"), ("inout", "patch"), ("sym1", "symmetry"), ("sym2", "symmetry")]
+    return _assemble(points, quads, ca, cb, pf, defs, cc)
+
+
+def channel(nx=20, ny=10, nz=1, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.15):
+    """Convergent channel: inlet (x=0), outlet (x=lx), lower/upper walls, two symmetry planes.
+    The upper wall descends by `contraction`*ly and interior lines are sheared by `skew`
+    so the mesh is non-orthogonal (exercises the corrected snGrad / laplacian terms)."""
+    xs = np.linspace(0.0, lx, nx + 1)
+    et = np.linspace(0.0, 1.0, ny + 1)
+    zs = np.linspace(0.0, lz, nz + 1)
+    h = ly * (1.0 - contraction * 0.5 * (1.0 - np.cos(np.pi * xs / lx)))
+    Xg = xs[:, None] + skew * ly * np.sin(np.pi * et)[None, :] * np.sin(np.pi * xs / lx)[:, None]
+    Yg = et[None, :] * h[:, None]
+
+    def pid(i, j, k):
+        return i + (nx + 1) * (j + (ny + 1) * k)
+
+    def cid(i, j, k):
+        return i + nx * (j + ny * k)
+
+    points = np.empty(((nx + 1) * (ny + 1) * (nz + 1), 3))
+    Ip, Jp, Kp = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    idx = pid(Ip, Jp, Kp).ravel()
+    points[idx, 0] = Xg[Ip.ravel(), Jp.ravel()]
+    points[idx, 1] = Yg[Ip.ravel(), Jp.ravel()]
+    points[idx, 2] = zs[Kp.ravel()]
+
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    corners = [pid(I + a, J + b, K + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+    cc = np.zeros((nx * ny * nz, 3))
+    cc[cid(I, J, K)] = sum(points[c] for c in corners) / 8.0
+
+    quads, ca, cb, pf = [], [], [], []
+
+    def add(q, a, b, patch):
+        quads.append(np.stack(q, axis=1))
+        ca.append(a)
+        cb.append(b)
+        pf.append(np.full(a.shape, patch, dtype=np.int64))
+
+    def xface(i, j, k):
+        return [pid(i, j, k), pid(i, j + 1, k), pid(i, j + 1, k + 1), pid(i, j, k + 1)]
+
+    def yface(i, j, k):
+        return [pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j, k + 1), pid(i, j, k + 1)]
+
+    def zface(i, j, k):
+        return [pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)]
+
+    m = I >= 1
+    add(xface(I[m], J[m], K[m]), cid(I[m] - 1, J[m], K[m]), cid(I[m], J[m], K[m]), -1)
+    m = J >= 1
+    add(yface(I[m], J[m], K[m]), cid(I[m], J[m] - 1, K[m]), cid(I[m], J[m], K[m]), -1)
+    m = K >= 1
+    if m.any():
+        add(zface(I[m], J[m], K[m]), cid(I[m], J[m], K[m] - 1), cid(I[m], J[m], K[m]), -1)
+    none = lambda m: np.full(int(m.sum()), -1)
+    m = I == 0
+    add(xface(I[m], J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 0)
+    m = I == nx - 1
+    add(xface(I[m] + 1, J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 1)
+    m = J == 0
+    add(yface(I[m], J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 2)
+    m = J == ny - 1
+    add(yface(I[m], J[m] + 1, K[m]), cid(I[m], J[m], K[m]), none(m), 2)
+    m = K == 0
+    add(zface(I[m], J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 3)
+    m = K == nz - 1
+    add(zface(I[m], J[m], K[m] + 1), cid(I[m], J[m], K[m]), none(m), 4)
+    quads = np.concatenate(quads).astype(np.int32)
+    defs = [("inlet", "patch"), ("outlet", "patch"), ("walls", "wall"), ("sym1", "symmetry"), ("sym2", "symmetry")]
+    return _assemble(points, quads, np.concatenate(ca).astype(np.int64), np.concatenate(cb).astype(np.int64),
+                     np.concatenate(pf), defs, cc)
+
+
+# ----------------------------------------------------------------------------------------------
+# OpenFOAM writers
+# ----------------------------------------------------------------------------------------------
+
+_HDR = """FoamFile
+{{
+    version     2.0;
+    format      {fmt};
+    class       {cls};
+    location    "{loc}";
+    object      {obj};
+}}
+"""
+
+
+def _header(cls, loc, obj, fmt="ascii", note=None):
+    s = _HDR.format(fmt=fmt, cls=cls, loc=loc, obj=obj)
+    if note:
+        s = s.replace("    object ", "    note        \"%s\";\n    object " % note)
+    return s
+
+
+def write_polymesh(case_dir, mesh: PolyMesh, binary=False):
+    pm = os.path.join(case_dir, "constant", "polyMesh")
+    os.makedirs(pm, exist_ok=True)
+    fmt = "binary" if binary else "ascii"
+    note = "nPoints:%d  nCells:%d  nFaces:%d  nInternalFaces:%d" % (
+        mesh.n_points, mesh.n_cells, mesh.n_faces, mesh.n_internal_faces)
+    # points
+    with open(os.path.join(pm, "points"), "wb") as f:
+        f.write(_header("vectorField", "constant/polyMesh", "points", fmt).encode())
+        f.write(b"\n%d\n(" % mesh.n_points)
+        if binary:
+            f.write(mesh.points.tobytes())
+        else:
+            f.write(b"\n")
+            f.write("\n".join("(%.17g %.17g %.17g)" % tuple(p) for p in mesh.points).encode())
+            f.write(b"\n")
+        f.write(b")\n")
+    # faces
+    with open(os.path.join(pm, "faces"), "wb") as f:
+        if binary:
+            # faceCompactList: offsets then flat labels
+            f.write(_header("faceCompactList", "constant/polyMesh", "faces", fmt).encode())
+            nf, w = mesh.faces.shape
+            offs = (np.arange(nf + 1, dtype=np.int32) * w).astype(np.int32)
+            f.write(b"\n%d\n(" % (nf + 1))
+            f.write(offs.tobytes())
+            f.write(b")\n\n%d\n(" % (nf * w))
+            f.write(mesh.faces.tobytes())
+            f.write(b")\n")
+        else:
+            f.write(_header("faceList", "constant/polyMesh", "faces", fmt).encode())
+            f.write(b"\n%d\n(\n" % mesh.n_faces)
+            f.write("\n".join("4(%d %d %d %d)" % tuple(q) for q in mesh.faces).encode())
+            f.write(b"\n)\n")
+    for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
+        with open(os.path.join(pm, name), "wb") as f:
+            f.write(_header("labelList", "constant/polyMesh", name, fmt, note).encode())
+            f.write(b"\n%d\n(" % arr.size)
+            if binary:
+                f.write(arr.astype(np.int32).tobytes())
+            else:
+                f.write(b"\n")
+                f.write("\n".join(str(int(v)) for v in arr).encode())
+                f.write(b"\n")
+            f.write(b")\n")
+    with open(os.path.join(pm, "boundary"), "w") as f:
+        f.write(_header("polyBoundaryMesh", "constant/polyMesh", "boundary"))
+        f.write("\n%d\n(\n" % len(mesh.patches))
+        for p in mesh.patches:
+            f.write("    %s\n    {\n        type            %s;\n" % (p["name"], p["type"]))
+            if p["type"] == "wall":
+                f.write("        inGroups        1(wall);\n")
+            f.write("        nFaces          %d;\n        startFace       %d;\n    }\n" % (p["size"], p["start"]))
+        f.write(")\n")
+
+
+def _fmt_val(v):
+    if np.ndim(v) == 0:
+        return "%.17g" % float(v)
+    return "(" + " ".join("%.17g" % float(x) for x in v) + ")"
+
+
+def write_field(case_dir, name, cls, dims, internal, bcs, time="0"):
+    """internal: scalar/3-vector (uniform) or ndarray (nonuniform).  bcs: {patch: dict(type=..., ...)}."""
+    d = os.path.join(case_dir, time)
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, name), "w") as f:
+        f.write(_header(cls, time, name))
+        f.write("\ndimensions      %s;\n\n" % dims)
+        arr = np.asarray(internal, dtype=np.float64)
+        is_vec = cls == "volVectorField"
+        if (is_vec and arr.ndim == 1) or (not is_vec and arr.ndim == 0):
+            f.write("internalField   uniform %s;\n\n" % _fmt_val(arr))
+        else:
+            f.write("internalField   nonuniform List<%s>\n%d\n(\n" % ("vector" if is_vec else "scalar", arr.shape[0]))
+            if is_vec:
+                f.write("\n".join("(%.17g %.17g %.17g)" % tuple(v) for v in arr))
+            else:
+                f.write("\n".join("%.17g" % v for v in arr))
+            f.write("\n)\n;\n\n")
+        f.write("boundaryField\n{\n")
+        for patch, bc in bcs.items():
+            f.write("    %s\n    {\n        type            %s;\n" % (patch, bc["type"]))
+            for k, v in bc.items():
+                if k == "type":
+                    continue
+                f.write("        %-15s uniform %s;\n" % (k, _fmt_val(np.asarray(v, dtype=np.float64))))
+            f.write("    }\n")
+        f.write("}\n")
+
+
+def write_dicts(case_dir, nu=1.5e-5, ras_model="SpalartAllmaras", div_u="bounded Gauss linearUpwind grad(U)",
+                div_nut="bounded Gauss upwind", relax_u=0.7, relax_p=0.3, relax_nut=0.7, consistent=False):
+    os.makedirs(os.path.join(case_dir, "constant"), exist_ok=True)
+    os.makedirs(os.path.join(case_dir, "system"), exist_ok=True)
+    with open(os.path.join(case_dir, "constant", "transportProperties"), "w") as f:
+        f.write(_header("dictionary", "constant", "transportProperties"))
+        f.write("\ntransportModel  Newtonian;\n\nnu              %.17g;\nPr 0.7;\nPrt 0.85;\n" % nu)
+    with open(os.path.join(case_dir, "constant", "turbulenceProperties"), "w") as f:
+        f.write(_header("dictionary", "constant", "turbulenceProperties"))
+        f.write("\nsimulationType RAS;\nRAS\n{\n    RASModel        %s;\n    turbulence      on;\n    printCoeffs     off;\n}\n" % ras_model)
+    with open(os.path.join(case_dir, "system", "fvSchemes"), "w") as f:
+        f.write(_header("dictionary", "system", "fvSchemes"))
+        f.write("""
+ddtSchemes { default steadyState; }
+gradSchemes { default Gauss linear; }
+divSchemes
+{
+    default         none;
+    div(phi,U)      %s;
+    div(phi,nuTilda) %s;
+    div((nuEff*dev2(T(grad(U))))) Gauss linear;
+    div(pc)         bounded Gauss upwind;
+}
+laplacianSchemes { default Gauss linear corrected; }
+interpolationSchemes { default linear; }
+snGradSchemes { default corrected; }
+wallDist { method meshWaveFrozen; }
+""" % (div_u, div_nut))
+    with open(os.path.join(case_dir, "system", "fvSolution"), "w") as f:
+        f.write(_header("dictionary", "system", "fvSolution"))
+        f.write("""
+SIMPLE
+{
+    nNonOrthogonalCorrectors 0;
+    consistent %s;
+}
+relaxationFactors
+{
+    fields { p %.17g; }
+    equations { U %.17g; nuTilda %.17g; }
+}
+""" % ("true" if consistent else "false", relax_p, relax_u, relax_nut))
+    with open(os.path.join(case_dir, "system", "controlDict"), "w") as f:
+        f.write(_header("dictionary", "system", "controlDict"))
+        f.write("\napplication simpleFoam;\nstartTime 0;\nendTime 1000;\ndeltaT 1;\n")
+
+
+def default_bcs_naca(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True):
+    """Boundary conditions of the reference's NACA0012 incompressible case family
+    (wing wall, inout farfield, symmetry planes)."""
+    U0 = tuple(float(x) for x in U0)
+    bcs = {
+        "U": ("volVectorField", "[0 1 -1 0 0 0 0]", U0, {
+            "wing": dict(type="fixedValue", value=(0.0, 0.0, 0.0)),
+            "inout": dict(type="inletOutlet", inletValue=U0, value=U0),
+            "sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")}),
+        "p": ("volScalarField", "[0 2 -2 0 0 0 0]", 0.0, {
+            "wing": dict(type="zeroGradient"),
+            "inout": dict(type="outletInlet", outletValue=0.0, value=0.0),
+            "sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")}),
+    }
+    if turbulent:
+        bcs["nuTilda"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, {
+            "wing": dict(type="fixedValue", value=0.0),
+            "inout": dict(type="inletOutlet", inletValue=nuTilda0, value=nuTilda0),
+            "sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")})
+        bcs["nut"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, {
+            "wing": dict(type="nutLowReWallFunction", value=0.0),
+            "inout": dict(type="calculated", value=0.0),
+            "sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")})
+    return bcs
+
+
+def default_bcs_channel(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True):
+    U0 = tuple(float(x) for x in U0)
+    sym = {"sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")}
+    bcs = {
+        "U": ("volVectorField", "[0 1 -1 0 0 0 0]", U0, dict(
+            inlet=dict(type="fixedValue", value=U0), outlet=dict(type="inletOutlet", inletValue=(0.0, 0.0, 0.0), value=U0),
+            walls=dict(type="fixedValue", value=(0.0, 0.0, 0.0)), **sym)),
+        "p": ("volScalarField", "[0 2 -2 0 0 0 0]", 0.0, dict(
+            inlet=dict(type="zeroGradient"), outlet=dict(type="fixedValue", value=0.0),
+            walls=dict(type="zeroGradient"), **sym)),
+    }
+    if turbulent:
+        bcs["nuTilda"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, dict(
+            inlet=dict(type="fixedValue", value=nuTilda0), outlet=dict(type="zeroGradient"),
+            walls=dict(type="fixedValue", value=0.0), **sym))
+        bcs["nut"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, dict(
+            inlet=dict(type="calculated", value=0.0), outlet=dict(type="calculated", value=0.0),
+            walls=dict(type="nutLowReWallFunction", value=0.0), **sym))
+    return bcs
+
+
+def write_case(case_dir, mesh: PolyMesh, bcs, binary=False, **dict_kw):
+    """Write polyMesh + 0/ fields + dictionaries.  `bcs` as returned by default_bcs_*."""
+    write_polymesh(case_dir, mesh, binary=binary)
+    for name, (cls, dims, internal, patch_bcs) in bcs.items():
+        write_field(case_dir, name, cls, dims, internal, patch_bcs)
+    ras = "SpalartAllmaras" if "nuTilda" in bcs else "dummy"
+    dict_kw.setdefault("ras_model", ras)
+    write_dicts(case_dir, **dict_kw)
+    return case_dir

@@ -1,0 +1,188 @@
+"""ctypes wrapper of the CPU oracle (oracle/oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package (dafoam_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+BC_KIND = {"fixedValue": 0, "zeroGradient": 1, "inletOutlet": 2, "outletInlet": 3, "symmetry": 4,
+           "calculated": 5, "nutLowReWallFunction": 6}
+GEOM_KIND = {"patch": 0, "wall": 1, "symmetry": 2}
+DIV_SCHEME = {"upwind": 0, "linearUpwind": 1, "linear": 2}
+FIELDS = ["U", "p", "nuTilda", "nut"]
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        L = _LIB
+        L.orc_create.restype = C.c_void_p
+        L.orc_ndof.argtypes = [C.c_void_p]
+        L.orc_ncells.argtypes = [C.c_void_p]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_record.restype = C.c_long
+        L.orc_force.restype = C.c_double
+        L.orc_tape_size.restype = C.c_long
+    return _LIB
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def bc_tables(mesh, bcs):
+    """Return (kind[4,nPatch] i32, value[4,nPatch,3] f64) from a cases.default_bcs_* dict."""
+    npatch = len(mesh.patches)
+    kind = np.full((4, npatch), BC_KIND["zeroGradient"], dtype=np.int32)
+    value = np.zeros((4, npatch, 3))
+    for fi, fname in enumerate(FIELDS):
+        if fname not in bcs:
+            continue
+        pb = bcs[fname][3]
+        for pi, patch in enumerate(mesh.patches):
+            bc = pb[patch["name"]]
+            kind[fi, pi] = BC_KIND[bc["type"]]
+            ref = None
+            for key in ("inletValue", "outletValue", "value"):
+                if key in bc:
+                    ref = bc[key]
+                    break
+            if ref is not None:
+                ref = np.atleast_1d(np.asarray(ref, dtype=np.float64))
+                value[fi, pi, :ref.size] = ref
+    return kind, value
+
+
+class Oracle:
+    def __init__(self, mesh, bcs, nu=1.5e-5, alphaU=0.7, divU="linearUpwind", divNut="upwind",
+                 normalizeStates=None, normalizeResiduals=("URes", "pRes", "nuTildaRes", "phiRes"),
+                 constrainHbyA=True, yWall=None):
+        L = lib()
+        self.mesh = mesh
+        self.turb = "nuTilda" in bcs
+        ns = dict(U=1.0, p=1.0, nuTilda=1.0, phi=1.0)
+        ns.update(normalizeStates or {})
+        kind, value = bc_tables(mesh, bcs)
+        nf, w = mesh.faces.shape
+        foff = (np.arange(nf + 1) * w).astype(np.int32)
+        flab = np.ascontiguousarray(mesh.faces.ravel(), dtype=np.int32)
+        pstart = np.array([p["start"] for p in mesh.patches], dtype=np.int32)
+        psize = np.array([p["size"] for p in mesh.patches], dtype=np.int32)
+        pgeom = np.array([GEOM_KIND.get(p["type"], 0) for p in mesh.patches], dtype=np.int32)
+        dpar = np.array([nu, alphaU, ns["U"], ns["p"], ns["nuTilda"], ns["phi"]], dtype=np.float64)
+        ipar = np.array([int(self.turb), DIV_SCHEME[divU], DIV_SCHEME[divNut],
+                         int("URes" in normalizeResiduals), int("pRes" in normalizeResiduals),
+                         int("nuTildaRes" in normalizeResiduals), int("phiRes" in normalizeResiduals),
+                         int(constrainHbyA)], dtype=np.int32)
+        yw = None if yWall is None else _p(np.ascontiguousarray(yWall, dtype=np.float64))
+        self._keep = (foff, flab, pstart, psize, pgeom, kind, value, dpar, ipar)
+        self.h = C.c_void_p(L.orc_create(
+            C.c_int(mesh.n_points), _p(mesh.points), C.c_int(nf), _p(foff, C.c_int), _p(flab, C.c_int),
+            _p(mesh.owner, C.c_int), C.c_int(mesh.n_internal_faces), _p(mesh.neighbour, C.c_int),
+            C.c_int(len(mesh.patches)), _p(pstart, C.c_int), _p(psize, C.c_int), _p(pgeom, C.c_int),
+            _p(kind, C.c_int), _p(value), _p(dpar), _p(ipar, C.c_int), yw))
+        self.ndof = L.orc_ndof(self.h)
+        self.ncells = L.orc_ncells(self.h)
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self.h)
+        except Exception:
+            pass
+
+    def geometry(self, what):
+        sizes = {"V": (0, self.ncells), "magSf": (1, self.mesh.n_faces), "w": (2, self.mesh.n_faces),
+                 "delta": (3, self.mesh.n_faces), "yWall": (4, self.ncells), "C": (5, 3 * self.ncells),
+                 "Sf": (6, 3 * self.mesh.n_faces), "Cf": (7, 3 * self.mesh.n_faces), "corr": (8, 3 * self.mesh.n_faces)}
+        code, n = sizes[what]
+        out = np.zeros(n)
+        lib().orc_get_geometry(self.h, C.c_int(code), _p(out))
+        return out
+
+    def residual(self, W, isPC=0):
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        R = np.zeros(self.ndof)
+        lib().orc_residual(self.h, _p(W), C.c_int(isPC), _p(R))
+        return R
+
+    def record(self, W, isPC=0):
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        return lib().orc_record(self.h, _p(W), C.c_int(isPC))
+
+    def jtvec(self, psi, normalize=True):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        out = np.zeros(self.ndof)
+        lib().orc_jtvec(self.h, _p(psi), _p(out), C.c_int(int(normalize)))
+        return out
+
+    def force(self, W, patch, direction, scale=1.0):
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        return lib().orc_force(self.h, _p(W), C.c_int(patch), _p(d), C.c_double(scale))
+
+    def dforce_dw(self, W, patch, direction, scale=1.0, seed=1.0, normalize=True):
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        d = np.ascontiguousarray(direction, dtype=np.float64)
+        out = np.zeros(self.ndof)
+        lib().orc_dforce_dw(self.h, _p(W), C.c_int(patch), _p(d), C.c_double(scale), C.c_double(seed), _p(out),
+                            C.c_int(int(normalize)))
+        return out
+
+    def jtvec_xv(self, W, psi):
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        out = np.zeros(3 * self.mesh.n_points)
+        lib().orc_jtvec_xv(self.h, _p(W), _p(psi), _p(out))
+        return out
+
+
+def synthetic_state(mesh, geomC, Sf, U0=(10.0, 0.5, 0.0), nuTilda0=4.5e-5, turbulent=True, seed=1234, noise=0.01):
+    """Smooth analytic field + seeded 1 % noise: U, p, nuTilda at cells and a
+    face flux phi = U_f . Sf (+ noise) on all faces, in the reference's state ordering."""
+    rng = np.random.default_rng(seed)
+    nC = geomC.size // 3
+    Cc = geomC.reshape(nC, 3)
+    U0 = np.asarray(U0, dtype=np.float64)
+    Umag = np.linalg.norm(U0)
+    r2 = (Cc[:, 0] - 0.5) ** 2 + Cc[:, 1] ** 2
+    damp = 1.0 - np.exp(-r2 / 0.5)
+    U = U0[None, :] * damp[:, None]
+    U[:, 0] += 0.1 * Umag * np.sin(1.3 * Cc[:, 1]) * damp
+    U[:, 1] += 0.1 * Umag * np.cos(0.7 * Cc[:, 0]) * damp
+    U *= 1.0 + noise * rng.uniform(-1, 1, U.shape)
+    p = 0.5 * Umag**2 * (np.exp(-r2) - 0.3 * np.sin(Cc[:, 0])) * (1.0 + noise * rng.uniform(-1, 1, nC))
+    nt = nuTilda0 * (1.0 + 3.0 * np.exp(-r2 / 4.0)) * (1.0 + noise * rng.uniform(-1, 1, nC))
+    nF = mesh.n_faces
+    nIF = mesh.n_internal_faces
+    S = Sf.reshape(nF, 3)
+    Uf = np.empty((nF, 3))
+    Uf[:nIF] = 0.5 * (U[mesh.owner[:nIF]] + U[mesh.neighbour])
+    Uf[nIF:] = U[mesh.owner[nIF:]]
+    phi = np.einsum("ij,ij->i", Uf, S)
+    magS = np.linalg.norm(S, axis=1)
+    phi += noise * Umag * magS * rng.uniform(-1, 1, nF)
+    # symmetry-plane and wall faces carry no flux
+    for pch in mesh.patches:
+        if pch["type"] in ("symmetry", "wall"):
+            phi[pch["start"]:pch["start"] + pch["size"]] = 0.0
+    parts = [U.ravel(), p]
+    if turbulent:
+        parts.append(nt)
+    parts.append(phi)
+    return np.concatenate(parts)
