@@ -1,0 +1,295 @@
+// C ABI of libdab200.so (include/dab200.h).  Compiled by nvcc as CUDA (`-x cu`, sm_100a).
+#include "../../include/dab200.h"
+#include "solver.hpp"
+#include <cstring>
+#include <string>
+
+using namespace dab;
+
+struct dab_solver
+{
+    Solver s;
+};
+
+static thread_local std::string g_err;
+
+#define DAB_TRY try {
+#define DAB_CATCH                                   \
+    }                                               \
+    catch (const std::exception& e)                 \
+    {                                               \
+        g_err = e.what();                           \
+        return 1;                                   \
+    }                                               \
+    catch (...)                                     \
+    {                                               \
+        g_err = "unknown error";                    \
+        return 1;                                   \
+    }                                               \
+    return 0;
+
+static void need(const void* p, const char* what)
+{
+    if (!p) throw Error(std::string("null pointer: ") + what);
+}
+
+extern "C"
+{
+
+const char* dab_last_error(void) { return g_err.c_str(); }
+
+const char* dab_version(void)
+{
+#ifdef DAB_HOSTSIM
+    return "dab200 0.1 (HOSTSIM test build -- not the product)";
+#else
+    return "dab200 0.1 (sm_100a)";
+#endif
+}
+
+int dab_create(const char* case_dir, const char* args_all, const char* options_json, int device, int rank, int n_ranks,
+               const void* nccl_unique_id, dab_solver** out)
+{
+    DAB_TRY
+    need(case_dir, "case_dir");
+    need(out, "out");
+    (void)nccl_unique_id;
+    dab_solver* h = new dab_solver();
+    try
+    {
+        h->s.create(case_dir, args_all ? args_all : "DASimpleFoam -python", options_json ? options_json : "", device, rank, n_ranks);
+    }
+    catch (...)
+    {
+        delete h;
+        throw;
+    }
+    *out = h;
+    DAB_CATCH
+}
+
+int dab_destroy(dab_solver* s)
+{
+    DAB_TRY
+    if (s)
+    {
+        s->s.be.sync();
+        delete s;
+    }
+    DAB_CATCH
+}
+
+int dab_nccl_unique_id(void* out128)
+{
+    DAB_TRY
+    need(out128, "out128");
+    throw Error("multi-rank support is not built into this library");
+    DAB_CATCH
+}
+
+int dab_n_local_adjoint_states(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.nDof(); DAB_CATCH }
+int dab_n_local_cells(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nC; DAB_CATCH }
+int dab_n_global_cells(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nC; DAB_CATCH }
+int dab_n_local_points(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nP; DAB_CATCH }
+int dab_n_local_faces(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nF; DAB_CATCH }
+int dab_n_local_internal_faces(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nIF; DAB_CATCH }
+
+int dab_update_options(dab_solver* s, const char* options_json)
+{
+    DAB_TRY
+    need(s, "solver");
+    s->s.applyOptions(options_json ? options_json : "", false);
+    DAB_CATCH
+}
+
+int dab_update_of_fields(dab_solver* s, const double* states)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(states, "states");
+    s->s.updateOFFields(states);
+    DAB_CATCH
+}
+
+int dab_get_of_fields(dab_solver* s, double* states)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(states, "states");
+    s->s.getOFFields(states);
+    DAB_CATCH
+}
+
+int dab_get_of_mesh_points(dab_solver* s, double* points)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(points, "points");
+    memcpy(points, s->s.hm.points.data(), s->s.hm.points.size() * sizeof(double));
+    DAB_CATCH
+}
+
+int dab_get_of_field(dab_solver* s, const char* name, const char* type, double* field)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(name, "name");
+    need(field, "field");
+    (void)type;
+    Solver& S = s->s;
+    const std::string n(name);
+    const size_t nC = S.hm.nC;
+    if (n == "U") S.be.d2h(field, S.dU.p, 3 * nC * sizeof(double));
+    else if (n == "p") S.be.d2h(field, S.dP.p, nC * sizeof(double));
+    else if (n == "nuTilda") S.be.d2h(field, S.dNt.p, nC * sizeof(double));
+    else if (n == "nut") { S.ensureRecorded(); S.be.d2h(field, S.rNut.p, nC * sizeof(double)); }
+    else if (n == "yWall") memcpy(field, S.hm.yWall.data(), nC * sizeof(double));
+    else if (n == "V") memcpy(field, S.hm.V.data(), nC * sizeof(double));
+    else throw Error("getOFField: unknown field " + n);
+    DAB_CATCH
+}
+
+int dab_get_residuals(dab_solver* s, int is_pc, double* residuals)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(residuals, "residuals");
+    s->s.getResiduals(is_pc, residuals);
+    DAB_CATCH
+}
+
+int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char* input_type, const double* input,
+                               const char* output_name, const char* output_type, const double* seed, double* product)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(input_type, "input_type");
+    need(output_type, "output_type");
+    need(seed, "seed");
+    need(product, "product");
+    (void)input_name;
+    Solver& S = s->s;
+    const std::string it(input_type), ot(output_type);
+    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar)");
+    // daInput->run(inputList): assign the input to the OpenFOAM fields (DAInputStateVar.C:35-140)
+    if (input) S.updateOFFields(input);
+    if (ot == "residual") S.matVec(seed, product);
+    else if (ot == "function")
+    {
+        need(output_name, "output_name");
+        S.dFdW(output_name, seed[0], product);
+    }
+    else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported (residual, function)");
+    DAB_CATCH
+}
+
+int dab_drdwt_mat_vec(dab_solver* s, const double* x, double* y)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(x, "x");
+    need(y, "y");
+    s->s.matVec(x, y);
+    DAB_CATCH
+}
+
+int dab_calc_drdwt_pc(dab_solver* s)
+{
+    DAB_TRY
+    need(s, "solver");
+    s->s.calcPC();
+    DAB_CATCH
+}
+
+int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(rhs, "rhs");
+    need(sol, "sol");
+    KspStats st;
+    const int f = s->s.solveLinearEqn(rhs, sol, st);
+    if (fail) *fail = f;
+    if (stats)
+    {
+        stats->iterations = st.iterations;
+        stats->converged_reason = st.reason;
+        stats->initial_residual = st.r0;
+        stats->final_residual = st.rn;
+        stats->solve_seconds = st.solveSec;
+        stats->pc_setup_seconds = st.pcSec;
+        stats->n_matvec = st.nMatvec;
+        stats->reserved = 0;
+    }
+    DAB_CATCH
+}
+
+int dab_calc_function(dab_solver* s, const char* name, double* value)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(name, "name");
+    need(value, "value");
+    *value = s->s.calcFunction(name);
+    DAB_CATCH
+}
+
+int dab_get_input_size(dab_solver* s, const char* name, const char* type, int64_t* out)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(type, "type");
+    (void)name;
+    if (std::string(type) == "stateVar") *out = s->s.nDof();
+    else throw Error(std::string("getInputSize: unsupported input type ") + type);
+    DAB_CATCH
+}
+
+int dab_get_output_size(dab_solver* s, const char* name, const char* type, int64_t* out)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(type, "type");
+    (void)name;
+    const std::string t(type);
+    if (t == "residual") *out = s->s.nDof();
+    else if (t == "function") *out = 1;
+    else throw Error("getOutputSize: unsupported output type " + t);
+    DAB_CATCH
+}
+
+int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64_t* kernel_launches)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(ms_per_call, "ms_per_call");
+    Solver& S = s->s;
+    S.ensureRecorded();
+    const long l0 = S.be.launches;
+    auto t = S.be.timer();
+    S.be.sync();
+    t.start();
+    for (int i = 0; i < n; i++)
+    {
+        if (which == 0) S.matVecDev(S.dX.p, S.dY2.p);
+        else S.forward(0, S.dR.p);
+    }
+    *ms_per_call = t.stopMs() / (n > 0 ? n : 1);
+    if (kernel_launches) *kernel_launches = S.be.launches - l0;
+    DAB_CATCH
+}
+
+int dab_algorithmic_bytes(dab_solver* s, int which, int64_t* bytes)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(bytes, "bytes");
+    const HostMesh& m = s->s.hm;
+    const int64_t nDof = s->s.nDof();
+    // W, psi, y (or W, R) + face geometry/addressing + cell geometry, each read once
+    const int64_t vecs = which == 0 ? 3 : 2;
+    *bytes = 8 * vecs * nDof + (int64_t)m.nIF * (8 * 10 + 4 * 2) + (int64_t)m.nBF * (8 * 6 + 4 * 2) + (int64_t)m.nC * (8 * 5);
+    DAB_CATCH
+}
+
+} // extern "C"

@@ -1,0 +1,239 @@
+// Host mesh: OpenFOAM polyMesh topology + finite-volume geometry, laid out as the SoA arrays the
+// device kernels read.  Replaces, for the adjoint hot path, OpenFOAM's fvMesh / surfaceInterpolation
+// geometry (primitiveMeshFaceCentresAndAreas, primitiveMeshCellCentresAndVols, makeWeights,
+// makeNonOrthDeltaCoeffs, makeNonOrthCorrectionVectors) that the reference reaches through
+// `meshPtr_` (reference src/adjoint/DASolver/DASolver.C:58-64) and the boundary-face maps of DAIndex
+// (reference src/adjoint/DAIndex/DAIndex.C:66-112).
+#pragma once
+#include "foam_io.hpp"
+#include <algorithm>
+#include <cmath>
+
+namespace dab
+{
+
+enum PatchGeom { PG_PATCH = 0, PG_WALL = 1, PG_SYMMETRY = 2, PG_PROCESSOR = 3 };
+
+struct HostMesh
+{
+    // topology
+    int nP = 0, nF = 0, nIF = 0, nBF = 0, nC = 0;
+    int nCtot = 0;        // owned + ghost cells (ghosts appended; nCtot == nC on one rank)
+    std::vector<double> points;          // 3*nP
+    std::vector<int32_t> fOff, fLab;     // faces -> points
+    std::vector<int32_t> own, nei;       // nei sized nIF
+    std::vector<PatchDef> patches;
+    std::vector<int32_t> patchGeom;      // PatchGeom per patch
+    std::vector<int32_t> bPatch;         // patch of boundary face b
+    int maxCF = 0;
+    std::vector<int32_t> cellFaces;      // ELL: [k*nC + c] = (f<<1)|isNeighbour, -1 padding
+    // geometry (SoA)
+    std::vector<double> Sf[3], Cf[3], corr[3]; // per face
+    std::vector<double> magSf, w, delta;       // per face (w = 1 on boundary faces)
+    std::vector<double> C[3], V, yWall;        // per cell
+
+    void read(const std::string& caseDir)
+    {
+        const std::string pm = caseDir + "/constant/polyMesh/";
+        readVectorField(pm + "points", points);
+        readFaceList(pm + "faces", fOff, fLab);
+        readLabelList(pm + "owner", own);
+        readLabelList(pm + "neighbour", nei);
+        patches = readBoundary(pm + "boundary");
+        finalizeTopology();
+    }
+
+    void finalizeTopology()
+    {
+        nP = (int)(points.size() / 3);
+        nF = (int)own.size();
+        nIF = (int)nei.size();
+        nBF = nF - nIF;
+        if ((int)fOff.size() != nF + 1) throw Error("polyMesh: faces/owner size mismatch");
+        nC = 0;
+        for (int f = 0; f < nF; f++) nC = std::max(nC, own[f] + 1);
+        for (int f = 0; f < nIF; f++) nC = std::max(nC, nei[f] + 1);
+        nCtot = nC;
+        patchGeom.resize(patches.size());
+        bPatch.assign(nBF, -1);
+        for (size_t p = 0; p < patches.size(); p++)
+        {
+            const std::string& ty = patches[p].type;
+            patchGeom[p] = ty == "wall" ? PG_WALL : ((ty == "symmetry" || ty == "symmetryPlane") ? PG_SYMMETRY : PG_PATCH);
+            if (patches[p].start < nIF || patches[p].start + patches[p].size > nF) throw Error("polyMesh: bad patch range " + patches[p].name);
+            for (int i = 0; i < patches[p].size; i++) bPatch[patches[p].start - nIF + i] = (int32_t)p;
+        }
+        for (int b = 0; b < nBF; b++)
+            if (bPatch[b] < 0) throw Error("polyMesh: boundary face without patch");
+        // ELL cell -> faces
+        std::vector<int> cnt(nC, 0);
+        for (int f = 0; f < nF; f++)
+        {
+            cnt[own[f]]++;
+            if (f < nIF) cnt[nei[f]]++;
+        }
+        maxCF = *std::max_element(cnt.begin(), cnt.end());
+        cellFaces.assign((size_t)maxCF * nC, -1);
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int f = 0; f < nF; f++)
+        {
+            int c = own[f];
+            cellFaces[(size_t)cnt[c]++ * nC + c] = (f << 1);
+            if (f < nIF)
+            {
+                c = nei[f];
+                cellFaces[(size_t)cnt[c]++ * nC + c] = (f << 1) | 1;
+            }
+        }
+    }
+
+    // OpenFOAM-v1812 geometry definitions (see file header)
+    void computeGeometry()
+    {
+        for (int k = 0; k < 3; k++)
+        {
+            Sf[k].assign(nF, 0.0); Cf[k].assign(nF, 0.0); corr[k].assign(nF, 0.0); C[k].assign(nC, 0.0);
+        }
+        magSf.assign(nF, 0.0); w.assign(nF, 1.0); delta.assign(nF, 0.0); V.assign(nC, 0.0);
+        const double* P = points.data();
+        for (int f = 0; f < nF; f++)
+        {
+            const int n = fOff[f + 1] - fOff[f];
+            const int32_t* l = &fLab[fOff[f]];
+            double cf[3], sf[3];
+            if (n == 3)
+            {
+                for (int k = 0; k < 3; k++) cf[k] = (P[3 * l[0] + k] + P[3 * l[1] + k] + P[3 * l[2] + k]) / 3.0;
+                double a[3], b[3];
+                for (int k = 0; k < 3; k++) { a[k] = P[3 * l[1] + k] - P[3 * l[0] + k]; b[k] = P[3 * l[2] + k] - P[3 * l[0] + k]; }
+                sf[0] = 0.5 * (a[1] * b[2] - a[2] * b[1]); sf[1] = 0.5 * (a[2] * b[0] - a[0] * b[2]); sf[2] = 0.5 * (a[0] * b[1] - a[1] * b[0]);
+            }
+            else
+            {
+                double est[3] = {0, 0, 0};
+                for (int i = 0; i < n; i++)
+                    for (int k = 0; k < 3; k++) est[k] += P[3 * l[i] + k];
+                for (int k = 0; k < 3; k++) est[k] /= n;
+                double sumN[3] = {0, 0, 0}, sumAc[3] = {0, 0, 0}, sumA = 0.0;
+                for (int i = 0; i < n; i++)
+                {
+                    const double* p0 = &P[3 * l[i]];
+                    const double* p1 = &P[3 * l[(i + 1) % n]];
+                    double a[3], b[3], nn[3], c[3];
+                    for (int k = 0; k < 3; k++) { a[k] = p1[k] - p0[k]; b[k] = est[k] - p0[k]; c[k] = p0[k] + p1[k] + est[k]; }
+                    nn[0] = a[1] * b[2] - a[2] * b[1]; nn[1] = a[2] * b[0] - a[0] * b[2]; nn[2] = a[0] * b[1] - a[1] * b[0];
+                    double an = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                    for (int k = 0; k < 3; k++) { sumN[k] += nn[k]; sumAc[k] += an * c[k]; }
+                    sumA += an;
+                }
+                for (int k = 0; k < 3; k++) { cf[k] = (1.0 / 3.0) / sumA * sumAc[k]; sf[k] = 0.5 * sumN[k]; }
+            }
+            for (int k = 0; k < 3; k++) { Cf[k][f] = cf[k]; Sf[k][f] = sf[k]; }
+            magSf[f] = std::sqrt(sf[0] * sf[0] + sf[1] * sf[1] + sf[2] * sf[2]);
+        }
+        std::vector<double> est((size_t)3 * nC, 0.0);
+        std::vector<int> cnt(nC, 0);
+        for (int f = 0; f < nF; f++)
+        {
+            for (int k = 0; k < 3; k++) est[3 * (size_t)own[f] + k] += Cf[k][f];
+            cnt[own[f]]++;
+            if (f < nIF)
+            {
+                for (int k = 0; k < 3; k++) est[3 * (size_t)nei[f] + k] += Cf[k][f];
+                cnt[nei[f]]++;
+            }
+        }
+        for (int c = 0; c < nC; c++)
+            for (int k = 0; k < 3; k++) est[3 * (size_t)c + k] /= cnt[c];
+        for (int f = 0; f < nF; f++)
+        {
+            for (int side = 0; side < (f < nIF ? 2 : 1); side++)
+            {
+                const int c = side == 0 ? own[f] : nei[f];
+                double pyr3 = 0.0;
+                for (int k = 0; k < 3; k++)
+                    pyr3 += Sf[k][f] * (side == 0 ? (Cf[k][f] - est[3 * (size_t)c + k]) : (est[3 * (size_t)c + k] - Cf[k][f]));
+                for (int k = 0; k < 3; k++) C[k][c] += pyr3 * (0.75 * Cf[k][f] + 0.25 * est[3 * (size_t)c + k]);
+                V[c] += pyr3;
+            }
+        }
+        for (int c = 0; c < nC; c++)
+        {
+            for (int k = 0; k < 3; k++) C[k][c] /= V[c];
+            V[c] /= 3.0;
+            if (!(V[c] > 0.0)) throw Error("polyMesh: non-positive cell volume");
+        }
+        for (int f = 0; f < nF; f++)
+        {
+            double nh[3] = {Sf[0][f] / magSf[f], Sf[1][f] / magSf[f], Sf[2][f] / magSf[f]};
+            if (f < nIF)
+            {
+                const int o = own[f], n = nei[f];
+                double dO = 0.0, dN = 0.0, d[3], nd = 0.0, md = 0.0;
+                for (int k = 0; k < 3; k++)
+                {
+                    dO += Sf[k][f] * (Cf[k][f] - C[k][o]);
+                    dN += Sf[k][f] * (C[k][n] - Cf[k][f]);
+                    d[k] = C[k][n] - C[k][o];
+                    nd += nh[k] * d[k];
+                    md += d[k] * d[k];
+                }
+                dO = std::fabs(dO); dN = std::fabs(dN);
+                w[f] = dN / (dO + dN);
+                md = std::sqrt(md);
+                delta[f] = 1.0 / std::max(nd, 0.05 * md);
+                for (int k = 0; k < 3; k++) corr[k][f] = nh[k] - delta[f] * d[k];
+            }
+            else
+            {
+                const int o = own[f];
+                double dn = 0.0;
+                for (int k = 0; k < 3; k++) dn += nh[k] * (Cf[k][f] - C[k][o]);
+                double d[3], nd = 0.0, md = 0.0;
+                for (int k = 0; k < 3; k++) { d[k] = dn * nh[k]; nd += nh[k] * d[k]; md += d[k] * d[k]; }
+                delta[f] = 1.0 / std::max(nd, 0.05 * std::sqrt(md));
+            }
+        }
+    }
+
+    // frozen wall distance (meshWaveFrozen role, reference src/adjoint/DAMisc/meshWaveFrozen): distance
+    // from the cell centre to the nearest wall-face centre, evaluated once
+    void computeWallDistance()
+    {
+        yWall.assign(nC, 1e30);
+        std::vector<int> wf;
+        for (int b = 0; b < nBF; b++)
+            if (patchGeom[bPatch[b]] == PG_WALL) wf.push_back(nIF + b);
+        if (wf.empty()) return;
+        // sort wall faces along x for a pruned search
+        std::sort(wf.begin(), wf.end(), [&](int a, int b) { return Cf[0][a] < Cf[0][b]; });
+        std::vector<double> wx(wf.size());
+        for (size_t i = 0; i < wf.size(); i++) wx[i] = Cf[0][wf[i]];
+        for (int c = 0; c < nC; c++)
+        {
+            const double x = C[0][c], y = C[1][c], z = C[2][c];
+            size_t mid = (size_t)(std::lower_bound(wx.begin(), wx.end(), x) - wx.begin());
+            double best = 1e300;
+            // expand outwards from mid until the x-distance alone exceeds the best distance
+            for (long i = (long)mid; i < (long)wf.size(); i++)
+            {
+                double dx = wx[i] - x;
+                if (dx * dx >= best) break;
+                int f = wf[i];
+                double dy = Cf[1][f] - y, dz = Cf[2][f] - z;
+                best = std::min(best, dx * dx + dy * dy + dz * dz);
+            }
+            for (long i = (long)mid - 1; i >= 0; i--)
+            {
+                double dx = wx[i] - x;
+                if (dx * dx >= best) break;
+                int f = wf[i];
+                double dy = Cf[1][f] - y, dz = Cf[2][f] - z;
+                best = std::min(best, dx * dx + dy * dy + dz * dz);
+            }
+            yWall[c] = std::sqrt(best);
+        }
+    }
+};
+
+} // namespace dab

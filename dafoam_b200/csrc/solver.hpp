@@ -1,0 +1,449 @@
+// dab::Solver -- orchestration of the adjoint hot path on one GPU (one process per GPU).
+//
+// Mirrors, for this path, the reference's DASolver (reference src/adjoint/DASolver/DASolver.H:55-850):
+//   construction        DASolver::DASolver + DASimpleFoam::initSolver  (DASolver.C:35-118, DASimpleFoam.C:81-121)
+//   updateOFFields      DASolver::updateOFFields                       (DASolver.C:1291-1300)
+//   getResiduals        DASolver::calcResiduals                        (DASolver.C:2847-2861)
+//   dRdWTMatVec         DASolver::dRdWTMatVecMultFunction              (DASolver.C:1364-1409)
+//   calcJacTVecProduct  DASolver::calcJacTVecProduct                   (DASolver.C:1690-1839)
+//   solveLinearEqn      DASolver::solveLinearEqn / DALinearEqn         (DASolver.C:1121-1155, DALinearEqn.C:28-437)
+#pragma once
+#include "backend.hpp"
+#include "mesh.hpp"
+#include "views.hpp"
+#include "fwd_kernels.hpp"
+#include "rev_kernels.hpp"
+#include "krylov.hpp"
+#include <map>
+#include <set>
+
+namespace dab
+{
+
+struct FunctionDef
+{
+    std::string name, type;
+    std::vector<int> patches;
+    double dir[3] = {1.0, 0.0, 0.0};
+    double scale = 1.0;
+};
+
+struct Solver
+{
+    Backend be;
+    HostMesh hm;
+    Params par;
+    std::string solverName;
+    int rank = 0, nRanks = 1;
+    // options
+    int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
+    double gmresRelTol = 1e-6, gmresAbsTol = 1e-14, gmresTolDiff = 1e2, fdStep = 1e-6;
+    std::string pcType = "ilu";
+    std::vector<FunctionDef> functions;
+
+    // device mesh
+    DevBuf<int32_t> dOwn, dNei, dCellFaces, dBPatch;
+    DevBuf<double> dS[3], dMagSf, dW, dDelta, dK[3], dCf[3], dC[3], dV, dY;
+    MeshView mv;
+    // state (internal working copies with ghost slots) and external-layout mirror
+    DevBuf<double> dWext, dU, dP, dNt, dPhi;
+    StateView sv;
+    // forward record and reverse work arrays
+    DevBuf<double> rNut, rGU, rGP, rGNt, rRAU, rHbyA, rD0, rFlag;
+    RecordView rv;
+    DevBuf<double> aMt, aDn, aUdir, aPdir, aGPb, aGUb, aGNtb, aNutb, aU2, aNt2;
+    AdjView av;
+    DevBuf<double> dR, dX, dY2; // residual / product scratch in external layout
+    bool recorded = false;
+    Krylov kry;
+
+    int nDof() const { return (par.turb ? 5 : 4) * hm.nC + hm.nF; }
+
+    // ------------------------------------------------------------------------------------------
+    void create(const std::string& caseDir, const std::string& argsAll, const std::string& optionsJson, int device, int rank_,
+                int nRanks_)
+    {
+        rank = rank_;
+        nRanks = nRanks_;
+        if (nRanks != 1) throw Error("multi-rank creation goes through Solver::createPartitioned");
+        {
+            auto t = tokenize(argsAll);
+            solverName = t.empty() ? "DASimpleFoam" : t[0];
+        }
+        if (solverName != "DASimpleFoam") throw Error("solver " + solverName + " is not supported (DASimpleFoam only in this build)");
+        be.init(device);
+        hm.read(caseDir);
+        hm.computeGeometry();
+        hm.computeWallDistance();
+        if ((int)hm.patches.size() > MAXP) throw Error("too many patches");
+        readCase(caseDir);
+        applyOptions(optionsJson, true);
+        upload();
+        initialStates(caseDir);
+    }
+
+    static int bcKindOf(const std::string& t, const std::string& where)
+    {
+        if (t == "fixedValue") return BC_FIXED_VALUE;
+        if (t == "zeroGradient") return BC_ZERO_GRADIENT;
+        if (t == "inletOutlet") return BC_INLET_OUTLET;
+        if (t == "outletInlet") return BC_OUTLET_INLET;
+        if (t == "symmetry" || t == "symmetryPlane") return BC_SYMMETRY;
+        if (t == "calculated") return BC_CALCULATED;
+        if (t == "nutLowReWallFunction") return BC_NUT_LOW_RE;
+        throw Error("unsupported boundary condition type '" + t + "' in " + where);
+    }
+
+    std::map<std::string, Dict> fieldDicts;
+
+    void readCase(const std::string& caseDir)
+    {
+        memset(&par, 0, sizeof(par));
+        Dict tp = readDict(caseDir + "/constant/transportProperties");
+        par.nu = tp.scalar("nu");
+        std::string ras = "dummy";
+        if (fileExists(caseDir + "/constant/turbulenceProperties"))
+        {
+            Dict tu = readDict(caseDir + "/constant/turbulenceProperties");
+            if (tu.hasSub("RAS")) ras = tu.sub("RAS").wordOr("RASModel", "dummy");
+        }
+        if (ras == "SpalartAllmaras") par.turb = 1;
+        else if (ras == "dummy" || ras == "dummyTurbulenceModel" || ras == "laminar") par.turb = 0;
+        else throw Error("RASModel " + ras + " is not supported (SpalartAllmaras, dummy)");
+        Dict fs = readDict(caseDir + "/system/fvSchemes");
+        auto scheme = [&](const std::string& key) {
+            std::string v = fs.sub("divSchemes").joined(key);
+            if (v.find("linearUpwindV") != std::string::npos) throw Error("linearUpwindV is not supported; use linearUpwind");
+            if (v.find("linearUpwind") != std::string::npos) return (int)DIV_LINEAR_UPWIND;
+            if (v.find("upwind") != std::string::npos) return (int)DIV_UPWIND;
+            if (v.find("linear") != std::string::npos) return (int)DIV_LINEAR;
+            throw Error("unsupported div scheme '" + v + "'");
+        };
+        par.divU = scheme("div(phi,U)");
+        par.divNut = par.turb ? scheme("div(phi,nuTilda)") : DIV_UPWIND;
+        Dict fso = readDict(caseDir + "/system/fvSolution");
+        par.alphaU = 1.0;
+        if (fso.hasSub("relaxationFactors") && fso.sub("relaxationFactors").hasSub("equations"))
+            par.alphaU = fso.sub("relaxationFactors").sub("equations").scalarOr("U", 1.0);
+        if (fso.hasSub("SIMPLE") && fso.sub("SIMPLE").wordOr("consistent", "false") == "true")
+            throw Error("SIMPLEC (consistent true) is not supported in this build");
+        // boundary conditions
+        const char* fn[N_FIELDS] = {"U", "p", "nuTilda", "nut"};
+        for (int fi = 0; fi < N_FIELDS; fi++)
+        {
+            if (fi >= F_NUTILDA && !par.turb) continue;
+            const std::string path = caseDir + "/0/" + fn[fi];
+            Dict d = readDict(path);
+            fieldDicts[fn[fi]] = d;
+            const Dict& bf = d.sub("boundaryField");
+            for (size_t p = 0; p < hm.patches.size(); p++)
+            {
+                const Dict& pd = bf.sub(hm.patches[p].name);
+                const std::string ty = pd.word("type");
+                const int kind = bcKindOf(ty, path);
+                par.bcKind[fi][p] = kind;
+                double v[3] = {0, 0, 0};
+                const char* key = kind == BC_INLET_OUTLET ? "inletValue" : (kind == BC_OUTLET_INLET ? "outletValue" : "value");
+                if (pd.has(key)) pd.uniform(key, v);
+                for (int k = 0; k < 3; k++) par.bcVal[fi][p][k] = v[k];
+            }
+        }
+        // defaults of the reference's DAOPTION (dafoam/pyDAFoam.py:526-563)
+        par.sU = par.sP = par.sNut = par.sPhi = 1.0;
+        par.nrU = par.nrP = par.nrNut = par.nrPhi = 1;
+        par.constrainHbyA = 1;
+    }
+
+    void applyOptions(const std::string& json, bool first)
+    {
+        if (json.empty()) return;
+        JVal o = parseJson(json);
+        if (o.kind != JVal::Obj) throw Error("options must be a JSON object");
+        if (const JVal* ns = o.get("normalizeStates"))
+        {
+            par.sU = ns->numOr("U", par.sU);
+            par.sP = ns->numOr("p", par.sP);
+            par.sNut = ns->numOr("nuTilda", par.sNut);
+            par.sPhi = ns->numOr("phi", par.sPhi);
+        }
+        if (const JVal* nr = o.get("normalizeResiduals"))
+        {
+            par.nrU = par.nrP = par.nrNut = par.nrPhi = 0;
+            for (const auto& v : nr->arr)
+            {
+                if (v.str == "URes") par.nrU = 1;
+                if (v.str == "pRes") par.nrP = 1;
+                if (v.str == "nuTildaRes") par.nrNut = 1;
+                if (v.str == "phiRes") par.nrPhi = 1;
+            }
+        }
+        par.constrainHbyA = (int)o.numOr("useConstrainHbyA", par.constrainHbyA);
+        if (const JVal* a = o.get("adjEqnOption"))
+        {
+            gmresRestart = (int)a->numOr("gmresRestart", gmresRestart);
+            gmresMaxIters = (int)a->numOr("gmresMaxIters", gmresMaxIters);
+            gmresRelTol = a->numOr("gmresRelTol", gmresRelTol);
+            gmresAbsTol = a->numOr("gmresAbsTol", gmresAbsTol);
+            gmresTolDiff = a->numOr("gmresTolDiff", gmresTolDiff);
+            useMGSO = (int)a->numOr("useMGSO", useMGSO);
+            pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
+            printInfo = (int)a->numOr("printInfo", printInfo);
+            pcType = a->strOr("pcType", pcType);
+        }
+        if (const JVal* s = o.get("adjPartDerivFDStep")) fdStep = s->numOr("State", fdStep);
+        if (const JVal* fd = o.get("function"))
+        {
+            functions.clear();
+            for (const auto& kv : fd->obj)
+            {
+                FunctionDef f;
+                f.name = kv.first;
+                f.type = kv.second.strOr("type", "force");
+                if (f.type != "force") throw Error("function type " + f.type + " is not supported (force)");
+                if (kv.second.strOr("directionMode", "fixedDirection") != "fixedDirection")
+                    throw Error("only directionMode fixedDirection is supported");
+                if (const JVal* pl = kv.second.get("patches"))
+                    for (const auto& pn : pl->arr)
+                    {
+                        int found = -1;
+                        for (size_t p = 0; p < hm.patches.size(); p++)
+                            if (hm.patches[p].name == pn.str) found = (int)p;
+                        if (found < 0) throw Error("function " + f.name + ": unknown patch " + pn.str);
+                        f.patches.push_back(found);
+                    }
+                if (const JVal* d = kv.second.get("direction"))
+                    for (size_t k = 0; k < 3 && k < d->arr.size(); k++) f.dir[k] = d->arr[k].num;
+                const double mg = std::sqrt(f.dir[0] * f.dir[0] + f.dir[1] * f.dir[1] + f.dir[2] * f.dir[2]);
+                if (std::fabs(mg - 1.0) > 1e-8) throw Error("the magnitude of the direction parameter in " + f.name + " is not 1.0!");
+                f.scale = kv.second.numOr("scale", 1.0);
+                functions.push_back(f);
+            }
+        }
+        (void)first;
+        recorded = false;
+    }
+
+    void upload()
+    {
+        dOwn.upload(be, hm.own);
+        dNei.upload(be, hm.nei);
+        dCellFaces.upload(be, hm.cellFaces);
+        dBPatch.upload(be, hm.bPatch);
+        for (int k = 0; k < 3; k++)
+        {
+            dS[k].upload(be, hm.Sf[k]);
+            dK[k].upload(be, hm.corr[k]);
+            dCf[k].upload(be, hm.Cf[k]);
+            dC[k].upload(be, hm.C[k]);
+        }
+        dMagSf.upload(be, hm.magSf);
+        dW.upload(be, hm.w);
+        dDelta.upload(be, hm.delta);
+        dV.upload(be, hm.V);
+        dY.upload(be, hm.yWall);
+        mv.nC = hm.nC; mv.nCtot = hm.nCtot; mv.nF = hm.nF; mv.nIF = hm.nIF; mv.nBF = hm.nBF; mv.maxCF = hm.maxCF;
+        mv.own = dOwn.p; mv.nei = dNei.p; mv.cellFaces = dCellFaces.p; mv.bPatch = dBPatch.p;
+        mv.Sx = dS[0].p; mv.Sy = dS[1].p; mv.Sz = dS[2].p; mv.magSf = dMagSf.p; mv.w = dW.p; mv.delta = dDelta.p;
+        mv.kx = dK[0].p; mv.ky = dK[1].p; mv.kz = dK[2].p; mv.Cfx = dCf[0].p; mv.Cfy = dCf[1].p; mv.Cfz = dCf[2].p;
+        mv.Cx = dC[0].p; mv.Cy = dC[1].p; mv.Cz = dC[2].p; mv.V = dV.p; mv.yWall = dY.p;
+        const size_t nT = hm.nCtot, nC = hm.nC, nF = hm.nF, nd = nDof();
+        dWext.alloc(be, nd);
+        dU.alloc(be, 3 * nT); dP.alloc(be, nT); dNt.alloc(be, nT); dPhi.alloc(be, nF);
+        sv.U = dU.p; sv.p = dP.p; sv.nt = dNt.p; sv.phi = dPhi.p;
+        rNut.alloc(be, nT); rGU.alloc(be, 9 * nT); rGP.alloc(be, 3 * nT); rGNt.alloc(be, 3 * nT);
+        rRAU.alloc(be, nT); rHbyA.alloc(be, 3 * nT); rD0.alloc(be, nT); rFlag.alloc(be, nT);
+        rv.nut = rNut.p; rv.gU = rGU.p; rv.gP = rGP.p; rv.gNt = rGNt.p; rv.rAU = rRAU.p; rv.HbyA = rHbyA.p; rv.D0 = rD0.p; rv.flag = rFlag.p;
+        aMt.alloc(be, 3 * nT); aDn.alloc(be, nT); aUdir.alloc(be, 3 * nC); aPdir.alloc(be, nC);
+        aGPb.alloc(be, 3 * nT); aGUb.alloc(be, 9 * nT); aGNtb.alloc(be, 3 * nT); aNutb.alloc(be, nC);
+        aU2.alloc(be, 3 * nC); aNt2.alloc(be, nC);
+        av.mt = aMt.p; av.Dn = aDn.p; av.Udir = aUdir.p; av.pdir = aPdir.p; av.gPb = aGPb.p; av.gUb = aGUb.p;
+        av.gNtb = aGNtb.p; av.nutb = aNutb.p; av.U2 = aU2.p; av.nt2 = aNt2.p;
+        dR.alloc(be, nd); dX.alloc(be, nd); dY2.alloc(be, nd);
+    }
+
+    // initial states from the 0/ files (DASimpleFoam::initSolver createFieldsSimple.H role); phi = linear-interpolated U . Sf
+    void initialStates(const std::string&)
+    {
+        const int nC = hm.nC, nF = hm.nF, nIF = hm.nIF;
+        std::vector<double> W(nDof(), 0.0);
+        auto internal = [&](const std::string& name, int nc, std::vector<double>& out) {
+            const Dict& d = fieldDicts.at(name);
+            const auto& t = d.tokens("internalField");
+            out.assign((size_t)nc * nC, 0.0);
+            if (t.at(0) == "uniform")
+            {
+                double v[3] = {0, 0, 0};
+                d.uniform("internalField", v);
+                for (int c = 0; c < nC; c++)
+                    for (int k = 0; k < nc; k++) out[(size_t)nc * c + k] = v[k];
+            }
+            else
+            {
+                // nonuniform List<type> N ( ... )
+                std::vector<double> vals;
+                size_t i = 0;
+                while (i < t.size() && t[i] != "(") i++;
+                for (i++; i < t.size(); i++)
+                {
+                    if (t[i] == "(" || t[i] == ")") continue;
+                    vals.push_back(atof(t[i].c_str()));
+                }
+                if (vals.size() < (size_t)nc * nC) throw Error("internalField of " + name + " has the wrong size");
+                for (size_t j = 0; j < (size_t)nc * nC; j++) out[j] = vals[j];
+            }
+        };
+        std::vector<double> U, p, nt;
+        internal("U", 3, U);
+        internal("p", 1, p);
+        for (int i = 0; i < 3 * nC; i++) W[i] = U[i];
+        for (int c = 0; c < nC; c++) W[3 * (size_t)nC + c] = p[c];
+        size_t off = 4 * (size_t)nC;
+        if (par.turb)
+        {
+            internal("nuTilda", 1, nt);
+            for (int c = 0; c < nC; c++) W[off + c] = nt[c];
+            off += nC;
+        }
+        for (int f = 0; f < nF; f++)
+        {
+            double uf[3];
+            const int o = hm.own[f];
+            if (f < nIF)
+                for (int k = 0; k < 3; k++) uf[k] = hm.w[f] * U[3 * (size_t)o + k] + (1.0 - hm.w[f]) * U[3 * (size_t)hm.nei[f] + k];
+            else
+            {
+                const int pa = hm.bPatch[f - nIF];
+                const int kind = par.bcKind[F_U][pa];
+                for (int k = 0; k < 3; k++) uf[k] = (kind == BC_FIXED_VALUE) ? par.bcVal[F_U][pa][k] : U[3 * (size_t)o + k];
+                if (kind == BC_SYMMETRY) uf[0] = uf[1] = uf[2] = 0.0;
+            }
+            W[off + f] = uf[0] * hm.Sf[0][f] + uf[1] * hm.Sf[1][f] + uf[2] * hm.Sf[2][f];
+            if (f >= nIF && par.bcKind[F_U][hm.bPatch[f - nIF]] == BC_SYMMETRY) W[off + f] = 0.0;
+        }
+        updateOFFields(W.data());
+    }
+
+    // ------------------------------------------------------------------------------------------
+    void updateOFFields(const double* W)
+    {
+        const size_t nC = hm.nC;
+        be.h2d(dWext.p, W, (size_t)nDof() * sizeof(double));
+        be.d2d(dU.p, dWext.p, 3 * nC * sizeof(double));
+        be.d2d(dP.p, dWext.p + 3 * nC, nC * sizeof(double));
+        size_t off = 4 * nC;
+        if (par.turb)
+        {
+            be.d2d(dNt.p, dWext.p + off, nC * sizeof(double));
+            off += nC;
+        }
+        be.d2d(dPhi.p, dWext.p + off, (size_t)hm.nF * sizeof(double));
+        recorded = false;
+        kry.pcValid = false;
+    }
+
+    void getOFFields(double* W) { be.d2h(W, dWext.p, (size_t)nDof() * sizeof(double)); }
+
+    // forward passes; record(isPC=0) leaves the intermediates the reverse sweep reuses
+    void forward(int isPC, double* Rdev)
+    {
+        FwdA a{mv, par, sv, rv};
+        be.launch(hm.nCtot, a);
+        FwdB b{mv, par, sv, rv, isPC, Rdev};
+        be.launch(hm.nC, b);
+        FwdC c{mv, par, sv, rv, Rdev};
+        be.launch(hm.nC, c);
+    }
+
+    void ensureRecorded()
+    {
+        if (recorded) return;
+        forward(0, dR.p);
+        recorded = true;
+    }
+
+    void getResiduals(int isPC, double* R)
+    {
+        forward(isPC, dR.p);
+        recorded = (isPC == 0);
+        be.d2h(R, dR.p, (size_t)nDof() * sizeof(double));
+    }
+
+    // y = diag(n) (dR/dW)^T x on device vectors (external layout)
+    void matVecDev(const double* x, double* y)
+    {
+        ensureRecorded();
+        RevA ra{mv, par, sv, rv, av, x};
+        be.launch(hm.nC, ra);
+        RevB rb{mv, par, sv, rv, av, x, y};
+        be.launch(hm.nC, rb);
+        RevC rc{mv, par, sv, rv, av, x, y};
+        be.launch(hm.nC, rc);
+    }
+
+    void matVec(const double* x, double* y)
+    {
+        be.h2d(dX.p, x, (size_t)nDof() * sizeof(double));
+        matVecDev(dX.p, dY2.p);
+        be.d2h(y, dY2.p, (size_t)nDof() * sizeof(double));
+    }
+
+    // ---- functions (DAFunctionForce) ------------------------------------------------------------
+    const FunctionDef& findFunction(const std::string& name) const
+    {
+        for (const auto& f : functions)
+            if (f.name == name) return f;
+        throw Error("function " + name + " is not defined in the options");
+    }
+
+    ForceSpec forceSpec(const FunctionDef& f) const
+    {
+        ForceSpec fs;
+        fs.mask = 0;
+        for (int p : f.patches) fs.mask |= (1u << p);
+        for (int k = 0; k < 3; k++) fs.dir[k] = f.dir[k];
+        fs.scale = f.scale;
+        return fs;
+    }
+
+    DevBuf<double> dFacePart;
+
+    double calcFunction(const std::string& name)
+    {
+        const FunctionDef& f = findFunction(name);
+        ensureRecorded();
+        if (dFacePart.n < (size_t)hm.nBF) dFacePart.alloc(be, hm.nBF);
+        ForceFwd k{mv, par, sv, rv, forceSpec(f), dFacePart.p};
+        be.launch(hm.nBF, k);
+        std::vector<double> part(hm.nBF);
+        be.d2h(part.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
+        // deterministic host summation in face order (the all-reduce of the reference, DAFunctionForce.C:146)
+        double s = 0.0;
+        for (int b = 0; b < hm.nBF; b++) s += part[b];
+        return s;
+    }
+
+    // [dF/dW]^T * seed, scaled by normalizeStates (DASolver.C:1819-1820)
+    void dFdW(const std::string& name, double seed, double* out)
+    {
+        const FunctionDef& f = findFunction(name);
+        ensureRecorded();
+        be.zero(av.gUb, (size_t)9 * hm.nCtot * sizeof(double));
+        be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
+        be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
+        ForceRevA ka{mv, par, sv, rv, av, forceSpec(f), seed};
+        be.launch(hm.nC, ka);
+        be.zero(dX.p, (size_t)nDof() * sizeof(double)); // zero residual seed for the shared gradient-adjoint stage
+        RevC rc{mv, par, sv, rv, av, dX.p, dY2.p};
+        rc.functionMode = 1;
+        be.launch(hm.nC, rc);
+        be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
+    }
+
+    // ---- Krylov -----------------------------------------------------------------------------------
+    void calcPC();
+    int solveLinearEqn(const double* rhs, double* sol, KspStats& st);
+};
+
+} // namespace dab
+
+#include "solver_krylov.hpp"

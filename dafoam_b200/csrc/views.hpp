@@ -1,0 +1,208 @@
+// Device-side views (plain pointers, passed to kernels by value) and small inline helpers shared by
+// the forward R(W) kernels and the hand-derived reverse kernels.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define DAB_HD __host__ __device__ __forceinline__
+#else
+#define DAB_HD inline
+#endif
+
+namespace dab
+{
+
+constexpr int MAXP = 16; // max patches per rank
+enum { F_U = 0, F_P = 1, F_NUTILDA = 2, F_NUT = 3, N_FIELDS = 4 };
+enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_INLET_OUTLET = 2, BC_OUTLET_INLET = 3, BC_SYMMETRY = 4, BC_CALCULATED = 5, BC_NUT_LOW_RE = 6 };
+enum { DIV_UPWIND = 0, DIV_LINEAR_UPWIND = 1, DIV_LINEAR = 2 };
+
+struct MeshView
+{
+    int nC, nCtot, nF, nIF, nBF, maxCF;
+    const int32_t* own;       // [nF]
+    const int32_t* nei;       // [nIF]
+    const int32_t* cellFaces; // ELL [maxCF][nC]
+    const int32_t* bPatch;    // [nBF]
+    const double *Sx, *Sy, *Sz, *magSf, *w, *delta, *kx, *ky, *kz, *Cfx, *Cfy, *Cfz; // [nF]
+    const double *Cx, *Cy, *Cz, *V, *yWall;                                          // [nCtot]
+};
+
+struct Params
+{
+    double nu, alphaU;
+    double sU, sP, sNut, sPhi;           // normalizeStates
+    int turb, divU, divNut;              // turb: 0 laminar (dummyTurbulenceModel), 1 SpalartAllmaras
+    int nrU, nrP, nrNut, nrPhi;          // residual listed in normalizeResiduals
+    int constrainHbyA;
+    int bcKind[N_FIELDS][MAXP];
+    double bcVal[N_FIELDS][MAXP][3];
+};
+
+// internal working state (ghost slots appended to the cell arrays)
+struct StateView
+{
+    const double* U;   // AoS [3*nCtot]
+    const double* p;   // [nCtot]
+    const double* nt;  // [nCtot] (nuTilda; unused when laminar)
+    const double* phi; // [nF]
+};
+
+// forward intermediates recorded once per state (the role of the reference's AD tape)
+struct RecordView
+{
+    double* nut;   // [nCtot]
+    double* gU;    // [9][nCtot]: gU[(j*3+i)*nCtot + c] = d_i U_j
+    double* gP;    // [3][nCtot]
+    double* gNt;   // [3][nCtot]
+    double* rAU;   // [nCtot]
+    double* HbyA;  // [3][nCtot]
+    double* D0;    // [nCtot] assembled momentum diagonal (without boundary coefficients)
+    double* flag;  // [nCtot] relax branch: +-1 -> |D1| branch with sign(D1); 0 -> sum-off-diagonal branch
+};
+
+// reverse intermediates (per product)
+struct AdjView
+{
+    double* mt;    // [3][nCtot]  m~ = Mbar / V
+    double* Dn;    // [nCtot]     adjoint of the relaxed diagonal
+    double* Udir;  // [3][nC]     direct U adjoint from stage R1
+    double* pdir;  // [nC]
+    double* gPb;   // [3][nCtot]  adjoint of grad(p)
+    double* gUb;   // [9][nCtot]  adjoint of grad(U)
+    double* gNtb;  // [3][nCtot]  adjoint of grad(nuTilda)
+    double* nutb;  // [nC]        adjoint of nut (cell value)
+    double* U2;    // [3][nC]     U adjoint from stage R2
+    double* nt2;   // [nC]        nuTilda adjoint from stage R2
+};
+
+struct FaceRef
+{
+    int f, n;   // face, other cell (-1 on a boundary face)
+    double s;   // +1 if the cell owns the face, -1 otherwise
+    bool bnd;
+};
+
+DAB_HD FaceRef faceOf(const MeshView& m, int c, int k)
+{
+    FaceRef r;
+    const int e = m.cellFaces[(size_t)k * m.nC + c];
+    if (e < 0)
+    {
+        r.f = -1; r.n = -1; r.s = 0.0; r.bnd = false;
+        return r;
+    }
+    r.f = e >> 1;
+    const int isN = e & 1;
+    r.s = isN ? -1.0 : 1.0;
+    r.bnd = r.f >= m.nIF;
+    r.n = r.bnd ? -1 : (isN ? m.own[r.f] : m.nei[r.f]);
+    return r;
+}
+
+// SA constants (reference src/adjoint/DAModel/DATurbulenceModel/DASpalartAllmaras.C:47-80)
+struct SA
+{
+    static constexpr double sigma = 0.66666, kappa = 0.41, Cb1 = 0.1355, Cb2 = 0.622, Cw2 = 0.3, Cw3 = 2.0, Cv1 = 7.1, Cs = 0.3;
+    static constexpr double Cw1 = Cb1 / (kappa * kappa) + (1.0 + Cb2) / sigma;
+    static constexpr double Cv1c = Cv1 * Cv1 * Cv1;
+    static constexpr double Cw3p6 = 64.0;
+};
+
+DAB_HD double fv1f(double chi)
+{
+    const double c3 = chi * chi * chi;
+    return c3 / (c3 + SA::Cv1c);
+}
+// d(nuTilda*fv1(nuTilda/nu))/d nuTilda
+DAB_HD double dnut_dnt(double nt, double nu)
+{
+    const double chi = nt / nu, c3 = chi * chi * chi, den = c3 + SA::Cv1c;
+    const double fv1 = c3 / den, dfv1 = 3.0 * chi * chi * SA::Cv1c / (den * den);
+    return fv1 + chi * dfv1;
+}
+
+// mixed-BC value fraction (fixedValue 1, zeroGradient 0, inletOutlet 1-pos0(phi), outletInlet pos0(phi))
+DAB_HD double bcFrac(int kind, double phib)
+{
+    switch (kind)
+    {
+    case BC_FIXED_VALUE:
+    case BC_NUT_LOW_RE: return 1.0;
+    case BC_INLET_OUTLET: return phib >= 0.0 ? 0.0 : 1.0;
+    case BC_OUTLET_INLET: return phib >= 0.0 ? 1.0 : 0.0;
+    default: return 0.0;
+    }
+}
+
+// scalar BC: value and snGrad; `fr` returned for the adjoint (dval/dxP = 1-fr, dsng/dxP = -fr*delta)
+DAB_HD void bcScalar(int kind, double ref, double xP, double phib, double dl, double& val, double& sng, double& fr)
+{
+    fr = bcFrac(kind, phib);
+    val = fr * ref + (1.0 - fr) * xP;
+    sng = fr * (ref - xP) * dl;
+}
+
+struct BCv
+{
+    double val[3], sng[3], vic[3], gic[3];
+};
+
+DAB_HD void bcVector(int kind, const double* ref, const double* xP, double phib, double dl, const double* nh, BCv& b)
+{
+    if (kind == BC_SYMMETRY)
+    {
+        const double xn = nh[0] * xP[0] + nh[1] * xP[1] + nh[2] * xP[2];
+        for (int k = 0; k < 3; k++)
+        {
+            const double an = nh[k] < 0.0 ? -nh[k] : nh[k];
+            b.val[k] = xP[k] - xn * nh[k];
+            b.sng[k] = -(xn * nh[k]) * dl;
+            b.vic[k] = 1.0 - an;
+            b.gic[k] = -(dl * an);
+        }
+    }
+    else
+    {
+        const double fr = bcFrac(kind, phib);
+        for (int k = 0; k < 3; k++)
+        {
+            b.val[k] = fr * ref[k] + (1.0 - fr) * xP[k];
+            b.sng[k] = fr * (ref[k] - xP[k]) * dl;
+            b.vic[k] = 1.0 - fr;
+            b.gic[k] = -fr * dl;
+        }
+    }
+}
+
+// adjoint of bcVector w.r.t. xP given adjoints of val and sng
+DAB_HD void bcVectorAdj(int kind, double phib, double dl, const double* nh, const double* valb, const double* sngb, double* xPb)
+{
+    if (kind == BC_SYMMETRY)
+    {
+        double xnb = 0.0;
+        for (int k = 0; k < 3; k++) xnb -= nh[k] * (valb[k] + dl * sngb[k]);
+        for (int k = 0; k < 3; k++) xPb[k] += valb[k] + nh[k] * xnb;
+    }
+    else
+    {
+        const double fr = bcFrac(kind, phib);
+        for (int k = 0; k < 3; k++) xPb[k] += (1.0 - fr) * valb[k] - fr * dl * sngb[k];
+    }
+}
+
+// nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP and d(nut_b)/d(nuTilda_b) in dNb
+DAB_HD double nutBoundary(int kind, double ref, double nutP, double ntB, double nu, double& dP, double& dNb)
+{
+    dP = 0.0;
+    dNb = 0.0;
+    switch (kind)
+    {
+    case BC_FIXED_VALUE:
+    case BC_NUT_LOW_RE: return ref;
+    case BC_CALCULATED: dNb = dnut_dnt(ntB, nu); return ntB * fv1f(ntB / nu);
+    default: dP = 1.0; return nutP; // symmetry, zeroGradient
+    }
+}
+
+} // namespace dab

@@ -1,0 +1,238 @@
+"""pyDASolvers -- the Python face of the drop-in boundary.
+
+Mirrors the reference's Cython class `pyDASolvers` (reference src/pyDASolvers/pyDASolvers.pyx:117-483):
+same method names, same argument meaning (caller-allocated C-contiguous float64 numpy arrays,
+size-asserted), same soft-failure convention (integer returns for solvePrimal/solveLinearEqn, hard
+errors raise).  Implemented as a thin ctypes binding of the C ABI in include/dab200.h; there is no CPU
+fallback: if libdab200.so (CUDA, sm_100a) is missing or no GPU is visible, construction raises.
+
+petsc4py is not available in this environment, so the PETSc handle arguments of the reference
+(`Mat`, `KSP`, `Vec`) are replaced by tiny handle classes defined here (`Mat`, `KSP`) and by plain
+numpy arrays for vectors; the call sequence of `DAFoamSolver.solve_linear`
+(reference dafoam/mphys/mphys_dafoam.py:433-574) is preserved.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+class DAB200Error(RuntimeError):
+    pass
+
+
+class KspStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged_reason", C.c_int32), ("initial_residual", C.c_double),
+                ("final_residual", C.c_double), ("solve_seconds", C.c_double), ("pc_setup_seconds", C.c_double),
+                ("n_matvec", C.c_int32), ("reserved", C.c_int32)]
+
+
+def load_library(path=None):
+    """Load libdab200.so.  `path` is only used by the test-suite to load the host-simulation build."""
+    path = path or os.path.join(_HERE, "libdab200.so")
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise DAB200Error("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    L.dab_last_error.restype = C.c_char_p
+    L.dab_version.restype = C.c_char_p
+    _LIBS[path] = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check_array(a, n, what):
+    assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "%s must be a C-contiguous float64 array" % what
+    assert len(a) == n, "invalid %s array size!" % what
+
+
+class Mat:
+    """Stand-in for the PETSc Mat handle of the reference's calcdRdWT(isPC, dRdWT)."""
+
+    def __init__(self):
+        self.assembled = False
+
+
+class KSP:
+    """Stand-in for the PETSc KSP handle (createMLRKSPMatrixFree / solveLinearEqn)."""
+
+    def __init__(self):
+        self.ready = False
+        self.stats = None
+
+
+class pyDASolvers:
+    def __init__(self, argsAll, pyOptions, caseDir=".", device=0, rank=0, nRanks=1, ncclUniqueId=None, _lib_path=None):
+        """argsAll: e.g. "DASimpleFoam -python"; pyOptions: the DAOPTION dict (reference dafoam/pyDAFoam.py:39-662).
+        caseDir replaces the reference's implicit os.getcwd() case directory."""
+        self._L = load_library(_lib_path)
+        self._h = C.c_void_p()
+        if isinstance(argsAll, bytes):
+            argsAll = argsAll.decode()
+        self._options = dict(pyOptions or {})
+        uid = None if ncclUniqueId is None else C.c_char_p(bytes(ncclUniqueId))
+        rc = self._L.dab_create(os.path.abspath(caseDir).encode(), argsAll.encode(), json.dumps(self._options).encode(),
+                                C.c_int(device), C.c_int(rank), C.c_int(nRanks), uid, C.byref(self._h))
+        self._raise(rc)
+        self._initialised = False
+
+    # ---- plumbing
+    def _raise(self, rc):
+        if rc != 0:
+            raise DAB200Error(self._L.dab_last_error().decode())
+
+    def _geti(self, fn):
+        v = C.c_int64()
+        self._raise(fn(self._h, C.byref(v)))
+        return int(v.value)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.dab_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- the reference's methods (pyDASolvers.pyx)
+    def initSolver(self):
+        self._initialised = True
+
+    def getNLocalAdjointStates(self):
+        return self._geti(self._L.dab_n_local_adjoint_states)
+
+    def getNLocalCells(self):
+        return self._geti(self._L.dab_n_local_cells)
+
+    def getNGlobalCells(self):
+        return self._geti(self._L.dab_n_global_cells)
+
+    def getNLocalPoints(self):
+        return self._geti(self._L.dab_n_local_points)
+
+    def getNLocalFaces(self):
+        return self._geti(self._L.dab_n_local_faces)
+
+    def getNLocalInternalFaces(self):
+        return self._geti(self._L.dab_n_local_internal_faces)
+
+    def updateDAOption(self, pyOptions):
+        self._options.update(pyOptions)
+        self._raise(self._L.dab_update_options(self._h, json.dumps(pyOptions).encode()))
+
+    def updateOFFields(self, states):
+        _check_array(states, self.getNLocalAdjointStates(), "states")
+        self._raise(self._L.dab_update_of_fields(self._h, _dp(states)))
+
+    def getOFFields(self, states):
+        _check_array(states, self.getNLocalAdjointStates(), "states")
+        self._raise(self._L.dab_get_of_fields(self._h, _dp(states)))
+
+    def getOFMeshPoints(self, points):
+        _check_array(points, self.getNLocalPoints() * 3, "points")
+        self._raise(self._L.dab_get_of_mesh_points(self._h, _dp(points)))
+
+    def getOFField(self, fieldName, fieldType, field):
+        n = self.getNLocalCells() * (3 if fieldType == "vector" else 1)
+        _check_array(field, n, "field")
+        self._raise(self._L.dab_get_of_field(self._h, fieldName.encode(), fieldType.encode(), _dp(field)))
+
+    def getResiduals(self, residuals, isPC=0):
+        _check_array(residuals, self.getNLocalAdjointStates(), "residuals")
+        self._raise(self._L.dab_get_residuals(self._h, C.c_int(isPC), _dp(residuals)))
+
+    def getInputSize(self, inputName, inputType):
+        v = C.c_int64()
+        self._raise(self._L.dab_get_input_size(self._h, inputName.encode(), inputType.encode(), C.byref(v)))
+        return int(v.value)
+
+    def getOutputSize(self, outputName, outputType):
+        v = C.c_int64()
+        self._raise(self._L.dab_get_output_size(self._h, outputName.encode(), outputType.encode(), C.byref(v)))
+        return int(v.value)
+
+    def getInputDistributed(self, inputName, inputType):
+        return 1 if inputType in ("stateVar", "volCoord") else 0
+
+    def getOutputDistributed(self, outputName, outputType):
+        return 1 if outputType == "residual" else 0
+
+    def calcJacTVecProduct(self, inputName, inputType, inputs, outputName, outputType, seeds, product):
+        inputSize = self.getInputSize(inputName, inputType)
+        outputSize = self.getOutputSize(outputName, outputType)
+        _check_array(inputs, inputSize, "input")
+        _check_array(seeds, outputSize, "seed")
+        _check_array(product, inputSize, "product")
+        self._raise(self._L.dab_calc_jac_t_vec_product(self._h, inputName.encode(), inputType.encode(), _dp(inputs),
+                                                       outputName.encode(), outputType.encode(), _dp(seeds), _dp(product)))
+
+    def calcFunction(self, functionName):
+        v = C.c_double()
+        self._raise(self._L.dab_calc_function(self._h, functionName.encode(), C.byref(v)))
+        return float(v.value)
+
+    def runColoring(self):
+        # the colouring is computed inside calcdRdWT on first use (reference DASolver.C:708-743)
+        return None
+
+    def calcdRdWT(self, isPC, dRdWT):
+        assert isPC == 1, "only the preconditioner matrix (isPC=1) is assembled explicitly; dRdWT itself is matrix-free"
+        self._raise(self._L.dab_calc_drdwt_pc(self._h))
+        dRdWT.assembled = True
+
+    def initializedRdWTMatrixFree(self):
+        return None
+
+    def destroydRdWTMatrixFree(self):
+        return None
+
+    def createMLRKSPMatrixFree(self, jacPCMat, myKSP):
+        assert jacPCMat.assembled, "call calcdRdWT(1, dRdWTPC) first"
+        myKSP.ready = True
+
+    def updateKSPPCMat(self, PCMat, myKSP):
+        myKSP.ready = PCMat.assembled
+
+    def solveLinearEqn(self, myKSP, rhsVec, solVec):
+        n = self.getNLocalAdjointStates()
+        _check_array(rhsVec, n, "rhs")
+        _check_array(solVec, n, "sol")
+        fail = C.c_int(1)
+        st = KspStats()
+        self._raise(self._L.dab_solve_linear_eqn(self._h, _dp(rhsVec), _dp(solVec), C.byref(fail), C.byref(st)))
+        if myKSP is not None:
+            myKSP.stats = st
+        return int(fail.value)
+
+    # ---- v2/v3-era names used by BASELINE.json's north_star (thin aliases)
+    def calcdRdWTPsiAD(self, psi, dRdWTPsi):
+        n = self.getNLocalAdjointStates()
+        _check_array(psi, n, "psi")
+        _check_array(dRdWTPsi, n, "dRdWTPsi")
+        self._raise(self._L.dab_drdwt_mat_vec(self._h, _dp(psi), _dp(dRdWTPsi)))
+
+    def solveAdjoint(self, dFdW, psi):
+        ksp = KSP()
+        return self.solveLinearEqn(ksp, dFdW, psi), ksp.stats
+
+    # ---- measurement hooks
+    def benchDevice(self, which, n):
+        ms = C.c_double()
+        nl = C.c_int64()
+        self._raise(self._L.dab_bench_device(self._h, C.c_int(which), C.c_int(n), C.byref(ms), C.byref(nl)))
+        return float(ms.value), int(nl.value)
+
+    def algorithmicBytes(self, which=0):
+        v = C.c_int64()
+        self._raise(self._L.dab_algorithmic_bytes(self._h, C.c_int(which), C.byref(v)))
+        return int(v.value)

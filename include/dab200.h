@@ -1,0 +1,136 @@
+/*
+ * dab200.h -- C ABI of the B200-native discrete-adjoint engine (libdab200.so).
+ *
+ * This is the drop-in boundary for the adjoint hot path of mdolab/dafoam: each entry point replaces
+ * one method of the reference's Cython class `pyDASolvers` (reference src/pyDASolvers/pyDASolvers.pyx:
+ * 45-114 extern block, class body :117-483) / C++ forwarding class `Foam::DASolvers`
+ * (reference src/pyDASolvers/DASolvers.H).  Plain pointers and sizes only; all arrays are
+ * caller-allocated HOST buffers of doubles, borrowed for the duration of the call (the same ownership
+ * convention as the reference's numpy arguments); the library owns all device memory.
+ *
+ * Every function returns 0 on success and a non-zero code on error; dab_last_error() returns the
+ * message of the last failing call of the calling thread.  The library requires a CUDA device; it
+ * never falls back to a CPU path.
+ *
+ * State-vector layout ("state" ordering, reference src/adjoint/DAIndex/DAIndex.C:188-257):
+ *     W = [ U(cell-major xyz) | p | nuTilda (SA only) | phi (internal faces, then boundary faces) ]
+ * Residual vectors use the same layout (reference src/adjoint/DAOutput/DAOutputResidual.C:50-118).
+ */
+#ifndef DAB200_H
+#define DAB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dab_solver dab_solver;
+
+/* boundary-condition kinds parsed from the case's 0/<field> files */
+enum dab_bc_kind
+{
+    DAB_BC_FIXED_VALUE = 0,
+    DAB_BC_ZERO_GRADIENT = 1,
+    DAB_BC_INLET_OUTLET = 2,
+    DAB_BC_OUTLET_INLET = 3,
+    DAB_BC_SYMMETRY = 4,
+    DAB_BC_CALCULATED = 5,
+    DAB_BC_NUT_LOW_RE = 6
+};
+
+/* statistics of one Krylov solve (reference prints these: src/adjoint/DALinearEqn/DALinearEqn.C:361-418) */
+typedef struct dab_ksp_stats
+{
+    int32_t iterations;
+    int32_t converged_reason; /* 2: rtol, 3: atol, -3: max iterations */
+    double initial_residual;
+    double final_residual;
+    double solve_seconds;      /* device time of the GMRES loop */
+    double pc_setup_seconds;   /* preconditioner assembly + factorisation */
+    int32_t n_matvec;          /* number of dRdWT*psi products */
+    int32_t reserved;
+} dab_ksp_stats;
+
+const char* dab_last_error(void);
+const char* dab_version(void);
+
+/* DASolvers::DASolvers(char* argsAll, PyObject* pyOptions) + initSolver()
+ * (reference pyDASolvers.pyx:136-155, DASolvers.C:15-23, DASolver.C:35-118, DASimpleFoam.C:81-121).
+ * case_dir: OpenFOAM case (constant/polyMesh, 0/, constant/, system/); args_all: e.g.
+ * "DASimpleFoam -python"; options_json: the DAOPTION dict serialised as JSON
+ * (reference dafoam/pyDAFoam.py:39-662 for the keys).  rank/n_ranks/nccl_unique_id describe the
+ * domain decomposition (nccl_unique_id may be NULL when n_ranks == 1). device: CUDA ordinal. */
+int dab_create(const char* case_dir, const char* args_all, const char* options_json, int device, int rank,
+               int n_ranks, const void* nccl_unique_id, dab_solver** out);
+int dab_destroy(dab_solver* s);
+
+/* 128-byte NCCL unique id for multi-rank creation (rank 0 calls it, the host broadcasts it) */
+int dab_nccl_unique_id(void* out128);
+
+/* getNLocalAdjointStates / getNLocalCells / getNGlobalCells / getNLocalPoints (pyDASolvers.pyx) */
+int dab_n_local_adjoint_states(dab_solver* s, int64_t* out);
+int dab_n_local_cells(dab_solver* s, int64_t* out);
+int dab_n_global_cells(dab_solver* s, int64_t* out);
+int dab_n_local_points(dab_solver* s, int64_t* out);
+int dab_n_local_faces(dab_solver* s, int64_t* out);
+int dab_n_local_internal_faces(dab_solver* s, int64_t* out);
+
+/* updateDAOption(pyOptions) (pyDASolvers.pyx; reference DASolver.H updateDAOption) */
+int dab_update_options(dab_solver* s, const char* options_json);
+
+/* updateOFFields(states) / getOFFields(states): DASolver::updateOFFields = state2OFField +
+ * updateStateBoundaryConditions (reference DASolver.C:1291-1300, 2863-2886).  Setting the states also
+ * records the forward intermediates the matrix-free product reuses (the role of the reference's
+ * initializeGlobalADTape4dRdWT, DASolver.C:1411-1441). */
+int dab_update_of_fields(dab_solver* s, const double* states);
+int dab_get_of_fields(dab_solver* s, double* states);
+
+/* getOFMeshPoints(points) (pyDASolvers.pyx:267-270) */
+int dab_get_of_mesh_points(dab_solver* s, double* points);
+/* getOFField(name, type, field): read-only access to a cell field ("U","p","nuTilda","nut","yWall","V") */
+int dab_get_of_field(dab_solver* s, const char* name, const char* type, double* field);
+
+/* getResiduals(residuals): R(W) at the current states (reference DASolver.C:2847-2861,
+ * DAResidualSimpleFoam.C:106-237, DASpalartAllmaras.C:407-488); is_pc selects the div(pc) schemes. */
+int dab_get_residuals(dab_solver* s, int is_pc, double* residuals);
+
+/* calcJacTVecProduct(inputName, inputType, input, outputName, outputType, seed, product)
+ * (reference DASolver.C:1690-1839).  Supported pairs: (stateVar -> residual), (stateVar -> function). */
+int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char* input_type, const double* input,
+                               const char* output_name, const char* output_type, const double* seed,
+                               double* product);
+
+/* Matrix-free product y = diag(n) * (dR/dW)^T x at the current states: the body of the reference's
+ * PETSc shell-matrix callback DASolver::dRdWTMatVecMultFunction (DASolver.C:1364-1409);
+ * v2/v3-era name: calcdRdWTPsiAD. */
+int dab_drdwt_mat_vec(dab_solver* s, const double* x, double* y);
+
+/* calcdRdWT(isPC=1, dRdWTPC) + createMLRKSPMatrixFree(dRdWTPC, ksp): assemble the preconditioner
+ * matrix from the first-order residual by coloured finite differences and factorise it
+ * (reference DASolver.C:948-1089, DAPartDeriv.C:350-474, DALinearEqn.C:28-339). */
+int dab_calc_drdwt_pc(dab_solver* s);
+
+/* solveLinearEqn(ksp, rhs, sol): right-preconditioned restarted GMRES on the device
+ * (reference DASolver.C:1121-1155, DALinearEqn.C:341-437).  *fail = 0/1 with the reference's
+ * success rule (relRatio > gmresTolDiff && absRatio > gmresTolDiff  =>  1). */
+int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats);
+
+/* calcFunction(name) (reference DASolver.H calcFunction, DAFunctionForce.C:79-153) */
+int dab_calc_function(dab_solver* s, const char* name, double* value);
+
+/* getInputSize / getOutputSize (pyDASolvers.pyx:189-199) */
+int dab_get_input_size(dab_solver* s, const char* name, const char* type, int64_t* out);
+int dab_get_output_size(dab_solver* s, const char* name, const char* type, int64_t* out);
+
+/* --- benchmarking hooks (no reference counterpart): run the product n times on device-resident
+ * vectors and return the mean device time per launch sequence in milliseconds (CUDA events on the
+ * solver's stream). which = 0: dRdWT*psi product, 1: R(W) */
+int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64_t* kernel_launches);
+/* algorithmic bytes of one dRdWT*psi product */
+int dab_algorithmic_bytes(dab_solver* s, int which, int64_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
