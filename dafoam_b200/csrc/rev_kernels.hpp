@@ -1,11 +1,655 @@
-// STUB (replaced below once the forward is verified)
+// Hand-derived reverse sweep y = diag(n) (dR/dW)^T x of the forward kernels in fwd_kernels.hpp: the
+// tape-free replacement of the reference's `globalADTape_.evaluate()` inside
+// DASolver::dRdWTMatVecMultFunction (reference src/adjoint/DASolver/DASolver.C:1364-1409) followed by
+// normalizeGradientVec (DASolver.C:2356-2455).
+//
+// The forward is cell <- faces <- cells gathers; its transpose is written as gathers too (each cell
+// collects the adjoint contributions that the rows of its neighbours make to *its* variables), so the
+// reverse needs no atomics and, on several GPUs, only plain ghost-cell copies between the stages.
+//
+//   RevA  adjoint of FwdC (pRes, phiRes -> HbyA, rAU, p, grad p) fused with the cell-level adjoint of
+//         the momentum row (URes, rAU, HbyA -> m~ = Mbar/V, adjoint of the relaxed diagonal)
+//   RevB  face-level adjoint of the momentum and SA rows: contributions of rows c and n to U_c, nuEff_c,
+//         grad(U)_c, nuTilda_c, grad(nuTilda)_c and (owner side) phi_f
+//   RevC  adjoint of FwdA (Gauss gradients, nut) + final assembly and state scaling
+//
+// Non-smooth intrinsics differentiate the active branch (max/min/fabs/upwind switches), sqrt has zero
+// derivative at zero -- the same conventions as CoDiPack in the reference and as oracle/tape.hpp.
 #pragma once
 #include "views.hpp"
-namespace dab {
-struct RevA { MeshView m; Params q; StateView s; RecordView r; AdjView a; const double* x; DAB_HD void operator()(int) const {} };
-struct RevB { MeshView m; Params q; StateView s; RecordView r; AdjView a; const double* x; double* y; DAB_HD void operator()(int) const {} };
-struct RevC { MeshView m; Params q; StateView s; RecordView r; AdjView a; const double* x; double* y; int functionMode = 0; DAB_HD void operator()(int) const {} };
-struct ForceSpec { unsigned mask; double dir[3]; double scale; };
-struct ForceFwd { MeshView m; Params q; StateView s; RecordView r; ForceSpec fs; double* out; DAB_HD void operator()(int) const {} };
-struct ForceRevA { MeshView m; Params q; StateView s; RecordView r; AdjView a; ForceSpec fs; double seed; DAB_HD void operator()(int) const {} };
+#include "fwd_kernels.hpp"
+#include <cmath>
+
+namespace dab
+{
+
+DAB_HD double sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
+
+// adjoint of saSource with seed z: accumulates into ntb, gUb[9], gNb[3]
+DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const double* gN, double z, double& ntb, double* gUb, double* gNb)
+{
+    const double chi = nt / nu;
+    const double c3 = chi * chi * chi, den1 = c3 + SA::Cv1c;
+    const double fv1 = c3 / den1;
+    const double den = 1.0 + chi * fv1;
+    const double fv2 = 1.0 - chi / den;
+    const double w01 = 0.5 * (gU[3] - gU[1]), w02 = 0.5 * (gU[6] - gU[2]), w12 = 0.5 * (gU[7] - gU[5]);
+    const double Q = w01 * w01 + w02 * w02 + w12 * w12;
+    const double sQ = sqrt(Q);
+    const double Omega = 2.0 * sQ;
+    const double ky2 = (SA::kappa * y) * (SA::kappa * y);
+    const double S1 = Omega + fv2 * nt / ky2, S2 = SA::Cs * Omega;
+    const bool b1 = S1 > S2;
+    const double St = b1 ? S1 : S2;
+    const bool bS = St > 1e-15;
+    const double Sm = bS ? St : 1e-15;
+    const double rr0 = nt / (Sm * ky2);
+    const bool bR = rr0 < 10.0;
+    const double rr = bR ? rr0 : 10.0;
+    const double r2 = rr * rr, r5 = r2 * r2 * rr;
+    const double g = rr + SA::Cw2 * (r5 * rr - rr);
+    const double g2 = g * g, g6 = g2 * g2 * g2;
+    const double h = pow((1.0 + SA::Cw3p6) / (g6 + SA::Cw3p6), 1.0 / 6.0);
+    const double fw = g * h;
+    // reverse
+    for (int i = 0; i < 3; i++) gNb[i] += -2.0 * (SA::Cb2 / SA::sigma) * gN[i] * z;
+    double Stb = -SA::Cb1 * nt * z;
+    ntb += (-SA::Cb1 * St + 2.0 * SA::Cw1 * fw * nt / (y * y)) * z;
+    const double fwb = SA::Cw1 * nt * nt / (y * y) * z;
+    const double gb = fwb * h * SA::Cw3p6 / (g6 + SA::Cw3p6);
+    const double rrb = gb * (1.0 + SA::Cw2 * (6.0 * r5 - 1.0));
+    const double rr0b = bR ? rrb : 0.0;
+    ntb += rr0b / (Sm * ky2);
+    const double Smb = -rr0b * nt / (Sm * Sm * ky2);
+    if (bS) Stb += Smb;
+    double Omegab = 0.0;
+    if (b1)
+    {
+        Omegab += Stb;
+        const double fv2b = Stb * nt / ky2;
+        ntb += Stb * fv2 / ky2;
+        double chib = -fv2b / (den * den);
+        const double fv1b = fv2b * chi * chi / (den * den);
+        chib += fv1b * 3.0 * chi * chi * SA::Cv1c / (den1 * den1);
+        ntb += chib / nu;
+    }
+    else
+        Omegab += SA::Cs * Stb;
+    if (sQ > 0.0)
+    {
+        const double Qb = Omegab / sQ;
+        const double w01b = 2.0 * w01 * Qb, w02b = 2.0 * w02 * Qb, w12b = 2.0 * w12 * Qb;
+        gUb[3] += 0.5 * w01b; gUb[1] -= 0.5 * w01b;
+        gUb[6] += 0.5 * w02b; gUb[2] -= 0.5 * w02b;
+        gUb[7] += 0.5 * w12b; gUb[5] -= 0.5 * w12b;
+    }
 }
+
+// adjoint of the boundary gradient construction Gb[j*3+i] = gU[j*3+i] + nh_i (sng_j - sum_i nh_i gU[j*3+i])
+DAB_HD void boundaryGradAdj(const double* nh, const double* Gbb, double* gUb, double* sngb)
+{
+    for (int j = 0; j < 3; j++)
+    {
+        const double t = nh[0] * Gbb[j * 3 + 0] + nh[1] * Gbb[j * 3 + 1] + nh[2] * Gbb[j * 3 + 2];
+        sngb[j] += t;
+        for (int i = 0; i < 3; i++) gUb[j * 3 + i] += Gbb[j * 3 + i] - nh[i] * t;
+    }
+}
+
+struct RevA
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    const double* x;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const size_t offP = (size_t)3 * nC, offPhi = (size_t)(q.turb ? 5 : 4) * nC;
+        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+        const double V = m.V[c];
+        const double psiPc = x[offP + c] * (q.nrP ? 1.0 / V : 1.0);
+        double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            const int f = fr.f;
+            const double mS = m.magSf[f], dl = m.delta[f];
+            const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
+            const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double psiPn = x[offP + n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
+                // F_f enters pRes_own with -1, pRes_nei with +1, phiRes_f with +1
+                const double Fb = cphi * x[offPhi + f] - fr.s * (psiPc - psiPn);
+                const double w = m.w[f];
+                const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
+                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                double cg = 0.0;
+                for (int j = 0; j < 3; j++) cg += kv[j] * (wc * r.gP[(size_t)j * nT + c] + wn * r.gP[(size_t)j * nT + n]);
+                const double sn = fr.s * dl * (s.p[n] - s.p[c]) + cg; // delta*(p_N - p_P) + corr
+                const double gam = wc * r.rAU[c] + wn * r.rAU[n];
+                for (int j = 0; j < 3; j++)
+                {
+                    HbA[j] += wc * Sv[j] * Fb;
+                    gPb[j] -= gam * mS * wc * kv[j] * Fb;
+                }
+                rAUb -= wc * mS * sn * Fb;
+                pb += fr.s * gam * mS * dl * Fb;
+            }
+            else
+            {
+                const int b = f - m.nIF, pa = m.bPatch[b];
+                const double phib = s.phi[f];
+                const double Fb = cphi * x[offPhi + f] - psiPc;
+                const int kU = q.bcKind[F_U][pa];
+                const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
+                if (q.constrainHbyA && !assignable)
+                {
+                    const double im = 1.0 / mS;
+                    const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+                    const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
+                    const double sngb[3] = {0.0, 0.0, 0.0};
+                    bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
+                }
+                else
+                    for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * Fb;
+                double pv, sn, frp;
+                bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, sn, frp);
+                rAUb -= mS * sn * Fb;
+                const double snb = -r.rAU[c] * mS * Fb;
+                pb -= frp * dl * snb;
+            }
+        }
+        // cell-level adjoint of the momentum row: URes = cU*(M + grad p), HbyA = U - rAU*M, rAU = V/(Dn + icAvg)
+        const double rAU = r.rAU[c];
+        const double cU = q.nrU ? 1.0 : V;
+        const double D0 = r.D0[c];
+        double rAUtot = rAUb;
+        for (int j = 0; j < 3; j++)
+        {
+            const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) / rAU;
+            const double psiU = cU * x[3 * c + j];
+            const double Mb = psiU - rAU * HbA[j];
+            rAUtot -= M * HbA[j];
+            const double mt = Mb / V;
+            a.mt[(size_t)j * nT + c] = mt;
+            a.Udir[(size_t)j * nC + c] = Ub[j] + HbA[j] + D0 * mt;
+            a.gPb[(size_t)j * nT + c] = gPb[j] + psiU;
+        }
+        a.Dn[c] = -rAU * rAU * rAUtot / V;
+        a.pdir[c] = pb;
+    }
+};
+
+struct RevB
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    const double* x;
+    double* y;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const size_t offN = (size_t)4 * nC, offPhi = (size_t)(q.turb ? 5 : 4) * nC;
+        const int schU = q.divU, schN = q.divNut;
+        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+        const double nuEc = r.nut[c] + q.nu;
+        double gUc[9], gNc[3];
+        for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
+        const double ntc = q.turb ? s.nt[c] : 0.0;
+        const double Gc = (ntc + q.nu) / SA::sigma;
+        for (int i = 0; i < 3; i++) gNc[i] = q.turb ? r.gNt[(size_t)i * nT + c] : 0.0;
+        const double trc = gUc[0] + gUc[4] + gUc[8];
+        const double V = m.V[c];
+        // cell-level adjoints of row c
+        const double mtc[3] = {a.mt[c], a.mt[(size_t)nT + c], a.mt[(size_t)2 * nT + c]};
+        const double Dnc = a.Dn[c], flc = r.flag[c];
+        const double D2c = Dnc / q.alphaU;
+        const double D1c = flc != 0.0 ? flc * D2c : 0.0;
+        const double soc = flc != 0.0 ? 0.0 : D2c;
+        const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
+        const double psiN = q.turb ? x[offN + c] : 0.0;
+        const double qc = psiN * (q.nrNut ? 1.0 / V : 1.0); // adjoint of NV
+        const double zc = psiN * (q.nrNut ? 1.0 : V);       // adjoint of the cell-local SA sources
+
+        double U2[3] = {0, 0, 0}, nt2 = 0.0, nuEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
+        for (int i = 0; i < 9; i++) gUb[i] = 0.0;
+
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            const int f = fr.f;
+            const double phi = s.phi[f];
+            const double mf = fr.s * phi;
+            const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+            const double mS = m.magSf[f], dl = m.delta[f];
+            double phib_acc = 0.0; // adjoint of phi_f (only meaningful on the owner side)
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f], wn = 1.0 - wc;
+                const bool pos0 = phi >= 0.0;
+                const double wupc = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
+                const double Un[3] = {s.U[3 * n], s.U[3 * n + 1], s.U[3 * n + 2]};
+                const double nuEn = r.nut[n] + q.nu;
+                const double mtn[3] = {a.mt[n], a.mt[(size_t)nT + n], a.mt[(size_t)2 * nT + n]};
+                const double Dnn = a.Dn[n], fln = r.flag[n];
+                const double D2n = Dnn / q.alphaU;
+                const double D1n = fln != 0.0 ? fln * D2n : 0.0;
+                const double son = fln != 0.0 ? 0.0 : D2n;
+                const double D0n = D1n + mtn[0] * Un[0] + mtn[1] * Un[1] + mtn[2] * Un[2];
+                const bool ownUp = phi > 0.0;
+                const bool cUp = fr.s > 0 ? ownUp : !ownUp;
+                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                const double dC[3] = {m.Cfx[f] - m.Cx[c], m.Cfy[f] - m.Cy[c], m.Cfz[f] - m.Cz[c]};
+                // ---- momentum rows c and n
+                {
+                    const double wpc = schU == DIV_LINEAR ? wc : wupc;
+                    const double wpn = schU == DIV_LINEAR ? wn : 1.0 - wupc;
+                    const double gf = (wc * nuEc + wn * nuEn) * mS;
+                    const double g = gf * dl;
+                    const double offc = mf - wpc * mf - g;
+                    const double offn = -mf + wpn * mf - g;
+                    const double offbc = mtc[0] * Un[0] + mtc[1] * Un[1] + mtc[2] * Un[2] + sgn(offc) * soc;
+                    const double offbn = mtn[0] * Uc[0] + mtn[1] * Uc[1] + mtn[2] * Uc[2] + sgn(offn) * son;
+                    for (int j = 0; j < 3; j++) U2[j] += offn * mtn[j];
+                    const double abc = D0c - offbc, abn = D0n - offbn;
+                    double gb = abc + abn;   // adjoint of g
+                    double gfb = 0.0;        // adjoint of gf (non-orthogonal correction)
+                    const double lam[3] = {fr.s * (mtc[0] - mtn[0]), fr.s * (mtc[1] - mtn[1]), fr.s * (mtc[2] - mtn[2])};
+                    double gUn[9];
+                    for (int i = 0; i < 9; i++) gUn[i] = r.gU[(size_t)i * nT + n];
+                    if (fr.s > 0)
+                    {
+                        const double mbc = -D0c + offbc + wpc * abc;
+                        const double mbn = -D0n + offbn + wpn * abn;
+                        phib_acc += mbc - mbn;
+                    }
+                    if (schU == DIV_LINEAR_UPWIND)
+                    {
+                        if (cUp)
+                            for (int j = 0; j < 3; j++)
+                                for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * phi * lam[j];
+                        if (fr.s > 0)
+                        {
+                            const double* gu = cUp ? gUc : gUn;
+                            const int u = cUp ? c : n;
+                            const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                            for (int j = 0; j < 3; j++)
+                                phib_acc += (d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2]) * lam[j];
+                        }
+                    }
+                    // non-orthogonal correction: MV_own -= gf*cg_j, MV_nei += gf*cg_j
+                    for (int j = 0; j < 3; j++)
+                    {
+                        double cg = 0.0;
+                        for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gUc[j * 3 + i] + wn * gUn[j * 3 + i]);
+                        gfb -= cg * lam[j];
+                        const double cgb = -gf * lam[j];
+                        for (int i = 0; i < 3; i++) gUb[j * 3 + i] += wc * kv[i] * cgb;
+                    }
+                    // dev2 term: MV_own -= fl_j, MV_nei += fl_j, fl = wc*tc + wn*tn
+                    double trb = 0.0;
+                    for (int j = 0; j < 3; j++)
+                    {
+                        const double tcb = -wc * lam[j];
+                        const double tcj = Sv[0] * gUc[0 * 3 + j] + Sv[1] * gUc[1 * 3 + j] + Sv[2] * gUc[2 * 3 + j] - (2.0 / 3.0) * trc * Sv[j];
+                        nuEb += tcb * tcj;
+                        for (int i = 0; i < 3; i++) gUb[i * 3 + j] += nuEc * Sv[i] * tcb;
+                        trb -= (2.0 / 3.0) * nuEc * Sv[j] * tcb;
+                    }
+                    gUb[0] += trb; gUb[4] += trb; gUb[8] += trb;
+                    nuEb += wc * mS * (dl * gb + gfb);
+                }
+                // ---- SA rows c and n
+                if (q.turb)
+                {
+                    const double ntn = s.nt[n];
+                    const double qn = x[offN + n] * (q.nrNut ? 1.0 / m.V[n] : 1.0);
+                    const double wpc = schN == DIV_LINEAR ? wc : wupc;
+                    const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
+                    const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
+                    const double g = gf * dl;
+                    nt2 += qc * (wpc * mf + g - mf) + qn * (-mf + wpn * mf - g);
+                    const double gb = (qc - qn) * (ntc - ntn);
+                    double gfb = 0.0;
+                    const double lam = fr.s * (qc - qn);
+                    if (fr.s > 0) phib_acc += qc * (1.0 - wpc) * (ntn - ntc) - qn * (1.0 - wpn) * (ntc - ntn);
+                    if (schN == DIV_LINEAR_UPWIND)
+                    {
+                        if (cUp)
+                            for (int i = 0; i < 3; i++) gNb[i] += dC[i] * phi * lam;
+                        if (fr.s > 0)
+                        {
+                            const int u = cUp ? c : n;
+                            const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                            double corr = 0.0;
+                            for (int i = 0; i < 3; i++) corr += d[i] * r.gNt[(size_t)i * nT + u];
+                            phib_acc += corr * lam;
+                        }
+                    }
+                    double cg = 0.0;
+                    for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gNc[i] + wn * r.gNt[(size_t)i * nT + n]);
+                    gfb -= cg * lam;
+                    const double cgb = -gf * lam;
+                    for (int i = 0; i < 3; i++) gNb[i] += wc * kv[i] * cgb;
+                    nt2 += wc * mS * (dl * gb + gfb) / SA::sigma;
+                }
+            }
+            else
+            {
+                const int b = f - m.nIF, pa = m.bPatch[b];
+                const double im = 1.0 / mS;
+                const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+                const int kU = q.bcKind[F_U][pa];
+                BCv bu;
+                bcVector(kU, q.bcVal[F_U][pa], Uc, mf, dl, nh, bu);
+                double ntb = 0.0, sngN = 0.0, frN = 0.0;
+                if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
+                double dP = 0.0, dNb = 0.0;
+                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb) : 0.0;
+                const double nuEB = nutb + q.nu;
+                const double G = nuEB * mS;
+                // internalCoeffs and the argmax/argmin components used by relax()
+                double ic[3];
+                int kmax = 0, kmin = 0;
+                for (int j = 0; j < 3; j++)
+                {
+                    ic[j] = mf * bu.vic[j] - G * bu.gic[j];
+                    if (j > 0)
+                    {
+                        if (fabs(ic[j]) > fabs(ic[kmax])) kmax = j;
+                        if (ic[j] < ic[kmin]) kmin = j;
+                    }
+                }
+                double mb = -D0c, Gb_ = 0.0;
+                for (int j = 0; j < 3; j++)
+                {
+                    double icb = Dnc / 3.0;
+                    if (j == kmin) icb -= Dnc;
+                    if (j == kmax) icb += D1c * sgn(ic[j]);
+                    mb += bu.vic[j] * icb + mtc[j] * bu.val[j];
+                    Gb_ += -bu.gic[j] * icb - mtc[j] * bu.sng[j];
+                }
+                double valb[3], sngb[3];
+                for (int j = 0; j < 3; j++) { valb[j] = mf * mtc[j]; sngb[j] = -G * mtc[j]; }
+                // dev2 boundary term: MV_j -= nuEB * X_j
+                double Gbd[9];
+                for (int j = 0; j < 3; j++)
+                {
+                    const double nG = nh[0] * gUc[j * 3 + 0] + nh[1] * gUc[j * 3 + 1] + nh[2] * gUc[j * 3 + 2];
+                    for (int i = 0; i < 3; i++) Gbd[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bu.sng[j] - nG);
+                }
+                const double trbv = Gbd[0] + Gbd[4] + Gbd[8];
+                double nuEBb = mS * Gb_;
+                double Gbb[9];
+                for (int i = 0; i < 9; i++) Gbb[i] = 0.0;
+                double trbb = 0.0;
+                for (int j = 0; j < 3; j++)
+                {
+                    const double X = Sv[0] * Gbd[0 * 3 + j] + Sv[1] * Gbd[1 * 3 + j] + Sv[2] * Gbd[2 * 3 + j] - (2.0 / 3.0) * trbv * Sv[j];
+                    nuEBb -= X * mtc[j];
+                    const double Xb = -nuEB * mtc[j];
+                    for (int i = 0; i < 3; i++) Gbb[i * 3 + j] += Sv[i] * Xb;
+                    trbb -= (2.0 / 3.0) * Sv[j] * Xb;
+                }
+                Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
+                boundaryGradAdj(nh, Gbb, gUb, sngb);
+                bcVectorAdj(kU, mf, dl, nh, valb, sngb, U2);
+                // nut_b -> nut_c / nuTilda_b
+                nuEb += dP * nuEBb;
+                double ntbb = dNb * nuEBb;
+                if (q.turb)
+                {
+                    const double Gs = (ntb + q.nu) / SA::sigma * mS;
+                    mb += qc * (ntb - ntc);
+                    ntbb += qc * mf - qc * sngN * mS / SA::sigma;
+                    const double sngNb = -qc * Gs;
+                    nt2 += -qc * mf + (1.0 - frN) * ntbb - frN * dl * sngNb;
+                }
+                phib_acc += mb;
+            }
+            if (fr.s > 0)
+                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x[offPhi + f]) * q.sPhi * mS;
+        }
+        if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb);
+        for (int j = 0; j < 3; j++) a.U2[(size_t)j * nC + c] = U2[j];
+        a.nt2[c] = nt2;
+        a.nutb[c] = nuEb;
+        for (int i = 0; i < 9; i++) a.gUb[(size_t)i * nT + c] = gUb[i];
+        for (int i = 0; i < 3; i++) a.gNtb[(size_t)i * nT + c] = gNb[i];
+    }
+};
+
+struct RevC
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    const double* x;
+    double* y;
+    int functionMode = 0;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+        const double iVc = 1.0 / m.V[c];
+        double Ub[3], pb = a.pdir[c], nb = 0.0;
+        for (int j = 0; j < 3; j++) Ub[j] = a.Udir[(size_t)j * nC + c] + a.U2[(size_t)j * nC + c];
+        double gUbc[9], gPbc[3], gNbc[3];
+        for (int i = 0; i < 9; i++) gUbc[i] = a.gUb[(size_t)i * nT + c] * iVc;
+        for (int i = 0; i < 3; i++)
+        {
+            gPbc[i] = a.gPb[(size_t)i * nT + c] * iVc;
+            gNbc[i] = q.turb ? a.gNtb[(size_t)i * nT + c] * iVc : 0.0;
+        }
+        if (q.turb) nb = a.nt2[c] + a.nutb[c] * dnut_dnt(s.nt[c], q.nu);
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            const int f = fr.f;
+            const double So[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]}; // outward
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f];
+                const double iVn = 1.0 / m.V[n];
+                for (int j = 0; j < 3; j++)
+                {
+                    double t = 0.0;
+                    for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - a.gUb[(size_t)(j * 3 + i) * nT + n] * iVn);
+                    Ub[j] += wc * t;
+                }
+                double tp = 0.0, tn = 0.0;
+                for (int i = 0; i < 3; i++)
+                {
+                    tp += So[i] * (gPbc[i] - a.gPb[(size_t)i * nT + n] * iVn);
+                    if (q.turb) tn += So[i] * (gNbc[i] - a.gNtb[(size_t)i * nT + n] * iVn);
+                }
+                pb += wc * tp;
+                nb += wc * tn;
+            }
+            else
+            {
+                const int b = f - m.nIF, pa = m.bPatch[b];
+                const double phib = s.phi[f], dl = m.delta[f];
+                const double im = 1.0 / m.magSf[f];
+                const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
+                double valb[3];
+                const double sngb[3] = {0.0, 0.0, 0.0};
+                for (int j = 0; j < 3; j++) valb[j] = So[0] * gUbc[j * 3 + 0] + So[1] * gUbc[j * 3 + 1] + So[2] * gUbc[j * 3 + 2];
+                bcVectorAdj(q.bcKind[F_U][pa], phib, dl, nh, valb, sngb, Ub);
+                const double frp = bcFrac(q.bcKind[F_P][pa], phib);
+                pb += (1.0 - frp) * (So[0] * gPbc[0] + So[1] * gPbc[1] + So[2] * gPbc[2]);
+                if (q.turb)
+                {
+                    const double frn = bcFrac(q.bcKind[F_NUTILDA][pa], phib);
+                    nb += (1.0 - frn) * (So[0] * gNbc[0] + So[1] * gNbc[1] + So[2] * gNbc[2]);
+                }
+            }
+        }
+        (void)Uc;
+        for (int j = 0; j < 3; j++) y[3 * c + j] = Ub[j] * q.sU;
+        y[(size_t)3 * nC + c] = pb * q.sP;
+        if (q.turb) y[(size_t)4 * nC + c] = nb * q.sNut;
+        if (functionMode)
+        {
+            // phi adjoint of a function: no face-flux dependence for the force function
+            const size_t offPhi = (size_t)(q.turb ? 5 : 4) * nC;
+            for (int k = 0; k < m.maxCF; k++)
+            {
+                const FaceRef fr = faceOf(m, c, k);
+                if (fr.f < 0) break;
+                if (fr.s > 0) y[offPhi + fr.f] = 0.0;
+            }
+        }
+    }
+};
+
+// ---- force function (DAFunctionForce.C:79-153) -------------------------------------------------------
+struct ForceSpec
+{
+    unsigned mask; // bit p set: patch p contributes
+    double dir[3];
+    double scale;
+};
+
+// boundary-face force contribution and (optionally) its adjoint w.r.t. the cell's variables
+DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, const RecordView& r, const ForceSpec& fs, int f, int c,
+                        double seed, double* Ub, double* pb, double* ntb_, double* nutPb, double* gUb)
+{
+    const int nT = m.nCtot;
+    const int b = f - m.nIF, pa = m.bPatch[b];
+    const double mS = m.magSf[f], dl = m.delta[f], phib = s.phi[f];
+    const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+    const double im = 1.0 / mS;
+    const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+    const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+    double gUc[9];
+    for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
+    const int kU = q.bcKind[F_U][pa];
+    BCv bu;
+    bcVector(kU, q.bcVal[F_U][pa], Uc, phib, dl, nh, bu);
+    double pv, snp, frp;
+    bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, snp, frp);
+    double ntb = 0.0, sngN = 0.0, frN = 0.0;
+    const double ntc = q.turb ? s.nt[c] : 0.0;
+    if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, phib, dl, ntb, sngN, frN);
+    double dP = 0.0, dNb = 0.0;
+    const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb) : 0.0;
+    const double nuEB = nutb + q.nu;
+    double Gbd[9];
+    for (int j = 0; j < 3; j++)
+    {
+        const double nG = nh[0] * gUc[j * 3 + 0] + nh[1] * gUc[j * 3 + 1] + nh[2] * gUc[j * 3 + 2];
+        for (int i = 0; i < 3; i++) Gbd[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bu.sng[j] - nG);
+    }
+    const double trb = Gbd[0] + Gbd[4] + Gbd[8];
+    double F = 0.0, sj[3];
+    for (int j = 0; j < 3; j++)
+    {
+        // (Sf & dev(twoSymm(G)))_j = sum_i S_i (d_i U_j + d_j U_i) - 2/3 tr S_j
+        double t = 0.0;
+        for (int i = 0; i < 3; i++) t += Sv[i] * (Gbd[j * 3 + i] + Gbd[i * 3 + j]);
+        sj[j] = t - (2.0 / 3.0) * trb * Sv[j];
+        F += (Sv[j] * pv - nuEB * sj[j]) * fs.dir[j];
+    }
+    F *= fs.scale;
+    if (gUb)
+    {
+        double Gbb[9], sngb[3] = {0, 0, 0}, valb[3] = {0, 0, 0};
+        for (int i = 0; i < 9; i++) Gbb[i] = 0.0;
+        double pvb = 0.0, nuEBb = 0.0, trbb = 0.0;
+        for (int j = 0; j < 3; j++)
+        {
+            const double fb = seed * fs.scale * fs.dir[j];
+            pvb += Sv[j] * fb;
+            nuEBb -= sj[j] * fb;
+            const double sb = -nuEB * fb;
+            for (int i = 0; i < 3; i++)
+            {
+                Gbb[j * 3 + i] += Sv[i] * sb;
+                Gbb[i * 3 + j] += Sv[i] * sb;
+            }
+            trbb -= (2.0 / 3.0) * Sv[j] * sb;
+        }
+        Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
+        boundaryGradAdj(nh, Gbb, gUb, sngb);
+        bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
+        *pb += (1.0 - frp) * pvb;
+        *nutPb += dP * nuEBb;
+        *ntb_ += (1.0 - frN) * dNb * nuEBb;
+    }
+    return F;
+}
+
+struct ForceFwd
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    ForceSpec fs;
+    double* out; // [nBF]
+    DAB_HD void operator()(int b) const
+    {
+        const int f = m.nIF + b;
+        const int pa = m.bPatch[b];
+        if (!((fs.mask >> pa) & 1u))
+        {
+            out[b] = 0.0;
+            return;
+        }
+        out[b] = forceFace(m, q, s, r, fs, f, m.own[f], 0.0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
+};
+
+// seeds the reverse work arrays with dF/d(cell variables); RevC then propagates through the gradients
+struct ForceRevA
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    ForceSpec fs;
+    double seed;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        double Ub[3] = {0, 0, 0}, pb = 0.0, ntb = 0.0, nutPb = 0.0, gUb[9];
+        for (int i = 0; i < 9; i++) gUb[i] = 0.0;
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            if (!fr.bnd) continue;
+            const int pa = m.bPatch[fr.f - m.nIF];
+            if (!((fs.mask >> pa) & 1u)) continue;
+            forceFace(m, q, s, r, fs, fr.f, c, seed, Ub, &pb, &ntb, &nutPb, gUb);
+        }
+        for (int j = 0; j < 3; j++)
+        {
+            a.Udir[(size_t)j * nC + c] = 0.0;
+            a.U2[(size_t)j * nC + c] = Ub[j];
+        }
+        a.pdir[c] = pb;
+        a.nt2[c] = ntb;
+        a.nutb[c] = nutPb;
+        for (int i = 0; i < 9; i++) a.gUb[(size_t)i * nT + c] = gUb[i];
+    }
+};
+
+} // namespace dab
