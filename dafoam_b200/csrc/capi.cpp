@@ -258,6 +258,15 @@ int dab_get_output_size(dab_solver* s, const char* name, const char* type, int64
     DAB_CATCH
 }
 
+int dab_bench_set_vector(dab_solver* s, const double* x)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(x, "x");
+    s->s.be.h2d(s->s.dX.p, x, (size_t)s->s.nDof() * sizeof(double));
+    DAB_CATCH
+}
+
 int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64_t* kernel_launches)
 {
     DAB_TRY
@@ -271,8 +280,15 @@ int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64
     t.start();
     for (int i = 0; i < n; i++)
     {
-        if (which == 0) S.matVecDev(S.dX.p, S.dY2.p);
-        else S.forward(0, S.dR.p);
+        switch (which)
+        {
+        case 0: S.matVecDev(S.dX.p, S.dY2.p); break;
+        case 1: S.forward(0, S.dR.p); break;
+        case 2: S.be.launch(S.hm.nC, RevA{S.mv, S.par, S.sv, S.rv, S.av, S.dX.p}); break;
+        case 3: S.be.launch(S.hm.nC, RevB{S.mv, S.par, S.sv, S.rv, S.av, S.dX.p, S.dY2.p}); break;
+        case 4: S.be.launch(S.hm.nC, RevC{S.mv, S.par, S.sv, S.rv, S.av, S.dX.p, S.dY2.p}); break;
+        default: throw Error("dab_bench_device: unknown selector");
+        }
     }
     *ms_per_call = t.stopMs() / (n > 0 ? n : 1);
     if (kernel_launches) *kernel_launches = S.be.launches - l0;

@@ -232,6 +232,10 @@ class pyDASolvers:
         self._raise(self._L.dab_bench_device(self._h, C.c_int(which), C.c_int(n), C.byref(ms), C.byref(nl)))
         return float(ms.value), int(nl.value)
 
+    def benchSetVector(self, x):
+        _check_array(x, self.getNLocalAdjointStates(), "x")
+        self._raise(self._L.dab_bench_set_vector(self._h, _dp(x)))
+
     def algorithmicBytes(self, which=0):
         v = C.c_int64()
         self._raise(self._L.dab_algorithmic_bytes(self._h, C.c_int(which), C.byref(v)))

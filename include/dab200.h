@@ -125,8 +125,11 @@ int dab_get_output_size(dab_solver* s, const char* name, const char* type, int64
 
 /* --- benchmarking hooks (no reference counterpart): run the product n times on device-resident
  * vectors and return the mean device time per launch sequence in milliseconds (CUDA events on the
- * solver's stream). which = 0: dRdWT*psi product, 1: R(W) */
+ * solver's stream). which = 0: dRdWT*psi product (3 kernels), 1: R(W) (3 kernels),
+ * 2/3/4: the reverse kernels RevA/RevB/RevC alone */
 int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64_t* kernel_launches);
+/* upload the device-resident input vector used by dab_bench_device (untimed) */
+int dab_bench_set_vector(dab_solver* s, const double* x);
 /* algorithmic bytes of one dRdWT*psi product */
 int dab_algorithmic_bytes(dab_solver* s, int which, int64_t* bytes);
 
