@@ -31,14 +31,13 @@ def grid_for(cells):
     return ni, nj
 
 
-def smooth_state(sol, seed=1234, noise=0.01):
-    """Initial (uniform) state from 0/ times (1 + 1 % seeded noise) -- SURVEY.md section 8d."""
-    n = sol.getNLocalAdjointStates()
-    W = np.zeros(n)
-    sol.getOFFields(W)
-    rng = np.random.default_rng(seed)
-    W *= 1.0 + noise * rng.uniform(-1, 1, n)
-    return W
+def smooth_state(sol, mesh, seed=1234, noise=0.001):
+    """Smooth analytic boundary-layer state (+0.1 % seeded noise) -- SURVEY.md section 8d; the reference
+    would supply a converged primal here, which needs the (out-of-scope) primal solver."""
+    from dafoam_b200 import cases
+    y = np.zeros(sol.getNLocalCells())
+    sol.getOFField("yWall", "scalar", y)
+    return cases.boundary_layer_state(mesh, y, seed=seed, noise=noise)
 
 
 class ClockSampler:
@@ -168,6 +167,8 @@ def main():
     ap.add_argument("--cells", type=int, default=980000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--restart", type=int, default=200)
+    ap.add_argument("--max-iters", type=int, default=2000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -193,11 +194,11 @@ def main():
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     opts = dict(normalizeStates=NORM_STATES, function=fn,
-                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=1000, gmresRestart=100))
+                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1))
     sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()
-    W = smooth_state(sol)
+    W = smooth_state(sol, mesh)
     sol.updateOFFields(W)
     t_setup = time.time() - t_setup
 

@@ -474,3 +474,55 @@ def write_case(case_dir, mesh: PolyMesh, bcs, binary=False, **dict_kw):
     dict_kw.setdefault("ras_model", ras)
     write_dicts(case_dir, **dict_kw)
     return case_dir
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic states
+# ----------------------------------------------------------------------------------------------
+
+
+def quad_face_geometry(mesh: PolyMesh):
+    """Area vectors and centres of quad faces (diagonal cross product / vertex mean): good enough to
+    synthesise a face-flux field; the engine computes the exact OpenFOAM geometry itself."""
+    p = mesh.points[mesh.faces]
+    Sf = 0.5 * np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 1])
+    return Sf, p.mean(axis=1)
+
+
+def boundary_layer_state(mesh: PolyMesh, yWall, U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, delta=0.02, turbulent=True,
+                         seed=1234, noise=0.0):
+    """Smooth analytic state in the reference's state ordering: a velocity
+    profile U0*(1-exp(-y/delta)) in the wall distance y, a pressure bump, a nuTilda hump inside the
+    layer, phi = U_f . S_f with zero flux through walls and symmetry planes; optional seeded noise."""
+    nC, nF, nIF = mesh.n_cells, mesh.n_faces, mesh.n_internal_faces
+    rng = np.random.default_rng(seed)
+    Sf, Cf = quad_face_geometry(mesh)
+    # cell centres as the mean of the cell's face centres
+    C = np.zeros((nC, 3))
+    cnt = np.zeros(nC)
+    np.add.at(C, mesh.owner, Cf)
+    np.add.at(cnt, mesh.owner, 1.0)
+    np.add.at(C, mesh.neighbour, Cf[:nIF])
+    np.add.at(cnt, mesh.neighbour, 1.0)
+    C /= cnt[:, None]
+    U0 = np.asarray(U0, dtype=np.float64)
+    prof = 1.0 - np.exp(-np.asarray(yWall) / delta)
+    U = U0[None, :] * prof[:, None]
+    p = 0.15 * float(U0 @ U0) * np.exp(-((C[:, 0] - 0.5) ** 2 + C[:, 1] ** 2) / 0.5)
+    nt = nuTilda0 * (1.0 + 20.0 * np.exp(-yWall / delta) * (1.0 - np.exp(-yWall / (0.1 * delta))))
+    if noise > 0.0:
+        U *= 1.0 + noise * rng.uniform(-1, 1, U.shape)
+        p *= 1.0 + noise * rng.uniform(-1, 1, nC)
+        nt *= 1.0 + noise * rng.uniform(-1, 1, nC)
+    Uf = np.empty((nF, 3))
+    Uf[:nIF] = 0.5 * (U[mesh.owner[:nIF]] + U[mesh.neighbour])
+    Uf[nIF:] = U[mesh.owner[nIF:]]
+    phi = np.einsum("ij,ij->i", Uf, Sf)
+    for pch in mesh.patches:
+        if pch["type"] in ("symmetry", "wall"):
+            phi[pch["start"]:pch["start"] + pch["size"]] = 0.0
+    parts = [U.ravel(), p]
+    if turbulent:
+        parts.append(nt)
+    parts.append(phi)
+    return np.concatenate(parts)

@@ -39,6 +39,7 @@ struct Solver
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
     double gmresRelTol = 1e-6, gmresAbsTol = 1e-14, gmresTolDiff = 1e2, fdStep = 1e-6;
     std::string pcType = "ilu";
+    int pcConLevel = 2; // cell-to-cell connectivity level of dRdWTPC (maxResConLv4JacPCMat role)
     std::vector<FunctionDef> functions;
 
     // device mesh
@@ -189,6 +190,8 @@ struct Solver
             pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
+            const int lv = (int)a->numOr("pcConLevel", pcConLevel);
+            if (lv != pcConLevel) { pcConLevel = lv; kry.symbolic = false; kry.pcValid = false; }
         }
         if (const JVal* s = o.get("adjPartDerivFDStep")) fdStep = s->numOr("State", fdStep);
         if (const JVal* fd = o.get("function"))
@@ -440,7 +443,9 @@ struct Solver
     }
 
     // ---- Krylov -----------------------------------------------------------------------------------
+    void pcSymbolic();
     void calcPC();
+    void applyPC(const double* v, double* z);
     int solveLinearEqn(const double* rhs, double* sol, KspStats& st);
 };
 

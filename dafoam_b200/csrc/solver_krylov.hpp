@@ -1,5 +1,503 @@
+// Solver::calcPC / applyPC / solveLinearEqn: preconditioner assembly (coloured finite differences of the
+// first-order residual, reference DAPartDeriv.C:350-474 + DASolver.C:948-1089), ILU(0), and the
+// right-preconditioned restarted GMRES that replaces KSPSolve (reference DALinearEqn.C:341-437).
 #pragma once
-namespace dab {
-inline void Solver::calcPC() { throw Error("not implemented"); }
-inline int Solver::solveLinearEqn(const double*, double*, KspStats&) { throw Error("not implemented"); }
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+
+namespace dab
+{
+
+namespace detail
+{
+// breadth-first ball over the cell graph with a stamp array (no clearing between calls)
+struct CellGraph
+{
+    int nC;
+    std::vector<int> off, adj, stamp, queue;
+    int tick = 0;
+    void build(const HostMesh& m)
+    {
+        nC = m.nC;
+        off.assign(nC + 1, 0);
+        for (int f = 0; f < m.nIF; f++)
+        {
+            off[m.own[f] + 1]++;
+            off[m.nei[f] + 1]++;
+        }
+        for (int c = 0; c < nC; c++) off[c + 1] += off[c];
+        adj.resize(off[nC]);
+        std::vector<int> pos(off.begin(), off.end() - 1);
+        for (int f = 0; f < m.nIF; f++)
+        {
+            adj[pos[m.own[f]]++] = m.nei[f];
+            adj[pos[m.nei[f]]++] = m.own[f];
+        }
+        stamp.assign(nC, 0);
+    }
+    // cells within `radius` hops of the seeds (seeds included), appended to out (cleared first)
+    void ball(const int* seeds, int nSeeds, int radius, std::vector<int>& out)
+    {
+        out.clear();
+        tick++;
+        for (int i = 0; i < nSeeds; i++)
+            if (stamp[seeds[i]] != tick)
+            {
+                stamp[seeds[i]] = tick;
+                out.push_back(seeds[i]);
+            }
+        size_t lo = 0;
+        for (int r = 0; r < radius; r++)
+        {
+            const size_t hi = out.size();
+            for (size_t q = lo; q < hi; q++)
+            {
+                const int c = out[q];
+                for (int e = off[c]; e < off[c + 1]; e++)
+                {
+                    const int x = adj[e];
+                    if (stamp[x] != tick)
+                    {
+                        stamp[x] = tick;
+                        out.push_back(x);
+                    }
+                }
+            }
+            lo = hi;
+        }
+    }
+};
+
+// greedy colouring: item i conflicts with the items listed by neighbours(i, out)
+template <class NbrFn>
+int greedyColour(int n, NbrFn nbr, std::vector<int>& colour)
+{
+    colour.assign(n, -1);
+    std::vector<int> mark, tmp;
+    int nCol = 0;
+    for (int i = 0; i < n; i++)
+    {
+        nbr(i, tmp);
+        if ((int)mark.size() < nCol + 1) mark.resize(nCol + 1, -1);
+        for (int x : tmp)
+            if (colour[x] >= 0) mark[colour[x]] = i;
+        int k = 0;
+        while (k < nCol && mark[k] == i) k++;
+        if (k == nCol)
+        {
+            nCol++;
+            mark.resize(nCol + 1, -1);
+        }
+        colour[i] = k;
+    }
+    return nCol;
 }
+} // namespace detail
+
+inline void Solver::pcSymbolic()
+{
+    using detail::CellGraph;
+    Krylov& K = kry;
+    const int nC = hm.nC, nF = hm.nF, nIF = hm.nIF;
+    const int ns = par.turb ? 5 : 4;
+    const int offPhi = ns * nC;
+    K.n = nDof();
+    CellGraph G;
+    G.build(hm);
+    const int Lcc = pcConLevel, Lfc = 0, Lcf = 0;
+    // owned faces per cell (a face belongs to the block of its owner cell)
+    std::vector<int> ofOff(nC + 1, 0), ofList(nF);
+    for (int f = 0; f < nF; f++) ofOff[hm.own[f] + 1]++;
+    for (int c = 0; c < nC; c++) ofOff[c + 1] += ofOff[c];
+    {
+        std::vector<int> pos(ofOff.begin(), ofOff.end() - 1);
+        for (int f = 0; f < nF; f++) ofList[pos[hm.own[f]]++] = f;
+    }
+    // all faces of a cell from the ELL table
+    auto facesOf = [&](int c, std::vector<int>& out) {
+        for (int k = 0; k < hm.maxCF; k++)
+        {
+            const int e = hm.cellFaces[(size_t)k * nC + c];
+            if (e < 0) break;
+            out.push_back(e >> 1);
+        }
+    };
+    // ---- 1. multicolour ordering of the cells: same-colour cells share no matrix entry
+    const int rho = std::max(std::max(Lcc, Lfc + 1), Lcf + 1);
+    std::vector<int> colour;
+    const int nCol = detail::greedyColour(nC, [&](int c, std::vector<int>& out) { G.ball(&c, 1, rho, out); }, colour);
+    std::vector<std::vector<int>> cellsOf(nCol);
+    for (int c = 0; c < nC; c++) cellsOf[colour[c]].push_back(c);
+    K.perm.assign(K.n, -1);
+    K.iperm.assign(K.n, -1);
+    K.colours.clear();
+    std::vector<int> groupOfRow(K.n), groupRows, groupStart;
+    int next = 0;
+    for (int k = 0; k < nCol; k++)
+    {
+        auto& cl = cellsOf[k];
+        std::stable_sort(cl.begin(), cl.end(), [&](int a, int b) { return (ofOff[a + 1] - ofOff[a]) > (ofOff[b + 1] - ofOff[b]); });
+        int maxOwned = 0;
+        for (int c : cl) maxOwned = std::max(maxOwned, ofOff[c + 1] - ofOff[c]);
+        if (ns + maxOwned > MAXSLOT) throw Error("calcdRdWT: too many faces per cell for the block ordering");
+        ColourView cv;
+        cv.nCells = (int)cl.size();
+        cv.nSlots = ns + maxOwned;
+        for (int s = 0; s < MAXSLOT; s++) cv.slotStart[s] = cv.slotCount[s] = 0;
+        for (int s = 0; s < cv.nSlots; s++)
+        {
+            cv.slotStart[s] = next;
+            int cnt = 0;
+            for (int c : cl)
+            {
+                int ext;
+                if (s < 3) ext = 3 * c + s;
+                else if (s < ns) ext = (s)*nC + c; // p at 3nC + c, nuTilda at 4nC + c
+                else
+                {
+                    const int q = s - ns;
+                    if (q >= ofOff[c + 1] - ofOff[c]) break; // cells sorted by owned-face count
+                    ext = offPhi + ofList[ofOff[c] + q];
+                }
+                K.perm[next] = ext;
+                K.iperm[ext] = next;
+                groupOfRow[next] = (int)groupRows.size();
+                next++;
+                cnt++;
+            }
+            cv.slotCount[s] = cnt;
+            groupStart.push_back(cv.slotStart[s]);
+            groupRows.push_back(cnt);
+        }
+        K.colours.push_back(cv);
+    }
+    if (next != K.n) throw Error("calcdRdWT: ordering does not cover all states");
+    // ---- 2. sparsity pattern (new numbering), two passes: lengths, then ELL fill
+    const int nG = (int)groupRows.size();
+    std::vector<int> width(nG, 0);
+    K.rowLen.assign(K.n, 0);
+    std::vector<int> cellsBall, cols, faces;
+    auto cellRowCols = [&](int c) {
+        cols.clear();
+        G.ball(&c, 1, Lcc, cellsBall);
+        for (int x : cellsBall)
+        {
+            for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
+            cols.push_back(K.iperm[3 * nC + x]);
+            if (par.turb) cols.push_back(K.iperm[4 * nC + x]);
+        }
+        G.ball(&c, 1, Lfc, cellsBall);
+        faces.clear();
+        for (int x : cellsBall) facesOf(x, faces);
+        std::sort(faces.begin(), faces.end());
+        faces.erase(std::unique(faces.begin(), faces.end()), faces.end());
+        for (int f : faces) cols.push_back(K.iperm[offPhi + f]);
+        std::sort(cols.begin(), cols.end());
+    };
+    auto faceRowCols = [&](int f) {
+        cols.clear();
+        int seeds[2] = {hm.own[f], f < nIF ? hm.nei[f] : hm.own[f]};
+        G.ball(seeds, f < nIF ? 2 : 1, Lcf, cellsBall);
+        for (int x : cellsBall)
+        {
+            for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
+            cols.push_back(K.iperm[3 * nC + x]);
+            if (par.turb) cols.push_back(K.iperm[4 * nC + x]);
+        }
+        cols.push_back(K.iperm[offPhi + f]);
+        std::sort(cols.begin(), cols.end());
+    };
+    for (int c = 0; c < nC; c++)
+    {
+        cellRowCols(c);
+        for (int s = 0; s < ns; s++)
+        {
+            const int i = K.iperm[s < 3 ? 3 * c + s : s * nC + c];
+            K.rowLen[i] = (int)cols.size();
+            width[groupOfRow[i]] = std::max(width[groupOfRow[i]], (int)cols.size());
+        }
+    }
+    for (int f = 0; f < nF; f++)
+    {
+        faceRowCols(f);
+        const int i = K.iperm[offPhi + f];
+        K.rowLen[i] = (int)cols.size();
+        width[groupOfRow[i]] = std::max(width[groupOfRow[i]], (int)cols.size());
+    }
+    std::vector<int64_t> gOff(nG + 1, 0);
+    for (int g = 0; g < nG; g++) gOff[g + 1] = gOff[g] + (int64_t)width[g] * groupRows[g];
+    K.ellSize = gOff[nG];
+    K.rowBase.resize(K.n);
+    K.rowStride.resize(K.n);
+    K.diag.assign(K.n, -1);
+    for (int i = 0; i < K.n; i++)
+    {
+        const int g = groupOfRow[i];
+        K.rowBase[i] = gOff[g] + (i - groupStart[g]);
+        K.rowStride[i] = groupRows[g];
+    }
+    K.hCol.assign((size_t)K.ellSize, -1);
+    K.nnz = 0;
+    auto putRow = [&](int i) {
+        for (size_t e = 0; e < cols.size(); e++)
+        {
+            K.hCol[(size_t)(K.rowBase[i] + (int64_t)e * K.rowStride[i])] = cols[e];
+            if (cols[e] == i) K.diag[i] = (int)e;
+        }
+        K.nnz += (int64_t)cols.size();
+        if (K.diag[i] < 0) throw Error("calcdRdWT: missing diagonal in the pattern");
+    };
+    for (int c = 0; c < nC; c++)
+    {
+        cellRowCols(c);
+        for (int s = 0; s < ns; s++) putRow(K.iperm[s < 3 ? 3 * c + s : s * nC + c]);
+    }
+    for (int f = 0; f < nF; f++)
+    {
+        faceRowCols(f);
+        putRow(K.iperm[offPhi + f]);
+    }
+    // ---- 3. colouring of the perturbations (DAColoring role).  Two states may share a colour when no
+    // residual row in the pattern of one is touched by the other: cells at distance > Lcc + 3 (the
+    // first-order pRes reaches 3 levels), faces whose cells are more than Lcf + 1 hops apart.
+    std::vector<int> fdCell;
+    const int nFdCell = detail::greedyColour(nC, [&](int c, std::vector<int>& out) { G.ball(&c, 1, Lcc + 3, out); }, fdCell);
+    std::vector<int> fdFace;
+    std::vector<int> tmpCells;
+    const int nFdFace = detail::greedyColour(nF, [&](int f, std::vector<int>& out) {
+        int seeds[2] = {hm.own[f], f < nIF ? hm.nei[f] : hm.own[f]};
+        G.ball(seeds, f < nIF ? 2 : 1, Lcf + 1, tmpCells);
+        out.clear();
+        for (int x : tmpCells) facesOf(x, out);
+    }, fdFace);
+    const int nFd = ns * nFdCell + nFdFace;
+    std::vector<int> cnt(nFd + 1, 0);
+    auto fdColourOf = [&](int ext) {
+        if (ext < 3 * nC) return (ext % 3) * nFdCell + fdCell[ext / 3];
+        if (ext < offPhi) return (ext / nC) * nFdCell + fdCell[ext % nC];
+        return ns * nFdCell + fdFace[ext - offPhi];
+    };
+    for (int j = 0; j < K.n; j++) cnt[fdColourOf(j) + 1]++;
+    for (int k = 0; k < nFd; k++) cnt[k + 1] += cnt[k];
+    K.fdStart.assign(cnt.begin(), cnt.end());
+    K.fdList.resize(K.n);
+    {
+        std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+        for (int j = 0; j < K.n; j++) K.fdList[pos[fdColourOf(j)]++] = j;
+    }
+    // ---- upload
+    K.dPerm.upload(be, K.perm);
+    K.dIPerm.upload(be, K.iperm);
+    K.dRowBase.upload(be, K.rowBase);
+    K.dRowStride.upload(be, K.rowStride);
+    K.dRowLen.upload(be, K.rowLen);
+    K.dDiag.upload(be, K.diag);
+    K.dCol.upload(be, K.hCol);
+    K.dVal.alloc(be, (size_t)K.ellSize);
+    K.dFdList.upload(be, K.fdList);
+    K.R0.alloc(be, K.n);
+    K.R1.alloc(be, K.n);
+    K.t1.alloc(be, K.n);
+    K.t2.alloc(be, K.n);
+    std::vector<int32_t>().swap(K.hCol);
+    K.symbolic = true;
+    if (printInfo)
+        fprintf(stderr, "[dab200] dRdWTPC: %d states, %lld nonzeros (%.1f/row), ELL %lld, %d ordering colours, %d FD colours (%d cell x %d + %d face)\n",
+                K.n, (long long)K.nnz, (double)K.nnz / K.n, (long long)K.ellSize, nCol, nFd, nFdCell, ns, nFdFace);
+}
+
+inline void Solver::calcPC()
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    Krylov& K = kry;
+    if (!K.symbolic) pcSymbolic();
+    be.zero(K.dVal.p, (size_t)K.ellSize * sizeof(double));
+    StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi};
+    // R0 at the unperturbed state with the div(pc) schemes (DASolver::calcdRdWT isPC=1)
+    forward(1, K.R0.p);
+    const int nFd = (int)K.fdStart.size() - 1;
+    EllView A = K.view();
+    for (int k = 0; k < nFd; k++)
+    {
+        const int n = K.fdStart[k + 1] - K.fdStart[k];
+        if (n == 0) continue;
+        const int32_t* list = K.dFdList.p + K.fdStart[k];
+        be.launch(n, FdPerturb{sp, list, fdStep});
+        forward(1, K.R1.p);
+        be.launch(n, FdFill{A, list, K.dIPerm.p, K.dPerm.p, K.R0.p, K.R1.p, 1.0 / fdStep});
+        be.launch(n, FdPerturb{sp, list, -fdStep});
+    }
+    // restore the exact states and invalidate the record (it now holds first-order intermediates)
+    {
+        const size_t nC = hm.nC;
+        be.d2d(dU.p, dWext.p, 3 * nC * sizeof(double));
+        be.d2d(dP.p, dWext.p + 3 * nC, nC * sizeof(double));
+        size_t off = 4 * nC;
+        if (par.turb)
+        {
+            be.d2d(dNt.p, dWext.p + off, nC * sizeof(double));
+            off += nC;
+        }
+        be.d2d(dPhi.p, dWext.p + off, (size_t)hm.nF * sizeof(double));
+        recorded = false;
+    }
+    // ILU(0), one kernel per colour
+    for (const ColourView& cv : K.colours) be.launch(cv.nCells, IluFactorColour{A, cv, 1e-10});
+    be.sync();
+    K.pcValid = true;
+    K.pcSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// z = M^{-1} v  (external layout in and out)
+inline void Solver::applyPC(const double* v, double* z)
+{
+    Krylov& K = kry;
+    EllView A = K.view();
+    be.launch(K.n, GatherVec{v, K.dPerm.p, K.t1.p});
+    for (size_t k = 0; k < K.colours.size(); k++) be.launch(K.colours[k].nCells, TriLowerColour{A, K.colours[k], K.t1.p});
+    for (size_t k = K.colours.size(); k-- > 0;) be.launch(K.colours[k].nCells, TriUpperColour{A, K.colours[k], K.t1.p});
+    be.launch(K.n, ScatterVec{K.t1.p, K.dPerm.p, z});
+}
+
+// DALinearEqn::solveLinearEqn: GMRES(restart), right PC, zero initial guess, unpreconditioned norm
+inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
+{
+    Krylov& K = kry;
+    if (!K.pcValid) calcPC();
+    ensureRecorded();
+    const int n = nDof();
+    const int m = std::max(1, std::min(gmresRestart, gmresMaxIters));
+    if (K.vCap < m + 1 || K.V.n < (size_t)(m + 1) * n)
+    {
+        K.V.alloc(be, (size_t)(m + 1) * n, false);
+        K.vCap = m + 1;
+        K.w.alloc(be, n);
+        K.z.alloc(be, n);
+        K.xdev.alloc(be, n);
+        K.bdev.alloc(be, n);
+        K.hdev.alloc(be, m + 2);
+        K.ops.init(be, m + 2);
+    }
+    be.h2d(K.bdev.p, rhs, (size_t)n * sizeof(double));
+    be.zero(K.xdev.p, (size_t)n * sizeof(double));
+    auto timer = be.timer();
+    be.sync();
+    timer.start();
+    const long l0 = be.launches;
+    const double bnorm = K.ops.norm2(K.bdev.p, n);
+    st.r0 = bnorm;
+    st.nMatvec = 0;
+    const double tol = std::max(gmresRelTol * bnorm, gmresAbsTol);
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), yv(m, 0.0), hcol(m + 2, 0.0);
+    int its = 0;
+    double rnorm = bnorm;
+    int reason = 0;
+    if (bnorm == 0.0)
+    {
+        reason = 3;
+    }
+    while (reason == 0)
+    {
+        // r = b - A x (x = 0 on the first cycle)
+        double beta;
+        if (its == 0)
+        {
+            be.d2d(K.w.p, K.bdev.p, (size_t)n * sizeof(double));
+            beta = bnorm;
+        }
+        else
+        {
+            matVecDev(K.xdev.p, K.w.p);
+            st.nMatvec++;
+            be.launch(n, SubVec{K.bdev.p, K.w.p});
+            beta = K.ops.norm2(K.w.p, n);
+        }
+        rnorm = beta;
+        if (rnorm <= tol) { reason = rnorm <= gmresRelTol * bnorm ? 2 : 3; break; }
+        be.launch(n, ScaleCopy{K.w.p, 1.0 / beta, K.V.p});
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int k = 0;
+        for (; k < m && its < gmresMaxIters; k++, its++)
+        {
+            double* vk = K.V.p + (size_t)k * n;
+            double* vk1 = K.V.p + (size_t)(k + 1) * n;
+            applyPC(vk, K.z.p);
+            matVecDev(K.z.p, vk1);
+            st.nMatvec++;
+            // classical Gram-Schmidt with refinement if needed (KSP_GMRES_CGS_REFINE_IFNEEDED)
+            const double* d = K.ops.dots(K.V.p, n, k + 2, vk1, n); // V_0..V_k . w and w . w (V_{k+1} = w)
+            for (int j = 0; j <= k; j++) hcol[j] = d[j];
+            const double wn2 = d[k + 1];
+            be.h2d(K.hdev.p, hcol.data(), (size_t)(k + 1) * sizeof(double));
+            be.launch(n, MultiAxpy{K.V.p, n, k + 1, K.hdev.p, vk1, 0});
+            double hn2 = 0.0;
+            for (int j = 0; j <= k; j++) hn2 += hcol[j] * hcol[j];
+            double nrm = K.ops.norm2(vk1, n);
+            (void)hn2;
+            if (nrm * nrm < 0.5 * wn2 * 0.5 || useMGSO)
+            {
+                const double* d2 = K.ops.dots(K.V.p, n, k + 1, vk1, n);
+                std::vector<double> h2(d2, d2 + k + 1);
+                be.h2d(K.hdev.p, h2.data(), (size_t)(k + 1) * sizeof(double));
+                be.launch(n, MultiAxpy{K.V.p, n, k + 1, K.hdev.p, vk1, 0});
+                for (int j = 0; j <= k; j++) hcol[j] += h2[j];
+                nrm = K.ops.norm2(vk1, n);
+            }
+            hcol[k + 1] = nrm;
+            if (nrm > 0.0) be.launch(n, ScaleCopy{vk1, 1.0 / nrm, vk1});
+            // Givens rotations
+            for (int j = 0; j < k; j++)
+            {
+                const double t = cs[j] * hcol[j] + sn[j] * hcol[j + 1];
+                hcol[j + 1] = -sn[j] * hcol[j] + cs[j] * hcol[j + 1];
+                hcol[j] = t;
+            }
+            const double dd = std::hypot(hcol[k], hcol[k + 1]);
+            cs[k] = dd > 0 ? hcol[k] / dd : 1.0;
+            sn[k] = dd > 0 ? hcol[k + 1] / dd : 0.0;
+            hcol[k] = dd;
+            hcol[k + 1] = 0.0;
+            g[k + 1] = -sn[k] * g[k];
+            g[k] = cs[k] * g[k];
+            for (int j = 0; j <= k; j++) H[(size_t)j * m + k] = hcol[j];
+            rnorm = std::fabs(g[k + 1]);
+            if (printInfo && (its % 50 == 0)) fprintf(stderr, "[dab200] GMRES %4d  residual %.6e\n", its, rnorm);
+            if (rnorm <= tol || nrm == 0.0)
+            {
+                k++;
+                its++;
+                break;
+            }
+        }
+        // y = H^{-1} g, x += M^{-1} (V y)
+        for (int i = k - 1; i >= 0; i--)
+        {
+            double s = g[i];
+            for (int j = i + 1; j < k; j++) s -= H[(size_t)i * m + j] * yv[j];
+            yv[i] = s / H[(size_t)i * m + i];
+        }
+        be.h2d(K.hdev.p, yv.data(), (size_t)k * sizeof(double));
+        be.launch(n, MultiAxpy{K.V.p, n, k, K.hdev.p, K.w.p, 1});
+        applyPC(K.w.p, K.z.p);
+        be.launch(n, AxpyVec{K.z.p, 1.0, K.xdev.p});
+        if (rnorm <= tol) reason = rnorm <= gmresRelTol * bnorm ? 2 : 3;
+        else if (its >= gmresMaxIters) reason = -3;
+    }
+    st.solveSec = timer.stopMs() * 1e-3;
+    (void)l0;
+    be.d2h(sol, K.xdev.p, (size_t)n * sizeof(double));
+    st.iterations = its;
+    st.reason = reason;
+    st.rn = rnorm;
+    st.pcSec = K.pcSec;
+    if (printInfo)
+        fprintf(stderr, "[dab200] Main iteration %d KSP Residual norm %14.12e %.3f s\n", its, rnorm, st.solveSec);
+    // reference success rule (DALinearEqn.C:422-434)
+    const double absRatio = rnorm / gmresAbsTol;
+    const double relRatio = bnorm > 0 ? rnorm / bnorm / gmresRelTol : 0.0;
+    return (relRatio > gmresTolDiff && absRatio > gmresTolDiff) ? 1 : 0;
+}
+
+} // namespace dab

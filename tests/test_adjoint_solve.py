@@ -1,0 +1,85 @@
+"""GMRES + ILU(0) adjoint solve: psi from the engine vs a dense direct solve of the same operator
+(assembled column by column through the engine's own matrix-free product)."""
+import numpy as np
+import pytest
+
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import KSP, Mat, pyDASolvers
+from tests.common import HOSTSIM, NORM_STATES
+
+FN = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
+             "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
+
+
+def adjoint_case(lib_path, ni=24, nj=12, restart=200, maxit=400):
+    import tempfile
+    mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1)
+    d = tempfile.mkdtemp(prefix="dab_adj_")
+    cases.write_case(d, mesh, cases.default_bcs_naca())
+    opts = dict(normalizeStates=NORM_STATES, function=FN,
+                adjEqnOption=dict(gmresRelTol=1e-9, gmresMaxIters=maxit, gmresRestart=restart))
+    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib_path)
+    nC = sol.getNLocalCells()
+    y = np.zeros(nC)
+    sol.getOFField("yWall", "scalar", y)
+    W = cases.boundary_layer_state(mesh, y)
+    sol.updateOFFields(W)
+    return mesh, sol, W
+
+
+def solve_and_check(lib_path):
+    mesh, sol, W = adjoint_case(lib_path)
+    n = sol.getNLocalAdjointStates()
+    # the reference's call order: dFdW, dRdWTPC, KSP, solveLinearEqn (mphys_dafoam.py:433-574)
+    dFdW = np.zeros(n)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+    sol.runColoring()
+    pc = Mat()
+    sol.calcdRdWT(1, pc)
+    ksp = KSP()
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    psi = np.zeros(n)
+    fail = sol.solveLinearEqn(ksp, dFdW, psi)
+    st = ksp.stats
+    assert fail == 0 and st.converged_reason == 2
+    assert st.final_residual <= 1e-9 * st.initial_residual * 1.01
+    # true residual through the matrix-free operator
+    r = np.zeros(n)
+    sol.calcdRdWTPsiAD(psi, r)
+    assert np.linalg.norm(r - dFdW) <= 2e-9 * np.linalg.norm(dFdW)
+    # dense direct solve of the same operator
+    A = np.zeros((n, n))
+    e, col = np.zeros(n), np.zeros(n)
+    for i in range(n):
+        e[:] = 0.0
+        e[i] = 1.0
+        sol.calcdRdWTPsiAD(e, col)
+        A[:, i] = col
+    psi_d = np.linalg.solve(A, dFdW)
+    assert np.linalg.norm(psi - psi_d) <= 1e-5 * np.linalg.norm(psi_d)
+    return st.iterations
+
+
+def test_adjoint_solve_host_build():
+    its = solve_and_check(HOSTSIM)
+    assert 0 < its < 400
+
+
+def test_failure_flag_follows_the_reference_rule():
+    mesh, sol, W = adjoint_case(HOSTSIM, maxit=3, restart=3)
+    n = sol.getNLocalAdjointStates()
+    dFdW = np.zeros(n)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+    pc = Mat()
+    sol.calcdRdWT(1, pc)
+    ksp = KSP()
+    psi = np.zeros(n)
+    # 3 iterations cannot reach 1e-9: relRatio and absRatio both exceed gmresTolDiff -> 1 (DALinearEqn.C:422-434)
+    assert sol.solveLinearEqn(ksp, dFdW, psi) == 1
+    assert ksp.stats.converged_reason == -3 and ksp.stats.iterations == 3
+
+
+@pytest.mark.gpu
+def test_adjoint_solve_cuda():
+    its = solve_and_check(None)
+    assert 0 < its < 400
