@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--restart", type=int, default=200)
+    ap.add_argument("--pc-level", type=int, default=2)
     ap.add_argument("--max-iters", type=int, default=2000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -194,7 +195,7 @@ def main():
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     opts = dict(normalizeStates=NORM_STATES, function=fn,
-                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1))
+                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level))
     sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()

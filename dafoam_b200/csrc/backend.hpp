@@ -24,8 +24,15 @@ namespace dab
         if (e_ != cudaSuccess) throw ::dab::Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); \
     } while (0)
 
+// per-functor occupancy hint: minimum resident blocks per SM (registers are capped accordingly)
 template <class F>
-__global__ void __launch_bounds__(128) kernel1d(int n, F f)
+struct LaunchTraits
+{
+    static constexpr int minBlocks = 1;
+};
+
+template <class F>
+__global__ void __launch_bounds__(128, LaunchTraits<F>::minBlocks) kernel1d(int n, F f)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) f(i);

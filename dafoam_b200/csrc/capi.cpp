@@ -201,6 +201,20 @@ int dab_calc_drdwt_pc(dab_solver* s)
     DAB_CATCH
 }
 
+int dab_pc_apply(dab_solver* s, const double* v, double* z)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(v, "v");
+    need(z, "z");
+    Solver& S = s->s;
+    if (!S.kry.pcValid) S.calcPC();
+    S.be.h2d(S.dX.p, v, (size_t)S.nDof() * sizeof(double));
+    S.applyPC(S.dX.p, S.dY2.p);
+    S.be.d2h(z, S.dY2.p, (size_t)S.nDof() * sizeof(double));
+    DAB_CATCH
+}
+
 int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats)
 {
     DAB_TRY

@@ -20,6 +20,17 @@
 namespace dab
 {
 
+#if !defined(DAB_HOSTSIM)
+#ifndef DAB_REVB_MINBLOCKS
+#define DAB_REVB_MINBLOCKS 3
+#endif
+#ifndef DAB_FWDB_MINBLOCKS
+#define DAB_FWDB_MINBLOCKS 1
+#endif
+template <> struct LaunchTraits<RevB> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
+template <> struct LaunchTraits<FwdB> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
+#endif
+
 struct FunctionDef
 {
     std::string name, type;

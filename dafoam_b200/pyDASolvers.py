@@ -214,6 +214,12 @@ class pyDASolvers:
             myKSP.stats = st
         return int(fail.value)
 
+    def applyPC(self, v, z):
+        n = self.getNLocalAdjointStates()
+        _check_array(v, n, "v")
+        _check_array(z, n, "z")
+        self._raise(self._L.dab_pc_apply(self._h, _dp(v), _dp(z)))
+
     # ---- v2/v3-era names used by BASELINE.json's north_star (thin aliases)
     def calcdRdWTPsiAD(self, psi, dRdWTPsi):
         n = self.getNLocalAdjointStates()

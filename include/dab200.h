@@ -111,6 +111,9 @@ int dab_drdwt_mat_vec(dab_solver* s, const double* x, double* y);
  * (reference DASolver.C:948-1089, DAPartDeriv.C:350-474, DALinearEqn.C:28-339). */
 int dab_calc_drdwt_pc(dab_solver* s);
 
+/* z = M^-1 v with the factorised dRdWTPC (the PCApply of the reference's KSP, DALinearEqn.C:142-310) */
+int dab_pc_apply(dab_solver* s, const double* v, double* z);
+
 /* solveLinearEqn(ksp, rhs, sol): right-preconditioned restarted GMRES on the device
  * (reference DASolver.C:1121-1155, DALinearEqn.C:341-437).  *fail = 0/1 with the reference's
  * success rule (relRatio > gmresTolDiff && absRatio > gmresTolDiff  =>  1). */

@@ -1,0 +1,27 @@
+"""Kernel micro-benchmark on the 980k-cell NACA0012 SA case: per-kernel device times for one or more
+builds of libdab200 (used to compare launch-bound / layout variants).  python scripts/kbench.py [lib.so ...]"""
+import os, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import pyDASolvers
+
+libs = sys.argv[1:] or [None]
+cells = int(os.environ.get("KB_CELLS", "980000"))
+nj = max(8, int(round((cells / 2.0) ** 0.5 / 2.0)) * 2)
+mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1)
+d = tempfile.mkdtemp(prefix="dab_kb_")
+cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
+for lib in libs:
+    sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0)), caseDir=d, _lib_path=lib)
+    n = sol.getNLocalAdjointStates()
+    y = np.zeros(sol.getNLocalCells()); sol.getOFField("yWall", "scalar", y)
+    sol.updateOFFields(cases.boundary_layer_state(mesh, y, noise=0.001))
+    sol.benchSetVector(np.random.default_rng(4321).uniform(-1, 1, n))
+    sol.benchDevice(0, 5)
+    out = {}
+    for name, which in (("product", 0), ("forward", 1), ("RevA", 2), ("RevB", 3), ("RevC", 4)):
+        out[name] = round(sol.benchDevice(which, 30)[0], 4)
+    print(os.path.basename(lib or "libdab200.so"), out, flush=True)
+    del sol
