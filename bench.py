@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--cells", type=int, default=980000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--solve-multi", action="store_true")
     ap.add_argument("--restart", type=int, default=200)
     ap.add_argument("--pc-level", type=int, default=2)
     ap.add_argument("--max-iters", type=int, default=2000)
@@ -187,19 +188,47 @@ def main():
     from dafoam_b200 import cases
     from dafoam_b200.pyDASolvers import pyDASolvers
 
-    ni, nj = grid_for(args.cells)
+    # weak scaling: the global mesh has world x args.cells cells and is split into `world` sub-domains (RCB)
+    ni, nj = grid_for(args.cells * world)
     t_setup = time.time()
     mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1)
-    case_dir = tempfile.mkdtemp(prefix="dab_bench_r%d_" % rank)
-    cases.write_case(case_dir, mesh, cases.default_bcs_naca(), binary=True)
+    shared = [None]
+    if rank == 0:
+        shared[0] = tempfile.mkdtemp(prefix="dab_bench_")
+        cases.write_case(shared[0], mesh, cases.default_bcs_naca(), binary=True)
+    uid = None
+    if world > 1:
+        from dafoam_b200.pyDASolvers import nccl_unique_id
+        box = [shared[0], nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        shared[0], uid = box
+    case_dir = shared[0]
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     opts = dict(normalizeStates=NORM_STATES, function=fn,
                 adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level))
-    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank)
+    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()
-    W = smooth_state(sol, mesh)
+    if world == 1:
+        W = smooth_state(sol, mesh)
+    else:
+        # global analytic state (wall distance by a KD-tree on the wall-face centres), then this rank's slice
+        from scipy.spatial import cKDTree
+        Sf, Cf = cases.quad_face_geometry(mesh)
+        wall = [p for p in mesh.patches if p["type"] == "wall"][0]
+        nIF = mesh.n_internal_faces
+        Cc = np.zeros((mesh.n_cells, 3))
+        cnt = np.zeros(mesh.n_cells)
+        np.add.at(Cc, mesh.owner, Cf)
+        np.add.at(cnt, mesh.owner, 1.0)
+        np.add.at(Cc, mesh.neighbour, Cf[:nIF])
+        np.add.at(cnt, mesh.neighbour, 1.0)
+        Cc /= cnt[:, None]
+        yw = cKDTree(Cf[wall["start"]:wall["start"] + wall["size"]]).query(Cc)[0]
+        Wg = cases.boundary_layer_state(mesh, yw, seed=1234, noise=0.001)
+        W = np.ascontiguousarray(Wg[sol.localStateIndex(mesh.n_cells, mesh.n_faces)])
+        del Wg
     sol.updateOFFields(W)
     t_setup = time.time() - t_setup
 
@@ -245,7 +274,7 @@ def main():
     ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
 
     adjoint = None
-    if not args.no_solve and hasattr(sol, "solveLinearEqn"):
+    if not args.no_solve and (world == 1 or args.solve_multi):
         try:
             from dafoam_b200.pyDASolvers import Mat, KSP
             t0 = time.perf_counter()
@@ -280,7 +309,8 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     alg = sol.algorithmicBytes(0)
     achieved = alg / (ms_max * 1e-3) / 1e9
-    value = world * nC / (ms_max * 1e-3) / 1e9
+    nC_global = sol.getNGlobalCells()
+    value = nC_global / (ms_max * 1e-3) / 1e9
     out = {
         "metric": "dRdWTPsi_GCells_per_s", "value": value, "unit": "GCells/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -288,9 +318,9 @@ def main():
         "config": {"workload": "DASimpleFoam NACA0012 SA %dx%dx1 O-grid, %d cells, %d DOF per GPU; adjoint matvec "
                                "dRdW^T*psi; working set per product ~%.0f MB >> 126 MB L2 (no explicit flush)"
                                % (ni, nj, nC, n, (alg + 60 * 8 * nC) / 1e6),
-                   "parallelism": "replica per GPU" if world > 1 else "single GPU", "setup_s": t_setup},
+                   "parallelism": ("domain decomposition (RCB) over %d GPUs, NCCL ghost-cell exchange" % world) if world > 1 else "single GPU", "setup_s": t_setup},
         "gpu_launches": launches,
-        "e2e": {"value": world * nC / (e2e_ms_max * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": e2e_ms_max,
+        "e2e": {"value": nC_global / (e2e_ms_max * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": e2e_ms_max,
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                 "call": "pyDASolvers.calcdRdWTPsiAD(psi_host, y_host) -> dab_drdwt_mat_vec (pinned host buffers)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

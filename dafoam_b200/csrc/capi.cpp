@@ -12,6 +12,10 @@ struct dab_solver
 };
 
 static thread_local std::string g_err;
+// communication callbacks for the next dab_create (test-only host build: torch.distributed/gloo drives the halos)
+static dab_exchange_fn g_cbExchange = nullptr;
+static dab_allreduce_fn g_cbAllreduce = nullptr;
+static void* g_cbCtx = nullptr;
 
 #define DAB_TRY try {
 #define DAB_CATCH                                   \
@@ -53,11 +57,14 @@ int dab_create(const char* case_dir, const char* args_all, const char* options_j
     DAB_TRY
     need(case_dir, "case_dir");
     need(out, "out");
-    (void)nccl_unique_id;
     dab_solver* h = new dab_solver();
     try
     {
-        h->s.create(case_dir, args_all ? args_all : "DASimpleFoam -python", options_json ? options_json : "", device, rank, n_ranks);
+        h->s.comm.cbExchange = g_cbExchange;
+        h->s.comm.cbAllreduce = g_cbAllreduce;
+        h->s.comm.cbCtx = g_cbCtx;
+        h->s.create(case_dir, args_all ? args_all : "DASimpleFoam -python", options_json ? options_json : "", device, rank, n_ranks,
+                    nccl_unique_id);
     }
     catch (...)
     {
@@ -74,6 +81,7 @@ int dab_destroy(dab_solver* s)
     if (s)
     {
         s->s.be.sync();
+        s->s.comm.destroy();
         delete s;
     }
     DAB_CATCH
@@ -83,13 +91,22 @@ int dab_nccl_unique_id(void* out128)
 {
     DAB_TRY
     need(out128, "out128");
-    throw Error("multi-rank support is not built into this library");
+#if !defined(DAB_HOSTSIM) && defined(DAB_WITH_NCCL)
+    static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id size");
+    ncclUniqueId id;
+    NcclApi& N = NcclApi::get();
+    ncclResult_t r = N.GetUniqueId(&id);
+    if (r != ncclSuccess) throw Error(std::string("ncclGetUniqueId: ") + N.GetErrorString(r));
+    memcpy(out128, &id, sizeof(id));
+#else
+    throw Error("NCCL is not built into this library");
+#endif
     DAB_CATCH
 }
 
 int dab_n_local_adjoint_states(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.nDof(); DAB_CATCH }
 int dab_n_local_cells(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nC; DAB_CATCH }
-int dab_n_global_cells(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nC; DAB_CATCH }
+int dab_n_global_cells(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.part.nGlobalCells; DAB_CATCH }
 int dab_n_local_points(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nP; DAB_CATCH }
 int dab_n_local_faces(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nF; DAB_CATCH }
 int dab_n_local_internal_faces(dab_solver* s, int64_t* out) { DAB_TRY need(s, "solver"); *out = s->s.hm.nIF; DAB_CATCH }
@@ -201,6 +218,36 @@ int dab_calc_drdwt_pc(dab_solver* s)
     DAB_CATCH
 }
 
+int dab_set_comm_callbacks(dab_exchange_fn exchange, dab_allreduce_fn allreduce, void* ctx)
+{
+    DAB_TRY
+#ifdef DAB_HOSTSIM
+    g_cbExchange = exchange;
+    g_cbAllreduce = allreduce;
+    g_cbCtx = ctx;
+#else
+    (void)exchange; (void)allreduce; (void)ctx;
+    throw Error("communication callbacks exist only in the test build; the product uses NCCL");
+#endif
+    DAB_CATCH
+}
+
+int dab_get_local_to_global(dab_solver* s, int what, int64_t* out)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(out, "out");
+    Solver& S = s->s;
+    if (what == 0)
+        for (int c = 0; c < S.hm.nC; c++) out[c] = S.nRanks > 1 ? S.part.cellGlobal[c] : c;
+    else if (what == 1)
+        for (int f = 0; f < S.hm.nF; f++) out[f] = S.nRanks > 1 ? S.part.faceGlobal[f] : f;
+    else if (what == 2)
+        for (int f = 0; f < S.hm.nF; f++) out[f] = S.nRanks > 1 ? S.part.faceOwned[f] : 1;
+    else throw Error("dab_get_local_to_global: what must be 0 (cells), 1 (faces) or 2 (face ownership)");
+    DAB_CATCH
+}
+
 int dab_pc_apply(dab_solver* s, const double* v, double* z)
 {
     DAB_TRY
@@ -298,9 +345,9 @@ int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64
         {
         case 0: S.matVecDev(S.dX.p, S.dY2.p); break;
         case 1: S.forward(0, S.dR.p); break;
-        case 2: S.be.launch(S.hm.nC, RevA{S.mv, S.par, S.sv, S.rv, S.av, S.dX.p}); break;
-        case 3: S.be.launch(S.hm.nC, RevB{S.mv, S.par, S.sv, S.rv, S.av, S.dX.p, S.dY2.p}); break;
-        case 4: S.be.launch(S.hm.nC, RevC{S.mv, S.par, S.sv, S.rv, S.av, S.dX.p, S.dY2.p}); break;
+        case 2: S.be.launch(S.hm.nC, RevA{S.mv, S.par, S.sv, S.rv, S.av, S.psiView(S.dX.p)}); break;
+        case 3: S.be.launch(S.hm.nC, RevB{S.mv, S.par, S.sv, S.rv, S.av, S.psiView(S.dX.p), S.dY2.p}); break;
+        case 4: S.be.launch(S.hm.nC, RevC{S.mv, S.par, S.sv, S.rv, S.av, S.dY2.p}); break;
         default: throw Error("dab_bench_device: unknown selector");
         }
     }

@@ -356,6 +356,7 @@ struct FwdC
             }
             div += fr.s * F;
             if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0);
+            else if (fr.n >= nC) R[offPhi + f] = 0.0; // cut face whose phi belongs to the neighbouring rank
         }
         R[offP + c] = -div * (q.nrP ? 1.0 / m.V[c] : 1.0);
     }

@@ -13,6 +13,7 @@
 #pragma once
 #include "backend.hpp"
 #include "views.hpp"
+#include "comm.hpp"
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -158,7 +159,7 @@ struct IluFactorColour
                 }
             }
             double d = A.val[bi + di * si];
-            if (fabs(d) < shift * rowMax || d != d) d = (d < 0.0 ? -1.0 : 1.0) * (rowMax > 0.0 ? shift * rowMax : 1.0);
+            if (!(fabs(d) > shift * rowMax)) d = (d < 0.0 ? -1.0 : 1.0) * (rowMax > 0.0 ? shift * rowMax : 1.0);
             A.val[bi + di * si] = d;
         }
     }
@@ -315,11 +316,13 @@ __global__ void multiDotFinal(const double* __restrict__ partial, int nb, int k,
 struct VecOps
 {
     Backend* be = nullptr;
+    Comm* comm = nullptr; // dot products are summed over the ranks (the MPI_Allreduce of the reference's KSP)
     DevBuf<double> partial, dOut;
     std::vector<double> hOut;
-    void init(Backend& b, int maxK)
+    void init(Backend& b, Comm* c, int maxK)
     {
         be = &b;
+        comm = c;
 #ifndef DAB_HOSTSIM
         partial.alloc(b, (size_t)DOT_BLOCKS * (maxK + 2));
 #endif
@@ -333,6 +336,7 @@ struct VecOps
         multiDotPartial<<<DOT_BLOCKS, DOT_THREADS, 0, be->stream>>>(V, ld, k, w, n, partial.p);
         multiDotFinal<<<(k + 63) / 64, 64, 0, be->stream>>>(partial.p, DOT_BLOCKS, k, dOut.p);
         be->launches += 2;
+        if (comm) comm->allreduceSum(*be, dOut.p, k);
         be->d2h(hOut.data(), dOut.p, (size_t)k * sizeof(double));
 #else
         for (int j = 0; j < k; j++)
@@ -342,6 +346,12 @@ struct VecOps
             hOut[j] = s;
         }
         be->launches += 2;
+        if (comm && comm->active())
+        {
+            be->h2d(dOut.p, hOut.data(), (size_t)k * sizeof(double));
+            comm->allreduceSum(*be, dOut.p, k);
+            be->d2h(hOut.data(), dOut.p, (size_t)k * sizeof(double));
+        }
 #endif
         return hOut.data();
     }

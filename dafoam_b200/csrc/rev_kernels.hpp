@@ -103,14 +103,13 @@ struct RevA
     StateView s;
     RecordView r;
     AdjView a;
-    const double* x;
+    PsiView x;
     DAB_HD void operator()(int c) const
     {
         const int nT = m.nCtot, nC = m.nC;
-        const size_t offP = (size_t)3 * nC, offPhi = (size_t)(q.turb ? 5 : 4) * nC;
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
         const double V = m.V[c];
-        const double psiPc = x[offP + c] * (q.nrP ? 1.0 / V : 1.0);
+        const double psiPc = x.p[c] * (q.nrP ? 1.0 / V : 1.0);
         double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
         for (int k = 0; k < m.maxCF; k++)
         {
@@ -123,9 +122,9 @@ struct RevA
             if (!fr.bnd)
             {
                 const int n = fr.n;
-                const double psiPn = x[offP + n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
+                const double psiPn = x.p[n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
                 // F_f enters pRes_own with -1, pRes_nei with +1, phiRes_f with +1
-                const double Fb = cphi * x[offPhi + f] - fr.s * (psiPc - psiPn);
+                const double Fb = cphi * x.phi[f] - fr.s * (psiPc - psiPn);
                 const double w = m.w[f];
                 const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
                 const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
@@ -145,7 +144,7 @@ struct RevA
             {
                 const int b = f - m.nIF, pa = m.bPatch[b];
                 const double phib = s.phi[f];
-                const double Fb = cphi * x[offPhi + f] - psiPc;
+                const double Fb = cphi * x.phi[f] - psiPc;
                 const int kU = q.bcKind[F_U][pa];
                 const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
                 if (q.constrainHbyA && !assignable)
@@ -173,7 +172,7 @@ struct RevA
         for (int j = 0; j < 3; j++)
         {
             const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) / rAU;
-            const double psiU = cU * x[3 * c + j];
+            const double psiU = cU * x.U[3 * c + j];
             const double Mb = psiU - rAU * HbA[j];
             rAUtot -= M * HbA[j];
             const double mt = Mb / V;
@@ -193,12 +192,12 @@ struct RevB
     StateView s;
     RecordView r;
     AdjView a;
-    const double* x;
+    PsiView x;
     double* y;
     DAB_HD void operator()(int c) const
     {
         const int nT = m.nCtot, nC = m.nC;
-        const size_t offN = (size_t)4 * nC, offPhi = (size_t)(q.turb ? 5 : 4) * nC;
+        const size_t offPhi = (size_t)(q.turb ? 5 : 4) * nC;
         const int schU = q.divU, schN = q.divNut;
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
         const double nuEc = r.nut[c] + q.nu;
@@ -216,7 +215,7 @@ struct RevB
         const double D1c = flc != 0.0 ? flc * D2c : 0.0;
         const double soc = flc != 0.0 ? 0.0 : D2c;
         const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
-        const double psiN = q.turb ? x[offN + c] : 0.0;
+        const double psiN = q.turb ? x.nt[c] : 0.0;
         const double qc = psiN * (q.nrNut ? 1.0 / V : 1.0); // adjoint of NV
         const double zc = psiN * (q.nrNut ? 1.0 : V);       // adjoint of the cell-local SA sources
 
@@ -314,7 +313,7 @@ struct RevB
                 if (q.turb)
                 {
                     const double ntn = s.nt[n];
-                    const double qn = x[offN + n] * (q.nrNut ? 1.0 / m.V[n] : 1.0);
+                    const double qn = x.nt[n] * (q.nrNut ? 1.0 / m.V[n] : 1.0);
                     const double wpc = schN == DIV_LINEAR ? wc : wupc;
                     const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
                     const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
@@ -419,7 +418,9 @@ struct RevB
                 phib_acc += mb;
             }
             if (fr.s > 0)
-                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x[offPhi + f]) * q.sPhi * mS;
+                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x.phi[f]) * q.sPhi * mS;
+            else if (fr.n >= nC)
+                y[offPhi + f] = 0.0; // cut face whose phi belongs to the neighbouring rank
         }
         if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb);
         for (int j = 0; j < 3; j++) a.U2[(size_t)j * nC + c] = U2[j];
@@ -437,7 +438,6 @@ struct RevC
     StateView s;
     RecordView r;
     AdjView a;
-    const double* x;
     double* y;
     int functionMode = 0;
     DAB_HD void operator()(int c) const
@@ -512,7 +512,7 @@ struct RevC
             {
                 const FaceRef fr = faceOf(m, c, k);
                 if (fr.f < 0) break;
-                if (fr.s > 0) y[offPhi + fr.f] = 0.0;
+                if (fr.s > 0 || fr.n >= nC) y[offPhi + fr.f] = 0.0;
             }
         }
     }

@@ -14,6 +14,8 @@
 #include "fwd_kernels.hpp"
 #include "rev_kernels.hpp"
 #include "krylov.hpp"
+#include "partition.hpp"
+#include "comm.hpp"
 #include <map>
 #include <set>
 
@@ -68,25 +70,46 @@ struct Solver
     DevBuf<double> dR, dX, dY2; // residual / product scratch in external layout
     bool recorded = false;
     Krylov kry;
+    // domain decomposition (one rank per GPU)
+    Comm comm;
+    Halo halo;
+    Partition part;
+    DevBuf<double> psiP, psiN, psiPhi; // working copies of the input vector with ghost slots (multi-rank only)
 
     int nDof() const { return (par.turb ? 5 : 4) * hm.nC + hm.nF; }
 
     // ------------------------------------------------------------------------------------------
     void create(const std::string& caseDir, const std::string& argsAll, const std::string& optionsJson, int device, int rank_,
-                int nRanks_)
+                int nRanks_, const void* ncclUid)
     {
         rank = rank_;
         nRanks = nRanks_;
-        if (nRanks != 1) throw Error("multi-rank creation goes through Solver::createPartitioned");
         {
             auto t = tokenize(argsAll);
             solverName = t.empty() ? "DASimpleFoam" : t[0];
         }
         if (solverName != "DASimpleFoam") throw Error("solver " + solverName + " is not supported (DASimpleFoam only in this build)");
         be.init(device);
-        hm.read(caseDir);
-        hm.computeGeometry();
-        hm.computeWallDistance();
+        if (nRanks == 1)
+        {
+            hm.read(caseDir);
+            hm.computeGeometry();
+            hm.computeWallDistance();
+            part.nGlobalCells = hm.nC;
+        }
+        else
+        {
+            // every rank reads the whole case, partitions it identically (RCB) and keeps its own sub-mesh
+            HostMesh g;
+            g.read(caseDir);
+            g.computeGeometry();
+            g.computeWallDistance();
+            std::vector<int> cellPart;
+            rcbPartition(g, nRanks, cellPart);
+            extractLocalMesh(g, cellPart, rank, nRanks, hm, part);
+            comm.initNccl(be, rank, nRanks, ncclUid);
+            halo.build(be, comm, part.halo);
+        }
         if ((int)hm.patches.size() > MAXP) throw Error("too many patches");
         readCase(caseDir);
         applyOptions(optionsJson, true);
@@ -283,12 +306,13 @@ struct Solver
         auto internal = [&](const std::string& name, int nc, std::vector<double>& out) {
             const Dict& d = fieldDicts.at(name);
             const auto& t = d.tokens("internalField");
-            out.assign((size_t)nc * nC, 0.0);
+            const int nT = hm.nCtot;
+            out.assign((size_t)nc * nT, 0.0);
             if (t.at(0) == "uniform")
             {
                 double v[3] = {0, 0, 0};
                 d.uniform("internalField", v);
-                for (int c = 0; c < nC; c++)
+                for (int c = 0; c < nT; c++)
                     for (int k = 0; k < nc; k++) out[(size_t)nc * c + k] = v[k];
             }
             else
@@ -302,8 +326,12 @@ struct Solver
                     if (t[i] == "(" || t[i] == ")") continue;
                     vals.push_back(atof(t[i].c_str()));
                 }
-                if (vals.size() < (size_t)nc * nC) throw Error("internalField of " + name + " has the wrong size");
-                for (size_t j = 0; j < (size_t)nc * nC; j++) out[j] = vals[j];
+                if (vals.size() < (size_t)nc * part.nGlobalCells) throw Error("internalField of " + name + " has the wrong size");
+                for (int c = 0; c < nT; c++)
+                {
+                    const size_t gc = nRanks > 1 ? (size_t)part.cellGlobal[c] : (size_t)c;
+                    for (int k = 0; k < nc; k++) out[(size_t)nc * c + k] = vals[(size_t)nc * gc + k];
+                }
             }
         };
         std::vector<double> U, p, nt;
@@ -351,19 +379,39 @@ struct Solver
             off += nC;
         }
         be.d2d(dPhi.p, dWext.p + off, (size_t)hm.nF * sizeof(double));
+        exchangeStates();
         recorded = false;
         kry.pcValid = false;
+    }
+
+    // ghost cells <- owners (U, p, nuTilda) and foreign cut faces <- owners (phi)
+    void exchangeStates()
+    {
+        if (!comm.active()) return;
+        const int nT = hm.nCtot;
+        std::vector<HaloItem> it{{dU.p, 3, 3, 1}, {dP.p, 1, 1, nT}};
+        if (par.turb) it.push_back({dNt.p, 1, 1, nT});
+        halo.exchangeCells(it);
+        halo.exchangeFaces({{dPhi.p, 1, 1, hm.nF}});
     }
 
     void getOFFields(double* W) { be.d2h(W, dWext.p, (size_t)nDof() * sizeof(double)); }
 
     // forward passes; record(isPC=0) leaves the intermediates the reverse sweep reuses
-    void forward(int isPC, double* Rdev)
+    void forward(int isPC, double* Rdev, bool exchange = true)
     {
+        const int nT = hm.nCtot;
         FwdA a{mv, par, sv, rv};
         be.launch(hm.nCtot, a);
+        if (exchange && comm.active())
+        {
+            std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};
+            if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
+            halo.exchangeCells(it);
+        }
         FwdB b{mv, par, sv, rv, isPC, Rdev};
         be.launch(hm.nC, b);
+        if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
         FwdC c{mv, par, sv, rv, Rdev};
         be.launch(hm.nC, c);
     }
@@ -383,14 +431,58 @@ struct Solver
     }
 
     // y = diag(n) (dR/dW)^T x on device vectors (external layout)
+    PsiView psiView(const double* x)
+    {
+        const size_t nC = hm.nC;
+        PsiView v;
+        v.U = x;
+        if (!comm.active())
+        {
+            v.p = x + 3 * nC;
+            v.nt = x + 4 * nC;
+            v.phi = x + (par.turb ? 5 : 4) * nC;
+            return v;
+        }
+        const int nT = hm.nCtot;
+        if (psiP.n < (size_t)nT)
+        {
+            psiP.alloc(be, nT);
+            psiN.alloc(be, nT);
+            psiPhi.alloc(be, hm.nF);
+        }
+        be.d2d(psiP.p, x + 3 * nC, nC * sizeof(double));
+        std::vector<HaloItem> it{{psiP.p, 1, 1, nT}};
+        if (par.turb)
+        {
+            be.d2d(psiN.p, x + 4 * nC, nC * sizeof(double));
+            it.push_back({psiN.p, 1, 1, nT});
+        }
+        be.d2d(psiPhi.p, x + (par.turb ? 5 : 4) * nC, (size_t)hm.nF * sizeof(double));
+        halo.exchangeCells(it);
+        halo.exchangeFaces({{psiPhi.p, 1, 1, hm.nF}});
+        v.p = psiP.p;
+        v.nt = psiN.p;
+        v.phi = psiPhi.p;
+        return v;
+    }
+
     void matVecDev(const double* x, double* y)
     {
         ensureRecorded();
-        RevA ra{mv, par, sv, rv, av, x};
+        const int nT = hm.nCtot;
+        const PsiView pv = psiView(x);
+        RevA ra{mv, par, sv, rv, av, pv};
         be.launch(hm.nC, ra);
-        RevB rb{mv, par, sv, rv, av, x, y};
+        if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nT}, {av.Dn, 1, 1, nT}, {av.gPb, 3, 1, nT}});
+        RevB rb{mv, par, sv, rv, av, pv, y};
         be.launch(hm.nC, rb);
-        RevC rc{mv, par, sv, rv, av, x, y};
+        if (comm.active())
+        {
+            std::vector<HaloItem> it{{av.gUb, 9, 1, nT}};
+            if (par.turb) it.push_back({av.gNtb, 3, 1, nT});
+            halo.exchangeCells(it);
+        }
+        RevC rc{mv, par, sv, rv, av, y};
         be.launch(hm.nC, rc);
     }
 
@@ -425,14 +517,20 @@ struct Solver
     {
         const FunctionDef& f = findFunction(name);
         ensureRecorded();
-        if (dFacePart.n < (size_t)hm.nBF) dFacePart.alloc(be, hm.nBF);
+        if (dFacePart.n < (size_t)hm.nBF + 1) dFacePart.alloc(be, hm.nBF + 1);
         ForceFwd k{mv, par, sv, rv, forceSpec(f), dFacePart.p};
         be.launch(hm.nBF, k);
-        std::vector<double> part(hm.nBF);
-        be.d2h(part.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
+        std::vector<double> facePart(hm.nBF);
+        be.d2h(facePart.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
         // deterministic host summation in face order (the all-reduce of the reference, DAFunctionForce.C:146)
         double s = 0.0;
-        for (int b = 0; b < hm.nBF; b++) s += part[b];
+        for (int b = 0; b < hm.nBF; b++) s += facePart[b];
+        if (comm.active())
+        {
+            be.h2d(dFacePart.p, &s, sizeof(double));
+            comm.allreduceSum(be, dFacePart.p, 1);
+            be.d2h(&s, dFacePart.p, sizeof(double));
+        }
         return s;
     }
 
@@ -446,8 +544,12 @@ struct Solver
         be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
         ForceRevA ka{mv, par, sv, rv, av, forceSpec(f), seed};
         be.launch(hm.nC, ka);
-        be.zero(dX.p, (size_t)nDof() * sizeof(double)); // zero residual seed for the shared gradient-adjoint stage
-        RevC rc{mv, par, sv, rv, av, dX.p, dY2.p};
+        if (comm.active())
+        {
+            std::vector<HaloItem> it{{av.gUb, 9, 1, hm.nCtot}};
+            halo.exchangeCells(it);
+        }
+        RevC rc{mv, par, sv, rv, av, dY2.p};
         rc.functionMode = 1;
         be.launch(hm.nC, rc);
         be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));

@@ -23,6 +23,7 @@ struct CellGraph
         off.assign(nC + 1, 0);
         for (int f = 0; f < m.nIF; f++)
         {
+            if (m.own[f] >= nC || m.nei[f] >= nC) continue; // cut face: the other cell is a ghost (block-Jacobi over ranks)
             off[m.own[f] + 1]++;
             off[m.nei[f] + 1]++;
         }
@@ -31,6 +32,7 @@ struct CellGraph
         std::vector<int> pos(off.begin(), off.end() - 1);
         for (int f = 0; f < m.nIF; f++)
         {
+            if (m.own[f] >= nC || m.nei[f] >= nC) continue;
             adj[pos[m.own[f]]++] = m.nei[f];
             adj[pos[m.nei[f]]++] = m.own[f];
         }
@@ -107,12 +109,14 @@ inline void Solver::pcSymbolic()
     G.build(hm);
     const int Lcc = pcConLevel, Lfc = 0, Lcf = 0;
     // owned faces per cell (a face belongs to the block of its owner cell)
+    // (a cut face whose owner is a ghost sits in the block of its local cell; its row is a trivial identity row)
+    auto blockCell = [&](int f) { return hm.own[f] < nC ? hm.own[f] : hm.nei[f]; };
     std::vector<int> ofOff(nC + 1, 0), ofList(nF);
-    for (int f = 0; f < nF; f++) ofOff[hm.own[f] + 1]++;
+    for (int f = 0; f < nF; f++) ofOff[blockCell(f) + 1]++;
     for (int c = 0; c < nC; c++) ofOff[c + 1] += ofOff[c];
     {
         std::vector<int> pos(ofOff.begin(), ofOff.end() - 1);
-        for (int f = 0; f < nF; f++) ofList[pos[hm.own[f]]++] = f;
+        for (int f = 0; f < nF; f++) ofList[pos[blockCell(f)]++] = f;
     }
     // all faces of a cell from the ELL table
     auto facesOf = [&](int c, std::vector<int>& out) {
@@ -195,10 +199,22 @@ inline void Solver::pcSymbolic()
         for (int f : faces) cols.push_back(K.iperm[offPhi + f]);
         std::sort(cols.begin(), cols.end());
     };
+    auto faceSeeds = [&](int f, int* seeds) {
+        int ns_ = 0;
+        if (hm.own[f] < nC) seeds[ns_++] = hm.own[f];
+        if (f < nIF && hm.nei[f] < nC) seeds[ns_++] = hm.nei[f];
+        return ns_;
+    };
     auto faceRowCols = [&](int f) {
         cols.clear();
-        int seeds[2] = {hm.own[f], f < nIF ? hm.nei[f] : hm.own[f]};
-        G.ball(seeds, f < nIF ? 2 : 1, Lcf, cellsBall);
+        if (hm.own[f] >= nC)
+        {
+            cols.push_back(K.iperm[offPhi + f]); // phi of this cut face belongs to the neighbouring rank
+            return;
+        }
+        int seeds[2];
+        const int nSeeds = faceSeeds(f, seeds);
+        G.ball(seeds, nSeeds, Lcf, cellsBall);
         for (int x : cellsBall)
         {
             for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
@@ -266,8 +282,9 @@ inline void Solver::pcSymbolic()
     std::vector<int> fdFace;
     std::vector<int> tmpCells;
     const int nFdFace = detail::greedyColour(nF, [&](int f, std::vector<int>& out) {
-        int seeds[2] = {hm.own[f], f < nIF ? hm.nei[f] : hm.own[f]};
-        G.ball(seeds, f < nIF ? 2 : 1, Lcf + 1, tmpCells);
+        int seeds[2];
+        const int nSeeds = faceSeeds(f, seeds);
+        G.ball(seeds, nSeeds, Lcf + 1, tmpCells);
         out.clear();
         for (int x : tmpCells) facesOf(x, out);
     }, fdFace);
@@ -315,7 +332,7 @@ inline void Solver::calcPC()
     be.zero(K.dVal.p, (size_t)K.ellSize * sizeof(double));
     StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi};
     // R0 at the unperturbed state with the div(pc) schemes (DASolver::calcdRdWT isPC=1)
-    forward(1, K.R0.p);
+    forward(1, K.R0.p, true);
     const int nFd = (int)K.fdStart.size() - 1;
     EllView A = K.view();
     for (int k = 0; k < nFd; k++)
@@ -324,7 +341,7 @@ inline void Solver::calcPC()
         if (n == 0) continue;
         const int32_t* list = K.dFdList.p + K.fdStart[k];
         be.launch(n, FdPerturb{sp, list, fdStep});
-        forward(1, K.R1.p);
+        forward(1, K.R1.p, false); // ghosts frozen: block-Jacobi over ranks, no collective inside the loop
         be.launch(n, FdFill{A, list, K.dIPerm.p, K.dPerm.p, K.R0.p, K.R1.p, 1.0 / fdStep});
         be.launch(n, FdPerturb{sp, list, -fdStep});
     }
@@ -377,7 +394,7 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
         K.xdev.alloc(be, n);
         K.bdev.alloc(be, n);
         K.hdev.alloc(be, m + 2);
-        K.ops.init(be, m + 2);
+        K.ops.init(be, &comm, m + 2);
     }
     be.h2d(K.bdev.p, rhs, (size_t)n * sizeof(double));
     be.zero(K.xdev.p, (size_t)n * sizeof(double));

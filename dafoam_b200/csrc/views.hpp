@@ -48,6 +48,16 @@ struct StateView
     const double* phi; // [nF]
 };
 
+// the input vector of a transpose product, field by field; on one GPU the pointers alias the caller's
+// vector (reference layout), on several GPUs p/nt/phi point at working copies with ghost slots
+struct PsiView
+{
+    const double* U;   // [3*nC]   adjoint of URes (own cell only)
+    const double* p;   // [nCtot]  adjoint of pRes
+    const double* nt;  // [nCtot]  adjoint of nuTildaRes
+    const double* phi; // [nF]     adjoint of phiRes
+};
+
 // forward intermediates recorded once per state (the role of the reference's AD tape)
 struct RecordView
 {

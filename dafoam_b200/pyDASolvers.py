@@ -56,6 +56,41 @@ def _check_array(a, n, what):
     assert len(a) == n, "invalid %s array size!" % what
 
 
+EXCHANGE_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int),
+                          C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_int))
+ALLREDUCE_CB = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_double), C.c_int)
+_CB_KEEP = []
+
+
+def nccl_unique_id(lib_path=None):
+    """128-byte NCCL unique id (rank 0 creates it, the caller broadcasts it, every rank passes it to pyDASolvers)."""
+    L = load_library(lib_path)
+    buf = C.create_string_buffer(128)
+    if L.dab_nccl_unique_id(buf) != 0:
+        raise DAB200Error(L.dab_last_error().decode())
+    return buf.raw
+
+
+def set_comm_callbacks(exchange, allreduce, lib_path):
+    """TEST BUILD ONLY: route halo exchanges / all-reduces of the next solver through Python callables
+    exchange(peers, send_arrays, recv_arrays) and allreduce(array) (numpy views of the library's buffers)."""
+    L = load_library(lib_path)
+
+    def _ex(ctx, n, peers, sb, sc, rb, rc):
+        ps = [peers[i] for i in range(n)]
+        sends = [np.ctypeslib.as_array(sb[i], shape=(sc[i],)) if sc[i] > 0 else np.zeros(0) for i in range(n)]
+        recvs = [np.ctypeslib.as_array(rb[i], shape=(rc[i],)) if rc[i] > 0 else np.zeros(0) for i in range(n)]
+        exchange(ps, sends, recvs)
+
+    def _ar(ctx, buf, n):
+        allreduce(np.ctypeslib.as_array(buf, shape=(n,)))
+
+    cbs = (EXCHANGE_CB(_ex), ALLREDUCE_CB(_ar))
+    _CB_KEEP.append(cbs)
+    if L.dab_set_comm_callbacks(cbs[0], cbs[1], None) != 0:
+        raise DAB200Error(L.dab_last_error().decode())
+
+
 class Mat:
     """Stand-in for the PETSc Mat handle of the reference's calcdRdWT(isPC, dRdWT)."""
 
@@ -125,6 +160,25 @@ class pyDASolvers:
 
     def getNLocalInternalFaces(self):
         return self._geti(self._L.dab_n_local_internal_faces)
+
+    def getLocalToGlobal(self, what):
+        """what: "cells" -> global cell ids, "faces" -> global face ids, "faceOwned" -> 0/1 ownership of the phi DOF."""
+        code = {"cells": 0, "faces": 1, "faceOwned": 2}[what]
+        n = self.getNLocalCells() if code == 0 else self.getNLocalFaces()
+        out = np.zeros(n, dtype=np.int64)
+        self._raise(self._L.dab_get_local_to_global(self._h, C.c_int(code), out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def localStateIndex(self, nGlobalCells, nGlobalFaces, turbulent=True):
+        """Indices into the global state vector (reference ordering) of this rank's local state vector."""
+        cg = self.getLocalToGlobal("cells")
+        fg = self.getLocalToGlobal("faces")
+        ns = 5 if turbulent else 4
+        parts = [(3 * cg[:, None] + np.arange(3)[None, :]).ravel(), 3 * nGlobalCells + cg]
+        if turbulent:
+            parts.append(4 * nGlobalCells + cg)
+        parts.append(ns * nGlobalCells + fg)
+        return np.concatenate(parts)
 
     def updateDAOption(self, pyOptions):
         self._options.update(pyOptions)

@@ -68,6 +68,19 @@ int dab_destroy(dab_solver* s);
 /* 128-byte NCCL unique id for multi-rank creation (rank 0 calls it, the host broadcasts it) */
 int dab_nccl_unique_id(void* out128);
 
+/* local -> global maps of a partitioned case: what = 0 cells [nLocalCells], 1 faces [nLocalFaces],
+ * 2 face ownership flags [nLocalFaces] (0: the phi DOF of this cut face lives on the neighbouring rank and the
+ * local slot is a structural zero).  Replaces reading processorN/polyMesh/{cell,face}ProcAddressing. */
+int dab_get_local_to_global(dab_solver* s, int what, int64_t* out);
+
+/* TEST BUILD ONLY: halo-exchange / all-reduce callbacks used by the next dab_create instead of NCCL
+ * (the product build returns an error).  exchange(ctx, nPeers, peers, sendBufs, sendCounts, recvBufs, recvCounts);
+ * allreduce(ctx, buf, n) sums n doubles over the ranks in place. */
+typedef void (*dab_exchange_cb)(void* ctx, int n_peers, const int* peers, const double* const* send_bufs, const int* send_counts,
+                                double* const* recv_bufs, const int* recv_counts);
+typedef void (*dab_allreduce_cb)(void* ctx, double* buf, int n);
+int dab_set_comm_callbacks(dab_exchange_cb exchange, dab_allreduce_cb allreduce, void* ctx);
+
 /* getNLocalAdjointStates / getNLocalCells / getNGlobalCells / getNLocalPoints (pyDASolvers.pyx) */
 int dab_n_local_adjoint_states(dab_solver* s, int64_t* out);
 int dab_n_local_cells(dab_solver* s, int64_t* out);

@@ -1,0 +1,114 @@
+"""Worker of the world_size-2 gloo test (launched by tests/test_multirank.py through torch.distributed.run).
+The test-only host build of the engine runs the kernels; torch.distributed/gloo carries the ghost-cell
+exchanges and the GMRES all-reduces through the library's communication callbacks."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from dafoam_b200 import cases  # noqa: E402
+from dafoam_b200.pyDASolvers import KSP, Mat, pyDASolvers, set_comm_callbacks  # noqa: E402
+from tests.common import HOSTSIM, NORM_STATES  # noqa: E402
+
+
+def main():
+    case_dir, kind = sys.argv[1], sys.argv[2]
+    cuda = len(sys.argv) > 3 and sys.argv[3] == "cuda"
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lib = None if cuda else HOSTSIM
+
+    def exchange(peers, sends, recvs):
+        reqs = []
+        for p, s, r in zip(peers, sends, recvs):
+            if r.size:
+                reqs.append(dist.irecv(torch.from_numpy(r), src=p))
+            if s.size:
+                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(s)), dst=p))
+        for q in reqs:
+            q.wait()
+
+    def allreduce(a):
+        dist.all_reduce(torch.from_numpy(a))
+
+    mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2) if kind == "naca" else cases.channel(nx=12, ny=8, nz=2)
+    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing" if kind == "naca" else "walls"],
+                 "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
+    opts = dict(normalizeStates=NORM_STATES, function=fn, adjEqnOption=dict(gmresRelTol=1e-10, gmresMaxIters=500, gmresRestart=250))
+    uid = None
+    if cuda:
+        # product path: NCCL over NVLink; gloo only broadcasts the unique id
+        from dafoam_b200.pyDASolvers import nccl_unique_id
+        box = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    else:
+        set_comm_callbacks(exchange, allreduce, HOSTSIM)
+    dev = rank if cuda else 0
+    serial = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=dev, _lib_path=lib)
+    par = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=dev, rank=rank, nRanks=world, ncclUniqueId=uid, _lib_path=lib)
+    nCg, nFg = mesh.n_cells, mesh.n_faces
+    assert par.getNGlobalCells() == nCg and serial.getNLocalCells() == nCg
+    idx = par.localStateIndex(nCg, nFg)
+    owned = np.concatenate([np.ones(5 * par.getNLocalCells(), dtype=bool), par.getLocalToGlobal("faceOwned").astype(bool)])
+    n_cells_total = torch.tensor([par.getNLocalCells()])
+    dist.all_reduce(n_cells_total)
+    assert int(n_cells_total) == nCg
+
+    y = np.zeros(nCg)
+    serial.getOFField("yWall", "scalar", y)
+    Wg = cases.boundary_layer_state(mesh, y, noise=0.01) if kind == "naca" else None
+    if Wg is None:
+        Wg = np.zeros(serial.getNLocalAdjointStates())
+        serial.getOFFields(Wg)
+        Wg *= 1.0 + 0.01 * np.random.default_rng(1).uniform(-1, 1, Wg.size)
+    serial.updateOFFields(Wg)
+    par.updateOFFields(np.ascontiguousarray(Wg[idx]))
+
+    def check(name, loc, glob, tol):
+        err = np.abs(loc[owned] - glob[idx][owned]).max() / max(np.abs(glob).max(), 1e-300)
+        assert np.all(loc[~owned] == 0.0), name + ": foreign slots must be structural zeros"
+        assert err < tol, (name, err)
+        return err
+
+    Rg, Rl = np.zeros(Wg.size), np.zeros(idx.size)
+    serial.getResiduals(Rg)
+    par.getResiduals(Rl)
+    e1 = check("residual", Rl, Rg, 1e-12)
+    psi = np.random.default_rng(4321).uniform(-1, 1, Wg.size)
+    yg, yl = np.zeros(Wg.size), np.zeros(idx.size)
+    serial.calcdRdWTPsiAD(psi, yg)
+    pl = np.ascontiguousarray(psi[idx])
+    pl[~owned] = 0.0
+    par.calcdRdWTPsiAD(pl, yl)
+    e2 = check("dRdWTPsi", yl, yg, 1e-12)
+    Fs, Fp = serial.calcFunction("CD"), par.calcFunction("CD")
+    assert abs(Fs - Fp) <= 1e-12 * abs(Fs)
+    dg, dl = np.zeros(Wg.size), np.zeros(idx.size)
+    serial.calcJacTVecProduct("s", "stateVar", Wg, "CD", "function", np.array([1.0]), dg)
+    par.calcJacTVecProduct("s", "stateVar", np.ascontiguousarray(Wg[idx]), "CD", "function", np.array([1.0]), dl)
+    e3 = check("dFdW", dl, dg, 1e-12)
+    # adjoint solve: block-Jacobi ILU over the two ranks, GMRES dot products all-reduced
+    ks, kp = KSP(), KSP()
+    ms, mp_ = Mat(), Mat()
+    serial.calcdRdWT(1, ms)
+    par.calcdRdWT(1, mp_)
+    xs, xp = np.zeros(Wg.size), np.zeros(idx.size)
+    fs = serial.solveLinearEqn(ks, dg, xs)
+    fp = par.solveLinearEqn(kp, dl, xp)
+    assert fs == 0 and fp == 0, (fs, fp, ks.stats.iterations, kp.stats.iterations)
+    e4 = np.linalg.norm(xp[owned] - xs[idx][owned]) / np.linalg.norm(xs)
+    assert e4 < 1e-6, e4
+    print("rank %d ok: residual %.1e dRdWTPsi %.1e dFdW %.1e psi %.1e (its serial %d, 2 ranks %d)"
+          % (rank, e1, e2, e3, e4, ks.stats.iterations, kp.stats.iterations), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

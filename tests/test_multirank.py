@@ -1,0 +1,47 @@
+"""world_size-2 domain-decomposed run on CPUs (gloo): partitioner, ghost-cell exchange plan, de-duplicated
+cut-face DOFs and the all-reduced GMRES, checked against the single-rank engine on the same case."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+from dafoam_b200 import cases
+from tests.common import ROOT
+
+
+def _run(kind, extra, port):
+    d = tempfile.mkdtemp(prefix="dab_mp_")
+    if kind == "naca":
+        cases.write_case(d, cases.naca0012_ogrid(ni=32, nj=16, nk=2), cases.default_bcs_naca())
+    else:
+        cases.write_case(d, cases.channel(nx=12, ny=8, nz=2), cases.default_bcs_channel())
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), d, kind] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2, r.stdout
+
+
+@pytest.mark.gpu
+def test_two_gpus_match_one_gpu_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run("naca", ["cuda"], 29735)
+
+
+@pytest.mark.parametrize("kind", ["naca", "channel"])
+def test_two_ranks_match_one_rank(kind):
+    d = tempfile.mkdtemp(prefix="dab_mp_")
+    if kind == "naca":
+        cases.write_case(d, cases.naca0012_ogrid(ni=32, nj=16, nk=2), cases.default_bcs_naca())
+    else:
+        cases.write_case(d, cases.channel(nx=12, ny=8, nz=2), cases.default_bcs_channel())
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29731" if kind == "naca" else "29733", os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2, r.stdout
