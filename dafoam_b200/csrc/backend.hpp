@@ -28,7 +28,7 @@ namespace dab
 template <class F>
 struct LaunchTraits
 {
-    static constexpr int minBlocks = 1;
+    static constexpr int minBlocks = 4; // <= 128 registers per thread unless a functor says otherwise
 };
 
 template <class F>

@@ -345,9 +345,9 @@ int dab_bench_device(dab_solver* s, int which, int n, double* ms_per_call, int64
         {
         case 0: S.matVecDev(S.dX.p, S.dY2.p); break;
         case 1: S.forward(0, S.dR.p); break;
-        case 2: S.be.launch(S.hm.nC, RevA{S.mv, S.par, S.sv, S.rv, S.av, S.psiView(S.dX.p)}); break;
-        case 3: S.be.launch(S.hm.nC, RevB{S.mv, S.par, S.sv, S.rv, S.av, S.psiView(S.dX.p), S.dY2.p}); break;
-        case 4: S.be.launch(S.hm.nC, RevC{S.mv, S.par, S.sv, S.rv, S.av, S.dY2.p}); break;
+        case 2: S.benchKernel(0); break;
+        case 3: S.benchKernel(1); break;
+        case 4: S.benchKernel(2); break;
         default: throw Error("dab_bench_device: unknown selector");
         }
     }

@@ -18,6 +18,7 @@
 namespace dab
 {
 
+template <int NF>
 struct FwdA
 {
     MeshView m;
@@ -36,7 +37,7 @@ struct FwdA
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
         const double pc = s.p[c];
         const double ntc = q.turb ? s.nt[c] : 0.0;
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;
@@ -104,6 +105,7 @@ DAB_HD double saSource(double nt, double nu, double y, const double* gU, const d
     return -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * nt + SA::Cw1 * fw * nt * nt / (y * y);
 }
 
+template <int NF>
 struct FwdB
 {
     MeshView m;
@@ -129,7 +131,7 @@ struct FwdB
         double D0 = 0.0, sumOff = 0.0, MV[3] = {0.0, 0.0, 0.0}; // MV = V*(UEqn & U)
         double icMax = 0.0, icMin = 0.0, icAvg = 0.0;
         double NV = 0.0; // V*(nuTildaEqn & nuTilda) without the cell-local sources
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;
@@ -309,6 +311,7 @@ DAB_HD double faceF(const MeshView& m, const StateView& s, const RecordView& r, 
     return ph - gam * mS * sn;
 }
 
+template <int NF>
 struct FwdC
 {
     MeshView m;
@@ -321,7 +324,7 @@ struct FwdC
         const int nT = m.nCtot, nC = m.nC;
         const size_t offP = (size_t)3 * nC, offPhi = (size_t)(q.turb ? 5 : 4) * nC;
         double div = 0.0;
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;

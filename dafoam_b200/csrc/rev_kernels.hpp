@@ -96,6 +96,7 @@ DAB_HD void boundaryGradAdj(const double* nh, const double* Gbb, double* gUb, do
     }
 }
 
+template <int NF>
 struct RevA
 {
     MeshView m;
@@ -111,7 +112,7 @@ struct RevA
         const double V = m.V[c];
         const double psiPc = x.p[c] * (q.nrP ? 1.0 / V : 1.0);
         double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;
@@ -185,6 +186,7 @@ struct RevA
     }
 };
 
+template <int NF>
 struct RevB
 {
     MeshView m;
@@ -222,7 +224,7 @@ struct RevB
         double U2[3] = {0, 0, 0}, nt2 = 0.0, nuEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
         for (int i = 0; i < 9; i++) gUb[i] = 0.0;
 
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;
@@ -431,6 +433,7 @@ struct RevB
     }
 };
 
+template <int NF>
 struct RevC
 {
     MeshView m;
@@ -439,7 +442,7 @@ struct RevC
     RecordView r;
     AdjView a;
     double* y;
-    int functionMode = 0;
+    int functionMode;
     DAB_HD void operator()(int c) const
     {
         const int nT = m.nCtot, nC = m.nC;
@@ -455,7 +458,7 @@ struct RevC
             gNbc[i] = q.turb ? a.gNtb[(size_t)i * nT + c] * iVc : 0.0;
         }
         if (q.turb) nb = a.nt2[c] + a.nutb[c] * dnut_dnt(s.nt[c], q.nu);
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;
@@ -508,7 +511,7 @@ struct RevC
         {
             // phi adjoint of a function: no face-flux dependence for the force function
             const size_t offPhi = (size_t)(q.turb ? 5 : 4) * nC;
-            for (int k = 0; k < m.maxCF; k++)
+            _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
             {
                 const FaceRef fr = faceOf(m, c, k);
                 if (fr.f < 0) break;
@@ -617,6 +620,7 @@ struct ForceFwd
 };
 
 // seeds the reverse work arrays with dF/d(cell variables); RevC then propagates through the gradients
+template <int NF>
 struct ForceRevA
 {
     MeshView m;
@@ -631,7 +635,7 @@ struct ForceRevA
         const int nT = m.nCtot, nC = m.nC;
         double Ub[3] = {0, 0, 0}, pb = 0.0, ntb = 0.0, nutPb = 0.0, gUb[9];
         for (int i = 0; i < 9; i++) gUb[i] = 0.0;
-        for (int k = 0; k < m.maxCF; k++)
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
             if (fr.f < 0) break;

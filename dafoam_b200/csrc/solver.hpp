@@ -27,11 +27,19 @@ namespace dab
 #define DAB_REVB_MINBLOCKS 3
 #endif
 #ifndef DAB_FWDB_MINBLOCKS
-#define DAB_FWDB_MINBLOCKS 1
+#define DAB_FWDB_MINBLOCKS 3
 #endif
-template <> struct LaunchTraits<RevB> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
-template <> struct LaunchTraits<FwdB> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
+template <int NF> struct LaunchTraits<RevB<NF>> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
+template <int NF> struct LaunchTraits<FwdB<NF>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 #endif
+
+// hexahedral meshes (6 faces per cell) get fully unrolled face loops; anything else the run-time loop
+#define DAB_LAUNCH_NF(n, F, ...)                                  \
+    do                                                            \
+    {                                                             \
+        if (hm.maxCF == 6) be.launch(n, F<6>{__VA_ARGS__});       \
+        else be.launch(n, F<0>{__VA_ARGS__});                     \
+    } while (0)
 
 struct FunctionDef
 {
@@ -401,19 +409,16 @@ struct Solver
     void forward(int isPC, double* Rdev, bool exchange = true)
     {
         const int nT = hm.nCtot;
-        FwdA a{mv, par, sv, rv};
-        be.launch(hm.nCtot, a);
+        DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);
         if (exchange && comm.active())
         {
             std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};
             if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
             halo.exchangeCells(it);
         }
-        FwdB b{mv, par, sv, rv, isPC, Rdev};
-        be.launch(hm.nC, b);
+        DAB_LAUNCH_NF(hm.nC, FwdB, mv, par, sv, rv, isPC, Rdev);
         if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
-        FwdC c{mv, par, sv, rv, Rdev};
-        be.launch(hm.nC, c);
+        DAB_LAUNCH_NF(hm.nC, FwdC, mv, par, sv, rv, Rdev);
     }
 
     void ensureRecorded()
@@ -471,19 +476,25 @@ struct Solver
         ensureRecorded();
         const int nT = hm.nCtot;
         const PsiView pv = psiView(x);
-        RevA ra{mv, par, sv, rv, av, pv};
-        be.launch(hm.nC, ra);
+        DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
         if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nT}, {av.Dn, 1, 1, nT}, {av.gPb, 3, 1, nT}});
-        RevB rb{mv, par, sv, rv, av, pv, y};
-        be.launch(hm.nC, rb);
+        DAB_LAUNCH_NF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
         if (comm.active())
         {
             std::vector<HaloItem> it{{av.gUb, 9, 1, nT}};
             if (par.turb) it.push_back({av.gNtb, 3, 1, nT});
             halo.exchangeCells(it);
         }
-        RevC rc{mv, par, sv, rv, av, y};
-        be.launch(hm.nC, rc);
+        DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
+    }
+
+    // one reverse kernel alone on the bench vectors (dab_bench_device selectors 2-4)
+    void benchKernel(int which)
+    {
+        const PsiView pv = psiView(dX.p);
+        if (which == 0) DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
+        else if (which == 1) DAB_LAUNCH_NF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
+        else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
     }
 
     void matVec(const double* x, double* y)
@@ -542,16 +553,13 @@ struct Solver
         be.zero(av.gUb, (size_t)9 * hm.nCtot * sizeof(double));
         be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
         be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
-        ForceRevA ka{mv, par, sv, rv, av, forceSpec(f), seed};
-        be.launch(hm.nC, ka);
+        DAB_LAUNCH_NF(hm.nC, ForceRevA, mv, par, sv, rv, av, forceSpec(f), seed);
         if (comm.active())
         {
             std::vector<HaloItem> it{{av.gUb, 9, 1, hm.nCtot}};
             halo.exchangeCells(it);
         }
-        RevC rc{mv, par, sv, rv, av, dY2.p};
-        rc.functionMode = 1;
-        be.launch(hm.nC, rc);
+        DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 1);
         be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
     }
 
