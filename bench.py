@@ -168,9 +168,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--solve-multi", action="store_true")
-    ap.add_argument("--restart", type=int, default=200)
-    ap.add_argument("--pc-level", type=int, default=2)
-    ap.add_argument("--max-iters", type=int, default=2000)
+    ap.add_argument("--restart", type=int, default=1500)
+    ap.add_argument("--pc-level", type=int, default=3)
+    ap.add_argument("--max-iters", type=int, default=3000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

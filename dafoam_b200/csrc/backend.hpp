@@ -28,7 +28,7 @@ namespace dab
 template <class F>
 struct LaunchTraits
 {
-    static constexpr int minBlocks = 4; // <= 128 registers per thread unless a functor says otherwise
+    static constexpr int minBlocks = 6; // <= 80 registers per thread unless a functor says otherwise (latency-bound gathers: occupancy wins)
 };
 
 template <class F>

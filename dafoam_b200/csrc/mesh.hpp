@@ -27,6 +27,7 @@ struct HostMesh
     std::vector<int32_t> bPatch;         // patch of boundary face b
     int maxCF = 0;
     std::vector<int32_t> cellFaces;      // ELL: [k*nC + c] = (f<<1)|isNeighbour, -1 padding
+    std::vector<int32_t> cellNbr;        // ELL: the cell across that face, -1 on boundary faces / padding
     // geometry (SoA)
     std::vector<double> Sf[3], Cf[3], corr[3]; // per face
     std::vector<double> magSf, w, delta;       // per face (w = 1 on boundary faces)
@@ -84,6 +85,18 @@ struct HostMesh
                 c = nei[f];
                 cellFaces[(size_t)cnt[c]++ * nC + c] = (f << 1) | 1;
             }
+        }
+    }
+
+    void buildCellNbr()
+    {
+        cellNbr.assign(cellFaces.size(), -1);
+        for (size_t i = 0; i < cellFaces.size(); i++)
+        {
+            const int e = cellFaces[i];
+            if (e < 0) continue;
+            const int f = e >> 1;
+            if (f < nIF) cellNbr[i] = (e & 1) ? own[f] : nei[f];
         }
     }
 

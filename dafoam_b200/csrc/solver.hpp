@@ -64,7 +64,7 @@ struct Solver
     std::vector<FunctionDef> functions;
 
     // device mesh
-    DevBuf<int32_t> dOwn, dNei, dCellFaces, dBPatch;
+    DevBuf<int32_t> dOwn, dNei, dCellFaces, dCellNbr, dBPatch;
     DevBuf<double> dS[3], dMagSf, dW, dDelta, dK[3], dCf[3], dC[3], dV, dY;
     MeshView mv;
     // state (internal working copies with ghost slots) and external-layout mirror
@@ -273,6 +273,8 @@ struct Solver
         dOwn.upload(be, hm.own);
         dNei.upload(be, hm.nei);
         dCellFaces.upload(be, hm.cellFaces);
+        hm.buildCellNbr();
+        dCellNbr.upload(be, hm.cellNbr);
         dBPatch.upload(be, hm.bPatch);
         for (int k = 0; k < 3; k++)
         {
@@ -287,7 +289,7 @@ struct Solver
         dV.upload(be, hm.V);
         dY.upload(be, hm.yWall);
         mv.nC = hm.nC; mv.nCtot = hm.nCtot; mv.nF = hm.nF; mv.nIF = hm.nIF; mv.nBF = hm.nBF; mv.maxCF = hm.maxCF;
-        mv.own = dOwn.p; mv.nei = dNei.p; mv.cellFaces = dCellFaces.p; mv.bPatch = dBPatch.p;
+        mv.own = dOwn.p; mv.nei = dNei.p; mv.cellFaces = dCellFaces.p; mv.cellNbr = dCellNbr.p; mv.bPatch = dBPatch.p;
         mv.Sx = dS[0].p; mv.Sy = dS[1].p; mv.Sz = dS[2].p; mv.magSf = dMagSf.p; mv.w = dW.p; mv.delta = dDelta.p;
         mv.kx = dK[0].p; mv.ky = dK[1].p; mv.kz = dK[2].p; mv.Cfx = dCf[0].p; mv.Cfy = dCf[1].p; mv.Cfz = dCf[2].p;
         mv.Cx = dC[0].p; mv.Cy = dC[1].p; mv.Cz = dC[2].p; mv.V = dV.p; mv.yWall = dY.p;

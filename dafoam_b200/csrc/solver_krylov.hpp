@@ -449,19 +449,28 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
             const double wn2 = d[k + 1];
             be.h2d(K.hdev.p, hcol.data(), (size_t)(k + 1) * sizeof(double));
             be.launch(n, MultiAxpy{K.V.p, n, k + 1, K.hdev.p, vk1, 0});
+            // ||w - V h||^2 = ||w||^2 - ||h||^2 (V orthonormal); refine -- and measure the norm explicitly -- only when
+            // cancellation makes that estimate unreliable (the IFNEEDED criterion of the reference's KSP)
             double hn2 = 0.0;
             for (int j = 0; j <= k; j++) hn2 += hcol[j] * hcol[j];
-            double nrm = K.ops.norm2(vk1, n);
-            (void)hn2;
-            if (nrm * nrm < 0.5 * wn2 * 0.5 || useMGSO)
+            double nrm;
+            if (wn2 - hn2 < 0.25 * wn2 || useMGSO)
             {
-                const double* d2 = K.ops.dots(K.V.p, n, k + 1, vk1, n);
+                const double* d2 = K.ops.dots(K.V.p, n, k + 2, vk1, n);
                 std::vector<double> h2(d2, d2 + k + 1);
+                const double wn2b = d2[k + 1];
                 be.h2d(K.hdev.p, h2.data(), (size_t)(k + 1) * sizeof(double));
                 be.launch(n, MultiAxpy{K.V.p, n, k + 1, K.hdev.p, vk1, 0});
-                for (int j = 0; j <= k; j++) hcol[j] += h2[j];
-                nrm = K.ops.norm2(vk1, n);
+                double h2n = 0.0;
+                for (int j = 0; j <= k; j++)
+                {
+                    hcol[j] += h2[j];
+                    h2n += h2[j] * h2[j];
+                }
+                nrm = (wn2b - h2n > 0.25 * wn2b) ? std::sqrt(wn2b - h2n) : K.ops.norm2(vk1, n);
             }
+            else
+                nrm = std::sqrt(wn2 - hn2);
             hcol[k + 1] = nrm;
             if (nrm > 0.0) be.launch(n, ScaleCopy{vk1, 1.0 / nrm, vk1});
             // Givens rotations

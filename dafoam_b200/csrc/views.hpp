@@ -23,6 +23,7 @@ struct MeshView
     const int32_t* own;       // [nF]
     const int32_t* nei;       // [nIF]
     const int32_t* cellFaces; // ELL [maxCF][nC]
+    const int32_t* cellNbr;   // ELL [maxCF][nC]: the cell across face k (-1: boundary face or padding)
     const int32_t* bPatch;    // [nBF]
     const double *Sx, *Sy, *Sz, *magSf, *w, *delta, *kx, *ky, *kz, *Cfx, *Cfy, *Cfz; // [nF]
     const double *Cx, *Cy, *Cz, *V, *yWall;                                          // [nCtot]
@@ -106,7 +107,7 @@ DAB_HD FaceRef faceOf(const MeshView& m, int c, int k)
     const int isN = e & 1;
     r.s = isN ? -1.0 : 1.0;
     r.bnd = r.f >= m.nIF;
-    r.n = r.bnd ? -1 : (isN ? m.own[r.f] : m.nei[r.f]);
+    r.n = m.cellNbr[(size_t)k * m.nC + c]; // one level of indirection less than own[]/nei[] (latency-bound gathers)
     return r;
 }
 
