@@ -187,7 +187,21 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
     (void)input_name;
     Solver& S = s->s;
     const std::string it(input_type), ot(output_type);
-    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar)");
+    if (it == "patchVelocity")
+    {
+        need(input_name, "input_name");
+        need(input, "input");
+        if (ot == "residual") S.patchVelocityProduct(input_name, input, seed, product);
+        else if (ot == "function")
+        {
+            // the force on the function's own patches does not depend on the far-field velocity for a fixed direction
+            S.setPatchVelocity(input_name, input);
+            product[0] = product[1] = 0.0;
+        }
+        else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
+        return 0;
+    }
+    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar, patchVelocity)");
     // daInput->run(inputList): assign the input to the OpenFOAM fields (DAInputStateVar.C:35-140)
     if (input) S.updateOFFields(input);
     if (ot == "residual") S.matVec(seed, product);
@@ -302,6 +316,7 @@ int dab_get_input_size(dab_solver* s, const char* name, const char* type, int64_
     need(type, "type");
     (void)name;
     if (std::string(type) == "stateVar") *out = s->s.nDof();
+    else if (std::string(type) == "patchVelocity") *out = 2;
     else throw Error(std::string("getInputSize: unsupported input type ") + type);
     DAB_CATCH
 }

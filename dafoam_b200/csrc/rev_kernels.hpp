@@ -112,6 +112,7 @@ struct RevA
         const double V = m.V[c];
         const double psiPc = x.p[c] * (q.nrP ? 1.0 / V : 1.0);
         double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
+        double refb[3] = {0, 0, 0};
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = faceOf(m, c, k);
@@ -155,6 +156,7 @@ struct RevA
                     const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
                     const double sngb[3] = {0.0, 0.0, 0.0};
                     bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
+                    if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, phib, dl, valb, sngb, refb);
                 }
                 else
                     for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * Fb;
@@ -183,6 +185,8 @@ struct RevA
         }
         a.Dn[c] = -rAU * rAU * rAUtot / V;
         a.pdir[c] = pb;
+        if (a.bcRefb)
+            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] = refb[j];
     }
 };
 
@@ -222,6 +226,7 @@ struct RevB
         const double zc = psiN * (q.nrNut ? 1.0 : V);       // adjoint of the cell-local SA sources
 
         double U2[3] = {0, 0, 0}, nt2 = 0.0, nuEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
+        double refb[3] = {0, 0, 0};
         for (int i = 0; i < 9; i++) gUb[i] = 0.0;
 
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
@@ -406,6 +411,7 @@ struct RevB
                 Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
                 boundaryGradAdj(nh, Gbb, gUb, sngb);
                 bcVectorAdj(kU, mf, dl, nh, valb, sngb, U2);
+                if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
                 // nut_b -> nut_c / nuTilda_b
                 nuEb += dP * nuEBb;
                 double ntbb = dNb * nuEBb;
@@ -426,6 +432,8 @@ struct RevB
         }
         if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb);
         for (int j = 0; j < 3; j++) a.U2[(size_t)j * nC + c] = U2[j];
+        if (a.bcRefb)
+            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += refb[j];
         a.nt2[c] = nt2;
         a.nutb[c] = nuEb;
         for (int i = 0; i < 9; i++) a.gUb[(size_t)i * nT + c] = gUb[i];
@@ -494,6 +502,12 @@ struct RevC
                 const double sngb[3] = {0.0, 0.0, 0.0};
                 for (int j = 0; j < 3; j++) valb[j] = So[0] * gUbc[j * 3 + 0] + So[1] * gUbc[j * 3 + 1] + So[2] * gUbc[j * 3 + 2];
                 bcVectorAdj(q.bcKind[F_U][pa], phib, dl, nh, valb, sngb, Ub);
+                if (a.bcRefb && ((a.bcMask >> pa) & 1u))
+                {
+                    double refb[3] = {0, 0, 0};
+                    bcVectorRefAdj(q.bcKind[F_U][pa], phib, dl, valb, sngb, refb);
+                    for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += refb[j];
+                }
                 const double frp = bcFrac(q.bcKind[F_P][pa], phib);
                 pb += (1.0 - frp) * (So[0] * gPbc[0] + So[1] * gPbc[1] + So[2] * gPbc[2]);
                 if (q.turb)

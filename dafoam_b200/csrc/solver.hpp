@@ -41,6 +41,14 @@ template <int NF> struct LaunchTraits<FwdB<NF>> { static constexpr int minBlocks
         else be.launch(n, F<0>{__VA_ARGS__});                     \
     } while (0)
 
+// DAInputPatchVelocity (reference src/adjoint/DAInput/DAInputPatchVelocity.C): input = (|U|, angle of attack in degrees)
+struct PatchVelocityDef
+{
+    std::string name;
+    std::vector<int> patches;
+    int flowAxis = 0, normalAxis = 1;
+};
+
 struct FunctionDef
 {
     std::string name, type;
@@ -62,6 +70,7 @@ struct Solver
     std::string pcType = "ilu";
     int pcConLevel = 2; // cell-to-cell connectivity level of dRdWTPC (maxResConLv4JacPCMat role)
     std::vector<FunctionDef> functions;
+    std::vector<PatchVelocityDef> patchVelocities;
 
     // device mesh
     DevBuf<int32_t> dOwn, dNei, dCellFaces, dCellNbr, dBPatch;
@@ -264,6 +273,34 @@ struct Solver
                 functions.push_back(f);
             }
         }
+        if (const JVal* ii = o.get("inputInfo"))
+        {
+            patchVelocities.clear();
+            for (const auto& kv : ii->obj)
+            {
+                if (kv.second.strOr("type", "") != "patchVelocity") continue;
+                PatchVelocityDef d;
+                d.name = kv.first;
+                auto axis = [&](const std::string& a) {
+                    if (a == "x") return 0;
+                    if (a == "y") return 1;
+                    if (a == "z") return 2;
+                    throw Error("inputInfo." + kv.first + ": axis must be x, y or z");
+                };
+                d.flowAxis = axis(kv.second.strOr("flowAxis", "x"));
+                d.normalAxis = axis(kv.second.strOr("normalAxis", "y"));
+                if (const JVal* pl = kv.second.get("patches"))
+                    for (const auto& pn : pl->arr)
+                    {
+                        int found = -1;
+                        for (size_t p = 0; p < hm.patches.size(); p++)
+                            if (hm.patches[p].name == pn.str) found = (int)p;
+                        if (found < 0) throw Error("inputInfo." + kv.first + ": unknown patch " + pn.str);
+                        d.patches.push_back(found);
+                    }
+                patchVelocities.push_back(d);
+            }
+        }
         (void)first;
         recorded = false;
     }
@@ -305,6 +342,7 @@ struct Solver
         aU2.alloc(be, 3 * nC); aNt2.alloc(be, nC);
         av.mt = aMt.p; av.Dn = aDn.p; av.Udir = aUdir.p; av.pdir = aPdir.p; av.gPb = aGPb.p; av.gUb = aGUb.p;
         av.gNtb = aGNtb.p; av.nutb = aNutb.p; av.U2 = aU2.p; av.nt2 = aNt2.p;
+        av.bcRefb = nullptr; av.bcMask = 0;
         dR.alloc(be, nd); dX.alloc(be, nd); dY2.alloc(be, nd);
     }
 
@@ -504,6 +542,61 @@ struct Solver
         be.h2d(dX.p, x, (size_t)nDof() * sizeof(double));
         matVecDev(dX.p, dY2.p);
         be.d2h(y, dY2.p, (size_t)nDof() * sizeof(double));
+    }
+
+    // ---- patchVelocity input (DAInputPatchVelocity::run + its reverse) --------------------------------
+    const PatchVelocityDef& findPatchVelocity(const std::string& name) const
+    {
+        for (const auto& d : patchVelocities)
+            if (d.name == name) return d;
+        throw Error("input " + name + " (patchVelocity) is not defined in inputInfo");
+    }
+
+    // assign (|U|, aoa[deg]) to the U boundary reference values of the patches
+    void setPatchVelocity(const std::string& name, const double* in)
+    {
+        const PatchVelocityDef& d = findPatchVelocity(name);
+        const double a = in[1] * 3.14159265358979323846 / 180.0;
+        for (int p : d.patches)
+        {
+            par.bcVal[F_U][p][d.flowAxis] = in[0] * std::cos(a);
+            par.bcVal[F_U][p][d.normalAxis] = in[0] * std::sin(a);
+        }
+        recorded = false;
+        kry.pcValid = false;
+    }
+
+    DevBuf<double> aBcRefb;
+
+    // product[2] = [dR/d(|U|, aoa)]^T psi
+    void patchVelocityProduct(const std::string& name, const double* in, const double* psi, double* product)
+    {
+        const PatchVelocityDef& d = findPatchVelocity(name);
+        setPatchVelocity(name, in);
+        const size_t nC = hm.nC;
+        if (aBcRefb.n < 3 * nC) aBcRefb.alloc(be, 3 * nC);
+        unsigned mask = 0;
+        for (int p : d.patches) mask |= 1u << p;
+        be.h2d(dX.p, psi, (size_t)nDof() * sizeof(double));
+        av.bcRefb = aBcRefb.p;
+        av.bcMask = mask;
+        matVecDev(dX.p, dY2.p);
+        av.bcRefb = nullptr;
+        av.bcMask = 0;
+        std::vector<double> part(3 * nC);
+        be.d2h(part.data(), aBcRefb.p, 3 * nC * sizeof(double));
+        double refb[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++)
+            for (size_t c = 0; c < nC; c++) refb[k] += part[k * nC + c];
+        if (comm.active())
+        {
+            be.h2d(aBcRefb.p, refb, 3 * sizeof(double));
+            comm.allreduceSum(be, aBcRefb.p, 3);
+            be.d2h(refb, aBcRefb.p, 3 * sizeof(double));
+        }
+        const double a = in[1] * 3.14159265358979323846 / 180.0;
+        product[0] = refb[d.flowAxis] * std::cos(a) + refb[d.normalAxis] * std::sin(a);
+        product[1] = (-refb[d.flowAxis] * in[0] * std::sin(a) + refb[d.normalAxis] * in[0] * std::cos(a)) * 3.14159265358979323846 / 180.0;
     }
 
     // ---- functions (DAFunctionForce) ------------------------------------------------------------

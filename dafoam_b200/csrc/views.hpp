@@ -85,6 +85,8 @@ struct AdjView
     double* nutb;  // [nC]        adjoint of nut (cell value)
     double* U2;    // [3][nC]     U adjoint from stage R2
     double* nt2;   // [nC]        nuTilda adjoint from stage R2
+    double* bcRefb; // [3][nC] or null: per-cell partial adjoint of the U boundary reference value of the patches in bcMask
+    unsigned bcMask;
 };
 
 struct FaceRef
@@ -200,6 +202,15 @@ DAB_HD void bcVectorAdj(int kind, double phib, double dl, const double* nh, cons
         const double fr = bcFrac(kind, phib);
         for (int k = 0; k < 3; k++) xPb[k] += (1.0 - fr) * valb[k] - fr * dl * sngb[k];
     }
+}
+
+// adjoint of bcVector w.r.t. the reference value (fixedValue `value` / inletOutlet `inletValue`): val = fr*ref + ...,
+// sng = fr*(ref - xP)*delta.  Used by the patchVelocity input (reference src/adjoint/DAInput/DAInputPatchVelocity.C).
+DAB_HD void bcVectorRefAdj(int kind, double phib, double dl, const double* valb, const double* sngb, double* refb)
+{
+    if (kind == BC_SYMMETRY) return;
+    const double fr = bcFrac(kind, phib);
+    for (int k = 0; k < 3; k++) refb[k] += fr * (valb[k] + dl * sngb[k]);
 }
 
 // nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP and d(nut_b)/d(nuTilda_b) in dNb

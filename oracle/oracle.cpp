@@ -237,19 +237,20 @@ struct BF
 
 // mixed form: x_b = f*ref + (1-f)*x_P (refGrad = 0 for all kinds used here)
 template <class T>
-void mixedCoeffs(BF<T>& bf, int k, int b, double fr, double ref, const T& xP, const T& delta)
+void mixedCoeffs(BF<T>& bf, int k, int b, double fr, const T& ref, const T& xP, const T& delta)
 {
     size_t i = bf.at(k, b);
     bf.val[i] = fr * ref + (1.0 - fr) * xP;
     bf.sng[i] = fr * (ref - xP) * delta;
     bf.vic[i] = T(1.0 - fr);
-    bf.vbc[i] = T(fr * ref);
+    bf.vbc[i] = fr * ref;
     bf.gic[i] = -fr * delta;
     bf.gbc[i] = fr * ref * delta;
 }
 
+// bcv: the boundary reference values as scalars of type T ([field][patch][3]) so that they can be AD inputs
 template <class T>
-void evalBC(const Topo& t, const Geom<T>& g, const BCSpec& bc, int field, int nc, const std::vector<T>& x /*nc*nC*/,
+void evalBC(const Topo& t, const Geom<T>& g, const BCSpec& bc, const std::vector<T>& bcv, int field, int nc, const std::vector<T>& x /*nc*nC*/,
             const std::vector<T>& phi, BF<T>& bf)
 {
     bf.init(nc, t.nBF);
@@ -257,7 +258,7 @@ void evalBC(const Topo& t, const Geom<T>& g, const BCSpec& bc, int field, int nc
     {
         const int f = t.nIF + b, c = t.own[f], pa = t.bPatch[b];
         const int kind = bc.kind[field * t.nPatch + pa];
-        const double* ref = &bc.value[(field * t.nPatch + pa) * 3];
+        const T* ref = &bcv[(field * t.nPatch + pa) * 3];
         const T& dl = g.delta[f];
         double fr = 0.0;
         switch (kind)
@@ -299,7 +300,7 @@ void evalBC(const Topo& t, const Geom<T>& g, const BCSpec& bc, int field, int nc
         else if (kind == BC_SYMMETRY || kind == BC_CALCULATED)
         {
             // scalar symmetry == zero gradient; `calculated` is overwritten by the caller (nut)
-            for (int k = 0; k < nc; k++) mixedCoeffs(bf, k, b, 0.0, 0.0, x[(size_t)k * t.nC + c], dl);
+            for (int k = 0; k < nc; k++) mixedCoeffs(bf, k, b, 0.0, T(0.0), x[(size_t)k * t.nC + c], dl);
         }
         else
         {
@@ -577,8 +578,16 @@ struct Work
 // R(W): DAResidualSimpleFoam::calcResiduals + DASpalartAllmaras::calcResiduals, preceded by
 // DASolver::updateStateBoundaryConditions (BCs + correctNut).
 template <class T>
-void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk = nullptr)
+void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk = nullptr,
+              const std::vector<T>* bcvIn = nullptr)
 {
+    std::vector<T> bcvLocal;
+    if (!bcvIn)
+    {
+        bcvLocal.resize(cs.bc.value.size());
+        for (size_t i = 0; i < bcvLocal.size(); i++) bcvLocal[i] = T(cs.bc.value[i]);
+    }
+    const std::vector<T>& bcv = bcvIn ? *bcvIn : bcvLocal;
     const Topo& t = cs.t;
     const Params& par = cs.par;
     const int nC = t.nC, nF = t.nF, nIF = t.nIF, nBF = t.nBF;
@@ -600,15 +609,15 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
 
     // --- boundary conditions and intermediate variables (DASolver::updateStateBoundaryConditions)
     BF<T> bU, bP, bNt, bNut;
-    evalBC(t, g, cs.bc, F_U, 3, U, phi, bU);
-    evalBC(t, g, cs.bc, F_P, 1, p, phi, bP);
+    evalBC(t, g, cs.bc, bcv, F_U, 3, U, phi, bU);
+    evalBC(t, g, cs.bc, bcv, F_P, 1, p, phi, bP);
     std::vector<T> nut(nC, T(0.0));
     if (turb)
     {
-        evalBC(t, g, cs.bc, F_NUTILDA, 1, nt, phi, bNt);
+        evalBC(t, g, cs.bc, bcv, F_NUTILDA, 1, nt, phi, bNt);
         // DASpalartAllmaras::correctNut: nut = nuTilda*fv1 (internal and boundary), then nut BCs
         for (int c = 0; c < nC; c++) nut[c] = nt[c] * fv1f(T(nt[c] / par.nu));
-        evalBC(t, g, cs.bc, F_NUT, 1, nut, phi, bNut);
+        evalBC(t, g, cs.bc, bcv, F_NUT, 1, nut, phi, bNut);
         for (int b = 0; b < nBF; b++)
             if (cs.bc.kind[F_NUT * t.nPatch + t.bPatch[b]] == BC_CALCULATED)
             {
@@ -1065,6 +1074,46 @@ void orc_jtvec_xv(void* h, const double* W, const double* psi, double* out /*3*n
     tp.evaluate(adj);
     for (size_t i = 0; i < ids.size(); i++) out[i] = adj[ids[i]];
     tp.reset();
+    cs->recorded = false;
+}
+
+// calcJacTVecProduct(patchVelocity -> residual) building block: [dR/d(U reference value of one patch)]^T psi
+// (the reference sets the patch values from (|U|, angle of attack) in DAInputPatchVelocity)
+void orc_jtvec_bcU(void* h, const double* W, const double* psi, int patch, double* out3)
+{
+    Case* cs = (Case*)h;
+    Tape& tp = tape();
+    tp.reset();
+    const int n = cs->nDof();
+    std::vector<AReal> bcv(cs->bc.value.size());
+    for (size_t i = 0; i < bcv.size(); i++) bcv[i] = AReal(cs->bc.value[i]);
+    int ids[3];
+    for (int k = 0; k < 3; k++)
+    {
+        AReal& a = bcv[(F_U * cs->t.nPatch + patch) * 3 + k];
+        a.registerInput();
+        ids[k] = a.id;
+    }
+    Geom<AReal> g;
+    std::vector<V3<AReal>> P(cs->t.nP);
+    for (int i = 0; i < cs->t.nP; i++) P[i] = V3<AReal>(AReal(cs->pts[3 * i]), AReal(cs->pts[3 * i + 1]), AReal(cs->pts[3 * i + 2]));
+    computeGeometry(cs->t, P, g);
+    std::vector<AReal> w(n), r;
+    for (int i = 0; i < n; i++) w[i] = AReal(W[i]);
+    residual<AReal>(*cs, g, w, 0, r, nullptr, &bcv);
+    std::vector<double> adj(tp.size() + 1, 0.0);
+    for (int i = 0; i < n; i++)
+        if (r[i].id) adj[r[i].id] += psi[i];
+    tp.evaluate(adj);
+    for (int k = 0; k < 3; k++) out3[k] = adj[ids[k]];
+    tp.reset();
+    cs->recorded = false;
+}
+
+void orc_set_bc_value(void* h, int field, int patch, const double* v3)
+{
+    Case* cs = (Case*)h;
+    for (int k = 0; k < 3; k++) cs->bc.value[(field * cs->t.nPatch + patch) * 3 + k] = v3[k];
     cs->recorded = false;
 }
 

@@ -144,6 +144,19 @@ class Oracle:
                             C.c_int(int(normalize)))
         return out
 
+    def jtvec_bcU(self, W, psi, patch):
+        """[dR/d(U boundary reference value of `patch`)]^T psi (3 numbers)."""
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        out = np.zeros(3)
+        lib().orc_jtvec_bcU(self.h, _p(W), _p(psi), C.c_int(patch), _p(out))
+        return out
+
+    def set_bc_value(self, field, patch, value):
+        v = np.zeros(3)
+        v[:len(np.atleast_1d(value))] = value
+        lib().orc_set_bc_value(self.h, C.c_int(FIELDS.index(field)), C.c_int(patch), _p(v))
+
     def jtvec_xv(self, W, psi):
         W = np.ascontiguousarray(W, dtype=np.float64)
         psi = np.ascontiguousarray(psi, dtype=np.float64)
