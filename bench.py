@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--solve-multi", action="store_true")
     ap.add_argument("--restart", type=int, default=1500)
     ap.add_argument("--pc-level", type=int, default=3)
+    ap.add_argument("--coarse", type=int, default=1000)
     ap.add_argument("--max-iters", type=int, default=3000)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +207,7 @@ def main():
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     opts = dict(normalizeStates=NORM_STATES, function=fn,
-                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level))
+                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level, coarseAggregates=args.coarse))
     sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()

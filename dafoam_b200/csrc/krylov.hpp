@@ -358,6 +358,106 @@ struct VecOps
     double norm2(const double* w, int n) { return std::sqrt(dots(w, 0, 1, w, n)[0]); }
 };
 
+// ---- aggregated pressure coarse space (two-level correction) ----------------------------------------------
+struct CoarseRestrict1 // partial[t] = sum of v_p over the cells of chunk t
+{
+    const double* vp; // pressure block of the vector
+    const int32_t* cells;
+    const int32_t* chunkStart; // [nChunks+1]
+    double* partial;
+    DAB_HD void operator()(int t) const
+    {
+        double s = 0.0;
+        for (int i = chunkStart[t]; i < chunkStart[t + 1]; i++) s += vp[cells[i]];
+        partial[t] = s;
+    }
+};
+struct CoarseRestrict2 // rc[a] = sum of the partials of aggregate a
+{
+    const double* partial;
+    const int32_t* aggChunkOff; // [nAgg+1]
+    double* rc;
+    DAB_HD void operator()(int a) const
+    {
+        double s = 0.0;
+        for (int i = aggChunkOff[a]; i < aggChunkOff[a + 1]; i++) s += partial[i];
+        rc[a] = s;
+    }
+};
+struct CoarseProlong // z = 0 except z_p[c] = yc[agg[c]]
+{
+    const double* yc;
+    const int32_t* aggOf;
+    int offP, nC, aggBase;
+    double* z;
+    DAB_HD void operator()(int i) const
+    {
+        const int c = i - offP;
+        z[i] = (c >= 0 && c < nC) ? yc[aggBase + aggOf[c]] : 0.0;
+    }
+};
+struct CoarseUnit // x = indicator of the pressure DOFs of local aggregate a (a < 0: zero vector)
+{
+    const int32_t* aggOf;
+    int offP, nC, a;
+    double* x;
+    DAB_HD void operator()(int i) const
+    {
+        const int c = i - offP;
+        x[i] = (c >= 0 && c < nC && aggOf[c] == a) ? 1.0 : 0.0;
+    }
+};
+
+struct Coarse
+{
+    bool enabled = false, valid = false;
+    int nAggLocal = 0, nAggGlobal = 0, aggBase = 0, nChunks = 0;
+    DevBuf<int32_t> dAggOf, dCells, dChunkStart, dAggChunkOff;
+    DevBuf<double> dPartial, dRc, dYc;
+    std::vector<double> lu;   // dense LU of the Galerkin coarse operator (row-major, nAggGlobal^2)
+    std::vector<int> piv;
+    std::vector<double> hRc;
+    void factor()
+    {
+        const int n = nAggGlobal;
+        piv.resize(n);
+        for (int k = 0; k < n; k++)
+        {
+            int p = k;
+            double mx = std::fabs(lu[(size_t)k * n + k]);
+            for (int i = k + 1; i < n; i++)
+                if (std::fabs(lu[(size_t)i * n + k]) > mx) { mx = std::fabs(lu[(size_t)i * n + k]); p = i; }
+            piv[k] = p;
+            if (p != k)
+                for (int j = 0; j < n; j++) std::swap(lu[(size_t)k * n + j], lu[(size_t)p * n + j]);
+            const double d = lu[(size_t)k * n + k];
+            if (d == 0.0) throw Error("coarse operator is singular");
+            for (int i = k + 1; i < n; i++)
+            {
+                const double l = lu[(size_t)i * n + k] / d;
+                lu[(size_t)i * n + k] = l;
+                if (l != 0.0)
+                    for (int j = k + 1; j < n; j++) lu[(size_t)i * n + j] -= l * lu[(size_t)k * n + j];
+            }
+        }
+    }
+    void solve(double* b) const
+    {
+        const int n = nAggGlobal;
+        for (int k = 0; k < n; k++)
+        {
+            std::swap(b[k], b[piv[k]]);
+            for (int i = k + 1; i < n; i++) b[i] -= lu[(size_t)i * n + k] * b[k];
+        }
+        for (int i = n - 1; i >= 0; i--)
+        {
+            double s = b[i];
+            for (int j = i + 1; j < n; j++) s -= lu[(size_t)i * n + j] * b[j];
+            b[i] = s / lu[(size_t)i * n + i];
+        }
+    }
+};
+
 struct Krylov
 {
     bool pcValid = false;
@@ -379,7 +479,8 @@ struct Krylov
     std::vector<int32_t> fdList, fdStart;
     DevBuf<int32_t> dFdList;
     // work
-    DevBuf<double> R0, R1, t1, t2;
+    DevBuf<double> R0, R1, t1, t2, t3;
+    Coarse coarse;
     // GMRES workspace
     DevBuf<double> V, w, z, xdev, bdev, hdev;
     int vCap = 0;

@@ -68,6 +68,7 @@ struct Solver
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
     double gmresRelTol = 1e-6, gmresAbsTol = 1e-14, gmresTolDiff = 1e2, fdStep = 1e-6;
     std::string pcType = "ilu";
+    int coarseAggregates = 0; // > 0: two-level preconditioner with that many pressure aggregates (global)
     int pcConLevel = 2; // cell-to-cell connectivity level of dRdWTPC (maxResConLv4JacPCMat role)
     std::vector<FunctionDef> functions;
     std::vector<PatchVelocityDef> patchVelocities;
@@ -241,6 +242,8 @@ struct Solver
             pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
+            const int ca = (int)a->numOr("coarseAggregates", coarseAggregates);
+            if (ca != coarseAggregates) { coarseAggregates = ca; kry.pcValid = false; }
             const int lv = (int)a->numOr("pcConLevel", pcConLevel);
             if (lv != pcConLevel) { pcConLevel = lv; kry.symbolic = false; kry.pcValid = false; }
         }
@@ -662,6 +665,10 @@ struct Solver
     void pcSymbolic();
     void calcPC();
     void applyPC(const double* v, double* z);
+    void applyIlu(const double* v, double* z);
+    void coarseSetup();
+    void coarseRestrict(const double* v);
+    int kspExtraMatvecs = 0;
     int solveLinearEqn(const double* rhs, double* sol, KspStats& st);
 };
 

@@ -363,11 +363,142 @@ inline void Solver::calcPC()
     for (const ColourView& cv : K.colours) be.launch(cv.nCells, IluFactorColour{A, cv, 1e-10});
     be.sync();
     K.pcValid = true;
+    K.coarse.enabled = coarseAggregates > 0;
+    K.coarse.valid = false;
+    if (K.coarse.enabled) coarseSetup();
+    be.sync();
     K.pcSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
-// z = M^{-1} v  (external layout in and out)
+// aggregated pressure coarse space: greedy breadth-first aggregates of ~nC/coarseAggregates cells; the Galerkin
+// coarse operator P^T A P is probed with the matrix-free product (one product per aggregate) and factorised
+// densely on the host.  Two-level role: the multicolour ILU(0) damps the short wavelengths, the coarse solve the
+// domain-wide pressure modes it cannot see.
+inline void Solver::coarseSetup()
+{
+    Krylov& K = kry;
+    Coarse& Cs = K.coarse;
+    const int nC = hm.nC, n = nDof(), offP = 3 * nC;
+    detail::CellGraph G;
+    G.build(hm);
+    const int target = std::max(1, nC / std::max(1, coarseAggregates / std::max(1, nRanks)));
+    std::vector<int32_t> aggOf(nC, -1);
+    int nAgg = 0;
+    std::vector<int> queue;
+    for (int seed = 0; seed < nC; seed++)
+    {
+        if (aggOf[seed] >= 0) continue;
+        queue.assign(1, seed);
+        aggOf[seed] = nAgg;
+        int cnt = 1;
+        for (size_t q = 0; q < queue.size() && cnt < target; q++)
+            for (int e = G.off[queue[q]]; e < G.off[queue[q] + 1] && cnt < target; e++)
+            {
+                const int x = G.adj[e];
+                if (aggOf[x] < 0)
+                {
+                    aggOf[x] = nAgg;
+                    queue.push_back(x);
+                    cnt++;
+                }
+            }
+        nAgg++;
+    }
+    // cells sorted by aggregate, chunks of 32
+    std::vector<int32_t> cnt(nAgg + 1, 0), cells(nC);
+    for (int c = 0; c < nC; c++) cnt[aggOf[c] + 1]++;
+    for (int a = 0; a < nAgg; a++) cnt[a + 1] += cnt[a];
+    {
+        std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+        for (int c = 0; c < nC; c++) cells[pos[aggOf[c]]++] = c;
+    }
+    std::vector<int32_t> chunkStart, aggChunkOff(1, 0);
+    for (int a = 0; a < nAgg; a++)
+    {
+        for (int i = cnt[a]; i < cnt[a + 1]; i += 32) chunkStart.push_back(i);
+        aggChunkOff.push_back((int32_t)chunkStart.size());
+    }
+    chunkStart.push_back(nC);
+    // chunks must not cross aggregates: the end of a chunk is min(next chunk start, end of its aggregate)
+    // (consecutive aggregates are contiguous in `cells`, so chunkStart[t+1] is already that end)
+    Cs.nChunks = (int)chunkStart.size() - 1;
+    Cs.nAggLocal = nAgg;
+    // global numbering of the aggregates (rank-major)
+    std::vector<double> counts(nRanks, 0.0);
+    counts[rank] = nAgg;
+    DevBuf<double> tmp;
+    tmp.upload(be, counts);
+    comm.allreduceSum(be, tmp.p, nRanks);
+    be.d2h(counts.data(), tmp.p, nRanks * sizeof(double));
+    Cs.aggBase = 0;
+    Cs.nAggGlobal = 0;
+    for (int r = 0; r < nRanks; r++)
+    {
+        if (r < rank) Cs.aggBase += (int)counts[r];
+        Cs.nAggGlobal += (int)counts[r];
+    }
+    Cs.dAggOf.upload(be, aggOf);
+    Cs.dCells.upload(be, cells);
+    Cs.dChunkStart.upload(be, chunkStart);
+    Cs.dAggChunkOff.upload(be, aggChunkOff);
+    Cs.dPartial.alloc(be, Cs.nChunks + 1);
+    Cs.dRc.alloc(be, Cs.nAggGlobal + 1);
+    Cs.dYc.alloc(be, Cs.nAggGlobal + 1);
+    Cs.hRc.assign(Cs.nAggGlobal, 0.0);
+    K.t3.alloc(be, n);
+    // Galerkin operator, column by column
+    const int Kg = Cs.nAggGlobal;
+    Cs.lu.assign((size_t)Kg * Kg, 0.0);
+    ensureRecorded();
+    for (int j = 0; j < Kg; j++)
+    {
+        const int local = (j >= Cs.aggBase && j < Cs.aggBase + nAgg) ? j - Cs.aggBase : -1;
+        be.launch(n, CoarseUnit{Cs.dAggOf.p, offP, nC, local, K.t2.p});
+        matVecDev(K.t2.p, K.t3.p);
+        coarseRestrict(K.t3.p);
+        for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
+    }
+    Cs.factor();
+    Cs.valid = true;
+    (void)offP;
+}
+
+// hRc = P^T v (global coarse vector on the host, summed over ranks)
+inline void Solver::coarseRestrict(const double* v)
+{
+    Coarse& Cs = kry.coarse;
+    const int offP = 3 * hm.nC;
+    be.launch(Cs.nChunks, CoarseRestrict1{v + offP, Cs.dCells.p, Cs.dChunkStart.p, Cs.dPartial.p});
+    be.zero(Cs.dRc.p, (size_t)Cs.nAggGlobal * sizeof(double));
+    be.launch(Cs.nAggLocal, CoarseRestrict2{Cs.dPartial.p, Cs.dAggChunkOff.p, Cs.dRc.p + Cs.aggBase});
+    comm.allreduceSum(be, Cs.dRc.p, Cs.nAggGlobal);
+    be.d2h(Cs.hRc.data(), Cs.dRc.p, (size_t)Cs.nAggGlobal * sizeof(double));
+}
+
+// z = M^{-1} v  (external layout in and out).  With the coarse space: multiplicative two-level,
+// z1 = P Ac^{-1} P^T v, z = z1 + ILU^{-1} (v - A z1).
 inline void Solver::applyPC(const double* v, double* z)
+{
+    Krylov& K = kry;
+    if (K.coarse.enabled && K.coarse.valid)
+    {
+        Coarse& Cs = K.coarse;
+        const int n = nDof();
+        coarseRestrict(v);
+        Cs.solve(Cs.hRc.data());
+        be.h2d(Cs.dYc.p, Cs.hRc.data(), (size_t)Cs.nAggGlobal * sizeof(double));
+        be.launch(n, CoarseProlong{Cs.dYc.p, Cs.dAggOf.p, 3 * hm.nC, hm.nC, Cs.aggBase, K.t2.p}); // z1
+        matVecDev(K.t2.p, K.t3.p);
+        kspExtraMatvecs++;
+        be.launch(n, SubVec{v, K.t3.p}); // t3 = v - A z1
+        applyIlu(K.t3.p, z);
+        be.launch(n, AxpyVec{K.t2.p, 1.0, z});
+        return;
+    }
+    applyIlu(v, z);
+}
+
+inline void Solver::applyIlu(const double* v, double* z)
 {
     Krylov& K = kry;
     EllView A = K.view();
@@ -405,9 +536,10 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
     const double bnorm = K.ops.norm2(K.bdev.p, n);
     st.r0 = bnorm;
     st.nMatvec = 0;
+    kspExtraMatvecs = 0;
     const double tol = std::max(gmresRelTol * bnorm, gmresAbsTol);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), yv(m, 0.0), hcol(m + 2, 0.0);
-    int its = 0;
+    int its = 0, nRefine = 0;
     double rnorm = bnorm;
     int reason = 0;
     if (bnorm == 0.0)
@@ -456,6 +588,7 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
             double nrm;
             if (wn2 - hn2 < 0.25 * wn2 || useMGSO)
             {
+                nRefine++;
                 const double* d2 = K.ops.dots(K.V.p, n, k + 2, vk1, n);
                 std::vector<double> h2(d2, d2 + k + 1);
                 const double wn2b = d2[k + 1];
@@ -514,12 +647,13 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
     st.solveSec = timer.stopMs() * 1e-3;
     (void)l0;
     be.d2h(sol, K.xdev.p, (size_t)n * sizeof(double));
+    st.nMatvec += kspExtraMatvecs;
     st.iterations = its;
     st.reason = reason;
     st.rn = rnorm;
     st.pcSec = K.pcSec;
     if (printInfo)
-        fprintf(stderr, "[dab200] Main iteration %d KSP Residual norm %14.12e %.3f s\n", its, rnorm, st.solveSec);
+        fprintf(stderr, "[dab200] Main iteration %d KSP Residual norm %14.12e %.3f s (%d Gram-Schmidt refinements)\n", its, rnorm, st.solveSec, nRefine);
     // reference success rule (DALinearEqn.C:422-434)
     const double absRatio = rnorm / gmresAbsTol;
     const double relRatio = bnorm > 0 ? rnorm / bnorm / gmresRelTol : 0.0;
