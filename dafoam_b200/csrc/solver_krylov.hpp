@@ -539,7 +539,7 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
     kspExtraMatvecs = 0;
     const double tol = std::max(gmresRelTol * bnorm, gmresAbsTol);
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), yv(m, 0.0), hcol(m + 2, 0.0);
-    int its = 0, nRefine = 0;
+    int its = 0, nRefine = 0, nTrueRestarts = 0;
     double rnorm = bnorm;
     int reason = 0;
     if (bnorm == 0.0)
@@ -586,7 +586,7 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
             double hn2 = 0.0;
             for (int j = 0; j <= k; j++) hn2 += hcol[j] * hcol[j];
             double nrm;
-            if (wn2 - hn2 < 0.25 * wn2 || useMGSO)
+            if (wn2 - hn2 < hn2 || useMGSO) // ||w_new|| < ||h||: the IFNEEDED test of PETSc's classical Gram-Schmidt
             {
                 nRefine++;
                 const double* d2 = K.ops.dots(K.V.p, n, k + 2, vk1, n);
@@ -641,7 +641,18 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
         be.launch(n, MultiAxpy{K.V.p, n, k, K.hdev.p, K.w.p, 1});
         applyPC(K.w.p, K.z.p);
         be.launch(n, AxpyVec{K.z.p, 1.0, K.xdev.p});
-        if (rnorm <= tol) reason = rnorm <= gmresRelTol * bnorm ? 2 : 3;
+        if (rnorm <= tol)
+        {
+            // the Givens recurrence says converged: verify with the true residual b - A x (classical Gram-Schmidt can
+            // lose enough orthogonality for the recurrence to be optimistic); if it is not there yet, the loop restarts from x
+            matVecDev(K.xdev.p, K.w.p);
+            st.nMatvec++;
+            be.launch(n, SubVec{K.bdev.p, K.w.p});
+            rnorm = K.ops.norm2(K.w.p, n);
+            if (rnorm <= tol * 1.0000001) reason = rnorm <= gmresRelTol * bnorm * 1.0000001 ? 2 : 3;
+            else if (its >= gmresMaxIters) reason = -3;
+            else nTrueRestarts++;
+        }
         else if (its >= gmresMaxIters) reason = -3;
     }
     st.solveSec = timer.stopMs() * 1e-3;
@@ -653,7 +664,7 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
     st.rn = rnorm;
     st.pcSec = K.pcSec;
     if (printInfo)
-        fprintf(stderr, "[dab200] Main iteration %d KSP Residual norm %14.12e %.3f s (%d Gram-Schmidt refinements)\n", its, rnorm, st.solveSec, nRefine);
+        fprintf(stderr, "[dab200] Main iteration %d KSP Residual norm %14.12e %.3f s (%d Gram-Schmidt refinements, %d true-residual restarts)\n", its, rnorm, st.solveSec, nRefine, nTrueRestarts);
     // reference success rule (DALinearEqn.C:422-434)
     const double absRatio = rnorm / gmresAbsTol;
     const double relRatio = bnorm > 0 ? rnorm / bnorm / gmresRelTol : 0.0;

