@@ -83,7 +83,7 @@ def test_two_level_preconditioner_reduces_iterations():
     its = {}
     for nagg in (0, 24):
         mesh, sol, W = adjoint_case(HOSTSIM, ni=48, nj=24)
-        sol.updateDAOption(dict(adjEqnOption=dict(coarseAggregates=nagg, gmresRelTol=1e-8, gmresMaxIters=600, gmresRestart=600)))
+        sol.updateDAOption(dict(adjEqnOption=dict(coarseAggregates=nagg, gmresRelTol=1e-8, gmresMaxIters=900, gmresRestart=150)))
         n = sol.getNLocalAdjointStates()
         b = np.zeros(n)
         sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), b)
