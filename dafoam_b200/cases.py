@@ -90,7 +90,7 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     return PolyMesh(points, faces, owner, neighbour, patches)
 
 
-def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3):
+def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None):
     """NACA0012 O-grid: ni cells around the airfoil, nj cells radially (geometric stretching
     from `first_dy` chord at the wall to the farfield circle of `radius` chords), nk cells in z.
     Patches: wing (wall), inout (patch), sym1/sym2 (symmetry)."""
@@ -131,8 +131,23 @@ def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3):
     def pid(i, j, k):
         return (i % ni) + ni * (j + (nj + 1) * k)
 
-    def cid(i, j, k):
+    def cid_lex(i, j, k):
         return (i % ni) + ni * (j + nj * k)
+
+    if tile is None:
+        cid = cid_lex
+    else:
+        # tile-major cell numbering (ti x tj cells per tile): neighbouring cells get nearby indices in both directions
+        ti, tj = tile
+        ii, jj = np.meshgrid(np.arange(ni), np.arange(nj), indexing="ij")
+        key = ((jj // tj) * ((ni + ti - 1) // ti) + (ii // ti)) * (ti * tj) + (jj % tj) * ti + (ii % ti)
+        order = np.argsort(key.ravel(), kind="stable")  # positions in lexicographic (i,j) raveled as i*nj + j
+        rank2d = np.empty(ni * nj, dtype=np.int64)
+        rank2d[order] = np.arange(ni * nj)
+        rank2d = rank2d.reshape(ni, nj)
+
+        def cid(i, j, k):
+            return rank2d[i % ni, j] + ni * nj * k
 
     I, J, K = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing="ij")
     I, J, K = I.ravel(), J.ravel(), K.ravel()

@@ -16,6 +16,7 @@
 #include "krylov.hpp"
 #include "partition.hpp"
 #include "comm.hpp"
+#include <cstdlib>
 #include <map>
 #include <set>
 
@@ -479,6 +480,11 @@ struct Solver
     }
 
     // y = diag(n) (dR/dW)^T x on device vectors (external layout)
+    void launchRevA(const PsiView& pv)
+    {
+        DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
+    }
+
     PsiView psiView(const double* x)
     {
         const size_t nC = hm.nC;
@@ -519,7 +525,7 @@ struct Solver
         ensureRecorded();
         const int nT = hm.nCtot;
         const PsiView pv = psiView(x);
-        DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
+        launchRevA(pv);
         if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nT}, {av.Dn, 1, 1, nT}, {av.gPb, 3, 1, nT}});
         DAB_LAUNCH_NF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
         if (comm.active())
@@ -535,7 +541,7 @@ struct Solver
     void benchKernel(int which)
     {
         const PsiView pv = psiView(dX.p);
-        if (which == 0) DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
+        if (which == 0) launchRevA(pv);
         else if (which == 1) DAB_LAUNCH_NF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
         else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
     }

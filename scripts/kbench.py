@@ -10,7 +10,8 @@ from dafoam_b200.pyDASolvers import pyDASolvers
 libs = sys.argv[1:] or [None]
 cells = int(os.environ.get("KB_CELLS", "980000"))
 nj = max(8, int(round((cells / 2.0) ** 0.5 / 2.0)) * 2)
-mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1)
+tile = os.environ.get("KB_TILE")
+mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1, tile=tuple(int(v) for v in tile.split("x")) if tile else None)
 d = tempfile.mkdtemp(prefix="dab_kb_")
 cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
 for lib in libs:
