@@ -154,11 +154,29 @@ def run_reference(args, rank):
            "config": {"workload": "DASimpleFoam NACA0012 SA %dx%dx1 O-grid (CPU arm: bounded sample of partitions)" % (ni, nj)},
            "cpu_baseline": base,
            "e2e": {"value": v, "unit": "GCells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line goes to the real stdout; everything else any library prints (e.g. NCCL's version banner)
+    was redirected to stderr at start-up."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -336,7 +354,7 @@ def main():
             out["cpu_baseline"] = cpu_reference(os.cpu_count() or 1, reps=10)
         except Exception as e:
             out["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -9,9 +9,10 @@ from dafoam_b200.pyDASolvers import pyDASolvers
 
 libs = sys.argv[1:] or [None]
 cells = int(os.environ.get("KB_CELLS", "980000"))
-nj = max(8, int(round((cells / 2.0) ** 0.5 / 2.0)) * 2)
+nk = int(os.environ.get("KB_NK", "1"))
+nj = max(8, int(round((cells / nk / 2.0) ** 0.5 / 2.0)) * 2)
 tile = os.environ.get("KB_TILE")
-mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1, tile=tuple(int(v) for v in tile.split("x")) if tile else None)
+mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=nk, span=1.0 if nk > 1 else 0.1, tile=tuple(int(v) for v in tile.split("x")) if tile else None)
 d = tempfile.mkdtemp(prefix="dab_kb_")
 cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
 for lib in libs:
@@ -24,5 +25,7 @@ for lib in libs:
     out = {}
     for name, which in (("product", 0), ("forward", 1), ("RevA", 2), ("RevB", 3), ("RevC", 4)):
         out[name] = round(sol.benchDevice(which, 30)[0], 4)
+    out["cells"] = sol.getNLocalCells()
+    out["GB_alg"] = round(sol.algorithmicBytes(0) / 1e9, 4)
     print(os.path.basename(lib or "libdab200.so"), out, flush=True)
     del sol
