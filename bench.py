@@ -326,6 +326,12 @@ def main():
         peaks = json.load(open(pk))
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    traffic, traffic_src = None, None
+    tf = os.path.join(ROOT, "profiles", "r01c_ncu_kernels_dram.json")
+    if os.path.exists(tf) and world == 1 and args.cells == 980000:
+        tj = json.load(open(tf))
+        traffic = sum(tj[k]["dram__bytes_read.sum"] + tj[k]["dram__bytes_write.sum"] for k in ("RevA", "RevB", "RevC"))
+        traffic_src = "profiles/r01c_ncu_kernels_dram.json (ncu dram__bytes_read+write of RevA+RevB+RevC, same workload)"
     alg = sol.algorithmicBytes(0)
     achieved = alg / (ms_max * 1e-3) / 1e9
     nC_global = sol.getNGlobalCells()
@@ -343,7 +349,7 @@ def main():
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
                 "call": "pyDASolvers.calcdRdWTPsiAD(psi_host, y_host) -> dab_drdwt_mat_vec (pinned host buffers)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_product": alg,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_product": alg,
                      "kernels_ms": per_kernel, "forward_R_ms": ms_fwd,
                      "note": "one product = RevA+RevB+RevC; achieved = algorithmic bytes of the product / its device time"},
         "adjoint_solve": adjoint,
