@@ -55,7 +55,7 @@ def _naca0012_y(x):
     return 0.6 * (0.2969 * np.sqrt(np.maximum(x, 0.0)) - 0.1260 * x - 0.3516 * x**2 + 0.2843 * x**3 - 0.1036 * x**4)
 
 
-def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_centres):
+def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_centres, family_major=None):
     """Orient faces (normal owner->neighbour / outward), sort, and build a PolyMesh.
 
     quads: (n,4) point ids; cell_a: (n,) one adjacent cell; cell_b: (n,) other cell or -1;
@@ -73,7 +73,13 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     quads[flip] = quads[flip][:, ::-1]
     # internal faces sorted by (owner, neighbour)
     ii = np.nonzero(internal)[0]
-    order_i = ii[np.lexsort((nei[ii], own[ii]))]
+    if family_major is not None:
+        # keep the generation order of the face families (all i-faces, then j-faces, then k-faces), each sorted by owner:
+        # faces that sit in the same slot of consecutive cells are then consecutive in memory
+        fam = np.asarray(family_major)[ii]
+        order_i = ii[np.lexsort((own[ii], fam))]
+    else:
+        order_i = ii[np.lexsort((nei[ii], own[ii]))]
     bi = np.nonzero(~internal)[0]
     order_b = bi[np.lexsort((np.arange(bi.size), patch_of_bface[bi]))]
     order = np.concatenate([order_i, order_b])
@@ -90,7 +96,7 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     return PolyMesh(points, faces, owner, neighbour, patches)
 
 
-def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None):
+def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None, family_major=False):
     """NACA0012 O-grid: ni cells around the airfoil, nj cells radially (geometric stretching
     from `first_dy` chord at the wall to the farfield circle of `radius` chords), nk cells in z.
     Patches: wing (wall), inout (patch), sym1/sym2 (symmetry)."""
@@ -192,12 +198,14 @@ def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, 
     add([pid(I[m], J[m], K[m] + 1), pid(I[m] + 1, J[m], K[m] + 1), pid(I[m] + 1, J[m] + 1, K[m] + 1), pid(I[m], J[m] + 1, K[m] + 1)],
         cid(I[m], J[m], K[m]), np.full(m.sum(), -1), 3)
 
+    quads_list = quads
     quads = np.concatenate(quads).astype(np.int32)
     ca = np.concatenate(ca).astype(np.int64)
     cb = np.concatenate(cb).astype(np.int64)
     pf = np.concatenate(pf)
     defs = [("wing", "wall"), ("inout", "patch"), ("sym1", "symmetry"), ("sym2", "symmetry")]
-    return _assemble(points, quads, ca, cb, pf, defs, cc)
+    fam = np.concatenate([np.full(q.shape[0], i) for i, q in enumerate(quads_list)]) if family_major else None
+    return _assemble(points, quads, ca, cb, pf, defs, cc, family_major=fam)
 
 
 def channel(nx=20, ny=10, nz=1, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.15):
