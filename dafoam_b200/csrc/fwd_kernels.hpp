@@ -160,18 +160,25 @@ struct FwdB
                     // explicit sources (moved to the left-hand side: MV -= Src)
                     double gUn[9];
                     for (int i = 0; i < 9; i++) gUn[i] = r.gU[(size_t)i * nT + n];
-                    if (schU == DIV_LINEAR_UPWIND)
+                    if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
                     {
                         const bool ownUp = s.phi[f] > 0.0;
                         const bool cUp = fr.s > 0 ? ownUp : !ownUp;
                         const double* gu = cUp ? gUc : gUn;
                         const int u = cUp ? c : n;
                         const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
-                        for (int j = 0; j < 3; j++)
+                        double corr[3];
+                        for (int j = 0; j < 3; j++) corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
+                        if (schU == DIV_LINEAR_UPWIND_V)
                         {
-                            const double corr = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
-                            MV[j] += mf * corr; // Src -= s*phi*corr
+                            // maxCorr = (1-w)(U_nei - U_own) for phi > 0, w (U_own - U_nei) otherwise
+                            const double wo_ = m.w[f];
+                            const double cf = ownUp ? (1.0 - wo_) : -wo_;
+                            double maxCorr[3];
+                            for (int j = 0; j < 3; j++) maxCorr[j] = cf * fr.s * (Un[j] - Uc[j]);
+                            luvLimit(corr, maxCorr, corr);
                         }
+                        for (int j = 0; j < 3; j++) MV[j] += mf * corr[j]; // Src -= s*phi*corr
                     }
                     const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
                     const double wo = m.w[f]; // owner weight for face-interpolated gradients

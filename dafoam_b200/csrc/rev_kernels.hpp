@@ -280,19 +280,34 @@ struct RevB
                         const double mbn = -D0n + offbn + wpn * abn;
                         phib_acc += mbc - mbn;
                     }
-                    if (schU == DIV_LINEAR_UPWIND)
+                    if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
                     {
+                        const double* gu = cUp ? gUc : gUn;
+                        const int u = cUp ? c : n;
+                        const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                        double corr[3], corrL[3], outb[3], corrb[3] = {0, 0, 0};
+                        for (int j = 0; j < 3; j++)
+                        {
+                            corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
+                            outb[j] = phi * lam[j]; // adjoint of the (limited) correction: +phi*corr into own row, -phi*corr into nei row
+                        }
+                        if (schU == DIV_LINEAR_UPWIND_V)
+                        {
+                            const double wo_ = m.w[f];
+                            const double cf = ownUp ? (1.0 - wo_) : -wo_;
+                            double maxCorr[3], maxCorrb[3] = {0, 0, 0};
+                            for (int j = 0; j < 3; j++) maxCorr[j] = cf * fr.s * (Un[j] - Uc[j]);
+                            luvLimit(corr, maxCorr, corrL);
+                            luvLimitAdj(corr, maxCorr, outb, corrb, maxCorrb);
+                            for (int j = 0; j < 3; j++) U2[j] -= cf * fr.s * maxCorrb[j];
+                        }
+                        else
+                            for (int j = 0; j < 3; j++) { corrL[j] = corr[j]; corrb[j] = outb[j]; }
                         if (cUp)
                             for (int j = 0; j < 3; j++)
-                                for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * phi * lam[j];
+                                for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * corrb[j];
                         if (fr.s > 0)
-                        {
-                            const double* gu = cUp ? gUc : gUn;
-                            const int u = cUp ? c : n;
-                            const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
-                            for (int j = 0; j < 3; j++)
-                                phib_acc += (d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2]) * lam[j];
-                        }
+                            for (int j = 0; j < 3; j++) phib_acc += corrL[j] * lam[j];
                     }
                     // non-orthogonal correction: MV_own -= gf*cg_j, MV_nei += gf*cg_j
                     for (int j = 0; j < 3; j++)

@@ -167,7 +167,11 @@ struct Solver
         Dict fs = readDict(caseDir + "/system/fvSchemes");
         auto scheme = [&](const std::string& key) {
             std::string v = fs.sub("divSchemes").joined(key);
-            if (v.find("linearUpwindV") != std::string::npos) throw Error("linearUpwindV is not supported; use linearUpwind");
+            if (v.find("linearUpwindV") != std::string::npos)
+            {
+                if (key != "div(phi,U)") throw Error("linearUpwindV applies to vector fields only (" + key + ")");
+                return (int)DIV_LINEAR_UPWIND_V;
+            }
             if (v.find("linearUpwind") != std::string::npos) return (int)DIV_LINEAR_UPWIND;
             if (v.find("upwind") != std::string::npos) return (int)DIV_UPWIND;
             if (v.find("linear") != std::string::npos) return (int)DIV_LINEAR;

@@ -15,7 +15,7 @@ namespace dab
 constexpr int MAXP = 16; // max patches per rank
 enum { F_U = 0, F_P = 1, F_NUTILDA = 2, F_NUT = 3, N_FIELDS = 4 };
 enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_INLET_OUTLET = 2, BC_OUTLET_INLET = 3, BC_SYMMETRY = 4, BC_CALCULATED = 5, BC_NUT_LOW_RE = 6 };
-enum { DIV_UPWIND = 0, DIV_LINEAR_UPWIND = 1, DIV_LINEAR = 2 };
+enum { DIV_UPWIND = 0, DIV_LINEAR_UPWIND = 1, DIV_LINEAR = 2, DIV_LINEAR_UPWIND_V = 3 };
 
 struct MeshView
 {
@@ -211,6 +211,41 @@ DAB_HD void bcVectorRefAdj(int kind, double phib, double dl, const double* valb,
     if (kind == BC_SYMMETRY) return;
     const double fr = bcFrac(kind, phib);
     for (int k = 0; k < 3; k++) refb[k] += fr * (valb[k] + dl * sngb[k]);
+}
+
+// linearUpwindV (OpenFOAM linearUpwindV<vector>::correction): the explicit correction `corr` is limited along
+// maxCorr = the linear-interpolation increment; out = ratio*corr with ratio in {0, 1, (corr.maxCorr)/(|corr|^2+VSMALL)}
+DAB_HD void luvLimit(const double* corr, const double* maxCorr, double* out)
+{
+    const double s = corr[0] * corr[0] + corr[1] * corr[1] + corr[2] * corr[2];
+    const double mm = corr[0] * maxCorr[0] + corr[1] * maxCorr[1] + corr[2] * maxCorr[2];
+    double ratio = 1.0;
+    if (s > 0.0)
+    {
+        if (mm < 0.0) ratio = 0.0;
+        else if (s > mm) ratio = mm / (s + 1e-300);
+    }
+    for (int j = 0; j < 3; j++) out[j] = ratio * corr[j];
+}
+// adjoint of luvLimit (active branch): accumulates into corrb and maxCorrb
+DAB_HD void luvLimitAdj(const double* corr, const double* maxCorr, const double* outb, double* corrb, double* maxCorrb)
+{
+    const double s = corr[0] * corr[0] + corr[1] * corr[1] + corr[2] * corr[2];
+    const double mm = corr[0] * maxCorr[0] + corr[1] * maxCorr[1] + corr[2] * maxCorr[2];
+    if (s > 0.0 && mm < 0.0) return;
+    if (s > 0.0 && s > mm)
+    {
+        const double den = s + 1e-300, r = mm / den;
+        const double g = outb[0] * corr[0] + outb[1] * corr[1] + outb[2] * corr[2];
+        const double mb = g / den, sb = -g * mm / (den * den);
+        for (int j = 0; j < 3; j++)
+        {
+            corrb[j] += r * outb[j] + mb * maxCorr[j] + 2.0 * sb * corr[j];
+            maxCorrb[j] += mb * corr[j];
+        }
+        return;
+    }
+    for (int j = 0; j < 3; j++) corrb[j] += outb[j];
 }
 
 // nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP and d(nut_b)/d(nuTilda_b) in dNb

@@ -76,7 +76,8 @@ enum DivScheme
 {
     DIV_UPWIND = 0,
     DIV_LINEAR_UPWIND = 1,
-    DIV_LINEAR = 2
+    DIV_LINEAR = 2,
+    DIV_LINEAR_UPWIND_V = 3
 };
 
 struct Topo
@@ -358,7 +359,7 @@ void fvcGrad(const Topo& t, const Geom<T>& g, int nc, const std::vector<T>& x, c
 // fvm::div(phi, x) with Gauss <scheme>; gaussConvectionScheme::fvmDiv (+ linearUpwind::correction)
 template <class T>
 void fvmDiv(Mat<T>& m, const Topo& t, const Geom<T>& g, const std::vector<T>& phi, int scheme, const BF<T>& bf,
-            const std::vector<T>& gradX, bool bounded)
+            const std::vector<T>& gradX, bool bounded, const std::vector<T>* xc = nullptr)
 {
     for (int f = 0; f < t.nIF; f++)
     {
@@ -373,15 +374,41 @@ void fvmDiv(Mat<T>& m, const Topo& t, const Geom<T>& g, const std::vector<T>& ph
         m.upper[f] += up;
         m.diag[t.own[f]] -= lo;
         m.diag[t.nei[f]] -= up;
-        if (scheme == DIV_LINEAR_UPWIND)
+        if (scheme == DIV_LINEAR_UPWIND || scheme == DIV_LINEAR_UPWIND_V)
         {
             const int u = (val(phi[f]) > 0.0) ? t.own[f] : t.nei[f];
             V3<T> d = g.Cf[f] - g.C[u];
+            std::vector<T> corr(m.nc);
+            for (int k = 0; k < m.nc; k++)
+                corr[k] = d.x * gradX[((size_t)k * 3 + 0) * t.nC + u] + d.y * gradX[((size_t)k * 3 + 1) * t.nC + u]
+                    + d.z * gradX[((size_t)k * 3 + 2) * t.nC + u];
+            if (scheme == DIV_LINEAR_UPWIND_V)
+            {
+                // linearUpwindV<vector>::correction (OpenFOAM-v1812): limit the correction along the linear increment
+                const std::vector<T>& x = *xc;
+                const int o = t.own[f], n = t.nei[f];
+                T sfCorrs(0.0), maxCorrs(0.0);
+                for (int k = 0; k < 3; k++)
+                {
+                    T mc = (val(phi[f]) > 0.0) ? (1.0 - g.w[f]) * (x[(size_t)k * t.nC + n] - x[(size_t)k * t.nC + o])
+                                               : g.w[f] * (x[(size_t)k * t.nC + o] - x[(size_t)k * t.nC + n]);
+                    sfCorrs += corr[k] * corr[k];
+                    maxCorrs += corr[k] * mc;
+                }
+                if (val(sfCorrs) > 0.0)
+                {
+                    if (val(maxCorrs) < 0.0)
+                        for (int k = 0; k < 3; k++) corr[k] = T(0.0);
+                    else if (val(sfCorrs) > val(maxCorrs))
+                    {
+                        T ratio = maxCorrs / (sfCorrs + 1e-300);
+                        for (int k = 0; k < 3; k++) corr[k] = corr[k] * ratio;
+                    }
+                }
+            }
             for (int k = 0; k < m.nc; k++)
             {
-                T corr = d.x * gradX[((size_t)k * 3 + 0) * t.nC + u] + d.y * gradX[((size_t)k * 3 + 1) * t.nC + u]
-                    + d.z * gradX[((size_t)k * 3 + 2) * t.nC + u];
-                T fl = phi[f] * corr;
+                T fl = phi[f] * corr[k];
                 m.src[(size_t)k * t.nC + t.own[f]] -= fl;
                 m.src[(size_t)k * t.nC + t.nei[f]] += fl;
             }
@@ -644,7 +671,7 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
     const int schemeU = isPC ? DIV_UPWIND : par.divU;
     Mat<T> UEqn;
     UEqn.init(t, 3);
-    fvmDiv(UEqn, t, g, phi, schemeU, bU, gradU, true);
+    fvmDiv(UEqn, t, g, phi, schemeU, bU, gradU, true, &U);
     fvmLaplacian(UEqn, t, g, -1.0, nuEff, nuEffB, bU, gradU, false);
     {
         // - fvc::div(nuEff*dev2(T(grad(U)))), "Gauss linear": source += sum_f Sf & T_f

@@ -29,7 +29,7 @@ def setup(kind="naca", turbulent=True, divU="linearUpwind", nk=2, nres=ALL_RES, 
     mesh = make_mesh(kind, nk, scale)
     bcs = make_bcs(kind, turbulent)
     d = tempfile.mkdtemp(prefix="dab_case_")
-    div_u = "bounded Gauss %s%s" % (divU, " grad(U)" if divU == "linearUpwind" else "")
+    div_u = "bounded Gauss %s%s" % (divU, " grad(U)" if divU.startswith("linearUpwind") else "")
     cases.write_case(d, mesh, bcs, binary=binary, div_u=div_u)
     opts = dict(normalizeStates=NORM_STATES, normalizeResiduals=list(nres))
     opts.update(extra_options or {})
@@ -65,6 +65,8 @@ CONFIGS = [
     ("channel", True, "linear", 1, ALL_RES),
     ("naca", True, "linearUpwind", 1, ("pRes",)),
     ("naca", True, "upwind", 1, ()),
+    ("naca", True, "linearUpwindV", 2, ALL_RES),   # the div(phi,U) scheme of the reference's NACA0012 tutorial cases
+    ("channel", True, "linearUpwindV", 1, ALL_RES),
 ]
 
 
