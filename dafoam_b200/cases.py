@@ -113,7 +113,10 @@ def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, 
     tot = radius
 
     def total(r):
-        return first_dy * (r**n - 1.0) / (r - 1.0)
+        e = n * np.log(r)
+        if e > 700.0:  # r**n would overflow (thousands of radial cells): certainly beyond the target length
+            return np.inf
+        return first_dy * np.expm1(e) / (r - 1.0)
 
     for _ in range(200):
         mid = 0.5 * (lo + hi)
@@ -441,7 +444,7 @@ relaxationFactors
         f.write("\napplication simpleFoam;\nstartTime 0;\nendTime 1000;\ndeltaT 1;\n")
 
 
-def default_bcs_naca(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True):
+def default_bcs_naca(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True, wall_function=False):
     """Boundary conditions of the reference's NACA0012 incompressible case family
     (wing wall, inout farfield, symmetry planes)."""
     U0 = tuple(float(x) for x in U0)
@@ -461,7 +464,7 @@ def default_bcs_naca(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True):
             "inout": dict(type="inletOutlet", inletValue=nuTilda0, value=nuTilda0),
             "sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")})
         bcs["nut"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, {
-            "wing": dict(type="nutLowReWallFunction", value=0.0),
+            "wing": dict(type="nutUSpaldingWallFunction" if wall_function else "nutLowReWallFunction", value=0.0),
             "inout": dict(type="calculated", value=0.0),
             "sym1": dict(type="symmetry"), "sym2": dict(type="symmetry")})
     return bcs

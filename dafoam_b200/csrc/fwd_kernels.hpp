@@ -237,8 +237,8 @@ struct FwdB
                 bcVector(q.bcKind[F_U][pa], q.bcVal[F_U][pa], Uc, mf, dl, nh, bu);
                 double ntb = 0.0, sngN = 0.0, frN;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
-                double dP, dNb;
-                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb) : 0.0;
+                double dP, dNb, dUn[3];
+                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
                 const double G = (nutb + q.nu) * mS;
                 D0 -= mf; // bounded
                 double mx = 0.0, mn = 0.0, av = 0.0;

@@ -376,8 +376,8 @@ struct RevB
                 bcVector(kU, q.bcVal[F_U][pa], Uc, mf, dl, nh, bu);
                 double ntb = 0.0, sngN = 0.0, frN = 0.0;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
-                double dP = 0.0, dNb = 0.0;
-                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb) : 0.0;
+                double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
+                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
                 const double nuEB = nutb + q.nu;
                 const double G = nuEB * mS;
                 // internalCoeffs and the argmax/argmin components used by relax()
@@ -427,8 +427,9 @@ struct RevB
                 boundaryGradAdj(nh, Gbb, gUb, sngb);
                 bcVectorAdj(kU, mf, dl, nh, valb, sngb, U2);
                 if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
-                // nut_b -> nut_c / nuTilda_b
+                // nut_b -> nut_c / nuTilda_b / U_c (wall function)
                 nuEb += dP * nuEBb;
+                for (int j = 0; j < 3; j++) U2[j] += dUn[j] * nuEBb;
                 double ntbb = dNb * nuEBb;
                 if (q.turb)
                 {
@@ -579,8 +580,8 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
     double ntb = 0.0, sngN = 0.0, frN = 0.0;
     const double ntc = q.turb ? s.nt[c] : 0.0;
     if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, phib, dl, ntb, sngN, frN);
-    double dP = 0.0, dNb = 0.0;
-    const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb) : 0.0;
+    double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
+    const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
     const double nuEB = nutb + q.nu;
     double Gbd[9];
     for (int j = 0; j < 3; j++)
@@ -623,6 +624,7 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
         *pb += (1.0 - frp) * pvb;
         *nutPb += dP * nuEBb;
         *ntb_ += (1.0 - frN) * dNb * nuEBb;
+        for (int j = 0; j < 3; j++) Ub[j] += dUn[j] * nuEBb;
     }
     return F;
 }

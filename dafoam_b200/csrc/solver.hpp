@@ -145,6 +145,7 @@ struct Solver
         if (t == "symmetry" || t == "symmetryPlane") return BC_SYMMETRY;
         if (t == "calculated") return BC_CALCULATED;
         if (t == "nutLowReWallFunction") return BC_NUT_LOW_RE;
+        if (t == "nutUSpaldingWallFunction" || t == "nutUSpaldingWallFunctionDF") return BC_NUT_SPALDING;
         throw Error("unsupported boundary condition type '" + t + "' in " + where);
     }
 

@@ -14,7 +14,7 @@ namespace dab
 
 constexpr int MAXP = 16; // max patches per rank
 enum { F_U = 0, F_P = 1, F_NUTILDA = 2, F_NUT = 3, N_FIELDS = 4 };
-enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_INLET_OUTLET = 2, BC_OUTLET_INLET = 3, BC_SYMMETRY = 4, BC_CALCULATED = 5, BC_NUT_LOW_RE = 6 };
+enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_INLET_OUTLET = 2, BC_OUTLET_INLET = 3, BC_SYMMETRY = 4, BC_CALCULATED = 5, BC_NUT_LOW_RE = 6, BC_NUT_SPALDING = 7 };
 enum { DIV_UPWIND = 0, DIV_LINEAR_UPWIND = 1, DIV_LINEAR = 2, DIV_LINEAR_UPWIND_V = 3 };
 
 struct MeshView
@@ -248,16 +248,67 @@ DAB_HD void luvLimitAdj(const double* corr, const double* maxCorr, const double*
     for (int j = 0; j < 3; j++) corrb[j] += outb[j];
 }
 
-// nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP and d(nut_b)/d(nuTilda_b) in dNb
-DAB_HD double nutBoundary(int kind, double ref, double nutP, double ntB, double nu, double& dP, double& dNb)
+// nutUSpaldingWallFunction (reference src/adjoint/DAMisc/nutUSpaldingWallFunctionDF/...DF.C:44-163): the friction
+// velocity u_tau solves Spalding's law f(u_tau) = 0 by Newton iterations (relative change < 1e-14, <= 1000 iterations),
+// nut_w = max(0, u_tau^2/(|dU/dn| + ROOTVSMALL) - nu).  dM = d(nut_w)/d(|U_P - U_w|) through the converged root
+// (implicit-function theorem; the reference differentiates the iterations with CoDiPack, equal up to the tolerance).
+DAB_HD double nutSpalding(double magUp, double dl, double nu, double& dM)
+{
+    const double kappa = 0.41, E = 9.8, ROOTVSMALL = 1.0e-150;
+    const double y = 1.0 / dl, G = magUp * dl;
+    dM = 0.0;
+    double ut = sqrt(nu * G);
+    if (!(ut > ROOTVSMALL)) return 0.0;
+    for (int it = 0; it < 1000; it++)
+    {
+        const double kUu = fmin(kappa * magUp / ut, 50.0);
+        const double fk = exp(kUu) - 1.0 - kUu * (1.0 + 0.5 * kUu);
+        const double f = -ut * y / nu + magUp / ut + (fk - kUu * kUu * kUu / 6.0) / E;
+        const double df = y / nu + magUp / (ut * ut) + kUu * fk / ut / E;
+        const double un = ut + f / df;
+        const double err = fabs((ut - un) / ut);
+        ut = un;
+        if (!(ut > ROOTVSMALL) || err < 1.0e-14) break;
+    }
+    if (!(ut > 0.0)) return 0.0;
+    const double den = G + ROOTVSMALL;
+    const double nutw = ut * ut / den - nu;
+    if (!(nutw > 0.0)) return 0.0;
+    const double k0 = kappa * magUp / ut;
+    const bool clip = !(k0 < 50.0);
+    const double k = clip ? 50.0 : k0;
+    const double P = exp(k) - 1.0 - k - 0.5 * k * k;
+    const double dkdm = clip ? 0.0 : kappa / ut, dkdu = clip ? 0.0 : -kappa * magUp / (ut * ut);
+    const double fm = 1.0 / ut + P * dkdm / E;
+    const double fu = -y / nu - magUp / (ut * ut) + P * dkdu / E;
+    const double dut = -fm / fu;
+    dM = 2.0 * ut * dut / den - ut * ut * dl / (den * den);
+    return nutw;
+}
+
+// nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP, d(nut_b)/d(nuTilda_b) in dNb and
+// d(nut_b)/d(U_P) in dU[3] (wall functions)
+DAB_HD double nutBoundary(int kind, double ref, double nutP, double ntB, double nu, const double* Uc, const double* Ub, double dl,
+                          double& dP, double& dNb, double* dU)
 {
     dP = 0.0;
     dNb = 0.0;
+    dU[0] = dU[1] = dU[2] = 0.0;
     switch (kind)
     {
     case BC_FIXED_VALUE:
     case BC_NUT_LOW_RE: return ref;
     case BC_CALCULATED: dNb = dnut_dnt(ntB, nu); return ntB * fv1f(ntB / nu);
+    case BC_NUT_SPALDING:
+    {
+        const double d[3] = {Uc[0] - Ub[0], Uc[1] - Ub[1], Uc[2] - Ub[2]};
+        const double magUp = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        double dM;
+        const double v = nutSpalding(magUp, dl, nu, dM);
+        if (magUp > 0.0)
+            for (int j = 0; j < 3; j++) dU[j] = dM * d[j] / magUp;
+        return v;
+    }
     default: dP = 1.0; return nutP; // symmetry, zeroGradient
     }
 }

@@ -62,7 +62,8 @@ enum BCKind
     BC_OUTLET_INLET = 3,
     BC_SYMMETRY = 4,
     BC_CALCULATED = 5,
-    BC_NUT_LOW_RE = 6
+    BC_NUT_LOW_RE = 6,
+    BC_NUT_SPALDING = 7
 };
 enum
 {
@@ -298,7 +299,7 @@ void evalBC(const Topo& t, const Geom<T>& g, const BCSpec& bc, const std::vector
                 bf.gbc[i] = bf.sng[i] - bf.gic[i] * xP[k];
             }
         }
-        else if (kind == BC_SYMMETRY || kind == BC_CALCULATED)
+        else if (kind == BC_SYMMETRY || kind == BC_CALCULATED || kind == BC_NUT_SPALDING)
         {
             // scalar symmetry == zero gradient; `calculated` is overwritten by the caller (nut)
             for (int k = 0; k < nc; k++) mixedCoeffs(bf, k, b, 0.0, T(0.0), x[(size_t)k * t.nC + c], dl);
@@ -646,11 +647,47 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
         for (int c = 0; c < nC; c++) nut[c] = nt[c] * fv1f(T(nt[c] / par.nu));
         evalBC(t, g, cs.bc, bcv, F_NUT, 1, nut, phi, bNut);
         for (int b = 0; b < nBF; b++)
-            if (cs.bc.kind[F_NUT * t.nPatch + t.bPatch[b]] == BC_CALCULATED)
+        {
+            const int kindN = cs.bc.kind[F_NUT * t.nPatch + t.bPatch[b]];
+            if (kindN == BC_CALCULATED)
             {
                 const T& nb = bNt.val[b];
                 bNut.val[b] = nb * fv1f(T(nb / par.nu));
             }
+            else if (kindN == BC_NUT_SPALDING)
+            {
+                // nutUSpaldingWallFunctionFvPatchScalarFieldDF::calcNut / calcUTau, differentiated through the
+                // Newton iterations like the reference's CoDiPack build
+                const int f = nIF + b, c = t.own[f];
+                const double kappa = 0.41, E = 9.8, ROOTVSMALL = 1.0e-150;
+                T d2(0.0);
+                for (int k = 0; k < 3; k++)
+                {
+                    T dd = U[(size_t)k * nC + c] - bU.val[bU.at(k, b)];
+                    d2 += dd * dd;
+                }
+                T magUp = sqrt(d2);
+                T G = magUp * g.delta[f];
+                T y = 1.0 / g.delta[f];
+                T ut = sqrt(par.nu * G);
+                if (val(ut) > ROOTVSMALL)
+                {
+                    for (int it = 0; it < 1000; it++)
+                    {
+                        T kUu = min(kappa * magUp / ut, T(50.0));
+                        T fk = exp(kUu) - 1.0 - kUu * (1.0 + 0.5 * kUu);
+                        T ff = -(ut * y) / par.nu + magUp / ut + (fk - kUu * kUu * kUu / 6.0) / E;
+                        T df = y / par.nu + magUp / (ut * ut) + kUu * fk / ut / E;
+                        T un = ut + ff / df;
+                        const double err = std::fabs((val(ut) - val(un)) / val(ut));
+                        ut = un;
+                        if (!(val(ut) > ROOTVSMALL) || err < 1.0e-14) break;
+                    }
+                }
+                ut = max(ut, T(0.0));
+                bNut.val[b] = max(T(0.0), ut * ut / (G + ROOTVSMALL) - par.nu);
+            }
+        }
     }
     else
     {

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BC_KIND = {"fixedValue": 0, "zeroGradient": 1, "inletOutlet": 2, "outletInlet": 3, "symmetry": 4,
-           "calculated": 5, "nutLowReWallFunction": 6}
+           "calculated": 5, "nutLowReWallFunction": 6, "nutUSpaldingWallFunction": 7}
 GEOM_KIND = {"patch": 0, "wall": 1, "symmetry": 2}
 DIV_SCHEME = {"upwind": 0, "linearUpwind": 1, "linear": 2, "linearUpwindV": 3}
 FIELDS = ["U", "p", "nuTilda", "nut"]

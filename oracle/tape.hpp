@@ -125,6 +125,7 @@ inline AReal max(const AReal& a, double b) { return a.v > b ? a : AReal(b); }
 inline AReal min(const AReal& a, double b) { return a.v < b ? a : AReal(b); }
 
 inline double sqrt(double a) { return std::sqrt(a); }
+inline double exp(double a) { return std::exp(a); }
 inline double fabs(double a) { return std::fabs(a); }
 inline double pow(double a, double e) { return std::pow(a, e); }
 inline double max(double a, double b) { return a > b ? a : b; }

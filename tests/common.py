@@ -15,12 +15,14 @@ ALL_RES = ("URes", "pRes", "nuTildaRes", "phiRes")
 
 
 def make_mesh(kind, nk=2, scale=1):
-    if kind == "naca":
+    if kind in ("naca", "nacawf"):
         return cases.naca0012_ogrid(ni=40 * scale, nj=20 * scale, nk=nk)
     return cases.channel(nx=12 * scale, ny=8 * scale, nz=nk)
 
 
 def make_bcs(kind, turbulent):
+    if kind == "nacawf":  # nutUSpaldingWallFunction on the wing (useWallFunction True in the reference's NACA0012 cases)
+        return cases.default_bcs_naca(turbulent=turbulent, wall_function=True)
     return cases.default_bcs_naca(turbulent=turbulent) if kind == "naca" else cases.default_bcs_channel(turbulent=turbulent)
 
 
@@ -67,6 +69,7 @@ CONFIGS = [
     ("naca", True, "upwind", 1, ()),
     ("naca", True, "linearUpwindV", 2, ALL_RES),   # the div(phi,U) scheme of the reference's NACA0012 tutorial cases
     ("channel", True, "linearUpwindV", 1, ALL_RES),
+    ("nacawf", True, "linearUpwindV", 1, ALL_RES),  # Spalding wall function (Newton solve per wall face)
 ]
 
 
