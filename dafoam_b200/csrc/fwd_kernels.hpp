@@ -105,7 +105,9 @@ DAB_HD double saSource(double nt, double nu, double y, const double* gU, const d
     return -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * nt + SA::Cw1 * fw * nt * nt / (y * y);
 }
 
-template <int NF>
+// FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in (the common
+// configuration without them keeps its register budget)
+template <int NF, int FEAT>
 struct FwdB
 {
     MeshView m;
@@ -160,7 +162,7 @@ struct FwdB
                     // explicit sources (moved to the left-hand side: MV -= Src)
                     double gUn[9];
                     for (int i = 0; i < 9; i++) gUn[i] = r.gU[(size_t)i * nT + n];
-                    if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
+                    if (schU == DIV_LINEAR_UPWIND || ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V))
                     {
                         const bool ownUp = s.phi[f] > 0.0;
                         const bool cUp = fr.s > 0 ? ownUp : !ownUp;
@@ -169,7 +171,7 @@ struct FwdB
                         const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
                         double corr[3];
                         for (int j = 0; j < 3; j++) corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
-                        if (schU == DIV_LINEAR_UPWIND_V)
+                        if ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V)
                         {
                             // maxCorr = (1-w)(U_nei - U_own) for phi > 0, w (U_own - U_nei) otherwise
                             const double wo_ = m.w[f];
@@ -238,7 +240,7 @@ struct FwdB
                 double ntb = 0.0, sngN = 0.0, frN;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
                 double dP, dNb, dUn[3];
-                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
+                const double nutb = q.turb ? nutBoundary<(FEAT & 2) != 0>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
                 const double G = (nutb + q.nu) * mS;
                 D0 -= mf; // bounded
                 double mx = 0.0, mn = 0.0, av = 0.0;

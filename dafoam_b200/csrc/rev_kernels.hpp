@@ -190,7 +190,9 @@ struct RevA
     }
 };
 
-template <int NF>
+// FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in (the common
+// configuration without them keeps its register budget)
+template <int NF, int FEAT>
 struct RevB
 {
     MeshView m;
@@ -280,7 +282,7 @@ struct RevB
                         const double mbn = -D0n + offbn + wpn * abn;
                         phib_acc += mbc - mbn;
                     }
-                    if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
+                    if (schU == DIV_LINEAR_UPWIND || ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V))
                     {
                         const double* gu = cUp ? gUc : gUn;
                         const int u = cUp ? c : n;
@@ -291,7 +293,7 @@ struct RevB
                             corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
                             outb[j] = phi * lam[j]; // adjoint of the (limited) correction: +phi*corr into own row, -phi*corr into nei row
                         }
-                        if (schU == DIV_LINEAR_UPWIND_V)
+                        if ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V)
                         {
                             const double wo_ = m.w[f];
                             const double cf = ownUp ? (1.0 - wo_) : -wo_;
@@ -377,7 +379,7 @@ struct RevB
                 double ntb = 0.0, sngN = 0.0, frN = 0.0;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
                 double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
-                const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
+                const double nutb = q.turb ? nutBoundary<(FEAT & 2) != 0>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
                 const double nuEB = nutb + q.nu;
                 const double G = nuEB * mS;
                 // internalCoeffs and the argmax/argmin components used by relax()
@@ -429,7 +431,8 @@ struct RevB
                 if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
                 // nut_b -> nut_c / nuTilda_b / U_c (wall function)
                 nuEb += dP * nuEBb;
-                for (int j = 0; j < 3; j++) U2[j] += dUn[j] * nuEBb;
+                if (FEAT & 2)
+                    for (int j = 0; j < 3; j++) U2[j] += dUn[j] * nuEBb;
                 double ntbb = dNb * nuEBb;
                 if (q.turb)
                 {
@@ -581,7 +584,7 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
     const double ntc = q.turb ? s.nt[c] : 0.0;
     if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, phib, dl, ntb, sngN, frN);
     double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
-    const double nutb = q.turb ? nutBoundary(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
+    const double nutb = q.turb ? nutBoundary<true>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
     const double nuEB = nutb + q.nu;
     double Gbd[9];
     for (int j = 0; j < 3; j++)

@@ -30,9 +30,26 @@ namespace dab
 #ifndef DAB_FWDB_MINBLOCKS
 #define DAB_FWDB_MINBLOCKS 3
 #endif
-template <int NF> struct LaunchTraits<RevB<NF>> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
-template <int NF> struct LaunchTraits<FwdB<NF>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
+template <int NF, int FEAT> struct LaunchTraits<RevB<NF, FEAT>> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
+template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 #endif
+
+// optional-feature dispatch for the two heavy kernels (hex meshes: 4 variants; other meshes: the full-featured one)
+#define DAB_LAUNCH_NFF(n, F, ...)                                     \
+    do                                                                \
+    {                                                                 \
+        if (hm.maxCF == 6)                                            \
+        {                                                             \
+            switch (featureMask())                                    \
+            {                                                         \
+            case 0: be.launch(n, F<6, 0>{__VA_ARGS__}); break;        \
+            case 1: be.launch(n, F<6, 1>{__VA_ARGS__}); break;        \
+            case 2: be.launch(n, F<6, 2>{__VA_ARGS__}); break;        \
+            default: be.launch(n, F<6, 3>{__VA_ARGS__}); break;       \
+            }                                                         \
+        }                                                             \
+        else be.launch(n, F<0, 3>{__VA_ARGS__});                      \
+    } while (0)
 
 // hexahedral meshes (6 faces per cell) get fully unrolled face loops; anything else the run-time loop
 #define DAB_LAUNCH_NF(n, F, ...)                                  \
@@ -96,6 +113,16 @@ struct Solver
     DevBuf<double> psiP, psiN, psiPhi; // working copies of the input vector with ghost slots (multi-rank only)
 
     int nDof() const { return (par.turb ? 5 : 4) * hm.nC + hm.nF; }
+
+    // bit 0: div(phi,U) is linearUpwindV; bit 1: some patch carries a wall-function nut BC
+    int featureMask() const
+    {
+        int f = par.divU == DIV_LINEAR_UPWIND_V ? 1 : 0;
+        if (par.turb)
+            for (size_t p = 0; p < hm.patches.size(); p++)
+                if (par.bcKind[F_NUT][p] == BC_NUT_SPALDING) f |= 2;
+        return f;
+    }
 
     // ------------------------------------------------------------------------------------------
     void create(const std::string& caseDir, const std::string& argsAll, const std::string& optionsJson, int device, int rank_,
@@ -465,7 +492,7 @@ struct Solver
             if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
             halo.exchangeCells(it);
         }
-        DAB_LAUNCH_NF(hm.nC, FwdB, mv, par, sv, rv, isPC, Rdev);
+        DAB_LAUNCH_NFF(hm.nC, FwdB, mv, par, sv, rv, isPC, Rdev);
         if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
         DAB_LAUNCH_NF(hm.nC, FwdC, mv, par, sv, rv, Rdev);
     }
@@ -532,7 +559,7 @@ struct Solver
         const PsiView pv = psiView(x);
         launchRevA(pv);
         if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nT}, {av.Dn, 1, 1, nT}, {av.gPb, 3, 1, nT}});
-        DAB_LAUNCH_NF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
+        DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
         if (comm.active())
         {
             std::vector<HaloItem> it{{av.gUb, 9, 1, nT}};
@@ -547,7 +574,7 @@ struct Solver
     {
         const PsiView pv = psiView(dX.p);
         if (which == 0) launchRevA(pv);
-        else if (which == 1) DAB_LAUNCH_NF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
+        else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
         else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
     }
 

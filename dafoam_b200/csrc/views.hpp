@@ -288,6 +288,7 @@ DAB_HD double nutSpalding(double magUp, double dl, double nu, double& dM)
 
 // nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP, d(nut_b)/d(nuTilda_b) in dNb and
 // d(nut_b)/d(U_P) in dU[3] (wall functions)
+template <bool WF>
 DAB_HD double nutBoundary(int kind, double ref, double nutP, double ntB, double nu, const double* Uc, const double* Ub, double dl,
                           double& dP, double& dNb, double* dU)
 {
@@ -300,6 +301,7 @@ DAB_HD double nutBoundary(int kind, double ref, double nutP, double ntB, double 
     case BC_NUT_LOW_RE: return ref;
     case BC_CALCULATED: dNb = dnut_dnt(ntB, nu); return ntB * fv1f(ntB / nu);
     case BC_NUT_SPALDING:
+    if (WF)
     {
         const double d[3] = {Uc[0] - Ub[0], Uc[1] - Ub[1], Uc[2] - Ub[2]};
         const double magUp = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -309,6 +311,7 @@ DAB_HD double nutBoundary(int kind, double ref, double nutP, double ntB, double 
             for (int j = 0; j < 3; j++) dU[j] = dM * d[j] / magUp;
         return v;
     }
+    return 0.0;
     default: dP = 1.0; return nutP; // symmetry, zeroGradient
     }
 }
