@@ -22,9 +22,10 @@ import numpy as np
 
 
 class PolyMesh:
-    """points (nP,3) f64; faces (nF,4) i32 (quads); owner (nF) i32; neighbour (nIF) i32;
-    patches: list of dict(name,type,start,size).  Internal faces come first, ordered by
-    (owner, neighbour); boundary faces are grouped patch by patch (OpenFOAM convention)."""
+    """points (nP,3) f64; faces (nF,4) i32 (quads; triangles are padded with -1 in the last column);
+    owner (nF) i32; neighbour (nIF) i32; patches: list of dict(name,type,start,size).  Internal faces
+    come first, ordered by (owner, neighbour); boundary faces are grouped patch by patch (OpenFOAM
+    convention)."""
 
     def __init__(self, points, faces, owner, neighbour, patches):
         self.points = np.ascontiguousarray(points, dtype=np.float64)
@@ -49,6 +50,17 @@ class PolyMesh:
     def n_points(self):
         return self.points.shape[0]
 
+    @property
+    def face_sizes(self):
+        return (self.faces >= 0).sum(axis=1).astype(np.int32)
+
+    def face_offsets_labels(self):
+        """CSR (offsets, labels) of the face -> point lists."""
+        sz = self.face_sizes
+        off = np.concatenate([[0], np.cumsum(sz)]).astype(np.int32)
+        lab = self.faces[self.faces >= 0].astype(np.int32)
+        return off, lab
+
 
 def _naca0012_y(x):
     # closed trailing edge variant (last coefficient -0.1036)
@@ -64,13 +76,19 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     internal = cell_b >= 0
     own = np.where(internal, np.minimum(cell_a, cell_b), cell_a)
     nei = np.where(internal, np.maximum(cell_a, cell_b), -1)
-    p = points[quads]  # (n,4,3)
+    tri = quads[:, 3] < 0
+    qq = quads.copy()
+    qq[tri, 3] = qq[tri, 0]  # a triangle as a degenerate quad: same area vector, centre slightly off (only used for orientation)
+    p = points[qq]  # (n,4,3)
     fc = p.mean(axis=1)
     # area vector of a quad by its diagonals
     nrm = 0.5 * np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 1])
     ref = np.where(internal[:, None], cell_centres[np.maximum(nei, 0)] - cell_centres[own], fc - cell_centres[own])
     flip = np.einsum("ij,ij->i", nrm, ref) < 0
-    quads[flip] = quads[flip][:, ::-1]
+    fq = flip & ~tri
+    quads[fq] = quads[fq][:, ::-1]
+    ft = flip & tri
+    quads[ft, :3] = quads[ft, :3][:, ::-1]
     # internal faces sorted by (owner, neighbour)
     ii = np.nonzero(internal)[0]
     if family_major is not None:
@@ -284,6 +302,63 @@ def channel(nx=20, ny=10, nz=1, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.
                      np.concatenate(pf), defs, cc)
 
 
+def prism_channel(nx=10, ny=6, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.15):
+    """The convergent channel meshed with triangular prisms (every quad column split along its diagonal): cells with
+    5 faces, triangular and quadrilateral faces -- exercises the general polyhedral paths of the engine."""
+    xs = np.linspace(0.0, lx, nx + 1)
+    et = np.linspace(0.0, 1.0, ny + 1)
+    h = ly * (1.0 - contraction * 0.5 * (1.0 - np.cos(np.pi * xs / lx)))
+    Xg = xs[:, None] + skew * ly * np.sin(np.pi * et)[None, :] * np.sin(np.pi * xs / lx)[:, None]
+    Yg = et[None, :] * h[:, None]
+
+    def pid(i, j, k):
+        return i + (nx + 1) * (j + (ny + 1) * k)
+
+    points = np.empty(((nx + 1) * (ny + 1) * 2, 3))
+    for k, z in enumerate((0.0, lz)):
+        for j in range(ny + 1):
+            for i in range(nx + 1):
+                points[pid(i, j, k)] = (Xg[i, j], Yg[i, j], z)
+    A = lambda i, j: 2 * (i + nx * j)       # prism on (p00, p10, p11)
+    B = lambda i, j: 2 * (i + nx * j) + 1   # prism on (p00, p11, p01)
+    faces, ca, cb, pf = [], [], [], []
+
+    def add(pts, a, b, patch):
+        faces.append(list(pts) + [-1] * (4 - len(pts)))
+        ca.append(a)
+        cb.append(b)
+        pf.append(patch)
+
+    for j in range(ny):
+        for i in range(nx):
+            p00, p10, p11, p01 = (i, j), (i + 1, j), (i + 1, j + 1), (i, j + 1)
+            q = lambda p, k: pid(p[0], p[1], k)
+            add([q(p00, 0), q(p11, 0), q(p11, 1), q(p00, 1)], A(i, j), B(i, j), -1)          # diagonal
+            for k, patch in ((0, 3), (1, 4)):                                                   # z planes (triangles)
+                add([q(p00, k), q(p10, k), q(p11, k)], A(i, j), -1, patch)
+                add([q(p00, k), q(p11, k), q(p01, k)], B(i, j), -1, patch)
+            # right edge of A: to B(i+1, j) or outlet
+            add([q(p10, 0), q(p11, 0), q(p11, 1), q(p10, 1)], A(i, j), B(i + 1, j) if i + 1 < nx else -1, -1 if i + 1 < nx else 1)
+            if i == 0:
+                add([q(p00, 0), q(p01, 0), q(p01, 1), q(p00, 1)], B(i, j), -1, 0)                 # inlet
+            # top edge of B: to A(i, j+1) or wall
+            add([q(p01, 0), q(p11, 0), q(p11, 1), q(p01, 1)], B(i, j), A(i, j + 1) if j + 1 < ny else -1, -1 if j + 1 < ny else 2)
+            if j == 0:
+                add([q(p00, 0), q(p10, 0), q(p10, 1), q(p00, 1)], A(i, j), -1, 2)                 # lower wall
+    faces = np.array(faces, dtype=np.int32)
+    ca, cb, pf = np.array(ca, dtype=np.int64), np.array(cb, dtype=np.int64), np.array(pf, dtype=np.int64)
+    # cell centres: mean of the 6 prism corners
+    cc = np.zeros((2 * nx * ny, 3))
+    for j in range(ny):
+        for i in range(nx):
+            c = [points[pid(a, b, k)] for (a, b) in ((i, j), (i + 1, j), (i + 1, j + 1)) for k in (0, 1)]
+            cc[A(i, j)] = np.mean(c, axis=0)
+            c = [points[pid(a, b, k)] for (a, b) in ((i, j), (i + 1, j + 1), (i, j + 1)) for k in (0, 1)]
+            cc[B(i, j)] = np.mean(c, axis=0)
+    defs = [("inlet", "patch"), ("outlet", "patch"), ("walls", "wall"), ("sym1", "symmetry"), ("sym2", "symmetry")]
+    return _assemble(points, faces, ca, cb, pf, defs, cc)
+
+
 # ----------------------------------------------------------------------------------------------
 # OpenFOAM writers
 # ----------------------------------------------------------------------------------------------
@@ -328,17 +403,16 @@ def write_polymesh(case_dir, mesh: PolyMesh, binary=False):
         if binary:
             # faceCompactList: offsets then flat labels
             f.write(_header("faceCompactList", "constant/polyMesh", "faces", fmt).encode())
-            nf, w = mesh.faces.shape
-            offs = (np.arange(nf + 1, dtype=np.int32) * w).astype(np.int32)
-            f.write(b"\n%d\n(" % (nf + 1))
+            offs, labs = mesh.face_offsets_labels()
+            f.write(b"\n%d\n(" % offs.size)
             f.write(offs.tobytes())
-            f.write(b")\n\n%d\n(" % (nf * w))
-            f.write(mesh.faces.tobytes())
+            f.write(b")\n\n%d\n(" % labs.size)
+            f.write(labs.tobytes())
             f.write(b")\n")
         else:
             f.write(_header("faceList", "constant/polyMesh", "faces", fmt).encode())
             f.write(b"\n%d\n(\n" % mesh.n_faces)
-            f.write("\n".join("4(%d %d %d %d)" % tuple(q) for q in mesh.faces).encode())
+            f.write("\n".join("%d(%s)" % ((q >= 0).sum(), " ".join(str(int(v)) for v in q if v >= 0)) for q in mesh.faces).encode())
             f.write(b"\n)\n")
     for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
         with open(os.path.join(pm, name), "wb") as f:
@@ -510,7 +584,10 @@ def write_case(case_dir, mesh: PolyMesh, bcs, binary=False, **dict_kw):
 def quad_face_geometry(mesh: PolyMesh):
     """Area vectors and centres of quad faces (diagonal cross product / vertex mean): good enough to
     synthesise a face-flux field; the engine computes the exact OpenFOAM geometry itself."""
-    p = mesh.points[mesh.faces]
+    fa = mesh.faces.copy()
+    tri = fa[:, 3] < 0
+    fa[tri, 3] = fa[tri, 0]
+    p = mesh.points[fa]
     Sf = 0.5 * np.cross(p[:, 2] - p[:, 0], p[:, 3] - p[:, 1])
     return Sf, p.mean(axis=1)
 

@@ -79,9 +79,10 @@ class Oracle:
         ns = dict(U=1.0, p=1.0, nuTilda=1.0, phi=1.0)
         ns.update(normalizeStates or {})
         kind, value = bc_tables(mesh, bcs)
-        nf, w = mesh.faces.shape
-        foff = (np.arange(nf + 1) * w).astype(np.int32)
-        flab = np.ascontiguousarray(mesh.faces.ravel(), dtype=np.int32)
+        nf = mesh.faces.shape[0]
+        foff, flab = mesh.face_offsets_labels()
+        foff = np.ascontiguousarray(foff, dtype=np.int32)
+        flab = np.ascontiguousarray(flab, dtype=np.int32)
         pstart = np.array([p["start"] for p in mesh.patches], dtype=np.int32)
         psize = np.array([p["size"] for p in mesh.patches], dtype=np.int32)
         pgeom = np.array([GEOM_KIND.get(p["type"], 0) for p in mesh.patches], dtype=np.int32)

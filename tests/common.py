@@ -17,6 +17,8 @@ ALL_RES = ("URes", "pRes", "nuTildaRes", "phiRes")
 def make_mesh(kind, nk=2, scale=1):
     if kind in ("naca", "nacawf"):
         return cases.naca0012_ogrid(ni=40 * scale, nj=20 * scale, nk=nk)
+    if kind == "prism":
+        return cases.prism_channel(nx=10 * scale, ny=6 * scale)
     return cases.channel(nx=12 * scale, ny=8 * scale, nz=nk)
 
 
@@ -70,6 +72,7 @@ CONFIGS = [
     ("naca", True, "linearUpwindV", 2, ALL_RES),   # the div(phi,U) scheme of the reference's NACA0012 tutorial cases
     ("channel", True, "linearUpwindV", 1, ALL_RES),
     ("nacawf", True, "linearUpwindV", 1, ALL_RES),  # Spalding wall function (Newton solve per wall face)
+    ("prism", True, "linearUpwind", 1, ALL_RES),    # triangular prisms: 5 faces per cell, triangles + quads
 ]
 
 
