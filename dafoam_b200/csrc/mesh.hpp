@@ -218,31 +218,62 @@ struct HostMesh
         for (int b = 0; b < nBF; b++)
             if (patchGeom[bPatch[b]] == PG_WALL) wf.push_back(nIF + b);
         if (wf.empty()) return;
-        // sort wall faces along x for a pruned search
-        std::sort(wf.begin(), wf.end(), [&](int a, int b) { return Cf[0][a] < Cf[0][b]; });
-        std::vector<double> wx(wf.size());
-        for (size_t i = 0; i < wf.size(); i++) wx[i] = Cf[0][wf[i]];
+        // k-d tree over the wall-face centres (median splits, implicit layout), exact nearest-neighbour query
+        const int nw = (int)wf.size();
+        std::vector<double> pts((size_t)3 * nw);
+        for (int i = 0; i < nw; i++)
+            for (int k = 0; k < 3; k++) pts[3 * (size_t)i + k] = Cf[k][wf[i]];
+        std::vector<int> idx(nw), axisOf(nw, 0);
+        for (int i = 0; i < nw; i++) idx[i] = i;
+        struct Range { int lo, hi, depth; };
+        {
+            std::vector<Range> st{{0, nw, 0}};
+            while (!st.empty())
+            {
+                Range r = st.back();
+                st.pop_back();
+                if (r.hi - r.lo <= 1) continue;
+                // split along the widest axis of the range
+                double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+                for (int i = r.lo; i < r.hi; i++)
+                    for (int k = 0; k < 3; k++)
+                    {
+                        mn[k] = std::min(mn[k], pts[3 * (size_t)idx[i] + k]);
+                        mx[k] = std::max(mx[k], pts[3 * (size_t)idx[i] + k]);
+                    }
+                int ax = 0;
+                for (int k = 1; k < 3; k++)
+                    if (mx[k] - mn[k] > mx[ax] - mn[ax]) ax = k;
+                const int mid = (r.lo + r.hi) / 2;
+                std::nth_element(idx.begin() + r.lo, idx.begin() + mid, idx.begin() + r.hi,
+                                 [&](int a, int b) { return pts[3 * (size_t)a + ax] < pts[3 * (size_t)b + ax]; });
+                axisOf[mid] = ax;
+                st.push_back({r.lo, mid, r.depth + 1});
+                st.push_back({mid + 1, r.hi, r.depth + 1});
+            }
+        }
+        std::vector<Range> stack;
         for (int c = 0; c < nC; c++)
         {
-            const double x = C[0][c], y = C[1][c], z = C[2][c];
-            size_t mid = (size_t)(std::lower_bound(wx.begin(), wx.end(), x) - wx.begin());
+            const double q[3] = {C[0][c], C[1][c], C[2][c]};
             double best = 1e300;
-            // expand outwards from mid until the x-distance alone exceeds the best distance
-            for (long i = (long)mid; i < (long)wf.size(); i++)
+            stack.assign(1, Range{0, nw, 0});
+            while (!stack.empty())
             {
-                double dx = wx[i] - x;
-                if (dx * dx >= best) break;
-                int f = wf[i];
-                double dy = Cf[1][f] - y, dz = Cf[2][f] - z;
-                best = std::min(best, dx * dx + dy * dy + dz * dz);
-            }
-            for (long i = (long)mid - 1; i >= 0; i--)
-            {
-                double dx = wx[i] - x;
-                if (dx * dx >= best) break;
-                int f = wf[i];
-                double dy = Cf[1][f] - y, dz = Cf[2][f] - z;
-                best = std::min(best, dx * dx + dy * dy + dz * dz);
+                Range r = stack.back();
+                stack.pop_back();
+                if (r.hi <= r.lo) continue;
+                const int mid = (r.lo + r.hi) / 2;
+                const double* pm = &pts[3 * (size_t)idx[mid]];
+                const double d2 = (pm[0] - q[0]) * (pm[0] - q[0]) + (pm[1] - q[1]) * (pm[1] - q[1]) + (pm[2] - q[2]) * (pm[2] - q[2]);
+                best = std::min(best, d2);
+                if (r.hi - r.lo == 1) continue;
+                const int ax = axisOf[mid];
+                const double diff = q[ax] - pm[ax];
+                const Range nearR = diff < 0 ? Range{r.lo, mid, 0} : Range{mid + 1, r.hi, 0};
+                const Range farR = diff < 0 ? Range{mid + 1, r.hi, 0} : Range{r.lo, mid, 0};
+                if (diff * diff < best) stack.push_back(farR); // visited after the near side (stack order)
+                stack.push_back(nearR);
             }
             yWall[c] = std::sqrt(best);
         }
