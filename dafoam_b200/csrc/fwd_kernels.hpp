@@ -240,7 +240,10 @@ struct FwdB
                 double ntb = 0.0, sngN = 0.0, frN;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
                 double dP, dNb, dUn[3];
-                const double nutb = q.turb ? nutBoundary<(FEAT & 2) != 0>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
+                double nutb = 0.0;
+                if (q.turb)
+                    nutb = (FEAT & 2) ? nutBoundary<true>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn)
+                                      : nutBoundaryBasic(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb);
                 const double G = (nutb + q.nu) * mS;
                 D0 -= mf; // bounded
                 double mx = 0.0, mn = 0.0, av = 0.0;

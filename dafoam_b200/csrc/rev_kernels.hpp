@@ -190,7 +190,8 @@ struct RevA
     }
 };
 
-// FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in (the common
+// FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in, bit 2 = adjoint of the
+// boundary reference values (patchVelocity input) compiled in (the common
 // configuration without them keeps its register budget)
 template <int NF, int FEAT>
 struct RevB
@@ -282,7 +283,25 @@ struct RevB
                         const double mbn = -D0n + offbn + wpn * abn;
                         phib_acc += mbc - mbn;
                     }
-                    if (schU == DIV_LINEAR_UPWIND || ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V))
+                    if (!(FEAT & 1))
+                    {
+                        // plain linearUpwind (compact form: no limiter state)
+                        if (schU == DIV_LINEAR_UPWIND)
+                        {
+                            if (cUp)
+                                for (int j = 0; j < 3; j++)
+                                    for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * phi * lam[j];
+                            if (fr.s > 0)
+                            {
+                                const double* gu = cUp ? gUc : gUn;
+                                const int u = cUp ? c : n;
+                                const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                                for (int j = 0; j < 3; j++)
+                                    phib_acc += (d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2]) * lam[j];
+                            }
+                        }
+                    }
+                    else if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
                     {
                         const double* gu = cUp ? gUc : gUn;
                         const int u = cUp ? c : n;
@@ -379,7 +398,10 @@ struct RevB
                 double ntb = 0.0, sngN = 0.0, frN = 0.0;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
                 double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
-                const double nutb = q.turb ? nutBoundary<(FEAT & 2) != 0>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn) : 0.0;
+                double nutb = 0.0;
+                if (q.turb)
+                    nutb = (FEAT & 2) ? nutBoundary<true>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn)
+                                      : nutBoundaryBasic(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb);
                 const double nuEB = nutb + q.nu;
                 const double G = nuEB * mS;
                 // internalCoeffs and the argmax/argmin components used by relax()
@@ -428,7 +450,7 @@ struct RevB
                 Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
                 boundaryGradAdj(nh, Gbb, gUb, sngb);
                 bcVectorAdj(kU, mf, dl, nh, valb, sngb, U2);
-                if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
+                if ((FEAT & 4) && a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
                 // nut_b -> nut_c / nuTilda_b / U_c (wall function)
                 nuEb += dP * nuEBb;
                 if (FEAT & 2)
@@ -451,7 +473,7 @@ struct RevB
         }
         if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb);
         for (int j = 0; j < 3; j++) a.U2[(size_t)j * nC + c] = U2[j];
-        if (a.bcRefb)
+        if ((FEAT & 4) && a.bcRefb)
             for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += refb[j];
         a.nt2[c] = nt2;
         a.nutb[c] = nuEb;

@@ -45,10 +45,11 @@ template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constex
             case 0: be.launch(n, F<6, 0>{__VA_ARGS__}); break;        \
             case 1: be.launch(n, F<6, 1>{__VA_ARGS__}); break;        \
             case 2: be.launch(n, F<6, 2>{__VA_ARGS__}); break;        \
-            default: be.launch(n, F<6, 3>{__VA_ARGS__}); break;       \
+            case 3: be.launch(n, F<6, 3>{__VA_ARGS__}); break;        \
+            default: be.launch(n, F<6, 7>{__VA_ARGS__}); break;       \
             }                                                         \
         }                                                             \
-        else be.launch(n, F<0, 3>{__VA_ARGS__});                      \
+        else be.launch(n, F<0, 7>{__VA_ARGS__});                      \
     } while (0)
 
 // hexahedral meshes (6 faces per cell) get fully unrolled face loops; anything else the run-time loop
@@ -121,6 +122,7 @@ struct Solver
         if (par.turb)
             for (size_t p = 0; p < hm.patches.size(); p++)
                 if (par.bcKind[F_NUT][p] == BC_NUT_SPALDING) f |= 2;
+        if (av.bcRefb) f = 7; // patchVelocity product: the full-featured variant also carries the BC-reference adjoint
         return f;
     }
 

@@ -286,6 +286,21 @@ DAB_HD double nutSpalding(double magUp, double dl, double nu, double& dM)
     return nutw;
 }
 
+// nut boundary value for the BC kinds without a wall function (the variant the common kernels are compiled with)
+DAB_HD double nutBoundaryBasic(int kind, double ref, double nutP, double ntB, double nu, double& dP, double& dNb)
+{
+    dP = 0.0;
+    dNb = 0.0;
+    switch (kind)
+    {
+    case BC_FIXED_VALUE:
+    case BC_NUT_LOW_RE: return ref;
+    case BC_CALCULATED: dNb = dnut_dnt(ntB, nu); return ntB * fv1f(ntB / nu);
+    case BC_NUT_SPALDING: return 0.0; // unreachable: kernels with a wall function use nutBoundary<true>
+    default: dP = 1.0; return nutP; // symmetry, zeroGradient
+    }
+}
+
 // nut boundary value from the nut BC kind; returns d(nut_b)/d(nut_P) in dP, d(nut_b)/d(nuTilda_b) in dNb and
 // d(nut_b)/d(U_P) in dU[3] (wall functions)
 template <bool WF>
