@@ -4,6 +4,7 @@
 // oracle on a machine without a GPU (tests/hostsim); it is never loaded by the product package.
 #pragma once
 #include "foam_io.hpp"
+#include "views.hpp"
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(128, LaunchTraits<F>::minBlocks) kernel1d(int 
 struct Backend
 {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr; // communication stream (halo exchange overlapped with interior cells)
     long launches = 0;
     void init(int device)
     {
@@ -50,11 +52,14 @@ struct Backend
             throw Error("dab200 requires a CUDA device (sm_100a); none is visible and there is no CPU fallback");
         DAB_CUDA_CHECK(cudaSetDevice(device));
         DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        DAB_CUDA_CHECK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
     }
     void destroy()
     {
         if (stream) cudaStreamDestroy(stream);
+        if (stream2) cudaStreamDestroy(stream2);
         stream = nullptr;
+        stream2 = nullptr;
     }
     void* alloc(size_t bytes)
     {
@@ -121,6 +126,22 @@ struct Backend
         double stopMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
     };
     Timer timer() { return Timer(); }
+};
+#endif
+
+// run a functor on the index range [c0, c0 + n)
+template <class F>
+struct Shifted
+{
+    F f;
+    int c0;
+    DAB_HD void operator()(int i) const { f(i + c0); }
+};
+#ifndef DAB_HOSTSIM
+template <class F>
+struct LaunchTraits<Shifted<F>>
+{
+    static constexpr int minBlocks = LaunchTraits<F>::minBlocks;
 };
 #endif
 

@@ -183,6 +183,10 @@ struct HaloSet
     DevBuf<int32_t> dSendIdx, dSendSegOff, dSendSegCnt, dRecvIdx, dRecvSegOff, dRecvSegCnt;
     DevBuf<double> sendBuf, recvBuf;
     int capComp = 0;
+#ifndef DAB_HOSTSIM
+    cudaEvent_t evPack = nullptr, evDone = nullptr;
+#endif
+    bool pending = false;
 
     void build(Backend& be, const std::vector<std::vector<int32_t>>& send, const std::vector<std::vector<int32_t>>& recv)
     {
@@ -281,6 +285,68 @@ struct Halo
     }
     void exchangeCells(const std::vector<HaloItem>& items) { run(cells, items); }
     void exchangeFaces(const std::vector<HaloItem>& items) { run(faces, items); }
+
+    // asynchronous variant: pack on the compute stream, exchange + unpack on the communication stream; the caller
+    // launches work that does not touch ghost slots in between and calls finish() before the work that does
+    void start(HaloSet& hs, const std::vector<HaloItem>& items)
+    {
+        if (!comm || !comm->active()) return;
+#ifdef DAB_HOSTSIM
+        run(hs, items);
+#else
+        if (!hs.evPack)
+        {
+            cudaEventCreateWithFlags(&hs.evPack, cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&hs.evDone, cudaEventDisableTiming);
+        }
+        int sumComp = 0;
+        for (const auto& it : items) sumComp += it.ncomp;
+        hs.reserve(*be, sumComp);
+        int base = 0;
+        for (const auto& it : items)
+        {
+            be->launch(hs.nSend * it.ncomp, HaloPack{it.arr, it.cellStride, it.compStride, it.ncomp, hs.dSendIdx.p, hs.dSendSegOff.p,
+                                                     hs.dSendSegCnt.p, hs.nSend, sumComp, base, hs.sendBuf.p});
+            base += it.ncomp;
+        }
+        cudaEventRecord(hs.evPack, be->stream);
+        std::swap(be->stream, be->stream2); // everything below goes to the communication stream
+        cudaStreamWaitEvent(be->stream, hs.evPack, 0);
+        std::vector<const double*> sb;
+        std::vector<double*> rb;
+        std::vector<int> sc, rc;
+        for (size_t p = 0; p < peers.size(); p++)
+        {
+            sb.push_back(hs.sendBuf.p + (size_t)hs.sendOffPeer[p] * sumComp);
+            rb.push_back(hs.recvBuf.p + (size_t)hs.recvOffPeer[p] * sumComp);
+            sc.push_back(hs.sendCntPeer[p] * sumComp);
+            rc.push_back(hs.recvCntPeer[p] * sumComp);
+        }
+        comm->exchange(*be, peers, sb, sc, rb, rc);
+        base = 0;
+        for (const auto& it : items)
+        {
+            be->launch(hs.nRecv * it.ncomp, HaloUnpack{it.arr, it.cellStride, it.compStride, it.ncomp, hs.dRecvIdx.p, hs.dRecvSegOff.p,
+                                                       hs.dRecvSegCnt.p, hs.nRecv, sumComp, base, hs.recvBuf.p});
+            base += it.ncomp;
+        }
+        cudaEventRecord(hs.evDone, be->stream);
+        std::swap(be->stream, be->stream2);
+        hs.pending = true;
+        exchanges++;
+#endif
+    }
+    void finish()
+    {
+#ifndef DAB_HOSTSIM
+        for (HaloSet* hs : {&cells, &faces})
+            if (hs->pending)
+            {
+                cudaStreamWaitEvent(be->stream, hs->evDone, 0);
+                hs->pending = false;
+            }
+#endif
+    }
 };
 
 } // namespace dab

@@ -19,6 +19,7 @@ struct HostMesh
     // topology
     int nP = 0, nF = 0, nIF = 0, nBF = 0, nC = 0;
     int nCtot = 0;        // owned + ghost cells (ghosts appended; nCtot == nC on one rank)
+    int nInterior = -1;   // owned cells [0, nInterior) have no neighbour on another rank (-1: all of them)
     std::vector<double> points;          // 3*nP
     std::vector<int32_t> fOff, fLab;     // faces -> points
     std::vector<int32_t> own, nei;       // nei sized nIF

@@ -74,14 +74,26 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
     P.nRanks = nRanks;
     P.nGlobalCells = g.nC;
     std::vector<int32_t> g2l(g.nC, -1);
-    // owned cells in global order
-    int nC = 0;
-    for (int c = 0; c < g.nC; c++)
-        if (part[c] == rank)
+    // owned cells: first the interior ones (no neighbour on another rank), then the ones along the cuts, each group
+    // in global order -- kernels can then run the interior range while the ghost exchange is in flight
+    std::vector<uint8_t> onCut(g.nC, 0);
+    for (int f = 0; f < g.nIF; f++)
+        if (part[g.own[f]] != part[g.nei[f]])
         {
-            g2l[c] = nC++;
-            P.cellGlobal.push_back(c);
+            onCut[g.own[f]] = 1;
+            onCut[g.nei[f]] = 1;
         }
+    int nC = 0;
+    for (int pass = 0; pass < 2; pass++)
+    {
+        for (int c = 0; c < g.nC; c++)
+            if (part[c] == rank && onCut[c] == pass)
+            {
+                g2l[c] = nC++;
+                P.cellGlobal.push_back(c);
+            }
+        if (pass == 0) l.nInterior = nC;
+    }
     // ghost cells grouped by owning rank, then global id
     std::vector<std::pair<int, int>> ghosts; // (rank, global)
     for (int f = 0; f < g.nIF; f++)
@@ -117,7 +129,10 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
             if (part[a] == rank && part[b] != rank) snd.emplace_back(part[b], g2l[a]);
             if (part[b] == rank && part[a] != rank) snd.emplace_back(part[a], g2l[b]);
         }
-        std::sort(snd.begin(), snd.end());
+        // the peer lists its ghosts by global id: send in the same order
+        std::sort(snd.begin(), snd.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+            return a.first != b.first ? a.first < b.first : P.cellGlobal[a.second] < P.cellGlobal[b.second];
+        });
         snd.erase(std::unique(snd.begin(), snd.end()), snd.end());
         for (auto& pr : snd) P.halo.sendCells[peerIndex(pr.first)].push_back(pr.second);
     }

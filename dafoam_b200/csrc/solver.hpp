@@ -52,6 +52,30 @@ template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constex
         else be.launch(n, F<0, 7>{__VA_ARGS__});                      \
     } while (0)
 
+// the same launches over the cell range [c0, c0 + n) (interior / cut-adjacent split for communication overlap)
+#define DAB_LAUNCH_NF_R(c0, n, F, ...)                                                      \
+    do                                                                                      \
+    {                                                                                       \
+        if (hm.maxCF == 6) be.launch(n, Shifted<F<6>>{F<6>{__VA_ARGS__}, c0});              \
+        else be.launch(n, Shifted<F<0>>{F<0>{__VA_ARGS__}, c0});                            \
+    } while (0)
+#define DAB_LAUNCH_NFF_R(c0, n, F, ...)                                                     \
+    do                                                                                      \
+    {                                                                                       \
+        if (hm.maxCF == 6)                                                                  \
+        {                                                                                   \
+            switch (featureMask())                                                          \
+            {                                                                               \
+            case 0: be.launch(n, Shifted<F<6, 0>>{F<6, 0>{__VA_ARGS__}, c0}); break;        \
+            case 1: be.launch(n, Shifted<F<6, 1>>{F<6, 1>{__VA_ARGS__}, c0}); break;        \
+            case 2: be.launch(n, Shifted<F<6, 2>>{F<6, 2>{__VA_ARGS__}, c0}); break;        \
+            case 3: be.launch(n, Shifted<F<6, 3>>{F<6, 3>{__VA_ARGS__}, c0}); break;        \
+            default: be.launch(n, Shifted<F<6, 7>>{F<6, 7>{__VA_ARGS__}, c0}); break;       \
+            }                                                                               \
+        }                                                                                   \
+        else be.launch(n, Shifted<F<0, 7>>{F<0, 7>{__VA_ARGS__}, c0});                      \
+    } while (0)
+
 // hexahedral meshes (6 faces per cell) get fully unrolled face loops; anything else the run-time loop
 #define DAB_LAUNCH_NF(n, F, ...)                                  \
     do                                                            \
@@ -558,17 +582,62 @@ struct Solver
     {
         ensureRecorded();
         const int nT = hm.nCtot;
-        const PsiView pv = psiView(x);
-        launchRevA(pv);
-        if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nT}, {av.Dn, 1, 1, nT}, {av.gPb, 3, 1, nT}});
-        DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
-        if (comm.active())
+        if (!comm.active())
+        {
+            const PsiView pv = psiView(x);
+            launchRevA(pv);
+            DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
+            DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
+            return;
+        }
+        // several ranks: every ghost exchange runs on the communication stream while the interior cells (no neighbour on
+        // another rank) of the next stage are processed; the cut-adjacent cells follow once the ghosts have arrived
+        const int nI = hm.nInterior < 0 ? hm.nC : hm.nInterior, nB = hm.nC - nI;
+        const PsiView pv = psiViewStart(x);
+        DAB_LAUNCH_NF_R(0, nI, RevA, mv, par, sv, rv, av, pv);
+        halo.finish();
+        DAB_LAUNCH_NF_R(nI, nB, RevA, mv, par, sv, rv, av, pv);
+        halo.start(halo.cells, {{av.mt, 3, 1, nT}, {av.Dn, 1, 1, nT}, {av.gPb, 3, 1, nT}});
+        DAB_LAUNCH_NFF_R(0, nI, RevB, mv, par, sv, rv, av, pv, y);
+        halo.finish();
+        DAB_LAUNCH_NFF_R(nI, nB, RevB, mv, par, sv, rv, av, pv, y);
         {
             std::vector<HaloItem> it{{av.gUb, 9, 1, nT}};
             if (par.turb) it.push_back({av.gNtb, 3, 1, nT});
-            halo.exchangeCells(it);
+            halo.start(halo.cells, it);
         }
-        DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
+        DAB_LAUNCH_NF_R(0, nI, RevC, mv, par, sv, rv, av, y, 0);
+        halo.finish();
+        DAB_LAUNCH_NF_R(nI, nB, RevC, mv, par, sv, rv, av, y, 0);
+    }
+
+    // ghost values of the input vector, exchange started but not awaited (halo.finish() before the first reader)
+    PsiView psiViewStart(const double* x)
+    {
+        const size_t nC = hm.nC;
+        const int nT = hm.nCtot;
+        if (psiP.n < (size_t)nT)
+        {
+            psiP.alloc(be, nT);
+            psiN.alloc(be, nT);
+            psiPhi.alloc(be, hm.nF);
+        }
+        PsiView v;
+        v.U = x;
+        be.d2d(psiP.p, x + 3 * nC, nC * sizeof(double));
+        std::vector<HaloItem> it{{psiP.p, 1, 1, nT}};
+        if (par.turb)
+        {
+            be.d2d(psiN.p, x + 4 * nC, nC * sizeof(double));
+            it.push_back({psiN.p, 1, 1, nT});
+        }
+        be.d2d(psiPhi.p, x + (par.turb ? 5 : 4) * nC, (size_t)hm.nF * sizeof(double));
+        halo.start(halo.cells, it);
+        halo.start(halo.faces, {{psiPhi.p, 1, 1, hm.nF}});
+        v.p = psiP.p;
+        v.nt = psiN.p;
+        v.phi = psiPhi.p;
+        return v;
     }
 
     // one reverse kernel alone on the bench vectors (dab_bench_device selectors 2-4)

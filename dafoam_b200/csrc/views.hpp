@@ -1,6 +1,7 @@
 // Device-side views (plain pointers, passed to kernels by value) and small inline helpers shared by
 // the forward R(W) kernels and the hand-derived reverse kernels.
 #pragma once
+#include <cmath>
 #include <cstdint>
 
 #if defined(__CUDACC__)
