@@ -194,9 +194,10 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
         if (ot == "residual") S.patchVelocityProduct(input_name, input, seed, product);
         else if (ot == "function")
         {
-            // the force on the function's own patches does not depend on the far-field velocity for a fixed direction
+            // only the flow-aligned direction modes (parallelToFlow / normalToFlow) depend on the angle of attack
+            need(output_name, "output_name");
             S.setPatchVelocity(input_name, input);
-            product[0] = product[1] = 0.0;
+            S.dFdPatchVelocity(output_name, seed[0], product);
         }
         else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
         return 0;

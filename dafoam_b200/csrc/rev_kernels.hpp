@@ -580,8 +580,10 @@ struct RevC
 struct ForceSpec
 {
     unsigned mask; // bit p set: patch p contributes
-    double dir[3];
+    double dir[3]; // force direction, or the moment axis
     double scale;
+    int mode;      // 0: force . dir (DAFunctionForce.C:79-153); 1: ((Cf - center) x force) . dir (DAFunctionMoment.C)
+    double center[3];
 };
 
 // boundary-face force contribution and (optionally) its adjoint w.r.t. the cell's variables
@@ -615,6 +617,15 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
         for (int i = 0; i < 3; i++) Gbd[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bu.sng[j] - nG);
     }
     const double trb = Gbd[0] + Gbd[4] + Gbd[8];
+    // effective direction of this face: dir for a force, axis x r for a moment ((r x F).a = F.(a x r))
+    double ed[3] = {fs.dir[0], fs.dir[1], fs.dir[2]};
+    if (fs.mode == 1)
+    {
+        const double rv[3] = {m.Cfx[f] - fs.center[0], m.Cfy[f] - fs.center[1], m.Cfz[f] - fs.center[2]};
+        ed[0] = fs.dir[1] * rv[2] - fs.dir[2] * rv[1];
+        ed[1] = fs.dir[2] * rv[0] - fs.dir[0] * rv[2];
+        ed[2] = fs.dir[0] * rv[1] - fs.dir[1] * rv[0];
+    }
     double F = 0.0, sj[3];
     for (int j = 0; j < 3; j++)
     {
@@ -622,7 +633,7 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
         double t = 0.0;
         for (int i = 0; i < 3; i++) t += Sv[i] * (Gbd[j * 3 + i] + Gbd[i * 3 + j]);
         sj[j] = t - (2.0 / 3.0) * trb * Sv[j];
-        F += (Sv[j] * pv - nuEB * sj[j]) * fs.dir[j];
+        F += (Sv[j] * pv - nuEB * sj[j]) * ed[j];
     }
     F *= fs.scale;
     if (gUb)
@@ -632,7 +643,7 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
         double pvb = 0.0, nuEBb = 0.0, trbb = 0.0;
         for (int j = 0; j < 3; j++)
         {
-            const double fb = seed * fs.scale * fs.dir[j];
+            const double fb = seed * fs.scale * ed[j];
             pvb += Sv[j] * fb;
             nuEBb -= sj[j] * fb;
             const double sb = -nuEB * fb;

@@ -90,13 +90,17 @@ struct PatchVelocityDef
     std::string name;
     std::vector<int> patches;
     int flowAxis = 0, normalAxis = 1;
+    double Umag = 0.0, aoaDeg = 0.0; // last assigned values (DAGlobalVar::patchVelocity role)
 };
 
 struct FunctionDef
 {
-    std::string name, type;
+    std::string name, type;              // type: force | moment
     std::vector<int> patches;
-    double dir[3] = {1.0, 0.0, 0.0};
+    std::string dirMode = "fixedDirection"; // fixedDirection | parallelToFlow | normalToFlow (DAFunctionForce.C:37-70)
+    std::string patchVelocityInput;      // input whose angle of attack steers the direction
+    double dir[3] = {1.0, 0.0, 0.0};     // force direction / moment axis
+    double center[3] = {0.0, 0.0, 0.0};  // moment centre
     double scale = 1.0;
 };
 
@@ -315,9 +319,7 @@ struct Solver
                 FunctionDef f;
                 f.name = kv.first;
                 f.type = kv.second.strOr("type", "force");
-                if (f.type != "force") throw Error("function type " + f.type + " is not supported (force)");
-                if (kv.second.strOr("directionMode", "fixedDirection") != "fixedDirection")
-                    throw Error("only directionMode fixedDirection is supported");
+                if (f.type != "force" && f.type != "moment") throw Error("function type " + f.type + " is not supported (force, moment)");
                 if (const JVal* pl = kv.second.get("patches"))
                     for (const auto& pn : pl->arr)
                     {
@@ -327,8 +329,29 @@ struct Solver
                         if (found < 0) throw Error("function " + f.name + ": unknown patch " + pn.str);
                         f.patches.push_back(found);
                     }
-                if (const JVal* d = kv.second.get("direction"))
-                    for (size_t k = 0; k < 3 && k < d->arr.size(); k++) f.dir[k] = d->arr[k].num;
+                if (f.type == "moment")
+                {
+                    if (const JVal* d = kv.second.get("axis"))
+                        for (size_t k = 0; k < 3 && k < d->arr.size(); k++) f.dir[k] = d->arr[k].num;
+                    if (const JVal* d = kv.second.get("center"))
+                        for (size_t k = 0; k < 3 && k < d->arr.size(); k++) f.center[k] = d->arr[k].num;
+                }
+                else
+                {
+                    f.dirMode = kv.second.strOr("directionMode", "fixedDirection");
+                    if (f.dirMode == "fixedDirection")
+                    {
+                        if (const JVal* d = kv.second.get("direction"))
+                            for (size_t k = 0; k < 3 && k < d->arr.size(); k++) f.dir[k] = d->arr[k].num;
+                    }
+                    else if (f.dirMode == "parallelToFlow" || f.dirMode == "normalToFlow")
+                    {
+                        f.patchVelocityInput = kv.second.strOr("patchVelocityInputName", "");
+                        if (f.patchVelocityInput.empty()) throw Error("function " + f.name + ": patchVelocityInputName is required");
+                    }
+                    else
+                        throw Error("directionMode for " + f.name + " not valid! Options: fixedDirection, parallelToFlow, normalToFlow.");
+                }
                 const double mg = std::sqrt(f.dir[0] * f.dir[0] + f.dir[1] * f.dir[1] + f.dir[2] * f.dir[2]);
                 if (std::fabs(mg - 1.0) > 1e-8) throw Error("the magnitude of the direction parameter in " + f.name + " is not 1.0!");
                 f.scale = kv.second.numOr("scale", 1.0);
@@ -360,6 +383,12 @@ struct Solver
                         if (found < 0) throw Error("inputInfo." + kv.first + ": unknown patch " + pn.str);
                         d.patches.push_back(found);
                     }
+                if (!d.patches.empty())
+                {
+                    const double uf = par.bcVal[F_U][d.patches[0]][d.flowAxis], un = par.bcVal[F_U][d.patches[0]][d.normalAxis];
+                    d.Umag = std::sqrt(uf * uf + un * un);
+                    d.aoaDeg = std::atan2(un, uf) * 180.0 / 3.14159265358979323846;
+                }
                 patchVelocities.push_back(d);
             }
         }
@@ -667,7 +696,9 @@ struct Solver
     // assign (|U|, aoa[deg]) to the U boundary reference values of the patches
     void setPatchVelocity(const std::string& name, const double* in)
     {
-        const PatchVelocityDef& d = findPatchVelocity(name);
+        PatchVelocityDef& d = const_cast<PatchVelocityDef&>(findPatchVelocity(name));
+        d.Umag = in[0];
+        d.aoaDeg = in[1];
         const double a = in[1] * 3.14159265358979323846 / 180.0;
         for (int p : d.patches)
         {
@@ -719,13 +750,35 @@ struct Solver
         throw Error("function " + name + " is not defined in the options");
     }
 
-    ForceSpec forceSpec(const FunctionDef& f) const
+    // dAlpha = true: the direction is replaced by its derivative w.r.t. the angle of attack [rad]
+    ForceSpec forceSpec(const FunctionDef& f, bool dAlpha = false) const
     {
         ForceSpec fs;
         fs.mask = 0;
         for (int p : f.patches) fs.mask |= (1u << p);
-        for (int k = 0; k < 3; k++) fs.dir[k] = f.dir[k];
+        for (int k = 0; k < 3; k++) { fs.dir[k] = f.dir[k]; fs.center[k] = f.center[k]; }
         fs.scale = f.scale;
+        fs.mode = f.type == "moment" ? 1 : 0;
+        if (f.type == "force" && f.dirMode != "fixedDirection")
+        {
+            // the angle of attack comes from the patchVelocity input (DAGlobalVar::patchVelocity, DAFunctionForce.C:92-114)
+            const PatchVelocityDef& d = findPatchVelocity(f.patchVelocityInput);
+            const double a = d.aoaDeg * 3.14159265358979323846 / 180.0;
+            const double ca = std::cos(a), sa = std::sin(a);
+            fs.dir[0] = fs.dir[1] = fs.dir[2] = 0.0;
+            if (f.dirMode == "parallelToFlow")
+            {
+                fs.dir[d.flowAxis] = dAlpha ? -sa : ca;
+                fs.dir[d.normalAxis] = dAlpha ? ca : sa;
+            }
+            else
+            {
+                fs.dir[d.flowAxis] = dAlpha ? -ca : -sa;
+                fs.dir[d.normalAxis] = dAlpha ? -sa : ca;
+            }
+        }
+        else if (dAlpha)
+            fs.dir[0] = fs.dir[1] = fs.dir[2] = 0.0;
         return fs;
     }
 
@@ -750,6 +803,29 @@ struct Solver
             be.d2h(&s, dFacePart.p, sizeof(double));
         }
         return s;
+    }
+
+    // dF/d(|U|, aoa[deg]) at fixed states: only the flow-aligned direction modes depend on the angle
+    void dFdPatchVelocity(const std::string& fname, double seed, double* product)
+    {
+        const FunctionDef& f = findFunction(fname);
+        product[0] = product[1] = 0.0;
+        if (f.type != "force" || f.dirMode == "fixedDirection") return;
+        ensureRecorded();
+        if (dFacePart.n < (size_t)hm.nBF + 1) dFacePart.alloc(be, hm.nBF + 1);
+        ForceFwd k{mv, par, sv, rv, forceSpec(f, true), dFacePart.p};
+        be.launch(hm.nBF, k);
+        std::vector<double> facePart(hm.nBF);
+        be.d2h(facePart.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
+        double s = 0.0;
+        for (int b = 0; b < hm.nBF; b++) s += facePart[b];
+        if (comm.active())
+        {
+            be.h2d(dFacePart.p, &s, sizeof(double));
+            comm.allreduceSum(be, dFacePart.p, 1);
+            be.d2h(&s, dFacePart.p, sizeof(double));
+        }
+        product[1] = seed * s * 3.14159265358979323846 / 180.0;
     }
 
     // [dF/dW]^T * seed, scaled by normalizeStates (DASolver.C:1819-1820)

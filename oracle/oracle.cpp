@@ -888,8 +888,10 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
 }
 
 // DAFunctionForce::calcFunction: sum over the faces of one patch of (Sf*p_b + Sf & devRhoReff_b) . dir
+// mode 0: force . dir (DAFunctionForce); mode 1: ((Cf - center) x force) . dir (DAFunctionMoment.C:60-140)
 template <class T>
-T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int patch, const double* dir, double scale)
+T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int patch, const double* dir, double scale, int mode = 0,
+                 const double* center = nullptr)
 {
     std::vector<T> R;
     Work<T> wk;
@@ -919,7 +921,15 @@ T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int p
             for (int i = 0; i < 3; i++) s += g.Sf[f][i] * (Gb[i][j] + Gb[j][i]);
             s -= (2.0 / 3.0) * tr * g.Sf[f][j];
             T fj = g.Sf[f][j] * wk.bP.val[b] - nuEffB * s;
-            fv += fj * dir[j];
+            if (mode == 0)
+                fv += fj * dir[j];
+            else
+            {
+                // (r x F) . a = F . (a x r)
+                const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                T r1 = g.Cf[f][j1] - center[j1], r2 = g.Cf[f][j2] - center[j2];
+                fv += fj * (dir[j1] * r2 - dir[j2] * r1);
+            }
         }
         F += scale * fv;
     }
@@ -1074,15 +1084,16 @@ void orc_jtvec(void* h, const double* psi, double* out, int normalize)
     if (normalize) scaleStates(cs, out);
 }
 
-double orc_force(void* h, const double* W, int patch, const double* dir, double scale)
+double orc_force(void* h, const double* W, int patch, const double* dir, double scale, int mode, const double* center)
 {
     Case* cs = (Case*)h;
     std::vector<double> w(W, W + cs->nDof());
-    return forceFunction<double>(*cs, cs->gd, w, patch, dir, scale);
+    return forceFunction<double>(*cs, cs->gd, w, patch, dir, scale, mode, center);
 }
 
 // calcJacTVecProduct(stateVar -> function): dF/dW * seed, scaled like the reference (DASolver.C:1819-1820)
-void orc_dforce_dw(void* h, const double* W, int patch, const double* dir, double scale, double seed, double* out, int normalize)
+void orc_dforce_dw(void* h, const double* W, int patch, const double* dir, double scale, double seed, double* out, int normalize, int mode,
+                   const double* center)
 {
     Case* cs = (Case*)h;
     Tape& tp = tape();
@@ -1100,7 +1111,7 @@ void orc_dforce_dw(void* h, const double* W, int patch, const double* dir, doubl
     std::vector<V3<AReal>> P(cs->t.nP);
     for (int i = 0; i < cs->t.nP; i++) P[i] = V3<AReal>(AReal(cs->pts[3 * i]), AReal(cs->pts[3 * i + 1]), AReal(cs->pts[3 * i + 2]));
     computeGeometry(cs->t, P, g);
-    AReal F = forceFunction<AReal>(*cs, g, w, patch, dir, scale);
+    AReal F = forceFunction<AReal>(*cs, g, w, patch, dir, scale, mode, center);
     std::vector<double> adj(tp.size() + 1, 0.0);
     if (F.id) adj[F.id] = seed;
     tp.evaluate(adj);

@@ -103,3 +103,47 @@ def check_parity(lib_path, tol=1e-10):
                 worst = max(worst, e)
                 assert e < tol, ("jtvec", kind, turb, divU, name, e)
     return worst
+
+
+def check_functions(lib_path, tol=1e-12):
+    """DAFunctionForce (fixedDirection / parallelToFlow / normalToFlow) and DAFunctionMoment of the engine vs
+    the oracle: values, [dF/dW]^T and the direct dF/d(aoa) term of the flow-aligned modes."""
+    aoa = 3.0
+    a = np.deg2rad(aoa)
+    dirv = [float(np.cos(0.05)), float(np.sin(0.05)), 0.0]
+    axis, center = [0.0, 0.0, 1.0], [0.25, 0.01, 0.05]
+    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
+                 "direction": dirv, "scale": 0.02},
+          "CDa": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "parallelToFlow",
+                  "patchVelocityInputName": "patchV", "scale": 0.5},
+          "CLa": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "normalToFlow",
+                  "patchVelocityInputName": "patchV", "scale": 0.5},
+          "CMZ": {"type": "moment", "source": "patchToFace", "patches": ["wing"], "axis": axis, "center": center,
+                  "scale": 2.0}}
+    inp = {"patchV": {"type": "patchVelocity", "patches": ["inout"], "flowAxis": "x", "normalAxis": "y"}}
+    mesh, bcs, orc, sol, W, _ = setup("naca", True, lib_path=lib_path, extra_options=dict(function=fn, inputInfo=inp))
+    sol.updateOFFields(W)
+    x = np.array([10.0, aoa])
+    one = np.array([1.0])
+    dpar = [np.cos(a), np.sin(a), 0.0]
+    dnor = [-np.sin(a), np.cos(a), 0.0]
+    # the far-field reference velocity changes with the input: keep the oracle consistent
+    orc.set_bc_value("U", 1, [10.0 * np.cos(a), 10.0 * np.sin(a), 0.0])
+    dFdx = np.zeros(2)
+    sol.calcJacTVecProduct("patchV", "patchVelocity", x, "CD", "function", one, dFdx)
+    assert np.all(dFdx == 0.0)
+    cases = {"CD": (dirv, 0.02, None), "CDa": (dpar, 0.5, None), "CLa": (dnor, 0.5, None), "CMZ": (axis, 2.0, center)}
+    for name, (d, scale, ctr) in cases.items():
+        F, Fo = sol.calcFunction(name), orc.force(W, 0, d, scale, center=ctr)
+        assert abs(F - Fo) <= tol * abs(Fo), (name, F, Fo)
+        prod = np.zeros(orc.ndof)
+        sol.calcJacTVecProduct("states", "stateVar", W, name, "function", one, prod)
+        assert rel_err(prod, orc.dforce_dw(W, 0, d, scale, center=ctr)) < tol, name
+    # d(force . dir(aoa))/d aoa[deg] at fixed states: d(par)/da = nor, d(nor)/da = -par
+    for name, d, sgn in (("CDa", dnor, 1.0), ("CLa", dpar, -1.0)):
+        sol.calcJacTVecProduct("patchV", "patchVelocity", x, name, "function", one, dFdx)
+        ref = sgn * orc.force(W, 0, d, 0.5) * np.pi / 180.0
+        assert dFdx[0] == 0.0 and abs(dFdx[1] - ref) <= tol * abs(ref), (name, dFdx, ref)
+    sol.calcJacTVecProduct("patchV", "patchVelocity", x, "CMZ", "function", one, dFdx)
+    assert np.all(dFdx == 0.0)
+    return True

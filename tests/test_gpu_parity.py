@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from tests.common import check_parity, rel_err, setup
+from tests.common import check_functions, check_parity, rel_err, setup
 
 pytestmark = pytest.mark.gpu
 
@@ -24,6 +24,10 @@ def test_force_function_and_dfdw_cuda():
     prod = np.zeros(orc.ndof)
     sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), prod)
     assert rel_err(prod, orc.dforce_dw(W, 0, dirv, 0.02)) < 1e-12
+
+
+def test_force_moment_and_direction_modes_cuda():
+    assert check_functions(None)
 
 
 def test_full_size_linearity_and_determinism_cuda():

@@ -3,7 +3,7 @@ hand-derived reverse sweep is checked on a machine without a GPU; the -m gpu tes
 checks through the CUDA library."""
 import numpy as np
 
-from tests.common import HOSTSIM, check_parity, setup, rel_err
+from tests.common import HOSTSIM, check_functions, check_parity, setup, rel_err
 
 
 def test_forward_and_reverse_parity_host_build():
@@ -22,6 +22,10 @@ def test_force_function_and_dfdw_host_build():
     prod = np.zeros(orc.ndof)
     sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), prod)
     assert rel_err(prod, orc.dforce_dw(W, 0, dirv, 0.02)) < 1e-12
+
+
+def test_force_moment_and_direction_modes_host_build():
+    assert check_functions(HOSTSIM)
 
 
 def test_dot_product_identity_host_build():
