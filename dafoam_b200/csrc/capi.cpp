@@ -277,6 +277,54 @@ int dab_pc_apply(dab_solver* s, const double* v, double* z)
     DAB_CATCH
 }
 
+int dab_set_solver_input(dab_solver* s, const char* input_name, const char* input_type, int input_size, const double* inputs,
+                         const double* seeds)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(input_type, "input_type");
+    need(inputs, "inputs");
+    (void)seeds;
+    Solver& S = s->s;
+    const std::string it(input_type);
+    if (it == "patchVelocity")
+    {
+        need(input_name, "input_name");
+        if (input_size != 2) throw Error("setSolverInput: patchVelocity takes 2 values (|U|, angle of attack)");
+        S.setPatchVelocity(input_name, inputs);
+    }
+    else if (it == "stateVar")
+    {
+        if (input_size != S.nDof()) throw Error("setSolverInput: stateVar has the wrong size");
+        S.updateOFFields(inputs);
+    }
+    else
+        throw Error("setSolverInput: inputType " + it + " is not supported (patchVelocity, stateVar)");
+    DAB_CATCH
+}
+
+int dab_solve_primal(dab_solver* s, int* fail, dab_primal_stats* stats)
+{
+    DAB_TRY
+    need(s, "solver");
+    PrimalStats st;
+    const int f = s->s.solvePrimal(st);
+    if (fail) *fail = f;
+    if (stats)
+    {
+        stats->iterations = st.iterations;
+        stats->converged = st.converged;
+        stats->p_iterations = st.pIterations;
+        stats->reserved = 0;
+        stats->max_residual = st.maxRes;
+        for (int j = 0; j < 3; j++) stats->res_u[j] = st.resU[j];
+        stats->res_p = st.resP;
+        stats->res_nutilda = st.resN;
+        stats->seconds = st.sec;
+    }
+    DAB_CATCH
+}
+
 int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats)
 {
     DAB_TRY

@@ -14,6 +14,7 @@
 #include "fwd_kernels.hpp"
 #include "rev_kernels.hpp"
 #include "krylov.hpp"
+#include "primal_kernels.hpp"
 #include "partition.hpp"
 #include "comm.hpp"
 #include <cstdlib>
@@ -32,6 +33,8 @@ namespace dab
 #endif
 template <int NF, int FEAT> struct LaunchTraits<RevB<NF, FEAT>> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
 template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
+template <int NF, int FEAT> struct LaunchTraits<UEqnAssemble<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
+template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
 #endif
 
 // optional-feature dispatch for the two heavy kernels (hex meshes: 4 variants; other meshes: the full-featured one)
@@ -243,6 +246,33 @@ struct Solver
             par.alphaU = fso.sub("relaxationFactors").sub("equations").scalarOr("U", 1.0);
         if (fso.hasSub("SIMPLE") && fso.sub("SIMPLE").wordOr("consistent", "false") == "true")
             throw Error("SIMPLEC (consistent true) is not supported in this build");
+        // primal solver controls (system/fvSolution, system/controlDict)
+        if (fso.hasSub("relaxationFactors"))
+        {
+            const Dict& rf = fso.sub("relaxationFactors");
+            if (rf.hasSub("fields")) primal.alphaP = rf.sub("fields").scalarOr("p", primal.alphaP);
+            if (rf.hasSub("equations")) primal.alphaN = rf.sub("equations").scalarOr("nuTilda", primal.alphaN);
+        }
+        if (fso.hasSub("SIMPLE")) primal.nNonOrth = (int)fso.sub("SIMPLE").scalarOr("nNonOrthogonalCorrectors", 0.0);
+        if (fso.hasSub("solvers"))
+        {
+            const Dict& sd = fso.sub("solvers");
+            auto ctl = [&](const char* name, SegControl& c) {
+                if (!sd.hasSub(name)) return;
+                c.tol = sd.sub(name).scalarOr("tolerance", c.tol);
+                c.relTol = sd.sub(name).scalarOr("relTol", c.relTol);
+                c.maxIter = (int)sd.sub(name).scalarOr("maxIter", (double)c.maxIter);
+            };
+            ctl("U", primal.cU);
+            ctl("p", primal.cP);
+            ctl("nuTilda", primal.cN);
+        }
+        if (fileExists(caseDir + "/system/controlDict"))
+        {
+            Dict cd = readDict(caseDir + "/system/controlDict");
+            const double endTime = cd.scalarOr("endTime", 1000.0), deltaT = cd.scalarOr("deltaT", 1.0), startTime = cd.scalarOr("startTime", 0.0);
+            primal.maxIters = (int)((endTime - startTime) / deltaT + 0.5);
+        }
         // boundary conditions
         const char* fn[N_FIELDS] = {"U", "p", "nuTilda", "nut"};
         for (int fi = 0; fi < N_FIELDS; fi++)
@@ -311,6 +341,16 @@ struct Solver
             if (lv != pcConLevel) { pcConLevel = lv; kry.symbolic = false; kry.pcValid = false; }
         }
         if (const JVal* s = o.get("adjPartDerivFDStep")) fdStep = s->numOr("State", fdStep);
+        primal.minResTol = o.numOr("primalMinResTol", primal.minResTol);
+        primal.minResTolDiff = o.numOr("primalMinResTolDiff", primal.minResTolDiff);
+        primal.minIters = (int)o.numOr("primalMinIters", primal.minIters);
+        primal.maxIters = (int)o.numOr("primalMaxIters", primal.maxIters); // extension: overrides controlDict endTime/deltaT
+        primal.printInterval = (int)o.numOr("printInterval", primal.printInterval);
+        if (const JVal* vb = o.get("primalVarBounds"))
+        {
+            primal.ntMin = vb->numOr("nuTildaMin", primal.ntMin);
+            primal.ntMax = vb->numOr("nuTildaMax", primal.ntMax);
+        }
         if (const JVal* fd = o.get("function"))
         {
             functions.clear();
@@ -846,6 +886,17 @@ struct Solver
         be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
     }
 
+    // ---- primal (SIMPLE) ----------------------------------------------------------------------------
+    Primal primal;
+    VecOps primalOps;
+    void primalSetup();
+    const double* primalSums(int k);
+    void primalResidual(const EqnView& e, const double* x, const double* g, double* res);
+    void primalJacobi(const EqnView& e, double* x, double* tmp, const double* g, const SegControl& ctl, double* res0);
+    void primalSgs(const EqnView& e, const double* r, double* z);
+    int primalPcg(const EqnView& e, double* x, const SegControl& ctl, double& res0);
+    int solvePrimal(PrimalStats& st);
+
     // ---- Krylov -----------------------------------------------------------------------------------
     void pcSymbolic();
     void calcPC();
@@ -860,3 +911,4 @@ struct Solver
 } // namespace dab
 
 #include "solver_krylov.hpp"
+#include "solver_primal.hpp"

@@ -1,0 +1,249 @@
+// Solver::solvePrimal -- SIMPLE iterations on the device (reference DASimpleFoam::solvePrimal,
+// src/adjoint/DASolver/DASimpleFoam/DASimpleFoam.C:123-185; loop/exit rule DASolver::loop, DASolver.C:156-228;
+// residual bookkeeping DAUtility::primalResidualControl, DAUtility.C:734-801; failure rule
+// DASolver::checkPrimalFailure).  Linear solvers: Jacobi sweeps for the (relaxed, diagonally dominant) momentum and
+// nuTilda equations, PCG + multicolour symmetric Gauss-Seidel for the pressure equation; residuals are OpenFOAM's
+// normalised L1 residuals so that primalMinResTol keeps its meaning.
+#pragma once
+
+namespace dab
+{
+
+inline void Solver::primalSetup()
+{
+    Primal& P = primal;
+    if (P.allocated) return;
+    if (comm.active()) throw Error("solvePrimal runs on one GPU in this build (the adjoint path is the multi-GPU one)");
+    const size_t nC = hm.nC, nT = hm.nCtot, mcf = hm.maxCF;
+    P.uOff.alloc(be, mcf * nC); P.uDiag.alloc(be, 3 * nC); P.uB.alloc(be, 3 * nC);
+    P.pOff.alloc(be, mcf * nC); P.pDiag.alloc(be, nC); P.pB.alloc(be, nC);
+    P.nOff.alloc(be, mcf * nC); P.nDiag.alloc(be, nC); P.nB.alloc(be, nC);
+    P.Utmp.alloc(be, 3 * nT); P.pOld.alloc(be, nT); P.ntTmp.alloc(be, nT);
+    P.red.alloc(be, 6 * nC); P.ones.alloc(be, nC);
+    P.r.alloc(be, nC); P.z.alloc(be, nT); P.d.alloc(be, nT); P.q.alloc(be, nC);
+    be.launch((int)nC, FillConst{P.ones.p, 1.0});
+    primalOps.init(be, nullptr, 8);
+    P.ops = &primalOps;
+    // greedy distance-1 colouring of the cell graph (hexahedral structured numbering: 2 colours)
+    std::vector<int32_t> colourOf(nC, -1);
+    int nCol = 0;
+    {
+        std::vector<int> mark;
+        for (size_t c = 0; c < nC; c++)
+        {
+            mark.assign(nCol + 1, 0);
+            for (size_t k = 0; k < mcf; k++)
+            {
+                const int n = hm.cellNbr[k * nC + c];
+                if (n >= 0 && n < (int)nC && colourOf[n] >= 0) mark[colourOf[n]] = 1;
+            }
+            int col = 0;
+            while (col < nCol && mark[col]) col++;
+            if (col == nCol) nCol++;
+            colourOf[c] = col;
+        }
+    }
+    std::vector<int32_t> list(nC);
+    P.colourStart.assign(nCol + 1, 0);
+    for (size_t c = 0; c < nC; c++) P.colourStart[colourOf[c] + 1]++;
+    for (int k = 0; k < nCol; k++) P.colourStart[k + 1] += P.colourStart[k];
+    {
+        std::vector<int> pos(P.colourStart.begin(), P.colourStart.end() - 1);
+        for (size_t c = 0; c < nC; c++) list[pos[colourOf[c]]++] = (int32_t)c;
+    }
+    P.dColourOf.upload(be, colourOf);
+    P.dColourList.upload(be, list);
+    P.allocated = true;
+}
+
+// sums of the rows of P.red ([k][nC]) -> host
+inline const double* Solver::primalSums(int k) { return primal.ops->dots(primal.red.p, hm.nC, k, primal.ones.p, hm.nC); }
+
+// OpenFOAM normalised residual of a segregated equation at the current x; res[j] per component
+inline void Solver::primalResidual(const EqnView& e, const double* x, const double* g, double* res)
+{
+    const int nC = hm.nC;
+    be.launch(nC, StridedCopy{x, e.nc, e.nc, nC, primal.red.p});
+    const double* s = primalSums(e.nc);
+    if (e.nc == 3)
+    {
+        EqnResidual<3> k{e, x, g, mv.V, hm.nCtot, {0, 0, 0}, primal.red.p};
+        for (int j = 0; j < 3; j++) k.xRef[j] = s[j] / (double)nC;
+        be.launch(nC, k);
+    }
+    else
+    {
+        EqnResidual<1> k{e, x, g, mv.V, hm.nCtot, {s[0] / (double)nC, 0, 0}, primal.red.p};
+        be.launch(nC, k);
+    }
+    s = primalSums(2 * e.nc);
+    for (int j = 0; j < e.nc; j++) res[j] = s[j] / (s[e.nc + j] + 1e-20);
+}
+
+// Jacobi sweeps in pairs (x -> tmp -> x); returns the initial residuals
+inline void Solver::primalJacobi(const EqnView& e, double* x, double* tmp, const double* g, const SegControl& ctl, double* res0)
+{
+    const int nC = hm.nC;
+    primalResidual(e, x, g, res0);
+    double mx0 = 0.0;
+    for (int j = 0; j < e.nc; j++) mx0 = std::max(mx0, res0[j]);
+    if (mx0 < ctl.tol) return;
+    double res[3];
+    for (int it = 0; it < ctl.maxIter; it += 4)
+    {
+        for (int rep = 0; rep < 2; rep++)
+        {
+            if (e.nc == 3)
+            {
+                be.launch(nC, JacobiSweep<3>{e, x, tmp, g, mv.V, hm.nCtot});
+                be.launch(nC, JacobiSweep<3>{e, tmp, x, g, mv.V, hm.nCtot});
+            }
+            else
+            {
+                be.launch(nC, JacobiSweep<1>{e, x, tmp, g, mv.V, hm.nCtot});
+                be.launch(nC, JacobiSweep<1>{e, tmp, x, g, mv.V, hm.nCtot});
+            }
+        }
+        primalResidual(e, x, g, res);
+        bool done = true;
+        for (int j = 0; j < e.nc; j++)
+            if (!(res[j] < ctl.tol || res[j] < ctl.relTol * res0[j])) done = false;
+        if (done) break;
+    }
+}
+
+// multicolour symmetric Gauss-Seidel preconditioner z = M^{-1} r, M = (D+L) D^{-1} (D+U)
+inline void Solver::primalSgs(const EqnView& e, const double* r, double* z)
+{
+    const Primal& P = primal;
+    const int nCol = (int)P.colourStart.size() - 1;
+    for (int k = 0; k < nCol; k++)
+        be.launch(P.colourStart[k + 1] - P.colourStart[k],
+                  SgsColour{e, P.dColourList.p + P.colourStart[k], P.dColourOf.p, k, 0, r, z});
+    for (int k = nCol - 2; k >= 0; k--)
+        be.launch(P.colourStart[k + 1] - P.colourStart[k],
+                  SgsColour{e, P.dColourList.p + P.colourStart[k], P.dColourOf.p, k, 1, r, z});
+}
+
+// PCG on the (sign-flipped, SPD) pressure equation; returns the iteration count, res0 = initial residual
+inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl, double& res0)
+{
+    Primal& P = primal;
+    const int nC = hm.nC;
+    double r1[3];
+    primalResidual(e, x, nullptr, r1);
+    res0 = r1[0];
+    if (res0 < ctl.tol) return 0;
+    // norm factor once (OpenFOAM keeps it fixed during the solve)
+    be.launch(nC, SpmvEll{e, x, P.q.p});
+    be.launch(nC, ResidualOf{e.b, P.q.p, P.r.p});
+    be.launch(nC, PcgProducts{P.r.p, P.r.p, P.r.p, P.red.p, P.red.p + nC});
+    const double sumAbs0 = primalSums(2)[1];
+    const double normFactor = sumAbs0 / res0;
+    double rzOld = 0.0;
+    int it = 0;
+    for (; it < ctl.maxIter; it++)
+    {
+        primalSgs(e, P.r.p, P.z.p);
+        be.launch(nC, PcgProducts{P.r.p, P.z.p, P.r.p, P.red.p, nullptr});
+        const double rz = primalSums(1)[0];
+        if (it == 0) be.d2d(P.d.p, P.z.p, (size_t)nC * sizeof(double));
+        else be.launch(nC, PcgUpdate2{rz / rzOld, P.z.p, P.d.p});
+        rzOld = rz;
+        be.launch(nC, SpmvEll{e, P.d.p, P.q.p});
+        be.launch(nC, PcgProducts{P.d.p, P.q.p, P.r.p, P.red.p, nullptr});
+        const double dq = primalSums(1)[0];
+        if (!(dq > 0.0)) break;
+        be.launch(nC, PcgUpdate1{rz / dq, P.d.p, P.q.p, x, P.r.p, P.red.p});
+        const double res = primalSums(1)[0] / normFactor;
+        if (res < ctl.tol || res < ctl.relTol * res0)
+        {
+            it++;
+            break;
+        }
+    }
+    return it;
+}
+
+inline int Solver::solvePrimal(PrimalStats& st)
+{
+    primalSetup();
+    Primal& P = primal;
+    const int nC = hm.nC, nT = hm.nCtot;
+    auto t0 = std::chrono::steady_clock::now();
+    EqnView eU{nC, hm.maxCF, 3, P.uOff.p, P.uDiag.p, P.uB.p, mv.cellNbr};
+    EqnView eP{nC, hm.maxCF, 1, P.pOff.p, P.pDiag.p, P.pB.p, mv.cellNbr};
+    EqnView eN{nC, hm.maxCF, 1, P.nOff.p, P.nDiag.p, P.nB.p, mv.cellNbr};
+    st = PrimalStats();
+    double maxRes = 0.0;
+    int it = 0;
+    for (it = 1; it <= P.maxIters; it++)
+    {
+        maxRes = -1e10;
+        be.d2d(P.pOld.p, dP.p, (size_t)nT * sizeof(double)); // p.storePrevIter()
+        // --- momentum predictor (UEqnSimple.H)
+        DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv);
+        DAB_LAUNCH_NFF(nC, UEqnAssemble, mv, par, sv, rv, eU);
+        primalJacobi(eU, dU.p, P.Utmp.p, rv.gP, P.cU, st.resU);
+        {
+            double s3[3] = {st.resU[0], st.resU[1], st.resU[2]};
+            std::sort(s3, s3 + 3);
+            maxRes = std::max(maxRes, s3[1]); // the median component (primalResidualControl for vectors)
+        }
+        // --- pressure corrector (pEqnSimple.H)
+        be.launch(nC, HbyAKernel{eU, sv, rv, mv.V, nT});
+        for (int no = 0; no <= P.nNonOrth; no++)
+        {
+            if (no > 0) DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad(p) of the latest p for the non-orthogonal correction
+            DAB_LAUNCH_NF(nC, PEqnAssemble, mv, par, sv, rv, eP);
+            double rp;
+            st.pIterations += primalPcg(eP, dP.p, P.cP, rp);
+            if (no == 0) st.resP = rp;
+            maxRes = std::max(maxRes, rp);
+        }
+        DAB_LAUNCH_NF(nC, PhiUpdate, mv, par, sv, rv, dPhi.p);
+        be.launch(nC, RelaxField{dP.p, P.pOld.p, P.alphaP});
+        DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad of the relaxed p
+        be.launch(nC, UCorrect{rv, dU.p, nT});
+        // --- turbulence (DASpalartAllmaras::correct)
+        if (par.turb)
+        {
+            DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv);
+            DAB_LAUNCH_NF(nC, NutEqnAssemble, mv, par, sv, rv, eN, P.alphaN);
+            double rn[3];
+            primalJacobi(eN, dNt.p, P.ntTmp.p, nullptr, P.cN, rn);
+            st.resN = rn[0];
+            maxRes = std::max(maxRes, rn[0]);
+            be.launch(nC, BoundField{dNt.p, P.ntMin, P.ntMax});
+        }
+        if (printInfo && (it % P.printInterval == 0 || it == 1))
+            fprintf(stderr, "[dab200] SIMPLE %5d  U %.3e %.3e %.3e  p %.3e  nuTilda %.3e\n", it, st.resU[0], st.resU[1], st.resU[2], st.resP, st.resN);
+        if (!(maxRes == maxRes)) break; // NaN
+        if (maxRes < P.minResTol && it > P.minIters) break;
+    }
+    st.iterations = std::min(it, P.maxIters);
+    st.maxRes = maxRes;
+    st.converged = maxRes < P.minResTol ? 1 : 0;
+    // mirror the new state into the external layout (getOFFields) and invalidate what depended on the old one
+    {
+        const size_t n = nC;
+        be.d2d(dWext.p, dU.p, 3 * n * sizeof(double));
+        be.d2d(dWext.p + 3 * n, dP.p, n * sizeof(double));
+        size_t off = 4 * n;
+        if (par.turb)
+        {
+            be.d2d(dWext.p + off, dNt.p, n * sizeof(double));
+            off += n;
+        }
+        be.d2d(dWext.p + off, dPhi.p, (size_t)hm.nF * sizeof(double));
+    }
+    be.sync();
+    recorded = false;
+    kry.pcValid = false;
+    st.sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    // DASolver::checkPrimalFailure: fail if the residual misses the tolerance by more than primalMinResTolDiff (or NaN)
+    if (!(maxRes == maxRes)) return 1;
+    return (maxRes / P.minResTol > P.minResTolDiff) ? 1 : 0;
+}
+
+} // namespace dab

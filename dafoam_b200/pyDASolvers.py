@@ -32,6 +32,12 @@ class KspStats(C.Structure):
                 ("n_matvec", C.c_int32), ("reserved", C.c_int32)]
 
 
+class PrimalStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("p_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("max_residual", C.c_double), ("res_u", C.c_double * 3), ("res_p", C.c_double), ("res_nutilda", C.c_double),
+                ("seconds", C.c_double)]
+
+
 def load_library(path=None):
     """Load libdab200.so.  `path` is only used by the test-suite to load the host-simulation build."""
     path = path or os.path.join(_HERE, "libdab200.so")
@@ -179,6 +185,20 @@ class pyDASolvers:
             parts.append(4 * nGlobalCells + cg)
         parts.append(ns * nGlobalCells + fg)
         return np.concatenate(parts)
+
+    def setSolverInput(self, inputName, inputType, inputSize, inputs, seeds=None):
+        inputs = np.ascontiguousarray(inputs, dtype=np.float64)
+        assert len(inputs) == inputSize, "invalid input array size!"
+        self._raise(self._L.dab_set_solver_input(self._h, inputName.encode(), inputType.encode(), C.c_int(inputSize), _dp(inputs), None))
+
+    def solvePrimal(self):
+        """SIMPLE iterations from the current states (reference pyDASolvers.pyx solvePrimal -> DASimpleFoam::solvePrimal).
+        Returns 0 (converged within primalMinResTolDiff of primalMinResTol) or 1; statistics in self.primalStats."""
+        fail = C.c_int(1)
+        st = PrimalStats()
+        self._raise(self._L.dab_solve_primal(self._h, C.byref(fail), C.byref(st)))
+        self.primalStats = st
+        return int(fail.value)
 
     def updateDAOption(self, pyOptions):
         self._options.update(pyOptions)

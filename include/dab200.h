@@ -52,6 +52,21 @@ typedef struct dab_ksp_stats
     int32_t reserved;
 } dab_ksp_stats;
 
+/* per-equation initial residuals of the last SIMPLE iteration (what the reference prints through
+ * DAUtility::primalResidualControl, src/adjoint/DAUtility/DAUtility.C:734-801) */
+typedef struct dab_primal_stats
+{
+    int32_t iterations;
+    int32_t converged;        /* 1: max residual < primalMinResTol */
+    int32_t p_iterations;     /* pressure-solver iterations summed over the run */
+    int32_t reserved;
+    double max_residual;      /* max over equations (median component for U) */
+    double res_u[3];
+    double res_p;
+    double res_nutilda;
+    double seconds;
+} dab_primal_stats;
+
 const char* dab_last_error(void);
 const char* dab_version(void);
 
@@ -131,6 +146,19 @@ int dab_pc_apply(dab_solver* s, const double* v, double* z);
  * (reference DASolver.C:1121-1155, DALinearEqn.C:341-437).  *fail = 0/1 with the reference's
  * success rule (relRatio > gmresTolDiff && absRatio > gmresTolDiff  =>  1). */
 int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats);
+
+/* setSolverInput(inputName, inputType, inputSize, inputs, seeds): assign an input to the solver's fields before
+ * solvePrimal / calcFunction (reference pyDASolvers.pyx:164-182, DASolver::setSolverInput -> DAInput::run;
+ * DAInputPatchVelocity.C, DAInputStateVar.C).  Types: "patchVelocity" (|U|, angle of attack [deg]) and "stateVar".
+ * `seeds` belongs to the reference's forward-mode AD and is ignored (may be NULL). */
+int dab_set_solver_input(dab_solver* s, const char* input_name, const char* input_type, int input_size, const double* inputs,
+                         const double* seeds);
+
+/* solvePrimal(): SIMPLE iterations from the current states until the largest initial residual drops below
+ * primalMinResTol or endTime is reached (reference pyDASolvers.pyx solvePrimal, DASimpleFoam.C:123-185,
+ * DASolver.C:156-228).  *fail = 0/1 with the reference's checkPrimalFailure rule (residual misses the
+ * tolerance by more than primalMinResTolDiff, or NaN).  The converged states are read with dab_get_of_fields. */
+int dab_solve_primal(dab_solver* s, int* fail, dab_primal_stats* stats);
 
 /* calcFunction(name) (reference DASolver.H calcFunction, DAFunctionForce.C:79-153) */
 int dab_calc_function(dab_solver* s, const char* name, double* value);

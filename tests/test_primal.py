@@ -1,0 +1,102 @@
+"""solvePrimal (device SIMPLE, reference DASimpleFoam::solvePrimal): the fixed point must be the root of the same R(W)
+the adjoint differentiates.  Checked on the host build (CPU suite) against the oracle: (i) the oracle's residual of the
+SIMPLE state vanishes, (ii) the state equals the oracle's own Newton-converged state, and (iii) the whole reference
+workflow solvePrimal -> solveAdjoint -> total derivative agrees with finite differences over re-converged primals."""
+import tempfile
+
+import numpy as np
+import pytest
+
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import KSP, Mat, pyDASolvers
+from oracle.pyoracle import Oracle
+from tests.common import HOSTSIM, NORM_STATES
+from tests.test_converged_primal import newton
+
+FN = {"CD": {"type": "force", "source": "patchToFace", "patches": ["walls"], "directionMode": "fixedDirection",
+             "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
+INP = {"patchV": {"type": "patchVelocity", "patches": ["inlet"], "flowAxis": "x", "normalAxis": "y"}}
+
+
+def make(lib_path, tol=1e-12):
+    mesh, bcs = cases.channel(nx=14, ny=8, nz=1), cases.default_bcs_channel()
+    d = tempfile.mkdtemp(prefix="dab_primal_")
+    cases.write_case(d, mesh, bcs)
+    opts = dict(normalizeStates=NORM_STATES, function=FN, inputInfo=INP, primalMinResTol=tol, primalMaxIters=2000,
+                adjEqnOption=dict(gmresRelTol=1e-12, gmresMaxIters=400, gmresRestart=400, pcConLevel=3))
+    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib_path)
+    return mesh, bcs, sol
+
+
+def run_fixed_point(lib_path):
+    mesh, bcs, sol = make(lib_path)
+    n = sol.getNLocalAdjointStates()
+    W0 = np.zeros(n)
+    sol.getOFFields(W0)
+    assert sol.solvePrimal() == 0
+    st = sol.primalStats
+    assert st.converged == 1 and st.max_residual < 1e-12 and 10 < st.iterations < 2000
+    W = np.zeros(n)
+    sol.getOFFields(W)
+    orc = Oracle(mesh, bcs, normalizeStates=NORM_STATES)
+    r0, r1 = np.linalg.norm(orc.residual(W0)), np.linalg.norm(orc.residual(W))
+    assert r1 < 1e-9 * r0, (r0, r1)
+    Wn = newton(orc, W0.copy(), tol=1e-9)
+    nC = mesh.n_cells
+    for name, a, b in (("U", 0, 3 * nC), ("p", 3 * nC, 4 * nC), ("nuTilda", 4 * nC, 5 * nC), ("phi", 5 * nC, n)):
+        err = np.linalg.norm(W[a:b] - Wn[a:b]) / np.linalg.norm(Wn[a:b])
+        assert err < 1e-8, (name, err)
+    # a second call starts from the converged state: only the round-off tail is left
+    assert sol.solvePrimal() == 0 and sol.primalStats.iterations <= 40
+
+
+def run_workflow(lib_path):
+    """solvePrimal -> dF/dW -> solveAdjoint -> total derivative w.r.t. (|U|, aoa), against FD of re-converged primals."""
+    mesh, bcs, sol = make(lib_path)
+    n = sol.getNLocalAdjointStates()
+    x0 = np.array([10.0, 2.0])
+
+    def F_at(x):
+        sol.setSolverInput("patchV", "patchVelocity", 2, x)
+        assert sol.solvePrimal() == 0
+        return sol.calcFunction("CD")
+
+    F0 = F_at(x0)
+    W = np.zeros(n)
+    sol.getOFFields(W)
+    one = np.array([1.0])
+    dFdW, dFdx, psi, prod = np.zeros(n), np.zeros(2), np.zeros(n), np.zeros(2)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", one, dFdW)
+    sol.calcJacTVecProduct("patchV", "patchVelocity", x0, "CD", "function", one, dFdx)
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    assert sol.solveLinearEqn(ksp, dFdW, psi) == 0
+    sol.calcJacTVecProduct("patchV", "patchVelocity", x0, "R", "residual", psi, prod)
+    total = dFdx - prod
+    fd = np.zeros(2)
+    for k, h in enumerate((1e-3, 1e-2)):
+        xp, xm = x0.copy(), x0.copy()
+        xp[k] += h
+        xm[k] -= h
+        fd[k] = (F_at(xp) - F_at(xm)) / (2 * h)
+    assert np.isfinite(F0)
+    assert np.allclose(total, fd, rtol=2e-5, atol=0.0), (total, fd)
+
+
+def test_simple_fixed_point_is_the_root_of_the_residual_host_build():
+    run_fixed_point(HOSTSIM)
+
+
+def test_primal_adjoint_workflow_matches_fd_host_build():
+    run_workflow(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_simple_fixed_point_is_the_root_of_the_residual_cuda():
+    run_fixed_point(None)
+
+
+@pytest.mark.gpu
+def test_primal_adjoint_workflow_matches_fd_cuda():
+    run_workflow(None)
