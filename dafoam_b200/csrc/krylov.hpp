@@ -355,6 +355,22 @@ struct VecOps
 #endif
         return hOut.data();
     }
+    // out[j] = V_j . w left on the device (no host synchronisation; single rank)
+    void dotsDev(const double* V, int64_t ld, int k, const double* w, int n, double* out)
+    {
+#ifndef DAB_HOSTSIM
+        multiDotPartial<<<DOT_BLOCKS, DOT_THREADS, 0, be->stream>>>(V, ld, k, w, n, partial.p);
+        multiDotFinal<<<(k + 63) / 64, 64, 0, be->stream>>>(partial.p, DOT_BLOCKS, k, out);
+#else
+        for (int j = 0; j < k; j++)
+        {
+            double s = 0.0;
+            for (int i = 0; i < n; i++) s += V[(int64_t)j * ld + i] * w[i];
+            out[j] = s;
+        }
+#endif
+        be->launches += 2;
+    }
     double norm2(const double* w, int n) { return std::sqrt(dots(w, 0, 1, w, n)[0]); }
 };
 

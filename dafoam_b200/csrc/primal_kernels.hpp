@@ -562,13 +562,30 @@ struct SgsColour
     }
 };
 
-struct PcgUpdate1 // x += a d; r -= a q; out = |r|
+// PCG scalars live on the device (no host round trip per iteration): S[0] rz, S[1] rzOld, S[2] dq, S[3] sum|r|, S[4] alpha, S[5] beta
+struct PcgScalarBeta
 {
-    double a;
+    double* S;
+    int first;
+    DAB_HD void operator()(int) const
+    {
+        S[5] = first ? 0.0 : S[0] / S[1];
+        S[1] = S[0];
+    }
+};
+struct PcgScalarAlpha
+{
+    double* S;
+    DAB_HD void operator()(int) const { S[4] = S[2] > 0.0 ? S[0] / S[2] : 0.0; }
+};
+struct PcgUpdate1 // x += alpha d; r -= alpha q; absr = |r|
+{
+    const double* S;
     const double *d, *q;
     double *x, *r, *absr;
     DAB_HD void operator()(int c) const
     {
+        const double a = S[4];
         x[c] += a * d[c];
         const double v = r[c] - a * q[c];
         r[c] = v;
@@ -577,10 +594,111 @@ struct PcgUpdate1 // x += a d; r -= a q; out = |r|
 };
 struct PcgUpdate2 // d = z + beta d
 {
-    double beta;
+    const double* S;
     const double* z;
     double* d;
-    DAB_HD void operator()(int c) const { d[c] = z[c] + beta * d[c]; }
+    DAB_HD void operator()(int c) const
+    {
+        const double beta = S[5];
+        d[c] = beta == 0.0 ? z[c] : z[c] + beta * d[c];
+    }
+};
+struct SpmvEllProd // y = A x, prod = x*y
+{
+    EqnView e;
+    const double* x;
+    double *y, *prod;
+    DAB_HD void operator()(int c) const
+    {
+        const int nC = e.nC;
+        double acc = e.diag[c] * x[c];
+        for (int k = 0; k < e.maxCF; k++)
+        {
+            const int n = e.cellNbr[(size_t)k * nC + c];
+            if (n >= 0) acc += e.off[(size_t)k * nC + c] * x[n];
+        }
+        y[c] = acc;
+        prod[c] = acc * x[c];
+    }
+};
+
+// ---- aggregation coarse space of the pressure preconditioner: z += P (P^T A P)^-1 P^T r ------------------------
+// Galerkin operator, one thread per aggregate (the thread owns its row: deterministic, no atomics)
+struct CoarseGalerkin
+{
+    EqnView e;
+    const int32_t* aggOf;
+    const int32_t* cells;    // cells sorted by aggregate
+    const int32_t* aggStart; // [nAgg+1]
+    int nAgg;
+    double* Ac;              // [nAgg][nAgg], zeroed
+    DAB_HD void operator()(int a) const
+    {
+        const int nC = e.nC;
+        double* row = Ac + (size_t)a * nAgg;
+        for (int i = aggStart[a]; i < aggStart[a + 1]; i++)
+        {
+            const int c = cells[i];
+            row[a] += e.diag[c];
+            for (int k = 0; k < e.maxCF; k++)
+            {
+                const int n = e.cellNbr[(size_t)k * nC + c];
+                if (n >= 0 && n < nC) row[aggOf[n]] += e.off[(size_t)k * nC + c];
+            }
+        }
+    }
+};
+// in-place Gauss-Jordan inversion without pivoting (symmetric positive definite operator), step k in two kernels
+struct GjStep1 // save column k, scale row k
+{
+    double* A;
+    double* colk;
+    int n, k;
+    DAB_HD void operator()(int j) const
+    {
+        const double p = A[(size_t)k * n + k];
+        colk[j] = A[(size_t)j * n + k];
+        if (j != k) A[(size_t)k * n + j] /= p;
+    }
+};
+struct GjStep2 // eliminate: thread per element
+{
+    double* A;
+    const double* colk;
+    int n, k;
+    DAB_HD void operator()(int t) const
+    {
+        const int i = t / n, j = t - i * n;
+        const double p = colk[k];
+        if (i == k)
+        {
+            if (j == k) A[(size_t)k * n + k] = 1.0 / p;
+            return;
+        }
+        const double f = colk[i];
+        if (j == k) A[(size_t)i * n + k] = -f / p;
+        else A[(size_t)i * n + j] -= f * A[(size_t)k * n + j];
+    }
+};
+struct CoarseApply // yc = Ainv rc (Ainv symmetric: column access is coalesced)
+{
+    const double* Ainv;
+    const double* rc;
+    int n;
+    double* yc;
+    DAB_HD void operator()(int i) const
+    {
+        double s = 0.0;
+        for (int j = 0; j < n; j++) s += Ainv[(size_t)j * n + i] * rc[j];
+        yc[i] = s;
+    }
+};
+struct CoarseProlongAdd // z[c] += yc[agg[c]]
+{
+    const double* yc;
+    const int32_t* aggOf;
+    double* z;
+    DAB_HD void operator()(int c) const { z[c] += yc[aggOf[c]]; }
 };
 
 struct PcgProducts // out0 = r*z (or d*q), out1 = |r|
@@ -633,6 +751,11 @@ struct Primal
     DevBuf<double> Utmp, pOld, ntTmp, red, ones, r, z, d, q;
     DevBuf<int32_t> dColourOf, dColourList;
     std::vector<int> colourStart; // [nColours+1] into dColourList
+    // pressure coarse space
+    int nAgg = -1, coarseRefresh = 10, nChunks = 0; // nAgg < 0: choose from the mesh size; 0: off
+    bool coarseValid = false;
+    DevBuf<int32_t> dAggOf, dAggCells, dAggStart, dChunkStart, dAggChunkOff;
+    DevBuf<double> dAc, dColk, dRc, dYc, dPartial, dS;
     VecOps* ops = nullptr;
 };
 

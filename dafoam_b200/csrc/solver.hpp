@@ -346,6 +346,11 @@ struct Solver
         primal.minIters = (int)o.numOr("primalMinIters", primal.minIters);
         primal.maxIters = (int)o.numOr("primalMaxIters", primal.maxIters); // extension: overrides controlDict endTime/deltaT
         primal.printInterval = (int)o.numOr("printInterval", primal.printInterval);
+        if (const JVal* ps = o.get("primalSolver")) // extension: controls of the device pressure solver
+        {
+            primal.nAgg = (int)ps->numOr("coarseAggregates", primal.nAgg);
+            primal.coarseRefresh = std::max(1, (int)ps->numOr("coarseRefresh", primal.coarseRefresh));
+        }
         if (const JVal* vb = o.get("primalVarBounds"))
         {
             primal.ntMin = vb->numOr("nuTildaMin", primal.ntMin);
@@ -893,7 +898,9 @@ struct Solver
     const double* primalSums(int k);
     void primalResidual(const EqnView& e, const double* x, const double* g, double* res);
     void primalJacobi(const EqnView& e, double* x, double* tmp, const double* g, const SegControl& ctl, double* res0);
-    void primalSgs(const EqnView& e, const double* r, double* z);
+    void primalCoarseSetup();
+    void primalCoarseRefresh(const EqnView& e);
+    void primalPrecond(const EqnView& e, const double* r, double* z);
     int primalPcg(const EqnView& e, double* x, const SegControl& ctl, double& res0);
     int solvePrimal(PrimalStats& st);
 

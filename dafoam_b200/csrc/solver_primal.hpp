@@ -53,6 +53,8 @@ inline void Solver::primalSetup()
     }
     P.dColourOf.upload(be, colourOf);
     P.dColourList.upload(be, list);
+    P.dS.alloc(be, 8);
+    primalCoarseSetup();
     P.allocated = true;
 }
 
@@ -112,8 +114,64 @@ inline void Solver::primalJacobi(const EqnView& e, double* x, double* tmp, const
     }
 }
 
-// multicolour symmetric Gauss-Seidel preconditioner z = M^{-1} r, M = (D+L) D^{-1} (D+U)
-inline void Solver::primalSgs(const EqnView& e, const double* r, double* z)
+// aggregates of the pressure coarse space: recursive coordinate bisection of the cell centres (compact boxes)
+inline void Solver::primalCoarseSetup()
+{
+    Primal& P = primal;
+    const int nC = hm.nC;
+    if (P.nAgg < 0) P.nAgg = std::min(1024, nC / 64);
+    if (P.nAgg < 2)
+    {
+        P.nAgg = 0;
+        return;
+    }
+    std::vector<int> part;
+    rcbPartition(hm, P.nAgg, part);
+    std::vector<int32_t> aggOf(part.begin(), part.end()), cnt(P.nAgg + 1, 0), cells(nC);
+    for (int c = 0; c < nC; c++) cnt[aggOf[c] + 1]++;
+    for (int a = 0; a < P.nAgg; a++) cnt[a + 1] += cnt[a];
+    {
+        std::vector<int32_t> pos(cnt.begin(), cnt.end() - 1);
+        for (int c = 0; c < nC; c++) cells[pos[aggOf[c]]++] = c;
+    }
+    std::vector<int32_t> chunkStart, aggChunkOff(1, 0);
+    for (int a = 0; a < P.nAgg; a++)
+    {
+        for (int i = cnt[a]; i < cnt[a + 1]; i += 32) chunkStart.push_back(i);
+        aggChunkOff.push_back((int32_t)chunkStart.size());
+    }
+    chunkStart.push_back(nC);
+    P.nChunks = (int)chunkStart.size() - 1;
+    P.dAggOf.upload(be, aggOf);
+    P.dAggCells.upload(be, cells);
+    P.dAggStart.upload(be, cnt);
+    P.dChunkStart.upload(be, chunkStart);
+    P.dAggChunkOff.upload(be, aggChunkOff);
+    P.dAc.alloc(be, (size_t)P.nAgg * P.nAgg);
+    P.dColk.alloc(be, P.nAgg);
+    P.dRc.alloc(be, P.nAgg);
+    P.dYc.alloc(be, P.nAgg);
+    P.dPartial.alloc(be, P.nChunks + 1);
+}
+
+// Galerkin coarse operator of the current pressure matrix and its inverse (device, Gauss-Jordan)
+inline void Solver::primalCoarseRefresh(const EqnView& e)
+{
+    Primal& P = primal;
+    if (P.nAgg == 0) return;
+    const int n = P.nAgg;
+    be.zero(P.dAc.p, (size_t)n * n * sizeof(double));
+    be.launch(n, CoarseGalerkin{e, P.dAggOf.p, P.dAggCells.p, P.dAggStart.p, n, P.dAc.p});
+    for (int k = 0; k < n; k++)
+    {
+        be.launch(n, GjStep1{P.dAc.p, P.dColk.p, n, k});
+        be.launch(n * n, GjStep2{P.dAc.p, P.dColk.p, n, k});
+    }
+    P.coarseValid = true;
+}
+
+// z = M^{-1} r: multicolour symmetric Gauss-Seidel, M = (D+L) D^{-1} (D+U), plus the additive coarse correction
+inline void Solver::primalPrecond(const EqnView& e, const double* r, double* z)
 {
     const Primal& P = primal;
     const int nCol = (int)P.colourStart.size() - 1;
@@ -123,9 +181,17 @@ inline void Solver::primalSgs(const EqnView& e, const double* r, double* z)
     for (int k = nCol - 2; k >= 0; k--)
         be.launch(P.colourStart[k + 1] - P.colourStart[k],
                   SgsColour{e, P.dColourList.p + P.colourStart[k], P.dColourOf.p, k, 1, r, z});
+    if (P.nAgg > 0 && P.coarseValid)
+    {
+        be.launch(P.nChunks, CoarseRestrict1{r, P.dAggCells.p, P.dChunkStart.p, P.dPartial.p});
+        be.launch(P.nAgg, CoarseRestrict2{P.dPartial.p, P.dAggChunkOff.p, P.dRc.p});
+        be.launch(P.nAgg, CoarseApply{P.dAc.p, P.dRc.p, P.nAgg, P.dYc.p});
+        be.launch(hm.nC, CoarseProlongAdd{P.dYc.p, P.dAggOf.p, z});
+    }
 }
 
-// PCG on the (sign-flipped, SPD) pressure equation; returns the iteration count, res0 = initial residual
+// PCG on the (sign-flipped, SPD) pressure equation with the scalars kept on the device; the host only looks at the
+// residual every few iterations.  Returns the iteration count, res0 = initial (OpenFOAM-normalised) residual
 inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl, double& res0)
 {
     Primal& P = primal;
@@ -140,26 +206,29 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
     be.launch(nC, PcgProducts{P.r.p, P.r.p, P.r.p, P.red.p, P.red.p + nC});
     const double sumAbs0 = primalSums(2)[1];
     const double normFactor = sumAbs0 / res0;
-    double rzOld = 0.0;
+    double* S = P.dS.p;
+    const int checkEvery = 4;
     int it = 0;
-    for (; it < ctl.maxIter; it++)
+    while (it < ctl.maxIter)
     {
-        primalSgs(e, P.r.p, P.z.p);
+        primalPrecond(e, P.r.p, P.z.p);
         be.launch(nC, PcgProducts{P.r.p, P.z.p, P.r.p, P.red.p, nullptr});
-        const double rz = primalSums(1)[0];
-        if (it == 0) be.d2d(P.d.p, P.z.p, (size_t)nC * sizeof(double));
-        else be.launch(nC, PcgUpdate2{rz / rzOld, P.z.p, P.d.p});
-        rzOld = rz;
-        be.launch(nC, SpmvEll{e, P.d.p, P.q.p});
-        be.launch(nC, PcgProducts{P.d.p, P.q.p, P.r.p, P.red.p, nullptr});
-        const double dq = primalSums(1)[0];
-        if (!(dq > 0.0)) break;
-        be.launch(nC, PcgUpdate1{rz / dq, P.d.p, P.q.p, x, P.r.p, P.red.p});
-        const double res = primalSums(1)[0] / normFactor;
-        if (res < ctl.tol || res < ctl.relTol * res0)
+        P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 0);
+        be.launch(1, PcgScalarBeta{S, it == 0 ? 1 : 0});
+        be.launch(nC, PcgUpdate2{S, P.z.p, P.d.p});
+        be.launch(nC, SpmvEllProd{e, P.d.p, P.q.p, P.red.p});
+        P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 2);
+        be.launch(1, PcgScalarAlpha{S});
+        be.launch(nC, PcgUpdate1{S, P.d.p, P.q.p, x, P.r.p, P.red.p});
+        P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 3);
+        it++;
+        if (it % checkEvery == 0 || it == ctl.maxIter)
         {
-            it++;
-            break;
+            double sumAbs;
+            be.d2h(&sumAbs, S + 3, sizeof(double));
+            const double res = sumAbs / normFactor;
+            if (!(res == res)) throw Error("pressure solver diverged (NaN)");
+            if (res < ctl.tol || res < ctl.relTol * res0) break;
         }
     }
     return it;
@@ -196,6 +265,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
         {
             if (no > 0) DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad(p) of the latest p for the non-orthogonal correction
             DAB_LAUNCH_NF(nC, PEqnAssemble, mv, par, sv, rv, eP);
+            if (no == 0 && (it == 1 || (it - 1) % P.coarseRefresh == 0)) primalCoarseRefresh(eP);
             double rp;
             st.pIterations += primalPcg(eP, dP.p, P.cP, rp);
             if (no == 0) st.resP = rp;
