@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--pc-level", type=int, default=3)
     ap.add_argument("--coarse", type=int, default=1000)
     ap.add_argument("--max-iters", type=int, default=3000)
+    ap.add_argument("--primal-iters", type=int, default=0,
+                    help="run that many SIMPLE iterations (solvePrimal on the GPU) from the synthetic state before the adjoint legs (1 GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -224,7 +226,7 @@ def main():
     case_dir = shared[0]
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
-    opts = dict(normalizeStates=NORM_STATES, function=fn,
+    opts = dict(normalizeStates=NORM_STATES, function=fn, primalMaxIters=max(args.primal_iters, 1), primalMinResTol=1e-8, printInterval=100,
                 adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level, coarseAggregates=args.coarse))
     sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
     n = sol.getNLocalAdjointStates()
@@ -250,6 +252,15 @@ def main():
         del Wg
     sol.updateOFFields(W)
     t_setup = time.time() - t_setup
+    primal = None
+    if args.primal_iters > 0 and world == 1:
+        # the step before the path (solve_nonlinear): SIMPLE iterations on the device, then the adjoint at that state
+        pfail = sol.solvePrimal()
+        ps = sol.primalStats
+        sol.getOFFields(W)
+        primal = {"iterations": ps.iterations, "seconds": ps.seconds, "max_residual": ps.max_residual, "converged": int(ps.converged),
+                  "fail": pfail, "p_iterations": ps.p_iterations, "ms_per_iteration": 1e3 * ps.seconds / max(ps.iterations, 1),
+                  "CD": sol.calcFunction("CD")}
 
     # pinned host buffers for the end-to-end (host-buffer) leg
     psi_h = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -353,6 +364,7 @@ def main():
                      "kernels_ms": per_kernel, "forward_R_ms": ms_fwd,
                      "note": "one product = RevA+RevB+RevC; achieved = algorithmic bytes of the product / its device time"},
         "adjoint_solve": adjoint,
+        "primal_solve": primal,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
