@@ -80,20 +80,36 @@ struct FwdA
     }
 };
 
-// SA cell-local source terms: P = -Cb2/sigma |grad nt|^2 - Cb1 Stilda nt + Cw1 fw nt^2 / y^2
-// (returned per unit volume).  gU: d_i U_j at [j*3+i].
-DAB_HD double saSource(double nt, double nu, double y, const double* gU, const double* gN)
+// Stilda of the SA model.  Standard (DASpalartAllmaras.C:144-157): max(Omega + fv2 nt/(kappa y)^2, Cs Omega) with
+// fv2 = 1 - chi/(1 + chi fv1); fv3 variant (DASpalartAllmarasFv3.C:158-175, 452-456): fv3 Omega + fv2 nt/(kappa y)^2
+// with fv2 = (1 + chi/Cv2)^-3, fv3 = (1 + chi fv1)(1/Cv2)(3(1 + chi/Cv2) + (chi/Cv2)^2)/(1 + chi/Cv2)^3, no clip.
+DAB_HD double saStilda(double nt, double nu, double y, const double* gU, int fv3)
 {
     const double chi = nt / nu;
     const double fv1 = fv1f(chi);
-    const double fv2 = 1.0 - chi / (1.0 + chi * fv1);
     const double w01 = 0.5 * (gU[1 * 3 + 0] - gU[0 * 3 + 1]);
     const double w02 = 0.5 * (gU[2 * 3 + 0] - gU[0 * 3 + 2]);
     const double w12 = 0.5 * (gU[2 * 3 + 1] - gU[1 * 3 + 2]);
     const double Omega = sqrt(2.0) * sqrt(2.0 * (w01 * w01 + w02 * w02 + w12 * w12));
     const double ky2 = (SA::kappa * y) * (SA::kappa * y);
+    if (fv3)
+    {
+        const double t = 1.0 + chi / SA::Cv2, t3 = t * t * t;
+        const double fv2 = 1.0 / t3;
+        const double f3 = (1.0 + chi * fv1) * (1.0 / SA::Cv2) * (3.0 * t + (chi / SA::Cv2) * (chi / SA::Cv2)) / t3;
+        return f3 * Omega + fv2 * nt / ky2;
+    }
+    const double fv2 = 1.0 - chi / (1.0 + chi * fv1);
     const double S1 = Omega + fv2 * nt / ky2, S2 = SA::Cs * Omega;
-    const double St = S1 > S2 ? S1 : S2;
+    return S1 > S2 ? S1 : S2;
+}
+
+// SA cell-local source terms: P = -Cb2/sigma |grad nt|^2 - Cb1 Stilda nt + Cw1 fw nt^2 / y^2
+// (returned per unit volume).  gU: d_i U_j at [j*3+i].
+DAB_HD double saSource(double nt, double nu, double y, const double* gU, const double* gN, int fv3)
+{
+    const double St = saStilda(nt, nu, y, gU, fv3);
+    const double ky2 = (SA::kappa * y) * (SA::kappa * y);
     const double Sm = St > 1e-15 ? St : 1e-15;
     double rr = nt / (Sm * ky2);
     rr = rr < 10.0 ? rr : 10.0;
@@ -299,7 +315,7 @@ struct FwdB
         }
         if (q.turb)
         {
-            const double src = saSource(ntc, q.nu, m.yWall[c], gUc, gNc);
+            const double src = saSource(ntc, q.nu, m.yWall[c], gUc, gNc, q.saFv3);
             R[4 * (size_t)nC + c] = (NV * iV + src) * (q.nrNut ? 1.0 : V);
         }
     }

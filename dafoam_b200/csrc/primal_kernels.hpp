@@ -483,15 +483,8 @@ struct NutEqnAssemble
         }
         const double V = m.V[c], y = m.yWall[c];
         // cell-local sources: the destruction term is implicit (fvm::Sp), the rest explicit
-        const double P = saSource(ntc, q.nu, y, gUc, gNc); // -Cb2/sigma|grad nt|^2 - Cb1 St nt + Cw1 fw nt^2/y^2
-        const double chi = ntc / q.nu;
-        const double fv1 = fv1f(chi);
-        const double fv2 = 1.0 - chi / (1.0 + chi * fv1);
-        const double w01 = 0.5 * (gUc[1 * 3 + 0] - gUc[0 * 3 + 1]), w02 = 0.5 * (gUc[2 * 3 + 0] - gUc[0 * 3 + 2]), w12 = 0.5 * (gUc[2 * 3 + 1] - gUc[1 * 3 + 2]);
-        const double Omega = sqrt(2.0) * sqrt(2.0 * (w01 * w01 + w02 * w02 + w12 * w12));
-        const double ky2 = (SA::kappa * y) * (SA::kappa * y);
-        const double S1 = Omega + fv2 * ntc / ky2, S2 = SA::Cs * Omega;
-        const double St = S1 > S2 ? S1 : S2;
+        const double P = saSource(ntc, q.nu, y, gUc, gNc, q.saFv3); // -Cb2/sigma|grad nt|^2 - Cb1 St nt + Cw1 fw nt^2/y^2
+        const double St = saStilda(ntc, q.nu, y, gUc, q.saFv3);
         const double mg2 = gNc[0] * gNc[0] + gNc[1] * gNc[1] + gNc[2] * gNc[2];
         const double expl = -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * ntc; // explicit part of P
         const double sp = ntc != 0.0 ? (P - expl) / ntc : 0.0;                  // Cw1 fw nt / y^2

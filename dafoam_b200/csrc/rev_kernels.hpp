@@ -26,7 +26,7 @@ namespace dab
 DAB_HD double sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
 
 // adjoint of saSource with seed z: accumulates into ntb, gUb[9], gNb[3]
-DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const double* gN, double z, double& ntb, double* gUb, double* gNb)
+DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const double* gN, double z, double& ntb, double* gUb, double* gNb, int fv3)
 {
     const double chi = nt / nu;
     const double c3 = chi * chi * chi, den1 = c3 + SA::Cv1c;
@@ -38,8 +38,13 @@ DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const 
     const double sQ = sqrt(Q);
     const double Omega = 2.0 * sQ;
     const double ky2 = (SA::kappa * y) * (SA::kappa * y);
-    const double S1 = Omega + fv2 * nt / ky2, S2 = SA::Cs * Omega;
-    const bool b1 = S1 > S2;
+    // fv3 variant: St = f3*Omega + f2v*nt/ky2 (no clip)
+    const double t = 1.0 + chi / SA::Cv2, t3 = t * t * t, c2 = chi / SA::Cv2;
+    const double f2v = 1.0 / t3;
+    const double Bq = (3.0 * t + c2 * c2) / t3;
+    const double f3 = den * Bq / SA::Cv2; // den = 1 + chi*fv1
+    const double S1 = fv3 ? f3 * Omega + f2v * nt / ky2 : Omega + fv2 * nt / ky2, S2 = SA::Cs * Omega;
+    const bool b1 = fv3 ? true : S1 > S2;
     const double St = b1 ? S1 : S2;
     const bool bS = St > 1e-15;
     const double Sm = bS ? St : 1e-15;
@@ -63,7 +68,19 @@ DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const 
     const double Smb = -rr0b * nt / (Sm * Sm * ky2);
     if (bS) Stb += Smb;
     double Omegab = 0.0;
-    if (b1)
+    if (fv3)
+    {
+        Omegab += f3 * Stb;
+        ntb += Stb * f2v / ky2;
+        // d f2v/d chi = -3 t^-4/Cv2;  d f3/d chi = [(fv1 + chi fv1') Bq + den dBq/dchi]/Cv2, dBq/dt = -(t^2 + 2t + 3)/t^4
+        const double dfv1 = 3.0 * chi * chi * SA::Cv1c / (den1 * den1);
+        const double df2v = -3.0 / (t3 * t * SA::Cv2);
+        const double dBq = -(t * t + 2.0 * t + 3.0) / (t3 * t) / SA::Cv2;
+        const double df3 = ((fv1 + chi * dfv1) * Bq + den * dBq) / SA::Cv2;
+        const double chib = Stb * (df3 * Omega + df2v * nt / ky2);
+        ntb += chib / nu;
+    }
+    else if (b1)
     {
         Omegab += Stb;
         const double fv2b = Stb * nt / ky2;
@@ -471,7 +488,7 @@ struct RevB
             else if (fr.n >= nC)
                 y[offPhi + f] = 0.0; // cut face whose phi belongs to the neighbouring rank
         }
-        if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb);
+        if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb, q.saFv3);
         for (int j = 0; j < 3; j++) a.U2[(size_t)j * nC + c] = U2[j];
         if ((FEAT & 4) && a.bcRefb)
             for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += refb[j];

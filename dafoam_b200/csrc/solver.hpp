@@ -223,8 +223,9 @@ struct Solver
             if (tu.hasSub("RAS")) ras = tu.sub("RAS").wordOr("RASModel", "dummy");
         }
         if (ras == "SpalartAllmaras") par.turb = 1;
+        else if (ras == "SpalartAllmarasFv3") { par.turb = 1; par.saFv3 = 1; }
         else if (ras == "dummy" || ras == "dummyTurbulenceModel" || ras == "laminar") par.turb = 0;
-        else throw Error("RASModel " + ras + " is not supported (SpalartAllmaras, dummy)");
+        else throw Error("RASModel " + ras + " is not supported (SpalartAllmaras, SpalartAllmarasFv3, dummy)");
         Dict fs = readDict(caseDir + "/system/fvSchemes");
         auto scheme = [&](const std::string& key) {
             std::string v = fs.sub("divSchemes").joined(key);

@@ -35,6 +35,7 @@ struct Params
     double nu, alphaU;
     double sU, sP, sNut, sPhi;           // normalizeStates
     int turb, divU, divNut;              // turb: 0 laminar (dummyTurbulenceModel), 1 SpalartAllmaras
+    int saFv3;                           // 1: SpalartAllmarasFv3 production term (DASpalartAllmarasFv3.C:158-175, 452-456)
     int nrU, nrP, nrNut, nrPhi;          // residual listed in normalizeResiduals
     int constrainHbyA;
     int bcKind[N_FIELDS][MAXP];
@@ -121,6 +122,7 @@ struct SA
     static constexpr double Cw1 = Cb1 / (kappa * kappa) + (1.0 + Cb2) / sigma;
     static constexpr double Cv1c = Cv1 * Cv1 * Cv1;
     static constexpr double Cw3p6 = 64.0;
+    static constexpr double Cv2 = 5.0; // fv3 variant
 };
 
 DAB_HD double fv1f(double chi)

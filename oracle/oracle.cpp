@@ -94,7 +94,7 @@ struct Params
 {
     double nu;
     double alphaU;    // momentum relaxation factor (fvSolution relaxationFactors.equations.U)
-    int turb;         // 0: dummyTurbulenceModel (laminar, no nuTilda state), 1: SpalartAllmaras
+    int turb;         // 0: dummyTurbulenceModel (laminar, no nuTilda state), 1: SpalartAllmaras, 2: SpalartAllmarasFv3
     int divU, divNut; // DivScheme for div(phi,U), div(phi,nuTilda)
     double sU, sP, sNut, sPhi; // normalizeStates
     int nrU, nrP, nrNut, nrPhi; // 1 = residual name listed in normalizeResiduals
@@ -847,7 +847,20 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
               w12 = 0.5 * (GU(1, 2, c) - GU(2, 1, c));
             T Omega = std::sqrt(2.0) * sqrt(2.0 * (w01 * w01 + w02 * w02 + w12 * w12));
             const double ky2 = (sa.kappa * cs.yWall[c]) * (sa.kappa * cs.yWall[c]);
-            T Stilda = max(Omega + fv2 * nt[c] / ky2, sa.Cs * Omega);
+            T Stilda;
+            if (par.turb == 2)
+            {
+                // DASpalartAllmarasFv3.C:158-175, 452-456: fv2 = (1 + chi/Cv2)^-3, fv3, no Cs clip
+                const double Cv2 = 5.0;
+                T tq = 1.0 + chi / Cv2;
+                T t3 = tq * tq * tq;
+                T f2 = 1.0 / t3;
+                T cb = chi / Cv2;
+                T f3 = (1.0 + chi * fv1) * (1.0 / Cv2) * (3.0 * tq + cb * cb) / t3;
+                Stilda = f3 * Omega + f2 * nt[c] / ky2;
+            }
+            else
+                Stilda = max(Omega + fv2 * nt[c] / ky2, sa.Cs * Omega);
             T r = min(nt[c] / (max(Stilda, T(1e-15)) * ky2), T(10.0));
             T r2 = r * r;
             T gg = r + sa.Cw2 * (r2 * r2 * r2 - r);

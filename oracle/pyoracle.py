@@ -72,7 +72,7 @@ def bc_tables(mesh, bcs):
 class Oracle:
     def __init__(self, mesh, bcs, nu=1.5e-5, alphaU=0.7, divU="linearUpwind", divNut="upwind",
                  normalizeStates=None, normalizeResiduals=("URes", "pRes", "nuTildaRes", "phiRes"),
-                 constrainHbyA=True, yWall=None):
+                 constrainHbyA=True, yWall=None, rasModel="SpalartAllmaras"):
         L = lib()
         self.mesh = mesh
         self.turb = "nuTilda" in bcs
@@ -87,7 +87,7 @@ class Oracle:
         psize = np.array([p["size"] for p in mesh.patches], dtype=np.int32)
         pgeom = np.array([GEOM_KIND.get(p["type"], 0) for p in mesh.patches], dtype=np.int32)
         dpar = np.array([nu, alphaU, ns["U"], ns["p"], ns["nuTilda"], ns["phi"]], dtype=np.float64)
-        ipar = np.array([int(self.turb), DIV_SCHEME[divU], DIV_SCHEME[divNut],
+        ipar = np.array([int(self.turb) * (2 if rasModel == "SpalartAllmarasFv3" else 1), DIV_SCHEME[divU], DIV_SCHEME[divNut],
                          int("URes" in normalizeResiduals), int("pRes" in normalizeResiduals),
                          int("nuTildaRes" in normalizeResiduals), int("phiRes" in normalizeResiduals),
                          int(constrainHbyA)], dtype=np.int32)

@@ -29,15 +29,15 @@ def make_bcs(kind, turbulent):
 
 
 def setup(kind="naca", turbulent=True, divU="linearUpwind", nk=2, nres=ALL_RES, lib_path=None, scale=1, binary=False,
-          extra_options=None, with_oracle=True):
+          extra_options=None, with_oracle=True, ras_model="SpalartAllmaras"):
     mesh = make_mesh(kind, nk, scale)
     bcs = make_bcs(kind, turbulent)
     d = tempfile.mkdtemp(prefix="dab_case_")
     div_u = "bounded Gauss %s%s" % (divU, " grad(U)" if divU.startswith("linearUpwind") else "")
-    cases.write_case(d, mesh, bcs, binary=binary, div_u=div_u)
+    cases.write_case(d, mesh, bcs, binary=binary, div_u=div_u, **({} if ras_model == "SpalartAllmaras" else dict(ras_model=ras_model)))
     opts = dict(normalizeStates=NORM_STATES, normalizeResiduals=list(nres))
     opts.update(extra_options or {})
-    orc = Oracle(mesh, bcs, normalizeStates=NORM_STATES, divU=divU, normalizeResiduals=nres) if with_oracle else None
+    orc = Oracle(mesh, bcs, normalizeStates=NORM_STATES, divU=divU, normalizeResiduals=nres, rasModel=ras_model) if with_oracle else None
     sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib_path)
     if orc is not None:
         W = synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), turbulent=turbulent)
@@ -72,6 +72,8 @@ CONFIGS = [
     ("naca", True, "linearUpwindV", 2, ALL_RES),   # the div(phi,U) scheme of the reference's NACA0012 tutorial cases
     ("channel", True, "linearUpwindV", 1, ALL_RES),
     ("nacawf", True, "linearUpwindV", 1, ALL_RES),  # Spalding wall function (Newton solve per wall face)
+    ("naca", True, "linearUpwindV", 1, ALL_RES, "SpalartAllmarasFv3"),  # fv3 production term (the reference's compressible tests use it)
+    ("channel", True, "linearUpwind", 2, ALL_RES, "SpalartAllmarasFv3"),
     ("prism", True, "linearUpwind", 1, ALL_RES),    # triangular prisms: 5 faces per cell, triangles + quads
 ]
 
@@ -79,8 +81,10 @@ CONFIGS = [
 def check_parity(lib_path, tol=1e-10):
     """R(W), dRdW^T psi, force and dF/dW of the engine vs the oracle on every configuration."""
     worst = 0.0
-    for kind, turb, divU, nk, nres in CONFIGS:
-        mesh, bcs, orc, sol, W, _ = setup(kind, turb, divU, nk, nres, lib_path)
+    for cfg in CONFIGS:
+        kind, turb, divU, nk, nres = cfg[:5]
+        ras = cfg[5] if len(cfg) > 5 else "SpalartAllmaras"
+        mesh, bcs, orc, sol, W, _ = setup(kind, turb, divU, nk, nres, lib_path, ras_model=ras)
         assert sol.getNLocalAdjointStates() == orc.ndof
         sol.updateOFFields(W)
         for isPC in (0, 1):
