@@ -146,6 +146,15 @@ int dab_get_of_mesh_points(dab_solver* s, double* points)
     DAB_CATCH
 }
 
+int dab_update_of_mesh(dab_solver* s, const double* points)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(points, "points");
+    s->s.updateMesh(points);
+    DAB_CATCH
+}
+
 int dab_get_of_field(dab_solver* s, const char* name, const char* type, double* field)
 {
     DAB_TRY
@@ -202,7 +211,25 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
         else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
         return 0;
     }
-    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar, patchVelocity)");
+    if (it == "volCoord")
+    {
+        // daInput->run: assign the point coordinates (DAInputVolCoord.C:35-70), then the transposed product
+        if (input)
+        {
+            bool same = true;
+            for (size_t i = 0; i < S.hm.points.size() && same; i++) same = (input[i] == S.hm.points[i]);
+            if (!same) S.updateMesh(input);
+        }
+        if (ot == "residual") S.volCoordProduct(seed, nullptr, 1.0, product);
+        else if (ot == "function")
+        {
+            need(output_name, "output_name");
+            S.volCoordProduct(nullptr, &S.findFunction(output_name), seed[0], product);
+        }
+        else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
+        return 0;
+    }
+    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar, patchVelocity, volCoord)");
     // daInput->run(inputList): assign the input to the OpenFOAM fields (DAInputStateVar.C:35-140)
     if (input) S.updateOFFields(input);
     if (ot == "residual") S.matVec(seed, product);
@@ -298,8 +325,13 @@ int dab_set_solver_input(dab_solver* s, const char* input_name, const char* inpu
         if (input_size != S.nDof()) throw Error("setSolverInput: stateVar has the wrong size");
         S.updateOFFields(inputs);
     }
+    else if (it == "volCoord")
+    {
+        if ((size_t)input_size != S.hm.points.size()) throw Error("setSolverInput: volCoord has the wrong size");
+        S.updateMesh(inputs);
+    }
     else
-        throw Error("setSolverInput: inputType " + it + " is not supported (patchVelocity, stateVar)");
+        throw Error("setSolverInput: inputType " + it + " is not supported (patchVelocity, stateVar, volCoord)");
     DAB_CATCH
 }
 
@@ -366,6 +398,7 @@ int dab_get_input_size(dab_solver* s, const char* name, const char* type, int64_
     (void)name;
     if (std::string(type) == "stateVar") *out = s->s.nDof();
     else if (std::string(type) == "patchVelocity") *out = 2;
+    else if (std::string(type) == "volCoord") *out = (int64_t)s->s.hm.points.size();
     else throw Error(std::string("getInputSize: unsupported input type ") + type);
     DAB_CATCH
 }

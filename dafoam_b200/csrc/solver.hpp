@@ -15,6 +15,7 @@
 #include "rev_kernels.hpp"
 #include "krylov.hpp"
 #include "primal_kernels.hpp"
+#include "geom_kernels.hpp"
 #include "partition.hpp"
 #include "comm.hpp"
 #include <cstdlib>
@@ -105,6 +106,18 @@ struct FunctionDef
     double dir[3] = {1.0, 0.0, 0.0};     // force direction / moment axis
     double center[3] = {0.0, 0.0, 0.0};  // moment centre
     double scale = 1.0;
+};
+
+// work data of the volCoord input (solver_volcoord.hpp)
+struct VolCoord
+{
+    bool ready = false;
+    int radius = 6;         // residual rows within `radius` cells of a point's home cell may depend on the point
+    double relStep = 3e-5;  // finite-difference step relative to the shortest edge at the point
+    int nColours = 0, maxSlots = 1;
+    std::vector<int> homeStart, listStart;
+    DevBuf<int32_t> dFOff, dFLab, dSlotPoint, dHomes, dLists, dLabelA, dLabelB;
+    DevBuf<double> dEps, dPts, dPts0, dR2, dOut, dF1, dF2;
 };
 
 struct Solver
@@ -341,7 +354,11 @@ struct Solver
             const int lv = (int)a->numOr("pcConLevel", pcConLevel);
             if (lv != pcConLevel) { pcConLevel = lv; kry.symbolic = false; kry.pcValid = false; }
         }
-        if (const JVal* s = o.get("adjPartDerivFDStep")) fdStep = s->numOr("State", fdStep);
+        if (const JVal* s = o.get("adjPartDerivFDStep"))
+        {
+            fdStep = s->numOr("State", fdStep);
+            volc.relStep = s->numOr("Coord", volc.relStep); // relative to the shortest edge at the point
+        }
         primal.minResTol = o.numOr("primalMinResTol", primal.minResTol);
         primal.minResTolDiff = o.numOr("primalMinResTolDiff", primal.minResTolDiff);
         primal.minIters = (int)o.numOr("primalMinIters", primal.minIters);
@@ -892,6 +909,13 @@ struct Solver
         be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
     }
 
+    // ---- mesh coordinates as an input (volCoord) ------------------------------------------------------
+    VolCoord volc;
+    void uploadGeometry();
+    void updateMesh(const double* pts);
+    void volCoordSetup();
+    void volCoordProduct(const double* psi, const FunctionDef* function, double seed, double* out);
+
     // ---- primal (SIMPLE) ----------------------------------------------------------------------------
     Primal primal;
     VecOps primalOps;
@@ -920,3 +944,4 @@ struct Solver
 
 #include "solver_krylov.hpp"
 #include "solver_primal.hpp"
+#include "solver_volcoord.hpp"

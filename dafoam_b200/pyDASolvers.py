@@ -216,6 +216,10 @@ class pyDASolvers:
         _check_array(points, self.getNLocalPoints() * 3, "points")
         self._raise(self._L.dab_get_of_mesh_points(self._h, _dp(points)))
 
+    def updateOFMesh(self, points):
+        _check_array(points, 3 * self.getNLocalPoints(), "points")
+        self._raise(self._L.dab_update_of_mesh(self._h, _dp(points)))
+
     def getOFField(self, fieldName, fieldType, field):
         n = self.getNLocalCells() * (3 if fieldType == "vector" else 1)
         _check_array(field, n, "field")

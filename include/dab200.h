@@ -116,6 +116,9 @@ int dab_get_of_fields(dab_solver* s, double* states);
 
 /* getOFMeshPoints(points) (pyDASolvers.pyx:267-270) */
 int dab_get_of_mesh_points(dab_solver* s, double* points);
+/* updateOFMesh(points): new point coordinates (3*nLocalPoints), geometry recomputed, wall distance frozen
+ * (reference pyDASolvers.pyx updateOFMesh, DASolver::updateOFMesh) */
+int dab_update_of_mesh(dab_solver* s, const double* points);
 /* getOFField(name, type, field): read-only access to a cell field ("U","p","nuTilda","nut","yWall","V") */
 int dab_get_of_field(dab_solver* s, const char* name, const char* type, double* field);
 
