@@ -84,12 +84,62 @@ def run_workflow(lib_path):
     assert np.allclose(total, fd, rtol=2e-5, atol=0.0), (total, fd)
 
 
+def run_shape_workflow(lib_path):
+    """Shape derivative, the reference's main use (DAFoamSolver.linearize/apply_linear + DAInputVolCoord): the total
+    dF/d(alpha) of a mesh deformation x = x0 + alpha*v, as dF/dx.v - psi^T dR/dx.v, against FD over deformed meshes with
+    re-converged primals."""
+    mesh, bcs, sol = make(lib_path)
+    n, nP3 = sol.getNLocalAdjointStates(), 3 * sol.getNLocalPoints()
+    x0 = np.zeros(nP3)
+    sol.getOFMeshPoints(x0)
+    X = x0.reshape(-1, 3)
+    ymin, ymax, xmin, xmax = X[:, 1].min(), X[:, 1].max(), X[:, 0].min(), X[:, 0].max()
+    s = (X[:, 0] - xmin) / (xmax - xmin)
+    t = (X[:, 1] - ymin) / (ymax - ymin)
+    v = np.zeros_like(X)
+    v[:, 1] = 0.05 * (ymax - ymin) * np.sin(np.pi * s) ** 2 * (1.0 - t)  # a bump on the lower wall, fading to the upper one
+    v = v.ravel()
+
+    def F_at(alpha):
+        sol.updateOFMesh(x0 + alpha * v)
+        assert sol.solvePrimal() == 0
+        return sol.calcFunction("CD")
+
+    F0 = F_at(0.0)
+    W = np.zeros(n)
+    sol.getOFFields(W)
+    one = np.array([1.0])
+    dFdW, psi, dFdx, dRdxTpsi = np.zeros(n), np.zeros(n), np.zeros(nP3), np.zeros(nP3)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", one, dFdW)
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    assert sol.solveLinearEqn(ksp, dFdW, psi) == 0
+    sol.calcJacTVecProduct("aero_vol_coords", "volCoord", x0, "CD", "function", one, dFdx)
+    sol.calcJacTVecProduct("aero_vol_coords", "volCoord", x0, "R", "residual", psi, dRdxTpsi)
+    total = (dFdx - dRdxTpsi) @ v
+    h = 1e-3
+    fd = (F_at(h) - F_at(-h)) / (2 * h)
+    sol.updateOFMesh(x0)
+    assert np.isfinite(F0) and abs(fd) > 0
+    assert abs(total - fd) <= 2e-5 * abs(fd), (total, fd)
+
+
 def test_simple_fixed_point_is_the_root_of_the_residual_host_build():
     run_fixed_point(HOSTSIM)
 
 
 def test_primal_adjoint_workflow_matches_fd_host_build():
     run_workflow(HOSTSIM)
+
+
+def test_shape_derivative_workflow_matches_fd_host_build():
+    run_shape_workflow(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_shape_derivative_workflow_matches_fd_cuda():
+    run_shape_workflow(None)
 
 
 @pytest.mark.gpu
