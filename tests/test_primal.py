@@ -125,6 +125,55 @@ def run_shape_workflow(lib_path):
     assert abs(total - fd) <= 2e-5 * abs(fd), (total, fd)
 
 
+def run_pydafoam_api(lib_path):
+    """The user-facing PYDAFOAM class (reference dafoam/pyDAFoam.py): primal, functions, adjoint, total derivatives."""
+    from dafoam_b200.pyDAFoam import PYDAFOAM
+    mesh, bcs = cases.channel(nx=14, ny=8, nz=1), cases.default_bcs_channel()
+    d = tempfile.mkdtemp(prefix="dab_pydafoam_")
+    cases.write_case(d, mesh, bcs)
+    inp = dict(INP, aero_vol_coords={"type": "volCoord", "components": ["solver", "function"]})
+    opts = dict(solverName="DASimpleFoam", normalizeStates=NORM_STATES, function=FN, inputInfo=inp, primalMinResTol=1e-12, primalMaxIters=2000,
+                adjEqnOption=dict(gmresRelTol=1e-12, gmresMaxIters=400, gmresRestart=400, pcConLevel=3))
+    DASolver = PYDAFOAM(options=opts, comm=None, caseDir=d, _lib_path=lib_path)
+    x = np.array([10.0, 2.0])
+    DASolver.set_solver_input({"patchV": x})
+    DASolver()
+    assert DASolver.primalFail == 0
+    funcs = {}
+    DASolver.evalFunctions(funcs)
+    assert set(funcs) == {"CD"} and np.isfinite(funcs["CD"])
+    assert np.linalg.norm(DASolver.getResiduals()) < 1e-6
+    total = DASolver.calcTotalDeriv("CD", "patchV", x)
+    assert DASolver.adjointFail == 0
+    h = 1e-3
+    fd = np.zeros(2)
+    for k in range(2):
+        f2 = []
+        for sgn in (1.0, -1.0):
+            xp = x.copy()
+            xp[k] += sgn * h
+            DASolver.set_solver_input({"patchV": xp})
+            DASolver()
+            fk = {}
+            DASolver.evalFunctions(fk)
+            f2.append(fk["CD"])
+        fd[k] = (f2[0] - f2[1]) / (2 * h)
+    assert np.allclose(total, fd, rtol=5e-5), (total, fd)
+    DASolver.set_solver_input({"patchV": x})
+    DASolver()
+    dFdxv = DASolver.calcTotalDeriv("CD", "aero_vol_coords")
+    assert dFdxv.shape == (3 * DASolver.getNLocalPoints(),) and np.linalg.norm(dFdxv) > 0
+
+
+def test_pydafoam_class_host_build():
+    run_pydafoam_api(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_pydafoam_class_cuda():
+    run_pydafoam_api(None)
+
+
 def test_simple_fixed_point_is_the_root_of_the_residual_host_build():
     run_fixed_point(HOSTSIM)
 
