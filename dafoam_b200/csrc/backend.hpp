@@ -26,14 +26,20 @@ namespace dab
     } while (0)
 
 // per-functor occupancy hint: minimum resident blocks per SM (registers are capped accordingly)
+#ifndef DAB_BLOCK
+#define DAB_BLOCK 128
+#endif
+#ifndef DAB_MINBLOCKS
+#define DAB_MINBLOCKS 6
+#endif
 template <class F>
 struct LaunchTraits
 {
-    static constexpr int minBlocks = 6; // <= 80 registers per thread unless a functor says otherwise (latency-bound gathers: occupancy wins)
+    static constexpr int minBlocks = DAB_MINBLOCKS; // <= 80 registers per thread unless a functor says otherwise (latency-bound gathers: occupancy wins)
 };
 
 template <class F>
-__global__ void __launch_bounds__(128, LaunchTraits<F>::minBlocks) kernel1d(int n, F f)
+__global__ void __launch_bounds__(DAB_BLOCK, LaunchTraits<F>::minBlocks) kernel1d(int n, F f)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) f(i);
@@ -77,7 +83,7 @@ struct Backend
     void launch(int n, const F& f)
     {
         if (n <= 0) return;
-        const int bs = 128;
+        const int bs = DAB_BLOCK;
         kernel1d<F><<<(n + bs - 1) / bs, bs, 0, stream>>>(n, f);
         launches++;
     }

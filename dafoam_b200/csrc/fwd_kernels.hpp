@@ -37,9 +37,10 @@ struct FwdA
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
         const double pc = s.p[c];
         const double ntc = q.turb ? s.nt[c] : 0.0;
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             const int f = fr.f;
             const double S[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]}; // outward
@@ -149,9 +150,10 @@ struct FwdB
         double D0 = 0.0, sumOff = 0.0, MV[3] = {0.0, 0.0, 0.0}; // MV = V*(UEqn & U)
         double icMax = 0.0, icMin = 0.0, icAvg = 0.0;
         double NV = 0.0; // V*(nuTildaEqn & nuTilda) without the cell-local sources
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             const int f = fr.f;
             const double mf = fr.s * s.phi[f];
@@ -352,9 +354,10 @@ struct FwdC
         const int nT = m.nCtot, nC = m.nC;
         const size_t offP = (size_t)3 * nC, offPhi = (size_t)(q.turb ? 5 : 4) * nC;
         double div = 0.0;
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             const int f = fr.f;
             double F;

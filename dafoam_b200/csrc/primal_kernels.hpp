@@ -45,9 +45,10 @@ struct UEqnAssemble
         const double trc = gUc[0] + gUc[4] + gUc[8];
         double D0 = 0.0, sumOff = 0.0, X[3] = {0.0, 0.0, 0.0}; // X = explicit part of V*(UEqn & U)
         double icMax = 0.0, icMin = 0.0, icAvg = 0.0, icS[3] = {0.0, 0.0, 0.0};
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0)
             {
                 for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
@@ -313,9 +314,10 @@ struct PEqnAssemble
     {
         const int nT = m.nCtot, nC = m.nC;
         double D = 0.0, B = 0.0;
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0)
             {
                 for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
@@ -366,9 +368,10 @@ struct PhiUpdate
     double* phi;
     DAB_HD void operator()(int c) const
     {
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             if (fr.s < 0) continue;
             const int f = fr.f;
@@ -426,9 +429,10 @@ struct NutEqnAssemble
         for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
         for (int i = 0; i < 3; i++) gNc[i] = r.gNt[(size_t)i * nT + c];
         double D0 = 0.0, sumOff = 0.0, X = 0.0, ic = 0.0, aic = 0.0;
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0)
             {
                 for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;

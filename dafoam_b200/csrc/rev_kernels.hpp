@@ -130,9 +130,10 @@ struct RevA
         const double psiPc = x.p[c] * (q.nrP ? 1.0 / V : 1.0);
         double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
         double refb[3] = {0, 0, 0};
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             const int f = fr.f;
             const double mS = m.magSf[f], dl = m.delta[f];
@@ -249,9 +250,10 @@ struct RevB
         double refb[3] = {0, 0, 0};
         for (int i = 0; i < 9; i++) gUb[i] = 0.0;
 
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             const int f = fr.f;
             const double phi = s.phi[f];
@@ -524,9 +526,10 @@ struct RevC
             gNbc[i] = q.turb ? a.gNtb[(size_t)i * nT + c] * iVc : 0.0;
         }
         if (q.turb) nb = a.nt2[c] + a.nutb[c] * dnut_dnt(s.nt[c], q.nu);
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             const int f = fr.f;
             const double So[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]}; // outward
@@ -583,9 +586,10 @@ struct RevC
         {
             // phi adjoint of a function: no face-flux dependence for the force function
             const size_t offPhi = (size_t)(q.turb ? 5 : 4) * nC;
+            DAB_FACE_PREFETCH(NF)
             _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
             {
-                const FaceRef fr = faceOf(m, c, k);
+                const FaceRef fr = DAB_FACE(NF, k);
                 if (fr.f < 0) break;
                 if (fr.s > 0 || fr.n >= nC) y[offPhi + fr.f] = 0.0;
             }
@@ -719,9 +723,10 @@ struct ForceRevA
         const int nT = m.nCtot, nC = m.nC;
         double Ub[3] = {0, 0, 0}, pb = 0.0, ntb = 0.0, nutPb = 0.0, gUb[9];
         for (int i = 0; i < 9; i++) gUb[i] = 0.0;
+        DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
-            const FaceRef fr = faceOf(m, c, k);
+            const FaceRef fr = DAB_FACE(NF, k);
             if (fr.f < 0) break;
             if (!fr.bnd) continue;
             const int pa = m.bPatch[fr.f - m.nIF];

@@ -115,6 +115,43 @@ DAB_HD FaceRef faceOf(const MeshView& m, int c, int k)
     return r;
 }
 
+// the same from pre-loaded table entries
+DAB_HD FaceRef faceOfE(const MeshView& m, int e, int n)
+{
+    FaceRef r;
+    if (e < 0)
+    {
+        r.f = -1; r.n = -1; r.s = 0.0; r.bnd = false;
+        return r;
+    }
+    r.f = e >> 1;
+    r.s = (e & 1) ? -1.0 : 1.0;
+    r.bnd = r.f >= m.nIF;
+    r.n = n;
+    return r;
+}
+
+// DAB_PREFETCH_IDX (default build): load the cell's whole row of the two ELL tables before the face loop (fixed-size
+// meshes), so that the index loads of all faces are in flight together instead of one dependent round trip per face
+// (measured on B200: product 0.855 -> 0.763 ms).  Requesting the NEXT face's cache lines with prefetch.global.L1 on top of
+// this was measured too and is slower (1.005 ms: the prefetches double the LSU transactions) -- not kept.
+#if defined(DAB_PREFETCH_IDX)
+#define DAB_FACE_PREFETCH(NF)                                                                    \
+    int e_[(NF) > 0 ? (NF) : 1], n_[(NF) > 0 ? (NF) : 1];                                        \
+    if ((NF) > 0)                                                                                \
+    {                                                                                            \
+        _Pragma("unroll") for (int k_ = 0; k_ < (NF); k_++)                                      \
+        {                                                                                        \
+            e_[k_] = m.cellFaces[(size_t)k_ * m.nC + c];                                         \
+            n_[k_] = m.cellNbr[(size_t)k_ * m.nC + c];                                           \
+        }                                                                                        \
+    }
+#define DAB_FACE(NF, k) ((NF) > 0 ? faceOfE(m, e_[(NF) > 0 ? (k) : 0], n_[(NF) > 0 ? (k) : 0]) : faceOf(m, c, k))
+#else
+#define DAB_FACE_PREFETCH(NF)
+#define DAB_FACE(NF, k) faceOf(m, c, k)
+#endif
+
 // SA constants (reference src/adjoint/DAModel/DATurbulenceModel/DASpalartAllmaras.C:47-80)
 struct SA
 {
