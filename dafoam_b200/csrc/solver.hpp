@@ -42,7 +42,7 @@ template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int
 #define DAB_LAUNCH_NFF(n, F, ...)                                     \
     do                                                                \
     {                                                                 \
-        if (hm.maxCF == 6)                                            \
+        if (hex6)                                            \
         {                                                             \
             switch (featureMask())                                    \
             {                                                         \
@@ -60,13 +60,13 @@ template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int
 #define DAB_LAUNCH_NF_R(c0, n, F, ...)                                                      \
     do                                                                                      \
     {                                                                                       \
-        if (hm.maxCF == 6) be.launch(n, Shifted<F<6>>{F<6>{__VA_ARGS__}, c0});              \
+        if (hex6) be.launch(n, Shifted<F<6>>{F<6>{__VA_ARGS__}, c0});              \
         else be.launch(n, Shifted<F<0>>{F<0>{__VA_ARGS__}, c0});                            \
     } while (0)
 #define DAB_LAUNCH_NFF_R(c0, n, F, ...)                                                     \
     do                                                                                      \
     {                                                                                       \
-        if (hm.maxCF == 6)                                                                  \
+        if (hex6)                                                                  \
         {                                                                                   \
             switch (featureMask())                                                          \
             {                                                                               \
@@ -84,7 +84,7 @@ template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int
 #define DAB_LAUNCH_NF(n, F, ...)                                  \
     do                                                            \
     {                                                             \
-        if (hm.maxCF == 6) be.launch(n, F<6>{__VA_ARGS__});       \
+        if (hex6) be.launch(n, F<6>{__VA_ARGS__});       \
         else be.launch(n, F<0>{__VA_ARGS__});                     \
     } while (0)
 
@@ -157,6 +157,7 @@ struct Solver
     Partition part;
     DevBuf<double> psiP, psiN, psiPhi; // working copies of the input vector with ghost slots (multi-rank only)
 
+    bool hex6 = false; // every owned cell has exactly 6 faces: the kernels with fully unrolled, break-free face loops apply
     int nDof() const { return (par.turb ? 5 : 4) * hm.nC + hm.nF; }
 
     // bit 0: div(phi,U) is linearUpwindV; bit 1: some patch carries a wall-function nut BC
@@ -464,6 +465,9 @@ struct Solver
         dOwn.upload(be, hm.own);
         dNei.upload(be, hm.nei);
         dCellFaces.upload(be, hm.cellFaces);
+        hex6 = hm.maxCF == 6;
+        for (size_t i = 0; i < hm.cellFaces.size() && hex6; i++)
+            if (hm.cellFaces[i] < 0) hex6 = false;
         hm.buildCellNbr();
         dCellNbr.upload(be, hm.cellNbr);
         dBPatch.upload(be, hm.bPatch);
