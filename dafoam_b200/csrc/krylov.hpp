@@ -495,7 +495,7 @@ struct Krylov
     std::vector<int32_t> fdList, fdStart;
     DevBuf<int32_t> dFdList;
     // work
-    DevBuf<double> R0, R1, t1, t2, t3;
+    DevBuf<double> R0, R1, t1, t2, t3, t4, t5;
     Coarse coarse;
     // GMRES workspace
     DevBuf<double> V, w, z, xdev, bdev, hdev;

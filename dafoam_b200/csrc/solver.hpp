@@ -129,6 +129,8 @@ struct Solver
     int rank = 0, nRanks = 1;
     // options
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
+    int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
+    double richardsonOmega = 1.0;
     double gmresRelTol = 1e-6, gmresAbsTol = 1e-14, gmresTolDiff = 1e2, fdStep = 1e-6;
     std::string pcType = "ilu";
     int coarseAggregates = 0; // > 0: two-level preconditioner with that many pressure aggregates (global)
@@ -350,6 +352,8 @@ struct Solver
             pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
+            globalPCIters = (int)a->numOr("globalPCIters", globalPCIters);
+            richardsonOmega = a->numOr("richardsonOmega", richardsonOmega);
             const int ca = (int)a->numOr("coarseAggregates", coarseAggregates);
             if (ca != coarseAggregates) { coarseAggregates = ca; kry.pcValid = false; }
             const int lv = (int)a->numOr("pcConLevel", pcConLevel);

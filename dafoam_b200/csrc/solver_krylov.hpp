@@ -493,9 +493,28 @@ inline void Solver::applyPC(const double* v, double* z)
         be.launch(n, SubVec{v, K.t3.p}); // t3 = v - A z1
         applyIlu(K.t3.p, z);
         be.launch(n, AxpyVec{K.t2.p, 1.0, z});
-        return;
     }
-    applyIlu(v, z);
+    else
+        applyIlu(v, z);
+    // Richardson sweeps on the exact operator (the reference's optional "globalPCIters" wrapper, DALinearEqn.C:74-140):
+    // z <- z + M^-1 (v - A z); a fixed linear operator, so plain (non-flexible) GMRES stays valid
+    if (globalPCIters > 0)
+    {
+        const int n = nDof();
+        if (K.t4.n < (size_t)n)
+        {
+            K.t4.alloc(be, n);
+            K.t5.alloc(be, n);
+        }
+        for (int it = 0; it < globalPCIters; it++)
+        {
+            matVecDev(z, K.t4.p);
+            kspExtraMatvecs++;
+            be.launch(n, SubVec{v, K.t4.p}); // t4 = v - A z
+            applyIlu(K.t4.p, K.t5.p);
+            be.launch(n, AxpyVec{K.t5.p, richardsonOmega, z});
+        }
+    }
 }
 
 inline void Solver::applyIlu(const double* v, double* z)
