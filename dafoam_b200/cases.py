@@ -565,6 +565,73 @@ def default_bcs_channel(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True):
     return bcs
 
 
+def default_thermo(energy="sensibleInternalEnergy", transport="const", mu=1.8e-5, Pr=0.7, Prt=1.0, Cp=1005.0, molWeight=28.96,
+                   divE="upwind", divEkp="upwind"):
+    """thermophysicalProperties of the reference's DARhoSimpleFoam cases: hePsiThermo, pureMixture, perfectGas, hConst,
+    const or sutherland transport (the combination DAResidual::updateThermoVars assumes, reference DAResidual.C:179-293)."""
+    return dict(energy=energy, transport=transport, mu=mu, Pr=Pr, Prt=Prt, Cp=Cp, molWeight=molWeight, As=1.4792e-6, Ts=116.0,
+                divE=divE, divEkp=divEkp)
+
+
+def compressible_bcs(bcs, U0mag=None, p0=101325.0, T0=300.0):
+    """Turn a default_bcs_* set into its compressible counterpart: absolute pressure level, a T field with the p-like
+    role swapped (fixed where U is fixed/inflow, zero-gradient at walls/outflow)."""
+    out = {k: (v[0], v[1], v[2], {pn: dict(pb) for pn, pb in v[3].items()}) for k, v in bcs.items()}
+    cls, dims, _, pbs = out["p"]
+    for pb in pbs.values():
+        for key in ("value", "outletValue", "inletValue"):
+            if key in pb:
+                pb[key] = p0
+    out["p"] = (cls, "[1 -1 -2 0 0 0 0]", p0, pbs)
+    tb = {}
+    for pn, ub in bcs["U"][3].items():
+        ty = ub["type"]
+        if ty == "symmetry":
+            tb[pn] = dict(type="symmetry")
+        elif ty == "inletOutlet":
+            tb[pn] = dict(type="inletOutlet", inletValue=T0, value=T0)
+        elif ty == "fixedValue" and any(abs(x) > 0 for x in ub["value"]):
+            tb[pn] = dict(type="fixedValue", value=T0)
+        else:
+            tb[pn] = dict(type="zeroGradient")
+    out["T"] = ("volScalarField", "[0 0 0 1 0 0 0]", T0, tb)
+    return out
+
+
+def write_thermo(case_dir, thermo):
+    with open(os.path.join(case_dir, "constant", "thermophysicalProperties"), "w") as f:
+        f.write(_header("dictionary", "constant", "thermophysicalProperties"))
+        tr = "sutherland" if thermo["transport"] == "sutherland" else "const"
+        f.write("""
+thermoType
+{
+    type            hePsiThermo;
+    mixture         pureMixture;
+    transport       %s;
+    thermo          hConst;
+    equationOfState perfectGas;
+    specie          specie;
+    energy          %s;
+}
+mixture
+{
+    specie { molWeight %.17g; }
+    thermodynamics { Cp %.17g; Hf 0; }
+    transport { mu %.17g; Pr %.17g; As %.17g; Ts %.17g; }
+}
+Prt %.17g;
+""" % (tr, thermo["energy"], thermo["molWeight"], thermo["Cp"], thermo["mu"], thermo["Pr"], thermo["As"], thermo["Ts"], thermo["Prt"]))
+    # compressible convection schemes next to the incompressible ones
+    path = os.path.join(case_dir, "system", "fvSchemes")
+    txt = open(path).read()
+    sch = {"upwind": "bounded Gauss upwind", "linear": "bounded Gauss linear", "linearUpwind": "bounded Gauss linearUpwind grad(e)"}
+    he = "e" if thermo["energy"] == "sensibleInternalEnergy" else "h"
+    extra = "    div(phi,%s)      %s;\n    div(phi,%s)    %s;\n    div(((rho*nuEff)*dev2(T(grad(U))))) Gauss linear;\n" % (
+        he, sch[thermo["divE"]], "Ekp" if he == "e" else "K", sch[thermo["divEkp"]])
+    txt = txt.replace("    div(pc)         bounded Gauss upwind;\n", extra + "    div(pc)         bounded Gauss upwind;\n")
+    open(path, "w").write(txt)
+
+
 def write_case(case_dir, mesh: PolyMesh, bcs, binary=False, **dict_kw):
     """Write polyMesh + 0/ fields + dictionaries.  `bcs` as returned by default_bcs_*."""
     write_polymesh(case_dir, mesh, binary=binary)
@@ -572,7 +639,10 @@ def write_case(case_dir, mesh: PolyMesh, bcs, binary=False, **dict_kw):
         write_field(case_dir, name, cls, dims, internal, patch_bcs)
     ras = "SpalartAllmaras" if "nuTilda" in bcs else "dummy"
     dict_kw.setdefault("ras_model", ras)
+    thermo = dict_kw.pop("thermo", None)
     write_dicts(case_dir, **dict_kw)
+    if thermo is not None:
+        write_thermo(case_dir, thermo)
     return case_dir
 
 

@@ -592,7 +592,18 @@ struct Case
     std::vector<int> inId, outId;
     std::vector<double> adj;
     bool recorded = false;
-    int nDof() const { return (par.turb ? 5 : 4) * t.nC + t.nF; }
+    // DARhoSimpleFoam (compressible) extension
+    struct Comp
+    {
+        int on = 0;
+        int heIsE = 1;      // energy variable: 1 sensibleInternalEnergy (e), 0 sensibleEnthalpy (h)
+        int sutherland = 0; // transport: 0 const (mu, Pr), 1 sutherland (As, Ts)
+        int divE = 0, divEkp = 0, nrT = 1;
+        double R = 287.0, Cp = 1005.0, mu = 1.8e-5, Pr = 0.7, Prt = 1.0, As = 1.4792e-6, Ts = 116.0, TRef = 298.15, sT = 1.0;
+        std::vector<int> kindT;     // [nPatch]
+        std::vector<double> valueT; // [nPatch]
+    } comp;
+    int nDof() const { return ((par.turb ? 5 : 4) + (comp.on ? 1 : 0)) * t.nC + t.nF; }
 };
 
 template <class T>
@@ -603,12 +614,20 @@ struct Work
     std::vector<T> gradU, nutC;
 };
 
+template <class T>
+void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk);
+
 // R(W): DAResidualSimpleFoam::calcResiduals + DASpalartAllmaras::calcResiduals, preceded by
 // DASolver::updateStateBoundaryConditions (BCs + correctNut).
 template <class T>
 void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk = nullptr,
               const std::vector<T>* bcvIn = nullptr)
 {
+    if (cs.comp.on)
+    {
+        residualComp<T>(cs, g, W, isPC, R, wk);
+        return;
+    }
     std::vector<T> bcvLocal;
     if (!bcvIn)
     {
@@ -900,6 +919,388 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
     }
 }
 
+
+// ---- DARhoSimpleFoam: compressible residual -----------------------------------------------------------------------
+// R(W) of DAResidualRhoSimpleFoam::calcResiduals (reference src/adjoint/DAResidual/DAResidualRhoSimpleFoam.C:84-211) with
+// DAResidual::updateThermoVars (DAResidual.C:179-293: hePsiThermo, pureMixture, perfectGas, hConst, const/sutherland
+// transport), the compressible branches of DATurbulenceModel (rho(), nu() = mu/rho, divDevRhoReff, correctAlphat:
+// DATurbulenceModel.C:195-212, 259-330, 378-398) and of DASpalartAllmaras::calcResiduals (DASpalartAllmaras.C:452-462).
+// State ordering [U | p | T | nuTilda | phi] (DAStateInfoRhoSimpleFoam.C:40-46); phi is the mass flux.
+// OpenFOAM semantics restated: heThermo::alphaEff = CpByCpv*(alpha + alphat) (gamma for e, 1 for h); the energy BCs
+// fixedEnergy/gradientEnergy/mixedEnergy reduce, for constant Cp, to T's BC mapped through the linear he(T).
+template <class T>
+void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk)
+{
+    const Topo& t = cs.t;
+    const Params& par = cs.par;
+    const Case::Comp& cp = cs.comp;
+    const int nC = t.nC, nF = t.nF, nIF = t.nIF, nBF = t.nBF;
+    const bool turb = par.turb != 0;
+    SAConst sa;
+    std::vector<T> bcv(cs.bc.value.size());
+    for (size_t i = 0; i < bcv.size(); i++) bcv[i] = T(cs.bc.value[i]);
+    // unpack
+    std::vector<T> U((size_t)3 * nC), p(nC), Tt(nC), nt(nC, T(0.0)), phi(nF);
+    for (int c = 0; c < nC; c++)
+        for (int k = 0; k < 3; k++) U[(size_t)k * nC + c] = W[(size_t)3 * c + k];
+    size_t off = (size_t)3 * nC;
+    for (int c = 0; c < nC; c++) p[c] = W[off + c];
+    off += nC;
+    for (int c = 0; c < nC; c++) Tt[c] = W[off + c];
+    off += nC;
+    if (turb)
+    {
+        for (int c = 0; c < nC; c++) nt[c] = W[off + c];
+        off += nC;
+    }
+    for (int f = 0; f < nF; f++) phi[f] = W[off + f];
+
+    // --- boundary conditions of the states
+    BF<T> bU, bP, bT, bNt, bNut;
+    evalBC(t, g, cs.bc, bcv, F_U, 3, U, phi, bU);
+    evalBC(t, g, cs.bc, bcv, F_P, 1, p, phi, bP);
+    BCSpec bcT;
+    bcT.kind.assign((size_t)N_FIELDS * t.nPatch, BC_ZERO_GRADIENT);
+    std::vector<T> bcvT((size_t)N_FIELDS * t.nPatch * 3, T(0.0));
+    for (int pa = 0; pa < t.nPatch; pa++)
+    {
+        bcT.kind[pa] = cp.kindT[pa]; // stored in slot 0 of a private table
+        bcvT[(size_t)pa * 3] = T(cp.valueT[pa]);
+    }
+    evalBC(t, g, bcT, bcvT, 0, 1, Tt, phi, bT);
+    // --- thermo (DAResidual::updateThermoVars): psi = 1/(R T), rho = psi p, he, mu, alpha; cells and boundary faces
+    const double Rg = cp.R, Cp = cp.Cp, Cv = cp.Cp - cp.R;
+    const double heA = cp.heIsE ? (Cp - Rg) : Cp, heB = -Cp * cp.TRef; // he = heA*T + heB
+    const double CpByCpv = cp.heIsE ? Cp / Cv : 1.0;
+    auto muOf = [&](const T& Tv) -> T {
+        if (!cp.sutherland) return T(cp.mu);
+        return cp.As * sqrt(Tv) / (1.0 + cp.Ts / Tv);
+    };
+    auto alphaOf = [&](const T& muv) -> T {
+        if (!cp.sutherland) return muv / cp.Pr;
+        return muv * Cv * (1.32 + 1.77 * Rg / Cv) / Cp;
+    };
+    std::vector<T> rho(nC), mu(nC), alpha(nC), he(nC), nu(nC), rhoB(nBF), muB(nBF), alphaB(nBF), nuB(nBF);
+    for (int c = 0; c < nC; c++)
+    {
+        rho[c] = p[c] / (Rg * Tt[c]);
+        mu[c] = muOf(Tt[c]);
+        alpha[c] = alphaOf(mu[c]);
+        he[c] = heA * Tt[c] + heB;
+        nu[c] = mu[c] / rho[c];
+    }
+    for (int b = 0; b < nBF; b++)
+    {
+        rhoB[b] = bP.val[b] / (Rg * bT.val[b]);
+        muB[b] = muOf(bT.val[b]);
+        alphaB[b] = alphaOf(muB[b]);
+        nuB[b] = muB[b] / rhoB[b];
+    }
+    // he boundary coefficients: T's BC kinds with the reference value mapped through he(T)
+    BF<T> bHe;
+    {
+        std::vector<T> bcvH(bcvT);
+        for (int pa = 0; pa < t.nPatch; pa++) bcvH[(size_t)pa * 3] = heA * bcvT[(size_t)pa * 3] + heB;
+        evalBC(t, g, bcT, bcvH, 0, 1, he, phi, bHe);
+    }
+    // --- turbulence closures: nut = nuTilda*fv1(nuTilda/nu) (cells and boundaries), alphat = rho*nut/Prt
+    std::vector<T> nut(nC, T(0.0));
+    if (turb)
+    {
+        evalBC(t, g, cs.bc, bcv, F_NUTILDA, 1, nt, phi, bNt);
+        for (int c = 0; c < nC; c++) nut[c] = nt[c] * fv1f(T(nt[c] / nu[c]));
+        evalBC(t, g, cs.bc, bcv, F_NUT, 1, nut, phi, bNut);
+        for (int b = 0; b < nBF; b++)
+        {
+            const int kindN = cs.bc.kind[F_NUT * t.nPatch + t.bPatch[b]];
+            if (kindN == BC_CALCULATED)
+            {
+                const T& nb = bNt.val[b];
+                bNut.val[b] = nb * fv1f(T(nb / nuB[b]));
+            }
+            else if (kindN == BC_NUT_SPALDING)
+            {
+                const int f = nIF + b, c = t.own[f];
+                const double kappa = 0.41, E = 9.8, ROOTVSMALL = 1.0e-150;
+                const T nuw = nuB[b];
+                T d2(0.0);
+                for (int k = 0; k < 3; k++)
+                {
+                    T dd = U[(size_t)k * nC + c] - bU.val[bU.at(k, b)];
+                    d2 += dd * dd;
+                }
+                T magUp = sqrt(d2);
+                T G = magUp * g.delta[f];
+                T y = 1.0 / g.delta[f];
+                T ut = sqrt(nuw * G);
+                if (val(ut) > ROOTVSMALL)
+                {
+                    for (int it = 0; it < 1000; it++)
+                    {
+                        T kUu = min(kappa * magUp / ut, T(50.0));
+                        T fk = exp(kUu) - 1.0 - kUu * (1.0 + 0.5 * kUu);
+                        T ff = -(ut * y) / nuw + magUp / ut + (fk - kUu * kUu * kUu / 6.0) / E;
+                        T df = y / nuw + magUp / (ut * ut) + kUu * fk / ut / E;
+                        T un = ut + ff / df;
+                        const double err = std::fabs((val(ut) - val(un)) / val(ut));
+                        ut = un;
+                        if (!(val(ut) > ROOTVSMALL) || err < 1.0e-14) break;
+                    }
+                }
+                ut = max(ut, T(0.0));
+                bNut.val[b] = max(T(0.0), ut * ut / (G + ROOTVSMALL) - nuw);
+            }
+        }
+    }
+    else
+        bNut.init(1, nBF);
+    // effective transport coefficients (cell fields interpolated linearly by the laplacians)
+    std::vector<T> muE(nC), muEB(nBF), aE(nC), aEB(nBF);
+    for (int c = 0; c < nC; c++)
+    {
+        muE[c] = rho[c] * (nu[c] + nut[c]);
+        aE[c] = CpByCpv * (alpha[c] + rho[c] * nut[c] / cp.Prt);
+    }
+    for (int b = 0; b < nBF; b++)
+    {
+        muEB[b] = rhoB[b] * (nuB[b] + bNut.val[b]);
+        aEB[b] = CpByCpv * (alphaB[b] + rhoB[b] * bNut.val[b] / cp.Prt);
+    }
+
+    // --- gradients
+    std::vector<T> gradU, gradP, gradNt, gradHe;
+    fvcGrad(t, g, 3, U, bU, gradU);
+    fvcGrad(t, g, 1, p, bP, gradP);
+    fvcGrad(t, g, 1, he, bHe, gradHe);
+    if (turb) fvcGrad(t, g, 1, nt, bNt, gradNt);
+    auto GU = [&](int i, int j, int c) -> const T& { return gradU[((size_t)j * 3 + i) * nC + c]; };
+
+    // --- UEqn = div(phi,U) - laplacian(rho*nuEff,U) - div(rho*nuEff*dev2(T(grad(U))))
+    const int schemeU = isPC ? DIV_UPWIND : par.divU;
+    Mat<T> UEqn;
+    UEqn.init(t, 3);
+    fvmDiv(UEqn, t, g, phi, schemeU, bU, gradU, true, &U);
+    fvmLaplacian(UEqn, t, g, -1.0, muE, muEB, bU, gradU, false);
+    {
+        auto cellT = [&](int c, const V3<T>& S, V3<T>& out) {
+            T tr = GU(0, 0, c) + GU(1, 1, c) + GU(2, 2, c);
+            for (int j = 0; j < 3; j++)
+            {
+                T s = S[0] * GU(j, 0, c) + S[1] * GU(j, 1, c) + S[2] * GU(j, 2, c);
+                out[j] = muE[c] * (s - (2.0 / 3.0) * tr * S[j]);
+            }
+        };
+        for (int f = 0; f < nIF; f++)
+        {
+            const int o = t.own[f], n = t.nei[f];
+            V3<T> a, b2;
+            cellT(o, g.Sf[f], a);
+            cellT(n, g.Sf[f], b2);
+            for (int j = 0; j < 3; j++)
+            {
+                T fl = g.w[f] * a[j] + (1.0 - g.w[f]) * b2[j];
+                UEqn.src[(size_t)j * nC + o] += fl;
+                UEqn.src[(size_t)j * nC + n] -= fl;
+            }
+        }
+        for (int b = 0; b < nBF; b++)
+        {
+            const int f = nIF + b, c = t.own[f];
+            V3<T> nh = (T(1.0) / g.magSf[f]) * g.Sf[f];
+            T Gb[3][3];
+            for (int j = 0; j < 3; j++)
+            {
+                T nG = nh[0] * GU(0, j, c) + nh[1] * GU(1, j, c) + nh[2] * GU(2, j, c);
+                for (int i = 0; i < 3; i++) Gb[i][j] = GU(i, j, c) + nh[i] * (bU.sng[bU.at(j, b)] - nG);
+            }
+            T tr = Gb[0][0] + Gb[1][1] + Gb[2][2];
+            for (int j = 0; j < 3; j++)
+            {
+                T s = g.Sf[f][0] * Gb[j][0] + g.Sf[f][1] * Gb[j][1] + g.Sf[f][2] * Gb[j][2];
+                UEqn.src[(size_t)j * nC + c] += muEB[b] * (s - (2.0 / 3.0) * tr * g.Sf[f][j]);
+            }
+        }
+    }
+    relax(UEqn, t, par.alphaU, U);
+    std::vector<T> URes;
+    matResidual(UEqn, t, g, U, URes);
+    for (int k = 0; k < 3; k++)
+        for (int c = 0; c < nC; c++)
+        {
+            URes[(size_t)k * nC + c] += gradP[(size_t)k * nC + c];
+            if (!par.nrU) URes[(size_t)k * nC + c] *= g.V[c];
+        }
+
+    // --- EEqn = div(phi,he) + div(phi, Ekp|K) - laplacian(alphaEff, he)   (relax does not change EEqn & he)
+    const int schemeE = isPC ? DIV_UPWIND : cp.divE;
+    Mat<T> EEqn;
+    EEqn.init(t, 1);
+    fvmDiv(EEqn, t, g, phi, schemeE, bHe, gradHe, true);
+    {
+        std::vector<T> Ek(nC), EkB(nBF);
+        for (int c = 0; c < nC; c++)
+        {
+            T k2 = U[c] * U[c] + U[(size_t)nC + c] * U[(size_t)nC + c] + U[(size_t)2 * nC + c] * U[(size_t)2 * nC + c];
+            Ek[c] = 0.5 * k2;
+            if (cp.heIsE) Ek[c] += p[c] / rho[c];
+        }
+        for (int b = 0; b < nBF; b++)
+        {
+            T k2(0.0);
+            for (int k = 0; k < 3; k++) k2 += bU.val[bU.at(k, b)] * bU.val[bU.at(k, b)];
+            EkB[b] = 0.5 * k2;
+            if (cp.heIsE) EkB[b] += bP.val[b] / rhoB[b];
+        }
+        // fvc::div(phi, Ekp) with "bounded Gauss upwind|linear": sum_f phi_f Ekp_f - (sum_f phi_f) Ekp_P
+        std::vector<T> dv(nC, T(0.0));
+        for (int f = 0; f < nF; f++)
+        {
+            const int o = t.own[f];
+            T ef;
+            if (f < nIF)
+            {
+                const int n = t.nei[f];
+                if (cp.divEkp == DIV_LINEAR) ef = g.w[f] * Ek[o] + (1.0 - g.w[f]) * Ek[n];
+                else ef = (val(phi[f]) >= 0.0) ? Ek[o] : Ek[n];
+            }
+            else
+                ef = EkB[f - nIF];
+            T fl = phi[f] * ef;
+            dv[o] += fl - phi[f] * Ek[o];
+            if (f < nIF) dv[t.nei[f]] -= fl - phi[f] * Ek[t.nei[f]];
+        }
+        for (int c = 0; c < nC; c++) EEqn.src[c] -= dv[c];
+    }
+    fvmLaplacian(EEqn, t, g, -1.0, aE, aEB, bHe, gradHe, false);
+    std::vector<T> TRes;
+    matResidual(EEqn, t, g, he, TRes);
+    if (!cp.nrT)
+        for (int c = 0; c < nC; c++) TRes[c] *= g.V[c];
+
+    // --- rAU, HbyA, phiHbyA = interpolate(rho)*flux(HbyA)
+    std::vector<T> A, H;
+    matAH(UEqn, t, g, U, A, H);
+    std::vector<T> rAU(nC), HbyA((size_t)3 * nC), rhorAU(nC), rhorAUB(nBF);
+    for (int c = 0; c < nC; c++)
+    {
+        rAU[c] = 1.0 / A[c];
+        rhorAU[c] = rho[c] * rAU[c];
+        for (int k = 0; k < 3; k++) HbyA[(size_t)k * nC + c] = rAU[c] * H[(size_t)k * nC + c];
+    }
+    for (int b = 0; b < nBF; b++) rhorAUB[b] = rhoB[b] * rAU[t.own[nIF + b]];
+    std::vector<T> phiHbyA(nF);
+    for (int f = 0; f < nIF; f++)
+    {
+        T s(0.0);
+        for (int k = 0; k < 3; k++)
+            s += g.Sf[f][k] * (g.w[f] * HbyA[(size_t)k * nC + t.own[f]] + (1.0 - g.w[f]) * HbyA[(size_t)k * nC + t.nei[f]]);
+        phiHbyA[f] = (g.w[f] * rho[t.own[f]] + (1.0 - g.w[f]) * rho[t.nei[f]]) * s;
+    }
+    for (int b = 0; b < nBF; b++)
+    {
+        const int f = nIF + b, c = t.own[f];
+        const int kind = cs.bc.kind[F_U * t.nPatch + t.bPatch[b]];
+        const bool assignable = (kind == BC_INLET_OUTLET || kind == BC_OUTLET_INLET || kind == BC_ZERO_GRADIENT);
+        T s(0.0);
+        for (int k = 0; k < 3; k++)
+        {
+            const T& hb = (par.constrainHbyA && !assignable) ? bU.val[bU.at(k, b)] : HbyA[(size_t)k * nC + c];
+            s += g.Sf[f][k] * hb;
+        }
+        phiHbyA[f] = rhoB[b] * s;
+    }
+    // --- pEqn = div(phiHbyA) - laplacian(rhorAUf, p)
+    Mat<T> pEqn;
+    pEqn.init(t, 1);
+    fvmLaplacian(pEqn, t, g, -1.0, rhorAU, rhorAUB, bP, gradP, true);
+    for (int f = 0; f < nF; f++)
+    {
+        pEqn.src[t.own[f]] -= phiHbyA[f];
+        if (f < nIF) pEqn.src[t.nei[f]] += phiHbyA[f];
+    }
+    std::vector<T> pRes;
+    matResidual(pEqn, t, g, p, pRes);
+    if (!par.nrP)
+        for (int c = 0; c < nC; c++) pRes[c] *= g.V[c];
+    // --- phiRes = phiHbyA + pEqn.flux() - phi
+    std::vector<T> pFlux;
+    matFlux(pEqn, t, p, pFlux);
+    std::vector<T> phiRes(nF);
+    for (int f = 0; f < nF; f++)
+    {
+        phiRes[f] = phiHbyA[f] + pFlux[f] - phi[f];
+        if (par.nrPhi) phiRes[f] /= g.magSf[f];
+    }
+
+    // --- SA residual (compressible form)
+    std::vector<T> ntRes;
+    if (turb)
+    {
+        const int schemeN = isPC ? DIV_UPWIND : par.divNut;
+        Mat<T> nEqn;
+        nEqn.init(t, 1);
+        fvmDiv(nEqn, t, g, phi, schemeN, bNt, gradNt, true);
+        std::vector<T> Dn(nC), DnB(nBF);
+        for (int c = 0; c < nC; c++) Dn[c] = rho[c] * (nt[c] + nu[c]) / sa.sigmaNut;
+        for (int b = 0; b < nBF; b++) DnB[b] = rhoB[b] * (bNt.val[b] + nuB[b]) / sa.sigmaNut;
+        fvmLaplacian(nEqn, t, g, -1.0, Dn, DnB, bNt, gradNt, false);
+        const double Cw1 = sa.Cw1();
+        for (int c = 0; c < nC; c++)
+        {
+            T chi = nt[c] / nu[c];
+            T fv1 = fv1f(chi);
+            T fv2 = 1.0 - chi / (1.0 + chi * fv1);
+            T w01 = 0.5 * (GU(0, 1, c) - GU(1, 0, c)), w02 = 0.5 * (GU(0, 2, c) - GU(2, 0, c)),
+              w12 = 0.5 * (GU(1, 2, c) - GU(2, 1, c));
+            T Omega = std::sqrt(2.0) * sqrt(2.0 * (w01 * w01 + w02 * w02 + w12 * w12));
+            const double ky2 = (sa.kappa * cs.yWall[c]) * (sa.kappa * cs.yWall[c]);
+            T Stilda;
+            if (par.turb == 2)
+            {
+                const double Cv2 = 5.0;
+                T tq = 1.0 + chi / Cv2;
+                T t3 = tq * tq * tq;
+                T f2 = 1.0 / t3;
+                T cb = chi / Cv2;
+                T f3 = (1.0 + chi * fv1) * (1.0 / Cv2) * (3.0 * tq + cb * cb) / t3;
+                Stilda = f3 * Omega + f2 * nt[c] / ky2;
+            }
+            else
+                Stilda = max(Omega + fv2 * nt[c] / ky2, sa.Cs * Omega);
+            T r = min(nt[c] / (max(Stilda, T(1e-15)) * ky2), T(10.0));
+            T r2 = r * r;
+            T gg = r + sa.Cw2 * (r2 * r2 * r2 - r);
+            T g2 = gg * gg;
+            const double c6 = std::pow(sa.Cw3, 6.0);
+            T fw = gg * pow((1.0 + c6) / (g2 * g2 * g2 + c6), 1.0 / 6.0);
+            T mg2 = gradNt[(size_t)0 * nC + c] * gradNt[(size_t)0 * nC + c] + gradNt[(size_t)1 * nC + c] * gradNt[(size_t)1 * nC + c]
+                + gradNt[(size_t)2 * nC + c] * gradNt[(size_t)2 * nC + c];
+            nEqn.src[c] += g.V[c] * rho[c] * (sa.Cb2 / sa.sigmaNut * mg2 + sa.Cb1 * Stilda * nt[c]);
+            nEqn.diag[c] += g.V[c] * rho[c] * (Cw1 * fw * nt[c] / (cs.yWall[c] * cs.yWall[c]));
+        }
+        matResidual(nEqn, t, g, nt, ntRes);
+        if (!par.nrNut)
+            for (int c = 0; c < nC; c++) ntRes[c] *= g.V[c];
+    }
+
+    // --- pack [URes | pRes | TRes | nuTildaRes | phiRes]
+    R.assign(cs.nDof(), T(0.0));
+    for (int c = 0; c < nC; c++)
+        for (int k = 0; k < 3; k++) R[(size_t)3 * c + k] = URes[(size_t)k * nC + c];
+    off = (size_t)3 * nC;
+    for (int c = 0; c < nC; c++) R[off + c] = pRes[c];
+    off += nC;
+    for (int c = 0; c < nC; c++) R[off + c] = TRes[c];
+    off += nC;
+    if (turb)
+    {
+        for (int c = 0; c < nC; c++) R[off + c] = ntRes[c];
+        off += nC;
+    }
+    for (int f = 0; f < nF; f++) R[off + f] = phiRes[f];
+    (void)wk;
+}
+
 // DAFunctionForce::calcFunction: sum over the faces of one patch of (Sf*p_b + Sf & devRhoReff_b) . dir
 // mode 0: force . dir (DAFunctionForce); mode 1: ((Cf - center) x force) . dir (DAFunctionMoment.C:60-140)
 template <class T>
@@ -1006,6 +1407,19 @@ void* orc_create(int nP, const double* points, int nF, const int* fOff, const in
     return cs;
 }
 
+// switch the case to DARhoSimpleFoam: dpar = R, Cp, mu, Pr, Prt, As, Ts, TRef, sT; ipar = heIsE, sutherland, divE, divEkp, nrT
+void orc_set_compressible(void* h, const double* dpar, const int* ipar, const int* kindT, const double* valueT)
+{
+    Case* cs = (Case*)h;
+    Case::Comp& c = cs->comp;
+    c.on = 1;
+    c.R = dpar[0]; c.Cp = dpar[1]; c.mu = dpar[2]; c.Pr = dpar[3]; c.Prt = dpar[4]; c.As = dpar[5]; c.Ts = dpar[6]; c.TRef = dpar[7]; c.sT = dpar[8];
+    c.heIsE = ipar[0]; c.sutherland = ipar[1]; c.divE = ipar[2]; c.divEkp = ipar[3]; c.nrT = ipar[4];
+    c.kindT.assign(kindT, kindT + cs->t.nPatch);
+    c.valueT.assign(valueT, valueT + cs->t.nPatch);
+    cs->recorded = false;
+}
+
 void orc_destroy(void* h) { delete (Case*)h; }
 int orc_ndof(void* h) { return ((Case*)h)->nDof(); }
 int orc_ncells(void* h) { return ((Case*)h)->t.nC; }
@@ -1049,6 +1463,11 @@ static void scaleStates(const Case* cs, double* y)
     off += (size_t)3 * t.nC;
     for (int i = 0; i < t.nC; i++) y[off + i] *= q.sP;
     off += t.nC;
+    if (cs->comp.on)
+    {
+        for (int i = 0; i < t.nC; i++) y[off + i] *= cs->comp.sT;
+        off += t.nC;
+    }
     if (q.turb)
     {
         for (int i = 0; i < t.nC; i++) y[off + i] *= q.sNut;

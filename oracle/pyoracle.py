@@ -72,11 +72,12 @@ def bc_tables(mesh, bcs):
 class Oracle:
     def __init__(self, mesh, bcs, nu=1.5e-5, alphaU=0.7, divU="linearUpwind", divNut="upwind",
                  normalizeStates=None, normalizeResiduals=("URes", "pRes", "nuTildaRes", "phiRes"),
-                 constrainHbyA=True, yWall=None, rasModel="SpalartAllmaras"):
+                 constrainHbyA=True, yWall=None, rasModel="SpalartAllmaras", thermo=None):
+        """thermo: None (DASimpleFoam) or the dict of cases.default_thermo() -> DARhoSimpleFoam (bcs must carry "T")."""
         L = lib()
         self.mesh = mesh
         self.turb = "nuTilda" in bcs
-        ns = dict(U=1.0, p=1.0, nuTilda=1.0, phi=1.0)
+        ns = dict(U=1.0, p=1.0, nuTilda=1.0, phi=1.0, T=1.0)
         ns.update(normalizeStates or {})
         kind, value = bc_tables(mesh, bcs)
         nf = mesh.faces.shape[0]
@@ -98,6 +99,26 @@ class Oracle:
             _p(mesh.owner, C.c_int), C.c_int(mesh.n_internal_faces), _p(mesh.neighbour, C.c_int),
             C.c_int(len(mesh.patches)), _p(pstart, C.c_int), _p(psize, C.c_int), _p(pgeom, C.c_int),
             _p(kind, C.c_int), _p(value), _p(dpar), _p(ipar, C.c_int), yw))
+        self.compressible = thermo is not None
+        if thermo is not None:
+            th = thermo
+            pbT = bcs["T"][3]
+            kindT = np.array([BC_KIND[pbT[p_["name"]]["type"]] for p_ in mesh.patches], dtype=np.int32)
+            valT = np.zeros(len(mesh.patches))
+            for pi, p_ in enumerate(mesh.patches):
+                bc = pbT[p_["name"]]
+                for key in ("inletValue", "outletValue", "value"):
+                    if key in bc:
+                        valT[pi] = float(bc[key])
+                        break
+            Rg = 8314.4700665 / th["molWeight"]
+            dth = np.array([Rg, th["Cp"], th["mu"], th["Pr"], th["Prt"], th.get("As", 1.4792e-6), th.get("Ts", 116.0), 298.15,
+                            ns.get("T", 1.0)], dtype=np.float64)
+            ith = np.array([int(th["energy"] == "sensibleInternalEnergy"), int(th["transport"] == "sutherland"),
+                            DIV_SCHEME[th.get("divE", "upwind")], DIV_SCHEME[th.get("divEkp", "upwind")],
+                            int("TRes" in normalizeResiduals)], dtype=np.int32)
+            self._keep_th = (dth, ith, kindT, valT)
+            L.orc_set_compressible(self.h, _p(dth), _p(ith, C.c_int), _p(kindT, C.c_int), _p(valT))
         self.ndof = L.orc_ndof(self.h)
         self.ncells = L.orc_ncells(self.h)
 
@@ -169,7 +190,8 @@ class Oracle:
         return out
 
 
-def synthetic_state(mesh, geomC, Sf, U0=(10.0, 0.5, 0.0), nuTilda0=4.5e-5, turbulent=True, seed=1234, noise=0.01):
+def synthetic_state(mesh, geomC, Sf, U0=(10.0, 0.5, 0.0), nuTilda0=4.5e-5, turbulent=True, seed=1234, noise=0.01, thermo=None,
+                    p0=101325.0, T0=300.0):
     """Smooth analytic field + seeded 1 % noise: U, p, nuTilda at cells and a
     face flux phi = U_f . Sf (+ noise) on all faces, in the reference's state ordering."""
     rng = np.random.default_rng(seed)
@@ -199,6 +221,17 @@ def synthetic_state(mesh, geomC, Sf, U0=(10.0, 0.5, 0.0), nuTilda0=4.5e-5, turbu
         if pch["type"] in ("symmetry", "wall"):
             phi[pch["start"]:pch["start"] + pch["size"]] = 0.0
     parts = [U.ravel(), p]
+    if thermo is not None:
+        # compressible: absolute pressure, temperature field, mass flux
+        Rg = 8314.4700665 / thermo["molWeight"]
+        p = p0 + p
+        Tt = T0 * (1.0 + 0.02 * np.sin(0.9 * Cc[:, 0]) * np.cos(1.1 * Cc[:, 1])) * (1.0 + 0.1 * noise * rng.uniform(-1, 1, nC))
+        rho = p / (Rg * Tt)
+        rf = np.empty(nF)
+        rf[:nIF] = 0.5 * (rho[mesh.owner[:nIF]] + rho[mesh.neighbour])
+        rf[nIF:] = rho[mesh.owner[nIF:]]
+        phi = phi * rf
+        parts = [U.ravel(), p, Tt]
     if turbulent:
         parts.append(nt)
     parts.append(phi)

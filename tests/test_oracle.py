@@ -47,3 +47,31 @@ def test_force_derivative_matches_fd():
     eps = 1e-6
     fd = (orc.force(W + eps * v, 0, d) - orc.force(W - eps * v, 0, d)) / (2 * eps)
     assert abs(fd - g @ v) <= 1e-7 * abs(fd)
+
+
+def test_compressible_oracle_tape_matches_fd():
+    """DARhoSimpleFoam restatement (oracle.cpp residualComp): state [U|p|T|nuTilda|phi], both energy forms, const and
+    sutherland transport; the tape's transpose product against central differences of the residual."""
+    from dafoam_b200 import cases
+    from oracle.pyoracle import Oracle, synthetic_state
+    mesh = cases.naca0012_ogrid(ni=24, nj=12, nk=1)
+    ns = dict(U=50.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0)
+    nres = ("URes", "pRes", "TRes", "nuTildaRes", "phiRes")
+    for energy, transport, ras in (("sensibleInternalEnergy", "const", "SpalartAllmaras"),
+                                   ("sensibleEnthalpy", "sutherland", "SpalartAllmarasFv3")):
+        th = cases.default_thermo(energy=energy, transport=transport)
+        bcs = cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0)))
+        orc = Oracle(mesh, bcs, normalizeStates=ns, normalizeResiduals=nres, thermo=th, rasModel=ras)
+        nC = mesh.n_cells
+        assert orc.ndof == 6 * nC + mesh.n_faces
+        W = synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=th)
+        R = orc.residual(W)
+        assert np.isfinite(R).all() and all(np.linalg.norm(R[a * nC:(a + 1) * nC]) > 0 for a in (3, 4, 5))
+        orc.record(W)
+        rng = np.random.default_rng(0)
+        psi = rng.uniform(-1, 1, orc.ndof)
+        g = orc.jtvec(psi, normalize=False)
+        v = rng.uniform(-1, 1, orc.ndof) * np.abs(W) * 1e-1 + 1e-12
+        eps = 1e-6
+        fd = psi @ (orc.residual(W + eps * v) - orc.residual(W - eps * v)) / (2 * eps)
+        assert abs(g @ v - fd) <= 1e-7 * abs(fd), (energy, g @ v, fd)
