@@ -338,11 +338,11 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     traffic, traffic_src = None, None
-    tf = os.path.join(ROOT, "profiles", "r01c_ncu_kernels_dram.json")
+    tf = os.path.join(ROOT, "profiles", "r01d_ncu_kernels_dram.json")
     if os.path.exists(tf) and world == 1 and args.cells == 980000:
         tj = json.load(open(tf))
         traffic = sum(tj[k]["dram__bytes_read.sum"] + tj[k]["dram__bytes_write.sum"] for k in ("RevA", "RevB", "RevC"))
-        traffic_src = "profiles/r01c_ncu_kernels_dram.json (ncu dram__bytes_read+write of RevA+RevB+RevC, same workload)"
+        traffic_src = "profiles/r01d_ncu_kernels_dram.json (ncu dram__bytes_read+write of RevA+RevB+RevC, same workload)"
     alg = sol.algorithmicBytes(0)
     achieved = alg / (ms_max * 1e-3) / 1e9
     nC_global = sol.getNGlobalCells()
