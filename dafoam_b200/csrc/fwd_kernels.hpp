@@ -41,7 +41,7 @@ struct FwdA
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             const int f = fr.f;
             const double S[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]}; // outward
             double Uf[3], pf, nf = 0.0;
@@ -154,7 +154,7 @@ struct FwdB
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             const int f = fr.f;
             const double mf = fr.s * s.phi[f];
             const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
@@ -358,7 +358,7 @@ struct FwdC
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             const int f = fr.f;
             double F;
             if (!fr.bnd)

@@ -49,7 +49,7 @@ struct UEqnAssemble
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0)
+            if (fr.f < 0)
             {
                 for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
                 break;
@@ -318,7 +318,7 @@ struct PEqnAssemble
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0)
+            if (fr.f < 0)
             {
                 for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
                 break;
@@ -372,7 +372,7 @@ struct PhiUpdate
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             if (fr.s < 0) continue;
             const int f = fr.f;
             if (!fr.bnd)
@@ -433,7 +433,7 @@ struct NutEqnAssemble
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0)
+            if (fr.f < 0)
             {
                 for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
                 break;

@@ -134,7 +134,7 @@ struct RevA
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             const int f = fr.f;
             const double mS = m.magSf[f], dl = m.delta[f];
             const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
@@ -254,7 +254,7 @@ struct RevB
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             const int f = fr.f;
             const double phi = s.phi[f];
             const double mf = fr.s * phi;
@@ -530,7 +530,7 @@ struct RevC
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             const int f = fr.f;
             const double So[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]}; // outward
             if (!fr.bnd)
@@ -590,7 +590,7 @@ struct RevC
             _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
             {
                 const FaceRef fr = DAB_FACE(NF, k);
-                if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+                if (fr.f < 0) break;
                 if (fr.s > 0 || fr.n >= nC) y[offPhi + fr.f] = 0.0;
             }
         }
@@ -727,7 +727,7 @@ struct ForceRevA
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
             const FaceRef fr = DAB_FACE(NF, k);
-            if (NF == 0 && fr.f < 0) break; // NF > 0: every cell has exactly NF faces (checked on the host)
+            if (fr.f < 0) break;
             if (!fr.bnd) continue;
             const int pa = m.bPatch[fr.f - m.nIF];
             if (!((fs.mask >> pa) & 1u)) continue;

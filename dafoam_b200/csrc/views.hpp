@@ -118,8 +118,12 @@ DAB_HD FaceRef faceOf(const MeshView& m, int c, int k)
 // the same from pre-loaded table entries
 DAB_HD FaceRef faceOfE(const MeshView& m, int e, int n)
 {
-    // only used with a fixed face count per cell (NF > 0): e is a valid entry
     FaceRef r;
+    if (e < 0)
+    {
+        r.f = -1; r.n = -1; r.s = 0.0; r.bnd = false;
+        return r;
+    }
     r.f = e >> 1;
     r.s = (e & 1) ? -1.0 : 1.0;
     r.bnd = r.f >= m.nIF;
