@@ -13,6 +13,7 @@
 #include "views.hpp"
 #include "fwd_kernels.hpp"
 #include "rev_kernels.hpp"
+#include "comp_kernels.hpp"
 #include "krylov.hpp"
 #include "primal_kernels.hpp"
 #include "geom_kernels.hpp"
@@ -36,6 +37,9 @@ template <int NF, int FEAT> struct LaunchTraits<RevB<NF, FEAT>> { static constex
 template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 template <int NF, int FEAT> struct LaunchTraits<UEqnAssemble<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
+template <int NF> struct LaunchTraits<cFwdB<NF>> { static constexpr int minBlocks = 2; };
+template <int NF> struct LaunchTraits<cFwdE<NF>> { static constexpr int minBlocks = 4; };
+template <int NF> struct LaunchTraits<cFwdC<NF>> { static constexpr int minBlocks = 4; };
 #endif
 
 // optional-feature dispatch for the two heavy kernels (hex meshes: 4 variants; other meshes: the full-featured one)
@@ -143,7 +147,8 @@ struct Solver
     DevBuf<double> dS[3], dMagSf, dW, dDelta, dK[3], dCf[3], dC[3], dV, dY;
     MeshView mv;
     // state (internal working copies with ghost slots) and external-layout mirror
-    DevBuf<double> dWext, dU, dP, dNt, dPhi;
+    DevBuf<double> dWext, dU, dP, dNt, dPhi, dT;
+    DevBuf<double> rRho, rNuL, rMuE, rAE, rHe, rEk, rGHe; // compressible closures
     StateView sv;
     // forward record and reverse work arrays
     DevBuf<double> rNut, rGU, rGP, rGNt, rRAU, rHbyA, rD0, rFlag;
@@ -160,7 +165,12 @@ struct Solver
     DevBuf<double> psiP, psiN, psiPhi; // working copies of the input vector with ghost slots (multi-rank only)
 
     bool hex6 = false; // every owned cell has exactly 6 faces: the kernels with fully unrolled, break-free face loops apply
-    int nDof() const { return (par.turb ? 5 : 4) * hm.nC + hm.nF; }
+    int nCellStates() const { return 4 + (par.comp ? 1 : 0) + (par.turb ? 1 : 0); }
+    int nDof() const { return nCellStates() * hm.nC + hm.nF; }
+    void requireIncompressible(const char* what) const
+    {
+        if (par.comp) throw Error(std::string(what) + ": not available for DARhoSimpleFoam yet (the forward residual is; DESIGN.md section 8)");
+    }
 
     // bit 0: div(phi,U) is linearUpwindV; bit 1: some patch carries a wall-function nut BC
     int featureMask() const
@@ -183,7 +193,9 @@ struct Solver
             auto t = tokenize(argsAll);
             solverName = t.empty() ? "DASimpleFoam" : t[0];
         }
-        if (solverName != "DASimpleFoam") throw Error("solver " + solverName + " is not supported (DASimpleFoam only in this build)");
+        if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam")
+            throw Error("solver " + solverName + " is not supported (DASimpleFoam; DARhoSimpleFoam: forward residual only)");
+        if (solverName == "DARhoSimpleFoam" && nRanks_ > 1) throw Error("DARhoSimpleFoam runs on one GPU in this build");
         be.init(device);
         if (nRanks == 1)
         {
@@ -230,8 +242,39 @@ struct Solver
     void readCase(const std::string& caseDir)
     {
         memset(&par, 0, sizeof(par));
-        Dict tp = readDict(caseDir + "/constant/transportProperties");
-        par.nu = tp.scalar("nu");
+        par.comp = solverName == "DARhoSimpleFoam" ? 1 : 0;
+        if (!par.comp)
+        {
+            Dict tp = readDict(caseDir + "/constant/transportProperties");
+            par.nu = tp.scalar("nu");
+        }
+        else
+        {
+            // constant/thermophysicalProperties: the combination DAResidual::updateThermoVars assumes (DAResidual.C:179-293)
+            Dict th = readDict(caseDir + "/constant/thermophysicalProperties");
+            const Dict& tt = th.sub("thermoType");
+            if (tt.wordOr("type", "hePsiThermo") != "hePsiThermo" || tt.wordOr("equationOfState", "perfectGas") != "perfectGas"
+                || tt.wordOr("thermo", "hConst") != "hConst")
+                throw Error("thermophysicalProperties: only hePsiThermo / perfectGas / hConst is supported");
+            const std::string en = tt.wordOr("energy", "sensibleInternalEnergy"), trn = tt.wordOr("transport", "const");
+            if (en != "sensibleInternalEnergy" && en != "sensibleEnthalpy") throw Error("thermophysicalProperties: unsupported energy " + en);
+            if (trn != "const" && trn != "sutherland") throw Error("thermophysicalProperties: unsupported transport " + trn);
+            par.heIsE = en == "sensibleInternalEnergy" ? 1 : 0;
+            par.sutherland = trn == "sutherland" ? 1 : 0;
+            const Dict& mx = th.sub("mixture");
+            par.Rg = 8314.4700665 / mx.sub("specie").scalar("molWeight");
+            par.Cp = mx.sub("thermodynamics").scalar("Cp");
+            const Dict& tr = mx.sub("transport");
+            par.muC = tr.scalarOr("mu", 1.8e-5);
+            par.Pr = tr.scalarOr("Pr", 0.7);
+            par.As = tr.scalarOr("As", 1.4792e-6);
+            par.Ts = tr.scalarOr("Ts", 116.0);
+            par.Prt = th.scalarOr("Prt", 1.0);
+            par.TRef = 298.15;
+            par.sT = 1.0;
+            par.nrT = 1;
+            par.nu = par.muC; // unused by the compressible kernels
+        }
         std::string ras = "dummy";
         if (fileExists(caseDir + "/constant/turbulenceProperties"))
         {
@@ -257,6 +300,27 @@ struct Solver
         };
         par.divU = scheme("div(phi,U)");
         par.divNut = par.turb ? scheme("div(phi,nuTilda)") : DIV_UPWIND;
+        if (par.comp)
+        {
+            par.divE = scheme(par.heIsE ? "div(phi,e)" : "div(phi,h)");
+            par.divEkp = scheme(par.heIsE ? "div(phi,Ekp)" : "div(phi,K)");
+            if (par.divEkp != DIV_UPWIND && par.divEkp != DIV_LINEAR) throw Error("div(phi,Ekp|K): upwind or linear");
+            // temperature boundary conditions
+            const std::string path = caseDir + "/0/T";
+            Dict d = readDict(path);
+            fieldDicts["T"] = d;
+            const Dict& bf = d.sub("boundaryField");
+            for (size_t p = 0; p < hm.patches.size(); p++)
+            {
+                const Dict& pd = bf.sub(hm.patches[p].name);
+                const int kind = bcKindOf(pd.word("type"), path);
+                par.bcKindT[p] = kind;
+                double v[3] = {0, 0, 0};
+                const char* key = kind == BC_INLET_OUTLET ? "inletValue" : (kind == BC_OUTLET_INLET ? "outletValue" : "value");
+                if (pd.has(key)) pd.uniform(key, v);
+                par.bcValT[p] = v[0];
+            }
+        }
         Dict fso = readDict(caseDir + "/system/fvSolution");
         par.alphaU = 1.0;
         if (fso.hasSub("relaxationFactors") && fso.sub("relaxationFactors").hasSub("equations"))
@@ -328,16 +392,18 @@ struct Solver
             par.sP = ns->numOr("p", par.sP);
             par.sNut = ns->numOr("nuTilda", par.sNut);
             par.sPhi = ns->numOr("phi", par.sPhi);
+            par.sT = ns->numOr("T", par.sT);
         }
         if (const JVal* nr = o.get("normalizeResiduals"))
         {
-            par.nrU = par.nrP = par.nrNut = par.nrPhi = 0;
+            par.nrU = par.nrP = par.nrNut = par.nrPhi = par.nrT = 0;
             for (const auto& v : nr->arr)
             {
                 if (v.str == "URes") par.nrU = 1;
                 if (v.str == "pRes") par.nrP = 1;
                 if (v.str == "nuTildaRes") par.nrNut = 1;
                 if (v.str == "phiRes") par.nrPhi = 1;
+                if (v.str == "TRes") par.nrT = 1;
             }
         }
         par.constrainHbyA = (int)o.numOr("useConstrainHbyA", par.constrainHbyA);
@@ -495,7 +561,16 @@ struct Solver
         const size_t nT = hm.nCtot, nC = hm.nC, nF = hm.nF, nd = nDof();
         dWext.alloc(be, nd);
         dU.alloc(be, 3 * nT); dP.alloc(be, nT); dNt.alloc(be, nT); dPhi.alloc(be, nF);
-        sv.U = dU.p; sv.p = dP.p; sv.nt = dNt.p; sv.phi = dPhi.p;
+        sv.U = dU.p; sv.p = dP.p; sv.nt = dNt.p; sv.phi = dPhi.p; sv.T = nullptr;
+        rv.rho = rv.nuL = rv.muE = rv.aE = rv.he = rv.Ek = rv.gHe = nullptr;
+        if (par.comp)
+        {
+            dT.alloc(be, nT);
+            sv.T = dT.p;
+            rRho.alloc(be, nT); rNuL.alloc(be, nT); rMuE.alloc(be, nT); rAE.alloc(be, nT); rHe.alloc(be, nT); rEk.alloc(be, nT);
+            rGHe.alloc(be, 3 * nT);
+            rv.rho = rRho.p; rv.nuL = rNuL.p; rv.muE = rMuE.p; rv.aE = rAE.p; rv.he = rHe.p; rv.Ek = rEk.p; rv.gHe = rGHe.p;
+        }
         rNut.alloc(be, nT); rGU.alloc(be, 9 * nT); rGP.alloc(be, 3 * nT); rGNt.alloc(be, 3 * nT);
         rRAU.alloc(be, nT); rHbyA.alloc(be, 3 * nT); rD0.alloc(be, nT); rFlag.alloc(be, nT);
         rv.nut = rNut.p; rv.gU = rGU.p; rv.gP = rGP.p; rv.gNt = rGNt.p; rv.rAU = rRAU.p; rv.HbyA = rHbyA.p; rv.D0 = rD0.p; rv.flag = rFlag.p;
@@ -544,12 +619,18 @@ struct Solver
                 }
             }
         };
-        std::vector<double> U, p, nt;
+        std::vector<double> U, p, nt, Tt;
         internal("U", 3, U);
         internal("p", 1, p);
         for (int i = 0; i < 3 * nC; i++) W[i] = U[i];
         for (int c = 0; c < nC; c++) W[3 * (size_t)nC + c] = p[c];
         size_t off = 4 * (size_t)nC;
+        if (par.comp)
+        {
+            internal("T", 1, Tt);
+            for (int c = 0; c < nC; c++) W[off + c] = Tt[c];
+            off += nC;
+        }
         if (par.turb)
         {
             internal("nuTilda", 1, nt);
@@ -571,6 +652,13 @@ struct Solver
             }
             W[off + f] = uf[0] * hm.Sf[0][f] + uf[1] * hm.Sf[1][f] + uf[2] * hm.Sf[2][f];
             if (f >= nIF && par.bcKind[F_U][hm.bPatch[f - nIF]] == BC_SYMMETRY) W[off + f] = 0.0;
+            if (par.comp)
+            {
+                // mass flux: rho_f from the cell values (createFieldsRhoSimple.H role)
+                const double ro = p[o] / (par.Rg * Tt[o]);
+                const double rf = f < nIF ? hm.w[f] * ro + (1.0 - hm.w[f]) * p[hm.nei[f]] / (par.Rg * Tt[hm.nei[f]]) : ro;
+                W[off + f] *= rf;
+            }
         }
         updateOFFields(W.data());
     }
@@ -583,6 +671,11 @@ struct Solver
         be.d2d(dU.p, dWext.p, 3 * nC * sizeof(double));
         be.d2d(dP.p, dWext.p + 3 * nC, nC * sizeof(double));
         size_t off = 4 * nC;
+        if (par.comp)
+        {
+            be.d2d(dT.p, dWext.p + off, nC * sizeof(double));
+            off += nC;
+        }
         if (par.turb)
         {
             be.d2d(dNt.p, dWext.p + off, nC * sizeof(double));
@@ -611,6 +704,15 @@ struct Solver
     void forward(int isPC, double* Rdev, bool exchange = true)
     {
         const int nT = hm.nCtot;
+        if (par.comp)
+        {
+            // DARhoSimpleFoam: closures + gradients, momentum/SA rows, energy row, pressure/flux rows (comp_kernels.hpp)
+            DAB_LAUNCH_NF(hm.nCtot, cFwdA, mv, par, sv, rv);
+            DAB_LAUNCH_NF(hm.nC, cFwdB, mv, par, sv, rv, isPC, Rdev);
+            DAB_LAUNCH_NF(hm.nC, cFwdE, mv, par, sv, rv, isPC, Rdev);
+            DAB_LAUNCH_NF(hm.nC, cFwdC, mv, par, sv, rv, Rdev);
+            return;
+        }
         DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);
         if (exchange && comm.active())
         {
@@ -680,6 +782,7 @@ struct Solver
 
     void matVecDev(const double* x, double* y)
     {
+        requireIncompressible("dRdWT*psi");
         ensureRecorded();
         const int nT = hm.nCtot;
         if (!comm.active())
@@ -857,6 +960,7 @@ struct Solver
 
     double calcFunction(const std::string& name)
     {
+        requireIncompressible("calcFunction");
         const FunctionDef& f = findFunction(name);
         ensureRecorded();
         if (dFacePart.n < (size_t)hm.nBF + 1) dFacePart.alloc(be, hm.nBF + 1);
@@ -902,6 +1006,7 @@ struct Solver
     // [dF/dW]^T * seed, scaled by normalizeStates (DASolver.C:1819-1820)
     void dFdW(const std::string& name, double seed, double* out)
     {
+        requireIncompressible("dF/dW");
         const FunctionDef& f = findFunction(name);
         ensureRecorded();
         be.zero(av.gUb, (size_t)9 * hm.nCtot * sizeof(double));

@@ -99,6 +99,7 @@ int greedyColour(int n, NbrFn nbr, std::vector<int>& colour)
 
 inline void Solver::pcSymbolic()
 {
+    requireIncompressible("calcdRdWT");
     using detail::CellGraph;
     Krylov& K = kry;
     const int nC = hm.nC, nF = hm.nF, nIF = hm.nIF;

@@ -11,6 +11,7 @@ namespace dab
 
 inline void Solver::primalSetup()
 {
+    requireIncompressible("solvePrimal");
     Primal& P = primal;
     if (P.allocated) return;
     if (comm.active()) throw Error("solvePrimal runs on one GPU in this build (the adjoint path is the multi-GPU one)");

@@ -37,6 +37,7 @@ inline void Solver::updateMesh(const double* pts)
 
 inline void Solver::volCoordSetup()
 {
+    requireIncompressible("volCoord");
     VolCoord& Vc = volc;
     if (Vc.ready) return;
     if (comm.active()) throw Error("the volCoord input runs on one GPU in this build");

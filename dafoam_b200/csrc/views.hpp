@@ -40,6 +40,14 @@ struct Params
     int constrainHbyA;
     int bcKind[N_FIELDS][MAXP];
     double bcVal[N_FIELDS][MAXP][3];
+    // DARhoSimpleFoam (compressible): hePsiThermo, pureMixture, perfectGas, hConst, const|sutherland transport
+    // (reference DAResidual::updateThermoVars, src/adjoint/DAResidual/DAResidual.C:179-293)
+    int comp;                 // 1: state ordering [U | p | T | nuTilda | phi], phi = mass flux
+    int heIsE, sutherland;    // energy variable e (1) or h (0); transport model
+    int divE, divEkp, nrT;    // div(phi,e|h), div(phi,Ekp|K) schemes; TRes listed in normalizeResiduals
+    double Rg, Cp, muC, Pr, Prt, As, Ts, TRef, sT;
+    int bcKindT[MAXP];
+    double bcValT[MAXP];
 };
 
 // internal working state (ghost slots appended to the cell arrays)
@@ -49,6 +57,7 @@ struct StateView
     const double* p;   // [nCtot]
     const double* nt;  // [nCtot] (nuTilda; unused when laminar)
     const double* phi; // [nF]
+    const double* T;   // [nCtot] (compressible only)
 };
 
 // the input vector of a transpose product, field by field; on one GPU the pointers alias the caller's
@@ -59,6 +68,7 @@ struct PsiView
     const double* p;   // [nCtot]  adjoint of pRes
     const double* nt;  // [nCtot]  adjoint of nuTildaRes
     const double* phi; // [nF]     adjoint of phiRes
+    const double* T;   // [nCtot]  adjoint of TRes (compressible only)
 };
 
 // forward intermediates recorded once per state (the role of the reference's AD tape)
@@ -72,6 +82,9 @@ struct RecordView
     double* HbyA;  // [3][nCtot]
     double* D0;    // [nCtot] assembled momentum diagonal (without boundary coefficients)
     double* flag;  // [nCtot] relax branch: +-1 -> |D1| branch with sign(D1); 0 -> sum-off-diagonal branch
+    // compressible closures (cell values; null for DASimpleFoam)
+    double *rho, *nuL, *muE, *aE, *he, *Ek; // [nCtot] density, laminar nu, rho*nuEff, alphaEff, energy variable, Ekp|K
+    double* gHe;                            // [3][nCtot] grad(he)
 };
 
 // reverse intermediates (per product)

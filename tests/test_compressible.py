@@ -1,0 +1,75 @@
+"""DARhoSimpleFoam: the compressible residual kernels (comp_kernels.hpp) against the oracle's
+restatement of DAResidualRhoSimpleFoam + updateThermoVars + the compressible SA model, over both energy variables, both
+transport models, both SA variants, every div(phi,U) scheme and the wall function."""
+import tempfile
+
+import numpy as np
+import pytest
+
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import pyDASolvers
+from oracle.pyoracle import Oracle, synthetic_state
+from tests.common import HOSTSIM, rel_err
+
+NS = dict(U=50.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0)
+NRES = ("URes", "pRes", "TRes", "nuTildaRes", "phiRes")
+CONFIGS = [
+    # mesh, energy, transport, RAS model, div(phi,U), div(phi,e|h), wall function, listed residuals
+    ("naca", "sensibleInternalEnergy", "const", "SpalartAllmaras", "linearUpwindV", "upwind", False, NRES),
+    ("naca", "sensibleEnthalpy", "sutherland", "SpalartAllmarasFv3", "linearUpwind", "linearUpwind", True, NRES),
+    ("channel", "sensibleInternalEnergy", "sutherland", "SpalartAllmaras", "upwind", "linear", False, NRES),
+    ("prism", "sensibleEnthalpy", "const", "SpalartAllmaras", "linearUpwind", "upwind", False, ("pRes", "TRes")),
+]
+
+
+def setup_comp(cfg, lib_path):
+    kind, energy, transport, ras, divU, divE, wf, nres = cfg
+    if kind == "naca":
+        mesh = cases.naca0012_ogrid(ni=40, nj=20, nk=2)
+        base = cases.default_bcs_naca(U0=(50.0, 2.0, 0.0), wall_function=wf)
+    elif kind == "prism":
+        mesh = cases.prism_channel(nx=10, ny=6)
+        base = cases.default_bcs_channel(U0=(50.0, 0.0, 0.0))
+    else:
+        mesh = cases.channel(nx=12, ny=8, nz=1)
+        base = cases.default_bcs_channel(U0=(50.0, 0.0, 0.0))
+    th = cases.default_thermo(energy=energy, transport=transport, divE=divE, divEkp="linear" if divE == "linear" else "upwind")
+    bcs = cases.compressible_bcs(base)
+    d = tempfile.mkdtemp(prefix="dab_comp_")
+    div_u = "bounded Gauss %s%s" % (divU, " grad(U)" if divU.startswith("linearUpwind") else "")
+    cases.write_case(d, mesh, bcs, div_u=div_u, ras_model=ras, thermo=th)
+    orc = Oracle(mesh, bcs, normalizeStates=NS, normalizeResiduals=nres, thermo=th, rasModel=ras, divU=divU)
+    sol = pyDASolvers("DARhoSimpleFoam -python", dict(normalizeStates=NS, normalizeResiduals=list(nres)), caseDir=d, _lib_path=lib_path)
+    W = synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=th)
+    return mesh, orc, sol, W
+
+
+def segments(mesh, ndof):
+    nC = mesh.n_cells
+    return (("U", 0, 3 * nC), ("p", 3 * nC, 4 * nC), ("T", 4 * nC, 5 * nC), ("nuTilda", 5 * nC, 6 * nC), ("phi", 6 * nC, ndof))
+
+
+def check_forward(lib_path, tol=1e-10):
+    for cfg in CONFIGS:
+        mesh, orc, sol, W = setup_comp(cfg, lib_path)
+        assert sol.getNLocalAdjointStates() == orc.ndof == 6 * mesh.n_cells + mesh.n_faces
+        sol.updateOFFields(W)
+        W2 = np.zeros(orc.ndof)
+        sol.getOFFields(W2)
+        assert np.array_equal(W, W2)
+        for isPC in (0, 1):
+            R = np.zeros(orc.ndof)
+            sol.getResiduals(R, isPC)
+            Ro = orc.residual(W, isPC)
+            for name, a, b in segments(mesh, orc.ndof):
+                e = rel_err(R[a:b], Ro[a:b])
+                assert e < tol, (cfg[:6], isPC, name, e)
+
+
+def test_compressible_residual_parity_host_build():
+    check_forward(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_compressible_residual_parity_cuda():
+    check_forward(None)
