@@ -26,7 +26,8 @@ namespace dab
 DAB_HD double sgn(double x) { return x < 0.0 ? -1.0 : 1.0; }
 
 // adjoint of saSource with seed z: accumulates into ntb, gUb[9], gNb[3]
-DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const double* gN, double z, double& ntb, double* gUb, double* gNb, int fv3)
+DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const double* gN, double z, double& ntb, double* gUb, double* gNb, int fv3,
+                        double* nub = nullptr) // nub: adjoint of the laminar viscosity (compressible: nu = mu(T)/rho)
 {
     const double chi = nt / nu;
     const double c3 = chi * chi * chi, den1 = c3 + SA::Cv1c;
@@ -79,6 +80,7 @@ DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const 
         const double df3 = ((fv1 + chi * dfv1) * Bq + den * dBq) / SA::Cv2;
         const double chib = Stb * (df3 * Omega + df2v * nt / ky2);
         ntb += chib / nu;
+        if (nub) *nub -= chib * nt / (nu * nu);
     }
     else if (b1)
     {
@@ -89,6 +91,7 @@ DAB_HD void saSourceAdj(double nt, double nu, double y, const double* gU, const 
         const double fv1b = fv2b * chi * chi / (den * den);
         chib += fv1b * 3.0 * chi * chi * SA::Cv1c / (den1 * den1);
         ntb += chib / nu;
+        if (nub) *nub -= chib * nt / (nu * nu);
     }
     else
         Omegab += SA::Cs * Stb;

@@ -14,6 +14,7 @@
 #include "fwd_kernels.hpp"
 #include "rev_kernels.hpp"
 #include "comp_kernels.hpp"
+#include "comp_rev_kernels.hpp"
 #include "krylov.hpp"
 #include "primal_kernels.hpp"
 #include "geom_kernels.hpp"
@@ -38,6 +39,10 @@ template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constex
 template <int NF, int FEAT> struct LaunchTraits<UEqnAssemble<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cFwdB<NF>> { static constexpr int minBlocks = 2; };
+template <int NF> struct LaunchTraits<cRevB<NF>> { static constexpr int minBlocks = 2; };
+template <int NF> struct LaunchTraits<cRevA<NF>> { static constexpr int minBlocks = 3; };
+template <int NF> struct LaunchTraits<cRevE<NF>> { static constexpr int minBlocks = 3; };
+template <int NF> struct LaunchTraits<cRevC<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cFwdE<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cFwdC<NF>> { static constexpr int minBlocks = 4; };
 #endif
@@ -149,6 +154,7 @@ struct Solver
     // state (internal working copies with ghost slots) and external-layout mirror
     DevBuf<double> dWext, dU, dP, dNt, dPhi, dT;
     DevBuf<double> rRho, rNuL, rMuE, rAE, rHe, rEk, rGHe; // compressible closures
+    DevBuf<double> aGHeb, aTdir, aCRho, aCNu, aCMuE, aCAE, aCHe, aCEk;
     StateView sv;
     // forward record and reverse work arrays
     DevBuf<double> rNut, rGU, rGP, rGNt, rRAU, rHbyA, rD0, rFlag;
@@ -580,6 +586,14 @@ struct Solver
         av.mt = aMt.p; av.Dn = aDn.p; av.Udir = aUdir.p; av.pdir = aPdir.p; av.gPb = aGPb.p; av.gUb = aGUb.p;
         av.gNtb = aGNtb.p; av.nutb = aNutb.p; av.U2 = aU2.p; av.nt2 = aNt2.p;
         av.bcRefb = nullptr; av.bcMask = 0;
+        av.gHeb = av.Tdir = av.cRho = av.cNu = av.cMuE = av.cAE = av.cHe = av.cEk = nullptr;
+        if (par.comp)
+        {
+            aGHeb.alloc(be, 3 * nT); aTdir.alloc(be, nC); aCRho.alloc(be, nC); aCNu.alloc(be, nC); aCMuE.alloc(be, nC);
+            aCAE.alloc(be, nC); aCHe.alloc(be, nC); aCEk.alloc(be, nC);
+            av.gHeb = aGHeb.p; av.Tdir = aTdir.p; av.cRho = aCRho.p; av.cNu = aCNu.p; av.cMuE = aCMuE.p; av.cAE = aCAE.p;
+            av.cHe = aCHe.p; av.cEk = aCEk.p;
+        }
         dR.alloc(be, nd); dX.alloc(be, nd); dY2.alloc(be, nd);
     }
 
@@ -750,11 +764,13 @@ struct Solver
         const size_t nC = hm.nC;
         PsiView v;
         v.U = x;
+        v.T = nullptr;
         if (!comm.active())
         {
             v.p = x + 3 * nC;
-            v.nt = x + 4 * nC;
-            v.phi = x + (par.turb ? 5 : 4) * nC;
+            v.T = par.comp ? x + 4 * nC : nullptr;
+            v.nt = x + (par.comp ? 5 : 4) * nC;
+            v.phi = x + (size_t)nCellStates() * nC;
             return v;
         }
         const int nT = hm.nCtot;
@@ -782,8 +798,17 @@ struct Solver
 
     void matVecDev(const double* x, double* y)
     {
-        requireIncompressible("dRdWT*psi");
         ensureRecorded();
+        if (par.comp)
+        {
+            // DARhoSimpleFoam reverse sweep (comp_rev_kernels.hpp), one GPU
+            const PsiView pv = psiView(x);
+            DAB_LAUNCH_NF(hm.nC, cRevA, mv, par, sv, rv, av, pv);
+            DAB_LAUNCH_NF(hm.nC, cRevB, mv, par, sv, rv, av, pv, y);
+            DAB_LAUNCH_NF(hm.nC, cRevE, mv, par, sv, rv, av, pv, y);
+            DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, y);
+            return;
+        }
         const int nT = hm.nCtot;
         if (!comm.active())
         {

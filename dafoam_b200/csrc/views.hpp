@@ -102,6 +102,9 @@ struct AdjView
     double* nt2;   // [nC]        nuTilda adjoint from stage R2
     double* bcRefb; // [3][nC] or null: per-cell partial adjoint of the U boundary reference value of the patches in bcMask
     unsigned bcMask;
+    // compressible (DARhoSimpleFoam): adjoints of the cell closures and of T
+    double* gHeb;                               // [3][nCtot] adjoint of grad(he)
+    double *Tdir, *cRho, *cNu, *cMuE, *cAE, *cHe, *cEk; // [nC]
 };
 
 struct FaceRef
@@ -336,6 +339,43 @@ DAB_HD double nutSpalding(double magUp, double dl, double nu, double& dM)
     const double fu = -y / nu - magUp / (ut * ut) + P * dkdu / E;
     const double dut = -fm / fu;
     dM = 2.0 * ut * dut / den - ut * ut * dl / (den * den);
+    return nutw;
+}
+
+// the same with the derivative w.r.t. the laminar viscosity as well (compressible: nu_w = mu(T_w)/rho_w is a variable)
+DAB_HD double nutSpalding2(double magUp, double dl, double nu, double& dM, double& dNu)
+{
+    const double kappa = 0.41, E = 9.8, ROOTVSMALL = 1.0e-150;
+    const double y = 1.0 / dl, G = magUp * dl;
+    dM = 0.0;
+    dNu = 0.0;
+    double ut = sqrt(nu * G);
+    if (!(ut > ROOTVSMALL)) return 0.0;
+    for (int it = 0; it < 1000; it++)
+    {
+        const double kUu = fmin(kappa * magUp / ut, 50.0);
+        const double fk = exp(kUu) - 1.0 - kUu * (1.0 + 0.5 * kUu);
+        const double f = -ut * y / nu + magUp / ut + (fk - kUu * kUu * kUu / 6.0) / E;
+        const double df = y / nu + magUp / (ut * ut) + kUu * fk / ut / E;
+        const double un = ut + f / df;
+        const double err = fabs((ut - un) / ut);
+        ut = un;
+        if (!(ut > ROOTVSMALL) || err < 1.0e-14) break;
+    }
+    if (!(ut > 0.0)) return 0.0;
+    const double den = G + ROOTVSMALL;
+    const double nutw = ut * ut / den - nu;
+    if (!(nutw > 0.0)) return 0.0;
+    const double k0 = kappa * magUp / ut;
+    const bool clip = !(k0 < 50.0);
+    const double k = clip ? 50.0 : k0;
+    const double P = exp(k) - 1.0 - k - 0.5 * k * k;
+    const double dkdm = clip ? 0.0 : kappa / ut, dkdu = clip ? 0.0 : -kappa * magUp / (ut * ut);
+    const double fm = 1.0 / ut + P * dkdm / E;
+    const double fu = -y / nu - magUp / (ut * ut) + P * dkdu / E;
+    const double fn = ut * y / (nu * nu);
+    dM = 2.0 * ut * (-fm / fu) / den - ut * ut * dl / (den * den);
+    dNu = 2.0 * ut * (-fn / fu) / den - 1.0;
     return nutw;
 }
 

@@ -66,10 +66,47 @@ def check_forward(lib_path, tol=1e-10):
                 assert e < tol, (cfg[:6], isPC, name, e)
 
 
+def check_reverse(lib_path, tol=1e-10):
+    """dRdW^T psi of the hand-derived compressible reverse sweep (comp_rev_kernels.hpp) vs the oracle's tape."""
+    worst = 0.0
+    for cfg in CONFIGS:
+        mesh, orc, sol, W = setup_comp(cfg, lib_path)
+        sol.updateOFFields(W)
+        orc.record(W)
+        rng = np.random.default_rng(4321)
+        for trial in range(2):
+            psi = rng.uniform(-1, 1, orc.ndof) if trial == 0 else np.full(orc.ndof, 1e-3)
+            y = np.zeros(orc.ndof)
+            sol.calcdRdWTPsiAD(psi, y)
+            yo = orc.jtvec(psi)
+            for name, a, b in segments(mesh, orc.ndof):
+                e = rel_err(y[a:b], yo[a:b])
+                worst = max(worst, e)
+                assert e < tol, (cfg[:6], trial, name, e)
+        # linearity and reproducibility of the operator
+        a_, b_ = rng.uniform(-1, 1, orc.ndof), rng.uniform(-1, 1, orc.ndof)
+        ya, yb, yab, ya2 = (np.zeros(orc.ndof) for _ in range(4))
+        sol.calcdRdWTPsiAD(a_, ya)
+        sol.calcdRdWTPsiAD(b_, yb)
+        sol.calcdRdWTPsiAD(2.0 * a_ - 3.0 * b_, yab)
+        sol.calcdRdWTPsiAD(a_, ya2)
+        assert np.array_equal(ya, ya2) and rel_err(yab, 2.0 * ya - 3.0 * yb) < 1e-12
+    return worst
+
+
 def test_compressible_residual_parity_host_build():
     check_forward(HOSTSIM)
+
+
+def test_compressible_transpose_product_parity_host_build():
+    assert check_reverse(HOSTSIM) < 1e-10
 
 
 @pytest.mark.gpu
 def test_compressible_residual_parity_cuda():
     check_forward(None)
+
+
+@pytest.mark.gpu
+def test_compressible_transpose_product_parity_cuda():
+    assert check_reverse(None) < 1e-10
