@@ -706,4 +706,127 @@ struct cRevC
     }
 };
 
+// ---- force / moment function (DAFunctionForce.C:79-153 with the compressible devRhoReff = -rho*nuEff*dev(twoSymm(grad U)))
+DAB_HD double cForceFace(const MeshView& m, const Params& q, const StateView& s, const RecordView& r, const ForceSpec& fs, int f, int c,
+                         double seed, double* Ub, double* pb, double* Tb, double* ntb, double* nutPb, double* gUb)
+{
+    const int nT = m.nCtot;
+    const double mS = m.magSf[f];
+    const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+    const double im = 1.0 / mS;
+    const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+    double gUc[9];
+    for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
+    BoundaryPoint bp;
+    boundaryPoint<true>(m, q, s, r, f, c, bp);
+    double Gbd[9];
+    for (int j = 0; j < 3; j++)
+    {
+        const double nG = nh[0] * gUc[j * 3 + 0] + nh[1] * gUc[j * 3 + 1] + nh[2] * gUc[j * 3 + 2];
+        for (int i = 0; i < 3; i++) Gbd[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bp.bu.sng[j] - nG);
+    }
+    const double trb = Gbd[0] + Gbd[4] + Gbd[8];
+    double ed[3] = {fs.dir[0], fs.dir[1], fs.dir[2]};
+    if (fs.mode == 1)
+    {
+        const double rv[3] = {m.Cfx[f] - fs.center[0], m.Cfy[f] - fs.center[1], m.Cfz[f] - fs.center[2]};
+        ed[0] = fs.dir[1] * rv[2] - fs.dir[2] * rv[1];
+        ed[1] = fs.dir[2] * rv[0] - fs.dir[0] * rv[2];
+        ed[2] = fs.dir[0] * rv[1] - fs.dir[1] * rv[0];
+    }
+    double F = 0.0, sj[3];
+    for (int j = 0; j < 3; j++)
+    {
+        double t = 0.0;
+        for (int i = 0; i < 3; i++) t += Sv[i] * (Gbd[j * 3 + i] + Gbd[i * 3 + j]);
+        sj[j] = t - (2.0 / 3.0) * trb * Sv[j];
+        F += (Sv[j] * bp.p - bp.muE * sj[j]) * ed[j];
+    }
+    F *= fs.scale;
+    if (gUb)
+    {
+        BoundaryAdj ba;
+        ba.clear();
+        double Gbb[9];
+        for (int i = 0; i < 9; i++) Gbb[i] = 0.0;
+        double trbb = 0.0;
+        for (int j = 0; j < 3; j++)
+        {
+            const double fb = seed * fs.scale * ed[j];
+            ba.p += Sv[j] * fb;
+            ba.muE -= sj[j] * fb;
+            const double sb = -bp.muE * fb;
+            for (int i = 0; i < 3; i++)
+            {
+                Gbb[j * 3 + i] += Sv[i] * sb;
+                Gbb[i * 3 + j] += Sv[i] * sb;
+            }
+            trbb -= (2.0 / 3.0) * Sv[j] * sb;
+        }
+        Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
+        boundaryGradAdj(nh, Gbb, gUb, ba.sng);
+        boundaryPointAdj<true>(m, q, s, r, f, c, bp, ba, Ub, *pb, *Tb, *ntb, *nutPb);
+    }
+    return F;
+}
+
+struct cForceFwd
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    ForceSpec fs;
+    double* out; // [nBF]
+    DAB_HD void operator()(int b) const
+    {
+        const int f = m.nIF + b;
+        if (!((fs.mask >> m.bPatch[b]) & 1u))
+        {
+            out[b] = 0.0;
+            return;
+        }
+        out[b] = cForceFace(m, q, s, r, fs, f, m.own[f], 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
+};
+
+// seeds every reverse work array of the cell with dF/d(cell variables); cRevC then finishes the sweep
+template <int NF>
+struct cForceRevA
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    ForceSpec fs;
+    double seed;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        double Ub[3] = {0, 0, 0}, pb = 0.0, Tb = 0.0, ntb = 0.0, nutPb = 0.0, gUb[9];
+        for (int i = 0; i < 9; i++) gUb[i] = 0.0;
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            if (!fr.bnd) continue;
+            if (!((fs.mask >> m.bPatch[fr.f - m.nIF]) & 1u)) continue;
+            cForceFace(m, q, s, r, fs, fr.f, c, seed, Ub, &pb, &Tb, &ntb, &nutPb, gUb);
+        }
+        for (int j = 0; j < 3; j++)
+        {
+            a.Udir[(size_t)j * nC + c] = 0.0;
+            a.U2[(size_t)j * nC + c] = Ub[j];
+        }
+        a.pdir[c] = pb;
+        a.Tdir[c] = Tb;
+        a.nt2[c] = ntb;
+        a.nutb[c] = nutPb;
+        a.cRho[c] = a.cNu[c] = a.cMuE[c] = a.cAE[c] = a.cHe[c] = a.cEk[c] = 0.0;
+        for (int i = 0; i < 9; i++) a.gUb[(size_t)i * nT + c] = gUb[i];
+        (void)NF;
+    }
+};
+
 } // namespace dab

@@ -56,12 +56,19 @@ struct StatePtrs
     int nC, turb;
     const double* magSf;
     double sU, sP, sNut, sPhi;
+    double* T = nullptr; // compressible: [U | p | T | nuTilda | phi]
+    double sT = 1.0;
     DAB_HD double* at(int ext, double& scale) const
     {
         if (ext < 3 * nC) { scale = sU; return U + ext; }
         ext -= 3 * nC;
         if (ext < nC) { scale = sP; return p + ext; }
         ext -= nC;
+        if (T)
+        {
+            if (ext < nC) { scale = sT; return T + ext; }
+            ext -= nC;
+        }
         if (turb)
         {
             if (ext < nC) { scale = sNut; return nt + ext; }

@@ -985,12 +985,11 @@ struct Solver
 
     double calcFunction(const std::string& name)
     {
-        requireIncompressible("calcFunction");
         const FunctionDef& f = findFunction(name);
         ensureRecorded();
         if (dFacePart.n < (size_t)hm.nBF + 1) dFacePart.alloc(be, hm.nBF + 1);
-        ForceFwd k{mv, par, sv, rv, forceSpec(f), dFacePart.p};
-        be.launch(hm.nBF, k);
+        if (par.comp) be.launch(hm.nBF, cForceFwd{mv, par, sv, rv, forceSpec(f), dFacePart.p});
+        else be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, forceSpec(f), dFacePart.p});
         std::vector<double> facePart(hm.nBF);
         be.d2h(facePart.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
         // deterministic host summation in face order (the all-reduce of the reference, DAFunctionForce.C:146)
@@ -1031,9 +1030,19 @@ struct Solver
     // [dF/dW]^T * seed, scaled by normalizeStates (DASolver.C:1819-1820)
     void dFdW(const std::string& name, double seed, double* out)
     {
-        requireIncompressible("dF/dW");
         const FunctionDef& f = findFunction(name);
         ensureRecorded();
+        if (par.comp)
+        {
+            be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
+            be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
+            be.zero(av.gHeb, (size_t)3 * hm.nCtot * sizeof(double));
+            DAB_LAUNCH_NF(hm.nC, cForceRevA, mv, par, sv, rv, av, forceSpec(f), seed);
+            DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, dY2.p);
+            be.zero(dY2.p + (size_t)nCellStates() * hm.nC, (size_t)hm.nF * sizeof(double)); // no face-flux dependence
+            be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
+            return;
+        }
         be.zero(av.gUb, (size_t)9 * hm.nCtot * sizeof(double));
         be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
         be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));

@@ -99,11 +99,10 @@ int greedyColour(int n, NbrFn nbr, std::vector<int>& colour)
 
 inline void Solver::pcSymbolic()
 {
-    requireIncompressible("calcdRdWT");
     using detail::CellGraph;
     Krylov& K = kry;
     const int nC = hm.nC, nF = hm.nF, nIF = hm.nIF;
-    const int ns = par.turb ? 5 : 4;
+    const int ns = nCellStates();
     const int offPhi = ns * nC;
     K.n = nDof();
     CellGraph G;
@@ -189,8 +188,7 @@ inline void Solver::pcSymbolic()
         for (int x : cellsBall)
         {
             for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
-            cols.push_back(K.iperm[3 * nC + x]);
-            if (par.turb) cols.push_back(K.iperm[4 * nC + x]);
+            for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
         }
         G.ball(&c, 1, Lfc, cellsBall);
         faces.clear();
@@ -219,8 +217,7 @@ inline void Solver::pcSymbolic()
         for (int x : cellsBall)
         {
             for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
-            cols.push_back(K.iperm[3 * nC + x]);
-            if (par.turb) cols.push_back(K.iperm[4 * nC + x]);
+            for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
         }
         cols.push_back(K.iperm[offPhi + f]);
         std::sort(cols.begin(), cols.end());
@@ -332,6 +329,11 @@ inline void Solver::calcPC()
     if (!K.symbolic) pcSymbolic();
     be.zero(K.dVal.p, (size_t)K.ellSize * sizeof(double));
     StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi};
+    if (par.comp)
+    {
+        sp.T = dT.p;
+        sp.sT = par.sT;
+    }
     // R0 at the unperturbed state with the div(pc) schemes (DASolver::calcdRdWT isPC=1)
     forward(1, K.R0.p, true);
     const int nFd = (int)K.fdStart.size() - 1;
@@ -352,6 +354,11 @@ inline void Solver::calcPC()
         be.d2d(dU.p, dWext.p, 3 * nC * sizeof(double));
         be.d2d(dP.p, dWext.p + 3 * nC, nC * sizeof(double));
         size_t off = 4 * nC;
+        if (par.comp)
+        {
+            be.d2d(dT.p, dWext.p + off, nC * sizeof(double));
+            off += nC;
+        }
         if (par.turb)
         {
             be.d2d(dNt.p, dWext.p + off, nC * sizeof(double));

@@ -612,6 +612,7 @@ struct Work
     // everything the force function needs after a residual evaluation
     BF<T> bU, bP, bNt, bNut;
     std::vector<T> gradU, nutC;
+    std::vector<T> muEB; // compressible: rho_b*nuEff_b on the boundary faces
 };
 
 template <class T>
@@ -1298,7 +1299,12 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
         off += nC;
     }
     for (int f = 0; f < nF; f++) R[off + f] = phiRes[f];
-    (void)wk;
+    if (wk)
+    {
+        wk->bU = bU; wk->bP = bP; wk->bNt = bNt; wk->bNut = bNut;
+        wk->gradU = gradU; wk->nutC = nut;
+        wk->muEB = muEB;
+    }
 }
 
 // DAFunctionForce::calcFunction: sum over the faces of one patch of (Sf*p_b + Sf & devRhoReff_b) . dir
@@ -1326,7 +1332,7 @@ T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int p
             for (int i = 0; i < 3; i++) Gb[i][j] = wk.gradU[((size_t)j * 3 + i) * nC + c] + nh[i] * (wk.bU.sng[wk.bU.at(j, b)] - nG);
         }
         T tr = Gb[0][0] + Gb[1][1] + Gb[2][2];
-        T nuEffB = wk.bNut.val[b] + cs.par.nu;
+        T nuEffB = cs.comp.on ? wk.muEB[b] : T(wk.bNut.val[b] + cs.par.nu); // compressible: devRhoReff = -rho*nuEff*dev(twoSymm(grad U))
         T fv(0.0);
         for (int j = 0; j < 3; j++)
         {
