@@ -236,7 +236,7 @@ DAB_HD void atomicAddD(double* a, double v)
 struct VolCoordAccumR
 {
     MeshView m;
-    int offP, offNt, offPhi, turb;
+    int ns, offPhi; // cell-state rows: U (3 per cell, AoS) then ns-3 scalar blocks; face rows from offPhi
     const double *Rp, *Rm, *psi;
     const int32_t* label;
     const int32_t* slotPoint; // [nC*maxSlots]
@@ -252,8 +252,7 @@ struct VolCoordAccumR
         const int nC = m.nC;
         double s = 0.0;
         for (int j = 0; j < 3; j++) s += psi[3 * c + j] * (Rp[3 * c + j] - Rm[3 * c + j]);
-        s += psi[offP + c] * (Rp[offP + c] - Rm[offP + c]);
-        if (turb) s += psi[offNt + c] * (Rp[offNt + c] - Rm[offNt + c]);
+        for (int b = 3; b < ns; b++) s += psi[(size_t)b * nC + c] * (Rp[(size_t)b * nC + c] - Rm[(size_t)b * nC + c]);
         for (int q = 0; q < m.maxCF; q++)
         {
             const int e = m.cellFaces[(size_t)q * nC + c];

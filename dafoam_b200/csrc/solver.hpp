@@ -915,6 +915,31 @@ struct Solver
     {
         const PatchVelocityDef& d = findPatchVelocity(name);
         setPatchVelocity(name, in);
+        if (par.comp)
+        {
+            // DARhoSimpleFoam: two scalar inputs -> central differences of psi . R on the device kernels (4 residual evaluations,
+            // O(eps^2)); the BC-reference adjoint of the incompressible reverse kernels is the exact alternative
+            const size_t n = nDof();
+            std::vector<double> Rp(n), Rm(n);
+            const double h[2] = {1e-6 * std::max(1.0, std::fabs(in[0])), 1e-6};
+            for (int k = 0; k < 2; k++)
+            {
+                double xp[2] = {in[0], in[1]}, xm[2] = {in[0], in[1]};
+                xp[k] += h[k];
+                xm[k] -= h[k];
+                setPatchVelocity(name, xp);
+                forward(0, dR.p);
+                be.d2h(Rp.data(), dR.p, n * sizeof(double));
+                setPatchVelocity(name, xm);
+                forward(0, dR.p);
+                be.d2h(Rm.data(), dR.p, n * sizeof(double));
+                double sdot = 0.0;
+                for (size_t i = 0; i < n; i++) sdot += psi[i] * (Rp[i] - Rm[i]);
+                product[k] = sdot / (2.0 * h[k]);
+            }
+            setPatchVelocity(name, in);
+            return;
+        }
         const size_t nC = hm.nC;
         if (aBcRefb.n < 3 * nC) aBcRefb.alloc(be, 3 * nC);
         unsigned mask = 0;

@@ -37,7 +37,6 @@ inline void Solver::updateMesh(const double* pts)
 
 inline void Solver::volCoordSetup()
 {
-    requireIncompressible("volCoord");
     VolCoord& Vc = volc;
     if (Vc.ready) return;
     if (comm.active()) throw Error("the volCoord input runs on one GPU in this build");
@@ -185,15 +184,23 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
     if (psi) be.h2d(dX.p, psi, (size_t)nDof() * sizeof(double));
     be.d2d(Vc.dPts.p, Vc.dPts0.p, (size_t)3 * nP * sizeof(double));
     be.zero(Vc.dOut.p, (size_t)3 * nP * sizeof(double));
-    const int offP = 3 * nC, offNt = 4 * nC, offPhi = (par.turb ? 5 : 4) * nC;
+    const int ns = nCellStates(), offPhi = ns * nC;
     ForceSpec fs;
     if (function) fs = forceSpec(*function);
     auto evaluate = [&](double* Rdev, double* Fdev) {
         geometry();
         if (function)
         {
-            DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);
-            be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, fs, Fdev});
+            if (par.comp)
+            {
+                DAB_LAUNCH_NF(hm.nCtot, cFwdA, mv, par, sv, rv);
+                be.launch(hm.nBF, cForceFwd{mv, par, sv, rv, fs, Fdev});
+            }
+            else
+            {
+                DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);
+                be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, fs, Fdev});
+            }
         }
         else
             forward(0, Rdev, false);
@@ -224,7 +231,7 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
                 if (function)
                     be.launch(hm.nBF, VolCoordAccumF{mv, Vc.dF1.p, Vc.dF2.p, la, Vc.dSlotPoint.p, Vc.maxSlots, slot, k, Vc.dEps.p, seed, Vc.dOut.p});
                 else
-                    be.launch(nC, VolCoordAccumR{mv, offP, offNt, offPhi, par.turb, dR.p, Vc.dR2.p, dX.p, la, Vc.dSlotPoint.p, Vc.maxSlots, slot, k,
+                    be.launch(nC, VolCoordAccumR{mv, ns, offPhi, dR.p, Vc.dR2.p, dX.p, la, Vc.dSlotPoint.p, Vc.maxSlots, slot, k,
                                                  Vc.dEps.p, Vc.dOut.p});
             }
         }

@@ -616,7 +616,8 @@ struct Work
 };
 
 template <class T>
-void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk);
+void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk,
+                  const std::vector<T>* bcvIn);
 
 // R(W): DAResidualSimpleFoam::calcResiduals + DASpalartAllmaras::calcResiduals, preceded by
 // DASolver::updateStateBoundaryConditions (BCs + correctNut).
@@ -626,7 +627,7 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
 {
     if (cs.comp.on)
     {
-        residualComp<T>(cs, g, W, isPC, R, wk);
+        residualComp<T>(cs, g, W, isPC, R, wk, bcvIn);
         return;
     }
     std::vector<T> bcvLocal;
@@ -930,7 +931,8 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
 // OpenFOAM semantics restated: heThermo::alphaEff = CpByCpv*(alpha + alphat) (gamma for e, 1 for h); the energy BCs
 // fixedEnergy/gradientEnergy/mixedEnergy reduce, for constant Cp, to T's BC mapped through the linear he(T).
 template <class T>
-void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk)
+void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk,
+                  const std::vector<T>* bcvIn)
 {
     const Topo& t = cs.t;
     const Params& par = cs.par;
@@ -938,8 +940,13 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
     const int nC = t.nC, nF = t.nF, nIF = t.nIF, nBF = t.nBF;
     const bool turb = par.turb != 0;
     SAConst sa;
-    std::vector<T> bcv(cs.bc.value.size());
-    for (size_t i = 0; i < bcv.size(); i++) bcv[i] = T(cs.bc.value[i]);
+    std::vector<T> bcvLocal;
+    if (!bcvIn)
+    {
+        bcvLocal.resize(cs.bc.value.size());
+        for (size_t i = 0; i < bcvLocal.size(); i++) bcvLocal[i] = T(cs.bc.value[i]);
+    }
+    const std::vector<T>& bcv = bcvIn ? *bcvIn : bcvLocal;
     // unpack
     std::vector<T> U((size_t)3 * nC), p(nC), Tt(nC), nt(nC, T(0.0)), phi(nF);
     for (int c = 0; c < nC; c++)

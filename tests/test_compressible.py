@@ -125,6 +125,29 @@ def check_function_and_adjoint(lib_path):
     assert rel_err(orc.jtvec(psi), dFdW) < 2e-5
 
 
+def check_patch_velocity(lib_path):
+    """[dR/d(|U|, aoa)]^T psi for DARhoSimpleFoam (central differences on the device kernels) vs the oracle's tape."""
+    cfg = CONFIGS[0]
+    mesh, orc, sol, W = setup_comp(cfg, lib_path)
+    inp = {"patchV": {"type": "patchVelocity", "patches": ["inout"], "flowAxis": "x", "normalAxis": "y"}}
+    sol.updateDAOption(dict(normalizeStates=NS, normalizeResiduals=list(cfg[7]), inputInfo=inp))
+    sol.updateOFFields(W)
+    x = np.array([50.0, 3.0])
+    a = np.deg2rad(x[1])
+    psi = np.random.default_rng(11).uniform(-1, 1, orc.ndof)
+    prod = np.zeros(2)
+    sol.calcJacTVecProduct("patchV", "patchVelocity", x, "R", "residual", psi, prod)
+    ip = [p["name"] for p in mesh.patches].index("inout")
+    orc.set_bc_value("U", ip, [x[0] * np.cos(a), x[0] * np.sin(a), 0.0])
+    rb = orc.jtvec_bcU(W, psi, ip)
+    ref = np.array([rb[0] * np.cos(a) + rb[1] * np.sin(a), (-rb[0] * x[0] * np.sin(a) + rb[1] * x[0] * np.cos(a)) * np.pi / 180.0])
+    assert np.allclose(prod, ref, rtol=1e-6), (prod, ref)
+
+
+def test_compressible_patch_velocity_product_host_build():
+    check_patch_velocity(HOSTSIM)
+
+
 def test_compressible_function_and_adjoint_solve_host_build():
     check_function_and_adjoint(HOSTSIM)
 
@@ -140,6 +163,11 @@ def test_compressible_transpose_product_parity_host_build():
 @pytest.mark.gpu
 def test_compressible_residual_parity_cuda():
     check_forward(None)
+
+
+@pytest.mark.gpu
+def test_compressible_patch_velocity_product_cuda():
+    check_patch_velocity(None)
 
 
 @pytest.mark.gpu

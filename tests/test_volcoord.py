@@ -84,6 +84,37 @@ def test_volcoord_residual_product_matches_oracle_tape_host_build():
         print(kind, "volCoord product vs oracle tape: %.2e" % err)
 
 
+def run_compressible(lib_path):
+    """DARhoSimpleFoam: the same coloured-FD product on the 6-state layout vs the oracle's tape through the geometry."""
+    from tests.test_compressible import CONFIGS, setup_comp
+    cfg = ("naca", "sensibleInternalEnergy", "const", "SpalartAllmaras", "linearUpwind", "upwind", False, CONFIGS[0][7])
+    mesh, orc, sol, W = setup_comp(cfg, lib_path)
+    sol.updateOFFields(W)
+    nP3 = 3 * sol.getNLocalPoints()
+    pts = np.zeros(nP3)
+    sol.getOFMeshPoints(pts)
+    psi = np.random.default_rng(7).uniform(-1, 1, orc.ndof)
+    prod = np.zeros(nP3)
+    sol.calcJacTVecProduct("aero_vol_coords", "volCoord", pts, "R", "residual", psi, prod)
+    ref = orc.jtvec_xv(W, psi)
+    mask = np.ones((nP3 // 3, 3), dtype=bool)
+    for pch in mesh.patches:
+        if pch["type"] == "symmetry":
+            fp = mesh.faces[pch["start"]:pch["start"] + pch["size"]]
+            mask[np.unique(fp[fp >= 0]), 2] = False
+    mask = mask.ravel()
+    assert rel_err(prod[mask], ref[mask]) < 1e-7
+
+
+def test_volcoord_compressible_host_build():
+    run_compressible(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_volcoord_compressible_cuda():
+    run_compressible(None)
+
+
 def test_volcoord_function_and_mesh_update_host_build():
     run_function_and_mesh_update(HOSTSIM)
 
