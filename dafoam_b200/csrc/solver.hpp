@@ -168,7 +168,7 @@ struct Solver
     Comm comm;
     Halo halo;
     Partition part;
-    DevBuf<double> psiP, psiN, psiPhi; // working copies of the input vector with ghost slots (multi-rank only)
+    DevBuf<double> psiP, psiN, psiPhi, psiT; // working copies of the input vector with ghost slots (multi-rank only)
 
     bool hex6 = false; // every owned cell has exactly 6 faces: the kernels with fully unrolled, break-free face loops apply
     int nCellStates() const { return 4 + (par.comp ? 1 : 0) + (par.turb ? 1 : 0); }
@@ -201,7 +201,6 @@ struct Solver
         }
         if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam")
             throw Error("solver " + solverName + " is not supported (DASimpleFoam; DARhoSimpleFoam: forward residual only)");
-        if (solverName == "DARhoSimpleFoam" && nRanks_ > 1) throw Error("DARhoSimpleFoam runs on one GPU in this build");
         be.init(device);
         if (nRanks == 1)
         {
@@ -708,6 +707,7 @@ struct Solver
         const int nT = hm.nCtot;
         std::vector<HaloItem> it{{dU.p, 3, 3, 1}, {dP.p, 1, 1, nT}};
         if (par.turb) it.push_back({dNt.p, 1, 1, nT});
+        if (par.comp) it.push_back({dT.p, 1, 1, nT});
         halo.exchangeCells(it);
         halo.exchangeFaces({{dPhi.p, 1, 1, hm.nF}});
     }
@@ -721,9 +721,16 @@ struct Solver
         if (par.comp)
         {
             // DARhoSimpleFoam: closures + gradients, momentum/SA rows, energy row, pressure/flux rows (comp_kernels.hpp)
-            DAB_LAUNCH_NF(hm.nCtot, cFwdA, mv, par, sv, rv);
+            DAB_LAUNCH_NF(hm.nCtot, cFwdA, mv, par, sv, rv); // closures of the ghost cells come from their exchanged states
+            if (exchange && comm.active())
+            {
+                std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}, {rv.gHe, 3, 1, nT}};
+                if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
+                halo.exchangeCells(it);
+            }
             DAB_LAUNCH_NF(hm.nC, cFwdB, mv, par, sv, rv, isPC, Rdev);
             DAB_LAUNCH_NF(hm.nC, cFwdE, mv, par, sv, rv, isPC, Rdev);
+            if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
             DAB_LAUNCH_NF(hm.nC, cFwdC, mv, par, sv, rv, Rdev);
             return;
         }
@@ -782,12 +789,19 @@ struct Solver
         }
         be.d2d(psiP.p, x + 3 * nC, nC * sizeof(double));
         std::vector<HaloItem> it{{psiP.p, 1, 1, nT}};
+        if (par.comp)
+        {
+            if (psiT.n < (size_t)nT) psiT.alloc(be, nT);
+            be.d2d(psiT.p, x + 4 * nC, nC * sizeof(double));
+            it.push_back({psiT.p, 1, 1, nT});
+            v.T = psiT.p;
+        }
         if (par.turb)
         {
-            be.d2d(psiN.p, x + 4 * nC, nC * sizeof(double));
+            be.d2d(psiN.p, x + (par.comp ? 5 : 4) * nC, nC * sizeof(double));
             it.push_back({psiN.p, 1, 1, nT});
         }
-        be.d2d(psiPhi.p, x + (par.turb ? 5 : 4) * nC, (size_t)hm.nF * sizeof(double));
+        be.d2d(psiPhi.p, x + (size_t)nCellStates() * nC, (size_t)hm.nF * sizeof(double));
         halo.exchangeCells(it);
         halo.exchangeFaces({{psiPhi.p, 1, 1, hm.nF}});
         v.p = psiP.p;
@@ -803,9 +817,17 @@ struct Solver
         {
             // DARhoSimpleFoam reverse sweep (comp_rev_kernels.hpp), one GPU
             const PsiView pv = psiView(x);
+            const int nTc = hm.nCtot;
             DAB_LAUNCH_NF(hm.nC, cRevA, mv, par, sv, rv, av, pv);
+            if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nTc}, {av.Dn, 1, 1, nTc}, {av.gPb, 3, 1, nTc}});
             DAB_LAUNCH_NF(hm.nC, cRevB, mv, par, sv, rv, av, pv, y);
             DAB_LAUNCH_NF(hm.nC, cRevE, mv, par, sv, rv, av, pv, y);
+            if (comm.active())
+            {
+                std::vector<HaloItem> it{{av.gUb, 9, 1, nTc}, {av.gHeb, 3, 1, nTc}};
+                if (par.turb) it.push_back({av.gNtb, 3, 1, nTc});
+                halo.exchangeCells(it);
+            }
             DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, y);
             return;
         }
@@ -1063,6 +1085,7 @@ struct Solver
             be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
             be.zero(av.gHeb, (size_t)3 * hm.nCtot * sizeof(double));
             DAB_LAUNCH_NF(hm.nC, cForceRevA, mv, par, sv, rv, av, forceSpec(f), seed);
+            if (comm.active()) halo.exchangeCells({{av.gUb, 9, 1, hm.nCtot}});
             DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, dY2.p);
             be.zero(dY2.p + (size_t)nCellStates() * hm.nC, (size_t)hm.nF * sizeof(double)); // no face-flux dependence
             be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));

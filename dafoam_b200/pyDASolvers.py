@@ -175,14 +175,16 @@ class pyDASolvers:
         self._raise(self._L.dab_get_local_to_global(self._h, C.c_int(code), out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out
 
-    def localStateIndex(self, nGlobalCells, nGlobalFaces, turbulent=True):
+    def localStateIndex(self, nGlobalCells, nGlobalFaces, turbulent=True, compressible=False):
         """Indices into the global state vector (reference ordering) of this rank's local state vector."""
         cg = self.getLocalToGlobal("cells")
         fg = self.getLocalToGlobal("faces")
-        ns = 5 if turbulent else 4
+        ns = 4 + int(bool(turbulent)) + int(bool(compressible))
         parts = [(3 * cg[:, None] + np.arange(3)[None, :]).ravel(), 3 * nGlobalCells + cg]
-        if turbulent:
+        if compressible:
             parts.append(4 * nGlobalCells + cg)
+        if turbulent:
+            parts.append((ns - 1) * nGlobalCells + cg)
         parts.append(ns * nGlobalCells + fg)
         return np.concatenate(parts)
 

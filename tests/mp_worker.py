@@ -36,10 +36,17 @@ def main():
     def allreduce(a):
         dist.all_reduce(torch.from_numpy(a))
 
-    mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2) if kind == "naca" else cases.channel(nx=12, ny=8, nz=2)
-    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing" if kind == "naca" else "walls"],
+    comp = kind == "nacacomp"
+    mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2) if kind in ("naca", "nacacomp") else cases.channel(nx=12, ny=8, nz=2)
+    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing" if kind in ("naca", "nacacomp") else "walls"],
                  "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     opts = dict(normalizeStates=NORM_STATES, function=fn, adjEqnOption=dict(gmresRelTol=1e-10, gmresMaxIters=500, gmresRestart=250))
+    solver_name = "DASimpleFoam -python"
+    if comp:
+        # DARhoSimpleFoam on the same decomposition: 6 cell states, looser linear-solver tolerance (p ~ 1e5)
+        solver_name = "DARhoSimpleFoam -python"
+        opts = dict(normalizeStates=dict(U=50.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0), function=fn,
+                    adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=900, gmresRestart=900, pcConLevel=3))
     uid = None
     if cuda:
         # product path: NCCL over NVLink; gloo only broadcasts the unique id
@@ -50,12 +57,12 @@ def main():
     else:
         set_comm_callbacks(exchange, allreduce, HOSTSIM)
     dev = rank if cuda else 0
-    serial = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=dev, _lib_path=lib)
-    par = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=dev, rank=rank, nRanks=world, ncclUniqueId=uid, _lib_path=lib)
+    serial = pyDASolvers(solver_name, opts, caseDir=case_dir, device=dev, _lib_path=lib)
+    par = pyDASolvers(solver_name, opts, caseDir=case_dir, device=dev, rank=rank, nRanks=world, ncclUniqueId=uid, _lib_path=lib)
     nCg, nFg = mesh.n_cells, mesh.n_faces
     assert par.getNGlobalCells() == nCg and serial.getNLocalCells() == nCg
-    idx = par.localStateIndex(nCg, nFg)
-    owned = np.concatenate([np.ones(5 * par.getNLocalCells(), dtype=bool), par.getLocalToGlobal("faceOwned").astype(bool)])
+    idx = par.localStateIndex(nCg, nFg, compressible=comp)
+    owned = np.concatenate([np.ones((6 if comp else 5) * par.getNLocalCells(), dtype=bool), par.getLocalToGlobal("faceOwned").astype(bool)])
     n_cells_total = torch.tensor([par.getNLocalCells()])
     dist.all_reduce(n_cells_total)
     assert int(n_cells_total) == nCg
@@ -63,6 +70,20 @@ def main():
     y = np.zeros(nCg)
     serial.getOFField("yWall", "scalar", y)
     Wg = cases.boundary_layer_state(mesh, y, noise=0.01) if kind == "naca" else None
+    if comp:
+        from oracle.pyoracle import synthetic_state  # a state generator only (no oracle evaluation in this test)
+        from tests.common import rel_err  # noqa: F401
+        import numpy as _np
+        th = cases.default_thermo()
+        Cc = _np.zeros(3 * nCg)
+        serial.getOFField("C", "vector", Cc) if False else None
+        # cell centres and face areas from the mesh points (quad faces)
+        Sf, Cf = cases.quad_face_geometry(mesh)
+        cc = _np.zeros((nCg, 3)); cnt = _np.zeros(nCg)
+        _np.add.at(cc, mesh.owner, Cf); _np.add.at(cnt, mesh.owner, 1.0)
+        _np.add.at(cc, mesh.neighbour, Cf[:mesh.n_internal_faces]); _np.add.at(cnt, mesh.neighbour, 1.0)
+        cc /= cnt[:, None]
+        Wg = synthetic_state(mesh, cc.ravel(), Sf.ravel(), U0=(50.0, 2.0, 0.0), thermo=th)
     if Wg is None:
         Wg = np.zeros(serial.getNLocalAdjointStates())
         serial.getOFFields(Wg)
@@ -103,7 +124,7 @@ def main():
     fp = par.solveLinearEqn(kp, dl, xp)
     assert fs == 0 and fp == 0, (fs, fp, ks.stats.iterations, kp.stats.iterations)
     e4 = np.linalg.norm(xp[owned] - xs[idx][owned]) / np.linalg.norm(xs)
-    assert e4 < 1e-6, e4
+    assert e4 < (1e-3 if comp else 1e-6), e4  # compressible: both solves stop at rtol 1e-6 of an ill-scaled system
     print("rank %d ok: residual %.1e dRdWTPsi %.1e dFdW %.1e psi %.1e (its serial %d, 2 ranks %d)"
           % (rank, e1, e2, e3, e4, ks.stats.iterations, kp.stats.iterations), flush=True)
     dist.barrier()
