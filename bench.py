@@ -151,7 +151,7 @@ def run_reference(args, rank):
     out = {"impl": "reference", "metric": "dRdWTPsi_GCells_per_s", "value": v, "unit": "GCells/s", "n_gpus": args.gpus,
            "steps": len(t_all), "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "DASimpleFoam NACA0012 SA %dx%dx1 O-grid (CPU arm: bounded sample of partitions)" % (ni, nj)},
+           "config": {"workload": args.solver + " NACA0012 SA %dx%dx1 O-grid (CPU arm: bounded sample of partitions)" % (ni, nj)},
            "cpu_baseline": base,
            "e2e": {"value": v, "unit": "GCells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--pc-level", type=int, default=3)
     ap.add_argument("--coarse", type=int, default=1000)
     ap.add_argument("--max-iters", type=int, default=3000)
+    ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam"],
+                    help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000); single GPU")
     ap.add_argument("--primal-iters", type=int, default=0,
                     help="run that many SIMPLE iterations (solvePrimal on the GPU) from the synthetic state before the adjoint legs (1 GPU)")
     args = ap.parse_args()
@@ -214,9 +216,15 @@ def main():
     t_setup = time.time()
     mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1)
     shared = [None]
+    comp = args.solver == "DARhoSimpleFoam"
+    U0c = (100.0, 0.0, 0.0)  # M ~ 0.29 at 300 K
+    thermo = cases.default_thermo() if comp else None
     if rank == 0:
         shared[0] = tempfile.mkdtemp(prefix="dab_bench_")
-        cases.write_case(shared[0], mesh, cases.default_bcs_naca(), binary=True)
+        if comp:
+            cases.write_case(shared[0], mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c)), binary=True, thermo=thermo)
+        else:
+            cases.write_case(shared[0], mesh, cases.default_bcs_naca(), binary=True)
     uid = None
     if world > 1:
         from dafoam_b200.pyDASolvers import nccl_unique_id
@@ -226,13 +234,19 @@ def main():
     case_dir = shared[0]
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
-    opts = dict(normalizeStates=NORM_STATES, function=fn, primalMaxIters=max(args.primal_iters, 1), primalMinResTol=1e-8, printInterval=100,
+    ns_opt = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else NORM_STATES
+    opts = dict(normalizeStates=ns_opt, function=fn, primalMaxIters=max(args.primal_iters, 1), primalMinResTol=1e-8, printInterval=100,
                 adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level, coarseAggregates=args.coarse))
-    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
+    sol = pyDASolvers(args.solver + " -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()
     if world == 1:
-        W = smooth_state(sol, mesh)
+        if comp:
+            y_ = np.zeros(sol.getNLocalCells())
+            sol.getOFField("yWall", "scalar", y_)
+            W = cases.to_compressible_state(mesh, cases.boundary_layer_state(mesh, y_, U0=U0c, seed=1234, noise=0.001), thermo)
+        else:
+            W = smooth_state(sol, mesh)
     else:
         # global analytic state (wall distance by a KD-tree on the wall-face centres), then this rank's slice
         from scipy.spatial import cKDTree
@@ -247,8 +261,10 @@ def main():
         np.add.at(cnt, mesh.neighbour, 1.0)
         Cc /= cnt[:, None]
         yw = cKDTree(Cf[wall["start"]:wall["start"] + wall["size"]]).query(Cc)[0]
-        Wg = cases.boundary_layer_state(mesh, yw, seed=1234, noise=0.001)
-        W = np.ascontiguousarray(Wg[sol.localStateIndex(mesh.n_cells, mesh.n_faces)])
+        Wg = cases.boundary_layer_state(mesh, yw, U0=U0c if comp else (10.0, 0.0, 0.0), seed=1234, noise=0.001)
+        if comp:
+            Wg = cases.to_compressible_state(mesh, Wg, thermo)
+        W = np.ascontiguousarray(Wg[sol.localStateIndex(mesh.n_cells, mesh.n_faces, compressible=comp)])
         del Wg
     sol.updateOFFields(W)
     t_setup = time.time() - t_setup
@@ -338,8 +354,10 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     traffic, traffic_src = None, None
+    if comp:
+        args.no_cpu_baseline = True  # the CPU port leg times the incompressible oracle; not comparable
     tf = os.path.join(ROOT, "profiles", "r01d_ncu_kernels_dram.json")
-    if os.path.exists(tf) and world == 1 and args.cells == 980000:
+    if os.path.exists(tf) and world == 1 and args.cells == 980000 and not comp:
         tj = json.load(open(tf))
         traffic = sum(tj[k]["dram__bytes_read.sum"] + tj[k]["dram__bytes_write.sum"] for k in ("RevA", "RevB", "RevC"))
         traffic_src = "profiles/r01d_ncu_kernels_dram.json (ncu dram__bytes_read+write of RevA+RevB+RevC, same workload)"

@@ -662,6 +662,31 @@ def quad_face_geometry(mesh: PolyMesh):
     return Sf, p.mean(axis=1)
 
 
+def to_compressible_state(mesh: PolyMesh, W, thermo, p0=101325.0, T0=300.0, turbulent=True):
+    """[U|p|nuTilda|phi] -> [U|p0+p|T|nuTilda|rho_f*phi] (DARhoSimpleFoam ordering, mass flux) with a smooth temperature field."""
+    nC, nF, nIF = mesh.n_cells, mesh.n_faces, mesh.n_internal_faces
+    Rg = 8314.4700665 / thermo["molWeight"]
+    U = W[:3 * nC]
+    p = p0 + W[3 * nC:4 * nC]
+    off = 4 * nC
+    nt = None
+    if turbulent:
+        nt = W[off:off + nC]
+        off += nC
+    phi = W[off:off + nF]
+    Um2 = (U.reshape(nC, 3) ** 2).sum(axis=1)
+    Tt = T0 - 0.5 * Um2 / thermo["Cp"] * 0.8  # roughly constant total temperature
+    rho = p / (Rg * Tt)
+    rf = np.empty(nF)
+    rf[:nIF] = 0.5 * (rho[mesh.owner[:nIF]] + rho[mesh.neighbour])
+    rf[nIF:] = rho[mesh.owner[nIF:]]
+    parts = [U, p, Tt]
+    if turbulent:
+        parts.append(nt)
+    parts.append(phi * rf)
+    return np.concatenate(parts)
+
+
 def boundary_layer_state(mesh: PolyMesh, yWall, U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, delta=0.02, turbulent=True,
                          seed=1234, noise=0.0):
     """Smooth analytic state in the reference's state ordering: a velocity

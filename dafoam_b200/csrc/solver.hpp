@@ -894,6 +894,18 @@ struct Solver
     void benchKernel(int which)
     {
         const PsiView pv = psiView(dX.p);
+        if (par.comp)
+        {
+            // DARhoSimpleFoam: 0 cRevA, 1 cRevB, 2 cRevE + cRevC
+            if (which == 0) DAB_LAUNCH_NF(hm.nC, cRevA, mv, par, sv, rv, av, pv);
+            else if (which == 1) DAB_LAUNCH_NF(hm.nC, cRevB, mv, par, sv, rv, av, pv, dY2.p);
+            else
+            {
+                DAB_LAUNCH_NF(hm.nC, cRevE, mv, par, sv, rv, av, pv, dY2.p);
+                DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, dY2.p);
+            }
+            return;
+        }
         if (which == 0) launchRevA(pv);
         else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
         else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
