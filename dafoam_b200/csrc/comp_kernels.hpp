@@ -72,6 +72,12 @@ DAB_HD void boundaryPoint(const MeshView& m, const Params& q, const StateView& s
     bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, b.p, b.sngP, b.frP);
     bcScalar(q.bcKindT[pa], q.bcValT[pa], s.T[c], phib, dl, b.T, b.sngT, b.frT);
     b.th = thermoOf(q, b.p, b.T);
+    if (q.rhoFrozen)
+    {
+        // SIMPLE iterations: the boundary density follows the stored (relaxed) cell density; equal to psi_b*p_b at the fixed point
+        b.th.rho = r.rho[c] * (b.p * s.T[c]) / (s.p[c] * b.T);
+        b.th.nu = b.th.mu / b.th.rho;
+    }
     b.nt = 0.0; b.sngN = 0.0; b.frN = 0.0; b.nut = 0.0;
     if (q.turb)
     {
@@ -100,7 +106,13 @@ struct cFwdA
         const double pc = s.p[c], Tc = s.T[c];
         const double ntc = q.turb ? s.nt[c] : 0.0;
         // cell closures
-        const ThermoPoint th = thermoOf(q, pc, Tc);
+        ThermoPoint th = thermoOf(q, pc, Tc);
+        if (q.rhoFrozen)
+        {
+            // SIMPLE iterations: rho is the relaxed field of the previous iteration (reference pEqnRhoSimple.H rho.relax())
+            th.rho = r.rho[c];
+            th.nu = th.mu / th.rho;
+        }
         const double nut = q.turb ? ntc * fv1f(ntc / th.nu) : 0.0;
         r.rho[c] = th.rho;
         r.nuL[c] = th.nu;

@@ -1,0 +1,448 @@
+// DARhoSimpleFoam primal: equation-assembly kernels of the compressible SIMPLE loop (reference
+// src/adjoint/DASolver/DARhoSimpleFoam/{UEqnRhoSimple,EEqnRhoSimple,pEqnRhoSimple}.H, DARhoSimpleFoam.C:106-164).
+// Same construction as primal_kernels.hpp: each equation is assembled by one cell-parallel gather into a per-cell ELL row
+// with the discretisation of the compressible residual kernels (comp_kernels.hpp), so the fixed point is R(W) = 0.
+// The density is rho = psi*p evaluated from the current (p, T) whenever the closures are refreshed (the reference keeps a
+// relaxed rho field between iterations; both have the same fixed point).
+#pragma once
+#include "comp_kernels.hpp"
+#include "primal_kernels.hpp"
+
+namespace dab
+{
+
+template <int NF>
+struct cUEqnAssemble
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    EqnView e;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const int schU = q.divU;
+        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+        const double muEc = r.muE[c];
+        double gUc[9];
+        for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
+        const double trc = gUc[0] + gUc[4] + gUc[8];
+        double D0 = 0.0, sumOff = 0.0, X[3] = {0.0, 0.0, 0.0};
+        double icMax = 0.0, icMin = 0.0, icAvg = 0.0, icS[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0)
+            {
+                for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
+                break;
+            }
+            const int f = fr.f;
+            const double mf = fr.s * s.phi[f];
+            const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+            const double mS = m.magSf[f], dl = m.delta[f];
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f], wn = 1.0 - wc;
+                const bool pos0 = s.phi[f] >= 0.0;
+                const double wup = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
+                const double Un[3] = {s.U[3 * n], s.U[3 * n + 1], s.U[3 * n + 2]};
+                const double muEn = r.muE[n];
+                const double wp = schU == DIV_LINEAR ? wc : wup;
+                const double a = wp * mf;
+                const double gf = (wc * muEc + wn * muEn) * mS;
+                const double g = gf * dl;
+                const double off = mf - a - g;
+                e.off[(size_t)k * nC + c] = off;
+                D0 += a + g - mf;
+                sumOff += fabs(off);
+                double gUn[9];
+                for (int i = 0; i < 9; i++) gUn[i] = r.gU[(size_t)i * nT + n];
+                if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
+                {
+                    const bool ownUp = s.phi[f] > 0.0;
+                    const bool cUp = fr.s > 0 ? ownUp : !ownUp;
+                    const double* gu = cUp ? gUc : gUn;
+                    const int u = cUp ? c : n;
+                    const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                    double corr[3];
+                    for (int j = 0; j < 3; j++) corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
+                    if (schU == DIV_LINEAR_UPWIND_V)
+                    {
+                        const double wo_ = m.w[f];
+                        const double cf = ownUp ? (1.0 - wo_) : -wo_;
+                        double maxCorr[3];
+                        for (int j = 0; j < 3; j++) maxCorr[j] = cf * fr.s * (Un[j] - Uc[j]);
+                        luvLimit(corr, maxCorr, corr);
+                    }
+                    for (int j = 0; j < 3; j++) X[j] += mf * corr[j];
+                }
+                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                const double wo = m.w[f];
+                const double* gO = fr.s > 0 ? gUc : gUn;
+                const double* gN_ = fr.s > 0 ? gUn : gUc;
+                for (int j = 0; j < 3; j++)
+                {
+                    double cg = 0.0;
+                    for (int i = 0; i < 3; i++) cg += kv[i] * (wo * gO[j * 3 + i] + (1.0 - wo) * gN_[j * 3 + i]);
+                    X[j] -= fr.s * gf * cg;
+                }
+                const double trn = gUn[0] + gUn[4] + gUn[8];
+                for (int j = 0; j < 3; j++)
+                {
+                    const double tc = muEc * (Sv[0] * gUc[0 * 3 + j] + Sv[1] * gUc[1 * 3 + j] + Sv[2] * gUc[2 * 3 + j] - (2.0 / 3.0) * trc * Sv[j]);
+                    const double tn = muEn * (Sv[0] * gUn[0 * 3 + j] + Sv[1] * gUn[1 * 3 + j] + Sv[2] * gUn[2 * 3 + j] - (2.0 / 3.0) * trn * Sv[j]);
+                    X[j] -= fr.s * (wc * tc + wn * tn);
+                }
+            }
+            else
+            {
+                e.off[(size_t)k * nC + c] = 0.0;
+                BoundaryPoint bp;
+                boundaryPoint<true>(m, q, s, r, f, c, bp);
+                const double im = 1.0 / mS;
+                const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+                const double G = bp.muE * mS;
+                D0 -= mf;
+                double mx = 0.0, mn = 0.0, av = 0.0;
+                for (int j = 0; j < 3; j++)
+                {
+                    const double ic = mf * bp.bu.vic[j] - G * bp.bu.gic[j];
+                    const double aic = fabs(ic);
+                    if (j == 0) { mx = aic; mn = ic; }
+                    else { mx = aic > mx ? aic : mx; mn = ic < mn ? ic : mn; }
+                    av += ic;
+                    icS[j] += ic;
+                    X[j] += mf * bp.bu.val[j] - G * bp.bu.sng[j] - ic * Uc[j];
+                }
+                icMax += mx; icMin += mn; icAvg += av / 3.0;
+                double Gb[9];
+                for (int j = 0; j < 3; j++)
+                {
+                    const double nG = nh[0] * gUc[j * 3 + 0] + nh[1] * gUc[j * 3 + 1] + nh[2] * gUc[j * 3 + 2];
+                    for (int i = 0; i < 3; i++) Gb[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bp.bu.sng[j] - nG);
+                }
+                const double trb = Gb[0] + Gb[4] + Gb[8];
+                for (int j = 0; j < 3; j++)
+                {
+                    const double x = Sv[0] * Gb[0 * 3 + j] + Sv[1] * Gb[1 * 3 + j] + Sv[2] * Gb[2 * 3 + j] - (2.0 / 3.0) * trb * Sv[j];
+                    X[j] -= bp.muE * x;
+                }
+            }
+        }
+        const double V = m.V[c];
+        const double D1 = D0 + icMax;
+        const double aD1 = fabs(D1);
+        const double D2 = aD1 > sumOff ? aD1 : sumOff;
+        const double Dn = D2 / q.alphaU - icMin;
+        r.rAU[c] = V / (Dn + icAvg);
+        for (int j = 0; j < 3; j++)
+        {
+            e.diag[(size_t)j * nC + c] = Dn + icS[j];
+            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j];
+        }
+        (void)NF;
+    }
+};
+
+// energy equation for he: div(phi,he) + div(phi,Ekp|K) - laplacian(alphaEff,he), relaxed
+template <int NF>
+struct cEEqnAssemble
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    EqnView e;
+    double alphaE;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const int schE = q.divE;
+        const double heA = q.heIsE ? (q.Cp - q.Rg) : q.Cp;
+        const double hec = r.he[c], aEc = r.aE[c], Ekc = r.Ek[c];
+        double gHc[3];
+        for (int i = 0; i < 3; i++) gHc[i] = r.gHe[(size_t)i * nT + c];
+        double D0 = 0.0, sumOff = 0.0, X = 0.0, ic = 0.0, aic = 0.0;
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0)
+            {
+                for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
+                break;
+            }
+            const int f = fr.f;
+            const double mf = fr.s * s.phi[f];
+            const double mS = m.magSf[f], dl = m.delta[f];
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f], wn = 1.0 - wc;
+                const bool pos0 = s.phi[f] >= 0.0;
+                const double wup = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
+                const double wp = schE == DIV_LINEAR ? wc : wup;
+                const double a = wp * mf;
+                const double gf = (wc * aEc + wn * r.aE[n]) * mS;
+                const double g = gf * dl;
+                const double off = mf - a - g;
+                e.off[(size_t)k * nC + c] = off;
+                D0 += a + g - mf;
+                sumOff += fabs(off);
+                if (schE == DIV_LINEAR_UPWIND)
+                {
+                    const bool ownUp = s.phi[f] > 0.0;
+                    const bool cUp = fr.s > 0 ? ownUp : !ownUp;
+                    const int u = cUp ? c : n;
+                    const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                    double corr = 0.0;
+                    for (int i = 0; i < 3; i++) corr += d[i] * r.gHe[(size_t)i * nT + u];
+                    X += mf * corr;
+                }
+                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                double cg = 0.0;
+                for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gHc[i] + wn * r.gHe[(size_t)i * nT + n]);
+                X -= fr.s * gf * cg;
+                const double wk = q.divEkp == DIV_LINEAR ? wc : wup;
+                X += mf * (wk * Ekc + (1.0 - wk) * r.Ek[n] - Ekc);
+            }
+            else
+            {
+                e.off[(size_t)k * nC + c] = 0.0;
+                BoundaryPoint bp;
+                boundaryPoint<true>(m, q, s, r, f, c, bp);
+                const double sngH = heA * bp.sngT;
+                const double icf = mf * (1.0 - bp.frT) + bp.aE * mS * bp.frT * dl;
+                ic += icf;
+                aic += fabs(icf);
+                D0 -= mf;
+                X += mf * bp.th.he - bp.aE * mS * sngH - icf * hec;
+                X += mf * (bp.Ek - Ekc);
+            }
+        }
+        const double D1 = D0 + aic;
+        const double aD1 = fabs(D1);
+        const double D2 = aD1 > sumOff ? aD1 : sumOff;
+        const double Dn = D2 / alphaE - ic;
+        e.diag[c] = Dn + ic;
+        e.b[c] = -X + (Dn - D0) * hec;
+        (void)NF;
+    }
+};
+
+struct RhoRelax // rho <- rho + alpha (psi p - rho)   (rho = thermo.rho(); rho.relax())
+{
+    Params q;
+    StateView s;
+    double* rho;
+    double alpha;
+    DAB_HD void operator()(int c) const
+    {
+        const double rn = s.p[c] / (q.Rg * s.T[c]);
+        rho[c] += alpha * (rn - rho[c]);
+    }
+};
+
+struct TFromHe // T = (he - heB)/heA on the owned cells
+{
+    Params q;
+    const double* he;
+    double* T;
+    DAB_HD void operator()(int c) const
+    {
+        const double heA = q.heIsE ? (q.Cp - q.Rg) : q.Cp;
+        T[c] = (he[c] + q.Cp * q.TRef) / heA;
+    }
+};
+
+// phiHbyA on a boundary face without the density factor (constrainHbyA rule)
+DAB_HD double cPhBoundary(const MeshView& m, const Params& q, const RecordView& r, const BoundaryPoint& bp, int f, int c)
+{
+    const int nT = m.nCtot;
+    const int kU = q.bcKind[F_U][m.bPatch[f - m.nIF]];
+    const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
+    if (q.constrainHbyA && !assignable) return m.Sx[f] * bp.bu.val[0] + m.Sy[f] * bp.bu.val[1] + m.Sz[f] * bp.bu.val[2];
+    return m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c];
+}
+
+// pressure equation div(phiHbyA) - laplacian(rho rAU, p) = 0, sign-flipped to the SPD form
+template <int NF>
+struct cPEqnAssemble
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    EqnView e;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        double D = 0.0, B = 0.0;
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0)
+            {
+                for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
+                break;
+            }
+            const int f = fr.f;
+            const double mS = m.magSf[f], dl = m.delta[f];
+            if (!fr.bnd)
+            {
+                const int o = fr.s > 0 ? c : fr.n, n = fr.s > 0 ? fr.n : c;
+                const double w = m.w[f];
+                double ph = 0.0, cg = 0.0;
+                const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                for (int j = 0; j < 3; j++)
+                {
+                    ph += Sv[j] * (w * r.HbyA[(size_t)j * nT + o] + (1.0 - w) * r.HbyA[(size_t)j * nT + n]);
+                    cg += kv[j] * (w * r.gP[(size_t)j * nT + o] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
+                }
+                const double rhof = w * r.rho[o] + (1.0 - w) * r.rho[n];
+                const double gam = (w * r.rho[o] * r.rAU[o] + (1.0 - w) * r.rho[n] * r.rAU[n]) * mS;
+                e.off[(size_t)k * nC + c] = -gam * dl;
+                D += gam * dl;
+                B -= fr.s * (rhof * ph - gam * cg);
+            }
+            else
+            {
+                e.off[(size_t)k * nC + c] = 0.0;
+                BoundaryPoint bp;
+                boundaryPoint<false>(m, q, s, r, f, c, bp);
+                const double gb = bp.th.rho * r.rAU[c] * mS * dl * bp.frP;
+                D += gb;
+                B += gb * q.bcVal[F_P][m.bPatch[f - m.nIF]][0] - bp.th.rho * cPhBoundary(m, q, r, bp, f, c);
+            }
+        }
+        e.diag[c] = D;
+        e.b[c] = B;
+        (void)NF;
+    }
+};
+
+template <int NF>
+struct cPhiUpdate
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    double* phi;
+    DAB_HD void operator()(int c) const
+    {
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            if (fr.s < 0) continue;
+            const int f = fr.f;
+            if (!fr.bnd)
+                phi[f] = cFaceF(m, s, r, f, c, fr.n);
+            else
+            {
+                BoundaryPoint bp;
+                boundaryPoint<false>(m, q, s, r, f, c, bp);
+                phi[f] = bp.th.rho * cPhBoundary(m, q, r, bp, f, c) - bp.th.rho * r.rAU[c] * m.magSf[f] * bp.sngP;
+            }
+        }
+        (void)NF;
+    }
+};
+
+// nuTilda equation, compressible form (DASpalartAllmaras.C:452-462 with rho)
+template <int NF>
+struct cNutEqnAssemble
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    EqnView e;
+    double alphaN;
+    DAB_HD void operator()(int c) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const int schN = q.divNut;
+        const double ntc = s.nt[c], rhoc = r.rho[c], nuc = r.nuL[c];
+        const double Gc = rhoc * (ntc + nuc) / SA::sigma;
+        double gUc[9], gNc[3];
+        for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
+        for (int i = 0; i < 3; i++) gNc[i] = r.gNt[(size_t)i * nT + c];
+        double D0 = 0.0, sumOff = 0.0, X = 0.0, ic = 0.0, aic = 0.0;
+        for (int k = 0; k < m.maxCF; k++)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0)
+            {
+                for (int kk = k; kk < m.maxCF; kk++) e.off[(size_t)kk * nC + c] = 0.0;
+                break;
+            }
+            const int f = fr.f;
+            const double mf = fr.s * s.phi[f];
+            const double mS = m.magSf[f], dl = m.delta[f];
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f], wn = 1.0 - wc;
+                const bool pos0 = s.phi[f] >= 0.0;
+                const double wup = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
+                const double ntn = s.nt[n];
+                const double wp = schN == DIV_LINEAR ? wc : wup;
+                const double a = wp * mf;
+                const double gf = (wc * Gc + wn * r.rho[n] * (ntn + r.nuL[n]) / SA::sigma) * mS;
+                const double g = gf * dl;
+                const double off = mf - a - g;
+                e.off[(size_t)k * nC + c] = off;
+                D0 += a + g - mf;
+                sumOff += fabs(off);
+                if (schN == DIV_LINEAR_UPWIND)
+                {
+                    const bool ownUp = s.phi[f] > 0.0;
+                    const bool cUp = fr.s > 0 ? ownUp : !ownUp;
+                    const int u = cUp ? c : n;
+                    const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
+                    double corr = 0.0;
+                    for (int i = 0; i < 3; i++) corr += d[i] * r.gNt[(size_t)i * nT + u];
+                    X += mf * corr;
+                }
+                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                double cg = 0.0;
+                for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gNc[i] + wn * r.gNt[(size_t)i * nT + n]);
+                X -= fr.s * gf * cg;
+            }
+            else
+            {
+                e.off[(size_t)k * nC + c] = 0.0;
+                BoundaryPoint bp;
+                boundaryPoint<true>(m, q, s, r, f, c, bp);
+                const double Gs = bp.th.rho * (bp.nt + bp.th.nu) / SA::sigma * mS;
+                const double icf = mf * (1.0 - bp.frN) + Gs * bp.frN * dl;
+                ic += icf;
+                aic += fabs(icf);
+                D0 -= mf;
+                X += mf * bp.nt - Gs * bp.sngN - icf * ntc;
+            }
+        }
+        const double V = m.V[c], y = m.yWall[c];
+        const double P = saSource(ntc, nuc, y, gUc, gNc, q.saFv3);
+        const double St = saStilda(ntc, nuc, y, gUc, q.saFv3);
+        const double mg2 = gNc[0] * gNc[0] + gNc[1] * gNc[1] + gNc[2] * gNc[2];
+        const double expl = -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * ntc;
+        const double sp = ntc != 0.0 ? (P - expl) / ntc : 0.0;
+        D0 += V * rhoc * sp;
+        X += V * rhoc * expl;
+        const double D1 = D0 + aic;
+        const double aD1 = fabs(D1);
+        const double D2 = aD1 > sumOff ? aD1 : sumOff;
+        const double Dn = D2 / alphaN - ic;
+        e.diag[c] = Dn + ic;
+        e.b[c] = -X + (Dn - D0) * ntc;
+        (void)NF;
+    }
+};
+
+} // namespace dab

@@ -725,7 +725,7 @@ struct FillConst
 struct PrimalStats
 {
     int iterations = 0, converged = 0, pIterations = 0;
-    double maxRes = 0.0, resU[3] = {0, 0, 0}, resP = 0.0, resN = 0.0, sec = 0.0;
+    double maxRes = 0.0, resU[3] = {0, 0, 0}, resP = 0.0, resN = 0.0, resE = 0.0, sec = 0.0;
 };
 
 struct SegControl
@@ -738,14 +738,15 @@ struct SegControl
 struct Primal
 {
     // system/fvSolution + DAOption (reference dafoam/pyDAFoam.py: primalMinResTol, primalMinResTolDiff, primalMinIters, primalVarBounds)
-    double alphaP = 0.3, alphaN = 0.7;
+    double alphaP = 0.3, alphaN = 0.7, alphaE = 0.7, alphaRho = 0.05;
     double minResTol = 1e-8, minResTolDiff = 1e2;
     int minIters = 1, maxIters = 1000, nNonOrth = 0, printInterval = 100;
-    SegControl cU, cP, cN;
+    SegControl cU, cP, cN, cE;
     double ntMin = 1e-16, ntMax = 1e16;
+    double pMin = 20000.0, pMax = 500000.0, TMin = 100.0, TMax = 1000.0, UMax = 1000.0; // DAOption primalVarBounds (compressible)
     bool allocated = false;
     DevBuf<double> uOff, uDiag, uB, pOff, pDiag, pB, nOff, nDiag, nB;
-    DevBuf<double> Utmp, pOld, ntTmp, red, ones, r, z, d, q;
+    DevBuf<double> Utmp, pOld, ntTmp, red, ones, r, z, d, q, eOff, eDiag, eB, heTmp;
     DevBuf<int32_t> dColourOf, dColourList;
     std::vector<int> colourStart; // [nColours+1] into dColourList
     // pressure coarse space

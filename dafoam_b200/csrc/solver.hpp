@@ -18,6 +18,7 @@
 #include "krylov.hpp"
 #include "primal_kernels.hpp"
 #include "geom_kernels.hpp"
+#include "comp_primal_kernels.hpp"
 #include "partition.hpp"
 #include "comm.hpp"
 #include <cstdlib>
@@ -39,6 +40,11 @@ template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constex
 template <int NF, int FEAT> struct LaunchTraits<UEqnAssemble<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cFwdB<NF>> { static constexpr int minBlocks = 2; };
+template <int NF> struct LaunchTraits<cUEqnAssemble<NF>> { static constexpr int minBlocks = 2; };
+template <int NF> struct LaunchTraits<cEEqnAssemble<NF>> { static constexpr int minBlocks = 3; };
+template <int NF> struct LaunchTraits<cNutEqnAssemble<NF>> { static constexpr int minBlocks = 3; };
+template <int NF> struct LaunchTraits<cPEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
+template <int NF> struct LaunchTraits<cPhiUpdate<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cRevB<NF>> { static constexpr int minBlocks = 2; };
 template <int NF> struct LaunchTraits<cRevA<NF>> { static constexpr int minBlocks = 3; };
 template <int NF> struct LaunchTraits<cRevE<NF>> { static constexpr int minBlocks = 3; };
@@ -337,7 +343,10 @@ struct Solver
         {
             const Dict& rf = fso.sub("relaxationFactors");
             if (rf.hasSub("fields")) primal.alphaP = rf.sub("fields").scalarOr("p", primal.alphaP);
+            if (rf.hasSub("fields")) primal.alphaRho = rf.sub("fields").scalarOr("rho", primal.alphaRho);
             if (rf.hasSub("equations")) primal.alphaN = rf.sub("equations").scalarOr("nuTilda", primal.alphaN);
+            if (rf.hasSub("equations"))
+                primal.alphaE = rf.sub("equations").scalarOr("e", rf.sub("equations").scalarOr("h", primal.alphaE));
         }
         if (fso.hasSub("SIMPLE")) primal.nNonOrth = (int)fso.sub("SIMPLE").scalarOr("nNonOrthogonalCorrectors", 0.0);
         if (fso.hasSub("solvers"))
@@ -352,6 +361,8 @@ struct Solver
             ctl("U", primal.cU);
             ctl("p", primal.cP);
             ctl("nuTilda", primal.cN);
+            ctl("e", primal.cE);
+            ctl("h", primal.cE);
         }
         if (fileExists(caseDir + "/system/controlDict"))
         {
@@ -444,11 +455,19 @@ struct Solver
         {
             primal.nAgg = (int)ps->numOr("coarseAggregates", primal.nAgg);
             primal.coarseRefresh = std::max(1, (int)ps->numOr("coarseRefresh", primal.coarseRefresh));
+            primal.alphaRho = ps->numOr("rhoRelax", primal.alphaRho);
+            primal.alphaE = ps->numOr("heRelax", primal.alphaE);
+            primal.alphaP = ps->numOr("pRelax", primal.alphaP);
         }
         if (const JVal* vb = o.get("primalVarBounds"))
         {
             primal.ntMin = vb->numOr("nuTildaMin", primal.ntMin);
             primal.ntMax = vb->numOr("nuTildaMax", primal.ntMax);
+            primal.pMin = vb->numOr("pMin", primal.pMin);
+            primal.pMax = vb->numOr("pMax", primal.pMax);
+            primal.TMin = vb->numOr("TMin", primal.TMin);
+            primal.TMax = vb->numOr("TMax", primal.TMax);
+            primal.UMax = vb->numOr("UMax", primal.UMax);
         }
         if (const JVal* fd = o.get("function"))
         {

@@ -11,7 +11,6 @@ namespace dab
 
 inline void Solver::primalSetup()
 {
-    requireIncompressible("solvePrimal");
     Primal& P = primal;
     if (P.allocated) return;
     if (comm.active()) throw Error("solvePrimal runs on one GPU in this build (the adjoint path is the multi-GPU one)");
@@ -22,6 +21,10 @@ inline void Solver::primalSetup()
     P.Utmp.alloc(be, 3 * nT); P.pOld.alloc(be, nT); P.ntTmp.alloc(be, nT);
     P.red.alloc(be, 6 * nC); P.ones.alloc(be, nC);
     P.r.alloc(be, nC); P.z.alloc(be, nT); P.d.alloc(be, nT); P.q.alloc(be, nC);
+    if (par.comp)
+    {
+        P.eOff.alloc(be, mcf * nC); P.eDiag.alloc(be, nC); P.eB.alloc(be, nC); P.heTmp.alloc(be, nT);
+    }
     be.launch((int)nC, FillConst{P.ones.p, 1.0});
     primalOps.init(be, nullptr, 8);
     P.ops = &primalOps;
@@ -247,7 +250,72 @@ inline int Solver::solvePrimal(PrimalStats& st)
     st = PrimalStats();
     double maxRes = 0.0;
     int it = 0;
-    for (it = 1; it <= P.maxIters; it++)
+    EqnView eE{nC, hm.maxCF, 1, P.eOff.p, P.eDiag.p, P.eB.p, mv.cellNbr};
+    Params pp = par; // the primal kernels see the stored, relaxed density
+    if (par.comp)
+    {
+        DAB_LAUNCH_NF(nT, cFwdA, mv, par, sv, rv); // rho = psi*p of the initial state
+        pp.rhoFrozen = 1;
+    }
+    for (it = 1; par.comp && it <= P.maxIters; it++)
+    {
+        // ---- DARhoSimpleFoam: UEqnRhoSimple.H, EEqnRhoSimple.H, pEqnRhoSimple.H, turbulence.correct()
+        maxRes = -1e10;
+        be.d2d(P.pOld.p, dP.p, (size_t)nT * sizeof(double));
+        DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+        DAB_LAUNCH_NF(nC, cUEqnAssemble, mv, pp, sv, rv, eU);
+        primalJacobi(eU, dU.p, P.Utmp.p, rv.gP, P.cU, st.resU);
+        {
+            double s3[3] = {st.resU[0], st.resU[1], st.resU[2]};
+            std::sort(s3, s3 + 3);
+            maxRes = std::max(maxRes, s3[1]);
+        }
+        // energy: solve for he, T from he (thermo.correct())
+        DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+        DAB_LAUNCH_NF(nC, cEEqnAssemble, mv, pp, sv, rv, eE, P.alphaE);
+        {
+            double re[3];
+            primalJacobi(eE, rv.he, P.heTmp.p, nullptr, P.cE, re);
+            st.resE = re[0];
+            maxRes = std::max(maxRes, re[0]);
+            be.launch(nC, TFromHe{pp, rv.he, dT.p});
+            be.launch(nC, BoundField{dT.p, P.TMin, P.TMax}); // DAUtility::boundVar
+        }
+        // pressure corrector
+        DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+        be.launch(nC, HbyAKernel{eU, sv, rv, mv.V, nT});
+        DAB_LAUNCH_NF(nC, cPEqnAssemble, mv, pp, sv, rv, eP);
+        if (it == 1 || (it - 1) % P.coarseRefresh == 0) primalCoarseRefresh(eP);
+        {
+            double rp;
+            st.pIterations += primalPcg(eP, dP.p, P.cP, rp);
+            st.resP = rp;
+            maxRes = std::max(maxRes, rp);
+        }
+        DAB_LAUNCH_NF(nC, cPhiUpdate, mv, pp, sv, rv, dPhi.p);
+        be.launch(nC, RelaxField{dP.p, P.pOld.p, P.alphaP});
+        be.launch(nC, BoundField{dP.p, P.pMin, P.pMax});
+        be.launch(nC, RhoRelax{pp, sv, rv.rho, P.alphaRho});
+        DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv); // grad of the relaxed p, closures at the new (p, T)
+        be.launch(nC, UCorrect{rv, dU.p, nT});
+        be.launch(3 * nC, BoundField{dU.p, -P.UMax, P.UMax});
+        if (par.turb)
+        {
+            DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+            DAB_LAUNCH_NF(nC, cNutEqnAssemble, mv, pp, sv, rv, eN, P.alphaN);
+            double rn[3];
+            primalJacobi(eN, dNt.p, P.ntTmp.p, nullptr, P.cN, rn);
+            st.resN = rn[0];
+            maxRes = std::max(maxRes, rn[0]);
+            be.launch(nC, BoundField{dNt.p, P.ntMin, P.ntMax});
+        }
+        if (printInfo && (it % P.printInterval == 0 || it == 1))
+            fprintf(stderr, "[dab200] SIMPLE %5d  U %.3e %.3e %.3e  he %.3e  p %.3e  nuTilda %.3e\n", it, st.resU[0], st.resU[1], st.resU[2], st.resE,
+                    st.resP, st.resN);
+        if (!(maxRes == maxRes)) break;
+        if (maxRes < P.minResTol && it > P.minIters) break;
+    }
+    for (it = par.comp ? it : 1; !par.comp && it <= P.maxIters; it++)
     {
         maxRes = -1e10;
         be.d2d(P.pOld.p, dP.p, (size_t)nT * sizeof(double)); // p.storePrevIter()
@@ -301,6 +369,11 @@ inline int Solver::solvePrimal(PrimalStats& st)
         be.d2d(dWext.p, dU.p, 3 * n * sizeof(double));
         be.d2d(dWext.p + 3 * n, dP.p, n * sizeof(double));
         size_t off = 4 * n;
+        if (par.comp)
+        {
+            be.d2d(dWext.p + off, dT.p, n * sizeof(double));
+            off += n;
+        }
         if (par.turb)
         {
             be.d2d(dWext.p + off, dNt.p, n * sizeof(double));

@@ -48,6 +48,7 @@ struct Params
     double Rg, Cp, muC, Pr, Prt, As, Ts, TRef, sT;
     int bcKindT[MAXP];
     double bcValT[MAXP];
+    int rhoFrozen;            // primal loop only: the cell density is the stored (relaxed) field, not p/(R T)
 };
 
 // internal working state (ghost slots appended to the cell arrays)

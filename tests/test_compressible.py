@@ -144,6 +144,37 @@ def check_patch_velocity(lib_path):
     assert np.allclose(prod, ref, rtol=1e-6), (prod, ref)
 
 
+def check_primal(lib_path):
+    """DARhoSimpleFoam::solvePrimal on the device: the SIMPLE fixed point is the root of the compressible residual (oracle),
+    and equals the oracle's Newton-converged state."""
+    from tests.test_converged_primal import newton
+    mesh = cases.channel(nx=14, ny=8, nz=1)
+    bcs = cases.compressible_bcs(cases.default_bcs_channel(U0=(60.0, 0.0, 0.0)))
+    th = cases.default_thermo()
+    d = tempfile.mkdtemp(prefix="dab_cprimal_")
+    cases.write_case(d, mesh, bcs, thermo=th)
+    sol = pyDASolvers("DARhoSimpleFoam -python", dict(normalizeStates=NS, primalMinResTol=1e-12, primalMaxIters=3000), caseDir=d, _lib_path=lib_path)
+    orc = Oracle(mesh, bcs, normalizeStates=NS, normalizeResiduals=NRES, thermo=th)
+    n = orc.ndof
+    W0 = np.zeros(n)
+    sol.getOFFields(W0)
+    assert sol.solvePrimal() == 0
+    st = sol.primalStats
+    assert st.converged == 1 and 10 < st.iterations < 3000
+    W = np.zeros(n)
+    sol.getOFFields(W)
+    r0, r1 = np.linalg.norm(orc.residual(W0)), np.linalg.norm(orc.residual(W))
+    assert r1 < 1e-8 * r0, (r0, r1)
+    Wn = newton(orc, W.copy() * (1.0 + 1e-6), tol=1e-7 * r0 * 1e-3, maxit=20)
+    for name, a, b in segments(mesh, n):
+        err = np.linalg.norm(W[a:b] - Wn[a:b]) / np.linalg.norm(Wn[a:b])
+        assert err < 1e-7, (name, err)
+
+
+def test_compressible_primal_fixed_point_host_build():
+    check_primal(HOSTSIM)
+
+
 def test_compressible_patch_velocity_product_host_build():
     check_patch_velocity(HOSTSIM)
 
@@ -163,6 +194,11 @@ def test_compressible_transpose_product_parity_host_build():
 @pytest.mark.gpu
 def test_compressible_residual_parity_cuda():
     check_forward(None)
+
+
+@pytest.mark.gpu
+def test_compressible_primal_fixed_point_cuda():
+    check_primal(None)
 
 
 @pytest.mark.gpu
