@@ -26,7 +26,36 @@ def golden_case(kind):
     return mesh, bcs, fpatch, ipatch, name
 
 
+NS_COMP = dict(U=50.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0)
+NRES_COMP = ("URes", "pRes", "TRes", "nuTildaRes", "phiRes")
+
+
+def golden_spec(kind):
+    """Everything needed to rebuild the case of a golden file: the two original kinds plus the SA-fv3 and DARhoSimpleFoam ones."""
+    if kind in ("naca", "channel"):
+        mesh, bcs, fpatch, ipatch, name = golden_case(kind)
+        return dict(mesh=mesh, bcs=bcs, fpatch=fpatch, name=name, solver="DASimpleFoam", ras="SpalartAllmaras", thermo=None, ns=NORM_STATES,
+                    nres=("URes", "pRes", "nuTildaRes", "phiRes"))
+    mesh = cases.naca0012_ogrid(ni=24, nj=12, nk=1)
+    if kind == "nacafv3":
+        return dict(mesh=mesh, bcs=cases.default_bcs_naca(), fpatch="wing", name="naca_safv3_24x12", solver="DASimpleFoam",
+                    ras="SpalartAllmarasFv3", thermo=None, ns=NORM_STATES, nres=("URes", "pRes", "nuTildaRes", "phiRes"))
+    if kind == "nacacomp":
+        return dict(mesh=mesh, bcs=cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0))), fpatch="wing", name="naca_rhosimple_24x12",
+                    solver="DARhoSimpleFoam", ras="SpalartAllmaras", thermo=cases.default_thermo(), ns=NS_COMP, nres=NRES_COMP)
+    raise ValueError(kind)
+
+
+def oracle_of(spec):
+    return Oracle(spec["mesh"], spec["bcs"], normalizeStates=spec["ns"], normalizeResiduals=spec["nres"], rasModel=spec["ras"], thermo=spec["thermo"])
+
+
 def state_for(kind, mesh, orc):
+    if kind == "nacacomp":
+        from oracle.pyoracle import synthetic_state
+        return synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=cases.default_thermo(), noise=0.01)
+    if kind == "nacafv3":
+        return cases.boundary_layer_state(mesh, orc.geometry("yWall"))
     if kind == "naca":
         return cases.boundary_layer_state(mesh, orc.geometry("yWall"))
     from oracle.pyoracle import synthetic_state
@@ -34,11 +63,12 @@ def state_for(kind, mesh, orc):
 
 
 def compute(kind):
-    mesh, bcs, fpatch, ipatch, name = golden_case(kind)
-    orc = Oracle(mesh, bcs, normalizeStates=NORM_STATES)
+    spec = golden_spec(kind)
+    mesh, name = spec["mesh"], spec["name"]
+    orc = oracle_of(spec)
     W = state_for(kind, mesh, orc)
     names = [p["name"] for p in mesh.patches]
-    fi, ii = names.index(fpatch), names.index(ipatch)
+    fi = names.index(spec["fpatch"])
     R = orc.residual(W)
     Rpc = orc.residual(W, 1)
     orc.record(W)
@@ -53,7 +83,8 @@ def compute(kind):
 
 
 if __name__ == "__main__":
-    for kind in ("naca", "channel"):
+    only = sys.argv[1:] or ("naca", "channel", "nacafv3", "nacacomp")
+    for kind in only:
         name, data = compute(kind)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)
         print(name, {k: (float(np.linalg.norm(v)) if np.ndim(v) else float(v)) for k, v in data.items()})

@@ -13,16 +13,19 @@ from dafoam_b200 import cases
 from dafoam_b200.pyDASolvers import pyDASolvers
 from oracle.pyoracle import Oracle
 from tests.common import HOSTSIM, NORM_STATES, ROOT, rel_err
-from tests.golden.make_golden import golden_case
+from tests.golden.make_golden import golden_spec, oracle_of
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-@pytest.mark.parametrize("kind", ["naca", "channel"])
+KINDS = ["naca", "channel", "nacafv3", "nacacomp"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
 def test_oracle_reproduces_golden(kind):
-    mesh, bcs, fpatch, ipatch, name = golden_case(kind)
-    g = np.load(os.path.join(GOLD, name + ".npz"))
-    orc = Oracle(mesh, bcs, normalizeStates=NORM_STATES)
+    spec = golden_spec(kind)
+    g = np.load(os.path.join(GOLD, spec["name"] + ".npz"))
+    orc = oracle_of(spec)
     assert rel_err(orc.residual(g["W"]), g["R"]) < 1e-13
     assert rel_err(orc.residual(g["W"], 1), g["Rpc"]) < 1e-13
     orc.record(g["W"])
@@ -31,13 +34,18 @@ def test_oracle_reproduces_golden(kind):
 
 
 def engine_vs_golden(kind, lib_path, tol=1e-11):
-    mesh, bcs, fpatch, ipatch, name = golden_case(kind)
-    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec = golden_spec(kind)
+    mesh, bcs, fpatch = spec["mesh"], spec["bcs"], spec["fpatch"]
+    g = np.load(os.path.join(GOLD, spec["name"] + ".npz"))
     d = tempfile.mkdtemp(prefix="dab_gold_")
-    cases.write_case(d, mesh, bcs)
+    kw = dict(ras_model=spec["ras"])
+    if spec["thermo"] is not None:
+        kw["thermo"] = spec["thermo"]
+    cases.write_case(d, mesh, bcs, **kw)
     fn = {"F": {"type": "force", "source": "patchToFace", "patches": [fpatch], "directionMode": "fixedDirection",
                 "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
-    sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=NORM_STATES, function=fn), caseDir=d, _lib_path=lib_path)
+    sol = pyDASolvers(spec["solver"] + " -python", dict(normalizeStates=spec["ns"], normalizeResiduals=list(spec["nres"]), function=fn),
+                      caseDir=d, _lib_path=lib_path)
     W = np.ascontiguousarray(g["W"])
     n = W.size
     sol.updateOFFields(W)
@@ -55,13 +63,13 @@ def engine_vs_golden(kind, lib_path, tol=1e-11):
     assert rel_err(dF, g["dFdW"]) < tol
 
 
-@pytest.mark.parametrize("kind", ["naca", "channel"])
+@pytest.mark.parametrize("kind", KINDS)
 def test_engine_host_build_reproduces_golden(kind):
     engine_vs_golden(kind, HOSTSIM)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["naca", "channel"])
+@pytest.mark.parametrize("kind", KINDS)
 def test_engine_cuda_reproduces_golden(kind):
     # FMA contraction on the GPU + 8 orders of magnitude of cell volumes on the O-grid: 5e-10 observed
     engine_vs_golden(kind, None, tol=5e-9)
