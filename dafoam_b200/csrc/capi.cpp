@@ -211,6 +211,20 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
         else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
         return 0;
     }
+    if (it == "patchVar")
+    {
+        need(input_name, "input_name");
+        need(input, "input");
+        if (ot == "residual") S.patchVarProduct(input_name, input, seed, nullptr, 1.0, product);
+        else if (ot == "function")
+        {
+            need(output_name, "output_name");
+            const std::string fn(output_name);
+            S.patchVarProduct(input_name, input, nullptr, &fn, seed[0], product);
+        }
+        else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
+        return 0;
+    }
     if (it == "volCoord")
     {
         // daInput->run: assign the point coordinates (DAInputVolCoord.C:35-70), then the transposed product
@@ -229,7 +243,7 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
         else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
         return 0;
     }
-    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar, patchVelocity, volCoord)");
+    if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar, patchVelocity, patchVar, volCoord)");
     // daInput->run(inputList): assign the input to the OpenFOAM fields (DAInputStateVar.C:35-140)
     if (input) S.updateOFFields(input);
     if (ot == "residual") S.matVec(seed, product);
@@ -330,8 +344,14 @@ int dab_set_solver_input(dab_solver* s, const char* input_name, const char* inpu
         if ((size_t)input_size != S.hm.points.size()) throw Error("setSolverInput: volCoord has the wrong size");
         S.updateMesh(inputs);
     }
+    else if (it == "patchVar")
+    {
+        need(input_name, "input_name");
+        if (input_size != S.findPatchVar(input_name).nComp) throw Error("setSolverInput: patchVar has the wrong size");
+        S.setPatchVar(input_name, inputs);
+    }
     else
-        throw Error("setSolverInput: inputType " + it + " is not supported (patchVelocity, stateVar, volCoord)");
+        throw Error("setSolverInput: inputType " + it + " is not supported (patchVelocity, patchVar, stateVar, volCoord)");
     DAB_CATCH
 }
 
@@ -399,6 +419,7 @@ int dab_get_input_size(dab_solver* s, const char* name, const char* type, int64_
     if (std::string(type) == "stateVar") *out = s->s.nDof();
     else if (std::string(type) == "patchVelocity") *out = 2;
     else if (std::string(type) == "volCoord") *out = (int64_t)s->s.hm.points.size();
+    else if (std::string(type) == "patchVar") { need(name, "name"); *out = s->s.findPatchVar(name).nComp; }
     else throw Error(std::string("getInputSize: unsupported input type ") + type);
     DAB_CATCH
 }

@@ -112,6 +112,15 @@ struct PatchVelocityDef
     double Umag = 0.0, aoaDeg = 0.0; // last assigned values (DAGlobalVar::patchVelocity role)
 };
 
+// DAInputPatchVar (reference src/adjoint/DAInput/DAInputPatchVar.C): the boundary reference value of one field on some patches
+struct PatchVarDef
+{
+    std::string name, varName;
+    int field = -1;   // F_U, F_P, F_NUTILDA, or -2 for T
+    int nComp = 1;
+    std::vector<int> patches;
+};
+
 struct FunctionDef
 {
     std::string name, type;              // type: force | moment
@@ -152,6 +161,7 @@ struct Solver
     int pcConLevel = 2; // cell-to-cell connectivity level of dRdWTPC (maxResConLv4JacPCMat role)
     std::vector<FunctionDef> functions;
     std::vector<PatchVelocityDef> patchVelocities;
+    std::vector<PatchVarDef> patchVars;
 
     // device mesh
     DevBuf<int32_t> dOwn, dNei, dCellFaces, dCellNbr, dBPatch;
@@ -299,6 +309,10 @@ struct Solver
         Dict fs = readDict(caseDir + "/system/fvSchemes");
         auto scheme = [&](const std::string& key) {
             std::string v = fs.sub("divSchemes").joined(key);
+            // the steady solvers of the reference run `bounded Gauss ...` convection (boundedConvectionScheme: - fvm::Sp(div(phi)));
+            // the kernels have that form built in
+            if (v.find("bounded") == std::string::npos)
+                throw Error("divSchemes " + key + " '" + v + "': only 'bounded Gauss <scheme>' is supported");
             if (v.find("linearUpwindV") != std::string::npos)
             {
                 if (key != "div(phi,U)") throw Error("linearUpwindV applies to vector fields only (" + key + ")");
@@ -518,6 +532,36 @@ struct Solver
         }
         if (const JVal* ii = o.get("inputInfo"))
         {
+            patchVars.clear();
+            for (const auto& kv : ii->obj)
+            {
+                if (kv.second.strOr("type", "") != "patchVar") continue;
+                PatchVarDef d;
+                d.name = kv.first;
+                d.varName = kv.second.strOr("varName", "");
+                const std::string vt = kv.second.strOr("varType", "scalar");
+                if (vt != "scalar" && vt != "vector") throw Error("inputInfo." + kv.first + ": varType not valid");
+                d.nComp = vt == "vector" ? 3 : 1;
+                if (d.varName == "U") d.field = F_U;
+                else if (d.varName == "p") d.field = F_P;
+                else if (d.varName == "nuTilda") d.field = F_NUTILDA;
+                else if (d.varName == "T" && par.comp) d.field = -2;
+                else throw Error("inputInfo." + kv.first + ": varName " + d.varName + " is not a boundary field of this solver");
+                if ((d.field == F_U) != (d.nComp == 3)) throw Error("inputInfo." + kv.first + ": varType does not match " + d.varName);
+                if (const JVal* pl = kv.second.get("patches"))
+                    for (const auto& pn : pl->arr)
+                    {
+                        int found = -1;
+                        for (size_t p = 0; p < hm.patches.size(); p++)
+                            if (hm.patches[p].name == pn.str) found = (int)p;
+                        if (found < 0) throw Error("inputInfo." + kv.first + ": unknown patch " + pn.str);
+                        const int kind = d.field == -2 ? par.bcKindT[found] : par.bcKind[d.field][found];
+                        if (kind != BC_FIXED_VALUE && kind != BC_INLET_OUTLET && kind != BC_OUTLET_INLET)
+                            throw Error("inputInfo." + kv.first + ": patch type not valid! only support fixedValue or inletOutlet");
+                        d.patches.push_back(found);
+                    }
+                patchVars.push_back(d);
+            }
             patchVelocities.clear();
             for (const auto& kv : ii->obj)
             {
@@ -962,6 +1006,72 @@ struct Solver
     }
 
     DevBuf<double> aBcRefb;
+
+    // ---- patchVar input (DAInputPatchVar): assignment and products by central differences on the device kernels
+    const PatchVarDef& findPatchVar(const std::string& name) const
+    {
+        for (const auto& d : patchVars)
+            if (d.name == name) return d;
+        throw Error("input " + name + " (patchVar) is not defined in inputInfo");
+    }
+    void setPatchVar(const std::string& name, const double* in)
+    {
+        const PatchVarDef& d = findPatchVar(name);
+        for (int p : d.patches)
+        {
+            if (d.field == -2) par.bcValT[p] = in[0];
+            else
+                for (int k = 0; k < d.nComp; k++) par.bcVal[d.field][p][k] = in[k];
+        }
+        recorded = false;
+        kry.pcValid = false;
+    }
+    double patchVarStep(const PatchVarDef& d, double x) const
+    {
+        const double sc = d.field == F_U ? par.sU : (d.field == F_P ? par.sP : (d.field == F_NUTILDA ? par.sNut : par.sT));
+        // compromise between the round-off of psi.(R+ - R-) (R ~ 1e6 for compressible cases) and the kinks of the limited schemes:
+        // accurate to ~1e-4; the exact alternative is the BC-reference adjoint of the reverse kernels (patchVelocity has it)
+        return std::max(1e-6 * std::fabs(sc), 1e-4 * std::fabs(x));
+    }
+    // product[nComp] = [dR/d(value)]^T psi, or seed * dF/d(value) when fname is given
+    void patchVarProduct(const std::string& name, const double* in, const double* psi, const std::string* fname, double seed, double* product)
+    {
+        const PatchVarDef& d = findPatchVar(name);
+        const size_t n = nDof();
+        std::vector<double> Rp, Rm, x(in, in + d.nComp);
+        if (!fname) { Rp.resize(n); Rm.resize(n); }
+        for (int k = 0; k < d.nComp; k++)
+        {
+            const double h = patchVarStep(d, in[k]);
+            double vp = 0.0, vm = 0.0;
+            for (int sgn = 0; sgn < 2; sgn++)
+            {
+                std::vector<double> xx(x);
+                xx[k] += sgn == 0 ? h : -h;
+                setPatchVar(name, xx.data());
+                if (fname) (sgn == 0 ? vp : vm) = calcFunction(*fname);
+                else
+                {
+                    forward(0, dR.p);
+                    be.d2h(sgn == 0 ? Rp.data() : Rm.data(), dR.p, n * sizeof(double));
+                }
+            }
+            if (fname) product[k] = seed * (vp - vm) / (2.0 * h);
+            else
+            {
+                double sdot = 0.0;
+                for (size_t i = 0; i < n; i++) sdot += psi[i] * (Rp[i] - Rm[i]);
+                if (comm.active())
+                {
+                    be.h2d(dY2.p, &sdot, sizeof(double));
+                    comm.allreduceSum(be, dY2.p, 1);
+                    be.d2h(&sdot, dY2.p, sizeof(double));
+                }
+                product[k] = sdot / (2.0 * h);
+            }
+        }
+        setPatchVar(name, in);
+    }
 
     // product[2] = [dR/d(|U|, aoa)]^T psi
     void patchVelocityProduct(const std::string& name, const double* in, const double* psi, double* product)

@@ -1599,7 +1599,11 @@ void orc_jtvec_xv(void* h, const double* W, const double* psi, double* out /*3*n
 
 // calcJacTVecProduct(patchVelocity -> residual) building block: [dR/d(U reference value of one patch)]^T psi
 // (the reference sets the patch values from (|U|, angle of attack) in DAInputPatchVelocity)
-void orc_jtvec_bcU(void* h, const double* W, const double* psi, int patch, double* out3)
+void orc_jtvec_bc(void* h, const double* W, const double* psi, int field, int patch, double* out3);
+void orc_jtvec_bcU(void* h, const double* W, const double* psi, int patch, double* out3) { orc_jtvec_bc(h, W, psi, F_U, patch, out3); }
+
+// [dR/d(boundary reference value of `field` on `patch`)]^T psi (DAInputPatchVar / DAInputPatchVelocity through the tape)
+void orc_jtvec_bc(void* h, const double* W, const double* psi, int field, int patch, double* out3)
 {
     Case* cs = (Case*)h;
     Tape& tp = tape();
@@ -1610,7 +1614,7 @@ void orc_jtvec_bcU(void* h, const double* W, const double* psi, int patch, doubl
     int ids[3];
     for (int k = 0; k < 3; k++)
     {
-        AReal& a = bcv[(F_U * cs->t.nPatch + patch) * 3 + k];
+        AReal& a = bcv[(field * cs->t.nPatch + patch) * 3 + k];
         a.registerInput();
         ids[k] = a.id;
     }

@@ -177,6 +177,14 @@ class Oracle:
         lib().orc_jtvec_bcU(self.h, _p(W), _p(psi), C.c_int(patch), _p(out))
         return out
 
+    def jtvec_bc(self, W, psi, field, patch):
+        """[dR/d(boundary reference value of `field` on `patch`)]^T psi (3 numbers; scalars use the first)."""
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        out = np.zeros(3)
+        lib().orc_jtvec_bc(self.h, _p(W), _p(psi), C.c_int(FIELDS.index(field)), C.c_int(patch), _p(out))
+        return out
+
     def set_bc_value(self, field, patch, value):
         v = np.zeros(3)
         v[:len(np.atleast_1d(value))] = value

@@ -94,3 +94,41 @@ def test_total_derivative_host_build():
 @pytest.mark.gpu
 def test_total_derivative_cuda():
     check(None)
+
+
+def check_patch_var(lib_path):
+    """DAInputPatchVar (scalar and vector boundary values): [dR/dx]^T psi of the engine (central differences on the device
+    kernels) against the oracle's tape, incompressible and compressible."""
+    from tests.common import setup
+    from tests.test_compressible import CONFIGS, setup_comp
+    inp = {"nutilda_in": {"type": "patchVar", "varName": "nuTilda", "varType": "scalar", "patches": ["inout"]},
+           "U_in": {"type": "patchVar", "varName": "U", "varType": "vector", "patches": ["inout"]},
+           "p_out": {"type": "patchVar", "varName": "p", "varType": "scalar", "patches": ["inout"]}}
+    for comp in (False, True):
+        if comp:
+            mesh, orc, sol, W = setup_comp(CONFIGS[0], lib_path)
+            sol.updateDAOption(dict(normalizeStates=dict(U=50.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0), inputInfo=inp))
+            vals = {"nutilda_in": [6e-5], "U_in": [49.0, 3.0, 0.0], "p_out": [101000.0]}
+        else:
+            mesh, bcs, orc, sol, W, _ = setup("naca", True, lib_path=lib_path, extra_options=dict(inputInfo=inp))
+            vals = {"nutilda_in": [6e-5], "U_in": [9.5, 0.7, 0.0], "p_out": [0.3]}
+        sol.updateOFFields(W)
+        ip = [p["name"] for p in mesh.patches].index("inout")
+        psi = np.random.default_rng(5).uniform(-1, 1, orc.ndof)
+        for name, field in (("nutilda_in", "nuTilda"), ("U_in", "U"), ("p_out", "p")):
+            x = np.array(vals[name])
+            assert sol.getInputSize(name, "patchVar") == len(x)
+            prod = np.zeros(len(x))
+            sol.calcJacTVecProduct(name, "patchVar", x, "R", "residual", psi, prod)
+            orc.set_bc_value(field, ip, x)
+            ref = orc.jtvec_bc(W, psi, field, ip)[:len(x)]
+            assert np.allclose(prod, ref, rtol=1e-3, atol=1e-6 * np.abs(ref).max()), (comp, name, prod, ref)
+
+
+def test_patch_var_products_host_build():
+    check_patch_var(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_patch_var_products_cuda():
+    check_patch_var(None)
