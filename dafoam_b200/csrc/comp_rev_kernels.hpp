@@ -719,6 +719,32 @@ DAB_HD double cForceFace(const MeshView& m, const Params& q, const StateView& s,
     for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
     BoundaryPoint bp;
     boundaryPoint<true>(m, q, s, r, f, c, bp);
+    if (fs.mode >= 2)
+    {
+        const double U2 = bp.bu.val[0] * bp.bu.val[0] + bp.bu.val[1] * bp.bu.val[1] + bp.bu.val[2] * bp.bu.val[2];
+        const double wA = mS / fs.areaSum;
+        const double SU = Sv[0] * bp.bu.val[0] + Sv[1] * bp.bu.val[1] + Sv[2] * bp.bu.val[2];
+        const double F = fs.scale * (fs.mode == 2 ? (bp.p + 0.5 * bp.th.rho * U2) * wA : bp.th.rho * SU);
+        if (gUb)
+        {
+            const double fb = seed * fs.scale;
+            BoundaryAdj ba;
+            ba.clear();
+            if (fs.mode == 2)
+            {
+                ba.p += fb * wA;
+                ba.rho += fb * wA * 0.5 * U2;
+                for (int j = 0; j < 3; j++) ba.val[j] += fb * wA * bp.th.rho * bp.bu.val[j];
+            }
+            else
+            {
+                ba.rho += fb * SU;
+                for (int j = 0; j < 3; j++) ba.val[j] += fb * bp.th.rho * Sv[j];
+            }
+            boundaryPointAdj<true>(m, q, s, r, f, c, bp, ba, Ub, *pb, *Tb, *ntb, *nutPb);
+        }
+        return F;
+    }
     double Gbd[9];
     for (int j = 0; j < 3; j++)
     {

@@ -606,8 +606,10 @@ struct ForceSpec
     unsigned mask; // bit p set: patch p contributes
     double dir[3]; // force direction, or the moment axis
     double scale;
-    int mode;      // 0: force . dir (DAFunctionForce.C:79-153); 1: ((Cf - center) x force) . dir (DAFunctionMoment.C)
+    int mode;      // 0: force . dir (DAFunctionForce.C:79-153); 1: ((Cf - center) x force) . dir (DAFunctionMoment.C);
+                   // 2: area-averaged total pressure p + 0.5 rho |U|^2 (DAFunctionTotalPressure.C); 3: mass flow rate rho U.Sf (DAFunctionMassFlowRate.C)
     double center[3];
+    double areaSum; // mode 2: total area of the function's faces (all ranks)
 };
 
 // boundary-face force contribution and (optionally) its adjoint w.r.t. the cell's variables
@@ -628,6 +630,23 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
     bcVector(kU, q.bcVal[F_U][pa], Uc, phib, dl, nh, bu);
     double pv, snp, frp;
     bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, snp, frp);
+    if (fs.mode >= 2)
+    {
+        // patch reductions of the boundary values (incompressible: rho = 1)
+        const double U2 = bu.val[0] * bu.val[0] + bu.val[1] * bu.val[1] + bu.val[2] * bu.val[2];
+        const double wA = mS / fs.areaSum;
+        const double F = fs.scale * (fs.mode == 2 ? (pv + 0.5 * U2) * wA : Sv[0] * bu.val[0] + Sv[1] * bu.val[1] + Sv[2] * bu.val[2]);
+        if (gUb)
+        {
+            const double fb = seed * fs.scale;
+            double valb[3];
+            const double sngb[3] = {0.0, 0.0, 0.0};
+            for (int j = 0; j < 3; j++) valb[j] = fs.mode == 2 ? fb * wA * bu.val[j] : fb * Sv[j];
+            bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
+            if (fs.mode == 2) *pb += (1.0 - frp) * fb * wA;
+        }
+        return F;
+    }
     double ntb = 0.0, sngN = 0.0, frN = 0.0;
     const double ntc = q.turb ? s.nt[c] : 0.0;
     if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, phib, dl, ntb, sngN, frN);

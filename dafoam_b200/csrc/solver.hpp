@@ -491,7 +491,8 @@ struct Solver
                 FunctionDef f;
                 f.name = kv.first;
                 f.type = kv.second.strOr("type", "force");
-                if (f.type != "force" && f.type != "moment") throw Error("function type " + f.type + " is not supported (force, moment)");
+                if (f.type != "force" && f.type != "moment" && f.type != "totalPressure" && f.type != "massFlowRate")
+                    throw Error("function type " + f.type + " is not supported (force, moment, totalPressure, massFlowRate)");
                 if (const JVal* pl = kv.second.get("patches"))
                     for (const auto& pn : pl->arr)
                     {
@@ -508,7 +509,7 @@ struct Solver
                     if (const JVal* d = kv.second.get("center"))
                         for (size_t k = 0; k < 3 && k < d->arr.size(); k++) f.center[k] = d->arr[k].num;
                 }
-                else
+                else if (f.type == "force")
                 {
                     f.dirMode = kv.second.strOr("directionMode", "fixedDirection");
                     if (f.dirMode == "fixedDirection")
@@ -1145,7 +1146,24 @@ struct Solver
         for (int p : f.patches) fs.mask |= (1u << p);
         for (int k = 0; k < 3; k++) { fs.dir[k] = f.dir[k]; fs.center[k] = f.center[k]; }
         fs.scale = f.scale;
-        fs.mode = f.type == "moment" ? 1 : 0;
+        fs.mode = f.type == "moment" ? 1 : (f.type == "totalPressure" ? 2 : (f.type == "massFlowRate" ? 3 : 0));
+        fs.areaSum = 1.0;
+        if (fs.mode == 2)
+        {
+            // areaSum_ of DAFunctionTotalPressure.C: total area of the function's faces, reduced over the ranks
+            double a = 0.0;
+            for (int p : f.patches)
+                for (int i = 0; i < hm.patches[p].size; i++) a += hm.magSf[hm.patches[p].start + i];
+            if (comm.active())
+            {
+                Solver* self = const_cast<Solver*>(this);
+                if (self->dFacePart.n < 1) self->dFacePart.alloc(self->be, hm.nBF + 1);
+                self->be.h2d(self->dFacePart.p, &a, sizeof(double));
+                self->comm.allreduceSum(self->be, self->dFacePart.p, 1);
+                self->be.d2h(&a, self->dFacePart.p, sizeof(double));
+            }
+            fs.areaSum = a;
+        }
         if (f.type == "force" && f.dirMode != "fixedDirection")
         {
             // the angle of attack comes from the patchVelocity input (DAGlobalVar::patchVelocity, DAFunctionForce.C:92-114)

@@ -613,6 +613,7 @@ struct Work
     BF<T> bU, bP, bNt, bNut;
     std::vector<T> gradU, nutC;
     std::vector<T> muEB; // compressible: rho_b*nuEff_b on the boundary faces
+    std::vector<T> rhoB; // compressible: boundary density
 };
 
 template <class T>
@@ -1311,6 +1312,7 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
         wk->bU = bU; wk->bP = bP; wk->bNt = bNt; wk->bNut = bNut;
         wk->gradU = gradU; wk->nutC = nut;
         wk->muEB = muEB;
+        wk->rhoB = rhoB;
     }
 }
 
@@ -1326,6 +1328,28 @@ T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int p
     const Topo& t = cs.t;
     const int nC = t.nC;
     T F(0.0);
+    if (mode >= 2)
+    {
+        // mode 2: DAFunctionTotalPressure (area-averaged p + 0.5 rho |U|^2); mode 3: DAFunctionMassFlowRate (rho U.Sf)
+        T areaSum(0.0);
+        for (int b = 0; b < t.nBF; b++)
+            if (t.bPatch[b] == patch) areaSum += g.magSf[t.nIF + b];
+        for (int b = 0; b < t.nBF; b++)
+        {
+            if (t.bPatch[b] != patch) continue;
+            const int f = t.nIF + b;
+            T rhob = cs.comp.on ? wk.rhoB[b] : T(1.0);
+            T U2(0.0), SU(0.0);
+            for (int k = 0; k < 3; k++)
+            {
+                U2 += wk.bU.val[wk.bU.at(k, b)] * wk.bU.val[wk.bU.at(k, b)];
+                SU += g.Sf[f][k] * wk.bU.val[wk.bU.at(k, b)];
+            }
+            if (mode == 2) F += scale * (wk.bP.val[b] + 0.5 * rhob * U2) * g.magSf[f] / areaSum;
+            else F += scale * rhob * SU;
+        }
+        return F;
+    }
     for (int b = 0; b < t.nBF; b++)
     {
         if (t.bPatch[b] != patch) continue;

@@ -153,20 +153,22 @@ class Oracle:
         lib().orc_jtvec(self.h, _p(psi), _p(out), C.c_int(int(normalize)))
         return out
 
-    def force(self, W, patch, direction, scale=1.0, center=None):
-        """force . direction, or (center given) the moment ((Cf - center) x force) . direction."""
+    def force(self, W, patch, direction, scale=1.0, center=None, mode=None):
+        """force . direction, or (center given) the moment ((Cf - center) x force) . direction; mode 2: area-averaged total
+        pressure, mode 3: mass flow rate of the patch (direction unused)."""
         W = np.ascontiguousarray(W, dtype=np.float64)
         d = np.ascontiguousarray(direction, dtype=np.float64)
         ctr = np.zeros(3) if center is None else np.ascontiguousarray(center, dtype=np.float64)
-        return lib().orc_force(self.h, _p(W), C.c_int(patch), _p(d), C.c_double(scale), C.c_int(0 if center is None else 1), _p(ctr))
+        m = mode if mode is not None else (0 if center is None else 1)
+        return lib().orc_force(self.h, _p(W), C.c_int(patch), _p(d), C.c_double(scale), C.c_int(m), _p(ctr))
 
-    def dforce_dw(self, W, patch, direction, scale=1.0, seed=1.0, normalize=True, center=None):
+    def dforce_dw(self, W, patch, direction, scale=1.0, seed=1.0, normalize=True, center=None, mode=None):
         W = np.ascontiguousarray(W, dtype=np.float64)
         d = np.ascontiguousarray(direction, dtype=np.float64)
         ctr = np.zeros(3) if center is None else np.ascontiguousarray(center, dtype=np.float64)
         out = np.zeros(self.ndof)
         lib().orc_dforce_dw(self.h, _p(W), C.c_int(patch), _p(d), C.c_double(scale), C.c_double(seed), _p(out),
-                            C.c_int(int(normalize)), C.c_int(0 if center is None else 1), _p(ctr))
+                            C.c_int(int(normalize)), C.c_int(mode if mode is not None else (0 if center is None else 1)), _p(ctr))
         return out
 
     def jtvec_bcU(self, W, psi, patch):

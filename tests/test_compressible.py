@@ -214,3 +214,36 @@ def test_compressible_function_and_adjoint_solve_cuda():
 @pytest.mark.gpu
 def test_compressible_transpose_product_parity_cuda():
     assert check_reverse(None) < 1e-10
+
+
+def check_patch_functions(lib_path):
+    """DAFunctionTotalPressure and DAFunctionMassFlowRate (patch reductions of p_b, U_b, rho_b) and their state derivatives,
+    incompressible (rho = 1) and compressible, vs the oracle."""
+    from tests.common import setup
+    fn = {"TP": {"type": "totalPressure", "source": "patchToFace", "patches": ["inout"], "scale": 0.5},
+          "MFR": {"type": "massFlowRate", "source": "patchToFace", "patches": ["inout"], "scale": 2.0}}
+    one = np.array([1.0])
+    for comp in (False, True):
+        if comp:
+            mesh, orc, sol, W = setup_comp(CONFIGS[0], lib_path)
+            sol.updateDAOption(dict(normalizeStates=NS, normalizeResiduals=list(NRES), function=fn))
+        else:
+            mesh, bcs, orc, sol, W, _ = setup("naca", True, lib_path=lib_path, extra_options=dict(function=fn))
+        sol.updateOFFields(W)
+        ip = [p["name"] for p in mesh.patches].index("inout")
+        for name, mode, scale in (("TP", 2, 0.5), ("MFR", 3, 2.0)):
+            F, Fo = sol.calcFunction(name), orc.force(W, ip, [1.0, 0.0, 0.0], scale, mode=mode)
+            assert abs(Fo) > 0 and abs(F - Fo) <= 1e-12 * abs(Fo), (comp, name, F, Fo)
+            g = np.zeros(orc.ndof)
+            sol.calcJacTVecProduct("states", "stateVar", W, name, "function", one, g)
+            go = orc.dforce_dw(W, ip, [1.0, 0.0, 0.0], scale, mode=mode)
+            assert np.linalg.norm(go) > 0 and rel_err(g, go) < 1e-12, (comp, name, rel_err(g, go))
+
+
+def test_total_pressure_and_mass_flow_rate_host_build():
+    check_patch_functions(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_total_pressure_and_mass_flow_rate_cuda():
+    check_patch_functions(None)
