@@ -211,6 +211,20 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
         else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
         return 0;
     }
+    if (it == "fvSourcePar")
+    {
+        need(input_name, "input_name");
+        need(input, "input");
+        if (ot == "residual") S.fvSourceParProduct(input_name, input, seed, nullptr, 1.0, product);
+        else if (ot == "function")
+        {
+            need(output_name, "output_name");
+            const std::string fn(output_name);
+            S.fvSourceParProduct(input_name, input, nullptr, &fn, seed[0], product);
+        }
+        else throw Error("calcJacTVecProduct: outputType " + ot + " is not supported");
+        return 0;
+    }
     if (it == "patchVar")
     {
         need(input_name, "input_name");
@@ -344,6 +358,12 @@ int dab_set_solver_input(dab_solver* s, const char* input_name, const char* inpu
         if ((size_t)input_size != S.hm.points.size()) throw Error("setSolverInput: volCoord has the wrong size");
         S.updateMesh(inputs);
     }
+    else if (it == "fvSourcePar")
+    {
+        need(input_name, "input_name");
+        if ((size_t)input_size != S.findFvSourcePar(input_name).indices.size()) throw Error("setSolverInput: fvSourcePar has the wrong size");
+        S.setFvSourcePar(input_name, inputs);
+    }
     else if (it == "patchVar")
     {
         need(input_name, "input_name");
@@ -420,6 +440,7 @@ int dab_get_input_size(dab_solver* s, const char* name, const char* type, int64_
     else if (std::string(type) == "patchVelocity") *out = 2;
     else if (std::string(type) == "volCoord") *out = (int64_t)s->s.hm.points.size();
     else if (std::string(type) == "patchVar") { need(name, "name"); *out = s->s.findPatchVar(name).nComp; }
+    else if (std::string(type) == "fvSourcePar") { need(name, "name"); *out = (int64_t)s->s.findFvSourcePar(name).indices.size(); }
     else throw Error(std::string("getInputSize: unsupported input type ") + type);
     DAB_CATCH
 }

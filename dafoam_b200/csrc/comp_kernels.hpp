@@ -340,7 +340,7 @@ struct cFwdB
         const double cU = q.nrU ? 1.0 : V;
         for (int j = 0; j < 3; j++)
         {
-            const double M = MV[j] * iV;
+            const double M = MV[j] * iV - (m.fvS ? m.fvS[(size_t)j * nC + c] : 0.0); // UEqn ... - fvSource
             r.HbyA[(size_t)j * nT + c] = Uc[j] - rAU * M;
             R[3 * c + j] = (M + r.gP[(size_t)j * nT + c]) * cU;
         }
@@ -419,6 +419,8 @@ struct cFwdE
                 EV += mf * (bp.Ek - Ekc);
             }
         }
+        if (m.fvS) // - fvSourceEnergy = -(fvSource & U)
+            EV -= m.V[c] * (m.fvS[c] * s.U[3 * c] + m.fvS[(size_t)nC + c] * s.U[3 * c + 1] + m.fvS[(size_t)2 * nC + c] * s.U[3 * c + 2]);
         R[4 * (size_t)nC + c] = EV * (q.nrT ? 1.0 / m.V[c] : 1.0);
     }
 };

@@ -141,7 +141,7 @@ struct cUEqnAssemble
         for (int j = 0; j < 3; j++)
         {
             e.diag[(size_t)j * nC + c] = Dn + icS[j];
-            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j];
+            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j] + (m.fvS ? V * m.fvS[(size_t)j * nC + c] : 0.0);
         }
         (void)NF;
     }
@@ -222,6 +222,7 @@ struct cEEqnAssemble
                 X += mf * (bp.Ek - Ekc);
             }
         }
+        if (m.fvS) X -= m.V[c] * (m.fvS[c] * s.U[3 * c] + m.fvS[(size_t)nC + c] * s.U[3 * c + 1] + m.fvS[(size_t)2 * nC + c] * s.U[3 * c + 2]);
         const double D1 = D0 + aic;
         const double aD1 = fabs(D1);
         const double D2 = aD1 > sumOff ? aD1 : sumOff;

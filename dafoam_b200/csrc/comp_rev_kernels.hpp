@@ -586,6 +586,8 @@ struct cRevE
         a.cHe[c] = he2;
         a.cEk[c] = Ekb;
         for (int i = 0; i < 3; i++) a.gHeb[(size_t)i * nT + c] = gHb[i];
+        if (m.fvS)
+            for (int j = 0; j < 3; j++) Ub[j] -= x.T[c] * (q.nrT ? 1.0 : m.V[c]) * m.fvS[(size_t)j * nC + c]; // EV -= V (fvSource . U)
         for (int j = 0; j < 3; j++) a.Udir[(size_t)j * nC + c] += Ub[j];
         a.pdir[c] += pb;
         a.Tdir[c] += Tb;

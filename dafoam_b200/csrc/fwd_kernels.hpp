@@ -311,7 +311,7 @@ struct FwdB
         const double cU = q.nrU ? 1.0 : V;
         for (int j = 0; j < 3; j++)
         {
-            const double M = MV[j] * iV;
+            const double M = MV[j] * iV - (m.fvS ? m.fvS[(size_t)j * nC + c] : 0.0); // UEqn ... - fvSource
             r.HbyA[(size_t)j * nT + c] = Uc[j] - rAU * M; // HbyA = rAU*H = U - rAU*(UEqn & U)
             R[3 * c + j] = (M + r.gP[(size_t)j * nT + c]) * cU;
         }

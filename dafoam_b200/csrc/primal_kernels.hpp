@@ -167,7 +167,7 @@ struct UEqnAssemble
         for (int j = 0; j < 3; j++)
         {
             e.diag[(size_t)j * nC + c] = Dn + icS[j];
-            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j];
+            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j] + (m.fvS ? V * m.fvS[(size_t)j * nC + c] : 0.0);
         }
     }
 };

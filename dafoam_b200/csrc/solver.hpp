@@ -162,6 +162,12 @@ struct Solver
     std::vector<FunctionDef> functions;
     std::vector<PatchVelocityDef> patchVelocities;
     std::vector<PatchVarDef> patchVars;
+    // fvSource (actuator disks) and the fvSourcePar inputs that address its parameters
+    FvSourceSpec fvSpec{};
+    std::vector<std::string> diskNames;
+    struct FvSourceParDef { std::string name, disk; std::vector<int> indices; };
+    std::vector<FvSourceParDef> fvSourcePars;
+    DevBuf<double> dFvS;
 
     // device mesh
     DevBuf<int32_t> dOwn, dNei, dCellFaces, dCellNbr, dBPatch;
@@ -186,6 +192,7 @@ struct Solver
     Partition part;
     DevBuf<double> psiP, psiN, psiPhi, psiT; // working copies of the input vector with ghost slots (multi-rank only)
 
+    bool fvSourceDirty = false;
     bool hex6 = false; // every owned cell has exactly 6 faces: the kernels with fully unrolled, break-free face loops apply
     int nCellStates() const { return 4 + (par.comp ? 1 : 0) + (par.turb ? 1 : 0); }
     int nDof() const { return nCellStates() * hm.nC + hm.nF; }
@@ -531,8 +538,55 @@ struct Solver
                 functions.push_back(f);
             }
         }
+        if (const JVal* fsd = o.get("fvSource"))
+        {
+            // DAFvSourceActuatorDisk::initFvSourcePars (reference DAFvSourceActuatorDisk.C:427-485)
+            fvSpec.nDisk = 0;
+            diskNames.clear();
+            for (const auto& kv : fsd->obj)
+            {
+                if (kv.second.strOr("type", "") != "actuatorDisk" || kv.second.strOr("source", "") != "cylinderAnnulusSmooth")
+                    throw Error("fvSource." + kv.first + ": only type actuatorDisk with source cylinderAnnulusSmooth is supported");
+                if (kv.second.numOr("adjustThrust", 0.0) != 0.0) throw Error("fvSource." + kv.first + ": adjustThrust is not supported");
+                if (fvSpec.nDisk >= MAXDISK) throw Error("too many actuator disks");
+                ActuatorDisk& d = fvSpec.disk[fvSpec.nDisk++];
+                diskNames.push_back(kv.first);
+                const JVal* c = kv.second.get("center");
+                const JVal* dr = kv.second.get("direction");
+                if (!c || !dr || c->arr.size() != 3 || dr->arr.size() != 3) throw Error("fvSource." + kv.first + ": center and direction (3 numbers) are required");
+                for (int k = 0; k < 3; k++) { d.par[k] = c->arr[k].num; d.par[3 + k] = dr->arr[k].num; }
+                d.par[6] = kv.second.numOr("innerRadius", 0.0);
+                d.par[7] = kv.second.numOr("outerRadius", 1.0);
+                d.par[8] = kv.second.numOr("scale", 1.0);
+                d.par[9] = kv.second.numOr("POD", 0.0);
+                d.par[10] = kv.second.numOr("expM", 1.0);
+                d.par[11] = kv.second.numOr("expN", 0.5);
+                d.par[12] = kv.second.numOr("targetThrust", 1.0);
+                d.eps = kv.second.numOr("eps", 0.1);
+                const std::string rd = kv.second.strOr("rotDir", "right");
+                if (rd != "left" && rd != "right") throw Error("rotDir not valid");
+                d.rotLeft = rd == "left" ? 1 : 0;
+            }
+            fvSourceDirty = true;
+        }
         if (const JVal* ii = o.get("inputInfo"))
         {
+            fvSourcePars.clear();
+            for (const auto& kv : ii->obj)
+            {
+                if (kv.second.strOr("type", "") != "fvSourcePar") continue;
+                FvSourceParDef d;
+                d.name = kv.first;
+                d.disk = kv.second.strOr("fvSourceName", "");
+                if (const JVal* il = kv.second.get("indices"))
+                    for (const auto& iv : il->arr)
+                    {
+                        const int idx = (int)iv.num;
+                        if (idx < 0 || idx > 12) throw Error("inputInfo." + kv.first + ": indices must be in 0..12");
+                        d.indices.push_back(idx);
+                    }
+                fvSourcePars.push_back(d);
+            }
             patchVars.clear();
             for (const auto& kv : ii->obj)
             {
@@ -627,6 +681,8 @@ struct Solver
         mv.Sx = dS[0].p; mv.Sy = dS[1].p; mv.Sz = dS[2].p; mv.magSf = dMagSf.p; mv.w = dW.p; mv.delta = dDelta.p;
         mv.kx = dK[0].p; mv.ky = dK[1].p; mv.kz = dK[2].p; mv.Cfx = dCf[0].p; mv.Cfy = dCf[1].p; mv.Cfz = dCf[2].p;
         mv.Cx = dC[0].p; mv.Cy = dC[1].p; mv.Cz = dC[2].p; mv.V = dV.p; mv.yWall = dY.p;
+        mv.fvS = nullptr;
+        fvSourceDirty = fvSpec.nDisk > 0;
         const size_t nT = hm.nCtot, nC = hm.nC, nF = hm.nF, nd = nDof();
         dWext.alloc(be, nd);
         dU.alloc(be, 3 * nT); dP.alloc(be, nT); dNt.alloc(be, nT); dPhi.alloc(be, nF);
@@ -778,10 +834,81 @@ struct Solver
 
     void getOFFields(double* W) { be.d2h(W, dWext.p, (size_t)nDof() * sizeof(double)); }
 
+    // fvSource field from the disk parameters and the current cell centres (DAFvSourceActuatorDisk::calcFvSource)
+    void updateFvSource()
+    {
+        if (fvSpec.nDisk == 0)
+        {
+            mv.fvS = nullptr;
+            fvSourceDirty = false;
+            return;
+        }
+        if (dFvS.n < (size_t)3 * hm.nC) dFvS.alloc(be, (size_t)3 * hm.nC);
+        be.launch(hm.nC, FvSourceK{fvSpec, mv.Cx, mv.Cy, mv.Cz, hm.nC, dFvS.p});
+        mv.fvS = dFvS.p;
+        fvSourceDirty = false;
+        recorded = false;
+        kry.pcValid = false;
+    }
+
+    int diskIndex(const std::string& name) const
+    {
+        for (size_t i = 0; i < diskNames.size(); i++)
+            if (diskNames[i] == name) return (int)i;
+        throw Error("fvSource " + name + " is not defined");
+    }
+    const FvSourceParDef& findFvSourcePar(const std::string& name) const
+    {
+        for (const auto& d : fvSourcePars)
+            if (d.name == name) return d;
+        throw Error("input " + name + " (fvSourcePar) is not defined in inputInfo");
+    }
+    void setFvSourcePar(const std::string& name, const double* in)
+    {
+        const FvSourceParDef& d = findFvSourcePar(name);
+        ActuatorDisk& k = fvSpec.disk[diskIndex(d.disk)];
+        for (size_t i = 0; i < d.indices.size(); i++) k.par[d.indices[i]] = in[i];
+        updateFvSource();
+    }
+    // product[i] = [dR/d(par_i)]^T psi (or seed * dF/d(par_i)) by central differences on the device kernels
+    void fvSourceParProduct(const std::string& name, const double* in, const double* psi, const std::string* fname, double seed, double* product)
+    {
+        const FvSourceParDef& d = findFvSourcePar(name);
+        const size_t n = nDof();
+        std::vector<double> Rp, Rm, x(in, in + d.indices.size());
+        if (!fname) { Rp.resize(n); Rm.resize(n); }
+        for (size_t k = 0; k < d.indices.size(); k++)
+        {
+            const double h = std::max(1e-6, 1e-5 * std::fabs(in[k]));
+            double vp = 0.0, vm = 0.0;
+            for (int sgn = 0; sgn < 2; sgn++)
+            {
+                std::vector<double> xx(x);
+                xx[k] += sgn == 0 ? h : -h;
+                setFvSourcePar(name, xx.data());
+                if (fname) (sgn == 0 ? vp : vm) = calcFunction(*fname);
+                else
+                {
+                    forward(0, dR.p);
+                    be.d2h(sgn == 0 ? Rp.data() : Rm.data(), dR.p, n * sizeof(double));
+                }
+            }
+            if (fname) product[k] = seed * (vp - vm) / (2.0 * h);
+            else
+            {
+                double sdot = 0.0;
+                for (size_t i = 0; i < n; i++) sdot += psi[i] * (Rp[i] - Rm[i]);
+                product[k] = sdot / (2.0 * h);
+            }
+        }
+        setFvSourcePar(name, in);
+    }
+
     // forward passes; record(isPC=0) leaves the intermediates the reverse sweep reuses
     void forward(int isPC, double* Rdev, bool exchange = true)
     {
         const int nT = hm.nCtot;
+        if (fvSourceDirty) updateFvSource();
         if (par.comp)
         {
             // DARhoSimpleFoam: closures + gradients, momentum/SA rows, energy row, pressure/flux rows (comp_kernels.hpp)

@@ -241,6 +241,7 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
 inline int Solver::solvePrimal(PrimalStats& st)
 {
     primalSetup();
+    if (fvSourceDirty) updateFvSource();
     Primal& P = primal;
     const int nC = hm.nC, nT = hm.nCtot;
     auto t0 = std::chrono::steady_clock::now();

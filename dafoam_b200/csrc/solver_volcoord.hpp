@@ -32,6 +32,7 @@ inline void Solver::updateMesh(const double* pts)
     std::copy(pts, pts + hm.points.size(), hm.points.begin());
     hm.computeGeometry();
     uploadGeometry();
+    fvSourceDirty = fvSpec.nDisk > 0;
     if (volc.ready) be.h2d(volc.dPts0.p, hm.points.data(), hm.points.size() * sizeof(double));
 }
 
@@ -180,6 +181,7 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
         be.launch(hm.nF, GeomFaceK{gv});
         be.launch(nC, GeomCellK{gv});
         be.launch(hm.nF, GeomDerivedK{gv});
+        if (fvSpec.nDisk > 0) be.launch(nC, FvSourceK{fvSpec, mv.Cx, mv.Cy, mv.Cz, nC, dFvS.p}); // the source follows the cell centres
     };
     if (psi) be.h2d(dX.p, psi, (size_t)nDof() * sizeof(double));
     be.d2d(Vc.dPts.p, Vc.dPts0.p, (size_t)3 * nP * sizeof(double));
@@ -238,6 +240,7 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
     }
     be.d2h(out, Vc.dOut.p, (size_t)3 * nP * sizeof(double));
     uploadGeometry(); // the unperturbed geometry exactly as the host computed it
+    if (fvSpec.nDisk > 0) updateFvSource();
 }
 
 } // namespace dab

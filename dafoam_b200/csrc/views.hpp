@@ -28,6 +28,67 @@ struct MeshView
     const int32_t* bPatch;    // [nBF]
     const double *Sx, *Sy, *Sz, *magSf, *w, *delta, *kx, *ky, *kz, *Cfx, *Cfy, *Cfz; // [nF]
     const double *Cx, *Cy, *Cz, *V, *yWall;                                          // [nCtot]
+    const double* fvS; // [3][nC] momentum source per unit volume (fvSource: actuator disks) or null
+};
+
+// DAFvSourceActuatorDisk, source = cylinderAnnulusSmooth (reference src/adjoint/DAFvSource/DAFvSourceActuatorDisk.C:205-407):
+// the 13 actuatorDiskPars (center, direction, innerRadius, outerRadius, scale, POD, expM, expN, targetThrust) + eps, rotDir
+struct ActuatorDisk
+{
+    double par[13];
+    double eps;
+    int rotLeft;
+};
+constexpr int MAXDISK = 4;
+struct FvSourceSpec
+{
+    int nDisk;
+    ActuatorDisk disk[MAXDISK];
+};
+
+// source vector (force per unit volume) of one disk at the cell centre C
+DAB_HD void actuatorDiskSource(const ActuatorDisk& d, const double* C, double* out)
+{
+    const double* a = d.par;
+    const double dm = sqrt(a[3] * a[3] + a[4] * a[4] + a[5] * a[5]);
+    const double dn[3] = {a[3] / dm, a[4] / dm, a[5] / dm};
+    const double rin = a[6], rout = a[7], scale = a[8], POD = a[9], expM = a[10], expN = a[11], eps = d.eps;
+    const double epsR = eps / (rout - rin), rMin = epsR, rMax = 1.0 - epsR;
+    const double fRMin = pow(rMin, expM) * pow(1.0 - rMin, expN), fRMax = pow(rMax, expM) * pow(1.0 - rMax, expN);
+    const double v[3] = {C[0] - a[0], C[1] - a[1], C[2] - a[2]};
+    // "cellC2AVecE & dirNorm" with a diagonal tensor: the component-wise product (the reference's definition)
+    const double vA[3] = {v[0] * dn[0], v[1] * dn[1], v[2] * dn[2]};
+    const double vR[3] = {v[0] - vA[0], v[1] - vA[1], v[2] - vA[2]};
+    double vC[3];
+    if (d.rotLeft) { vC[0] = vR[1] * dn[2] - vR[2] * dn[1]; vC[1] = vR[2] * dn[0] - vR[0] * dn[2]; vC[2] = vR[0] * dn[1] - vR[1] * dn[0]; }
+    else { vC[0] = dn[1] * vR[2] - dn[2] * vR[1]; vC[1] = dn[2] * vR[0] - dn[0] * vR[2]; vC[2] = dn[0] * vR[1] - dn[1] * vR[0]; }
+    const double rLen = sqrt(vR[0] * vR[0] + vR[1] * vR[1] + vR[2] * vR[2]);
+    const double cLen = sqrt(vC[0] * vC[0] + vC[1] * vC[1] + vC[2] * vC[2]);
+    const double dA2 = vA[0] * vA[0] + vA[1] * vA[1] + vA[2] * vA[2];
+    const double rPrime = rLen / rout, rHub = rin / rout;
+    const double rStar = (rPrime - rHub) / (1.0 - rHub);
+    double fR;
+    if (rStar < rMin) fR = fRMin * exp(-(rStar - rMin) * (rStar - rMin) / epsR / epsR) * scale;
+    else if (rStar <= rMax) fR = pow(rStar, expM) * pow(1.0 - rStar, expN) * scale;
+    else fR = fRMax * exp(-(rStar - rMax) * (rStar - rMax) / epsR / epsR) * scale;
+    const double fAxial = fR * exp(-dA2 / eps / eps);
+    const double fCirc = fAxial * POD / 3.14159265358979323846 / (rPrime + 0.01 * eps / rout);
+    for (int j = 0; j < 3; j++) out[j] += fAxial * dn[j] + (cLen > 0.0 ? fCirc * vC[j] / cLen : 0.0);
+}
+
+struct FvSourceK // fvS[j][c] = sum over the disks
+{
+    FvSourceSpec sp;
+    const double *Cx, *Cy, *Cz;
+    int nC;
+    double* fvS;
+    DAB_HD void operator()(int c) const
+    {
+        const double C[3] = {Cx[c], Cy[c], Cz[c]};
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int k = 0; k < sp.nDisk; k++) actuatorDiskSource(sp.disk[k], C, s);
+        for (int j = 0; j < 3; j++) fvS[(size_t)j * nC + c] = s[j];
+    }
 };
 
 struct Params

@@ -592,6 +592,8 @@ struct Case
     std::vector<int> inId, outId;
     std::vector<double> adj;
     bool recorded = false;
+    // fvSource: actuator disks (cylinderAnnulusSmooth), 15 numbers per disk: the 13 actuatorDiskPars, eps, rotLeft
+    std::vector<double> disks;
     // DARhoSimpleFoam (compressible) extension
     struct Comp
     {
@@ -615,6 +617,51 @@ struct Work
     std::vector<T> muEB; // compressible: rho_b*nuEff_b on the boundary faces
     std::vector<T> rhoB; // compressible: boundary density
 };
+
+// DAFvSourceActuatorDisk::calcFvSource, source = cylinderAnnulusSmooth (reference DAFvSourceActuatorDisk.C:205-407), adjustThrust 0;
+// S[(j*nC + c)] = force per unit volume (depends on the cell centres, hence on the mesh points)
+template <class T>
+void actuatorSource(const Case& cs, const Geom<T>& g, std::vector<T>& S)
+{
+    const int nC = cs.t.nC;
+    S.assign((size_t)3 * nC, T(0.0));
+    const int nd = (int)cs.disks.size() / 15;
+    for (int k = 0; k < nd; k++)
+    {
+        const double* a = &cs.disks[(size_t)15 * k];
+        const double dm = std::sqrt(a[3] * a[3] + a[4] * a[4] + a[5] * a[5]);
+        const double dn[3] = {a[3] / dm, a[4] / dm, a[5] / dm};
+        const double rin = a[6], rout = a[7], scale = a[8], POD = a[9], expM = a[10], expN = a[11], eps = a[13];
+        const bool rotLeft = a[14] != 0.0;
+        const double epsR = eps / (rout - rin), rMin = epsR, rMax = 1.0 - epsR;
+        const double fRMin = std::pow(rMin, expM) * std::pow(1.0 - rMin, expN), fRMax = std::pow(rMax, expM) * std::pow(1.0 - rMax, expN);
+        for (int c = 0; c < nC; c++)
+        {
+            V3<T> v(g.C[c][0] - a[0], g.C[c][1] - a[1], g.C[c][2] - a[2]);
+            V3<T> vA(v[0] * dn[0], v[1] * dn[1], v[2] * dn[2]);
+            V3<T> vR = v - vA;
+            V3<T> dnT;
+            dnT.x = T(dn[0]); dnT.y = T(dn[1]); dnT.z = T(dn[2]);
+            V3<T> vC = rotLeft ? cross(vR, dnT) : cross(dnT, vR);
+            T rLen = mag(vR), cLen = mag(vC);
+            T dA2 = dot(vA, vA);
+            T rPrime = rLen / rout;
+            const double rHub = rin / rout;
+            T rStar = (rPrime - rHub) / (1.0 - rHub);
+            T fR;
+            if (val(rStar) < rMin) fR = fRMin * exp(-((rStar - rMin) * (rStar - rMin)) / epsR / epsR) * scale;
+            else if (val(rStar) <= rMax) fR = pow(rStar, expM) * pow(1.0 - rStar, expN) * scale;
+            else fR = fRMax * exp(-((rStar - rMax) * (rStar - rMax)) / epsR / epsR) * scale;
+            T fAxial = fR * exp(-dA2 / eps / eps);
+            T fCirc = fAxial * POD / 3.14159265358979323846 / (rPrime + 0.01 * eps / rout);
+            for (int j = 0; j < 3; j++)
+            {
+                S[(size_t)j * nC + c] += fAxial * dn[j];
+                if (val(cLen) > 0.0) S[(size_t)j * nC + c] += fCirc * vC[j] / cLen;
+            }
+        }
+    }
+}
 
 template <class T>
 void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isPC, std::vector<T>& R, Work<T>* wk,
@@ -774,6 +821,14 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
                 UEqn.src[(size_t)j * nC + c] += nuEffB[b] * (s - (2.0 / 3.0) * tr * g.Sf[f][j]);
             }
         }
+    }
+    if (!cs.disks.empty())
+    {
+        // ... - fvSource (UEqnSimple.H): matrix source += fvSource*V
+        std::vector<T> S;
+        actuatorSource(cs, g, S);
+        for (int k = 0; k < 3; k++)
+            for (int c = 0; c < nC; c++) UEqn.src[(size_t)k * nC + c] += g.V[c] * S[(size_t)k * nC + c];
     }
     relax(UEqn, t, par.alphaU, U);
 
@@ -1130,6 +1185,13 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
             }
         }
     }
+    std::vector<T> fvS;
+    if (!cs.disks.empty())
+    {
+        actuatorSource(cs, g, fvS);
+        for (int k = 0; k < 3; k++)
+            for (int c = 0; c < nC; c++) UEqn.src[(size_t)k * nC + c] += g.V[c] * fvS[(size_t)k * nC + c];
+    }
     relax(UEqn, t, par.alphaU, U);
     std::vector<T> URes;
     matResidual(UEqn, t, g, U, URes);
@@ -1181,6 +1243,9 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
         for (int c = 0; c < nC; c++) EEqn.src[c] -= dv[c];
     }
     fvmLaplacian(EEqn, t, g, -1.0, aE, aEB, bHe, gradHe, false);
+    if (!fvS.empty())
+        for (int c = 0; c < nC; c++) // - fvSourceEnergy = -(fvSource & U)
+            EEqn.src[c] += g.V[c] * (fvS[c] * U[c] + fvS[(size_t)nC + c] * U[(size_t)nC + c] + fvS[(size_t)2 * nC + c] * U[(size_t)2 * nC + c]);
     std::vector<T> TRes;
     matResidual(EEqn, t, g, he, TRes);
     if (!cp.nrT)
@@ -1454,6 +1519,14 @@ void orc_set_compressible(void* h, const double* dpar, const int* ipar, const in
     c.heIsE = ipar[0]; c.sutherland = ipar[1]; c.divE = ipar[2]; c.divEkp = ipar[3]; c.nrT = ipar[4];
     c.kindT.assign(kindT, kindT + cs->t.nPatch);
     c.valueT.assign(valueT, valueT + cs->t.nPatch);
+    cs->recorded = false;
+}
+
+// actuator disks: 15 numbers each (13 actuatorDiskPars, eps, rotLeft)
+void orc_set_fvsource(void* h, int nDisk, const double* pars)
+{
+    Case* cs = (Case*)h;
+    cs->disks.assign(pars, pars + (size_t)15 * nDisk);
     cs->recorded = false;
 }
 

@@ -179,6 +179,16 @@ class Oracle:
         lib().orc_jtvec_bcU(self.h, _p(W), _p(psi), C.c_int(patch), _p(out))
         return out
 
+    def set_fvsource(self, fvSource):
+        """fvSource option of the reference (actuatorDisk / cylinderAnnulusSmooth, adjustThrust 0)."""
+        rows = []
+        for d in fvSource.values():
+            rows.append(list(d["center"]) + list(d["direction"]) + [d["innerRadius"], d["outerRadius"], d["scale"], d["POD"], d["expM"], d["expN"],
+                                                                       d.get("targetThrust", 1.0), d["eps"], 1.0 if d.get("rotDir", "right") == "left" else 0.0])
+        a = np.ascontiguousarray(rows, dtype=np.float64).ravel()
+        self._keep_disks = a
+        lib().orc_set_fvsource(self.h, C.c_int(len(rows)), _p(a))
+
     def jtvec_bc(self, W, psi, field, patch):
         """[dR/d(boundary reference value of `field` on `patch`)]^T psi (3 numbers; scalars use the first)."""
         W = np.ascontiguousarray(W, dtype=np.float64)

@@ -247,3 +247,80 @@ def test_total_pressure_and_mass_flow_rate_host_build():
 @pytest.mark.gpu
 def test_total_pressure_and_mass_flow_rate_cuda():
     check_patch_functions(None)
+
+
+FVSOURCE = {"disk1": {"type": "actuatorDisk", "source": "cylinderAnnulusSmooth", "center": [1.6, 0.1, 0.05], "direction": [1.0, 0.0, 0.0],
+                      "innerRadius": 0.05, "outerRadius": 0.6, "rotDir": "right", "scale": 100.0, "POD": 0.8, "eps": 0.25, "expM": 1.0,
+                      "expN": 0.5, "adjustThrust": 0, "targetThrust": 1.0}}
+
+
+def check_fvsource(lib_path):
+    """fvSource actuator disk (DAFvSourceActuatorDisk, cylinderAnnulusSmooth) in the momentum and energy rows, the fvSourcePar
+    input and the mesh dependence of the source in the volCoord product -- incompressible and compressible, vs the oracle."""
+    from tests.common import setup
+    inp = {"actuator_disk": {"type": "fvSourcePar", "fvSourceName": "disk1", "indices": [0, 7, 8, 9]}}
+    for comp in (False, True):
+        if comp:
+            mesh, orc, sol, W = setup_comp(("naca", "sensibleInternalEnergy", "const", "SpalartAllmaras", "linearUpwind", "upwind", False, NRES), lib_path)
+            sol.updateDAOption(dict(normalizeStates=NS, normalizeResiduals=list(NRES), fvSource=FVSOURCE, inputInfo=inp))
+        else:
+            mesh, bcs, orc, sol, W, _ = setup("naca", True, lib_path=lib_path, extra_options=dict(fvSource=FVSOURCE, inputInfo=inp))
+        base = orc.residual(W)
+        orc.set_fvsource(FVSOURCE)
+        sol.updateOFFields(W)
+        R = np.zeros(orc.ndof)
+        sol.getResiduals(R)
+        Ro = orc.residual(W)
+        assert rel_err(Ro, base) > 1e-6  # the disk sits inside the mesh
+        assert rel_err(R, Ro) < 1e-11, (comp, rel_err(R, Ro))
+        orc.record(W)
+        psi = np.random.default_rng(9).uniform(-1, 1, orc.ndof)
+        y = np.zeros(orc.ndof)
+        sol.calcdRdWTPsiAD(psi, y)
+        assert rel_err(y, orc.jtvec(psi)) < 1e-11
+        # fvSourcePar: d(psi.R)/d(center_x, outerRadius, scale, POD) vs central differences of the oracle
+        d = FVSOURCE["disk1"]
+        x = np.array([d["center"][0], d["outerRadius"], d["scale"], d["POD"]])
+        assert sol.getInputSize("actuator_disk", "fvSourcePar") == 4
+        prod = np.zeros(4)
+        sol.calcJacTVecProduct("actuator_disk", "fvSourcePar", x, "R", "residual", psi, prod)
+        ref = np.zeros(4)
+        import copy
+        for k, key in enumerate(("center", "outerRadius", "scale", "POD")):
+            h = 1e-5 * max(1.0, abs(x[k]))
+            vals = []
+            for sgn in (1.0, -1.0):
+                fs = copy.deepcopy(FVSOURCE)
+                if key == "center":
+                    fs["disk1"]["center"][0] += sgn * h
+                else:
+                    fs["disk1"][key] += sgn * h
+                orc.set_fvsource(fs)
+                vals.append(psi @ orc.residual(W))
+            ref[k] = (vals[0] - vals[1]) / (2 * h)
+        orc.set_fvsource(FVSOURCE)
+        # both sides are central differences of psi.R; R ~ 1e6 in the compressible case limits them to ~1e-4
+        assert np.allclose(prod, ref, rtol=3e-4 if comp else 1e-5, atol=1e-7 * np.abs(ref).max()), (comp, prod, ref)
+        # the source moves with the cell centres: volCoord product vs the oracle's tape through the geometry
+        nP3 = 3 * sol.getNLocalPoints()
+        pts = np.zeros(nP3)
+        sol.getOFMeshPoints(pts)
+        pv = np.zeros(nP3)
+        sol.calcJacTVecProduct("aero_vol_coords", "volCoord", pts, "R", "residual", psi, pv)
+        refv = orc.jtvec_xv(W, psi)
+        mask = np.ones((nP3 // 3, 3), dtype=bool)
+        for pch in mesh.patches:
+            if pch["type"] == "symmetry":
+                fp = mesh.faces[pch["start"]:pch["start"] + pch["size"]]
+                mask[np.unique(fp[fp >= 0]), 2] = False
+        mask = mask.ravel()
+        assert rel_err(pv[mask], refv[mask]) < 1e-7
+
+
+def test_fvsource_actuator_disk_host_build():
+    check_fvsource(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_fvsource_actuator_disk_cuda():
+    check_fvsource(None)
