@@ -50,8 +50,8 @@ def test_argument_errors_mirror_the_reference():
         sol.updateOFFields(np.zeros(3))
     from dafoam_b200.pyDASolvers import DAB200Error
     with pytest.raises(DAB200Error, match="not supported"):
-        sol.calcJacTVecProduct("x", "fvSourcePar", np.zeros(1), "R", "residual", np.zeros(orc.ndof), np.zeros(1)) if False else \
-            sol._raise(sol._L.dab_calc_jac_t_vec_product(sol._h, b"x", b"fvSourcePar", None, b"R", b"residual",
+        sol.calcJacTVecProduct("x", "regressionPar", np.zeros(1), "R", "residual", np.zeros(orc.ndof), np.zeros(1)) if False else \
+            sol._raise(sol._L.dab_calc_jac_t_vec_product(sol._h, b"x", b"regressionPar", None, b"R", b"residual",
                                                          W.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                                          W.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
     with pytest.raises(DAB200Error, match="is not defined"):
