@@ -362,7 +362,7 @@ struct VecOps
 #endif
         return hOut.data();
     }
-    // out[j] = V_j . w left on the device (no host synchronisation; single rank)
+    // out[j] = V_j . w left on the device (no host synchronisation); summed over the ranks
     void dotsDev(const double* V, int64_t ld, int k, const double* w, int n, double* out)
     {
 #ifndef DAB_HOSTSIM
@@ -377,6 +377,7 @@ struct VecOps
         }
 #endif
         be->launches += 2;
+        if (comm && comm->active()) comm->allreduceSum(*be, out, k);
     }
     double norm2(const double* w, int n) { return std::sqrt(dots(w, 0, 1, w, n)[0]); }
 };

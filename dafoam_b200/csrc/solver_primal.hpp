@@ -13,7 +13,6 @@ inline void Solver::primalSetup()
 {
     Primal& P = primal;
     if (P.allocated) return;
-    if (comm.active()) throw Error("solvePrimal runs on one GPU in this build (the adjoint path is the multi-GPU one)");
     const size_t nC = hm.nC, nT = hm.nCtot, mcf = hm.maxCF;
     P.uOff.alloc(be, mcf * nC); P.uDiag.alloc(be, 3 * nC); P.uB.alloc(be, 3 * nC);
     P.pOff.alloc(be, mcf * nC); P.pDiag.alloc(be, nC); P.pB.alloc(be, nC);
@@ -26,7 +25,7 @@ inline void Solver::primalSetup()
         P.eOff.alloc(be, mcf * nC); P.eDiag.alloc(be, nC); P.eB.alloc(be, nC); P.heTmp.alloc(be, nT);
     }
     be.launch((int)nC, FillConst{P.ones.p, 1.0});
-    primalOps.init(be, nullptr, 8);
+    primalOps.init(be, &comm, 8); // sums are all-reduced over the ranks
     P.ops = &primalOps;
     // greedy distance-1 colouring of the cell graph (hexahedral structured numbering: 2 colours)
     std::vector<int32_t> colourOf(nC, -1);
@@ -69,17 +68,19 @@ inline const double* Solver::primalSums(int k) { return primal.ops->dots(primal.
 inline void Solver::primalResidual(const EqnView& e, const double* x, const double* g, double* res)
 {
     const int nC = hm.nC;
+    const double nG = comm.active() ? (double)part.nGlobalCells : (double)nC;
+    if (comm.active()) halo.exchangeCells({{const_cast<double*>(x), e.nc, e.nc == 3 ? 3 : 1, e.nc == 3 ? 1 : hm.nCtot}});
     be.launch(nC, StridedCopy{x, e.nc, e.nc, nC, primal.red.p});
     const double* s = primalSums(e.nc);
     if (e.nc == 3)
     {
         EqnResidual<3> k{e, x, g, mv.V, hm.nCtot, {0, 0, 0}, primal.red.p};
-        for (int j = 0; j < 3; j++) k.xRef[j] = s[j] / (double)nC;
+        for (int j = 0; j < 3; j++) k.xRef[j] = s[j] / (double)nG;
         be.launch(nC, k);
     }
     else
     {
-        EqnResidual<1> k{e, x, g, mv.V, hm.nCtot, {s[0] / (double)nC, 0, 0}, primal.red.p};
+        EqnResidual<1> k{e, x, g, mv.V, hm.nCtot, {s[0] / (double)nG, 0, 0}, primal.red.p};
         be.launch(nC, k);
     }
     s = primalSums(2 * e.nc);
@@ -99,15 +100,20 @@ inline void Solver::primalJacobi(const EqnView& e, double* x, double* tmp, const
     {
         for (int rep = 0; rep < 2; rep++)
         {
+            // ghost copies of the iterate after every sweep (one exchange per sweep on several ranks)
             if (e.nc == 3)
             {
                 be.launch(nC, JacobiSweep<3>{e, x, tmp, g, mv.V, hm.nCtot});
+                if (comm.active()) halo.exchangeCells({{tmp, 3, 3, 1}});
                 be.launch(nC, JacobiSweep<3>{e, tmp, x, g, mv.V, hm.nCtot});
+                if (comm.active()) halo.exchangeCells({{x, 3, 3, 1}});
             }
             else
             {
                 be.launch(nC, JacobiSweep<1>{e, x, tmp, g, mv.V, hm.nCtot});
+                if (comm.active()) halo.exchangeCells({{tmp, 1, 1, hm.nCtot}});
                 be.launch(nC, JacobiSweep<1>{e, tmp, x, g, mv.V, hm.nCtot});
+                if (comm.active()) halo.exchangeCells({{x, 1, 1, hm.nCtot}});
             }
         }
         primalResidual(e, x, g, res);
@@ -205,6 +211,7 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
     res0 = r1[0];
     if (res0 < ctl.tol) return 0;
     // norm factor once (OpenFOAM keeps it fixed during the solve)
+    if (comm.active()) halo.exchangeCells({{x, 1, 1, hm.nCtot}});
     be.launch(nC, SpmvEll{e, x, P.q.p});
     be.launch(nC, ResidualOf{e.b, P.q.p, P.r.p});
     be.launch(nC, PcgProducts{P.r.p, P.r.p, P.r.p, P.red.p, P.red.p + nC});
@@ -220,6 +227,7 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
         P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 0);
         be.launch(1, PcgScalarBeta{S, it == 0 ? 1 : 0});
         be.launch(nC, PcgUpdate2{S, P.z.p, P.d.p});
+        if (comm.active()) halo.exchangeCells({{P.d.p, 1, 1, hm.nCtot}});
         be.launch(nC, SpmvEllProd{e, P.d.p, P.q.p, P.red.p});
         P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 2);
         be.launch(1, PcgScalarAlpha{S});
@@ -316,12 +324,22 @@ inline int Solver::solvePrimal(PrimalStats& st)
         if (!(maxRes == maxRes)) break;
         if (maxRes < P.minResTol && it > P.minIters) break;
     }
+    const bool mr = comm.active();
+    if (mr && par.comp) throw Error("solvePrimal of DARhoSimpleFoam runs on one GPU in this build");
+    auto exGrad = [&]() {
+        if (!mr) return;
+        std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};
+        if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
+        halo.exchangeCells(it);
+    };
+    if (mr) exchangeStates();
     for (it = par.comp ? it : 1; !par.comp && it <= P.maxIters; it++)
     {
         maxRes = -1e10;
         be.d2d(P.pOld.p, dP.p, (size_t)nT * sizeof(double)); // p.storePrevIter()
         // --- momentum predictor (UEqnSimple.H)
         DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv);
+        exGrad();
         DAB_LAUNCH_NFF(nC, UEqnAssemble, mv, par, sv, rv, eU);
         primalJacobi(eU, dU.p, P.Utmp.p, rv.gP, P.cU, st.resU);
         {
@@ -331,9 +349,14 @@ inline int Solver::solvePrimal(PrimalStats& st)
         }
         // --- pressure corrector (pEqnSimple.H)
         be.launch(nC, HbyAKernel{eU, sv, rv, mv.V, nT});
+        if (mr) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}});
         for (int no = 0; no <= P.nNonOrth; no++)
         {
-            if (no > 0) DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad(p) of the latest p for the non-orthogonal correction
+            if (no > 0)
+            {
+                DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad(p) of the latest p for the non-orthogonal correction
+                exGrad();
+            }
             DAB_LAUNCH_NF(nC, PEqnAssemble, mv, par, sv, rv, eP);
             if (no == 0 && (it == 1 || (it - 1) % P.coarseRefresh == 0)) primalCoarseRefresh(eP);
             double rp;
@@ -341,20 +364,27 @@ inline int Solver::solvePrimal(PrimalStats& st)
             if (no == 0) st.resP = rp;
             maxRes = std::max(maxRes, rp);
         }
+        if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}});
         DAB_LAUNCH_NF(nC, PhiUpdate, mv, par, sv, rv, dPhi.p);
+        if (mr) halo.exchangeFaces({{dPhi.p, 1, 1, hm.nF}}); // cut faces: the owner rank's flux
         be.launch(nC, RelaxField{dP.p, P.pOld.p, P.alphaP});
+        if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}});
         DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad of the relaxed p
+        exGrad();
         be.launch(nC, UCorrect{rv, dU.p, nT});
+        if (mr) halo.exchangeCells({{dU.p, 3, 3, 1}});
         // --- turbulence (DASpalartAllmaras::correct)
         if (par.turb)
         {
             DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv);
+            exGrad();
             DAB_LAUNCH_NF(nC, NutEqnAssemble, mv, par, sv, rv, eN, P.alphaN);
             double rn[3];
             primalJacobi(eN, dNt.p, P.ntTmp.p, nullptr, P.cN, rn);
             st.resN = rn[0];
             maxRes = std::max(maxRes, rn[0]);
             be.launch(nC, BoundField{dNt.p, P.ntMin, P.ntMax});
+            if (mr) halo.exchangeCells({{dNt.p, 1, 1, nT}});
         }
         if (printInfo && (it % P.printInterval == 0 || it == 1))
             fprintf(stderr, "[dab200] SIMPLE %5d  U %.3e %.3e %.3e  p %.3e  nuTilda %.3e\n", it, st.resU[0], st.resU[1], st.resU[2], st.resP, st.resN);

@@ -36,6 +36,9 @@ def main():
     def allreduce(a):
         dist.all_reduce(torch.from_numpy(a))
 
+    primal_mode = kind == "channelprimal"
+    if primal_mode:
+        kind = "channel"
     comp = kind == "nacacomp"
     mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2) if kind in ("naca", "nacacomp") else cases.channel(nx=12, ny=8, nz=2)
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing" if kind in ("naca", "nacacomp") else "walls"],
@@ -67,6 +70,30 @@ def main():
     dist.all_reduce(n_cells_total)
     assert int(n_cells_total) == nCg
 
+    if primal_mode:
+        # solvePrimal on two ranks (ghost exchanges per sweep / CG iteration, all-reduced residual norms, per-rank coarse
+        # spaces) against the single-rank SIMPLE: same fixed point
+        o2 = dict(opts, primalMinResTol=1e-11, primalMaxIters=3000)
+        serial.updateDAOption(o2)
+        par.updateDAOption(o2)
+        fs, fp = serial.solvePrimal(), par.solvePrimal()
+        assert fs == 0 and fp == 0, (fs, fp, serial.primalStats.max_residual, par.primalStats.max_residual)
+        Ws, Wp = np.zeros(serial.getNLocalAdjointStates()), np.zeros(idx.size)
+        serial.getOFFields(Ws)
+        par.getOFFields(Wp)
+        nCl = par.getNLocalCells()
+        errs = []
+        for a, b in ((0, 3 * nCl), (3 * nCl, 4 * nCl), (4 * nCl, 5 * nCl)):
+            ref = Ws[idx][a:b]
+            errs.append(np.linalg.norm(Wp[a:b] - ref) / np.linalg.norm(ref))
+        fo = owned[5 * nCl:]
+        errs.append(np.linalg.norm(Wp[5 * nCl:][fo] - Ws[idx][5 * nCl:][fo]) / np.linalg.norm(Ws[idx][5 * nCl:][fo]))
+        assert max(errs) < 1e-7, errs
+        print("rank %d ok: primal iterations serial %d, 2 ranks %d, state difference %.1e" % (rank, serial.primalStats.iterations,
+                                                                                               par.primalStats.iterations, max(errs)), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     y = np.zeros(nCg)
     serial.getOFField("yWall", "scalar", y)
     Wg = cases.boundary_layer_state(mesh, y, noise=0.01) if kind == "naca" else None

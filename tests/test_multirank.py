@@ -32,7 +32,7 @@ def test_two_gpus_match_one_gpu_nccl():
     _run("naca", ["cuda"], 29735)
 
 
-@pytest.mark.parametrize("kind", ["naca", "channel", "nacacomp"])
+@pytest.mark.parametrize("kind", ["naca", "channel", "nacacomp", "channelprimal"])
 def test_two_ranks_match_one_rank(kind):
     d = tempfile.mkdtemp(prefix="dab_mp_")
     if kind == "naca":
@@ -43,7 +43,7 @@ def test_two_ranks_match_one_rank(kind):
     else:
         cases.write_case(d, cases.channel(nx=12, ny=8, nz=2), cases.default_bcs_channel())
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", {"naca": "29731", "channel": "29733", "nacacomp": "29737"}[kind], os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
+           "--master-port", {"naca": "29731", "channel": "29733", "nacacomp": "29737", "channelprimal": "29739"}[kind], os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
