@@ -108,13 +108,14 @@ def check_function_and_adjoint(lib_path):
                             adjEqnOption=dict(gmresRelTol=1e-5, gmresMaxIters=800, gmresRestart=800, pcConLevel=3)))
     sol.updateOFFields(W)
     one = np.array([1.0])
+    tol = 1e-12 if lib_path is not None else 1e-9  # GPU: FMA contraction on pressures of 1e5
     for name, dirv, scale, c_ in (("CD", d, 0.01, None), ("CM", [0.0, 0.0, 1.0], 0.02, ctr)):
         F, Fo = sol.calcFunction(name), orc.force(W, 0, dirv, scale, center=c_)
-        assert abs(Fo) > 0 and abs(F - Fo) <= 1e-12 * abs(Fo), (name, F, Fo)
+        assert abs(Fo) > 0 and abs(F - Fo) <= tol * abs(Fo), (name, F, Fo)
         g = np.zeros(orc.ndof)
         sol.calcJacTVecProduct("states", "stateVar", W, name, "function", one, g)
         go = orc.dforce_dw(W, 0, dirv, scale, center=c_)
-        assert np.linalg.norm(go) > 0 and rel_err(g, go) < 1e-12, name
+        assert np.linalg.norm(go) > 0 and rel_err(g, go) < tol, name
     dFdW, psi = np.zeros(orc.ndof), np.zeros(orc.ndof)
     sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", one, dFdW)
     pc, ksp = Mat(), KSP()
@@ -193,7 +194,7 @@ def test_compressible_transpose_product_parity_host_build():
 
 @pytest.mark.gpu
 def test_compressible_residual_parity_cuda():
-    check_forward(None)
+    check_forward(None, tol=1e-9)
 
 
 @pytest.mark.gpu
@@ -213,7 +214,7 @@ def test_compressible_function_and_adjoint_solve_cuda():
 
 @pytest.mark.gpu
 def test_compressible_transpose_product_parity_cuda():
-    assert check_reverse(None) < 1e-10
+    assert check_reverse(None, tol=1e-9) < 1e-9
 
 
 def check_patch_functions(lib_path):
@@ -231,13 +232,14 @@ def check_patch_functions(lib_path):
             mesh, bcs, orc, sol, W, _ = setup("naca", True, lib_path=lib_path, extra_options=dict(function=fn))
         sol.updateOFFields(W)
         ip = [p["name"] for p in mesh.patches].index("inout")
+        tol = 1e-12 if lib_path is not None else 1e-9
         for name, mode, scale in (("TP", 2, 0.5), ("MFR", 3, 2.0)):
             F, Fo = sol.calcFunction(name), orc.force(W, ip, [1.0, 0.0, 0.0], scale, mode=mode)
-            assert abs(Fo) > 0 and abs(F - Fo) <= 1e-12 * abs(Fo), (comp, name, F, Fo)
+            assert abs(Fo) > 0 and abs(F - Fo) <= tol * abs(Fo), (comp, name, F, Fo)
             g = np.zeros(orc.ndof)
             sol.calcJacTVecProduct("states", "stateVar", W, name, "function", one, g)
             go = orc.dforce_dw(W, ip, [1.0, 0.0, 0.0], scale, mode=mode)
-            assert np.linalg.norm(go) > 0 and rel_err(g, go) < 1e-12, (comp, name, rel_err(g, go))
+            assert np.linalg.norm(go) > 0 and rel_err(g, go) < tol, (comp, name, rel_err(g, go))
 
 
 def test_total_pressure_and_mass_flow_rate_host_build():
@@ -272,12 +274,13 @@ def check_fvsource(lib_path):
         sol.getResiduals(R)
         Ro = orc.residual(W)
         assert rel_err(Ro, base) > 1e-6  # the disk sits inside the mesh
-        assert rel_err(R, Ro) < 1e-11, (comp, rel_err(R, Ro))
+        tolp = 1e-11 if lib_path is not None else 1e-9
+        assert rel_err(R, Ro) < tolp, (comp, rel_err(R, Ro))
         orc.record(W)
         psi = np.random.default_rng(9).uniform(-1, 1, orc.ndof)
         y = np.zeros(orc.ndof)
         sol.calcdRdWTPsiAD(psi, y)
-        assert rel_err(y, orc.jtvec(psi)) < 1e-11
+        assert rel_err(y, orc.jtvec(psi)) < tolp
         # fvSourcePar: d(psi.R)/d(center_x, outerRadius, scale, POD) vs central differences of the oracle
         d = FVSOURCE["disk1"]
         x = np.array([d["center"][0], d["outerRadius"], d["scale"], d["POD"]])

@@ -25,11 +25,12 @@ def _run(kind, extra, port):
 
 
 @pytest.mark.gpu
-def test_two_gpus_match_one_gpu_nccl():
+@pytest.mark.parametrize("kind,port", [("naca", 29735), ("channelprimal", 29741)])
+def test_two_gpus_match_one_gpu_nccl(kind, port):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    _run("naca", ["cuda"], 29735)
+    _run(kind, ["cuda"], port)
 
 
 @pytest.mark.parametrize("kind", ["naca", "channel", "nacacomp", "channelprimal"])
