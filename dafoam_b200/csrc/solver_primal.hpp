@@ -260,10 +260,19 @@ inline int Solver::solvePrimal(PrimalStats& st)
     double maxRes = 0.0;
     int it = 0;
     EqnView eE{nC, hm.maxCF, 1, P.eOff.p, P.eDiag.p, P.eB.p, mv.cellNbr};
+    const bool mr = comm.active();
+    auto exGrad = [&]() {
+        if (!mr) return;
+        std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};
+        if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
+        if (par.comp) it.push_back({rv.gHe, 3, 1, nT});
+        halo.exchangeCells(it);
+    };
+    if (mr) exchangeStates();
     Params pp = par; // the primal kernels see the stored, relaxed density
     if (par.comp)
     {
-        DAB_LAUNCH_NF(nT, cFwdA, mv, par, sv, rv); // rho = psi*p of the initial state
+        DAB_LAUNCH_NF(nT, cFwdA, mv, par, sv, rv); // rho = psi*p of the initial state (ghost cells included)
         pp.rhoFrozen = 1;
     }
     for (it = 1; par.comp && it <= P.maxIters; it++)
@@ -272,6 +281,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
         maxRes = -1e10;
         be.d2d(P.pOld.p, dP.p, (size_t)nT * sizeof(double));
         DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+        exGrad();
         DAB_LAUNCH_NF(nC, cUEqnAssemble, mv, pp, sv, rv, eU);
         primalJacobi(eU, dU.p, P.Utmp.p, rv.gP, P.cU, st.resU);
         {
@@ -281,6 +291,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
         }
         // energy: solve for he, T from he (thermo.correct())
         DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+        exGrad();
         DAB_LAUNCH_NF(nC, cEEqnAssemble, mv, pp, sv, rv, eE, P.alphaE);
         {
             double re[3];
@@ -289,10 +300,13 @@ inline int Solver::solvePrimal(PrimalStats& st)
             maxRes = std::max(maxRes, re[0]);
             be.launch(nC, TFromHe{pp, rv.he, dT.p});
             be.launch(nC, BoundField{dT.p, P.TMin, P.TMax}); // DAUtility::boundVar
+            if (mr) halo.exchangeCells({{dT.p, 1, 1, nT}});
         }
         // pressure corrector
         DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+        exGrad();
         be.launch(nC, HbyAKernel{eU, sv, rv, mv.V, nT});
+        if (mr) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}});
         DAB_LAUNCH_NF(nC, cPEqnAssemble, mv, pp, sv, rv, eP);
         if (it == 1 || (it - 1) % P.coarseRefresh == 0) primalCoarseRefresh(eP);
         {
@@ -301,22 +315,29 @@ inline int Solver::solvePrimal(PrimalStats& st)
             st.resP = rp;
             maxRes = std::max(maxRes, rp);
         }
+        if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}});
         DAB_LAUNCH_NF(nC, cPhiUpdate, mv, pp, sv, rv, dPhi.p);
+        if (mr) halo.exchangeFaces({{dPhi.p, 1, 1, hm.nF}});
         be.launch(nC, RelaxField{dP.p, P.pOld.p, P.alphaP});
         be.launch(nC, BoundField{dP.p, P.pMin, P.pMax});
         be.launch(nC, RhoRelax{pp, sv, rv.rho, P.alphaRho});
+        if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}, {rv.rho, 1, 1, nT}});
         DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv); // grad of the relaxed p, closures at the new (p, T)
+        exGrad();
         be.launch(nC, UCorrect{rv, dU.p, nT});
         be.launch(3 * nC, BoundField{dU.p, -P.UMax, P.UMax});
+        if (mr) halo.exchangeCells({{dU.p, 3, 3, 1}});
         if (par.turb)
         {
             DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv);
+            exGrad();
             DAB_LAUNCH_NF(nC, cNutEqnAssemble, mv, pp, sv, rv, eN, P.alphaN);
             double rn[3];
             primalJacobi(eN, dNt.p, P.ntTmp.p, nullptr, P.cN, rn);
             st.resN = rn[0];
             maxRes = std::max(maxRes, rn[0]);
             be.launch(nC, BoundField{dNt.p, P.ntMin, P.ntMax});
+            if (mr) halo.exchangeCells({{dNt.p, 1, 1, nT}});
         }
         if (printInfo && (it % P.printInterval == 0 || it == 1))
             fprintf(stderr, "[dab200] SIMPLE %5d  U %.3e %.3e %.3e  he %.3e  p %.3e  nuTilda %.3e\n", it, st.resU[0], st.resU[1], st.resU[2], st.resE,
@@ -324,15 +345,6 @@ inline int Solver::solvePrimal(PrimalStats& st)
         if (!(maxRes == maxRes)) break;
         if (maxRes < P.minResTol && it > P.minIters) break;
     }
-    const bool mr = comm.active();
-    if (mr && par.comp) throw Error("solvePrimal of DARhoSimpleFoam runs on one GPU in this build");
-    auto exGrad = [&]() {
-        if (!mr) return;
-        std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};
-        if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
-        halo.exchangeCells(it);
-    };
-    if (mr) exchangeStates();
     for (it = par.comp ? it : 1; !par.comp && it <= P.maxIters; it++)
     {
         maxRes = -1e10;

@@ -36,10 +36,11 @@ def main():
     def allreduce(a):
         dist.all_reduce(torch.from_numpy(a))
 
-    primal_mode = kind == "channelprimal"
+    primal_mode = kind in ("channelprimal", "channelcompprimal")
+    comp_primal = kind == "channelcompprimal"
     if primal_mode:
         kind = "channel"
-    comp = kind == "nacacomp"
+    comp = kind == "nacacomp" or comp_primal
     mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2) if kind in ("naca", "nacacomp") else cases.channel(nx=12, ny=8, nz=2)
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing" if kind in ("naca", "nacacomp") else "walls"],
                  "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
@@ -73,7 +74,7 @@ def main():
     if primal_mode:
         # solvePrimal on two ranks (ghost exchanges per sweep / CG iteration, all-reduced residual norms, per-rank coarse
         # spaces) against the single-rank SIMPLE: same fixed point
-        o2 = dict(opts, primalMinResTol=1e-11, primalMaxIters=3000)
+        o2 = dict(opts, primalMinResTol=1e-11, primalMaxIters=4000)
         serial.updateDAOption(o2)
         par.updateDAOption(o2)
         fs, fp = serial.solvePrimal(), par.solvePrimal()
@@ -82,12 +83,13 @@ def main():
         serial.getOFFields(Ws)
         par.getOFFields(Wp)
         nCl = par.getNLocalCells()
+        ns_ = 6 if comp else 5
         errs = []
-        for a, b in ((0, 3 * nCl), (3 * nCl, 4 * nCl), (4 * nCl, 5 * nCl)):
+        for a, b in [(0, 3 * nCl)] + [(k * nCl, (k + 1) * nCl) for k in range(3, ns_)]:
             ref = Ws[idx][a:b]
             errs.append(np.linalg.norm(Wp[a:b] - ref) / np.linalg.norm(ref))
-        fo = owned[5 * nCl:]
-        errs.append(np.linalg.norm(Wp[5 * nCl:][fo] - Ws[idx][5 * nCl:][fo]) / np.linalg.norm(Ws[idx][5 * nCl:][fo]))
+        fo = owned[ns_ * nCl:]
+        errs.append(np.linalg.norm(Wp[ns_ * nCl:][fo] - Ws[idx][ns_ * nCl:][fo]) / np.linalg.norm(Ws[idx][ns_ * nCl:][fo]))
         assert max(errs) < 1e-7, errs
         print("rank %d ok: primal iterations serial %d, 2 ranks %d, state difference %.1e" % (rank, serial.primalStats.iterations,
                                                                                                par.primalStats.iterations, max(errs)), flush=True)
