@@ -153,6 +153,7 @@ struct Solver
     int rank = 0, nRanks = 1;
     // options
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
+    int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
     double richardsonOmega = 1.0;
     double gmresRelTol = 1e-6, gmresAbsTol = 1e-14, gmresTolDiff = 1e2, fdStep = 1e-6;
@@ -456,6 +457,10 @@ struct Solver
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
             globalPCIters = (int)a->numOr("globalPCIters", globalPCIters);
+            {
+                const int cr = (int)a->numOr("pcColourRadius", pcExtraColourRadius);
+                if (cr != pcExtraColourRadius) { pcExtraColourRadius = cr; kry.symbolic = false; kry.pcValid = false; }
+            }
             richardsonOmega = a->numOr("richardsonOmega", richardsonOmega);
             const int ca = (int)a->numOr("coarseAggregates", coarseAggregates);
             if (ca != coarseAggregates) { coarseAggregates = ca; kry.pcValid = false; }

@@ -128,7 +128,9 @@ inline void Solver::pcSymbolic()
         }
     };
     // ---- 1. multicolour ordering of the cells: same-colour cells share no matrix entry
-    const int rho = std::max(std::max(Lcc, Lfc + 1), Lcf + 1);
+    // same-colour cells must be further than `rho` apart; a larger radius gives more colours = an ordering closer to the
+    // natural one (better ILU) at the price of more, smaller launches per application (adjEqnOption.pcColourRadius, extension)
+    const int rho = std::max(std::max(Lcc, Lfc + 1), Lcf + 1) + pcExtraColourRadius;
     std::vector<int> colour;
     const int nCol = detail::greedyColour(nC, [&](int c, std::vector<int>& out) { G.ball(&c, 1, rho, out); }, colour);
     std::vector<std::vector<int>> cellsOf(nCol);
