@@ -155,6 +155,34 @@ int dab_update_of_mesh(dab_solver* s, const double* points)
     DAB_CATCH
 }
 
+// OpenFOAM's time name of a value (general format, 6 significant digits: Time::timeName with the default precision)
+static std::string timeNameOf(double t)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.6g", t);
+    return buf;
+}
+
+int dab_write_adjoint_fields(dab_solver* s, const char* function, double write_time, const double* psi)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(function, "function");
+    need(psi, "psi");
+    s->s.writeStateVector(timeNameOf(write_time), std::string("adjoint_") + function + "_", psi);
+    DAB_CATCH
+}
+
+int dab_write_fields(dab_solver* s, double write_time)
+{
+    DAB_TRY
+    need(s, "solver");
+    std::vector<double> W(s->s.nDof());
+    s->s.getOFFields(W.data());
+    s->s.writeStateVector(timeNameOf(write_time), "", W.data());
+    DAB_CATCH
+}
+
 int dab_get_of_field(dab_solver* s, const char* name, const char* type, double* field)
 {
     DAB_TRY

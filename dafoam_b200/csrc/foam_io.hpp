@@ -150,7 +150,14 @@ inline std::vector<std::string> tokenize(const std::string& s)
         while (j < n)
         {
             char d = s[j];
-            if (d == '(') depth++;
+            if (d == '(')
+            {
+                // `6(a b c)`: OpenFOAM writes short lists with the size glued to the bracket
+                bool count = depth == 0 && j > i;
+                for (size_t q = i; count && q < j; q++) count = isdigit((unsigned char)s[q]) != 0;
+                if (count) break;
+                depth++;
+            }
             else if (d == ')')
             {
                 if (depth == 0) break;

@@ -22,7 +22,10 @@
 #include "partition.hpp"
 #include "comm.hpp"
 #include <cstdlib>
+#include <cstdio>
+#include <fstream>
 #include <map>
+#include <sys/stat.h>
 #include <set>
 
 namespace dab
@@ -149,7 +152,7 @@ struct Solver
     Backend be;
     HostMesh hm;
     Params par;
-    std::string solverName;
+    std::string solverName, caseDirectory;
     int rank = 0, nRanks = 1;
     // options
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
@@ -219,6 +222,7 @@ struct Solver
     {
         rank = rank_;
         nRanks = nRanks_;
+        caseDirectory = caseDir;
         {
             auto t = tokenize(argsAll);
             solverName = t.empty() ? "DASimpleFoam" : t[0];
@@ -796,6 +800,34 @@ struct Solver
                 const double ro = p[o] / (par.Rg * Tt[o]);
                 const double rf = f < nIF ? hm.w[f] * ro + (1.0 - hm.w[f]) * p[hm.nei[f]] / (par.Rg * Tt[hm.nei[f]]) : ro;
                 W[off + f] *= rf;
+            }
+        }
+        // a flux field written by a previous run (writeFields / OpenFOAM's own phi) takes precedence over the interpolated one
+        if (nRanks == 1 && fileExists(caseDirectory + "/0/phi"))
+        {
+            Dict d = readDict(caseDirectory + "/0/phi");
+            auto listOf = [&](const std::vector<std::string>& t, size_t n, std::vector<double>& out) {
+                out.clear();
+                if (!t.empty() && t[0] == "uniform")
+                {
+                    out.assign(n, atof(t.at(1).c_str()));
+                    return;
+                }
+                size_t i = 0;
+                while (i < t.size() && t[i] != "(") i++;
+                for (i++; i < t.size() && t[i] != ")"; i++) out.push_back(atof(t[i].c_str()));
+                if (out.size() != n) throw Error("0/phi: a list has " + std::to_string(out.size()) + " entries, expected " + std::to_string(n));
+            };
+            std::vector<double> v;
+            listOf(d.tokens("internalField"), (size_t)nIF, v);
+            for (int f = 0; f < nIF; f++) W[off + f] = v[f];
+            const Dict& bf = d.sub("boundaryField");
+            for (const PatchDef& p : hm.patches)
+            {
+                const Dict& pd = bf.sub(p.name);
+                if (!pd.has("value")) continue; // e.g. symmetry: stays zero
+                listOf(pd.tokens("value"), (size_t)p.size, v);
+                for (int i = 0; i < p.size; i++) W[off + p.start + i] = v[i];
             }
         }
         updateOFFields(W.data());
@@ -1393,6 +1425,78 @@ struct Solver
         }
         DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 1);
         be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
+    }
+
+    // ---- OpenFOAM field files (runTime.write() / DASolver::writeAdjointFields, DASolver.C:4055-4160) ---------------
+    // ASCII vol/surface fields of a state-layout vector under <case>/<timeName>/<prefix><state>; one GPU
+    void writeStateVector(const std::string& timeName, const std::string& prefix, const double* W) const
+    {
+        if (comm.active()) throw Error("field output runs on one GPU in this build");
+        const std::string dir = caseDirectory + "/" + timeName;
+        ::mkdir(dir.c_str(), 0755);
+        const int nC = hm.nC, nIF = hm.nIF;
+        // stdio rather than iostreams: number formatting must not depend on the C++ locale machinery of the host process
+        struct File
+        {
+            FILE* f;
+            explicit File(const std::string& path) : f(fopen(path.c_str(), "w"))
+            {
+                if (!f) throw Error("cannot write " + path);
+            }
+            ~File() { fclose(f); }
+        };
+        auto header = [&](FILE* f, const char* cls, const std::string& name, const char* dims) {
+            fprintf(f, "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class %s;\n    location \"%s\";\n    object %s;\n}\n\n"
+                       "dimensions %s;\n\n", cls, timeName.c_str(), name.c_str(), dims);
+        };
+        auto patches = [&](FILE* f, bool surface, const double* faceVals) {
+            fprintf(f, "boundaryField\n{\n");
+            for (size_t ip = 0; ip < hm.patches.size(); ip++)
+            {
+                const PatchDef& p = hm.patches[ip];
+                fprintf(f, "    %s\n    {\n", p.name.c_str());
+                if (surface)
+                {
+                    fprintf(f, "        type calculated;\n        value nonuniform List<scalar> %d(", p.size);
+                    for (int i = 0; i < p.size; i++) fprintf(f, "%s%.17g", i ? " " : "", faceVals[p.start + i]);
+                    fprintf(f, ");\n");
+                }
+                else
+                    fprintf(f, "        type %s;\n", hm.patchGeom[ip] == PG_SYMMETRY ? "symmetry" : "zeroGradient");
+                fprintf(f, "    }\n");
+            }
+            fprintf(f, "}\n");
+        };
+        {
+            File o(dir + "/" + prefix + "U");
+            header(o.f, "volVectorField", prefix + "U", "[0 1 -1 0 0 0 0]");
+            fprintf(o.f, "internalField nonuniform List<vector> %d\n(\n", nC);
+            for (int c = 0; c < nC; c++) fprintf(o.f, "(%.17g %.17g %.17g)\n", W[3 * c], W[3 * c + 1], W[3 * c + 2]);
+            fprintf(o.f, ");\n\n");
+            patches(o.f, false, nullptr);
+        }
+        std::vector<std::pair<std::string, const char*>> scal{{"p", par.comp ? "[1 -1 -2 0 0 0 0]" : "[0 2 -2 0 0 0 0]"}};
+        if (par.comp) scal.push_back({"T", "[0 0 0 1 0 0 0]"});
+        if (par.turb) scal.push_back({"nuTilda", "[0 2 -1 0 0 0 0]"});
+        size_t off = (size_t)3 * nC;
+        for (const auto& sc : scal)
+        {
+            File o(dir + "/" + prefix + sc.first);
+            header(o.f, "volScalarField", prefix + sc.first, sc.second);
+            fprintf(o.f, "internalField nonuniform List<scalar> %d\n(\n", nC);
+            for (int c = 0; c < nC; c++) fprintf(o.f, "%.17g\n", W[off + c]);
+            fprintf(o.f, ");\n\n");
+            patches(o.f, false, nullptr);
+            off += nC;
+        }
+        {
+            File o(dir + "/" + prefix + "phi");
+            header(o.f, "surfaceScalarField", prefix + "phi", par.comp ? "[1 0 -1 0 0 0 0]" : "[0 3 -1 0 0 0 0]");
+            fprintf(o.f, "internalField nonuniform List<scalar> %d\n(\n", nIF);
+            for (int i = 0; i < nIF; i++) fprintf(o.f, "%.17g\n", W[off + i]);
+            fprintf(o.f, ");\n\n");
+            patches(o.f, true, W + off);
+        }
     }
 
     // ---- mesh coordinates as an input (volCoord) ------------------------------------------------------

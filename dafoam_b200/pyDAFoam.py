@@ -5,7 +5,7 @@ compute_jacvec_product` do in dafoam/mphys/mphys_dafoam.py:405-574, 778-792 -- a
 `solveAdjoint` / `calcTotalDeriv`).
 
 Not reproduced (out of scope): OpenMDAO/MPhys components, pyGeo/IDWarp hooks, family groups and
-surface maps, decomposePar, file output, option type checking.  There is no CPU fallback: constructing the object needs
+surface maps, decomposePar, option type checking.  There is no CPU fallback: constructing the object needs
 libdab200.so and a B200."""
 from __future__ import annotations
 
@@ -130,6 +130,15 @@ class PYDAFOAM:
         residuals = np.zeros(self.solver.getNLocalAdjointStates(), self.dtype)
         self.solver.getResiduals(residuals)
         return residuals
+
+    # ---- output --------------------------------------------------------------------------------------------
+    def writeFields(self, writeTime=None):
+        """The current states as OpenFOAM fields under <case>/<writeTime>/ (what the reference's primal leaves on disk)."""
+        self.solver.writeFields(self.nSolvePrimals if writeTime is None else writeTime)
+
+    def writeAdjointFields(self, function, writeTime, psi):
+        """adjoint_<function>_<state> fields for post-processing (reference pyDAFoam.py:907-915)."""
+        self.solver.writeAdjointFields(function, writeTime, np.ascontiguousarray(psi, dtype=np.float64))
 
     # ---- adjoint -------------------------------------------------------------------------------------------
     def solveAdjoint(self, functionName):

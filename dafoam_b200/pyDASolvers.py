@@ -218,6 +218,14 @@ class pyDASolvers:
         _check_array(points, self.getNLocalPoints() * 3, "points")
         self._raise(self._L.dab_get_of_mesh_points(self._h, _dp(points)))
 
+    def writeAdjointFields(self, function, writeTime, psi):
+        _check_array(psi, self.getNLocalAdjointStates(), "psi")
+        self._raise(self._L.dab_write_adjoint_fields(self._h, function.encode(), C.c_double(writeTime), _dp(psi)))
+
+    def writeFields(self, writeTime):
+        """The current states as OpenFOAM field files under <case>/<writeTime>/ (runTime.write() of the primal solver)."""
+        self._raise(self._L.dab_write_fields(self._h, C.c_double(writeTime)))
+
     def updateOFMesh(self, points):
         _check_array(points, 3 * self.getNLocalPoints(), "points")
         self._raise(self._L.dab_update_of_mesh(self._h, _dp(points)))

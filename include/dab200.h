@@ -116,6 +116,12 @@ int dab_get_of_fields(dab_solver* s, double* states);
 
 /* getOFMeshPoints(points) (pyDASolvers.pyx:267-270) */
 int dab_get_of_mesh_points(dab_solver* s, double* points);
+/* writeAdjointFields(function, writeTime, psi): the adjoint vector as OpenFOAM fields adjoint_<function>_<state> under
+ * <case>/<writeTime>/ (reference pyDASolvers.pyx writeAdjointFields, DASolver.C:4055-4160), and the current states the way
+ * runTime.write() leaves them (U, p, [T], [nuTilda], phi) -- readable back as a case's 0/ fields. ASCII, one GPU. */
+int dab_write_adjoint_fields(dab_solver* s, const char* function, double write_time, const double* psi);
+int dab_write_fields(dab_solver* s, double write_time);
+
 /* updateOFMesh(points): new point coordinates (3*nLocalPoints), geometry recomputed, wall distance frozen
  * (reference pyDASolvers.pyx updateOFMesh, DASolver::updateOFMesh) */
 int dab_update_of_mesh(dab_solver* s, const double* points);

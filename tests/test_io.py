@@ -1,4 +1,6 @@
 """Host readers: ASCII and binary polyMesh give the same engine; dictionaries are parsed like OpenFOAM."""
+import os
+
 import numpy as np
 
 from tests.common import HOSTSIM, setup
@@ -28,3 +30,43 @@ def test_initial_states_come_from_the_zero_directory():
     pts = np.zeros(3 * mesh.n_points)
     sol.getOFMeshPoints(pts)
     assert np.array_equal(pts.reshape(-1, 3), mesh.points)
+
+
+def test_field_output_round_trip():
+    """writeFields / writeAdjointFields (OpenFOAM ASCII vol and surface fields) and reading the written states back as the 0/
+    fields of a case: an exact restart."""
+    import re
+    import shutil
+    import tempfile
+    from dafoam_b200 import cases
+    from dafoam_b200.pyDASolvers import pyDASolvers
+    from tests.common import HOSTSIM
+    mesh, bcs = cases.channel(nx=10, ny=6, nz=1), cases.default_bcs_channel()
+    d = tempfile.mkdtemp(prefix="dab_out_")
+    cases.write_case(d, mesh, bcs)
+    sol = pyDASolvers("DASimpleFoam -python", dict(primalMaxIters=25), caseDir=d, _lib_path=HOSTSIM)
+    sol.solvePrimal()
+    n = sol.getNLocalAdjointStates()
+    W = np.zeros(n)
+    sol.getOFFields(W)
+    sol.writeFields(25)
+    psi = np.random.default_rng(2).uniform(-1, 1, n)
+    sol.writeAdjointFields("CD", 25, psi)
+    for name in ("U", "p", "nuTilda", "phi", "adjoint_CD_U", "adjoint_CD_p", "adjoint_CD_nuTilda", "adjoint_CD_phi"):
+        assert os.path.exists(os.path.join(d, "25", name)), name
+    txt = open(os.path.join(d, "25", "adjoint_CD_p")).read()
+    vals = np.array(re.search(r"internalField nonuniform List<scalar> \d+\s*\(([^)]*)\)", txt).group(1).split(), dtype=float)
+    nC = mesh.n_cells
+    assert np.array_equal(vals, psi[3 * nC:4 * nC])
+    # restart: the case's own boundary conditions with the written internal fields (+ the written flux)
+    d2 = tempfile.mkdtemp(prefix="dab_restart_")
+    shutil.copytree(d, d2, dirs_exist_ok=True)
+    for name in ("U", "p", "nuTilda"):
+        new = re.search(r"internalField[^;]*;", open(os.path.join(d, "25", name)).read(), re.S).group(0)
+        old = open(os.path.join(d2, "0", name)).read()
+        open(os.path.join(d2, "0", name), "w").write(re.sub(r"internalField[^;]*;", lambda m: new, old, count=1, flags=re.S))
+    shutil.copy(os.path.join(d, "25", "phi"), os.path.join(d2, "0", "phi"))
+    sol2 = pyDASolvers("DASimpleFoam -python", {}, caseDir=d2, _lib_path=HOSTSIM)
+    W2 = np.zeros(n)
+    sol2.getOFFields(W2)
+    assert np.array_equal(W, W2)
