@@ -121,6 +121,7 @@ class pyDASolvers:
         if isinstance(argsAll, bytes):
             argsAll = argsAll.decode()
         self._options = dict(pyOptions or {})
+        self._solverName = argsAll.split()[0] if argsAll.split() else "DASimpleFoam"
         uid = None if ncclUniqueId is None else C.c_char_p(bytes(ncclUniqueId))
         rc = self._L.dab_create(os.path.abspath(caseDir).encode(), argsAll.encode(), json.dumps(self._options).encode(),
                                 C.c_int(device), C.c_int(rank), C.c_int(nRanks), uid, C.byref(self._h))
@@ -268,6 +269,64 @@ class pyDASolvers:
         v = C.c_double()
         self._raise(self._L.dab_calc_function(self._h, functionName.encode(), C.byref(v)))
         return float(v.value)
+
+    def calcOutput(self, outputName, outputType, output):
+        """output[:] = the value of one output object (reference pyDASolvers.pyx calcOutput -> DAOutput::run;
+        DAOutputFunction.C, DAOutputResidual.C).  The coupling outputs (force/thermal) are outside this path."""
+        _check_array(output, self.getOutputSize(outputName, outputType), "output")
+        if outputType == "function":
+            output[0] = self.calcFunction(outputName)
+        elif outputType == "residual":
+            self.getResiduals(output)
+        else:
+            raise DAB200Error("calcOutput: output type %s is not supported (function, residual)" % outputType)
+
+    def calcPrimalResidualStatistics(self, mode):
+        """Norm2 / mean / max of every residual block of this rank, and the total norm (reference DASolver.C:745-1000).
+        mode "print" also prints them in the reference's format; returns {stateName: {"norm2","mean","max"}, "total": norm2}."""
+        if mode not in ("print", "calc"):
+            raise DAB200Error("mode not valid")
+        n, nC = self.getNLocalAdjointStates(), self.getNLocalCells()
+        res = np.zeros(n)
+        self.getResiduals(res)
+        blocks = {"U": res[:3 * nC].reshape(nC, 3)}
+        off, nCellStates = 3 * nC, (n - self.getNLocalFaces()) // nC
+        comp = self._solverName != "DASimpleFoam"
+        names = (["p", "T"] if comp else ["p"]) + (["nuTilda"] if nCellStates == (6 if comp else 5) else [])
+        for nm in names:
+            blocks[nm] = res[off:off + nC]
+            off += nC
+        blocks["phi"] = res[off:]
+        out, total = {}, 0.0
+        for nm, r in blocks.items():
+            a = np.abs(r)
+            st = {"norm2": np.sqrt((r * r).sum(axis=0)), "mean": a.mean(axis=0), "max": a.max(axis=0)}
+            total += float((r * r).sum())
+            out[nm] = st
+            if mode == "print":
+                for key, label in (("norm2", "Norm2"), ("mean", "Mean"), ("max", "Max")):
+                    v = st[key]
+                    txt = "(%s)" % " ".join("%g" % x for x in v) if np.ndim(v) else "%g" % v
+                    print("%s Residual %s: %s" % (nm, label, txt))
+        out["total"] = float(np.sqrt(total))
+        if mode == "print":
+            print("Total Residual Norm2: %g" % out["total"])
+        return out
+
+    def updateStateBoundaryConditions(self):
+        """Reference DASolver.C:2863-2886 re-evaluates BCs, nut and the thermo fields after a state change.  Here they are
+        functions evaluated inside the kernels from the current states, so there is nothing stored to refresh."""
+        return None
+
+    def updateBoundaryConditions(self, fieldName, fieldType):
+        """Reference DASolver.C:2814-2845 (correctBoundaryConditions of one field): same remark as above."""
+        if fieldType not in ("scalar", "vector"):
+            raise DAB200Error("%s not support. Options are: vector or scalar " % fieldType)
+        return None
+
+    def printAllOptions(self):
+        """Reference DASolver.H printAllOptions: dump the options dictionary."""
+        print(json.dumps(self._options, indent=2, sort_keys=True, default=str))
 
     def runColoring(self):
         # the colouring is computed inside calcdRdWT on first use (reference DASolver.C:708-743)

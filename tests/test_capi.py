@@ -56,3 +56,34 @@ def test_argument_errors_mirror_the_reference():
                                                          W.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
     with pytest.raises(DAB200Error, match="is not defined"):
         sol.calcFunction("CL")
+
+
+def test_output_and_statistics_helpers(capsys):
+    """calcOutput / calcPrimalResidualStatistics / BC refresh no-ops of the reference's pyDASolvers API."""
+    from dafoam_b200.pyDASolvers import DAB200Error
+    from tests.common import HOSTSIM
+    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
+                 "direction": [1.0, 0.0, 0.0], "scale": 0.02}}
+    mesh, bcs, orc, sol, W, _ = setup("naca", True, nk=1, lib_path=HOSTSIM, extra_options=dict(function=fn))
+    sol.updateOFFields(W)
+    sol.updateStateBoundaryConditions()
+    sol.updateBoundaryConditions("U", "vector")
+    with pytest.raises(DAB200Error):
+        sol.updateBoundaryConditions("U", "tensor")
+    R = np.zeros(orc.ndof)
+    sol.calcOutput("R", "residual", R)
+    R2 = np.zeros(orc.ndof)
+    sol.getResiduals(R2)
+    assert np.array_equal(R, R2)
+    st = sol.calcPrimalResidualStatistics("print")
+    txt = capsys.readouterr().out
+    assert "U Residual Norm2: (" in txt and "Total Residual Norm2" in txt
+    assert abs(st["total"] - np.linalg.norm(R)) <= 1e-12 * np.linalg.norm(R)
+    nC = mesh.n_cells
+    assert np.allclose(st["nuTilda"]["max"], np.abs(R[4 * nC:5 * nC]).max())
+    with pytest.raises(DAB200Error):
+        sol.calcPrimalResidualStatistics("dump")
+    name = list(sol._options["function"].keys())[0]
+    v = np.zeros(1)
+    sol.calcOutput(name, "function", v)
+    assert v[0] == sol.calcFunction(name)
