@@ -253,6 +253,30 @@ struct StridedCopy
 };
 
 // HbyA = rAU*H = U - rAU*(UEqn & U) with the matrix frozen and U the solution of the momentum predictor
+// SIMPLEC (fvSolution SIMPLE { consistent yes; }, reference pEqnSimple.H:27-33): rAtU = 1/(1/rAU - H1) replaces rAU in the
+// pressure laplacian and the correctors; phiHbyA and HbyA carry the (rAtU - rAU) part of the old pressure gradient.
+// rAt == nullptr: plain SIMPLE.
+struct Simplec
+{
+    const double* rAt = nullptr;   // [nT]
+    const double* pOld = nullptr;  // [nT] p at the start of the iteration
+    const double* gPOld = nullptr; // [3*nT] its gradient
+};
+
+// H1 = -(sum of the off-diagonal coefficients)/V of the relaxed momentum matrix (fvMatrix::H1), rAtU from it
+struct RAtKernel
+{
+    EqnView e;
+    const double *rAU, *V;
+    double* rAt;
+    DAB_HD void operator()(int c) const
+    {
+        double h1 = 0.0;
+        for (int k = 0; k < e.maxCF; k++) h1 -= e.off[(size_t)k * e.nC + c];
+        rAt[c] = 1.0 / (1.0 / rAU[c] - h1 / V[c]);
+    }
+};
+
 struct HbyAKernel
 {
     EqnView e;
@@ -310,6 +334,7 @@ struct PEqnAssemble
     StateView s;
     RecordView r;
     EqnView e;
+    Simplec sc;
     DAB_HD void operator()(int c) const
     {
         const int nT = m.nCtot, nC = m.nC;
@@ -337,7 +362,15 @@ struct PEqnAssemble
                     ph += Sv[j] * (w * r.HbyA[(size_t)j * nT + o] + (1.0 - w) * r.HbyA[(size_t)j * nT + n]);
                     cg += kv[j] * (w * r.gP[(size_t)j * nT + o] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
                 }
-                const double gam = (w * r.rAU[o] + (1.0 - w) * r.rAU[n]) * mS;
+                double gam = (w * r.rAU[o] + (1.0 - w) * r.rAU[n]) * mS;
+                if (sc.rAt)
+                {
+                    const double gamT = (w * sc.rAt[o] + (1.0 - w) * sc.rAt[n]) * mS;
+                    double cgOld = 0.0;
+                    for (int j = 0; j < 3; j++) cgOld += kv[j] * (w * sc.gPOld[(size_t)j * nT + o] + (1.0 - w) * sc.gPOld[(size_t)j * nT + n]);
+                    ph += (gamT - gam) * (dl * (sc.pOld[n] - sc.pOld[o]) + cgOld);
+                    gam = gamT;
+                }
                 e.off[(size_t)k * nC + c] = -gam * dl;
                 D += gam * dl;
                 B -= fr.s * (ph - gam * cg);
@@ -347,9 +380,17 @@ struct PEqnAssemble
                 e.off[(size_t)k * nC + c] = 0.0;
                 const int b = f - m.nIF, pa = m.bPatch[b];
                 const double frp = bcFrac(q.bcKind[F_P][pa], s.phi[f]);
-                const double gb = r.rAU[c] * mS * dl * frp;
+                double ph = phiHbyABoundary(m, q, s, r, f, c), gU = r.rAU[c] * mS;
+                if (sc.rAt)
+                {
+                    double pv, snOld, fr_;
+                    bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], sc.pOld[c], s.phi[f], dl, pv, snOld, fr_);
+                    ph += (sc.rAt[c] * mS - gU) * snOld;
+                    gU = sc.rAt[c] * mS;
+                }
+                const double gb = gU * dl * frp;
                 D += gb;
-                B += gb * q.bcVal[F_P][pa][0] - phiHbyABoundary(m, q, s, r, f, c);
+                B += gb * q.bcVal[F_P][pa][0] - ph;
             }
         }
         e.diag[c] = D;
@@ -366,8 +407,10 @@ struct PhiUpdate
     StateView s;
     RecordView r;
     double* phi;
+    Simplec sc;
     DAB_HD void operator()(int c) const
     {
+        const int nT = m.nCtot;
         DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
@@ -376,14 +419,38 @@ struct PhiUpdate
             if (fr.s < 0) continue;
             const int f = fr.f;
             if (!fr.bnd)
-                phi[f] = faceF(m, s, r, f, c, fr.n);
+            {
+                double F = faceF(m, s, r, f, c, fr.n);
+                if (sc.rAt)
+                {
+                    // + (rAtU - rAU)_f snGrad(pOld) |Sf| of phiHbyA, - (rAtU - rAU)_f snGrad(p) |Sf| of the flux
+                    const int n = fr.n;
+                    const double w = m.w[f], dl = m.delta[f];
+                    const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                    double cg = 0.0, cgOld = 0.0;
+                    for (int j = 0; j < 3; j++)
+                    {
+                        cg += kv[j] * (w * r.gP[(size_t)j * nT + c] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
+                        cgOld += kv[j] * (w * sc.gPOld[(size_t)j * nT + c] + (1.0 - w) * sc.gPOld[(size_t)j * nT + n]);
+                    }
+                    const double dg = (w * (sc.rAt[c] - r.rAU[c]) + (1.0 - w) * (sc.rAt[n] - r.rAU[n])) * m.magSf[f];
+                    F += dg * ((dl * (sc.pOld[n] - sc.pOld[c]) + cgOld) - (dl * (s.p[n] - s.p[c]) + cg));
+                }
+                phi[f] = F;
+            }
             else
             {
                 const int b = f - m.nIF, pa = m.bPatch[b];
-                const double ph = phiHbyABoundary(m, q, s, r, f, c);
+                double ph = phiHbyABoundary(m, q, s, r, f, c), gU = r.rAU[c] * m.magSf[f];
                 double pv, sn, fr_;
+                if (sc.rAt)
+                {
+                    bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], sc.pOld[c], s.phi[f], m.delta[f], pv, sn, fr_);
+                    ph += (sc.rAt[c] * m.magSf[f] - gU) * sn;
+                    gU = sc.rAt[c] * m.magSf[f];
+                }
                 bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], s.phi[f], m.delta[f], pv, sn, fr_);
-                phi[f] = ph - r.rAU[c] * m.magSf[f] * sn;
+                phi[f] = ph - gU * sn;
             }
         }
     }
@@ -397,13 +464,21 @@ struct RelaxField // x = xOld + alpha*(x - xOld)
     DAB_HD void operator()(int c) const { x[c] = xOld[c] + alpha * (x[c] - xOld[c]); }
 };
 
-struct UCorrect // U = HbyA - rAU*grad(p)
+struct UCorrect // U = HbyA - rAU*grad(p); SIMPLEC: HbyA - (rAU - rAtU)*grad(pOld) - rAtU*grad(p)
 {
     RecordView r;
     double* U;
     int nT;
+    Simplec sc;
     DAB_HD void operator()(int c) const
     {
+        if (sc.rAt)
+        {
+            const double a = r.rAU[c] - sc.rAt[c];
+            for (int j = 0; j < 3; j++)
+                U[3 * c + j] = r.HbyA[(size_t)j * nT + c] - a * sc.gPOld[(size_t)j * nT + c] - sc.rAt[c] * r.gP[(size_t)j * nT + c];
+            return;
+        }
         for (int j = 0; j < 3; j++) U[3 * c + j] = r.HbyA[(size_t)j * nT + c] - r.rAU[c] * r.gP[(size_t)j * nT + c];
     }
 };
@@ -741,12 +816,13 @@ struct Primal
     double alphaP = 0.3, alphaN = 0.7, alphaE = 0.7, alphaRho = 0.05;
     double minResTol = 1e-8, minResTolDiff = 1e2;
     int minIters = 1, maxIters = 1000, nNonOrth = 0, printInterval = 100;
+    bool consistent = false; // SIMPLEC
     SegControl cU, cP, cN, cE;
     double ntMin = 1e-16, ntMax = 1e16;
     double pMin = 20000.0, pMax = 500000.0, TMin = 100.0, TMax = 1000.0, UMax = 1000.0; // DAOption primalVarBounds (compressible)
     bool allocated = false;
     DevBuf<double> uOff, uDiag, uB, pOff, pDiag, pB, nOff, nDiag, nB;
-    DevBuf<double> Utmp, pOld, ntTmp, red, ones, r, z, d, q, eOff, eDiag, eB, heTmp;
+    DevBuf<double> Utmp, pOld, ntTmp, red, ones, r, z, d, q, eOff, eDiag, eB, heTmp, rAt, gPOld;
     DevBuf<int32_t> dColourOf, dColourList;
     std::vector<int> colourStart; // [nColours+1] into dColourList
     // pressure coarse space

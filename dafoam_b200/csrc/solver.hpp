@@ -362,8 +362,12 @@ struct Solver
         par.alphaU = 1.0;
         if (fso.hasSub("relaxationFactors") && fso.sub("relaxationFactors").hasSub("equations"))
             par.alphaU = fso.sub("relaxationFactors").sub("equations").scalarOr("U", 1.0);
-        if (fso.hasSub("SIMPLE") && fso.sub("SIMPLE").wordOr("consistent", "false") == "true")
-            throw Error("SIMPLEC (consistent true) is not supported in this build");
+        if (fso.hasSub("SIMPLE"))
+        {
+            const std::string c = fso.sub("SIMPLE").wordOr("consistent", "false");
+            primal.consistent = (c == "true" || c == "yes" || c == "on");
+            if (primal.consistent && par.comp) throw Error("SIMPLEC (consistent yes) is built for DASimpleFoam only");
+        }
         // primal solver controls (system/fvSolution, system/controlDict)
         if (fso.hasSub("relaxationFactors"))
         {

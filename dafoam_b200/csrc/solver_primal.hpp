@@ -20,6 +20,10 @@ inline void Solver::primalSetup()
     P.Utmp.alloc(be, 3 * nT); P.pOld.alloc(be, nT); P.ntTmp.alloc(be, nT);
     P.red.alloc(be, 6 * nC); P.ones.alloc(be, nC);
     P.r.alloc(be, nC); P.z.alloc(be, nT); P.d.alloc(be, nT); P.q.alloc(be, nC);
+    if (P.consistent)
+    {
+        P.rAt.alloc(be, nT); P.gPOld.alloc(be, 3 * nT);
+    }
     if (par.comp)
     {
         P.eOff.alloc(be, mcf * nC); P.eDiag.alloc(be, nC); P.eB.alloc(be, nC); P.heTmp.alloc(be, nT);
@@ -324,7 +328,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
         if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}, {rv.rho, 1, 1, nT}});
         DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv); // grad of the relaxed p, closures at the new (p, T)
         exGrad();
-        be.launch(nC, UCorrect{rv, dU.p, nT});
+        be.launch(nC, UCorrect{rv, dU.p, nT, Simplec()});
         be.launch(3 * nC, BoundField{dU.p, -P.UMax, P.UMax});
         if (mr) halo.exchangeCells({{dU.p, 3, 3, 1}});
         if (par.turb)
@@ -362,6 +366,14 @@ inline int Solver::solvePrimal(PrimalStats& st)
         // --- pressure corrector (pEqnSimple.H)
         be.launch(nC, HbyAKernel{eU, sv, rv, mv.V, nT});
         if (mr) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}});
+        Simplec sc;
+        if (P.consistent)
+        {
+            be.launch(nC, RAtKernel{eU, rv.rAU, mv.V, P.rAt.p});
+            if (mr) halo.exchangeCells({{P.rAt.p, 1, 1, nT}});
+            be.d2d(P.gPOld.p, rv.gP, (size_t)3 * nT * sizeof(double));
+            sc = Simplec{P.rAt.p, P.pOld.p, P.gPOld.p};
+        }
         for (int no = 0; no <= P.nNonOrth; no++)
         {
             if (no > 0)
@@ -369,7 +381,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
                 DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad(p) of the latest p for the non-orthogonal correction
                 exGrad();
             }
-            DAB_LAUNCH_NF(nC, PEqnAssemble, mv, par, sv, rv, eP);
+            DAB_LAUNCH_NF(nC, PEqnAssemble, mv, par, sv, rv, eP, sc);
             if (no == 0 && (it == 1 || (it - 1) % P.coarseRefresh == 0)) primalCoarseRefresh(eP);
             double rp;
             st.pIterations += primalPcg(eP, dP.p, P.cP, rp);
@@ -377,13 +389,13 @@ inline int Solver::solvePrimal(PrimalStats& st)
             maxRes = std::max(maxRes, rp);
         }
         if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}});
-        DAB_LAUNCH_NF(nC, PhiUpdate, mv, par, sv, rv, dPhi.p);
+        DAB_LAUNCH_NF(nC, PhiUpdate, mv, par, sv, rv, dPhi.p, sc);
         if (mr) halo.exchangeFaces({{dPhi.p, 1, 1, hm.nF}}); // cut faces: the owner rank's flux
         be.launch(nC, RelaxField{dP.p, P.pOld.p, P.alphaP});
         if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}});
         DAB_LAUNCH_NF(nT, FwdA, mv, par, sv, rv); // grad of the relaxed p
         exGrad();
-        be.launch(nC, UCorrect{rv, dU.p, nT});
+        be.launch(nC, UCorrect{rv, dU.p, nT, sc});
         if (mr) halo.exchangeCells({{dU.p, 3, 3, 1}});
         // --- turbulence (DASpalartAllmaras::correct)
         if (par.turb)

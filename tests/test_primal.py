@@ -18,10 +18,10 @@ FN = {"CD": {"type": "force", "source": "patchToFace", "patches": ["walls"], "di
 INP = {"patchV": {"type": "patchVelocity", "patches": ["inlet"], "flowAxis": "x", "normalAxis": "y"}}
 
 
-def make(lib_path, tol=1e-12):
+def make(lib_path, tol=1e-12, **dicts):
     mesh, bcs = cases.channel(nx=14, ny=8, nz=1), cases.default_bcs_channel()
     d = tempfile.mkdtemp(prefix="dab_primal_")
-    cases.write_case(d, mesh, bcs)
+    cases.write_case(d, mesh, bcs, **dicts)
     opts = dict(normalizeStates=NORM_STATES, function=FN, inputInfo=INP, primalMinResTol=tol, primalMaxIters=2000,
                 adjEqnOption=dict(gmresRelTol=1e-12, gmresMaxIters=400, gmresRestart=400, pcConLevel=3))
     sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib_path)
@@ -48,6 +48,28 @@ def run_fixed_point(lib_path):
         assert err < 1e-8, (name, err)
     # a second call starts from the converged state: only the round-off tail is left
     assert sol.solvePrimal() == 0 and sol.primalStats.iterations <= 40
+
+
+def run_simplec(lib_path):
+    """fvSolution SIMPLE { consistent yes; } (SIMPLEC, reference pEqnSimple.H:27-33): the same fixed point, reached in
+    fewer iterations without pressure under-relaxation."""
+    mesh, bcs, sol = make(lib_path)
+    assert sol.solvePrimal() == 0
+    itSimple = sol.primalStats.iterations
+    n = sol.getNLocalAdjointStates()
+    W = np.zeros(n)
+    sol.getOFFields(W)
+    mesh, bcs, solc = make(lib_path, consistent=True, relax_u=0.7, relax_p=1.0)
+    assert solc.solvePrimal() == 0
+    st = solc.primalStats
+    assert st.converged == 1 and st.max_residual < 1e-12
+    Wc = np.zeros(n)
+    solc.getOFFields(Wc)
+    nC = mesh.n_cells
+    for name, a, b in (("U", 0, 3 * nC), ("p", 3 * nC, 4 * nC), ("nuTilda", 4 * nC, 5 * nC), ("phi", 5 * nC, n)):
+        err = np.linalg.norm(W[a:b] - Wc[a:b]) / np.linalg.norm(W[a:b])
+        assert err < 1e-8, (name, err)
+    assert st.iterations < 0.8 * itSimple, (st.iterations, itSimple)
 
 
 def run_workflow(lib_path):
@@ -176,6 +198,15 @@ def test_pydafoam_class_cuda():
 
 def test_simple_fixed_point_is_the_root_of_the_residual_host_build():
     run_fixed_point(HOSTSIM)
+
+
+def test_simplec_reaches_the_same_fixed_point_host_build():
+    run_simplec(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_simplec_reaches_the_same_fixed_point_cuda():
+    run_simplec(None)
 
 
 def test_primal_adjoint_workflow_matches_fd_host_build():
