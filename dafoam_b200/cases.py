@@ -640,10 +640,28 @@ def write_case(case_dir, mesh: PolyMesh, bcs, binary=False, **dict_kw):
     ras = "SpalartAllmaras" if "nuTilda" in bcs else "dummy"
     dict_kw.setdefault("ras_model", ras)
     thermo = dict_kw.pop("thermo", None)
+    mrf = dict_kw.pop("mrf", None)
     write_dicts(case_dir, **dict_kw)
     if thermo is not None:
         write_thermo(case_dir, thermo)
+    if mrf is not None:
+        write_mrf(case_dir, mrf)
     return case_dir
+
+
+def write_mrf(case_dir, mrf):
+    """constant/MRFProperties + constant/polyMesh/cellZones of one rotating zone.  mrf = dict(cellZone=name, cells=[...],
+    origin=(3), axis=(3), omega=rad/s, nonRotatingPatches=[...]) -- the entries of OpenFOAM's MRFZone dictionary."""
+    cells = np.asarray(mrf["cells"], dtype=np.int64)
+    with open(os.path.join(case_dir, "constant", "polyMesh", "cellZones"), "w") as f:
+        f.write(_header("regIOobject", "constant/polyMesh", "cellZones"))
+        f.write("\n1\n(\n%s\n{\n    type cellZone;\n    cellLabels List<label> %d\n(\n%s\n);\n}\n)\n" % (
+            mrf["cellZone"], cells.size, "\n".join(str(int(c)) for c in cells)))
+    with open(os.path.join(case_dir, "constant", "MRFProperties"), "w") as f:
+        f.write(_header("dictionary", "constant", "MRFProperties"))
+        f.write("\nMRF\n{\n    cellZone %s;\n    active yes;\n    nonRotatingPatches (%s);\n    origin (%.17g %.17g %.17g);\n"
+                "    axis (%.17g %.17g %.17g);\n    omega %.17g;\n}\n" % ((mrf["cellZone"], " ".join(mrf.get("nonRotatingPatches", [])))
+                                                                         + tuple(mrf["origin"]) + tuple(mrf["axis"]) + (mrf["omega"],)))
 
 
 # ----------------------------------------------------------------------------------------------

@@ -68,7 +68,9 @@ DAB_HD void boundaryPoint(const MeshView& m, const Params& q, const StateView& s
     const double phib = s.phi[f], dl = m.delta[f], im = 1.0 / m.magSf[f];
     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
     const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-    bcVector(q.bcKind[F_U][pa], q.bcVal[F_U][pa], Uc, phib, dl, nh, b.bu);
+    double uw[3];
+    mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+    bcVector(q.bcKind[F_U][pa], uw, Uc, phib, dl, nh, b.bu);
     bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, b.p, b.sngP, b.frP);
     bcScalar(q.bcKindT[pa], q.bcValT[pa], s.T[c], phib, dl, b.T, b.sngT, b.frT);
     b.th = thermoOf(q, b.p, b.T);
@@ -148,7 +150,9 @@ struct cFwdA
                 const double phib = s.phi[f], dl = m.delta[f], im = 1.0 / m.magSf[f];
                 const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                 BCv bu;
-                bcVector(q.bcKind[F_U][pa], q.bcVal[F_U][pa], Uc, phib, dl, nh, bu);
+                double uw[3];
+                mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+                bcVector(q.bcKind[F_U][pa], uw, Uc, phib, dl, nh, bu);
                 for (int j = 0; j < 3; j++) Uf[j] = bu.val[j];
                 double sn, fr_, Tb;
                 bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], pc, phib, dl, pf, sn, fr_);
@@ -338,9 +342,17 @@ struct cFwdB
         r.D0[c] = D0;
         r.flag[c] = flag;
         const double cU = q.nrU ? 1.0 : V;
+        double cor[3] = {0.0, 0.0, 0.0}; // MRF.DDt(rho, U) = rho * (Omega x U) in the zone cells
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            const double* w = m.mrfOmega;
+            cor[0] = rhoc * (w[1] * Uc[2] - w[2] * Uc[1]);
+            cor[1] = rhoc * (w[2] * Uc[0] - w[0] * Uc[2]);
+            cor[2] = rhoc * (w[0] * Uc[1] - w[1] * Uc[0]);
+        }
         for (int j = 0; j < 3; j++)
         {
-            const double M = MV[j] * iV - (m.fvS ? m.fvS[(size_t)j * nC + c] : 0.0); // UEqn ... - fvSource
+            const double M = MV[j] * iV + cor[j] - (m.fvS ? m.fvS[(size_t)j * nC + c] : 0.0); // UEqn ... + MRF.DDt - fvSource
             r.HbyA[(size_t)j * nT + c] = Uc[j] - rAU * M;
             R[3 * c + j] = (M + r.gP[(size_t)j * nT + c]) * cU;
         }
@@ -441,6 +453,7 @@ DAB_HD double cFaceF(const MeshView& m, const StateView& s, const RecordView& r,
     const double rhof = w * r.rho[o] + (1.0 - w) * r.rho[n];
     const double gam = w * r.rho[o] * r.rAU[o] + (1.0 - w) * r.rho[n] * r.rAU[n];
     const double sn = m.delta[f] * (s.p[n] - s.p[o]) + cg;
+    if (m.mrfFlux) ph -= m.mrfFlux[f]; // MRF.makeRelative(interpolate(rho), phiHbyA)
     return rhof * ph - gam * mS * sn;
 }
 
@@ -481,6 +494,7 @@ struct cFwdC
                     ph = m.Sx[f] * bp.bu.val[0] + m.Sy[f] * bp.bu.val[1] + m.Sz[f] * bp.bu.val[2];
                 else
                     ph = m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c];
+                ph = mrfBoundaryFlux(m, f, ph, 1.0);
                 F = bp.th.rho * ph - bp.th.rho * r.rAU[c] * m.magSf[f] * bp.sngP;
             }
             div += fr.s * F;

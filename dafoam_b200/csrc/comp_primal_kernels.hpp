@@ -138,10 +138,19 @@ struct cUEqnAssemble
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
         const double Dn = D2 / q.alphaU - icMin;
         r.rAU[c] = V / (Dn + icAvg);
+        double cor[3] = {0.0, 0.0, 0.0}; // MRF.DDt(rho, U), explicit
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            const double* w = m.mrfOmega;
+            const double rc = r.rho[c];
+            cor[0] = rc * (w[1] * Uc[2] - w[2] * Uc[1]);
+            cor[1] = rc * (w[2] * Uc[0] - w[0] * Uc[2]);
+            cor[2] = rc * (w[0] * Uc[1] - w[1] * Uc[0]);
+        }
         for (int j = 0; j < 3; j++)
         {
             e.diag[(size_t)j * nC + c] = Dn + icS[j];
-            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j] + (m.fvS ? V * m.fvS[(size_t)j * nC + c] : 0.0);
+            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j] + (m.fvS ? V * m.fvS[(size_t)j * nC + c] : 0.0) - V * cor[j];
         }
         (void)NF;
     }
@@ -264,8 +273,9 @@ DAB_HD double cPhBoundary(const MeshView& m, const Params& q, const RecordView& 
     const int nT = m.nCtot;
     const int kU = q.bcKind[F_U][m.bPatch[f - m.nIF]];
     const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
-    if (q.constrainHbyA && !assignable) return m.Sx[f] * bp.bu.val[0] + m.Sy[f] * bp.bu.val[1] + m.Sz[f] * bp.bu.val[2];
-    return m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c];
+    if (q.constrainHbyA && !assignable)
+        return mrfBoundaryFlux(m, f, m.Sx[f] * bp.bu.val[0] + m.Sy[f] * bp.bu.val[1] + m.Sz[f] * bp.bu.val[2], 1.0);
+    return mrfBoundaryFlux(m, f, m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c], 1.0);
 }
 
 // pressure equation div(phiHbyA) - laplacian(rho rAU, p) = 0, sign-flipped to the SPD form
@@ -303,6 +313,7 @@ struct cPEqnAssemble
                     ph += Sv[j] * (w * r.HbyA[(size_t)j * nT + o] + (1.0 - w) * r.HbyA[(size_t)j * nT + n]);
                     cg += kv[j] * (w * r.gP[(size_t)j * nT + o] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
                 }
+                if (m.mrfFlux) ph -= m.mrfFlux[f];
                 const double rhof = w * r.rho[o] + (1.0 - w) * r.rho[n];
                 const double gam = (w * r.rho[o] * r.rAU[o] + (1.0 - w) * r.rho[n] * r.rAU[n]) * mS;
                 e.off[(size_t)k * nC + c] = -gam * dl;

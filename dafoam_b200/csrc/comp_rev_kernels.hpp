@@ -162,6 +162,7 @@ struct cRevA
                     HbA[j] += wc * Sv[j] * rhof * Fb;
                     gPb[j] -= gam * mS * wc * kv[j] * Fb;
                 }
+                if (m.mrfFlux) ph -= m.mrfFlux[f]; // owner-oriented, like ph, sn and Fb
                 rhob += wc * (ph - rAUc * mS * sn) * Fb;
                 rAUb -= wc * rhoc * mS * sn * Fb;
                 pb += fr.s * gam * mS * dl * Fb;
@@ -177,7 +178,10 @@ struct cRevA
                 BoundaryAdj ba;
                 ba.clear();
                 double ph;
-                if (q.constrainHbyA && !assignable)
+                const int mty = m.mrfType ? m.mrfType[f - m.nIF] : 0;
+                if (mty == 1)
+                    ph = 0.0; // rotating wall of the MRF zone: zero relative flux
+                else if (q.constrainHbyA && !assignable)
                 {
                     ph = Sv[0] * bp.bu.val[0] + Sv[1] * bp.bu.val[1] + Sv[2] * bp.bu.val[2];
                     for (int j = 0; j < 3; j++) ba.val[j] += Sv[j] * bp.th.rho * Fb;
@@ -187,6 +191,7 @@ struct cRevA
                     ph = Sv[0] * r.HbyA[c] + Sv[1] * r.HbyA[(size_t)nT + c] + Sv[2] * r.HbyA[(size_t)2 * nT + c];
                     for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * bp.th.rho * Fb;
                 }
+                if (mty == 2) ph -= m.mrfFlux[f];
                 ba.rho += (ph - rAUc * mS * bp.sngP) * Fb;
                 rAUb -= bp.th.rho * mS * bp.sngP * Fb;
                 ba.sngP -= bp.th.rho * rAUc * mS * Fb;
@@ -197,16 +202,27 @@ struct cRevA
         const double cU = q.nrU ? 1.0 : V;
         const double D0 = r.D0[c];
         double rAUtot = rAUb;
+        double Mbv[3];
         for (int j = 0; j < 3; j++)
         {
             const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) / rAUc;
             const double psiU = cU * x.U[3 * c + j];
             const double Mb = psiU - rAUc * HbA[j];
+            Mbv[j] = Mb;
             rAUtot -= M * HbA[j];
             const double mt = Mb / V;
             a.mt[(size_t)j * nT + c] = mt;
             a.Udir[(size_t)j * nC + c] = Ub[j] + HbA[j] + D0 * mt;
             a.gPb[(size_t)j * nT + c] = gPb[j] + psiU;
+        }
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            // adjoint of M += rho * (Omega x U): Ub += rho * (Mb x Omega), rhob += Mb . (Omega x U)
+            const double* w = m.mrfOmega;
+            a.Udir[c] += rhoc * (Mbv[1] * w[2] - Mbv[2] * w[1]);
+            a.Udir[(size_t)nC + c] += rhoc * (Mbv[2] * w[0] - Mbv[0] * w[2]);
+            a.Udir[(size_t)2 * nC + c] += rhoc * (Mbv[0] * w[1] - Mbv[1] * w[0]);
+            rhob += Mbv[0] * (w[1] * Uc[2] - w[2] * Uc[1]) + Mbv[1] * (w[2] * Uc[0] - w[0] * Uc[2]) + Mbv[2] * (w[0] * Uc[1] - w[1] * Uc[0]);
         }
         a.Dn[c] = -rAUc * rAUc * rAUtot / V;
         a.pdir[c] = pb;

@@ -61,7 +61,9 @@ struct FwdA
                 const double im = 1.0 / m.magSf[f];
                 const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                 BCv bu;
-                bcVector(q.bcKind[F_U][pa], q.bcVal[F_U][pa], Uc, phib, dl, nh, bu);
+                double uw[3];
+                mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+                bcVector(q.bcKind[F_U][pa], uw, Uc, phib, dl, nh, bu);
                 for (int j = 0; j < 3; j++) Uf[j] = bu.val[j];
                 double sn, fr_;
                 bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], pc, phib, dl, pf, sn, fr_);
@@ -254,7 +256,9 @@ struct FwdB
                 const double im = 1.0 / mS;
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 BCv bu;
-                bcVector(q.bcKind[F_U][pa], q.bcVal[F_U][pa], Uc, mf, dl, nh, bu);
+                double uw[3];
+                mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+                bcVector(q.bcKind[F_U][pa], uw, Uc, mf, dl, nh, bu);
                 double ntb = 0.0, sngN = 0.0, frN;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
                 double dP, dNb, dUn[3];
@@ -309,9 +313,17 @@ struct FwdB
         r.D0[c] = D0;
         r.flag[c] = flag;
         const double cU = q.nrU ? 1.0 : V;
+        double cor[3] = {0.0, 0.0, 0.0}; // MRF.DDt(U): Omega x U in the zone cells
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            const double* w = m.mrfOmega;
+            cor[0] = w[1] * Uc[2] - w[2] * Uc[1];
+            cor[1] = w[2] * Uc[0] - w[0] * Uc[2];
+            cor[2] = w[0] * Uc[1] - w[1] * Uc[0];
+        }
         for (int j = 0; j < 3; j++)
         {
-            const double M = MV[j] * iV - (m.fvS ? m.fvS[(size_t)j * nC + c] : 0.0); // UEqn ... - fvSource
+            const double M = MV[j] * iV + cor[j] - (m.fvS ? m.fvS[(size_t)j * nC + c] : 0.0); // UEqn ... + MRF.DDt(U) - fvSource
             r.HbyA[(size_t)j * nT + c] = Uc[j] - rAU * M; // HbyA = rAU*H = U - rAU*(UEqn & U)
             R[3 * c + j] = (M + r.gP[(size_t)j * nT + c]) * cU;
         }
@@ -338,6 +350,7 @@ DAB_HD double faceF(const MeshView& m, const StateView& s, const RecordView& r, 
     }
     const double gam = w * r.rAU[o] + (1.0 - w) * r.rAU[n];
     const double sn = m.delta[f] * (s.p[n] - s.p[o]) + cg;
+    if (m.mrfFlux) ph -= m.mrfFlux[f]; // MRF.makeRelative(phiHbyA)
     return ph - gam * mS * sn;
 }
 
@@ -379,11 +392,14 @@ struct FwdC
                     const double im = 1.0 / mS;
                     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                     BCv bu;
-                    bcVector(kU, q.bcVal[F_U][pa], Uc, phib, dl, nh, bu);
+                    double uw[3];
+                    mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+                    bcVector(kU, uw, Uc, phib, dl, nh, bu);
                     ph = m.Sx[f] * bu.val[0] + m.Sy[f] * bu.val[1] + m.Sz[f] * bu.val[2];
                 }
                 else
                     ph = m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c];
+                ph = mrfBoundaryFlux(m, f, ph, 1.0);
                 double pv, sn, fr_;
                 bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, sn, fr_);
                 F = ph - r.rAU[c] * mS * sn;

@@ -120,7 +120,9 @@ struct UEqnAssemble
                 const double im = 1.0 / mS;
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 BCv bu;
-                bcVector(q.bcKind[F_U][pa], q.bcVal[F_U][pa], Uc, mf, dl, nh, bu);
+                double uw[3];
+                mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+                bcVector(q.bcKind[F_U][pa], uw, Uc, mf, dl, nh, bu);
                 double ntb = 0.0, sngN = 0.0, frN;
                 const double ntc = q.turb ? s.nt[c] : 0.0;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
@@ -164,10 +166,18 @@ struct UEqnAssemble
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
         const double Dn = D2 / q.alphaU - icMin;
         r.rAU[c] = V / (Dn + icAvg);
+        double cor[3] = {0.0, 0.0, 0.0}; // MRF.DDt(U), explicit
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            const double* w = m.mrfOmega;
+            cor[0] = w[1] * Uc[2] - w[2] * Uc[1];
+            cor[1] = w[2] * Uc[0] - w[0] * Uc[2];
+            cor[2] = w[0] * Uc[1] - w[1] * Uc[0];
+        }
         for (int j = 0; j < 3; j++)
         {
             e.diag[(size_t)j * nC + c] = Dn + icS[j];
-            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j] + (m.fvS ? V * m.fvS[(size_t)j * nC + c] : 0.0);
+            e.b[(size_t)j * nC + c] = -X[j] + (Dn - D0) * Uc[j] + (m.fvS ? V * m.fvS[(size_t)j * nC + c] : 0.0) - V * cor[j];
         }
     }
 };
@@ -317,10 +327,12 @@ DAB_HD double phiHbyABoundary(const MeshView& m, const Params& q, const StateVie
         const double im = 1.0 / m.magSf[f];
         const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
         BCv bu;
-        bcVector(kU, q.bcVal[F_U][pa], Uc, s.phi[f], m.delta[f], nh, bu);
-        return m.Sx[f] * bu.val[0] + m.Sy[f] * bu.val[1] + m.Sz[f] * bu.val[2];
+        double uw[3];
+        mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+        bcVector(kU, uw, Uc, s.phi[f], m.delta[f], nh, bu);
+        return mrfBoundaryFlux(m, f, m.Sx[f] * bu.val[0] + m.Sy[f] * bu.val[1] + m.Sz[f] * bu.val[2], 1.0);
     }
-    return m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c];
+    return mrfBoundaryFlux(m, f, m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c], 1.0);
 }
 
 // pressure equation laplacian(rAU, p) == div(phiHbyA), assembled with the sign flipped (symmetric positive definite):
@@ -362,6 +374,7 @@ struct PEqnAssemble
                     ph += Sv[j] * (w * r.HbyA[(size_t)j * nT + o] + (1.0 - w) * r.HbyA[(size_t)j * nT + n]);
                     cg += kv[j] * (w * r.gP[(size_t)j * nT + o] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
                 }
+                if (m.mrfFlux) ph -= m.mrfFlux[f];
                 double gam = (w * r.rAU[o] + (1.0 - w) * r.rAU[n]) * mS;
                 if (sc.rAt)
                 {

@@ -170,7 +170,9 @@ struct RevA
                 const double Fb = cphi * x.phi[f] - psiPc;
                 const int kU = q.bcKind[F_U][pa];
                 const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
-                if (q.constrainHbyA && !assignable)
+                if (m.mrfType && m.mrfType[b] == 1)
+                    ; // rotating wall of the MRF zone: the relative phiHbyA is identically zero
+                else if (q.constrainHbyA && !assignable)
                 {
                     const double im = 1.0 / mS;
                     const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
@@ -193,16 +195,26 @@ struct RevA
         const double cU = q.nrU ? 1.0 : V;
         const double D0 = r.D0[c];
         double rAUtot = rAUb;
+        double Mbv[3];
         for (int j = 0; j < 3; j++)
         {
             const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) / rAU;
             const double psiU = cU * x.U[3 * c + j];
             const double Mb = psiU - rAU * HbA[j];
+            Mbv[j] = Mb;
             rAUtot -= M * HbA[j];
             const double mt = Mb / V;
             a.mt[(size_t)j * nT + c] = mt;
             a.Udir[(size_t)j * nC + c] = Ub[j] + HbA[j] + D0 * mt;
             a.gPb[(size_t)j * nT + c] = gPb[j] + psiU;
+        }
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            // adjoint of the Coriolis term M += Omega x U: Ub += Mb x Omega
+            const double* w = m.mrfOmega;
+            a.Udir[c] += Mbv[1] * w[2] - Mbv[2] * w[1];
+            a.Udir[(size_t)nC + c] += Mbv[2] * w[0] - Mbv[0] * w[2];
+            a.Udir[(size_t)2 * nC + c] += Mbv[0] * w[1] - Mbv[1] * w[0];
         }
         a.Dn[c] = -rAU * rAU * rAUtot / V;
         a.pdir[c] = pb;
@@ -416,7 +428,9 @@ struct RevB
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 const int kU = q.bcKind[F_U][pa];
                 BCv bu;
-                bcVector(kU, q.bcVal[F_U][pa], Uc, mf, dl, nh, bu);
+                double uw[3];
+                mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+                bcVector(kU, uw, Uc, mf, dl, nh, bu);
                 double ntb = 0.0, sngN = 0.0, frN = 0.0;
                 if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
                 double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
@@ -627,7 +641,9 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
     for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
     const int kU = q.bcKind[F_U][pa];
     BCv bu;
-    bcVector(kU, q.bcVal[F_U][pa], Uc, phib, dl, nh, bu);
+    double uw[3];
+    mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
+    bcVector(kU, uw, Uc, phib, dl, nh, bu);
     double pv, snp, frp;
     bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, snp, frp);
     if (fs.mode >= 2)

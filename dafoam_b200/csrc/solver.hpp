@@ -172,6 +172,20 @@ struct Solver
     struct FvSourceParDef { std::string name, disk; std::vector<int> indices; };
     std::vector<FvSourceParDef> fvSourcePars;
     DevBuf<double> dFvS;
+    // MRF zone (constant/MRFProperties + constant/polyMesh/cellZones; reference src/adjoint/DAMisc/MRFDF)
+    struct MrfZone
+    {
+        bool on = false;
+        std::string zone;
+        double omega[3] = {0, 0, 0}, origin[3] = {0, 0, 0};
+        std::vector<unsigned char> cell, type, faceIn; // [nCtot], [nBF], [nF]
+    } mrf;
+    DevBuf<unsigned char> dMrfCell, dMrfType, dMrfFaceIn;
+    DevBuf<double> dMrfFlux;
+    void updateMrfFlux()
+    {
+        if (mrf.on) be.launch(hm.nF, MrfFluxK{mv, dMrfFaceIn.p, dMrfFlux.p});
+    }
 
     // device mesh
     DevBuf<int32_t> dOwn, dNei, dCellFaces, dCellNbr, dBPatch;
@@ -227,8 +241,8 @@ struct Solver
             auto t = tokenize(argsAll);
             solverName = t.empty() ? "DASimpleFoam" : t[0];
         }
-        if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam")
-            throw Error("solver " + solverName + " is not supported (DASimpleFoam; DARhoSimpleFoam: forward residual only)");
+        if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam" && solverName != "DATurboFoam")
+            throw Error("solver " + solverName + " is not supported (DASimpleFoam, DARhoSimpleFoam, DATurboFoam)");
         be.init(device);
         if (nRanks == 1)
         {
@@ -252,6 +266,12 @@ struct Solver
         }
         if ((int)hm.patches.size() > MAXP) throw Error("too many patches");
         readCase(caseDir);
+        readMrf(caseDir);
+        if (mrf.on)
+            for (int b = 0; b < hm.nBF; b++)
+                if (mrf.type[b] == 1 && par.bcKind[F_U][hm.bPatch[b]] != BC_FIXED_VALUE)
+                    throw Error("MRF: patch " + hm.patches[hm.bPatch[b]].name
+                                + " rotates with the zone and needs a fixedValue U (list it in nonRotatingPatches otherwise)");
         applyOptions(optionsJson, true);
         upload();
         initialStates(caseDir);
@@ -272,10 +292,78 @@ struct Solver
 
     std::map<std::string, Dict> fieldDicts;
 
+    // one active zone of constant/MRFProperties; the face classification is MRFZoneDF::setMRFFaces (MRFZoneDF.C)
+    void readMrf(const std::string& caseDir)
+    {
+        mrf = MrfZone();
+        if (!fileExists(caseDir + "/constant/MRFProperties")) return;
+        Dict d = readDict(caseDir + "/constant/MRFProperties");
+        const Dict* z = nullptr;
+        for (const auto& kv : d.subs)
+        {
+            if (kv.first == "FoamFile") continue;
+            const std::string act = kv.second.wordOr("active", "true");
+            if (act == "false" || act == "no" || act == "off") continue;
+            if (z) throw Error("MRFProperties: more than one active zone is not supported");
+            z = &kv.second;
+        }
+        if (!z) return;
+        mrf.on = true;
+        mrf.zone = z->word("cellZone");
+        double ax[3] = {0, 0, 1};
+        z->uniform("axis", ax);
+        z->uniform("origin", mrf.origin);
+        const double om = z->scalarOr("omega", 0.0), an = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        for (int k = 0; k < 3; k++) mrf.omega[k] = om * ax[k] / an;
+        std::vector<std::string> nonRot;
+        if (z->has("nonRotatingPatches"))
+            for (const auto& t : z->tokens("nonRotatingPatches"))
+                if (t != "(" && t != ")") nonRot.push_back(t);
+        // the zone's cells (global labels)
+        const std::string czPath = caseDir + "/constant/polyMesh/cellZones";
+        if (!fileExists(czPath)) throw Error("cannot find MRF cellZone " + mrf.zone + " (no constant/polyMesh/cellZones)");
+        const std::string txt = readFile(czPath);
+        if (txt.find("format") != std::string::npos && txt.find("binary") != std::string::npos && txt.find("binary") < txt.find("}"))
+            throw Error("cellZones: binary format is not supported");
+        const std::vector<std::string> t = tokenize(txt);
+        std::vector<unsigned char> gmask((size_t)part.nGlobalCells, 0);
+        bool found = false;
+        for (size_t i = 0; i + 1 < t.size() && !found; i++)
+        {
+            if (t[i] != mrf.zone || t[i + 1] != "{") continue;
+            size_t j = i + 2;
+            while (j < t.size() && t[j] != "cellLabels") j++;
+            while (j < t.size() && t[j] != "(") j++;
+            for (j++; j < t.size() && t[j] != ")"; j++)
+            {
+                const long c = atol(t[j].c_str());
+                if (c < 0 || c >= (long)gmask.size()) throw Error("cellZones: cell label out of range");
+                gmask[c] = 1;
+            }
+            found = true;
+        }
+        if (!found) throw Error("cannot find MRF cellZone " + mrf.zone);
+        const int nT = hm.nCtot, nIF = hm.nIF;
+        mrf.cell.assign(nT, 0);
+        for (int c = 0; c < nT; c++) mrf.cell[c] = gmask[nRanks > 1 ? (size_t)part.cellGlobal[c] : (size_t)c];
+        mrf.type.assign(hm.nBF, 0);
+        mrf.faceIn.assign(hm.nF, 0);
+        for (int f = 0; f < nIF; f++)
+            if (mrf.cell[hm.own[f]] || mrf.cell[hm.nei[f]]) mrf.faceIn[f] = 1;
+        for (int b = 0; b < hm.nBF; b++)
+        {
+            if (!mrf.cell[hm.own[nIF + b]]) continue;
+            const std::string& pn = hm.patches[hm.bPatch[b]].name;
+            const bool excluded = std::find(nonRot.begin(), nonRot.end(), pn) != nonRot.end();
+            mrf.type[b] = excluded ? 2 : 1;
+            if (excluded) mrf.faceIn[nIF + b] = 1;
+        }
+    }
+
     void readCase(const std::string& caseDir)
     {
         memset(&par, 0, sizeof(par));
-        par.comp = solverName == "DARhoSimpleFoam" ? 1 : 0;
+        par.comp = solverName == "DASimpleFoam" ? 0 : 1;
         if (!par.comp)
         {
             Dict tp = readDict(caseDir + "/constant/transportProperties");
@@ -293,6 +381,9 @@ struct Solver
             if (en != "sensibleInternalEnergy" && en != "sensibleEnthalpy") throw Error("thermophysicalProperties: unsupported energy " + en);
             if (trn != "const" && trn != "sutherland") throw Error("thermophysicalProperties: unsupported transport " + trn);
             par.heIsE = en == "sensibleInternalEnergy" ? 1 : 0;
+            if (solverName == "DATurboFoam" && !par.heIsE)
+                throw Error("DATurboFoam: the sensibleEnthalpy energy equation (viscous-work and p(U - URel) terms, "
+                            "DAResidualTurboFoam.C:119-121) is not built; use sensibleInternalEnergy");
             par.sutherland = trn == "sutherland" ? 1 : 0;
             const Dict& mx = th.sub("mixture");
             par.Rg = 8314.4700665 / mx.sub("specie").scalar("molWeight");
@@ -695,6 +786,21 @@ struct Solver
         mv.kx = dK[0].p; mv.ky = dK[1].p; mv.kz = dK[2].p; mv.Cfx = dCf[0].p; mv.Cfy = dCf[1].p; mv.Cfz = dCf[2].p;
         mv.Cx = dC[0].p; mv.Cy = dC[1].p; mv.Cz = dC[2].p; mv.V = dV.p; mv.yWall = dY.p;
         mv.fvS = nullptr;
+        mv.mrfCell = nullptr; mv.mrfType = nullptr; mv.mrfFlux = nullptr;
+        if (mrf.on)
+        {
+            dMrfCell.upload(be, mrf.cell);
+            dMrfType.upload(be, mrf.type);
+            dMrfFaceIn.upload(be, mrf.faceIn);
+            dMrfFlux.alloc(be, hm.nF);
+            for (int k = 0; k < 3; k++)
+            {
+                mv.mrfOmega[k] = mrf.omega[k];
+                mv.mrfOrigin[k] = mrf.origin[k];
+            }
+            mv.mrfCell = dMrfCell.p; mv.mrfType = dMrfType.p; mv.mrfFlux = dMrfFlux.p;
+            updateMrfFlux();
+        }
         fvSourceDirty = fvSpec.nDisk > 0;
         const size_t nT = hm.nCtot, nC = hm.nC, nF = hm.nF, nd = nDof();
         dWext.alloc(be, nd);

@@ -21,6 +21,7 @@ inline void Solver::uploadGeometry()
     put(dW, hm.w);
     put(dDelta, hm.delta);
     put(dV, hm.V);
+    updateMrfFlux();
     recorded = false;
     kry.pcValid = false;
 }
@@ -182,6 +183,7 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
         be.launch(nC, GeomCellK{gv});
         be.launch(hm.nF, GeomDerivedK{gv});
         if (fvSpec.nDisk > 0) be.launch(nC, FvSourceK{fvSpec, mv.Cx, mv.Cy, mv.Cz, nC, dFvS.p}); // the source follows the cell centres
+        updateMrfFlux();                                                                           // and the relative fluxes the faces
     };
     if (psi) be.h2d(dX.p, psi, (size_t)nDof() * sizeof(double));
     be.d2d(Vc.dPts.p, Vc.dPts0.p, (size_t)3 * nP * sizeof(double));

@@ -29,6 +29,57 @@ struct MeshView
     const double *Sx, *Sy, *Sz, *magSf, *w, *delta, *kx, *ky, *kz, *Cfx, *Cfy, *Cfz; // [nF]
     const double *Cx, *Cy, *Cz, *V, *yWall;                                          // [nCtot]
     const double* fvS; // [3][nC] momentum source per unit volume (fvSource: actuator disks) or null
+    // MRF zone (reference src/adjoint/DAMisc/MRFDF/MRFZoneDF.C) or null pointers: cell mask, boundary-face type
+    // (MRFZoneDF::setMRFFaces: 1 included = rotating wall, 2 excluded), (Omega x (Cf - origin)) . Sf of the zone faces
+    const unsigned char* mrfCell; // [nCtot]
+    const unsigned char* mrfType; // [nBF]
+    const double* mrfFlux;        // [nF], zero outside the zone
+    double mrfOmega[3], mrfOrigin[3];
+};
+
+// reference value of the velocity boundary condition on boundary face f of patch value `patchVal`: the patch's own value, or the
+// wall velocity Omega x (Cf - origin) on a rotating wall of the MRF zone (MRFZoneDF::correctBoundaryVelocity)
+DAB_HD void mrfWallRef(const MeshView& m, int f, const double* patchVal, double* ref)
+{
+    ref[0] = patchVal[0];
+    ref[1] = patchVal[1];
+    ref[2] = patchVal[2];
+    if (m.mrfType && m.mrfType[f - m.nIF] == 1)
+    {
+        const double r[3] = {m.Cfx[f] - m.mrfOrigin[0], m.Cfy[f] - m.mrfOrigin[1], m.Cfz[f] - m.mrfOrigin[2]};
+        const double* w = m.mrfOmega;
+        ref[0] = w[1] * r[2] - w[2] * r[1];
+        ref[1] = w[2] * r[0] - w[0] * r[2];
+        ref[2] = w[0] * r[1] - w[1] * r[0];
+    }
+}
+
+// relative boundary flux (MRFZoneDF::makeRelativeRhoFlux): zero on a rotating wall, minus rho_b (Omega x r).Sf on an excluded face
+DAB_HD double mrfBoundaryFlux(const MeshView& m, int f, double ph, double rhob)
+{
+    if (!m.mrfType) return ph;
+    const int ty = m.mrfType[f - m.nIF];
+    return ty == 1 ? 0.0 : (ty == 2 ? ph - rhob * m.mrfFlux[f] : ph);
+}
+
+// mrfFlux[f] = (Omega x (Cf - origin)) . Sf on the faces flagged in faceIn (internal faces touching the zone, excluded boundary
+// faces of zone cells), zero elsewhere; recomputed whenever the geometry changes
+struct MrfFluxK
+{
+    MeshView m;
+    const unsigned char* faceIn;
+    double* out;
+    DAB_HD void operator()(int f) const
+    {
+        double v = 0.0;
+        if (faceIn[f])
+        {
+            const double r[3] = {m.Cfx[f] - m.mrfOrigin[0], m.Cfy[f] - m.mrfOrigin[1], m.Cfz[f] - m.mrfOrigin[2]};
+            const double* w = m.mrfOmega;
+            v = (w[1] * r[2] - w[2] * r[1]) * m.Sx[f] + (w[2] * r[0] - w[0] * r[2]) * m.Sy[f] + (w[0] * r[1] - w[1] * r[0]) * m.Sz[f];
+        }
+        out[f] = v;
+    }
 };
 
 // DAFvSourceActuatorDisk, source = cylinderAnnulusSmooth (reference src/adjoint/DAFvSource/DAFvSourceActuatorDisk.C:205-407):

@@ -605,8 +605,52 @@ struct Case
         std::vector<int> kindT;     // [nPatch]
         std::vector<double> valueT; // [nPatch]
     } comp;
+    // MRF zone (reference src/adjoint/DAMisc/MRFDF/MRFZoneDF.C): one rotating cellZone
+    struct Mrf
+    {
+        int on = 0;
+        double omega[3] = {0, 0, 0}, origin[3] = {0, 0, 0}; // Omega = omega*axis [rad/s]
+        std::vector<unsigned char> cell;     // [nC] in the zone
+        std::vector<unsigned char> faceType; // [nF] MRFZoneDF::setMRFFaces: 1 internal-or-included, 2 excluded boundary face
+    } mrf;
     int nDof() const { return ((par.turb ? 5 : 4) + (comp.on ? 1 : 0)) * t.nC + t.nF; }
 };
+
+// Omega x (x - origin)
+template <class T>
+V3<T> mrfVelocity(const Case& cs, const V3<T>& x)
+{
+    const double* w = cs.mrf.omega;
+    const double* o = cs.mrf.origin;
+    T r0 = x[0] - o[0], r1 = x[1] - o[1], r2 = x[2] - o[2];
+    V3<T> v;
+    v[0] = w[1] * r2 - w[2] * r1;
+    v[1] = w[2] * r0 - w[0] * r2;
+    v[2] = w[0] * r1 - w[1] * r0;
+    return v;
+}
+
+// (Omega x (Cf - origin)) . Sf of one face (MRFZoneDF::makeRelativeRhoFlux, MRFZoneTemplatesDF.C:34-95)
+template <class T>
+T mrfFaceFlux(const Case& cs, const Geom<T>& g, int f)
+{
+    V3<T> v = mrfVelocity(cs, g.Cf[f]);
+    return v[0] * g.Sf[f][0] + v[1] * g.Sf[f][1] + v[2] * g.Sf[f][2];
+}
+
+// MRFZoneDF::correctBoundaryVelocity (MRFZoneDF.C: included faces get U_b = Omega x (Cf - origin), forced like a fixed value)
+template <class T>
+void mrfWallVelocity(const Case& cs, const Geom<T>& g, const std::vector<T>& U, BF<T>& bU)
+{
+    const Topo& t = cs.t;
+    for (int b = 0; b < t.nBF; b++)
+    {
+        const int f = t.nIF + b, c = t.own[f];
+        if (cs.mrf.faceType[f] != 1) continue;
+        V3<T> v = mrfVelocity(cs, g.Cf[f]);
+        for (int k = 0; k < 3; k++) mixedCoeffs(bU, k, b, 1.0, v[k], U[(size_t)k * t.nC + c], g.delta[f]);
+    }
+}
 
 template <class T>
 struct Work
@@ -707,6 +751,7 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
     // --- boundary conditions and intermediate variables (DASolver::updateStateBoundaryConditions)
     BF<T> bU, bP, bNt, bNut;
     evalBC(t, g, cs.bc, bcv, F_U, 3, U, phi, bU);
+    if (cs.mrf.on) mrfWallVelocity(cs, g, U, bU);
     evalBC(t, g, cs.bc, bcv, F_P, 1, p, phi, bP);
     std::vector<T> nut(nC, T(0.0));
     if (turb)
@@ -830,6 +875,19 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
         for (int k = 0; k < 3; k++)
             for (int c = 0; c < nC; c++) UEqn.src[(size_t)k * nC + c] += g.V[c] * S[(size_t)k * nC + c];
     }
+    if (cs.mrf.on)
+    {
+        // + MRF.DDt(U): the Coriolis acceleration Omega x U of the zone cells, explicit (fvMatrix + field: source -= V*field)
+        const double* w = cs.mrf.omega;
+        for (int c = 0; c < nC; c++)
+        {
+            if (!cs.mrf.cell[c]) continue;
+            const T &u0 = U[c], &u1 = U[(size_t)nC + c], &u2 = U[(size_t)2 * nC + c];
+            UEqn.src[c] -= g.V[c] * (w[1] * u2 - w[2] * u1);
+            UEqn.src[(size_t)nC + c] -= g.V[c] * (w[2] * u0 - w[0] * u2);
+            UEqn.src[(size_t)2 * nC + c] -= g.V[c] * (w[0] * u1 - w[1] * u0);
+        }
+    }
     relax(UEqn, t, par.alphaU, U);
 
     // --- URes = (UEqn & U) + grad(p)
@@ -873,6 +931,17 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
             s += g.Sf[f][k] * hb;
         }
         phiHbyA[f] = s;
+    }
+    if (cs.mrf.on)
+    {
+        // MRF.makeRelative(phiHbyA)
+        for (int f = 0; f < nF; f++)
+        {
+            const int ty = cs.mrf.faceType[f];
+            if (ty == 0) continue;
+            if (f >= nIF && ty == 1) phiHbyA[f] = T(0.0);
+            else phiHbyA[f] -= mrfFaceFlux(cs, g, f);
+        }
     }
 
     // --- pEqn: laplacian(rAU, p) == div(phiHbyA)
@@ -1022,6 +1091,7 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
     // --- boundary conditions of the states
     BF<T> bU, bP, bT, bNt, bNut;
     evalBC(t, g, cs.bc, bcv, F_U, 3, U, phi, bU);
+    if (cs.mrf.on) mrfWallVelocity(cs, g, U, bU);
     evalBC(t, g, cs.bc, bcv, F_P, 1, p, phi, bP);
     BCSpec bcT;
     bcT.kind.assign((size_t)N_FIELDS * t.nPatch, BC_ZERO_GRADIENT);
@@ -1192,6 +1262,19 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
         for (int k = 0; k < 3; k++)
             for (int c = 0; c < nC; c++) UEqn.src[(size_t)k * nC + c] += g.V[c] * fvS[(size_t)k * nC + c];
     }
+    if (cs.mrf.on)
+    {
+        // + MRF.DDt(rho, U) = rho * (Omega x U) in the zone cells
+        const double* w = cs.mrf.omega;
+        for (int c = 0; c < nC; c++)
+        {
+            if (!cs.mrf.cell[c]) continue;
+            const T &u0 = U[c], &u1 = U[(size_t)nC + c], &u2 = U[(size_t)2 * nC + c];
+            UEqn.src[c] -= g.V[c] * rho[c] * (w[1] * u2 - w[2] * u1);
+            UEqn.src[(size_t)nC + c] -= g.V[c] * rho[c] * (w[2] * u0 - w[0] * u2);
+            UEqn.src[(size_t)2 * nC + c] -= g.V[c] * rho[c] * (w[0] * u1 - w[1] * u0);
+        }
+    }
     relax(UEqn, t, par.alphaU, U);
     std::vector<T> URes;
     matResidual(UEqn, t, g, U, URes);
@@ -1282,6 +1365,22 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
             s += g.Sf[f][k] * hb;
         }
         phiHbyA[f] = rhoB[b] * s;
+    }
+    if (cs.mrf.on)
+    {
+        // MRF.makeRelative(fvc::interpolate(rho), phiHbyA)
+        for (int f = 0; f < nF; f++)
+        {
+            const int ty = cs.mrf.faceType[f];
+            if (ty == 0) continue;
+            if (f >= nIF)
+            {
+                if (ty == 1) phiHbyA[f] = T(0.0);
+                else phiHbyA[f] -= rhoB[f - nIF] * mrfFaceFlux(cs, g, f);
+            }
+            else
+                phiHbyA[f] -= (g.w[f] * rho[t.own[f]] + (1.0 - g.w[f]) * rho[t.nei[f]]) * mrfFaceFlux(cs, g, f);
+        }
     }
     // --- pEqn = div(phiHbyA) - laplacian(rhorAUf, p)
     Mat<T> pEqn;
@@ -1527,6 +1626,32 @@ void orc_set_fvsource(void* h, int nDisk, const double* pars)
 {
     Case* cs = (Case*)h;
     cs->disks.assign(pars, pars + (size_t)15 * nDisk);
+    cs->recorded = false;
+}
+
+// MRF zone: Omega = omega*axis [rad/s], origin, cell mask [nC], mask of the nonRotatingPatches [nPatch]; the face types follow
+// MRFZoneDF::setMRFFaces (reference MRFZoneDF.C)
+void orc_set_mrf(void* h, const double* omega, const double* origin, const int* cellMask, const int* excludedPatch)
+{
+    Case* cs = (Case*)h;
+    const Topo& t = cs->t;
+    Case::Mrf& m = cs->mrf;
+    m.on = 1;
+    for (int k = 0; k < 3; k++)
+    {
+        m.omega[k] = omega[k];
+        m.origin[k] = origin[k];
+    }
+    m.cell.assign(t.nC, 0);
+    for (int c = 0; c < t.nC; c++) m.cell[c] = cellMask[c] ? 1 : 0;
+    m.faceType.assign(t.nF, 0);
+    for (int f = 0; f < t.nIF; f++)
+        if (m.cell[t.own[f]] || m.cell[t.nei[f]]) m.faceType[f] = 1;
+    for (int b = 0; b < t.nBF; b++)
+    {
+        const int f = t.nIF + b;
+        if (m.cell[t.own[f]]) m.faceType[f] = excludedPatch[t.bPatch[b]] ? 2 : 1;
+    }
     cs->recorded = false;
 }
 

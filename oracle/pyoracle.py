@@ -189,6 +189,16 @@ class Oracle:
         self._keep_disks = a
         lib().orc_set_fvsource(self.h, C.c_int(len(rows)), _p(a))
 
+    def set_mrf(self, mesh, mrf):
+        """One MRF zone (see dafoam_b200.cases.write_mrf for the dict)."""
+        axis = np.asarray(mrf["axis"], dtype=np.float64)
+        omega = np.ascontiguousarray(mrf["omega"] * axis / np.linalg.norm(axis))
+        origin = np.ascontiguousarray(mrf["origin"], dtype=np.float64)
+        mask = np.zeros(mesh.n_cells, dtype=np.int32)
+        mask[np.asarray(mrf["cells"], dtype=np.int64)] = 1
+        excl = np.ascontiguousarray([1 if p["name"] in mrf.get("nonRotatingPatches", []) else 0 for p in mesh.patches], dtype=np.int32)
+        lib().orc_set_mrf(self.h, _p(omega), _p(origin), mask.ctypes.data_as(C.POINTER(C.c_int)), excl.ctypes.data_as(C.POINTER(C.c_int)))
+
     def jtvec_bc(self, W, psi, field, patch):
         """[dR/d(boundary reference value of `field` on `patch`)]^T psi (3 numbers; scalars use the first)."""
         W = np.ascontiguousarray(W, dtype=np.float64)

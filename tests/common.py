@@ -151,3 +151,21 @@ def check_functions(lib_path, tol=1e-12):
     sol.calcJacTVecProduct("patchV", "patchVelocity", x, "CMZ", "function", one, dFdx)
     assert np.all(dFdx == 0.0)
     return True
+
+
+def mrf_zone(mesh, wall="wing", omega=40.0, axis=(0.0, 0.1, 1.0)):
+    """A rotating cellZone for the MRF tests: the cells within a radius of the aerofoil (centres estimated from the quad-face
+    means); every patch but the wall itself is a nonRotatingPatch."""
+    Sf, Cf = cases.quad_face_geometry(mesh)
+    nC = mesh.n_cells
+    cc, cnt = np.zeros((nC, 3)), np.zeros(nC)
+    np.add.at(cc, mesh.owner, Cf)
+    np.add.at(cnt, mesh.owner, 1.0)
+    np.add.at(cc, mesh.neighbour, Cf[:mesh.n_internal_faces])
+    np.add.at(cnt, mesh.neighbour, 1.0)
+    cc /= cnt[:, None]
+    origin = np.array([0.3, 0.02, 0.0])
+    r = np.linalg.norm((cc - origin)[:, :2], axis=1)
+    cells = np.nonzero(r < 0.45 * r.max())[0]
+    return dict(cellZone="rotor", cells=cells, origin=origin.tolist(), axis=list(axis), omega=omega,
+                nonRotatingPatches=[p["name"] for p in mesh.patches if p["name"] != wall])

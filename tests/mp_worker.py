@@ -40,6 +40,8 @@ def main():
     comp_primal = kind == "channelcompprimal"
     if primal_mode:
         kind = "channel"
+    if kind == "nacamrf":
+        kind = "naca"  # the same checks on a case with an MRF zone (constant/MRFProperties, cellZones): the zone is cut by the partition
     comp = kind == "nacacomp" or comp_primal
     mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2) if kind in ("naca", "nacacomp") else cases.channel(nx=12, ny=8, nz=2)
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing" if kind in ("naca", "nacacomp") else "walls"],

@@ -33,11 +33,15 @@ def test_two_gpus_match_one_gpu_nccl(kind, port):
     _run(kind, ["cuda"], port)
 
 
-@pytest.mark.parametrize("kind", ["naca", "channel", "nacacomp", "channelprimal", "channelcompprimal"])
+@pytest.mark.parametrize("kind", ["naca", "channel", "nacacomp", "channelprimal", "channelcompprimal", "nacamrf"])
 def test_two_ranks_match_one_rank(kind):
     d = tempfile.mkdtemp(prefix="dab_mp_")
     if kind == "naca":
         cases.write_case(d, cases.naca0012_ogrid(ni=32, nj=16, nk=2), cases.default_bcs_naca())
+    elif kind == "nacamrf":
+        from tests.common import mrf_zone
+        mesh = cases.naca0012_ogrid(ni=32, nj=16, nk=2)
+        cases.write_case(d, mesh, cases.default_bcs_naca(), mrf=mrf_zone(mesh, omega=2.0))
     elif kind == "nacacomp":
         cases.write_case(d, cases.naca0012_ogrid(ni=32, nj=16, nk=2), cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0))),
                          thermo=cases.default_thermo())
@@ -47,7 +51,7 @@ def test_two_ranks_match_one_rank(kind):
     else:
         cases.write_case(d, cases.channel(nx=12, ny=8, nz=2), cases.default_bcs_channel())
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", {"naca": "29731", "channel": "29733", "nacacomp": "29737", "channelprimal": "29739", "channelcompprimal": "29743"}[kind], os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
+           "--master-port", {"naca": "29731", "channel": "29733", "nacacomp": "29737", "channelprimal": "29739", "channelcompprimal": "29743", "nacamrf": "29745"}[kind], os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
