@@ -616,11 +616,11 @@ thermoType
 mixture
 {
     specie { molWeight %.17g; }
-    thermodynamics { Cp %.17g; Hf 0; }
+    thermodynamics { Cp %.17g; Hf 0; gamma %.17g; }
     transport { mu %.17g; Pr %.17g; As %.17g; Ts %.17g; }
 }
 Prt %.17g;
-""" % (tr, thermo["energy"], thermo["molWeight"], thermo["Cp"], thermo["mu"], thermo["Pr"], thermo["As"], thermo["Ts"], thermo["Prt"]))
+""" % (tr, thermo["energy"], thermo["molWeight"], thermo["Cp"], thermo.get("gamma", 1.4), thermo["mu"], thermo["Pr"], thermo["As"], thermo["Ts"], thermo["Prt"]))
     # compressible convection schemes next to the incompressible ones
     path = os.path.join(case_dir, "system", "fvSchemes")
     txt = open(path).read()

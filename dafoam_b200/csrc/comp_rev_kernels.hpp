@@ -742,13 +742,34 @@ DAB_HD double cForceFace(const MeshView& m, const Params& q, const StateView& s,
         const double U2 = bp.bu.val[0] * bp.bu.val[0] + bp.bu.val[1] * bp.bu.val[1] + bp.bu.val[2] * bp.bu.val[2];
         const double wA = mS / fs.areaSum;
         const double SU = Sv[0] * bp.bu.val[0] + Sv[1] * bp.bu.val[1] + Sv[2] * bp.bu.val[2];
-        const double F = fs.scale * (fs.mode == 2 ? (bp.p + 0.5 * bp.th.rho * U2) * wA : bp.th.rho * SU);
+        double F, pTp = 0.0, pTT = 0.0, pTU = 0.0; // mode 4: d(pT)/dp, /dT, /d(|U|^2)
+        if (fs.mode == 4)
+        {
+            // p (1 + (gamma-1)/2 Ma^2)^(gamma/(gamma-1)), Ma^2 = |U|^2/(gamma R T), R = Cp - Cp/gamma (DAFunctionTotalPressureRatio.C:96-125)
+            const double gam = fs.gamma, Rg = q.Cp - q.Cp / gam, ex = gam / (gam - 1.0);
+            const double Ma2 = U2 / (gam * Rg * bp.T);
+            const double base = 1.0 + 0.5 * (gam - 1.0) * Ma2;
+            const double pw = pow(base, ex);
+            const double dMa = bp.p * ex * pw / base * 0.5 * (gam - 1.0); // d(pT)/d(Ma2)
+            F = fs.scale * (bp.p * pw - fs.shift) * wA;
+            pTp = pw;
+            pTU = dMa / (gam * Rg * bp.T);
+            pTT = -dMa * Ma2 / bp.T;
+        }
+        else
+            F = fs.scale * (fs.mode == 2 ? (bp.p + 0.5 * bp.th.rho * U2 - fs.shift) * wA : bp.th.rho * SU);
         if (gUb)
         {
             const double fb = seed * fs.scale;
             BoundaryAdj ba;
             ba.clear();
-            if (fs.mode == 2)
+            if (fs.mode == 4)
+            {
+                ba.p += fb * wA * pTp;
+                ba.T += fb * wA * pTT;
+                for (int j = 0; j < 3; j++) ba.val[j] += fb * wA * pTU * 2.0 * bp.bu.val[j];
+            }
+            else if (fs.mode == 2)
             {
                 ba.p += fb * wA;
                 ba.rho += fb * wA * 0.5 * U2;
@@ -827,7 +848,7 @@ struct cForceFwd
         const int f = m.nIF + b;
         if (!((fs.mask >> m.bPatch[b]) & 1u))
         {
-            out[b] = 0.0;
+            if (!fs.accumulate) out[b] = 0.0;
             return;
         }
         out[b] = cForceFace(m, q, s, r, fs, f, m.own[f], 0.0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);

@@ -621,9 +621,14 @@ struct ForceSpec
     double dir[3]; // force direction, or the moment axis
     double scale;
     int mode;      // 0: force . dir (DAFunctionForce.C:79-153); 1: ((Cf - center) x force) . dir (DAFunctionMoment.C);
-                   // 2: area-averaged total pressure p + 0.5 rho |U|^2 (DAFunctionTotalPressure.C); 3: mass flow rate rho U.Sf (DAFunctionMassFlowRate.C)
+                   // 2: area-averaged total pressure p + 0.5 rho |U|^2 (DAFunctionTotalPressure.C); 3: mass flow rate rho U.Sf (DAFunctionMassFlowRate.C);
+                   // 4 (compressible): area-averaged isentropic total pressure, one side of DAFunctionTotalPressureRatio.C
     double center[3];
-    double areaSum; // mode 2: total area of the function's faces (all ranks)
+    double areaSum;      // modes 2, 4: total area of the function's faces (all ranks)
+    double gamma = 1.4;  // mode 4
+    double shift = 0.0;  // modes 2, 4: subtracted from the face value before the area weighting; with shift = the average itself
+                         // the geometric derivative of the area average needs no derivative of areaSum
+    int accumulate = 0;  // ForceFwd: leave the faces outside the mask untouched (a second face group)
 };
 
 // boundary-face force contribution and (optionally) its adjoint w.r.t. the cell's variables
@@ -651,7 +656,7 @@ DAB_HD double forceFace(const MeshView& m, const Params& q, const StateView& s, 
         // patch reductions of the boundary values (incompressible: rho = 1)
         const double U2 = bu.val[0] * bu.val[0] + bu.val[1] * bu.val[1] + bu.val[2] * bu.val[2];
         const double wA = mS / fs.areaSum;
-        const double F = fs.scale * (fs.mode == 2 ? (pv + 0.5 * U2) * wA : Sv[0] * bu.val[0] + Sv[1] * bu.val[1] + Sv[2] * bu.val[2]);
+        const double F = fs.scale * (fs.mode == 2 ? (pv + 0.5 * U2 - fs.shift) * wA : Sv[0] * bu.val[0] + Sv[1] * bu.val[1] + Sv[2] * bu.val[2]);
         if (gUb)
         {
             const double fb = seed * fs.scale;
@@ -738,7 +743,7 @@ struct ForceFwd
         const int pa = m.bPatch[b];
         if (!((fs.mask >> pa) & 1u))
         {
-            out[b] = 0.0;
+            if (!fs.accumulate) out[b] = 0.0;
             return;
         }
         out[b] = forceFace(m, q, s, r, fs, f, m.own[f], 0.0, nullptr, nullptr, nullptr, nullptr, nullptr);

@@ -126,8 +126,10 @@ struct PatchVarDef
 
 struct FunctionDef
 {
-    std::string name, type;              // type: force | moment
+    std::string name, type;              // type: force | moment | totalPressure | massFlowRate | totalPressureRatio
     std::vector<int> patches;
+    std::vector<int> inletPatches, outletPatches; // totalPressureRatio (DAFunctionTotalPressureRatio.C:33-34)
+    double gamma = 1.4;                  // totalPressureRatio: mixture.thermodynamics.gamma
     std::string dirMode = "fixedDirection"; // fixedDirection | parallelToFlow | normalToFlow (DAFunctionForce.C:37-70)
     std::string patchVelocityInput;      // input whose angle of attack steers the direction
     double dir[3] = {1.0, 0.0, 0.0};     // force direction / moment axis
@@ -388,6 +390,7 @@ struct Solver
             const Dict& mx = th.sub("mixture");
             par.Rg = 8314.4700665 / mx.sub("specie").scalar("molWeight");
             par.Cp = mx.sub("thermodynamics").scalar("Cp");
+            gammaTPR = mx.sub("thermodynamics").scalarOr("gamma", par.Cp / (par.Cp - par.Rg));
             const Dict& tr = mx.sub("transport");
             par.muC = tr.scalarOr("mu", 1.8e-5);
             par.Pr = tr.scalarOr("Pr", 0.7);
@@ -594,6 +597,78 @@ struct Solver
             primal.TMax = vb->numOr("TMax", primal.TMax);
             primal.UMax = vb->numOr("UMax", primal.UMax);
         }
+        if (const JVal* pb = o.get("primalBC"))
+        {
+            // DAField::setPrimalBoundaryConditions (reference DAField.C:698-1260): boundary values, nut wall treatment, MRF speed
+            // and the laminar viscosity from the options, applied before the primal solution
+            for (const auto& kv : pb->obj)
+            {
+                const std::string& key = kv.first;
+                if (key == "useWallFunction")
+                {
+                    const bool wf = kv.second.kind == JVal::Bool ? kv.second.b : kv.second.num != 0.0;
+                    for (size_t p = 0; p < hm.patches.size(); p++)
+                        if (hm.patchGeom[p] == PG_WALL && par.turb) par.bcKind[F_NUT][p] = wf ? BC_NUT_SPALDING : BC_NUT_LOW_RE;
+                    continue;
+                }
+                if (key == "MRF")
+                {
+                    if (!mrf.on) throw Error("primalBC.MRF: the case has no MRF zone");
+                    const double mg = std::sqrt(mrf.omega[0] * mrf.omega[0] + mrf.omega[1] * mrf.omega[1] + mrf.omega[2] * mrf.omega[2]);
+                    if (mg == 0.0) throw Error("primalBC.MRF: omega 0 in MRFProperties leaves the sense of rotation undefined");
+                    for (int k = 0; k < 3; k++)
+                    {
+                        mrf.omega[k] *= kv.second.num / mg;
+                        mv.mrfOmega[k] = mrf.omega[k];
+                    }
+                    if (dMrfFlux.p) updateMrfFlux();
+                    continue;
+                }
+                if (key == "transport:nu")
+                {
+                    if (par.comp) throw Error("primalBC transport:nu: incompressible solvers only");
+                    par.nu = kv.second.num;
+                    continue;
+                }
+                if (key == "thermo:mu")
+                {
+                    if (!par.comp) throw Error("primalBC thermo:mu: compressible solvers only");
+                    par.muC = kv.second.num;
+                    continue;
+                }
+                if (kv.second.kind != JVal::Obj) throw Error("primalBC." + key + " is not supported");
+                const std::string var = kv.second.strOr("variable", "");
+                const JVal* val = kv.second.get("value");
+                const JVal* pl = kv.second.get("patches");
+                if (!val || !pl) throw Error("primalBC." + key + ": patches, variable and value are required");
+                if (val->arr.size() != 1 && val->arr.size() != 3)
+                    throw Error("value should be a list of either 1 (scalar) or 3 (vector) elements");
+                int field = -1;
+                if (var == "U") field = F_U;
+                else if (var == "p") field = F_P;
+                else if (var == "nuTilda") field = F_NUTILDA;
+                else if (var == "nut") field = F_NUT;
+                const bool isT = var == "T";
+                if (field < 0 && !isT) continue; // "<variable> not found, skip it."
+                if ((field == F_U) != (val->arr.size() == 3)) throw Error("primalBC." + key + ": value size does not fit " + var);
+                if ((isT && !par.comp) || (field == F_NUTILDA && !par.turb)) continue;
+                for (const auto& pn : pl->arr)
+                {
+                    int p = -1;
+                    for (size_t q = 0; q < hm.patches.size(); q++)
+                        if (hm.patches[q].name == pn.str) p = (int)q;
+                    if (p < 0) throw Error("primalBC." + key + ": unknown patch " + pn.str);
+                    const int kind = isT ? par.bcKindT[p] : par.bcKind[field][p];
+                    if (kind != BC_FIXED_VALUE && kind != BC_INLET_OUTLET && kind != BC_OUTLET_INLET)
+                        throw Error("only support fixedValues, inletOutlet, outletInlet");
+                    if (isT) par.bcValT[p] = val->arr[0].num;
+                    else
+                        for (size_t k = 0; k < val->arr.size(); k++) par.bcVal[field][p][k] = val->arr[k].num;
+                }
+            }
+            recorded = false;
+            kry.pcValid = false;
+        }
         if (const JVal* fd = o.get("function"))
         {
             functions.clear();
@@ -602,17 +677,33 @@ struct Solver
                 FunctionDef f;
                 f.name = kv.first;
                 f.type = kv.second.strOr("type", "force");
-                if (f.type != "force" && f.type != "moment" && f.type != "totalPressure" && f.type != "massFlowRate")
-                    throw Error("function type " + f.type + " is not supported (force, moment, totalPressure, massFlowRate)");
-                if (const JVal* pl = kv.second.get("patches"))
-                    for (const auto& pn : pl->arr)
-                    {
-                        int found = -1;
-                        for (size_t p = 0; p < hm.patches.size(); p++)
-                            if (hm.patches[p].name == pn.str) found = (int)p;
-                        if (found < 0) throw Error("function " + f.name + ": unknown patch " + pn.str);
-                        f.patches.push_back(found);
-                    }
+                if (f.type != "force" && f.type != "moment" && f.type != "totalPressure" && f.type != "massFlowRate"
+                    && f.type != "totalPressureRatio")
+                    throw Error("function type " + f.type + " is not supported (force, moment, totalPressure, massFlowRate, totalPressureRatio)");
+                auto patchList = [&](const char* key, std::vector<int>& out) {
+                    if (const JVal* pl = kv.second.get(key))
+                        for (const auto& pn : pl->arr)
+                        {
+                            int found = -1;
+                            for (size_t p = 0; p < hm.patches.size(); p++)
+                                if (hm.patches[p].name == pn.str) found = (int)p;
+                            if (found < 0) throw Error("function " + f.name + ": unknown patch " + pn.str);
+                            out.push_back(found);
+                        }
+                };
+                patchList("patches", f.patches);
+                if (f.type == "totalPressureRatio")
+                {
+                    if (!par.comp) throw Error("function " + f.name + ": totalPressureRatio needs a compressible solver");
+                    patchList("inletPatches", f.inletPatches);
+                    patchList("outletPatches", f.outletPatches);
+                    for (int p : f.patches)
+                        if (std::find(f.inletPatches.begin(), f.inletPatches.end(), p) == f.inletPatches.end()
+                            && std::find(f.outletPatches.begin(), f.outletPatches.end(), p) == f.outletPatches.end())
+                            throw Error("inlet/outletPatches names are not in patches");
+                    if (f.inletPatches.empty() || f.outletPatches.empty()) throw Error("function " + f.name + ": inletPatches / outletPatches are required");
+                    f.gamma = gammaTPR;
+                }
                 if (f.type == "moment")
                 {
                     if (const JVal* d = kv.second.get("axis"))
@@ -1462,11 +1553,66 @@ struct Solver
     }
 
     DevBuf<double> dFacePart;
+    double gammaTPR = 1.4;
+
+    // the two area averages of DAFunctionTotalPressureRatio: side 0 = outlet (numerator), 1 = inlet
+    ForceSpec tprSpec(const FunctionDef& f, int side) const
+    {
+        FunctionDef g = f;
+        g.type = "totalPressure"; // the area sum of the side's patches
+        g.patches = side == 0 ? f.outletPatches : f.inletPatches;
+        g.scale = 1.0;
+        ForceSpec fs = forceSpec(g);
+        fs.mode = 4;
+        fs.gamma = f.gamma;
+        return fs;
+    }
+    double sumFaceParts(const ForceSpec& fs)
+    {
+        if (dFacePart.n < (size_t)hm.nBF + 1) dFacePart.alloc(be, hm.nBF + 1);
+        if (par.comp) be.launch(hm.nBF, cForceFwd{mv, par, sv, rv, fs, dFacePart.p});
+        else be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, fs, dFacePart.p});
+        std::vector<double> facePart(hm.nBF);
+        be.d2h(facePart.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
+        double s = 0.0;
+        for (int b = 0; b < hm.nBF; b++) s += facePart[b];
+        if (comm.active())
+        {
+            be.h2d(dFacePart.p, &s, sizeof(double));
+            comm.allreduceSum(be, dFacePart.p, 1);
+            be.d2h(&s, dFacePart.p, sizeof(double));
+        }
+        return s;
+    }
+    // the face groups of a function with the weights of its derivative: F = sum_g (value of group g), or for the ratio
+    // d(A/B) = dA/B - A/B^2 dB; `shift` makes the geometric derivative of the area averages exact (rev_kernels.hpp ForceSpec)
+    std::vector<ForceSpec> derivativeSpecs(const FunctionDef& f)
+    {
+        std::vector<ForceSpec> out;
+        if (f.type == "totalPressureRatio")
+        {
+            ForceSpec a = tprSpec(f, 0), b = tprSpec(f, 1);
+            const double A = sumFaceParts(a), B = sumFaceParts(b);
+            a.scale = 1.0 / B;
+            a.shift = A;
+            b.scale = -A / (B * B);
+            b.shift = B;
+            b.accumulate = 1;
+            out.push_back(a);
+            out.push_back(b);
+            return out;
+        }
+        ForceSpec fs = forceSpec(f);
+        if (fs.mode == 2) fs.shift = sumFaceParts(fs) / fs.scale;
+        out.push_back(fs);
+        return out;
+    }
 
     double calcFunction(const std::string& name)
     {
         const FunctionDef& f = findFunction(name);
         ensureRecorded();
+        if (f.type == "totalPressureRatio") return sumFaceParts(tprSpec(f, 0)) / sumFaceParts(tprSpec(f, 1));
         if (dFacePart.n < (size_t)hm.nBF + 1) dFacePart.alloc(be, hm.nBF + 1);
         if (par.comp) be.launch(hm.nBF, cForceFwd{mv, par, sv, rv, forceSpec(f), dFacePart.p});
         else be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, forceSpec(f), dFacePart.p});
@@ -1514,14 +1660,29 @@ struct Solver
         ensureRecorded();
         if (par.comp)
         {
-            be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
-            be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
-            be.zero(av.gHeb, (size_t)3 * hm.nCtot * sizeof(double));
-            DAB_LAUNCH_NF(hm.nC, cForceRevA, mv, par, sv, rv, av, forceSpec(f), seed);
-            if (comm.active()) halo.exchangeCells({{av.gUb, 9, 1, hm.nCtot}});
-            DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, dY2.p);
-            be.zero(dY2.p + (size_t)nCellStates() * hm.nC, (size_t)hm.nF * sizeof(double)); // no face-flux dependence
-            be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
+            std::vector<ForceSpec> specs;
+            if (f.type == "totalPressureRatio") specs = derivativeSpecs(f);
+            else specs.push_back(forceSpec(f));
+            std::vector<double> part;
+            for (size_t g = 0; g < specs.size(); g++)
+            {
+                be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
+                be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
+                be.zero(av.gHeb, (size_t)3 * hm.nCtot * sizeof(double));
+                DAB_LAUNCH_NF(hm.nC, cForceRevA, mv, par, sv, rv, av, specs[g], seed);
+                if (comm.active()) halo.exchangeCells({{av.gUb, 9, 1, hm.nCtot}});
+                DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, dY2.p);
+                be.zero(dY2.p + (size_t)nCellStates() * hm.nC, (size_t)hm.nF * sizeof(double)); // no face-flux dependence
+                if (g == 0)
+                    be.d2h(out, dY2.p, (size_t)nDof() * sizeof(double));
+                else
+                {
+                    // the second face group of a ratio: the two sweeps add
+                    part.resize(nDof());
+                    be.d2h(part.data(), dY2.p, (size_t)nDof() * sizeof(double));
+                    for (size_t i = 0; i < part.size(); i++) out[i] += part[i];
+                }
+            }
             return;
         }
         be.zero(av.gUb, (size_t)9 * hm.nCtot * sizeof(double));

@@ -189,8 +189,12 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
     be.d2d(Vc.dPts.p, Vc.dPts0.p, (size_t)3 * nP * sizeof(double));
     be.zero(Vc.dOut.p, (size_t)3 * nP * sizeof(double));
     const int ns = nCellStates(), offPhi = ns * nC;
-    ForceSpec fs;
-    if (function) fs = forceSpec(*function);
+    std::vector<ForceSpec> fsv;
+    if (function)
+    {
+        ensureRecorded();
+        fsv = derivativeSpecs(*function); // at the unperturbed geometry
+    }
     auto evaluate = [&](double* Rdev, double* Fdev) {
         geometry();
         if (function)
@@ -198,12 +202,12 @@ inline void Solver::volCoordProduct(const double* psi, const FunctionDef* functi
             if (par.comp)
             {
                 DAB_LAUNCH_NF(hm.nCtot, cFwdA, mv, par, sv, rv);
-                be.launch(hm.nBF, cForceFwd{mv, par, sv, rv, fs, Fdev});
+                for (const ForceSpec& fs : fsv) be.launch(hm.nBF, cForceFwd{mv, par, sv, rv, fs, Fdev});
             }
             else
             {
                 DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);
-                be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, fs, Fdev});
+                for (const ForceSpec& fs : fsv) be.launch(hm.nBF, ForceFwd{mv, par, sv, rv, fs, Fdev});
             }
         }
         else

@@ -660,6 +660,7 @@ struct Work
     std::vector<T> gradU, nutC;
     std::vector<T> muEB; // compressible: rho_b*nuEff_b on the boundary faces
     std::vector<T> rhoB; // compressible: boundary density
+    std::vector<T> TB;   // compressible: boundary temperature
 };
 
 // DAFvSourceActuatorDisk::calcFvSource, source = cylinderAnnulusSmooth (reference DAFvSourceActuatorDisk.C:205-407), adjustThrust 0;
@@ -1477,6 +1478,7 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
         wk->gradU = gradU; wk->nutC = nut;
         wk->muEB = muEB;
         wk->rhoB = rhoB;
+        wk->TB = bT.val;
     }
 }
 
@@ -1494,7 +1496,9 @@ T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int p
     T F(0.0);
     if (mode >= 2)
     {
-        // mode 2: DAFunctionTotalPressure (area-averaged p + 0.5 rho |U|^2); mode 3: DAFunctionMassFlowRate (rho U.Sf)
+        // mode 2: DAFunctionTotalPressure (area-averaged p + 0.5 rho |U|^2); mode 3: DAFunctionMassFlowRate (rho U.Sf);
+        // mode 4: the area-averaged isentropic total pressure p (1 + (gamma-1)/2 Ma^2)^(gamma/(gamma-1)) of one side of
+        // DAFunctionTotalPressureRatio (DAFunctionTotalPressureRatio.C:50-140), gamma = dir[0], R = Cp - Cp/gamma
         T areaSum(0.0);
         for (int b = 0; b < t.nBF; b++)
             if (t.bPatch[b] == patch) areaSum += g.magSf[t.nIF + b];
@@ -1510,6 +1514,13 @@ T forceFunction(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int p
                 SU += g.Sf[f][k] * wk.bU.val[wk.bU.at(k, b)];
             }
             if (mode == 2) F += scale * (wk.bP.val[b] + 0.5 * rhob * U2) * g.magSf[f] / areaSum;
+            else if (mode == 4)
+            {
+                const double gam = dir[0], Rg = cs.comp.Cp - cs.comp.Cp / gam;
+                T Ma2 = U2 / (gam * Rg * wk.TB[b]);
+                T pT = wk.bP.val[b] * pow(T(1.0 + 0.5 * (gam - 1.0) * Ma2), gam / (gam - 1.0));
+                F += scale * pT * g.magSf[f] / areaSum;
+            }
             else F += scale * rhob * SU;
         }
         return F;

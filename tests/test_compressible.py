@@ -243,6 +243,56 @@ def check_patch_functions(lib_path):
             assert np.linalg.norm(go) > 0 and rel_err(g, go) < tol, (comp, name, rel_err(g, go))
 
 
+def check_total_pressure_ratio(lib_path):
+    """DAFunctionTotalPressureRatio (outlet / inlet area-averaged isentropic total pressure): value and state derivative vs the
+    oracle; its mesh derivative, and the one of the area-averaged totalPressure, vs central differences through updateOFMesh
+    (the area sums move with the points)."""
+    cfg = CONFIGS[2]
+    mesh, orc, sol, W = setup_comp(cfg, lib_path)
+    gamma = 1.4
+    fn = {"TPR": {"type": "totalPressureRatio", "source": "patchToFace", "patches": ["inlet", "outlet"], "inletPatches": ["inlet"],
+                  "outletPatches": ["outlet"], "scale": 1.0},
+          "TP": {"type": "totalPressure", "source": "patchToFace", "patches": ["outlet"], "scale": 0.5}}
+    sol.updateDAOption(dict(normalizeStates=NS, normalizeResiduals=list(cfg[7]), function=fn))
+    sol.updateOFFields(W)
+    names = [p["name"] for p in mesh.patches]
+    i_in, i_out = names.index("inlet"), names.index("outlet")
+    g3 = [gamma, 0.0, 0.0]
+    A, B = orc.force(W, i_out, g3, 1.0, mode=4), orc.force(W, i_in, g3, 1.0, mode=4)
+    tol = 1e-12 if lib_path is not None else 1e-9
+    F = sol.calcFunction("TPR")
+    assert abs(F - A / B) <= tol * abs(A / B), (F, A / B)
+    g = np.zeros(orc.ndof)
+    sol.calcJacTVecProduct("states", "stateVar", W, "TPR", "function", np.array([1.0]), g)
+    go = orc.dforce_dw(W, i_out, g3, 1.0, mode=4) / B - A / B**2 * orc.dforce_dw(W, i_in, g3, 1.0, mode=4)
+    assert np.linalg.norm(go) > 0 and rel_err(g, go) < max(tol, 1e-11), rel_err(g, go)
+    nP3 = 3 * sol.getNLocalPoints()
+    pts = np.zeros(nP3)
+    sol.getOFMeshPoints(pts)
+    X = pts.reshape(-1, 3)
+    v = np.stack([np.sin(3.0 * X[:, 1]) * 1e-3, np.cos(2.0 * X[:, 0] + X[:, 1]) * 1e-3, np.zeros(len(X))], axis=1).ravel()
+    h = 1e-3
+    for name in ("TPR", "TP"):
+        dFdx = np.zeros(nP3)
+        sol.calcJacTVecProduct("aero_vol_coords", "volCoord", pts, name, "function", np.array([1.0]), dFdx)
+        sol.updateOFMesh(pts + h * v)
+        Fp = sol.calcFunction(name)
+        sol.updateOFMesh(pts - h * v)
+        Fm = sol.calcFunction(name)
+        sol.updateOFMesh(pts)
+        fd = (Fp - Fm) / (2 * h)
+        assert abs(fd) > 0 and abs(fd - dFdx @ v) <= 2e-5 * abs(fd), (name, fd, dFdx @ v)
+
+
+def test_total_pressure_ratio_host_build():
+    check_total_pressure_ratio(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_total_pressure_ratio_cuda():
+    check_total_pressure_ratio(None)
+
+
 def test_total_pressure_and_mass_flow_rate_host_build():
     check_patch_functions(HOSTSIM)
 

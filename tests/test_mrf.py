@@ -166,3 +166,39 @@ def test_mrf_function_volcoord_and_primal_host_build():
 @pytest.mark.gpu
 def test_mrf_function_volcoord_and_primal_cuda():
     check_function_volcoord_primal(None, tol=1e-9)
+
+
+def test_primal_bc_option_host_build():
+    """primalBC (reference DAField::setPrimalBoundaryConditions): boundary values, MRF speed, laminar viscosity and the nut wall
+    treatment from the options give the residual of a case written with those values."""
+    import tempfile
+    from dafoam_b200.pyDASolvers import pyDASolvers
+    from tests.common import rel_err
+    mesh = cases.naca0012_ogrid(ni=24, nj=12, nk=2)
+    th = cases.default_thermo(mu=2.5e-5)
+    U1 = (60.0, 1.0, 0.0)
+    # the target: written BCs U1, T 310, wall function, omega 20, mu 2.5e-5
+    bcs1 = cases.compressible_bcs(cases.default_bcs_naca(U0=U1, wall_function=True), T0=310.0)
+    orc = Oracle(mesh, bcs1, normalizeStates=NS_C, normalizeResiduals=NRES_C, thermo=th, divU="linearUpwindV")
+    orc.set_mrf(mesh, mrf_zone(mesh, omega=20.0))
+    W = synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=th)
+    # the case on disk: other values everywhere, corrected through primalBC
+    bcs0 = cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0)))
+    d = tempfile.mkdtemp(prefix="dab_pbc_")
+    cases.write_case(d, mesh, bcs0, div_u="bounded Gauss linearUpwindV grad(U)", mrf=mrf_zone(mesh, omega=5.0), thermo=cases.default_thermo())
+    pbc = {"U0": {"variable": "U", "patches": ["inout"], "value": list(U1)},
+           "T0": {"variable": "T", "patches": ["inout"], "value": [310.0]},
+           "k0": {"variable": "k", "patches": ["inout"], "value": [0.1]},  # not a field of this solver: skipped
+           "useWallFunction": True, "MRF": 20.0, "thermo:mu": 2.5e-5}
+    sol = pyDASolvers("DATurboFoam -python", dict(normalizeStates=NS_C, normalizeResiduals=list(NRES_C), primalBC=pbc), caseDir=d,
+                      _lib_path=HOSTSIM)
+    sol.updateOFFields(W)
+    R = np.zeros(orc.ndof)
+    sol.getResiduals(R)
+    assert rel_err(R, orc.residual(W)) < 1e-10
+    # ... and again after a later option update
+    sol.updateDAOption(dict(primalBC={"MRF": 5.0}))
+    R2 = np.zeros(orc.ndof)
+    sol.getResiduals(R2)
+    orc.set_mrf(mesh, mrf_zone(mesh, omega=5.0))
+    assert rel_err(R2, orc.residual(W)) < 1e-10
