@@ -287,6 +287,7 @@ struct cPEqnAssemble
     StateView s;
     RecordView r;
     EqnView e;
+    Simplec sc; // DATurboFoam / consistent: AtU = AU - H1 (reference pEqnTurbo.H:13-15, 64-70)
     DAB_HD void operator()(int c) const
     {
         const int nT = m.nCtot, nC = m.nC;
@@ -315,19 +316,39 @@ struct cPEqnAssemble
                 }
                 if (m.mrfFlux) ph -= m.mrfFlux[f];
                 const double rhof = w * r.rho[o] + (1.0 - w) * r.rho[n];
-                const double gam = (w * r.rho[o] * r.rAU[o] + (1.0 - w) * r.rho[n] * r.rAU[n]) * mS;
+                double gam = (w * r.rho[o] * r.rAU[o] + (1.0 - w) * r.rho[n] * r.rAU[n]) * mS;
+                double phr = rhof * ph;
+                if (sc.rAt)
+                {
+                    // phiHbyA += interpolate(rho/AtU - rho/AU) snGrad(p) |Sf|, laplacian(rho/AtU, p)
+                    const double gamT = (w * r.rho[o] * sc.rAt[o] + (1.0 - w) * r.rho[n] * sc.rAt[n]) * mS;
+                    double cgOld = 0.0;
+                    for (int j = 0; j < 3; j++) cgOld += kv[j] * (w * sc.gPOld[(size_t)j * nT + o] + (1.0 - w) * sc.gPOld[(size_t)j * nT + n]);
+                    phr += (gamT - gam) * (dl * (sc.pOld[n] - sc.pOld[o]) + cgOld);
+                    gam = gamT;
+                }
                 e.off[(size_t)k * nC + c] = -gam * dl;
                 D += gam * dl;
-                B -= fr.s * (rhof * ph - gam * cg);
+                B -= fr.s * (phr - gam * cg);
             }
             else
             {
                 e.off[(size_t)k * nC + c] = 0.0;
                 BoundaryPoint bp;
                 boundaryPoint<false>(m, q, s, r, f, c, bp);
-                const double gb = bp.th.rho * r.rAU[c] * mS * dl * bp.frP;
+                double gU = bp.th.rho * r.rAU[c] * mS, phr = bp.th.rho * cPhBoundary(m, q, r, bp, f, c);
+                if (sc.rAt)
+                {
+                    const int pa = m.bPatch[f - m.nIF];
+                    double pv, snOld, fr_;
+                    bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], sc.pOld[c], s.phi[f], dl, pv, snOld, fr_);
+                    const double gT = bp.th.rho * sc.rAt[c] * mS;
+                    phr += (gT - gU) * snOld;
+                    gU = gT;
+                }
+                const double gb = gU * dl * bp.frP;
                 D += gb;
-                B += gb * q.bcVal[F_P][m.bPatch[f - m.nIF]][0] - bp.th.rho * cPhBoundary(m, q, r, bp, f, c);
+                B += gb * q.bcVal[F_P][m.bPatch[f - m.nIF]][0] - phr;
             }
         }
         e.diag[c] = D;
@@ -344,8 +365,10 @@ struct cPhiUpdate
     StateView s;
     RecordView r;
     double* phi;
+    Simplec sc;
     DAB_HD void operator()(int c) const
     {
+        const int nT = m.nCtot;
         for (int k = 0; k < m.maxCF; k++)
         {
             const FaceRef fr = faceOf(m, c, k);
@@ -353,12 +376,39 @@ struct cPhiUpdate
             if (fr.s < 0) continue;
             const int f = fr.f;
             if (!fr.bnd)
-                phi[f] = cFaceF(m, s, r, f, c, fr.n);
+            {
+                double F = cFaceF(m, s, r, f, c, fr.n);
+                if (sc.rAt)
+                {
+                    const int n = fr.n;
+                    const double w = m.w[f], dl = m.delta[f];
+                    const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+                    double cg = 0.0, cgOld = 0.0;
+                    for (int j = 0; j < 3; j++)
+                    {
+                        cg += kv[j] * (w * r.gP[(size_t)j * nT + c] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
+                        cgOld += kv[j] * (w * sc.gPOld[(size_t)j * nT + c] + (1.0 - w) * sc.gPOld[(size_t)j * nT + n]);
+                    }
+                    const double dg = (w * r.rho[c] * (sc.rAt[c] - r.rAU[c]) + (1.0 - w) * r.rho[n] * (sc.rAt[n] - r.rAU[n])) * m.magSf[f];
+                    F += dg * ((dl * (sc.pOld[n] - sc.pOld[c]) + cgOld) - (dl * (s.p[n] - s.p[c]) + cg));
+                }
+                phi[f] = F;
+            }
             else
             {
                 BoundaryPoint bp;
                 boundaryPoint<false>(m, q, s, r, f, c, bp);
-                phi[f] = bp.th.rho * cPhBoundary(m, q, r, bp, f, c) - bp.th.rho * r.rAU[c] * m.magSf[f] * bp.sngP;
+                double gU = bp.th.rho * r.rAU[c] * m.magSf[f], phr = bp.th.rho * cPhBoundary(m, q, r, bp, f, c);
+                if (sc.rAt)
+                {
+                    const int pa = m.bPatch[f - m.nIF];
+                    double pv, snOld, fr_;
+                    bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], sc.pOld[c], s.phi[f], m.delta[f], pv, snOld, fr_);
+                    const double gT = bp.th.rho * sc.rAt[c] * m.magSf[f];
+                    phr += (gT - gU) * snOld;
+                    gU = gT;
+                }
+                phi[f] = phr - gU * bp.sngP;
             }
         }
         (void)NF;

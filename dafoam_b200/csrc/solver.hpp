@@ -460,8 +460,8 @@ struct Solver
         {
             const std::string c = fso.sub("SIMPLE").wordOr("consistent", "false");
             primal.consistent = (c == "true" || c == "yes" || c == "on");
-            if (primal.consistent && par.comp) throw Error("SIMPLEC (consistent yes) is built for DASimpleFoam only");
         }
+        if (solverName == "DATurboFoam") primal.consistent = true; // its pressure corrector always uses AtU = AU - H1 (pEqnTurbo.H:13)
         // primal solver controls (system/fvSolution, system/controlDict)
         if (fso.hasSub("relaxationFactors"))
         {

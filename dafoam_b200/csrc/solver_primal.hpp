@@ -311,7 +311,15 @@ inline int Solver::solvePrimal(PrimalStats& st)
         exGrad();
         be.launch(nC, HbyAKernel{eU, sv, rv, mv.V, nT});
         if (mr) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}});
-        DAB_LAUNCH_NF(nC, cPEqnAssemble, mv, pp, sv, rv, eP);
+        Simplec sc;
+        if (P.consistent)
+        {
+            be.launch(nC, RAtKernel{eU, rv.rAU, mv.V, P.rAt.p});
+            if (mr) halo.exchangeCells({{P.rAt.p, 1, 1, nT}});
+            be.d2d(P.gPOld.p, rv.gP, (size_t)3 * nT * sizeof(double));
+            sc = Simplec{P.rAt.p, P.pOld.p, P.gPOld.p};
+        }
+        DAB_LAUNCH_NF(nC, cPEqnAssemble, mv, pp, sv, rv, eP, sc);
         if (it == 1 || (it - 1) % P.coarseRefresh == 0) primalCoarseRefresh(eP);
         {
             double rp;
@@ -320,7 +328,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
             maxRes = std::max(maxRes, rp);
         }
         if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}});
-        DAB_LAUNCH_NF(nC, cPhiUpdate, mv, pp, sv, rv, dPhi.p);
+        DAB_LAUNCH_NF(nC, cPhiUpdate, mv, pp, sv, rv, dPhi.p, sc);
         if (mr) halo.exchangeFaces({{dPhi.p, 1, 1, hm.nF}});
         be.launch(nC, RelaxField{dP.p, P.pOld.p, P.alphaP});
         be.launch(nC, BoundField{dP.p, P.pMin, P.pMax});
@@ -328,7 +336,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
         if (mr) halo.exchangeCells({{dP.p, 1, 1, nT}, {rv.rho, 1, 1, nT}});
         DAB_LAUNCH_NF(nT, cFwdA, mv, pp, sv, rv); // grad of the relaxed p, closures at the new (p, T)
         exGrad();
-        be.launch(nC, UCorrect{rv, dU.p, nT, Simplec()});
+        be.launch(nC, UCorrect{rv, dU.p, nT, sc});
         be.launch(3 * nC, BoundField{dU.p, -P.UMax, P.UMax});
         if (mr) halo.exchangeCells({{dU.p, 3, 3, 1}});
         if (par.turb)

@@ -123,7 +123,7 @@ def check_function_volcoord_primal(lib_path, tol=1e-10):
         sol.updateOFFields(W)
         wing = [p["name"] for p in mesh.patches].index("wing")
         F, Fo = sol.calcFunction("CD"), orc.force(W, wing, dirv, 0.02)
-        assert abs(F - Fo) <= 1e-11 * abs(Fo), (solver, F, Fo)
+        assert abs(F - Fo) <= max(1e-11, 0.1 * tol) * abs(Fo), (solver, F, Fo)
         n = orc.ndof
         g = np.zeros(n)
         sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), g)
