@@ -442,8 +442,8 @@ int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fai
         stats->final_residual = st.rn;
         stats->solve_seconds = st.solveSec;
         stats->pc_setup_seconds = st.pcSec;
+        stats->pc_assemblies = s->s.kry.pcAssemblies;
         stats->n_matvec = st.nMatvec;
-        stats->reserved = 0;
     }
     DAB_CATCH
 }

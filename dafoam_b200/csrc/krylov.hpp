@@ -485,6 +485,8 @@ struct Coarse
 struct Krylov
 {
     bool pcValid = false;
+    bool pcFactored = false; // a factorisation exists (possibly of an earlier state: adjPCLag)
+    int pcAssemblies = 0;
     bool symbolic = false;
     double pcSec = 0.0;
     int n = 0;

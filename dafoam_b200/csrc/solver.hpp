@@ -597,6 +597,7 @@ struct Solver
             primal.TMax = vb->numOr("TMax", primal.TMax);
             primal.UMax = vb->numOr("UMax", primal.UMax);
         }
+        adjPCLag = (int)o.numOr("adjPCLag", (double)adjPCLag);
         if (const JVal* pb = o.get("primalBC"))
         {
             // DAField::setPrimalBoundaryConditions (reference DAField.C:698-1260): boundary values, nut wall treatment, MRF speed
@@ -1554,6 +1555,7 @@ struct Solver
 
     DevBuf<double> dFacePart;
     double gammaTPR = 1.4;
+    int adjPCLag = 1; // > 1: solveLinearEqn keeps a preconditioner factorised at an earlier state
 
     // the two area averages of DAFunctionTotalPressureRatio: side 0 = outlet (numerator), 1 = inlet
     ForceSpec tprSpec(const FunctionDef& f, int side) const

@@ -373,6 +373,8 @@ inline void Solver::calcPC()
     for (const ColourView& cv : K.colours) be.launch(cv.nCells, IluFactorColour{A, cv, 1e-10});
     be.sync();
     K.pcValid = true;
+    K.pcFactored = true;
+    K.pcAssemblies++;
     K.coarse.enabled = coarseAggregates > 0;
     K.coarse.valid = false;
     if (K.coarse.enabled) coarseSetup();
@@ -541,7 +543,9 @@ inline void Solver::applyIlu(const double* v, double* z)
 inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
 {
     Krylov& K = kry;
-    if (!K.pcValid) calcPC();
+    // adjPCLag > 1 (reference mphys_dafoam.py:511-530): the caller decides when calcdRdWT refreshes the preconditioner; a
+    // factorisation of an earlier design keeps being used in between
+    if (!K.pcValid && !(K.pcFactored && adjPCLag > 1 && K.symbolic)) calcPC();
     ensureRecorded();
     const int n = nDof();
     const int m = std::max(1, std::min(gmresRestart, gmresMaxIters));

@@ -62,6 +62,7 @@ class PYDAFOAM:
         self._pc = None
         self._ksp = None
         self._psi = {}
+        self._pcAge = 0  # primal solutions since the preconditioner was assembled (adjPCLag)
 
     # ---- options -----------------------------------------------------------------------------------------
     def getOption(self, name):
@@ -83,7 +84,7 @@ class PYDAFOAM:
         """Solve the primal (reference pyDAFoam.py:800-821)."""
         self.primalFail = self.solver.solvePrimal()
         self.nSolvePrimals += 1
-        self._pc = None  # the preconditioner belongs to the previous state
+        self._pcAge += 1  # the preconditioner now belongs to an earlier design: refreshed every adjPCLag (below)
         self._psi = {}
 
     def evalFunctions(self, funcs):
@@ -123,8 +124,7 @@ class PYDAFOAM:
 
     def setVolCoords(self, vol_coords):
         self.solver.updateOFMesh(np.ascontiguousarray(vol_coords, dtype=np.float64))
-        self._pc = None
-        self._psi = {}
+        self._psi = {}  # the preconditioner is kept: it is refreshed every adjPCLag primal solutions
 
     def getResiduals(self):
         residuals = np.zeros(self.solver.getNLocalAdjointStates(), self.dtype)
@@ -148,7 +148,8 @@ class PYDAFOAM:
         W = self.getStates()
         dFdW = np.zeros(n)
         self.solver.calcJacTVecProduct("states", "stateVar", W, functionName, "function", np.array([1.0]), dFdW)
-        if self._pc is None:
+        if self._pc is None or self._pcAge >= max(1, int(self.getOption("adjPCLag"))):
+            self._pcAge = 0
             self._pc, self._ksp = Mat(), KSP()
             self.solver.calcdRdWT(1, self._pc)
             self.solver.createMLRKSPMatrixFree(self._pc, self._ksp)

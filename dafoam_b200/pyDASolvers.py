@@ -29,7 +29,7 @@ class DAB200Error(RuntimeError):
 class KspStats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged_reason", C.c_int32), ("initial_residual", C.c_double),
                 ("final_residual", C.c_double), ("solve_seconds", C.c_double), ("pc_setup_seconds", C.c_double),
-                ("n_matvec", C.c_int32), ("reserved", C.c_int32)]
+                ("n_matvec", C.c_int32), ("pc_assemblies", C.c_int32)]
 
 
 class PrimalStats(C.Structure):

@@ -49,7 +49,7 @@ typedef struct dab_ksp_stats
     double solve_seconds;      /* device time of the GMRES loop */
     double pc_setup_seconds;   /* preconditioner assembly + factorisation */
     int32_t n_matvec;          /* number of dRdWT*psi products */
-    int32_t reserved;
+    int32_t pc_assemblies;     /* preconditioner assemblies of this handle so far (adjPCLag bookkeeping) */
 } dab_ksp_stats;
 
 /* per-equation initial residuals of the last SIMPLE iteration (what the reference prints through

@@ -185,6 +185,26 @@ def run_pydafoam_api(lib_path):
     DASolver()
     dFdxv = DASolver.calcTotalDeriv("CD", "aero_vol_coords")
     assert dFdxv.shape == (3 * DASolver.getNLocalPoints(),) and np.linalg.norm(dFdxv) > 0
+    # adjPCLag (reference mphys_dafoam.py:511-530): the preconditioner of an earlier design keeps being used; the adjoint still
+    # converges to the same derivative, the assembly count only moves every adjPCLag designs
+    n0 = DASolver._ksp.stats.pc_assemblies
+    DASolver.setOption("adjPCLag", 2)
+    DASolver.updateDAOption()
+    counts, totals = [], []
+    for k in range(3):
+        xk = x + np.array([0.2 * (k + 1), 0.1 * (k + 1)])
+        DASolver.set_solver_input({"patchV": xk})
+        DASolver()
+        totals.append(DASolver.calcTotalDeriv("CD", "patchV", xk))
+        assert DASolver.adjointFail == 0
+        counts.append(DASolver._ksp.stats.pc_assemblies - n0)
+    assert counts == [1, 1, 2], counts  # assembled for the 1st and 3rd design, reused for the 2nd
+    DASolver.setOption("adjPCLag", 1)
+    DASolver.updateDAOption()
+    DASolver.set_solver_input({"patchV": x + np.array([0.4, 0.2])})
+    DASolver()
+    fresh = DASolver.calcTotalDeriv("CD", "patchV", x + np.array([0.4, 0.2]))
+    assert np.allclose(totals[1], fresh, rtol=1e-7), (totals[1], fresh)
 
 
 def test_pydafoam_class_host_build():
