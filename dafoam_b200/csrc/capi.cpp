@@ -346,6 +346,34 @@ int dab_get_local_to_global(dab_solver* s, int what, int64_t* out)
     DAB_CATCH
 }
 
+int dab_get_pc_matrix(dab_solver* s, int64_t* n_rows, int64_t* nnz, int64_t* row_ptr, int32_t* cols, double* vals)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(n_rows, "n_rows");
+    need(nnz, "nnz");
+    Solver& S = s->s;
+    if (!row_ptr)
+    {
+        *n_rows = S.kry.n;
+        *nnz = S.kry.nnz;
+        return 0;
+    }
+    need(cols, "cols");
+    need(vals, "vals");
+    std::vector<int64_t> rp;
+    std::vector<int32_t> cl;
+    std::vector<double> vl;
+    S.exportPC(rp, cl, vl);
+    if ((int64_t)cl.size() > *nnz || (int64_t)rp.size() - 1 > *n_rows) throw Error("dab_get_pc_matrix: the buffers are too small");
+    *n_rows = (int64_t)rp.size() - 1;
+    *nnz = (int64_t)cl.size();
+    std::copy(rp.begin(), rp.end(), row_ptr);
+    std::copy(cl.begin(), cl.end(), cols);
+    std::copy(vl.begin(), vl.end(), vals);
+    DAB_CATCH
+}
+
 int dab_pc_apply(dab_solver* s, const double* v, double* z)
 {
     DAB_TRY

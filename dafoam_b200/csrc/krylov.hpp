@@ -500,6 +500,7 @@ struct Krylov
     DevBuf<int64_t> dRowBase;
     DevBuf<int32_t> dRowStride, dRowLen, dDiag, dCol;
     DevBuf<double> dVal, dDinv;
+    std::vector<double> hValAssembled; // host copy of the assembled (unfactorised) values when writeJacobians asks for dRdWTPC
     int64_t nnz = 0, ellSize = 0;
     // FD colours
     std::vector<int32_t> fdList, fdStart;

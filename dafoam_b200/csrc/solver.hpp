@@ -598,6 +598,12 @@ struct Solver
             primal.UMax = vb->numOr("UMax", primal.UMax);
         }
         adjPCLag = (int)o.numOr("adjPCLag", (double)adjPCLag);
+        if (const JVal* wj = o.get("writeJacobians"))
+        {
+            keepPCMatrix = false;
+            for (const auto& v : wj->arr)
+                if (v.str == "dRdWTPC" || v.str == "all") keepPCMatrix = true;
+        }
         if (const JVal* pb = o.get("primalBC"))
         {
             // DAField::setPrimalBoundaryConditions (reference DAField.C:698-1260): boundary values, nut wall treatment, MRF speed
@@ -1556,6 +1562,41 @@ struct Solver
     DevBuf<double> dFacePart;
     double gammaTPR = 1.4;
     int adjPCLag = 1; // > 1: solveLinearEqn keeps a preconditioner factorised at an earlier state
+    bool keepPCMatrix = false; // writeJacobians lists dRdWTPC (or all): calcPC keeps the assembled values for export
+
+    // dRdWTPC as assembled (rows: states, columns: residuals, both in the external numbering of this rank), CSR with sorted
+    // columns -- what DAUtility::writeMatrixBinary(dRdWT, "dRdWTPC") stores (DASolver.C:1080-1085)
+    void exportPC(std::vector<int64_t>& rowPtr, std::vector<int32_t>& cols, std::vector<double>& vals)
+    {
+        Krylov& K = kry;
+        if (K.hValAssembled.size() != (size_t)K.ellSize || K.ellSize == 0)
+            throw Error("the assembled dRdWTPC is not kept: list dRdWTPC in the writeJacobians option before calcdRdWT");
+        std::vector<int32_t> hc((size_t)K.ellSize);
+        be.d2h(hc.data(), K.dCol.p, (size_t)K.ellSize * sizeof(int32_t));
+        rowPtr.assign((size_t)K.n + 1, 0);
+        cols.clear();
+        vals.clear();
+        cols.reserve((size_t)K.nnz);
+        vals.reserve((size_t)K.nnz);
+        std::vector<std::pair<int32_t, double>> row;
+        for (int e = 0; e < K.n; e++)
+        {
+            const int i = K.iperm[e];
+            row.clear();
+            for (int q = 0; q < K.rowLen[i]; q++)
+            {
+                const size_t at = (size_t)(K.rowBase[i] + (int64_t)q * K.rowStride[i]);
+                row.emplace_back(K.perm[hc[at]], K.hValAssembled[at]);
+            }
+            std::sort(row.begin(), row.end());
+            for (const auto& x : row)
+            {
+                cols.push_back(x.first);
+                vals.push_back(x.second);
+            }
+            rowPtr[(size_t)e + 1] = (int64_t)cols.size();
+        }
+    }
 
     // the two area averages of DAFunctionTotalPressureRatio: side 0 = outlet (numerator), 1 = inlet
     ForceSpec tprSpec(const FunctionDef& f, int side) const

@@ -369,6 +369,11 @@ inline void Solver::calcPC()
         be.d2d(dPhi.p, dWext.p + off, (size_t)hm.nF * sizeof(double));
         recorded = false;
     }
+    if (keepPCMatrix)
+    {
+        K.hValAssembled.resize((size_t)K.ellSize);
+        be.d2h(K.hValAssembled.data(), K.dVal.p, (size_t)K.ellSize * sizeof(double));
+    }
     // ILU(0), one kernel per colour
     for (const ColourView& cv : K.colours) be.launch(cv.nCells, IluFactorColour{A, cv, 1e-10});
     be.sync();

@@ -122,6 +122,7 @@ class pyDASolvers:
             argsAll = argsAll.decode()
         self._options = dict(pyOptions or {})
         self._solverName = argsAll.split()[0] if argsAll.split() else "DASimpleFoam"
+        self._caseDir, self._rank, self._nRanks = os.path.abspath(caseDir), rank, nRanks
         uid = None if ncclUniqueId is None else C.c_char_p(bytes(ncclUniqueId))
         rc = self._L.dab_create(os.path.abspath(caseDir).encode(), argsAll.encode(), json.dumps(self._options).encode(),
                                 C.c_int(device), C.c_int(rank), C.c_int(nRanks), uid, C.byref(self._h))
@@ -336,6 +337,22 @@ class pyDASolvers:
         assert isPC == 1, "only the preconditioner matrix (isPC=1) is assembled explicitly; dRdWT itself is matrix-free"
         self._raise(self._L.dab_calc_drdwt_pc(self._h))
         dRdWT.assembled = True
+        wj = self._options.get("writeJacobians", [])
+        if "dRdWTPC" in wj or "all" in wj:
+            # DAUtility::writeMatrixBinary(dRdWT, "dRdWTPC") (reference DASolver.C:1080-1085): PETSc binary AIJ in the case directory
+            from . import petsc_io
+            rp, cl, vl = self.getPCMatrix()
+            name = "dRdWTPC.bin" if self._nRanks == 1 else "dRdWTPC_rank%d.bin" % self._rank
+            petsc_io.write_mat(os.path.join(self._caseDir, name), rp, cl, vl)
+
+    def getPCMatrix(self):
+        """(row_ptr, cols, vals) of the assembled dRdWTPC (CSR, external numbering); needs "dRdWTPC" in writeJacobians."""
+        n, nnz = C.c_int64(), C.c_int64()
+        self._raise(self._L.dab_get_pc_matrix(self._h, C.byref(n), C.byref(nnz), None, None, None))
+        rp, cl, vl = np.zeros(n.value + 1, dtype=np.int64), np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value)
+        self._raise(self._L.dab_get_pc_matrix(self._h, C.byref(n), C.byref(nnz), rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              cl.ctypes.data_as(C.POINTER(C.c_int32)), _dp(vl)))
+        return rp, cl[:nnz.value], vl[:nnz.value]
 
     def initializedRdWTMatrixFree(self):
         return None

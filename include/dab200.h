@@ -156,6 +156,13 @@ int dab_pc_apply(dab_solver* s, const double* v, double* z);
  * success rule (relRatio > gmresTolDiff && absRatio > gmresTolDiff  =>  1). */
 int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats);
 
+/* The assembled preconditioner matrix dRdWTPC of this rank as CSR (rows: states, columns: residuals, external numbering,
+ * sorted columns) -- the matrix the reference writes with DAUtility::writeMatrixBinary(dRdWT, "dRdWTPC") when the
+ * writeJacobians option lists it (DASolver.C:1080-1085, DAUtility.C:411-441).  Call with row_ptr == NULL to get the sizes,
+ * then with buffers of n_rows+1 / nnz / nnz entries.  The option writeJacobians must list "dRdWTPC" (or "all") before
+ * dab_calc_drdwt_pc, otherwise only the factorisation is kept. */
+int dab_get_pc_matrix(dab_solver* s, int64_t* n_rows, int64_t* nnz, int64_t* row_ptr, int32_t* cols, double* vals);
+
 /* setSolverInput(inputName, inputType, inputSize, inputs, seeds): assign an input to the solver's fields before
  * solvePrimal / calcFunction (reference pyDASolvers.pyx:164-182, DASolver::setSolverInput -> DAInput::run;
  * DAInputPatchVelocity.C, DAInputStateVar.C).  Types: "patchVelocity" (|U|, angle of attack [deg]) and "stateVar".

@@ -70,3 +70,42 @@ def test_field_output_round_trip():
     W2 = np.zeros(n)
     sol2.getOFFields(W2)
     assert np.array_equal(W, W2)
+
+
+def test_pc_matrix_export_petsc_binary():
+    """writeJacobians: ["dRdWTPC"] leaves dRdWTPC.bin (PETSc binary AIJ, reference DAUtility::writeMatrixBinary) in the case
+    directory: the matrix is the coloured-FD transpose Jacobian of the first-order residual, checked column by column against
+    finite differences of getResiduals(isPC=1)."""
+    from dafoam_b200 import petsc_io
+    from dafoam_b200.pyDASolvers import Mat
+    from tests.common import NORM_STATES
+    mesh, bcs, orc, sol, W, _ = setup("naca", True, nk=1, lib_path=HOSTSIM, extra_options=dict(writeJacobians=["dRdWTPC"]))
+    sol.updateOFFields(W)
+    sol.calcdRdWT(1, Mat())
+    path = os.path.join(sol._caseDir, "dRdWTPC.bin")
+    m, n, rp, cl, vl = petsc_io.read_mat(path)
+    assert m == n == orc.ndof and rp[-1] == len(cl) == len(vl)
+    assert all(np.all(np.diff(cl[rp[i]:rp[i + 1]]) > 0) for i in range(0, m, 97))  # sorted columns
+    nC = mesh.n_cells
+    scale = np.concatenate([np.full(3 * nC, NORM_STATES["U"]), np.full(nC, NORM_STATES["p"]), np.full(nC, NORM_STATES["nuTilda"]),
+                            NORM_STATES["phi"] * orc.geometry("magSf")])
+    R0 = np.zeros(m)
+    sol.getResiduals(R0, 1)
+    rng = np.random.default_rng(0)
+    for i in rng.choice(m, 12, replace=False):
+        Wp = W.copy()
+        h = 1e-6 * scale[i]
+        Wp[i] += h
+        sol.updateOFFields(Wp)
+        R1 = np.zeros(m)
+        sol.getResiduals(R1, 1)
+        col = (R1 - R0) / 1e-6  # row i of dRdWT in the scaled-state convention of the reference (perturbation = eps * scale)
+        row = np.zeros(m)
+        row[cl[rp[i]:rp[i + 1]]] = vl[rp[i]:rp[i + 1]]
+        inside = np.zeros(m, dtype=bool)
+        inside[cl[rp[i]:rp[i + 1]]] = True
+        assert np.abs(row - col)[inside].max() <= 1e-4 * max(np.abs(col).max(), 1e-30), i
+    sol.updateOFFields(W)
+    # the vector format round-trips
+    petsc_io.write_vec(os.path.join(sol._caseDir, "psi.bin"), W)
+    assert np.array_equal(petsc_io.read_vec(os.path.join(sol._caseDir, "psi.bin")), W)
