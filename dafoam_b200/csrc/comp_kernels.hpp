@@ -364,6 +364,54 @@ struct cFwdB
     }
 };
 
+// DATurboFoam, enthalpy form (DAResidualTurboFoam.C:117-121): the vector Teff & U - p (U - URel) whose Gauss-linear divergence
+// is subtracted from the energy row; Teff = muEff dev(twoSymm(grad U)), gU[j*3+i] = d_i U_j, vrel = Omega x r or null
+DAB_HD void turboWork(const double* gU, double mu, const double* u, double p, const double* vrel, double* out)
+{
+    const double tr = gU[0] + gU[4] + gU[8];
+    for (int j = 0; j < 3; j++)
+    {
+        double acc = 0.0;
+        for (int i = 0; i < 3; i++)
+        {
+            double te = gU[j * 3 + i] + gU[i * 3 + j];
+            if (i == j) te -= (2.0 / 3.0) * tr;
+            acc += te * u[i];
+        }
+        out[j] = mu * acc - (vrel ? p * vrel[j] : 0.0);
+    }
+}
+// adjoint: qb = d(row)/d(out); accumulates d/d(gU), d/d(mu), d/d(u), d/d(p)
+DAB_HD void turboWorkAdj(const double* gU, double mu, const double* u, const double* vrel, const double* qb, double* gUb, double& mub, double* ub,
+                         double& pb)
+{
+    const double tr = gU[0] + gU[4] + gU[8];
+    double trb = 0.0;
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++)
+        {
+            double te = gU[j * 3 + i] + gU[i * 3 + j];
+            if (i == j) te -= (2.0 / 3.0) * tr;
+            mub += te * u[i] * qb[j];
+            ub[i] += mu * te * qb[j];
+            const double teb = mu * u[i] * qb[j];
+            gUb[j * 3 + i] += teb;
+            gUb[i * 3 + j] += teb;
+            if (i == j) trb -= (2.0 / 3.0) * teb;
+        }
+    gUb[0] += trb; gUb[4] += trb; gUb[8] += trb;
+    if (vrel) pb -= vrel[0] * qb[0] + vrel[1] * qb[1] + vrel[2] * qb[2];
+}
+// Omega x (x - origin)
+DAB_HD void mrfVelocityAt(const MeshView& m, double x, double y, double z, double* v)
+{
+    const double r[3] = {x - m.mrfOrigin[0], y - m.mrfOrigin[1], z - m.mrfOrigin[2]};
+    const double* w = m.mrfOmega;
+    v[0] = w[1] * r[2] - w[2] * r[1];
+    v[1] = w[2] * r[0] - w[0] * r[2];
+    v[2] = w[0] * r[1] - w[1] * r[0];
+}
+
 // energy row: TRes = (EEqn & he), EEqn = div(phi,he) + div(phi,Ekp|K) - laplacian(alphaEff,he)
 template <int NF>
 struct cFwdE
@@ -382,6 +430,16 @@ struct cFwdE
         double gHc[3];
         for (int i = 0; i < 3; i++) gHc[i] = r.gHe[(size_t)i * nT + c];
         double EV = 0.0;
+        double twc[3] = {0.0, 0.0, 0.0}, gUt[9]; // turboH: the work vector of this cell
+        if (q.turboH)
+        {
+            for (int i = 0; i < 9; i++) gUt[i] = r.gU[(size_t)i * nT + c];
+            const double uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+            double vr[3];
+            const bool inZone = m.mrfCell && m.mrfCell[c];
+            if (inZone) mrfVelocityAt(m, m.Cx[c], m.Cy[c], m.Cz[c], vr);
+            turboWork(gUt, r.muE[c], uc, s.p[c], inZone ? vr : nullptr, twc);
+        }
         DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
@@ -420,6 +478,16 @@ struct cFwdE
                 const double wk = q.divEkp == DIV_LINEAR ? wc : wup;
                 const double Ekf = wk * Ekc + (1.0 - wk) * r.Ek[n];
                 EV += mf * (Ekf - Ekc);
+                if (q.turboH)
+                {
+                    double gn[9], twn[3], vr[3];
+                    for (int i = 0; i < 9; i++) gn[i] = r.gU[(size_t)i * nT + n];
+                    const double un[3] = {s.U[3 * n], s.U[3 * n + 1], s.U[3 * n + 2]};
+                    const bool inZone = m.mrfCell && m.mrfCell[n];
+                    if (inZone) mrfVelocityAt(m, m.Cx[n], m.Cy[n], m.Cz[n], vr);
+                    turboWork(gn, r.muE[n], un, s.p[n], inZone ? vr : nullptr, twn);
+                    EV -= fr.s * (m.Sx[f] * (wc * twc[0] + wn * twn[0]) + m.Sy[f] * (wc * twc[1] + wn * twn[1]) + m.Sz[f] * (wc * twc[2] + wn * twn[2]));
+                }
             }
             else
             {
@@ -429,6 +497,21 @@ struct cFwdE
                 const double sngH = (q.heIsE ? (q.Cp - q.Rg) : q.Cp) * bp.sngT;
                 EV += mf * heb - bp.aE * mS * sngH - mf * hec;
                 EV += mf * (bp.Ek - Ekc);
+                if (q.turboH)
+                {
+                    const double im = 1.0 / mS;
+                    const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
+                    double Gb[9], twb[3], vr[3];
+                    for (int j = 0; j < 3; j++)
+                    {
+                        const double nG = nh[0] * gUt[j * 3 + 0] + nh[1] * gUt[j * 3 + 1] + nh[2] * gUt[j * 3 + 2];
+                        for (int i = 0; i < 3; i++) Gb[j * 3 + i] = gUt[j * 3 + i] + nh[i] * (bp.bu.sng[j] - nG);
+                    }
+                    const bool onZone = m.mrfType && m.mrfType[f - m.nIF] != 0;
+                    if (onZone) mrfVelocityAt(m, m.Cfx[f], m.Cfy[f], m.Cfz[f], vr);
+                    turboWork(Gb, bp.muE, bp.bu.val, bp.p, onZone ? vr : nullptr, twb);
+                    EV -= m.Sx[f] * twb[0] + m.Sy[f] * twb[1] + m.Sz[f] * twb[2];
+                }
             }
         }
         if (m.fvS) // - fvSourceEnergy = -(fvSource & U)

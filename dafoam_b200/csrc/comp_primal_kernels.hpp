@@ -175,6 +175,16 @@ struct cEEqnAssemble
         double gHc[3];
         for (int i = 0; i < 3; i++) gHc[i] = r.gHe[(size_t)i * nT + c];
         double D0 = 0.0, sumOff = 0.0, X = 0.0, ic = 0.0, aic = 0.0;
+        double twc[3] = {0.0, 0.0, 0.0}, gUt[9]; // DATurboFoam enthalpy form: explicit - div(Teff & U) + div(p (U - URel))
+        if (q.turboH)
+        {
+            for (int i = 0; i < 9; i++) gUt[i] = r.gU[(size_t)i * nT + c];
+            const double uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+            double vr[3];
+            const bool inZone = m.mrfCell && m.mrfCell[c];
+            if (inZone) mrfVelocityAt(m, m.Cx[c], m.Cy[c], m.Cz[c], vr);
+            turboWork(gUt, r.muE[c], uc, s.p[c], inZone ? vr : nullptr, twc);
+        }
         for (int k = 0; k < m.maxCF; k++)
         {
             const FaceRef fr = faceOf(m, c, k);
@@ -190,6 +200,16 @@ struct cEEqnAssemble
             {
                 const int n = fr.n;
                 const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f], wn = 1.0 - wc;
+                if (q.turboH)
+                {
+                    double gn[9], twn[3], vr[3];
+                    for (int i = 0; i < 9; i++) gn[i] = r.gU[(size_t)i * nT + n];
+                    const double un[3] = {s.U[3 * n], s.U[3 * n + 1], s.U[3 * n + 2]};
+                    const bool inZone = m.mrfCell && m.mrfCell[n];
+                    if (inZone) mrfVelocityAt(m, m.Cx[n], m.Cy[n], m.Cz[n], vr);
+                    turboWork(gn, r.muE[n], un, s.p[n], inZone ? vr : nullptr, twn);
+                    X -= fr.s * (m.Sx[f] * (wc * twc[0] + wn * twn[0]) + m.Sy[f] * (wc * twc[1] + wn * twn[1]) + m.Sz[f] * (wc * twc[2] + wn * twn[2]));
+                }
                 const bool pos0 = s.phi[f] >= 0.0;
                 const double wup = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
                 const double wp = schE == DIV_LINEAR ? wc : wup;
@@ -229,6 +249,21 @@ struct cEEqnAssemble
                 D0 -= mf;
                 X += mf * bp.th.he - bp.aE * mS * sngH - icf * hec;
                 X += mf * (bp.Ek - Ekc);
+                if (q.turboH)
+                {
+                    const double im = 1.0 / mS;
+                    const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
+                    double Gb[9], twb[3], vr[3];
+                    for (int j = 0; j < 3; j++)
+                    {
+                        const double nG = nh[0] * gUt[j * 3 + 0] + nh[1] * gUt[j * 3 + 1] + nh[2] * gUt[j * 3 + 2];
+                        for (int i = 0; i < 3; i++) Gb[j * 3 + i] = gUt[j * 3 + i] + nh[i] * (bp.bu.sng[j] - nG);
+                    }
+                    const bool onZone = m.mrfType && m.mrfType[f - m.nIF] != 0;
+                    if (onZone) mrfVelocityAt(m, m.Cfx[f], m.Cfy[f], m.Cfz[f], vr);
+                    turboWork(Gb, bp.muE, bp.bu.val, bp.p, onZone ? vr : nullptr, twb);
+                    X -= m.Sx[f] * twb[0] + m.Sy[f] * twb[1] + m.Sz[f] * twb[2];
+                }
             }
         }
         if (m.fvS) X -= m.V[c] * (m.fvS[c] * s.U[3 * c] + m.fvS[(size_t)nC + c] * s.U[3 * c + 1] + m.fvS[(size_t)2 * nC + c] * s.U[3 * c + 2]);

@@ -524,6 +524,13 @@ struct cRevE
         const double qc = x.T[c] * (q.nrT ? 1.0 / m.V[c] : 1.0);
         double he2 = 0.0, aEb = 0.0, Ekb = 0.0, gHb[3] = {0, 0, 0};
         double Ub[3] = {0, 0, 0}, pb = 0.0, Tb = 0.0, ntb = 0.0, nutPb = 0.0;
+        double twb[3] = {0.0, 0.0, 0.0}, gUt[9], gUtb[9]; // turboH: adjoint of this cell's work vector, grad(U) and its adjoint
+        if (q.turboH)
+            for (int i = 0; i < 9; i++)
+            {
+                gUt[i] = r.gU[(size_t)i * nT + c];
+                gUtb[i] = 0.0;
+            }
         DAB_FACE_PREFETCH(NF)
         _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
         {
@@ -578,6 +585,14 @@ struct cRevE
                 const double wk = q.divEkp == DIV_LINEAR ? wc : wupc;
                 Ekb -= mf * (qc * (1.0 - wk) + qn * wk);
                 if (fr.s > 0) phib_acc += (qc * (1.0 - wk) + qn * wk) * (r.Ek[n] - Ekc);
+                if (q.turboH)
+                {
+                    // the cell's work vector enters row c and row n through this face with weight wc
+                    const double cf = -fr.s * wc * (qc - qn);
+                    twb[0] += cf * m.Sx[f];
+                    twb[1] += cf * m.Sy[f];
+                    twb[2] += cf * m.Sz[f];
+                }
             }
             else
             {
@@ -594,9 +609,39 @@ struct cRevE
                 he2 -= qc * mf;
                 Ekb -= qc * mf;
                 phib_acc += qc * (bp.th.he - hec + bp.Ek - Ekc);
+                if (q.turboH)
+                {
+                    const double im = 1.0 / mS;
+                    const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
+                    double Gb[9], Gbb[9], vr[3];
+                    for (int j = 0; j < 3; j++)
+                    {
+                        const double nG = nh[0] * gUt[j * 3 + 0] + nh[1] * gUt[j * 3 + 1] + nh[2] * gUt[j * 3 + 2];
+                        for (int i = 0; i < 3; i++)
+                        {
+                            Gb[j * 3 + i] = gUt[j * 3 + i] + nh[i] * (bp.bu.sng[j] - nG);
+                            Gbb[j * 3 + i] = 0.0;
+                        }
+                    }
+                    const bool onZone = m.mrfType && m.mrfType[f - m.nIF] != 0;
+                    if (onZone) mrfVelocityAt(m, m.Cfx[f], m.Cfy[f], m.Cfz[f], vr);
+                    const double qb3[3] = {-qc * m.Sx[f], -qc * m.Sy[f], -qc * m.Sz[f]};
+                    turboWorkAdj(Gb, bp.muE, bp.bu.val, onZone ? vr : nullptr, qb3, Gbb, ba.muE, ba.val, ba.p);
+                    boundaryGradAdj(nh, Gbb, gUtb, ba.sng);
+                }
                 boundaryPointAdj<true>(m, q, s, r, f, c, bp, ba, Ub, pb, Tb, ntb, nutPb);
             }
             if (fr.s > 0) y[offPhi + f] += phib_acc * q.sPhi * mS;
+        }
+        if (q.turboH)
+        {
+            const double uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
+            double vr[3], mub = 0.0;
+            const bool inZone = m.mrfCell && m.mrfCell[c];
+            if (inZone) mrfVelocityAt(m, m.Cx[c], m.Cy[c], m.Cz[c], vr);
+            turboWorkAdj(gUt, r.muE[c], uc, inZone ? vr : nullptr, twb, gUtb, mub, Ub, pb);
+            a.cMuE[c] += mub;
+            for (int i = 0; i < 9; i++) a.gUb[(size_t)i * nT + c] += gUtb[i];
         }
         a.cAE[c] = aEb;
         a.cHe[c] = he2;

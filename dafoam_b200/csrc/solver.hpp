@@ -383,9 +383,7 @@ struct Solver
             if (en != "sensibleInternalEnergy" && en != "sensibleEnthalpy") throw Error("thermophysicalProperties: unsupported energy " + en);
             if (trn != "const" && trn != "sutherland") throw Error("thermophysicalProperties: unsupported transport " + trn);
             par.heIsE = en == "sensibleInternalEnergy" ? 1 : 0;
-            if (solverName == "DATurboFoam" && !par.heIsE)
-                throw Error("DATurboFoam: the sensibleEnthalpy energy equation (viscous-work and p(U - URel) terms, "
-                            "DAResidualTurboFoam.C:119-121) is not built; use sensibleInternalEnergy");
+            par.turboH = (solverName == "DATurboFoam" && !par.heIsE) ? 1 : 0;
             par.sutherland = trn == "sutherland" ? 1 : 0;
             const Dict& mx = th.sub("mixture");
             par.Rg = 8314.4700665 / mx.sub("specie").scalar("molWeight");

@@ -161,6 +161,7 @@ struct Params
     int bcKindT[MAXP];
     double bcValT[MAXP];
     int rhoFrozen;            // primal loop only: the cell density is the stored (relaxed) field, not p/(R T)
+    int turboH;               // DATurboFoam with sensibleEnthalpy: - div(Teff & U) + div(p (U - URel)) in the energy row
 };
 
 // internal working state (ghost slots appended to the cell arrays)

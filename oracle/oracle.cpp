@@ -601,6 +601,7 @@ struct Case
         int heIsE = 1;      // energy variable: 1 sensibleInternalEnergy (e), 0 sensibleEnthalpy (h)
         int sutherland = 0; // transport: 0 const (mu, Pr), 1 sutherland (As, Ts)
         int divE = 0, divEkp = 0, nrT = 1;
+        int turbo = 0; // DATurboFoam: the sensibleEnthalpy energy equation carries the viscous-work and p(U - URel) terms
         double R = 287.0, Cp = 1005.0, mu = 1.8e-5, Pr = 0.7, Prt = 1.0, As = 1.4792e-6, Ts = 116.0, TRef = 298.15, sT = 1.0;
         std::vector<int> kindT;     // [nPatch]
         std::vector<double> valueT; // [nPatch]
@@ -1326,6 +1327,67 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
         }
         for (int c = 0; c < nC; c++) EEqn.src[c] -= dv[c];
     }
+    if (cp.turbo && !cp.heIsE)
+    {
+        // DAResidualTurboFoam.C:117-121 (the ternary binds the two extra terms to the enthalpy branch):
+        //   - fvc::div(Teff.T() & U) + fvc::div(p*(U - URel)),  Teff = -devRhoReff = muEff dev(twoSymm(grad U)),  Gauss linear
+        auto workVec = [&](const T G[3][3], const T& mu, const T* u, V3<T>& out) {
+            T tr = G[0][0] + G[1][1] + G[2][2];
+            for (int j = 0; j < 3; j++)
+            {
+                T a(0.0);
+                for (int i = 0; i < 3; i++)
+                {
+                    T te = G[i][j] + G[j][i];
+                    if (i == j) te -= (2.0 / 3.0) * tr;
+                    a += mu * te * u[i];
+                }
+                out[j] = a;
+            }
+        };
+        std::vector<V3<T>> qC(nC), qB(nBF), vC(nC), vB(nBF);
+        for (int c = 0; c < nC; c++)
+        {
+            T G[3][3], u[3];
+            for (int i = 0; i < 3; i++)
+            {
+                u[i] = U[(size_t)i * nC + c];
+                for (int j = 0; j < 3; j++) G[i][j] = GU(i, j, c);
+            }
+            workVec(G, muE[c], u, qC[c]);
+            vC[c] = (cs.mrf.on && cs.mrf.cell[c]) ? mrfVelocity(cs, g.C[c]) : V3<T>();
+        }
+        for (int b = 0; b < nBF; b++)
+        {
+            const int f = nIF + b, c = t.own[f];
+            V3<T> nh = (T(1.0) / g.magSf[f]) * g.Sf[f];
+            T Gb[3][3], u[3];
+            for (int j = 0; j < 3; j++)
+            {
+                T nG = nh[0] * GU(0, j, c) + nh[1] * GU(1, j, c) + nh[2] * GU(2, j, c);
+                for (int i = 0; i < 3; i++) Gb[i][j] = GU(i, j, c) + nh[i] * (bU.sng[bU.at(j, b)] - nG);
+                u[j] = bU.val[bU.at(j, b)];
+            }
+            workVec(Gb, muEB[b], u, qB[b]);
+            // U - URel on the boundary (MRFZoneDF::makeRelative): Omega x r on the included and excluded faces of the zone
+            vB[b] = (cs.mrf.on && cs.mrf.faceType[f] != 0) ? mrfVelocity(cs, g.Cf[f]) : V3<T>();
+        }
+        for (int f = 0; f < nF; f++)
+        {
+            const int o = t.own[f];
+            T fl(0.0);
+            if (f < nIF)
+            {
+                const int n = t.nei[f];
+                for (int k = 0; k < 3; k++)
+                    fl += g.Sf[f][k] * (g.w[f] * (qC[o][k] - p[o] * vC[o][k]) + (1.0 - g.w[f]) * (qC[n][k] - p[n] * vC[n][k]));
+            }
+            else
+                for (int k = 0; k < 3; k++) fl += g.Sf[f][k] * (qB[f - nIF][k] - bP.val[f - nIF] * vB[f - nIF][k]);
+            EEqn.src[o] += fl;
+            if (f < nIF) EEqn.src[t.nei[f]] -= fl;
+        }
+    }
     fvmLaplacian(EEqn, t, g, -1.0, aE, aEB, bHe, gradHe, false);
     if (!fvS.empty())
         for (int c = 0; c < nC; c++) // - fvSourceEnergy = -(fvSource & U)
@@ -1629,6 +1691,13 @@ void orc_set_compressible(void* h, const double* dpar, const int* ipar, const in
     c.heIsE = ipar[0]; c.sutherland = ipar[1]; c.divE = ipar[2]; c.divEkp = ipar[3]; c.nrT = ipar[4];
     c.kindT.assign(kindT, kindT + cs->t.nPatch);
     c.valueT.assign(valueT, valueT + cs->t.nPatch);
+    cs->recorded = false;
+}
+
+void orc_set_turbo(void* h, int on)
+{
+    Case* cs = (Case*)h;
+    cs->comp.turbo = on;
     cs->recorded = false;
 }
 

@@ -189,6 +189,10 @@ class Oracle:
         self._keep_disks = a
         lib().orc_set_fvsource(self.h, C.c_int(len(rows)), _p(a))
 
+    def set_turbo(self, on=True):
+        """DATurboFoam's energy equation (the enthalpy form carries the viscous-work and p(U - URel) terms)."""
+        lib().orc_set_turbo(self.h, C.c_int(int(on)))
+
     def set_mrf(self, mesh, mrf):
         """One MRF zone (see dafoam_b200.cases.write_mrf for the dict)."""
         axis = np.asarray(mrf["axis"], dtype=np.float64)

@@ -49,15 +49,16 @@ NRES_C = ("URes", "pRes", "TRes", "nuTildaRes", "phiRes")
 NS_I = dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0)
 
 
-def setup_mrf(solver, lib_path, function=None, omega=40.0):
+def setup_mrf(solver, lib_path, function=None, omega=40.0, energy="sensibleInternalEnergy"):
     import tempfile
     from dafoam_b200.pyDASolvers import pyDASolvers
     mesh = cases.naca0012_ogrid(ni=24, nj=12, nk=2)
     comp = solver != "DASimpleFoam"
     if comp:
-        th = cases.default_thermo()
+        th = cases.default_thermo(energy=energy)
         bcs = cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0)))
         orc = Oracle(mesh, bcs, normalizeStates=NS_C, normalizeResiduals=NRES_C, thermo=th, divU="linearUpwindV")
+        orc.set_turbo(solver == "DATurboFoam")
         W = synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=th)
         opts = dict(normalizeStates=NS_C, normalizeResiduals=list(NRES_C))
         kw = dict(thermo=th)
@@ -79,12 +80,19 @@ def setup_mrf(solver, lib_path, function=None, omega=40.0):
 
 def check_engine(lib_path, tol=1e-10):
     from tests.common import rel_err
-    for solver in ("DASimpleFoam", "DARhoSimpleFoam", "DATurboFoam"):
-        mesh, orc, sol, W = setup_mrf(solver, lib_path)
+    for solver, energy in (("DASimpleFoam", None), ("DARhoSimpleFoam", "sensibleInternalEnergy"), ("DATurboFoam", "sensibleInternalEnergy"),
+                           ("DATurboFoam", "sensibleEnthalpy")):
+        mesh, orc, sol, W = setup_mrf(solver, lib_path, energy=energy)
         n = orc.ndof
         assert sol.getNLocalAdjointStates() == n
         sol.updateOFFields(W)
         nC = mesh.n_cells
+        if energy == "sensibleEnthalpy":
+            # the viscous-work and p(U - URel) terms of DATurboFoam's enthalpy equation are really there
+            Rt = orc.residual(W)
+            orc.set_turbo(False)
+            assert np.linalg.norm((Rt - orc.residual(W))[4 * nC:5 * nC]) > 1e-3 * np.linalg.norm(Rt[4 * nC:5 * nC])
+            orc.set_turbo(True)
         ns = (n - mesh.n_faces) // nC
         segs = [("U", 0, 3 * nC)] + [("s%d" % k, k * nC, (k + 1) * nC) for k in range(3, ns)] + [("phi", ns * nC, n)]
         for isPC in (0, 1):
@@ -146,8 +154,9 @@ def check_function_volcoord_primal(lib_path, tol=1e-10):
     mask = mask.ravel()
     assert rel_err(prod[mask], ref[mask]) < 1e-7, rel_err(prod[mask], ref[mask])
     # SIMPLE with the Coriolis source, the rotating wall and the relative fluxes: its fixed point is the root of the same R(W)
-    for solver, its in (("DASimpleFoam", 1000), ("DATurboFoam", 4000)):
-        mesh, orc, sol, W = setup_mrf(solver, lib_path, omega=0.3)
+    for solver, its, energy in (("DASimpleFoam", 1000, None), ("DATurboFoam", 4000, "sensibleInternalEnergy"),
+                                ("DATurboFoam", 4000, "sensibleEnthalpy")):
+        mesh, orc, sol, W = setup_mrf(solver, lib_path, omega=0.3, energy=energy)
         sol.updateDAOption(dict(primalMinResTol=1e-9, primalMaxIters=its))
         n = orc.ndof
         W0 = np.zeros(n)
