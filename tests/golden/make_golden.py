@@ -43,18 +43,33 @@ def golden_spec(kind):
     if kind == "nacacomp":
         return dict(mesh=mesh, bcs=cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0))), fpatch="wing", name="naca_rhosimple_24x12",
                     solver="DARhoSimpleFoam", ras="SpalartAllmaras", thermo=cases.default_thermo(), ns=NS_COMP, nres=NRES_COMP)
+    from tests.common import mrf_zone
+    if kind == "nacamrf":
+        # DASimpleFoam with an MRF zone around the (rotating) aerofoil wall
+        return dict(mesh=mesh, bcs=cases.default_bcs_naca(), fpatch="wing", name="naca_mrf_24x12", solver="DASimpleFoam", ras="SpalartAllmaras",
+                    thermo=None, ns=NORM_STATES, nres=("URes", "pRes", "nuTildaRes", "phiRes"), mrf=mrf_zone(mesh, omega=25.0))
+    if kind == "nacaturbo":
+        # DATurboFoam, enthalpy form (viscous work + p(U - URel) in the energy row), sutherland transport, MRF zone
+        return dict(mesh=mesh, bcs=cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0))), fpatch="wing", name="naca_turbo_h_24x12",
+                    solver="DATurboFoam", ras="SpalartAllmaras", thermo=cases.default_thermo(energy="sensibleEnthalpy", transport="sutherland"),
+                    ns=NS_COMP, nres=NRES_COMP, mrf=mrf_zone(mesh, omega=25.0))
     raise ValueError(kind)
 
 
 def oracle_of(spec):
-    return Oracle(spec["mesh"], spec["bcs"], normalizeStates=spec["ns"], normalizeResiduals=spec["nres"], rasModel=spec["ras"], thermo=spec["thermo"])
+    orc = Oracle(spec["mesh"], spec["bcs"], normalizeStates=spec["ns"], normalizeResiduals=spec["nres"], rasModel=spec["ras"], thermo=spec["thermo"])
+    if spec["solver"] == "DATurboFoam":
+        orc.set_turbo(True)
+    if spec.get("mrf"):
+        orc.set_mrf(spec["mesh"], spec["mrf"])
+    return orc
 
 
 def state_for(kind, mesh, orc):
-    if kind == "nacacomp":
+    if kind in ("nacacomp", "nacaturbo"):
         from oracle.pyoracle import synthetic_state
         return synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=cases.default_thermo(), noise=0.01)
-    if kind == "nacafv3":
+    if kind in ("nacafv3", "nacamrf"):
         return cases.boundary_layer_state(mesh, orc.geometry("yWall"))
     if kind == "naca":
         return cases.boundary_layer_state(mesh, orc.geometry("yWall"))
@@ -83,7 +98,7 @@ def compute(kind):
 
 
 if __name__ == "__main__":
-    only = sys.argv[1:] or ("naca", "channel", "nacafv3", "nacacomp")
+    only = sys.argv[1:] or ("naca", "channel", "nacafv3", "nacacomp", "nacamrf", "nacaturbo")
     for kind in only:
         name, data = compute(kind)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)

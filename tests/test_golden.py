@@ -18,7 +18,7 @@ from tests.golden.make_golden import golden_spec, oracle_of
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-KINDS = ["naca", "channel", "nacafv3", "nacacomp"]
+KINDS = ["naca", "channel", "nacafv3", "nacacomp", "nacamrf", "nacaturbo"]
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -41,6 +41,8 @@ def engine_vs_golden(kind, lib_path, tol=1e-11):
     kw = dict(ras_model=spec["ras"])
     if spec["thermo"] is not None:
         kw["thermo"] = spec["thermo"]
+    if spec.get("mrf"):
+        kw["mrf"] = spec["mrf"]
     cases.write_case(d, mesh, bcs, **kw)
     fn = {"F": {"type": "force", "source": "patchToFace", "patches": [fpatch], "directionMode": "fixedDirection",
                 "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
