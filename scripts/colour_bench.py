@@ -1,0 +1,38 @@
+"""Adjoint solve for several multicolour-ILU ordering radii (adjEqnOption.pcColourRadius) on the bench O-grid.
+env: CB_CELLS, CB_RADII="0,2,4", CB_LIB (library path; default = the CUDA build), CB_AGG (coarse aggregates), CB_RESTART"""
+import json, os, sys, tempfile, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import pyDASolvers, Mat, KSP
+
+cells = int(os.environ.get("CB_CELLS", 250000))
+nj = max(8, int(round((cells / 2.0) ** 0.5 / 2.0)) * 2)
+mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1)
+d = tempfile.mkdtemp(prefix="dab_cb_")
+cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
+fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
+adj = dict(gmresRelTol=1e-6, gmresMaxIters=3000, gmresRestart=int(os.environ.get("CB_RESTART", 1500)), printInfo=0, pcConLevel=3,
+           coarseAggregates=int(os.environ.get("CB_AGG", 1000)))
+opts = dict(normalizeStates=dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0), function=fn, adjEqnOption=adj)
+sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=os.environ.get("CB_LIB") or None)
+n = sol.getNLocalAdjointStates()
+y = np.zeros(sol.getNLocalCells()); sol.getOFField("yWall", "scalar", y)
+W = cases.boundary_layer_state(mesh, y, noise=0.001)
+sol.updateOFFields(W)
+dFdW = np.zeros(n)
+sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+out = []
+for r in [int(x) for x in os.environ.get("CB_RADII", "0,2,4").split(",")]:
+    sol.updateDAOption(dict(opts, adjEqnOption=dict(adj, pcColourRadius=r)))
+    pc, ksp = Mat(), KSP()
+    t0 = time.time(); sol.calcdRdWT(1, pc); sol.createMLRKSPMatrixFree(pc, ksp); t_pc = time.time() - t0
+    psi = np.zeros(n)
+    t0 = time.time(); fail = sol.solveLinearEqn(ksp, dFdW, psi); t = time.time() - t0
+    st = ksp.stats
+    res = dict(cells=sol.getNLocalCells(), radius=r, fail=fail, iterations=st.iterations, pc_s=round(t_pc, 3), solve_s=round(t, 3),
+               gmres_device_s=round(st.solve_seconds, 3), rel_residual=st.final_residual / st.initial_residual)
+    print(json.dumps(res), flush=True)
+    out.append(res)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/colour_bench_%d.json" % cells, "w"), indent=1)
