@@ -183,6 +183,75 @@ int dab_write_fields(dab_solver* s, double write_time)
     DAB_CATCH
 }
 
+int dab_check_mesh(dab_solver* s, double max_non_orth, double max_skewness, double max_aspect_ratio, int max_incorrectly_oriented_faces,
+                   int* mesh_ok, double* report)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(mesh_ok, "mesh_ok");
+    const HostMesh::Quality q = s->s.hm.checkMesh(max_non_orth, max_skewness, max_aspect_ratio, max_incorrectly_oriented_faces);
+    *mesh_ok = q.nFailedChecks == 0 ? 1 : 0;
+    if (report)
+    {
+        const double r[DAB_CHECK_MESH_REPORT] = {q.maxNonOrth, q.avgNonOrth, q.maxSkewness, q.maxAspectRatio, q.minVolume, q.minFaceArea,
+                                                 q.maxOpenness, (double)q.nSevereNonOrth, (double)q.nErrorNonOrth,
+                                                 (double)q.nNegativePyramids, (double)q.nFailedChecks};
+        for (int i = 0; i < DAB_CHECK_MESH_REPORT; i++) report[i] = r[i];
+    }
+    DAB_CATCH
+}
+
+int dab_read_state_vars(dab_solver* s, double time_val)
+{
+    DAB_TRY
+    need(s, "solver");
+    s->s.readStateVars(timeNameOf(time_val));
+    DAB_CATCH
+}
+
+int dab_read_mesh_points(dab_solver* s, double time_val)
+{
+    DAB_TRY
+    need(s, "solver");
+    s->s.readMeshPoints(timeNameOf(time_val));
+    DAB_CATCH
+}
+
+int dab_write_mesh_points(dab_solver* s, const double* points, const char* dir_name)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(dir_name, "dir_name");
+    s->s.writeMeshPoints(points ? points : s->s.hm.points.data(), dir_name);
+    DAB_CATCH
+}
+
+int dab_write_sens_map_surface(dab_solver* s, const char* name, const double* dfdxs, const double* xs, int size, double time_name,
+                               double* min_distance_norm)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(name, "name");
+    need(dfdxs, "dFdXs");
+    need(xs, "Xs");
+    const double nrm = s->s.writeSensMapSurface(name, dfdxs, xs, size, timeNameOf(time_name));
+    if (min_distance_norm) *min_distance_norm = nrm;
+    DAB_CATCH
+}
+
+int dab_write_sens_map_field(dab_solver* s, const char* name, const double* dfdfield, const char* field_type, double time_name)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(name, "name");
+    need(dfdfield, "dFdField");
+    need(field_type, "field_type");
+    const std::string ft(field_type);
+    if (ft != "scalar" && ft != "vector") throw Error("writeSensMapField: fieldType can be either scalar or vector");
+    s->s.writeSensMapField(name, dfdfield, ft == "vector", timeNameOf(time_name));
+    DAB_CATCH
+}
+
 int dab_get_of_field(dab_solver* s, const char* name, const char* type, double* field)
 {
     DAB_TRY

@@ -279,6 +279,122 @@ struct HostMesh
             yWall[c] = std::sqrt(best);
         }
     }
+    // Mesh quality report of DACheckMesh::run (reference src/adjoint/DACheckMesh/DACheckMesh.C:45-79, DACheckGeometry.C:256-478;
+    // OpenFOAM primitiveMeshCheck semantics): the checks that count as failures there - open boundary, open cells /
+    // aspect ratio above the threshold, zero face areas, non-positive cell volumes, faces more than 90 degrees non-orthogonal,
+    // more than maxIncorrectlyOrientedFaces negative face pyramids, skewness above the threshold.  Severe non-orthogonality
+    // (> maxNonOrth) is reported but, as in OpenFOAM, is not a failure.
+    struct Quality
+    {
+        double maxNonOrth = 0, avgNonOrth = 0, maxSkewness = 0, maxAspectRatio = 0, minVolume = 0, minFaceArea = 0, maxOpenness = 0;
+        int nSevereNonOrth = 0, nErrorNonOrth = 0, nNegativePyramids = 0, nFailedChecks = 0;
+    };
+    Quality checkMesh(double maxNonOrthDeg, double maxSkew, double maxAspect, int maxBadPyramids) const
+    {
+        const double SMALL = 1e-15, VSMALL = 1e-300, ROOTVSMALL = 1e-150, PI = 3.14159265358979323846;
+        Quality q;
+        q.minVolume = 1e300;
+        q.minFaceArea = 1e300;
+        // closed boundary
+        double sb[3] = {0, 0, 0}, smb = 0;
+        for (int f = nIF; f < nF; f++)
+        {
+            if (patchGeomOfFace(f) == PG_PROCESSOR) continue;
+            for (int k = 0; k < 3; k++) sb[k] += Sf[k][f];
+            smb += magSf[f];
+        }
+        const bool openBoundary = std::sqrt(sb[0] * sb[0] + sb[1] * sb[1] + sb[2] * sb[2]) > 1e-6 * smb;
+        // closed cells + aspect ratio
+        std::vector<double> sumC((size_t)3 * nC, 0.0), sumM((size_t)3 * nC, 0.0);
+        for (int f = 0; f < nF; f++)
+        {
+            q.minFaceArea = std::min(q.minFaceArea, magSf[f]);
+            const int o = own[f];
+            if (o < nC)
+                for (int k = 0; k < 3; k++) { sumC[(size_t)3 * o + k] += Sf[k][f]; sumM[(size_t)3 * o + k] += std::fabs(Sf[k][f]); }
+            if (f < nIF && nei[f] < nC)
+                for (int k = 0; k < 3; k++) { sumC[(size_t)3 * nei[f] + k] -= Sf[k][f]; sumM[(size_t)3 * nei[f] + k] += std::fabs(Sf[k][f]); }
+        }
+        int nOpen = 0, nAspect = 0;
+        for (int c = 0; c < nC; c++)
+        {
+            double open = 0, mn = 1e300, mx = 0, sm = 0;
+            for (int k = 0; k < 3; k++)
+            {
+                open = std::max(open, std::fabs(sumC[(size_t)3 * c + k]) / (sumM[(size_t)3 * c + k] + ROOTVSMALL));
+                mn = std::min(mn, sumM[(size_t)3 * c + k]);
+                mx = std::max(mx, sumM[(size_t)3 * c + k]);
+                sm += sumM[(size_t)3 * c + k];
+            }
+            double ar = mx / (mn + ROOTVSMALL);
+            ar = std::max(ar, sm / 6.0 / std::pow(std::max(ROOTVSMALL, V[c]), 2.0 / 3.0));
+            q.maxOpenness = std::max(q.maxOpenness, open);
+            q.maxAspectRatio = std::max(q.maxAspectRatio, ar);
+            q.minVolume = std::min(q.minVolume, V[c]);
+            if (open > 1e-6) nOpen++;
+            if (ar > maxAspect) nAspect++;
+        }
+        // orthogonality of internal faces
+        const double severe = std::cos(maxNonOrthDeg * PI / 180.0);
+        double sumOrtho = 0;
+        double minOrtho = 1.0;
+        for (int f = 0; f < nIF; f++)
+        {
+            const int o = own[f], n = nei[f];
+            double d[3], dd = 0, ds = 0;
+            for (int k = 0; k < 3; k++) { d[k] = C[k][n] - C[k][o]; dd += d[k] * d[k]; ds += d[k] * Sf[k][f]; }
+            const double ortho = ds / (std::sqrt(dd) * magSf[f] + VSMALL);
+            if (ortho < severe) { if (ortho > SMALL) q.nSevereNonOrth++; else q.nErrorNonOrth++; }
+            minOrtho = std::min(minOrtho, ortho);
+            sumOrtho += ortho;
+        }
+        if (nIF > 0)
+        {
+            q.maxNonOrth = std::acos(std::max(-1.0, std::min(1.0, minOrtho))) * 180.0 / PI;
+            q.avgNonOrth = std::acos(std::max(-1.0, std::min(1.0, sumOrtho / nIF))) * 180.0 / PI;
+        }
+        // face pyramids and skewness
+        for (int f = 0; f < nF; f++)
+        {
+            const int o = own[f];
+            double cpf[3], pyr = 0;
+            for (int k = 0; k < 3; k++) { cpf[k] = Cf[k][f] - C[k][o]; pyr += Sf[k][f] * cpf[k]; }
+            bool bad = pyr / 3.0 < -SMALL;
+            double d[3], sd = 0, sc = 0, dm = 0;
+            if (f < nIF)
+            {
+                const int n = nei[f];
+                double pn = 0;
+                for (int k = 0; k < 3; k++) pn += Sf[k][f] * (C[k][n] - Cf[k][f]);
+                bad = bad || pn / 3.0 < -SMALL;
+                for (int k = 0; k < 3; k++) d[k] = C[k][n] - C[k][o];
+            }
+            else
+            {
+                double nc = 0;
+                for (int k = 0; k < 3; k++) nc += Sf[k][f] / magSf[f] * cpf[k];
+                for (int k = 0; k < 3; k++) d[k] = Sf[k][f] / magSf[f] * nc;
+            }
+            if (bad) q.nNegativePyramids++;
+            for (int k = 0; k < 3; k++) { sd += Sf[k][f] * d[k]; sc += Sf[k][f] * cpf[k]; dm += d[k] * d[k]; }
+            double sv[3], svm = 0;
+            for (int k = 0; k < 3; k++) { sv[k] = cpf[k] - sc / (sd + ROOTVSMALL) * d[k]; svm += sv[k] * sv[k]; }
+            svm = std::sqrt(svm);
+            double fd = (f < nIF ? 0.2 : 0.4) * std::sqrt(dm) + ROOTVSMALL;
+            for (int i = fOff[f]; i < fOff[f + 1]; i++)
+            {
+                double t = 0;
+                for (int k = 0; k < 3; k++) t += sv[k] / (svm + ROOTVSMALL) * (points[(size_t)3 * fLab[i] + k] - Cf[k][f]);
+                fd = std::max(fd, std::fabs(t));
+            }
+            q.maxSkewness = std::max(q.maxSkewness, svm / fd);
+        }
+        q.nFailedChecks = (openBoundary ? 1 : 0) + (nOpen > 0 ? 1 : 0) + (nAspect > 0 ? 1 : 0) + (q.minFaceArea < VSMALL ? 1 : 0)
+            + (q.minVolume < VSMALL ? 1 : 0) + (q.nErrorNonOrth > 0 ? 1 : 0) + (q.nNegativePyramids > maxBadPyramids ? 1 : 0)
+            + (q.maxSkewness > maxSkew ? 1 : 0);
+        return q;
+    }
+    int patchGeomOfFace(int f) const { return patchGeom[bPatch[f - nIF]]; }
 };
 
 } // namespace dab

@@ -932,12 +932,21 @@ struct Solver
     }
 
     // initial states from the 0/ files (DASimpleFoam::initSolver createFieldsSimple.H role); phi = linear-interpolated U . Sf
-    void initialStates(const std::string&)
+    // timeName != "0": DASolver::readStateVars (DASolver.C readStateVars role) - the internal fields (and phi, when written) of
+    // <case>/<timeName>/ replace the states; the boundary conditions stay those of 0/
+    void initialStates(const std::string&, const std::string& timeName = "0")
     {
         const int nC = hm.nC, nF = hm.nF, nIF = hm.nIF;
         std::vector<double> W(nDof(), 0.0);
+        std::map<std::string, Dict> timeDicts;
         auto internal = [&](const std::string& name, int nc, std::vector<double>& out) {
-            const Dict& d = fieldDicts.at(name);
+            if (timeName != "0")
+            {
+                const std::string path = caseDirectory + "/" + timeName + "/" + name;
+                if (!fileExists(path)) throw Error("readStateVars: " + path + " does not exist");
+                timeDicts[name] = readDict(path);
+            }
+            const Dict& d = timeName != "0" ? timeDicts.at(name) : fieldDicts.at(name);
             const auto& t = d.tokens("internalField");
             const int nT = hm.nCtot;
             out.assign((size_t)nc * nT, 0.0);
@@ -1009,9 +1018,9 @@ struct Solver
             }
         }
         // a flux field written by a previous run (writeFields / OpenFOAM's own phi) takes precedence over the interpolated one
-        if (nRanks == 1 && fileExists(caseDirectory + "/0/phi"))
+        if (nRanks == 1 && fileExists(caseDirectory + "/" + timeName + "/phi"))
         {
-            Dict d = readDict(caseDirectory + "/0/phi");
+            Dict d = readDict(caseDirectory + "/" + timeName + "/phi");
             auto listOf = [&](const std::vector<std::string>& t, size_t n, std::vector<double>& out) {
                 out.clear();
                 if (!t.empty() && t[0] == "uniform")
@@ -1022,7 +1031,7 @@ struct Solver
                 size_t i = 0;
                 while (i < t.size() && t[i] != "(") i++;
                 for (i++; i < t.size() && t[i] != ")"; i++) out.push_back(atof(t[i].c_str()));
-                if (out.size() != n) throw Error("0/phi: a list has " + std::to_string(out.size()) + " entries, expected " + std::to_string(n));
+                if (out.size() != n) throw Error(timeName + "/phi: a list has " + std::to_string(out.size()) + " entries, expected " + std::to_string(n));
             };
             std::vector<double> v;
             listOf(d.tokens("internalField"), (size_t)nIF, v);
@@ -1810,6 +1819,121 @@ struct Solver
             patches(o.f, true, W + off);
         }
     }
+
+    // writeSensMapField (DASolver.C:3962-4053): a cell field of derivatives as a dimensionless vol field <name> under <case>/<timeName>/,
+    // boundary patches fixedValue zero
+    void writeSensMapField(const std::string& name, const double* v, bool vector, const std::string& timeName) const
+    {
+        if (comm.active()) throw Error("field output runs on one GPU in this build");
+        const std::string dir = caseDirectory + "/" + timeName;
+        ::mkdir(dir.c_str(), 0755);
+        FILE* f = fopen((dir + "/" + name).c_str(), "w");
+        if (!f) throw Error("cannot write " + dir + "/" + name);
+        fprintf(f, "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class %s;\n    location \"%s\";\n    object %s;\n}\n\n"
+                   "dimensions [0 0 0 0 0 0 0];\n\n", vector ? "volVectorField" : "volScalarField", timeName.c_str(), name.c_str());
+        fprintf(f, "internalField nonuniform List<%s> %d\n(\n", vector ? "vector" : "scalar", hm.nC);
+        for (int c = 0; c < hm.nC; c++)
+        {
+            if (vector) fprintf(f, "(%.17g %.17g %.17g)\n", v[3 * c], v[3 * c + 1], v[3 * c + 2]);
+            else fprintf(f, "%.17g\n", v[c]);
+        }
+        fprintf(f, ");\n\nboundaryField\n{\n");
+        for (const PatchDef& p : hm.patches)
+            fprintf(f, "    %s\n    {\n        type fixedValue;\n        value uniform %s;\n    }\n", p.name.c_str(), vector ? "(0 0 0)" : "0");
+        fprintf(f, "}\n");
+        fclose(f);
+    }
+
+    // writeSensMapSurface (DASolver.C:3840-3960): every point of every wall face takes the derivative of the closest design-surface
+    // point; a face holds the sum over its points divided by 3 (the reference divides by vector::size(), not by the point count).
+    // Returns the norm of the closest distances the reference prints.
+    double writeSensMapSurface(const std::string& name, const double* dFdXs, const double* Xs, int size, const std::string& timeName) const
+    {
+        if (comm.active()) throw Error("field output runs on one GPU in this build");
+        const int nS = (int)std::lround(size / 3.0);
+        if (nS <= 0) throw Error("writeSensMapSurface: empty surface");
+        std::vector<double> sens((size_t)3 * hm.nBF, 0.0);
+        double norm2 = 0.0;
+        for (size_t ip = 0; ip < hm.patches.size(); ip++)
+        {
+            if (hm.patchGeom[ip] != PG_WALL) continue;
+            const PatchDef& p = hm.patches[ip];
+            for (int i = 0; i < p.size; i++)
+            {
+                const int f = p.start + i;
+                for (int q = hm.fOff[f]; q < hm.fOff[f + 1]; q++)
+                {
+                    const int pt = hm.fLab[q];
+                    double best = 9999999.0;
+                    int bj = -1;
+                    for (int j = 0; j < nS; j++)
+                    {
+                        double d2 = 0.0;
+                        for (int k = 0; k < 3; k++) { const double d = Xs[3 * j + k] - hm.points[(size_t)3 * pt + k]; d2 += d * d; }
+                        const double d = std::sqrt(d2);
+                        if (d < best) { best = d; bj = j; }
+                    }
+                    if (bj < 0) throw Error("writeSensMapSurface: no surface point within 9999999 of a wall point");
+                    norm2 += best * best;
+                    for (int k = 0; k < 3; k++) sens[(size_t)3 * (f - hm.nIF) + k] += dFdXs[3 * bj + k];
+                }
+                for (int k = 0; k < 3; k++) sens[(size_t)3 * (f - hm.nIF) + k] /= 3.0;
+            }
+        }
+        const std::string dir = caseDirectory + "/" + timeName;
+        ::mkdir(dir.c_str(), 0755);
+        FILE* f = fopen((dir + "/" + name).c_str(), "w");
+        if (!f) throw Error("cannot write " + dir + "/" + name);
+        fprintf(f, "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class volVectorField;\n    location \"%s\";\n    object %s;\n}\n\n"
+                   "dimensions [0 0 0 0 0 0 0];\n\ninternalField uniform (0 0 0);\n\nboundaryField\n{\n", timeName.c_str(), name.c_str());
+        for (size_t ip = 0; ip < hm.patches.size(); ip++)
+        {
+            const PatchDef& p = hm.patches[ip];
+            fprintf(f, "    %s\n    {\n        type fixedValue;\n", p.name.c_str());
+            if (hm.patchGeom[ip] == PG_WALL)
+            {
+                fprintf(f, "        value nonuniform List<vector> %d(", p.size);
+                for (int i = 0; i < p.size; i++)
+                {
+                    const double* v = &sens[(size_t)3 * (p.start + i - hm.nIF)];
+                    fprintf(f, "%s(%.17g %.17g %.17g)", i ? " " : "", v[0], v[1], v[2]);
+                }
+                fprintf(f, ");\n");
+            }
+            else
+                fprintf(f, "        value uniform (0 0 0);\n");
+            fprintf(f, "    }\n");
+        }
+        fprintf(f, "}\n");
+        fclose(f);
+        return std::sqrt(norm2);
+    }
+
+    // writeMeshPoints (pyDASolvers.pyx:388-392) / writeCurrentMeshPointsToConstant / writeFailedMesh: <case>/<dirName>/polyMesh/points
+    void writeMeshPoints(const double* pts, const std::string& dirName) const
+    {
+        if (comm.active()) throw Error("mesh output runs on one GPU in this build");
+        const std::string d1 = caseDirectory + "/" + dirName, d2 = d1 + "/polyMesh";
+        ::mkdir(d1.c_str(), 0755);
+        ::mkdir(d2.c_str(), 0755);
+        FILE* f = fopen((d2 + "/points").c_str(), "w");
+        if (!f) throw Error("cannot write " + d2 + "/points");
+        fprintf(f, "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class vectorField;\n    location \"%s/polyMesh\";\n    object points;\n}\n\n%d\n(\n",
+                dirName.c_str(), hm.nP);
+        for (int i = 0; i < hm.nP; i++) fprintf(f, "(%.17g %.17g %.17g)\n", pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        fprintf(f, ")\n");
+        fclose(f);
+    }
+    // readMeshPoints (pyDASolvers.pyx:385-386): the points written under a time directory become the mesh
+    void readMeshPoints(const std::string& timeName)
+    {
+        std::vector<double> pts;
+        readVectorField(caseDirectory + "/" + timeName + "/polyMesh/points", pts);
+        if (pts.size() != hm.points.size()) throw Error("readMeshPoints: " + timeName + "/polyMesh/points has the wrong size");
+        updateMesh(pts.data());
+    }
+    // readStateVars (pyDASolvers.pyx:382-383): the fields of a time directory become the states
+    void readStateVars(const std::string& timeName) { initialStates(caseDirectory, timeName); }
 
     // ---- mesh coordinates as an input (volCoord) ------------------------------------------------------
     VolCoord volc;

@@ -38,6 +38,10 @@ class Error(Exception):
     """Fatal error of the wrapper (reference dafoam/pyDAFoam.py:2296-2316)."""
 
 
+class AnalysisError(Exception):
+    """OpenMDAO's AnalysisError role (reference mphys_dafoam.py:329, 346, 557): a recoverable failure the optimiser may step back from."""
+
+
 class PYDAFOAM:
     def __init__(self, comm=None, options=None, caseDir=".", device=0, _lib_path=None):
         """options: the daOptions dict of a run script; caseDir replaces the reference's implicit os.getcwd().
@@ -86,6 +90,24 @@ class PYDAFOAM:
         self.nSolvePrimals += 1
         self._pcAge += 1  # the preconditioner now belongs to an earlier design: refreshed every adjPCLag (below)
         self._psi = {}
+
+    def solve_nonlinear(self, inputs=None):
+        """The body of DAFoamSolver.solve_nonlinear (reference mphys_dafoam.py:314-368) without the OpenMDAO vectors: assign the
+        solver inputs, refuse a mesh that fails checkMesh (the failed mesh is written for inspection), honour prepareCaseOnly,
+        solve the primal, raise AnalysisError when it fails, print the residual statistics, and return the states."""
+        if inputs:
+            self.set_solver_input(inputs)
+        if self.solver.checkMesh() != 1:
+            self.solver.writeFailedMesh()
+            raise AnalysisError("Mesh quality error!")
+        if self.options.get("prepareCaseOnly", False):
+            self.solver.writeCurrentMeshPointsToConstant()
+            return None
+        self()
+        if self.primalFail != 0:
+            raise AnalysisError("Primal solution failed!")
+        self.solver.calcPrimalResidualStatistics("print")
+        return self.getStates()
 
     def evalFunctions(self, funcs):
         """funcs[name] = value for every entry of the `function` option (reference pyDAFoam.py:917-939)."""

@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import time
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -128,6 +129,7 @@ class pyDASolvers:
                                 C.c_int(device), C.c_int(rank), C.c_int(nRanks), uid, C.byref(self._h))
         self._raise(rc)
         self._initialised = False
+        self._t0Clock, self._t0Cpu = time.time(), time.process_time()
 
     # ---- plumbing
     def _raise(self, rc):
@@ -202,6 +204,7 @@ class pyDASolvers:
         st = PrimalStats()
         self._raise(self._L.dab_solve_primal(self._h, C.byref(fail), C.byref(st)))
         self.primalStats = st
+        self._prevPrimalSolTime = getattr(self, "_prevPrimalSolTime", 0.0) + st.iterations * self.getDeltaT()
         return int(fail.value)
 
     def updateDAOption(self, pyOptions):
@@ -324,6 +327,132 @@ class pyDASolvers:
         if fieldType not in ("scalar", "vector"):
             raise DAB200Error("%s not support. Options are: vector or scalar " % fieldType)
         return None
+
+    # ---- mesh quality, mesh / state files, sensitivity maps (pyDASolvers.pyx:320-321, 382-395, 421-462)
+    def checkMesh(self):
+        """1 if the mesh passes the quality checks of DACheckMesh (thresholds: option checkMeshThreshold, defaults of
+        reference pyDAFoam.py:611-616), else 0; the measured values are kept in self.meshQuality."""
+        th = dict(maxAspectRatio=1000.0, maxNonOrth=70.0, maxSkewness=4.0, maxIncorrectlyOrientedFaces=0)
+        th.update(self._options.get("checkMeshThreshold", {}) or {})
+        ok = C.c_int(0)
+        rep = (C.c_double * 11)()
+        self._raise(self._L.dab_check_mesh(self._h, C.c_double(th["maxNonOrth"]), C.c_double(th["maxSkewness"]), C.c_double(th["maxAspectRatio"]),
+                                           C.c_int(int(th["maxIncorrectlyOrientedFaces"])), C.byref(ok), rep))
+        keys = ("maxNonOrth", "avgNonOrth", "maxSkewness", "maxAspectRatio", "minVolume", "minFaceArea", "maxOpenness", "nSevereNonOrth",
+                "nErrorNonOrth", "nNegativePyramids", "nFailedChecks")
+        self.meshQuality = dict(zip(keys, [float(v) for v in rep]))
+        return int(ok.value)
+
+    def readStateVars(self, timeVal, timeLevel=0):
+        """Fields of <case>/<timeVal>/ -> states.  timeLevel > 0 (old-time levels) belongs to the unsteady solvers."""
+        if timeLevel != 0:
+            raise DAB200Error("readStateVars: old-time levels belong to the unsteady solvers (not built)")
+        self._raise(self._L.dab_read_state_vars(self._h, C.c_double(timeVal)))
+
+    def readMeshPoints(self, timeVal):
+        self._raise(self._L.dab_read_mesh_points(self._h, C.c_double(timeVal)))
+
+    def writeMeshPoints(self, points, timeVal):
+        _check_array(points, self.getNLocalPoints() * 3, "points")
+        name = ("%.6g" % timeVal) if not isinstance(timeVal, str) else timeVal
+        self._raise(self._L.dab_write_mesh_points(self._h, _dp(points), name.encode()))
+
+    def writeCurrentMeshPointsToConstant(self):
+        self._raise(self._L.dab_write_mesh_points(self._h, None, b"constant"))
+
+    def writeFailedMesh(self, timeVal=9999):
+        """The current points under a far time directory for inspection (reference DASolver::writeFailedMesh writes the failed mesh
+        to the time the option writeMinorIterations / failed-mesh logic selects; the default here is 9999)."""
+        self._raise(self._L.dab_write_mesh_points(self._h, None, ("%.6g" % timeVal).encode()))
+
+    def writeSensMapSurface(self, name, dFdXs, Xs, size, timeName):
+        _check_array(dFdXs, size, "dFdXs")
+        _check_array(Xs, size, "Xs")
+        nrm = C.c_double(0.0)
+        self._raise(self._L.dab_write_sens_map_surface(self._h, name.encode(), _dp(dFdXs), _dp(Xs), C.c_int(size), C.c_double(timeName),
+                                                       C.byref(nrm)))
+        return float(nrm.value)
+
+    def writeSensMapField(self, name, dFdField, fieldType, timeName):
+        if fieldType not in ("scalar", "vector"):
+            raise DAB200Error("fieldType can be either scalar or vector")
+        _check_array(dFdField, self.getNLocalCells() * (3 if fieldType == "vector" else 1), "dFdField")
+        self._raise(self._L.dab_write_sens_map_field(self._h, name.encode(), _dp(dFdField), fieldType.encode(), C.c_double(timeName)))
+
+    # ---- index and bookkeeping queries
+    def getNLocalAdjointBoundaryStates(self):
+        """(3 nVolVectorStates + nVolScalarStates + nModelStates) * nLocalBoundaryFaces (reference DAIndex.C:105-107)."""
+        nCellStates = (self.getNLocalAdjointStates() - self.getNLocalFaces()) // self.getNLocalCells()
+        return nCellStates * (self.getNLocalFaces() - self.getNLocalInternalFaces())
+
+    def setGlobalXvOffset(self, offset):
+        """Several ranks: the sum of 3*nLocalPoints over the lower ranks (the caller owns the communicator)."""
+        self._xvOffset = int(offset)
+
+    def getGlobalXvIndex(self, pointI, coordI):
+        """Reference DAIndex.C:704-733: rank offset + pointI*3 + coordI."""
+        if self._nRanks > 1 and not hasattr(self, "_xvOffset"):
+            raise DAB200Error("getGlobalXvIndex on several ranks: call setGlobalXvOffset(sum of 3*nLocalPoints of the lower ranks) first")
+        assert 0 <= pointI < self.getNLocalPoints() and 0 <= coordI < 3
+        return getattr(self, "_xvOffset", 0) + 3 * pointI + coordI
+
+    def hasVolCoordInput(self):
+        """1 if any inputInfo entry is of type volCoord (reference DASolver::hasVolCoordInput)."""
+        info = self._options.get("inputInfo", {}) or {}
+        return int(any(isinstance(v, dict) and v.get("type") == "volCoord" for v in info.values()))
+
+    def getElapsedClockTime(self):
+        return time.time() - self._t0Clock
+
+    def getElapsedCpuTime(self):
+        return time.process_time() - self._t0Cpu
+
+    # steady solvers: the "time" is the SIMPLE iteration counter of system/controlDict (reference runTime bookkeeping)
+    def _controlDict(self):
+        if not hasattr(self, "_ctl"):
+            self._ctl = {}
+            path = os.path.join(self._caseDir, "system", "controlDict")
+            if os.path.exists(path):
+                for line in open(path):
+                    t = line.split("//")[0].strip().rstrip(";").split()
+                    if len(t) == 2:
+                        self._ctl[t[0]] = t[1]
+        return self._ctl
+
+    def getDeltaT(self):
+        return float(self._controlDict().get("deltaT", 1.0))
+
+    def getEndTime(self):
+        return float(self._controlDict().get("endTime", 0.0))
+
+    def getDdtSchemeOrder(self):
+        """Steady solvers run ddtSchemes steadyState; the reference returns 1 for Euler and 2 for backward (unsteady only)."""
+        return 1
+
+    def setTime(self, time_, timeIndex):
+        self._time, self._timeIndex = float(time_), int(timeIndex)
+
+    def getPrevPrimalSolTime(self):
+        return getattr(self, "_prevPrimalSolTime", 0.0)
+
+    def getLatestTime(self):
+        """Largest numeric time directory of the case (reference runTime.times().last())."""
+        best = 0.0
+        for d in os.listdir(self._caseDir):
+            try:
+                v = float(d)
+            except ValueError:
+                continue
+            if os.path.isdir(os.path.join(self._caseDir, d)):
+                best = max(best, v)
+        return best
+
+    def runFPAdj(self, dFdW, psi):
+        raise DAB200Error("runFPAdj: the fixed-point adjoint (reference DASimpleFoam.C:189-909) is not built; use adjEqnSolMethod Krylov "
+                          "(calcdRdWT + createMLRKSPMatrixFree + solveLinearEqn)")
+
+    def solveAdjointFP(self, dFdW, psi):
+        return self.runFPAdj(dFdW, psi)
 
     def printAllOptions(self):
         """Reference DASolver.H printAllOptions: dump the options dictionary."""

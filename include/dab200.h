@@ -122,6 +122,25 @@ int dab_get_of_mesh_points(dab_solver* s, double* points);
 int dab_write_adjoint_fields(dab_solver* s, const char* function, double write_time, const double* psi);
 int dab_write_fields(dab_solver* s, double write_time);
 
+/* readStateVars(timeVal, timeLevel) (pyDASolvers.pyx:382-383, DASolver::readStateVars): the fields U, p, [T], [nuTilda] and, when present,
+ * phi of <case>/<timeVal>/ become the states (boundary conditions stay those of 0/).  readMeshPoints(timeVal) (pyDASolvers.pyx:385-386):
+ * <case>/<timeVal>/polyMesh/points become the mesh points.  writeMeshPoints(points, timeVal) (pyDASolvers.pyx:388-392), also the body of
+ * writeCurrentMeshPointsToConstant ("constant") and writeFailedMesh: points == NULL writes the current points. */
+int dab_read_state_vars(dab_solver* s, double time_val);
+int dab_read_mesh_points(dab_solver* s, double time_val);
+int dab_write_mesh_points(dab_solver* s, const double* points, const char* dir_name);
+/* writeSensMapSurface(name, dFdXs, Xs, size, timeName) / writeSensMapField(name, dFdField, fieldType, timeName)
+ * (pyDASolvers.pyx:421-462, DASolver.C:3840-4053): derivative maps as dimensionless OpenFOAM fields under <case>/<timeName>/ */
+int dab_write_sens_map_surface(dab_solver* s, const char* name, const double* dfdxs, const double* xs, int size, double time_name,
+                               double* min_distance_norm);
+int dab_write_sens_map_field(dab_solver* s, const char* name, const double* dfdfield, const char* field_type, double time_name);
+/* checkMesh() (pyDASolvers.pyx:320-321, DACheckMesh.C:45-79, DACheckGeometry.C:256-478): mesh_ok = 1 when no check fails with the
+ * thresholds of the option checkMeshThreshold.  report (may be NULL): maxNonOrth, avgNonOrth [deg], maxSkewness, maxAspectRatio,
+ * minVolume, minFaceArea, maxOpenness, nSevereNonOrth, nErrorNonOrth, nNegativePyramids, nFailedChecks */
+#define DAB_CHECK_MESH_REPORT 11
+int dab_check_mesh(dab_solver* s, double max_non_orth, double max_skewness, double max_aspect_ratio, int max_incorrectly_oriented_faces,
+                   int* mesh_ok, double* report);
+
 /* updateOFMesh(points): new point coordinates (3*nLocalPoints), geometry recomputed, wall distance frozen
  * (reference pyDASolvers.pyx updateOFMesh, DASolver::updateOFMesh) */
 int dab_update_of_mesh(dab_solver* s, const double* points);
