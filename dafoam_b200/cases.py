@@ -472,7 +472,8 @@ def write_field(case_dir, name, cls, dims, internal, bcs, time="0"):
 
 
 def write_dicts(case_dir, nu=1.5e-5, ras_model="SpalartAllmaras", div_u="bounded Gauss linearUpwind grad(U)",
-                div_nut="bounded Gauss upwind", relax_u=0.7, relax_p=0.3, relax_nut=0.7, consistent=False):
+                div_nut="bounded Gauss upwind", relax_u=0.7, relax_p=0.3, relax_nut=0.7, consistent=False, transonic=False,
+                div_phid_p="Gauss upwind"):
     os.makedirs(os.path.join(case_dir, "constant"), exist_ok=True)
     os.makedirs(os.path.join(case_dir, "system"), exist_ok=True)
     with open(os.path.join(case_dir, "constant", "transportProperties"), "w") as f:
@@ -492,13 +493,14 @@ divSchemes
     div(phi,U)      %s;
     div(phi,nuTilda) %s;
     div((nuEff*dev2(T(grad(U))))) Gauss linear;
+    div(phid,p)     %s;
     div(pc)         bounded Gauss upwind;
 }
 laplacianSchemes { default Gauss linear corrected; }
 interpolationSchemes { default linear; }
 snGradSchemes { default corrected; }
 wallDist { method meshWaveFrozen; }
-""" % (div_u, div_nut))
+""" % (div_u, div_nut, div_phid_p))
     with open(os.path.join(case_dir, "system", "fvSolution"), "w") as f:
         f.write(_header("dictionary", "system", "fvSolution"))
         f.write("""
@@ -506,13 +508,14 @@ SIMPLE
 {
     nNonOrthogonalCorrectors 0;
     consistent %s;
+    transonic %s;
 }
 relaxationFactors
 {
     fields { p %.17g; }
     equations { U %.17g; nuTilda %.17g; }
 }
-""" % ("true" if consistent else "false", relax_p, relax_u, relax_nut))
+""" % ("true" if consistent else "false", "yes" if transonic else "no", relax_p, relax_u, relax_nut))
     with open(os.path.join(case_dir, "system", "controlDict"), "w") as f:
         f.write(_header("dictionary", "system", "controlDict"))
         f.write("\napplication simpleFoam;\nstartTime 0;\nendTime 1000;\ndeltaT 1;\n")

@@ -520,8 +520,29 @@ struct cFwdE
     }
 };
 
-// F_f of an internal face from the owner's point of view (compressible)
-DAB_HD double cFaceF(const MeshView& m, const StateView& s, const RecordView& r, int f, int o, int n)
+// limitedLinear(k) limiter of the face value of p convected by phid (OpenFOAM limitedLinear.H, NVDTVD.H::r): returns the limiter
+// and (for the adjoint) its slope d(limiter)/d(r) (0 where clipped) with r = 2 gradcf/gradf - 1, gradcf = d . grad(p)_upwind.
+// fluxPositive: phid > 0 (strict, as in NVDTVD::r); o/n owner and neighbour of the face
+DAB_HD double limitedLinearLimiter(const MeshView& m, const StateView& s, const RecordView& r, double k, bool fluxPositive, int o, int n,
+                                   double& dLimDr, double& gradf, double& gradcf, bool& farBranch)
+{
+    const int nT = m.nCtot;
+    const int u = fluxPositive ? o : n;
+    const double d[3] = {m.Cx[n] - m.Cx[o], m.Cy[n] - m.Cy[o], m.Cz[n] - m.Cz[o]};
+    gradf = s.p[n] - s.p[o];
+    gradcf = d[0] * r.gP[u] + d[1] * r.gP[(size_t)nT + u] + d[2] * r.gP[(size_t)2 * nT + u];
+    farBranch = fabs(gradcf) >= 1000.0 * fabs(gradf);
+    const double rr = farBranch ? 2.0 * 1000.0 * (gradcf >= 0.0 ? 1.0 : -1.0) * (gradf >= 0.0 ? 1.0 : -1.0) - 1.0 : 2.0 * (gradcf / gradf) - 1.0;
+    const double twoByk = 2.0 / (k > 1e-15 ? k : 1e-15);
+    const double lim = twoByk * rr;
+    dLimDr = (lim > 0.0 && lim < 1.0 && !farBranch) ? twoByk : 0.0;
+    return lim > 1.0 ? 1.0 : (lim < 0.0 ? 0.0 : lim);
+}
+
+// F_f of an internal face from the owner's point of view (compressible).  Transonic (q.transonic, DAResidualTurboFoam.C:148-189,
+// DAResidualRhoSimpleCFoam.C:160-183): phid p_f - (rho rAU)_f |S_f| snGrad(p), phid = psi_f (S_f.HbyA_f - relative-frame flux),
+// p_f by the div(phid,p) scheme (weights only: the matrix flux and the matrix residual see the same face value)
+DAB_HD double cFaceF(const MeshView& m, const Params& q, const StateView& s, const RecordView& r, int f, int o, int n)
 {
     const int nT = m.nCtot;
     const double w = m.w[f], mS = m.magSf[f];
@@ -533,10 +554,26 @@ DAB_HD double cFaceF(const MeshView& m, const StateView& s, const RecordView& r,
         ph += Sv[j] * (w * r.HbyA[(size_t)j * nT + o] + (1.0 - w) * r.HbyA[(size_t)j * nT + n]);
         cg += kv[j] * (w * r.gP[(size_t)j * nT + o] + (1.0 - w) * r.gP[(size_t)j * nT + n]);
     }
-    const double rhof = w * r.rho[o] + (1.0 - w) * r.rho[n];
     const double gam = w * r.rho[o] * r.rAU[o] + (1.0 - w) * r.rho[n] * r.rAU[n];
     const double sn = m.delta[f] * (s.p[n] - s.p[o]) + cg;
     if (m.mrfFlux) ph -= m.mrfFlux[f]; // MRF.makeRelative(interpolate(rho), phiHbyA)
+    if (q.transonic)
+    {
+        if (q.transonic == 2) return -gam * mS * sn; // preconditioner residual without div(phid,p)
+        const double phid = (w / (q.Rg * s.T[o]) + (1.0 - w) / (q.Rg * s.T[n])) * ph;
+        double wf;
+        if (q.divPhidP == DIV_LINEAR) wf = w;
+        else if (q.divPhidP == DIV_LIMITED_LINEAR)
+        {
+            double dl, gf, gc;
+            bool fb;
+            const double lim = limitedLinearLimiter(m, s, r, q.phidK, phid > 0.0, o, n, dl, gf, gc, fb);
+            wf = lim * w + (1.0 - lim) * (phid >= 0.0 ? 1.0 : 0.0);
+        }
+        else wf = phid >= 0.0 ? 1.0 : 0.0;
+        return phid * (wf * s.p[o] + (1.0 - wf) * s.p[n]) - gam * mS * sn;
+    }
+    const double rhof = w * r.rho[o] + (1.0 - w) * r.rho[n];
     return rhof * ph - gam * mS * sn;
 }
 
@@ -563,7 +600,7 @@ struct cFwdC
             if (!fr.bnd)
             {
                 const int o = fr.s > 0 ? c : fr.n, n = fr.s > 0 ? fr.n : c;
-                F = cFaceF(m, s, r, f, o, n);
+                F = cFaceF(m, q, s, r, f, o, n);
             }
             else
             {
@@ -578,10 +615,12 @@ struct cFwdC
                 else
                     ph = m.Sx[f] * r.HbyA[c] + m.Sy[f] * r.HbyA[(size_t)nT + c] + m.Sz[f] * r.HbyA[(size_t)2 * nT + c];
                 ph = mrfBoundaryFlux(m, f, ph, 1.0);
+                if (q.transonic == 2) ph = 0.0; // preconditioner residual without div(phid,p): its boundary part psi_b p_b ph = rho_b ph goes too
                 F = bp.th.rho * ph - bp.th.rho * r.rAU[c] * m.magSf[f] * bp.sngP;
             }
             div += fr.s * F;
-            if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0);
+            if (q.transonic == 3 && fr.s > 0) R[offPhi + f] = s.phi[f] * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0); // transonicPCOption 2
+            else if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0);
             else if (fr.n >= nC) R[offPhi + f] = 0.0;
         }
         R[offP + c] = div * (q.nrP ? 1.0 / m.V[c] : 1.0);

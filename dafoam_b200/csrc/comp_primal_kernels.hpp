@@ -412,7 +412,7 @@ struct cPhiUpdate
             const int f = fr.f;
             if (!fr.bnd)
             {
-                double F = cFaceF(m, s, r, f, c, fr.n);
+                double F = cFaceF(m, q, s, r, f, c, fr.n);
                 if (sc.rAt)
                 {
                     const int n = fr.n;

@@ -157,13 +157,45 @@ struct cRevA
                 const double rhon = r.rho[n];
                 const double rhof = wc * rhoc + wn * rhon;
                 const double gam = wc * rhoc * rAUc + wn * rhon * r.rAU[n];
-                for (int j = 0; j < 3; j++)
-                {
-                    HbA[j] += wc * Sv[j] * rhof * Fb;
-                    gPb[j] -= gam * mS * wc * kv[j] * Fb;
-                }
                 if (m.mrfFlux) ph -= m.mrfFlux[f]; // owner-oriented, like ph, sn and Fb
-                rhob += wc * (ph - rAUc * mS * sn) * Fb;
+                if (q.transonic)
+                {
+                    // F = phid p_f - gam |S| sn, phid = psi_f ph, p_f = wf p_own + (1 - wf) p_nei (cFaceF); this cell's share
+                    const int o = fr.s > 0 ? c : n, nn = fr.s > 0 ? n : c;
+                    const double Tc = s.T[c];
+                    const double psif = wc / (q.Rg * Tc) + wn / (q.Rg * s.T[n]);
+                    const double phid = psif * ph;
+                    const double up = phid >= 0.0 ? 1.0 : 0.0;
+                    double wf = up, dLimDr = 0.0, gradf = 1.0, gradcf = 0.0;
+                    bool farBranch = false;
+                    if (q.divPhidP == DIV_LINEAR) wf = w;
+                    else if (q.divPhidP == DIV_LIMITED_LINEAR)
+                    {
+                        const double lim = limitedLinearLimiter(m, s, r, q.phidK, phid > 0.0, o, nn, dLimDr, gradf, gradcf, farBranch);
+                        wf = lim * w + (1.0 - lim) * up;
+                    }
+                    const double pS = wf * s.p[o] + (1.0 - wf) * s.p[nn];
+                    for (int j = 0; j < 3; j++) HbA[j] += wc * Sv[j] * psif * pS * Fb;
+                    Tb -= wc / (q.Rg * Tc * Tc) * ph * pS * Fb;
+                    pb += (fr.s > 0 ? wf : 1.0 - wf) * phid * Fb;
+                    if (dLimDr != 0.0)
+                    {
+                        const double G = phid * Fb * (s.p[o] - s.p[nn]) * (w - up) * dLimDr;
+                        pb += G * (-2.0 * gradcf / (gradf * gradf)) * (-fr.s);
+                        if ((phid > 0.0 ? o : nn) == c)
+                        {
+                            const double d[3] = {m.Cx[nn] - m.Cx[o], m.Cy[nn] - m.Cy[o], m.Cz[nn] - m.Cz[o]};
+                            for (int j = 0; j < 3; j++) gPb[j] += G * (2.0 / gradf) * d[j];
+                        }
+                    }
+                    rhob -= wc * rAUc * mS * sn * Fb;
+                }
+                else
+                {
+                    for (int j = 0; j < 3; j++) HbA[j] += wc * Sv[j] * rhof * Fb;
+                    rhob += wc * (ph - rAUc * mS * sn) * Fb;
+                }
+                for (int j = 0; j < 3; j++) gPb[j] -= gam * mS * wc * kv[j] * Fb;
                 rAUb -= wc * rhoc * mS * sn * Fb;
                 pb += fr.s * gam * mS * dl * Fb;
             }

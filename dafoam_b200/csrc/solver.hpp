@@ -158,6 +158,7 @@ struct Solver
     int rank = 0, nRanks = 1;
     // options
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
+    int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
     double richardsonOmega = 1.0;
@@ -243,8 +244,8 @@ struct Solver
             auto t = tokenize(argsAll);
             solverName = t.empty() ? "DASimpleFoam" : t[0];
         }
-        if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam" && solverName != "DATurboFoam")
-            throw Error("solver " + solverName + " is not supported (DASimpleFoam, DARhoSimpleFoam, DATurboFoam)");
+        if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam" && solverName != "DATurboFoam" && solverName != "DARhoSimpleCFoam")
+            throw Error("solver " + solverName + " is not supported (DASimpleFoam, DARhoSimpleFoam, DARhoSimpleCFoam, DATurboFoam)");
         be.init(device);
         if (nRanks == 1)
         {
@@ -459,6 +460,32 @@ struct Solver
             const std::string c = fso.sub("SIMPLE").wordOr("consistent", "false");
             primal.consistent = (c == "true" || c == "yes" || c == "on");
         }
+        // transonic pressure equation: SIMPLE { transonic yes; } (simpleControl::transonic()); DARhoSimpleCFoam has no other form
+        // (DAResidualRhoSimpleCFoam.C:160 "we don't support transonic = false")
+        par.transonic = 0;
+        par.divPhidP = DIV_UPWIND;
+        par.phidK = 1.0;
+        if (par.comp)
+        {
+            std::string tr = fso.hasSub("SIMPLE") ? fso.sub("SIMPLE").wordOr("transonic", "no") : "no";
+            if (solverName == "DARhoSimpleCFoam" || tr == "yes" || tr == "true" || tr == "on")
+            {
+                par.transonic = 1;
+                const std::string v = fs.sub("divSchemes").joined("div(phid,p)");
+                const size_t ll = v.find("limitedLinear");
+                if (ll != std::string::npos)
+                {
+                    par.divPhidP = DIV_LIMITED_LINEAR;
+                    par.phidK = atof(v.c_str() + ll + 13);
+                    if (!(par.phidK > 0.0 && par.phidK <= 1.0)) throw Error("div(phid,p) '" + v + "': limitedLinear needs 0 < k <= 1");
+                }
+                else if (v.find("linearUpwind") != std::string::npos)
+                    throw Error("div(phid,p) '" + v + "': upwind, linear or limitedLinear k");
+                else if (v.find("upwind") != std::string::npos) par.divPhidP = DIV_UPWIND;
+                else if (v.find("linear") != std::string::npos) par.divPhidP = DIV_LINEAR;
+                else throw Error("div(phid,p) '" + v + "': upwind, linear or limitedLinear k");
+            }
+        }
         if (solverName == "DATurboFoam") primal.consistent = true; // its pressure corrector always uses AtU = AU - H1 (pEqnTurbo.H:13)
         // primal solver controls (system/fvSolution, system/controlDict)
         if (fso.hasSub("relaxationFactors"))
@@ -545,6 +572,10 @@ struct Solver
             }
         }
         par.constrainHbyA = (int)o.numOr("useConstrainHbyA", par.constrainHbyA);
+        {
+            const int tpo = (int)o.numOr("transonicPCOption", transonicPCOption);
+            if (tpo != transonicPCOption) { transonicPCOption = tpo; kry.pcValid = false; }
+        }
         if (const JVal* a = o.get("adjEqnOption"))
         {
             gmresRestart = (int)a->numOr("gmresRestart", gmresRestart);
@@ -1174,7 +1205,15 @@ struct Solver
             DAB_LAUNCH_NF(hm.nC, cFwdB, mv, par, sv, rv, isPC, Rdev);
             DAB_LAUNCH_NF(hm.nC, cFwdE, mv, par, sv, rv, isPC, Rdev);
             if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
-            DAB_LAUNCH_NF(hm.nC, cFwdC, mv, par, sv, rv, Rdev);
+            if (isPC && par.transonic)
+            {
+                Params pq = par; // div(pc) scheme and transonicPCOption for the preconditioner residual
+                pq.divPhidP = DIV_UPWIND;
+                pq.transonic = transonicPCOption == 1 ? 2 : (transonicPCOption == 2 ? 3 : 1);
+                DAB_LAUNCH_NF(hm.nC, cFwdC, mv, pq, sv, rv, Rdev);
+            }
+            else
+                DAB_LAUNCH_NF(hm.nC, cFwdC, mv, par, sv, rv, Rdev);
             return;
         }
         DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);

@@ -252,6 +252,9 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
 
 inline int Solver::solvePrimal(PrimalStats& st)
 {
+    if (par.transonic)
+        throw Error("solvePrimal: the transonic pressure corrector (pEqnRhoSimpleC.H / pEqnTurbo.H transonic branch, a non-symmetric "
+                    "convection-diffusion pressure equation) is not built; the residual, its transpose product and the adjoint solve are");
     primalSetup();
     if (fvSourceDirty) updateFvSource();
     Primal& P = primal;

@@ -16,7 +16,7 @@ namespace dab
 constexpr int MAXP = 16; // max patches per rank
 enum { F_U = 0, F_P = 1, F_NUTILDA = 2, F_NUT = 3, N_FIELDS = 4 };
 enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_INLET_OUTLET = 2, BC_OUTLET_INLET = 3, BC_SYMMETRY = 4, BC_CALCULATED = 5, BC_NUT_LOW_RE = 6, BC_NUT_SPALDING = 7 };
-enum { DIV_UPWIND = 0, DIV_LINEAR_UPWIND = 1, DIV_LINEAR = 2, DIV_LINEAR_UPWIND_V = 3 };
+enum { DIV_UPWIND = 0, DIV_LINEAR_UPWIND = 1, DIV_LINEAR = 2, DIV_LINEAR_UPWIND_V = 3, DIV_LIMITED_LINEAR = 4 /* div(phid,p) only */ };
 
 struct MeshView
 {
@@ -161,6 +161,12 @@ struct Params
     int bcKindT[MAXP];
     double bcValT[MAXP];
     int rhoFrozen;            // primal loop only: the cell density is the stored (relaxed) field, not p/(R T)
+    // simple_.transonic() (DAResidualTurboFoam.C:148-189; DARhoSimpleCFoam always): pEqn = fvm::div(phid, p) - fvm::laplacian(rho rAU, p).
+    // 0 off, 1 on, 2 = preconditioner residual without the div(phid,p) term (transonicPCOption 1), 3 = on with phiRes = phi in the
+    // preconditioner residual (transonicPCOption 2)
+    int transonic;
+    int divPhidP;             // DIV_UPWIND | DIV_LINEAR | DIV_LIMITED_LINEAR
+    double phidK;             // k of "limitedLinear k"
     int turboH;               // DATurboFoam with sensibleEnthalpy: - div(Teff & U) + div(p (U - URel)) in the energy row
 };
 

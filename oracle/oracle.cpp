@@ -78,7 +78,8 @@ enum DivScheme
     DIV_UPWIND = 0,
     DIV_LINEAR_UPWIND = 1,
     DIV_LINEAR = 2,
-    DIV_LINEAR_UPWIND_V = 3
+    DIV_LINEAR_UPWIND_V = 3,
+    DIV_LIMITED_LINEAR = 4 // limitedLinear k (NVD/TVD limited scheme, weights only)
 };
 
 struct Topo
@@ -360,13 +361,33 @@ void fvcGrad(const Topo& t, const Geom<T>& g, int nc, const std::vector<T>& x, c
 // fvm::div(phi, x) with Gauss <scheme>; gaussConvectionScheme::fvmDiv (+ linearUpwind::correction)
 template <class T>
 void fvmDiv(Mat<T>& m, const Topo& t, const Geom<T>& g, const std::vector<T>& phi, int scheme, const BF<T>& bf,
-            const std::vector<T>& gradX, bool bounded, const std::vector<T>* xc = nullptr)
+            const std::vector<T>& gradX, bool bounded, const std::vector<T>* xc = nullptr, double limitedLinearK = 1.0)
 {
     for (int f = 0; f < t.nIF; f++)
     {
         T w;
         if (scheme == DIV_LINEAR)
             w = g.w[f];
+        else if (scheme == DIV_LIMITED_LINEAR)
+        {
+            // limitedScheme::weights with LimitedLinearLimiter (OpenFOAM limitedLinear.H, NVDTVD.H::r): scalar fields only
+            const std::vector<T>& x = *xc;
+            const int o = t.own[f], n = t.nei[f];
+            const T gradf = x[n] - x[o];
+            const int u = (val(phi[f]) > 0.0) ? o : n;
+            V3<T> d = g.C[n] - g.C[o];
+            const T gradcf = d.x * gradX[(size_t)0 * t.nC + u] + d.y * gradX[(size_t)1 * t.nC + u] + d.z * gradX[(size_t)2 * t.nC + u];
+            T r;
+            auto sgn = [](double v) { return v >= 0.0 ? 1.0 : -1.0; };
+            if (std::fabs(val(gradcf)) >= 1000.0 * std::fabs(val(gradf)))
+                r = T(2.0 * 1000.0 * sgn(val(gradcf)) * sgn(val(gradf)) - 1.0);
+            else
+                r = 2.0 * (gradcf / gradf) - 1.0;
+            T lim = (2.0 / std::max(limitedLinearK, 1e-15)) * r;
+            if (val(lim) > 1.0) lim = T(1.0);
+            if (val(lim) < 0.0) lim = T(0.0);
+            w = lim * g.w[f] + (1.0 - lim) * (val(phi[f]) >= 0.0 ? 1.0 : 0.0);
+        }
         else
             w = T(val(phi[f]) >= 0.0 ? 1.0 : 0.0);
         T lo = -(w * phi[f]);
@@ -601,6 +622,8 @@ struct Case
         int heIsE = 1;      // energy variable: 1 sensibleInternalEnergy (e), 0 sensibleEnthalpy (h)
         int sutherland = 0; // transport: 0 const (mu, Pr), 1 sutherland (As, Ts)
         int divE = 0, divEkp = 0, nrT = 1;
+        int transonic = 0, divPhidP = 0, transonicPCOption = -1; // simple_.transonic(): fvm::div(phid, p) pressure equation
+        double phidK = 1.0;                                      // k of 'limitedLinear k' for div(phid,p)
         int turbo = 0; // DATurboFoam: the sensibleEnthalpy energy equation carries the viscous-work and p(U - URel) terms
         double R = 287.0, Cp = 1005.0, mu = 1.8e-5, Pr = 0.7, Prt = 1.0, As = 1.4792e-6, Ts = 116.0, TRef = 298.15, sT = 1.0;
         std::vector<int> kindT;     // [nPatch]
@@ -1449,6 +1472,33 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
     Mat<T> pEqn;
     pEqn.init(t, 1);
     fvmLaplacian(pEqn, t, g, -1.0, rhorAU, rhorAUB, bP, gradP, true);
+    if (cp.transonic)
+    {
+        // simple_.transonic() (DAResidualTurboFoam.C:148-189; DAResidualRhoSimpleCFoam.C:148-200 reduces to the same rows because
+        // interpolate(psi*p) == interpolate(rho) cancels its phiHbyA): phid = interpolate(psi)*(interpolate(HbyA) & Sf), made
+        // relative; pEqn = fvm::div(phid, p) - fvm::laplacian(rho*rAU, p); phiRes = pEqn.flux() - phi.  pEqn.relax() leaves
+        // (pEqn & p) and the flux unchanged.  phiHbyA (already rho_f * relative volume flux) / rho_f = the relative volume flux.
+        std::vector<T> phid(nF);
+        for (int f = 0; f < nF; f++)
+        {
+            T psif, rhof;
+            if (f < nIF)
+            {
+                const int o = t.own[f], n = t.nei[f];
+                psif = g.w[f] * (rho[o] / p[o]) + (1.0 - g.w[f]) * (rho[n] / p[n]);
+                rhof = g.w[f] * rho[o] + (1.0 - g.w[f]) * rho[n];
+            }
+            else
+            {
+                psif = rhoB[f - nIF] / bP.val[f - nIF];
+                rhof = rhoB[f - nIF];
+            }
+            phid[f] = psif * (phiHbyA[f] / rhof);
+            phiHbyA[f] = T(0.0);
+        }
+        const bool dropped = isPC && cp.transonicPCOption == 1; // "for PC we do not include the div(phid, p) term"
+        if (!dropped) fvmDiv(pEqn, t, g, phid, isPC ? (int)DIV_UPWIND : cp.divPhidP, bP, gradP, false, &p, cp.phidK);
+    }
     for (int f = 0; f < nF; f++)
     {
         pEqn.src[t.own[f]] -= phiHbyA[f];
@@ -1465,6 +1515,7 @@ void residualComp(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int
     for (int f = 0; f < nF; f++)
     {
         phiRes[f] = phiHbyA[f] + pFlux[f] - phi[f];
+        if (cp.transonic && isPC && cp.transonicPCOption == 2) phiRes[f] = phi[f]; // DAResidualTurboFoam.C:173-178
         if (par.nrPhi) phiRes[f] /= g.magSf[f];
     }
 
@@ -1691,6 +1742,17 @@ void orc_set_compressible(void* h, const double* dpar, const int* ipar, const in
     c.heIsE = ipar[0]; c.sutherland = ipar[1]; c.divE = ipar[2]; c.divEkp = ipar[3]; c.nrT = ipar[4];
     c.kindT.assign(kindT, kindT + cs->t.nPatch);
     c.valueT.assign(valueT, valueT + cs->t.nPatch);
+    cs->recorded = false;
+}
+
+// transonic pressure equation: scheme of div(phid,p) (DivScheme; 4 = limitedLinear k), transonicPCOption (-1, 1, 2)
+void orc_set_transonic(void* h, int on, int scheme, double k, int pcOption)
+{
+    Case* cs = (Case*)h;
+    cs->comp.transonic = on;
+    cs->comp.divPhidP = scheme;
+    cs->comp.phidK = k;
+    cs->comp.transonicPCOption = pcOption;
     cs->recorded = false;
 }
 

@@ -193,6 +193,11 @@ class Oracle:
         """DATurboFoam's energy equation (the enthalpy form carries the viscous-work and p(U - URel) terms)."""
         lib().orc_set_turbo(self.h, C.c_int(int(on)))
 
+    def set_transonic(self, on=True, scheme=0, k=1.0, pc_option=-1):
+        """simple_.transonic(): pEqn = fvm::div(phid, p) - fvm::laplacian(rho rAU, p) (DAResidualTurboFoam.C:148-189,
+        DAResidualRhoSimpleCFoam.C:148-200).  scheme: 0 upwind, 2 linear, 4 limitedLinear k; pc_option = transonicPCOption."""
+        lib().orc_set_transonic(self.h, C.c_int(int(on)), C.c_int(int(scheme)), C.c_double(float(k)), C.c_int(int(pc_option)))
+
     def set_mrf(self, mesh, mrf):
         """One MRF zone (see dafoam_b200.cases.write_mrf for the dict)."""
         axis = np.asarray(mrf["axis"], dtype=np.float64)

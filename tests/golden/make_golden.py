@@ -53,6 +53,11 @@ def golden_spec(kind):
         return dict(mesh=mesh, bcs=cases.compressible_bcs(cases.default_bcs_naca(U0=(50.0, 2.0, 0.0))), fpatch="wing", name="naca_turbo_h_24x12",
                     solver="DATurboFoam", ras="SpalartAllmaras", thermo=cases.default_thermo(energy="sensibleEnthalpy", transport="sutherland"),
                     ns=NS_COMP, nres=NRES_COMP, mrf=mrf_zone(mesh, omega=25.0))
+    if kind == "nacatransonic":
+        # DARhoSimpleCFoam (transonic pressure equation, div(phid,p) limitedLinear 1.0), freestream Mach 0.66
+        return dict(mesh=mesh, bcs=cases.compressible_bcs(cases.default_bcs_naca(U0=(230.0, 8.0, 0.0))), fpatch="wing",
+                    name="naca_rhosimplec_24x12", solver="DARhoSimpleCFoam", ras="SpalartAllmaras", thermo=cases.default_thermo(),
+                    ns=dict(NS_COMP, U=230.0), nres=NRES_COMP, transonic=dict(scheme="Gauss limitedLinear 1.0", code=4, k=1.0), U0=(230.0, 8.0, 0.0))
     raise ValueError(kind)
 
 
@@ -62,10 +67,15 @@ def oracle_of(spec):
         orc.set_turbo(True)
     if spec.get("mrf"):
         orc.set_mrf(spec["mesh"], spec["mrf"])
+    if spec.get("transonic"):
+        orc.set_transonic(True, spec["transonic"]["code"], spec["transonic"]["k"], -1)
     return orc
 
 
 def state_for(kind, mesh, orc):
+    if kind == "nacatransonic":
+        from oracle.pyoracle import synthetic_state
+        return synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(230.0, 8.0, 0.0), thermo=cases.default_thermo(), noise=0.01)
     if kind in ("nacacomp", "nacaturbo"):
         from oracle.pyoracle import synthetic_state
         return synthetic_state(mesh, orc.geometry("C"), orc.geometry("Sf"), U0=(50.0, 2.0, 0.0), thermo=cases.default_thermo(), noise=0.01)
@@ -98,7 +108,7 @@ def compute(kind):
 
 
 if __name__ == "__main__":
-    only = sys.argv[1:] or ("naca", "channel", "nacafv3", "nacacomp", "nacamrf", "nacaturbo")
+    only = sys.argv[1:] or ("naca", "channel", "nacafv3", "nacacomp", "nacamrf", "nacaturbo", "nacatransonic")
     for kind in only:
         name, data = compute(kind)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **data)

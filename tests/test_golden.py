@@ -18,7 +18,7 @@ from tests.golden.make_golden import golden_spec, oracle_of
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-KINDS = ["naca", "channel", "nacafv3", "nacacomp", "nacamrf", "nacaturbo"]
+KINDS = ["naca", "channel", "nacafv3", "nacacomp", "nacamrf", "nacaturbo", "nacatransonic"]
 
 
 @pytest.mark.parametrize("kind", KINDS)
@@ -43,6 +43,8 @@ def engine_vs_golden(kind, lib_path, tol=1e-11):
         kw["thermo"] = spec["thermo"]
     if spec.get("mrf"):
         kw["mrf"] = spec["mrf"]
+    if spec.get("transonic"):
+        kw["div_phid_p"] = spec["transonic"]["scheme"]
     cases.write_case(d, mesh, bcs, **kw)
     fn = {"F": {"type": "force", "source": "patchToFace", "patches": [fpatch], "directionMode": "fixedDirection",
                 "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
