@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--cells", type=int, default=980000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-idrs", action="store_true", help="skip the IDR(s) leg of the adjoint solve")
     ap.add_argument("--solve-multi", action="store_true")
     ap.add_argument("--restart", type=int, default=1500)
     ap.add_argument("--pc-level", type=int, default=3)
@@ -338,7 +339,26 @@ def main():
             st = ksp.stats
             adjoint = {"wall_s": t_pc + t_solve, "pc_s": t_pc, "solve_s": t_solve, "fail": fail, "iterations": st.iterations,
                        "rel_residual": st.final_residual / st.initial_residual if st.initial_residual else None,
-                       "n_matvec": st.n_matvec, "gmres_device_s": st.solve_seconds}
+                       "n_matvec": st.n_matvec, "gmres_device_s": st.solve_seconds, "method": "GMRES(%d), the reference's KSP" % args.restart}
+            # the same system with IDR(s) on the same preconditioner (adjEqnOption.kspType idrs, an extension: short recurrences,
+            # no orthogonalisation against the whole basis); reported beside the GMRES number, never instead of it
+            if not args.no_idrs:
+                try:
+                    sol.updateDAOption(dict(adjEqnOption=dict(kspType="idrs", idrS=4, gmresMaxIters=3 * args.max_iters)))
+                    psi2 = np.zeros(n)
+                    t0 = time.perf_counter()
+                    fail2 = sol.solveLinearEqn(ksp, dFdW, psi2)
+                    t2 = time.perf_counter() - t0
+                    st = ksp.stats
+                    dn = float(np.linalg.norm(psi_sol))
+                    adjoint["idrs"] = {"method": "IDR(4)", "wall_s": t_pc + t2, "solve_s": t2, "fail": fail2, "operator_applications": st.iterations,
+                                       "rel_residual": st.final_residual / st.initial_residual if st.initial_residual else None,
+                                       "n_matvec": st.n_matvec, "device_s": st.solve_seconds,
+                                       "psi_rel_diff_vs_gmres": float(np.linalg.norm(psi2 - psi_sol)) / dn if dn > 0 else None}
+                except Exception as e:
+                    adjoint["idrs"] = {"error": str(e)}
+                finally:
+                    sol.updateDAOption(dict(adjEqnOption=dict(kspType="gmres", gmresMaxIters=args.max_iters)))
         except Exception as e:  # reported, never hidden
             adjoint = {"error": str(e)}
 

@@ -511,6 +511,8 @@ struct Krylov
     // GMRES workspace
     DevBuf<double> V, w, z, xdev, bdev, hdev;
     int vCap = 0;
+    DevBuf<double> idr; // IDR(s) workspace: P(s) | G(s) | U(s) | r | t | v | z
+    int idrS = 0;
     VecOps ops;
     EllView view()
     {

@@ -158,6 +158,8 @@ struct Solver
     int rank = 0, nRanks = 1;
     // options
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
+    std::string kspType = "gmres"; // adjEqnOption.kspType (extension): gmres (the reference's KSP) | idrs (IDR(s), short recurrences)
+    int idrS = 4;
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
@@ -587,6 +589,10 @@ struct Solver
             pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
+            kspType = a->strOr("kspType", kspType);
+            if (kspType != "gmres" && kspType != "idrs") throw Error("adjEqnOption.kspType " + kspType + ": gmres or idrs");
+            idrS = (int)a->numOr("idrS", idrS);
+            if (idrS < 1 || idrS > 16) throw Error("adjEqnOption.idrS: 1..16");
             globalPCIters = (int)a->numOr("globalPCIters", globalPCIters);
             {
                 const int cr = (int)a->numOr("pcColourRadius", pcExtraColourRadius);
@@ -2003,6 +2009,7 @@ struct Solver
     void coarseRestrict(const double* v);
     int kspExtraMatvecs = 0;
     int solveLinearEqn(const double* rhs, double* sol, KspStats& st);
+    int solveIdrs(const double* rhs, double* sol, KspStats& st);
 };
 
 } // namespace dab

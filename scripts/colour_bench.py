@@ -1,4 +1,4 @@
-"""Adjoint solve for several multicolour-ILU ordering radii (adjEqnOption.pcColourRadius) on the bench O-grid.
+"""Adjoint solve for several multicolour-ILU ordering radii (adjEqnOption.pcColourRadius) and Krylov methods (CB_KSP) on the bench O-grid.
 env: CB_CELLS, CB_RADII="0,2,4", CB_LIB (library path; default = the CUDA build), CB_AGG (coarse aggregates), CB_RESTART"""
 import json, os, sys, tempfile, time
 import numpy as np
@@ -23,14 +23,16 @@ sol.updateOFFields(W)
 dFdW = np.zeros(n)
 sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
 out = []
-for r in [int(x) for x in os.environ.get("CB_RADII", "0,2,4").split(",")]:
-    sol.updateDAOption(dict(opts, adjEqnOption=dict(adj, pcColourRadius=r)))
+ksps = os.environ.get("CB_KSP", "gmres").split(",")  # e.g. "gmres,idrs:4,idrs:8"
+for r, ksp_name in [(int(x), kk) for x in os.environ.get("CB_RADII", "0,2,4").split(",") for kk in ksps]:
+    kt, ks = (ksp_name.split(":") + ["4"])[:2]
+    sol.updateDAOption(dict(opts, adjEqnOption=dict(adj, pcColourRadius=r, kspType=kt, idrS=int(ks))))
     pc, ksp = Mat(), KSP()
     t0 = time.time(); sol.calcdRdWT(1, pc); sol.createMLRKSPMatrixFree(pc, ksp); t_pc = time.time() - t0
     psi = np.zeros(n)
     t0 = time.time(); fail = sol.solveLinearEqn(ksp, dFdW, psi); t = time.time() - t0
     st = ksp.stats
-    res = dict(cells=sol.getNLocalCells(), radius=r, fail=fail, iterations=st.iterations, pc_s=round(t_pc, 3), solve_s=round(t, 3),
+    res = dict(cells=sol.getNLocalCells(), radius=r, ksp=ksp_name, n_matvec=st.n_matvec, fail=fail, iterations=st.iterations, pc_s=round(t_pc, 3), solve_s=round(t, 3),
                gmres_device_s=round(st.solve_seconds, 3), rel_residual=st.final_residual / st.initial_residual)
     print(json.dumps(res), flush=True)
     out.append(res)

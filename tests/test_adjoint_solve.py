@@ -102,3 +102,45 @@ def test_two_level_preconditioner_reduces_iterations():
 def test_adjoint_solve_cuda():
     its = solve_and_check(None)
     assert 0 < its < 400
+
+
+def idrs_check(lib_path):
+    """adjEqnOption.kspType idrs (extension): IDR(s) with the same preconditioner, tolerance rule and statistics reaches the solution
+    of the dense direct solve; switching back to gmres in the same solver object still works; the iteration cap sets the fail flag."""
+    mesh, sol, W = adjoint_case(lib_path)
+    n = sol.getNLocalAdjointStates()
+    dFdW = np.zeros(n)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    psis, its = {}, {}
+    for name, extra in (("gmres", dict(kspType="gmres")), ("idrs4", dict(kspType="idrs", idrS=4)), ("idrs1", dict(kspType="idrs", idrS=1)),
+                        ("gmres2", dict(kspType="gmres"))):
+        sol.updateDAOption(dict(adjEqnOption=dict(gmresRelTol=1e-9, gmresMaxIters=1500, gmresRestart=200, **extra)))
+        psi = np.zeros(n)
+        assert sol.solveLinearEqn(ksp, dFdW, psi) == 0, name
+        st = ksp.stats
+        assert st.converged_reason == 2 and st.final_residual <= 1e-9 * st.initial_residual * 1.01, name
+        r = np.zeros(n)
+        sol.calcdRdWTPsiAD(psi, r)
+        assert np.linalg.norm(r - dFdW) <= 2e-9 * np.linalg.norm(dFdW), name
+        psis[name], its[name] = psi, st.iterations
+    assert np.array_equal(psis["gmres"], psis["gmres2"])
+    for name in ("idrs4", "idrs1"):
+        assert np.linalg.norm(psis[name] - psis["gmres"]) <= 1e-6 * np.linalg.norm(psis["gmres"]), name
+    assert its["idrs4"] < 3 * its["gmres"], its  # short recurrences cost some operator applications, not multiples
+    sol.updateDAOption(dict(adjEqnOption=dict(kspType="idrs", idrS=4, gmresMaxIters=5)))
+    psi = np.zeros(n)
+    assert sol.solveLinearEqn(ksp, dFdW, psi) == 1 and ksp.stats.converged_reason == -3 and ksp.stats.iterations == 5
+    with pytest.raises(Exception, match="kspType"):
+        sol.updateDAOption(dict(adjEqnOption=dict(kspType="cg")))
+
+
+def test_idrs_host_build():
+    idrs_check(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_idrs_cuda():
+    idrs_check(None)
