@@ -496,7 +496,7 @@ struct Krylov
     DevBuf<int32_t> dPerm, dIPerm;
     // matrix
     std::vector<int64_t> rowBase;
-    std::vector<int32_t> rowStride, rowLen, diag, hCol;
+    std::vector<int32_t> rowStride, rowLen, diag;
     DevBuf<int64_t> dRowBase;
     DevBuf<int32_t> dRowStride, dRowLen, dDiag, dCol;
     DevBuf<double> dVal, dDinv;

@@ -160,6 +160,7 @@ struct Solver
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
     std::string kspType = "gmres"; // adjEqnOption.kspType (extension): gmres (the reference's KSP) | idrs (IDR(s), short recurrences)
     int idrS = 4;
+    int pcSymbolicOnly = 0;
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
@@ -589,6 +590,7 @@ struct Solver
             pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
+            pcSymbolicOnly = (int)a->numOr("pcSymbolicOnly", pcSymbolicOnly);
             kspType = a->strOr("kspType", kspType);
             if (kspType != "gmres" && kspType != "idrs") throw Error("adjEqnOption.kspType " + kspType + ": gmres or idrs");
             idrS = (int)a->numOr("idrS", idrS);

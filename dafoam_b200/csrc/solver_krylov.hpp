@@ -6,6 +6,9 @@
 #include <chrono>
 #include <cstdio>
 
+#include <memory>
+#include <thread>
+
 namespace dab
 {
 
@@ -38,8 +41,20 @@ struct CellGraph
         }
         stamp.assign(nC, 0);
     }
+    // scratch of one traversal stream (one per host thread in the parallel pattern build)
+    struct Scratch
+    {
+        std::vector<int> stamp;
+        int tick = 0;
+    };
+    void ball(const int* seeds, int nSeeds, int radius, std::vector<int>& out) { ballWith(seeds, nSeeds, radius, out, stamp, tick); }
+    void ball(const int* seeds, int nSeeds, int radius, std::vector<int>& out, Scratch& sc) const
+    {
+        if ((int)sc.stamp.size() != nC) sc.stamp.assign(nC, 0);
+        ballWith(seeds, nSeeds, radius, out, sc.stamp, sc.tick);
+    }
     // cells within `radius` hops of the seeds (seeds included), appended to out (cleared first)
-    void ball(const int* seeds, int nSeeds, int radius, std::vector<int>& out)
+    void ballWith(const int* seeds, int nSeeds, int radius, std::vector<int>& out, std::vector<int>& stamp, int& tick) const
     {
         out.clear();
         tick++;
@@ -70,6 +85,36 @@ struct CellGraph
         }
     }
 };
+
+// host threads for the set-up loops whose iterations are independent (DAB_HOST_THREADS overrides; default: the hardware
+// concurrency, at most 64).  fn(threadIndex, begin, end); exceptions are re-thrown on the calling thread.
+inline int hostThreads()
+{
+    if (const char* e = getenv("DAB_HOST_THREADS")) return std::max(1, atoi(e));
+    const unsigned h = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(h ? h : 1u, 64u));
+}
+template <class Fn>
+void parallelFor(int n, int nThreads, Fn fn)
+{
+    nThreads = std::max(1, std::min(nThreads, n / 4096 + 1));
+    if (nThreads == 1)
+    {
+        fn(0, 0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    std::vector<std::string> err(nThreads);
+    for (int t = 0; t < nThreads; t++)
+        th.emplace_back([&, t]() {
+            const int b = (int)((int64_t)n * t / nThreads), e = (int)((int64_t)n * (t + 1) / nThreads);
+            try { fn(t, b, e); }
+            catch (const std::exception& ex) { err[t] = ex.what(); if (err[t].empty()) err[t] = "error"; }
+        });
+    for (auto& x : th) x.join();
+    for (auto& m : err)
+        if (!m.empty()) throw Error(m);
+}
 
 // greedy colouring: item i conflicts with the items listed by neighbours(i, out)
 template <class NbrFn>
@@ -105,8 +150,15 @@ inline void Solver::pcSymbolic()
     const int ns = nCellStates();
     const int offPhi = ns * nC;
     K.n = nDof();
+    auto tPrev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (printInfo) fprintf(stderr, "[dab200] pcSymbolic %-28s %.3f s\n", what, std::chrono::duration<double>(now - tPrev).count());
+        tPrev = now;
+    };
     CellGraph G;
     G.build(hm);
+    lap("cell graph");
     const int Lcc = pcConLevel, Lfc = 0, Lcf = 0;
     // owned faces per cell (a face belongs to the block of its owner cell)
     // (a cut face whose owner is a ghost sits in the block of its local cell; its row is a trivial identity row)
@@ -179,34 +231,46 @@ inline void Solver::pcSymbolic()
         K.colours.push_back(cv);
     }
     if (next != K.n) throw Error("calcdRdWT: ordering does not cover all states");
+    lap("ordering colours + permutation");
     // ---- 2. sparsity pattern (new numbering), two passes: lengths, then ELL fill
     const int nG = (int)groupRows.size();
     std::vector<int> width(nG, 0);
     K.rowLen.assign(K.n, 0);
-    std::vector<int> cellsBall, cols, faces;
-    auto cellRowCols = [&](int c) {
-        cols.clear();
-        G.ball(&c, 1, Lcc, cellsBall);
-        for (int x : cellsBall)
-        {
-            for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
-            for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
-        }
-        G.ball(&c, 1, Lfc, cellsBall);
-        faces.clear();
-        for (int x : cellsBall) facesOf(x, faces);
-        std::sort(faces.begin(), faces.end());
-        faces.erase(std::unique(faces.begin(), faces.end()), faces.end());
-        for (int f : faces) cols.push_back(K.iperm[offPhi + f]);
-        std::sort(cols.begin(), cols.end());
-    };
     auto faceSeeds = [&](int f, int* seeds) {
         int ns_ = 0;
         if (hm.own[f] < nC) seeds[ns_++] = hm.own[f];
         if (f < nIF && hm.nei[f] < nC) seeds[ns_++] = hm.nei[f];
         return ns_;
     };
-    auto faceRowCols = [&](int f) {
+    // per-thread scratch: the rows of different cells / faces are independent
+    struct Work
+    {
+        CellGraph::Scratch sc;
+        std::vector<int> cellsBall, cols, faces, width;
+        int64_t nnz = 0;
+    };
+    const int nThreads = detail::hostThreads();
+    std::vector<Work> work(nThreads);
+    for (Work& w : work) w.width.assign(nG, 0);
+    auto cellRowCols = [&](Work& w, int c) {
+        std::vector<int>& cols = w.cols;
+        cols.clear();
+        G.ball(&c, 1, Lcc, w.cellsBall, w.sc);
+        for (int x : w.cellsBall)
+        {
+            for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
+            for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
+        }
+        G.ball(&c, 1, Lfc, w.cellsBall, w.sc);
+        w.faces.clear();
+        for (int x : w.cellsBall) facesOf(x, w.faces);
+        std::sort(w.faces.begin(), w.faces.end());
+        w.faces.erase(std::unique(w.faces.begin(), w.faces.end()), w.faces.end());
+        for (int f : w.faces) cols.push_back(K.iperm[offPhi + f]);
+        std::sort(cols.begin(), cols.end());
+    };
+    auto faceRowCols = [&](Work& w, int f) {
+        std::vector<int>& cols = w.cols;
         cols.clear();
         if (hm.own[f] >= nC)
         {
@@ -215,8 +279,8 @@ inline void Solver::pcSymbolic()
         }
         int seeds[2];
         const int nSeeds = faceSeeds(f, seeds);
-        G.ball(seeds, nSeeds, Lcf, cellsBall);
-        for (int x : cellsBall)
+        G.ball(seeds, nSeeds, Lcf, w.cellsBall, w.sc);
+        for (int x : w.cellsBall)
         {
             for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
             for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
@@ -224,23 +288,32 @@ inline void Solver::pcSymbolic()
         cols.push_back(K.iperm[offPhi + f]);
         std::sort(cols.begin(), cols.end());
     };
-    for (int c = 0; c < nC; c++)
-    {
-        cellRowCols(c);
-        for (int s = 0; s < ns; s++)
+    detail::parallelFor(nC, nThreads, [&](int t, int b, int e) {
+        Work& w = work[t];
+        for (int c = b; c < e; c++)
         {
-            const int i = K.iperm[s < 3 ? 3 * c + s : s * nC + c];
-            K.rowLen[i] = (int)cols.size();
-            width[groupOfRow[i]] = std::max(width[groupOfRow[i]], (int)cols.size());
+            cellRowCols(w, c);
+            for (int s = 0; s < ns; s++)
+            {
+                const int i = K.iperm[s < 3 ? 3 * c + s : s * nC + c];
+                K.rowLen[i] = (int)w.cols.size();
+                w.width[groupOfRow[i]] = std::max(w.width[groupOfRow[i]], (int)w.cols.size());
+            }
         }
-    }
-    for (int f = 0; f < nF; f++)
-    {
-        faceRowCols(f);
-        const int i = K.iperm[offPhi + f];
-        K.rowLen[i] = (int)cols.size();
-        width[groupOfRow[i]] = std::max(width[groupOfRow[i]], (int)cols.size());
-    }
+    });
+    detail::parallelFor(nF, nThreads, [&](int t, int b, int e) {
+        Work& w = work[t];
+        for (int f = b; f < e; f++)
+        {
+            faceRowCols(w, f);
+            const int i = K.iperm[offPhi + f];
+            K.rowLen[i] = (int)w.cols.size();
+            w.width[groupOfRow[i]] = std::max(w.width[groupOfRow[i]], (int)w.cols.size());
+        }
+    });
+    lap("pattern: row lengths");
+    for (const Work& w : work)
+        for (int g = 0; g < nG; g++) width[g] = std::max(width[g], w.width[g]);
     std::vector<int64_t> gOff(nG + 1, 0);
     for (int g = 0; g < nG; g++) gOff[g + 1] = gOff[g] + (int64_t)width[g] * groupRows[g];
     K.ellSize = gOff[nG];
@@ -253,27 +326,40 @@ inline void Solver::pcSymbolic()
         K.rowBase[i] = gOff[g] + (i - groupStart[g]);
         K.rowStride[i] = groupRows[g];
     }
-    K.hCol.assign((size_t)K.ellSize, -1);
+    // uninitialised on purpose: every row writes its own entries *and* its padding below, so the 4*ellSize bytes (2.7 GB at 1M
+    // cells) are first touched by the worker threads instead of one serial fill
+    std::unique_ptr<int32_t[]> hCol(new int32_t[(size_t)K.ellSize]);
     K.nnz = 0;
-    auto putRow = [&](int i) {
+    lap("pattern: ELL allocation");
+    auto putRow = [&](Work& w, int i) {
+        const std::vector<int>& cols = w.cols;
         for (size_t e = 0; e < cols.size(); e++)
         {
-            K.hCol[(size_t)(K.rowBase[i] + (int64_t)e * K.rowStride[i])] = cols[e];
+            hCol[(size_t)(K.rowBase[i] + (int64_t)e * K.rowStride[i])] = cols[e];
             if (cols[e] == i) K.diag[i] = (int)e;
         }
-        K.nnz += (int64_t)cols.size();
+        for (int e = (int)cols.size(); e < width[groupOfRow[i]]; e++) hCol[(size_t)(K.rowBase[i] + (int64_t)e * K.rowStride[i])] = -1;
+        w.nnz += (int64_t)cols.size();
         if (K.diag[i] < 0) throw Error("calcdRdWT: missing diagonal in the pattern");
     };
-    for (int c = 0; c < nC; c++)
-    {
-        cellRowCols(c);
-        for (int s = 0; s < ns; s++) putRow(K.iperm[s < 3 ? 3 * c + s : s * nC + c]);
-    }
-    for (int f = 0; f < nF; f++)
-    {
-        faceRowCols(f);
-        putRow(K.iperm[offPhi + f]);
-    }
+    detail::parallelFor(nC, nThreads, [&](int t, int b, int e) {
+        Work& w = work[t];
+        for (int c = b; c < e; c++)
+        {
+            cellRowCols(w, c);
+            for (int s = 0; s < ns; s++) putRow(w, K.iperm[s < 3 ? 3 * c + s : s * nC + c]);
+        }
+    });
+    detail::parallelFor(nF, nThreads, [&](int t, int b, int e) {
+        Work& w = work[t];
+        for (int f = b; f < e; f++)
+        {
+            faceRowCols(w, f);
+            putRow(w, K.iperm[offPhi + f]);
+        }
+    });
+    for (const Work& w : work) K.nnz += w.nnz;
+    lap("pattern: ELL fill");
     // ---- 3. colouring of the perturbations (DAColoring role).  Two states may share a colour when no
     // residual row in the pattern of one is touched by the other: cells at distance > Lcc + 3 (the
     // first-order pRes reaches 3 levels), faces whose cells are more than Lcf + 1 hops apart.
@@ -303,6 +389,7 @@ inline void Solver::pcSymbolic()
         std::vector<int> pos(cnt.begin(), cnt.end() - 1);
         for (int j = 0; j < K.n; j++) K.fdList[pos[fdColourOf(j)]++] = j;
     }
+    lap("perturbation colours");
     // ---- upload
     K.dPerm.upload(be, K.perm);
     K.dIPerm.upload(be, K.iperm);
@@ -310,15 +397,17 @@ inline void Solver::pcSymbolic()
     K.dRowStride.upload(be, K.rowStride);
     K.dRowLen.upload(be, K.rowLen);
     K.dDiag.upload(be, K.diag);
-    K.dCol.upload(be, K.hCol);
+    K.dCol.alloc(be, (size_t)K.ellSize, false);
+    be.h2d(K.dCol.p, hCol.get(), (size_t)K.ellSize * sizeof(int32_t));
+    hCol.reset();
     K.dVal.alloc(be, (size_t)K.ellSize);
     K.dFdList.upload(be, K.fdList);
     K.R0.alloc(be, K.n);
     K.R1.alloc(be, K.n);
     K.t1.alloc(be, K.n);
     K.t2.alloc(be, K.n);
-    std::vector<int32_t>().swap(K.hCol);
     K.symbolic = true;
+    lap("upload");
     if (printInfo)
         fprintf(stderr, "[dab200] dRdWTPC: %d states, %lld nonzeros (%.1f/row), ELL %lld, %d ordering colours, %d FD colours (%d cell x %d + %d face)\n",
                 K.n, (long long)K.nnz, (double)K.nnz / K.n, (long long)K.ellSize, nCol, nFd, nFdCell, ns, nFdFace);
@@ -329,6 +418,7 @@ inline void Solver::calcPC()
     const auto t0 = std::chrono::steady_clock::now();
     Krylov& K = kry;
     if (!K.symbolic) pcSymbolic();
+    if (pcSymbolicOnly) return; // profiling hook (adjEqnOption.pcSymbolicOnly): host set-up only, nothing assembled
     be.zero(K.dVal.p, (size_t)K.ellSize * sizeof(double));
     StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi};
     if (par.comp)
