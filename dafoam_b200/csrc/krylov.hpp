@@ -432,6 +432,19 @@ struct CoarseUnit // x = indicator of the pressure DOFs of local aggregate a (a 
     }
 };
 
+struct CoarseUnitColour // x = indicator of the pressure DOFs of every local aggregate of probing colour k
+{
+    const int32_t* aggOf;
+    const int32_t* aggColour;
+    int offP, nC, k;
+    double* x;
+    DAB_HD void operator()(int i) const
+    {
+        const int c = i - offP;
+        x[i] = (c >= 0 && c < nC && aggColour[aggOf[c]] == k) ? 1.0 : 0.0;
+    }
+};
+
 struct Coarse
 {
     bool enabled = false, valid = false;

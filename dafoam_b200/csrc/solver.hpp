@@ -161,6 +161,7 @@ struct Solver
     std::string kspType = "gmres"; // adjEqnOption.kspType (extension): gmres (the reference's KSP) | idrs (IDR(s), short recurrences)
     int idrS = 4;
     int pcSymbolicOnly = 0;
+    int coarseProbeReach = 6; // cell levels a pressure perturbation reaches through the transposed Jacobian (coloured probing of the coarse operator; 0 = one product per aggregate)
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
@@ -591,6 +592,10 @@ struct Solver
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
             pcSymbolicOnly = (int)a->numOr("pcSymbolicOnly", pcSymbolicOnly);
+            {
+                const int pr = (int)a->numOr("coarseProbeReach", coarseProbeReach);
+                if (pr != coarseProbeReach) { coarseProbeReach = pr; kry.pcValid = false; }
+            }
             kspType = a->strOr("kspType", kspType);
             if (kspType != "gmres" && kspType != "idrs") throw Error("adjEqnOption.kspType " + kspType + ": gmres or idrs");
             idrS = (int)a->numOr("idrS", idrS);

@@ -557,14 +557,80 @@ inline void Solver::coarseSetup()
     const int Kg = Cs.nAggGlobal;
     Cs.lu.assign((size_t)Kg * Kg, 0.0);
     ensureRecorded();
-    for (int j = 0; j < Kg; j++)
+    int nProbes = 0;
+    if (nRanks == 1 && coarseProbeReach > 0 && nAgg > 64)
     {
-        const int local = (j >= Cs.aggBase && j < Cs.aggBase + nAgg) ? j - Cs.aggBase : -1;
-        be.launch(n, CoarseUnit{Cs.dAggOf.p, offP, nC, local, K.t2.p});
-        matVecDev(K.t2.p, K.t3.p);
-        coarseRestrict(K.t3.p);
-        for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
+        // Coloured probing (one GPU): the transposed Jacobian couples a pressure DOF to residual rows at most `coarseProbeReach` cell
+        // levels away, far less than an aggregate's diameter, so aggregates whose reach sets N(a) (the aggregates within that many
+        // levels of a's cells) are disjoint share one probing vector; entry (i, a) is read from the restricted response at the only
+        // aggregate a of the colour with i in N(a).  ~10-20 products instead of one per aggregate.  A response outside every reach
+        // set means the reach was too short: fall back to one product per aggregate.
+        std::vector<std::vector<int>> reach(nAgg);
+        {
+            std::vector<int> ballCells, seeds;
+            std::vector<int> mark(nAgg, -1);
+            for (int a = 0; a < nAgg; a++)
+            {
+                seeds.assign(cells.begin() + cnt[a], cells.begin() + cnt[a + 1]);
+                G.ball(seeds.data(), (int)seeds.size(), coarseProbeReach, ballCells);
+                for (int c : ballCells)
+                    if (mark[aggOf[c]] != a)
+                    {
+                        mark[aggOf[c]] = a;
+                        reach[a].push_back(aggOf[c]);
+                    }
+            }
+        }
+        std::vector<std::vector<int>> reachedBy(nAgg); // i -> the aggregates a with i in N(a)
+        for (int a = 0; a < nAgg; a++)
+            for (int i : reach[a]) reachedBy[i].push_back(a);
+        std::vector<int> colour;
+        const int nColours = detail::greedyColour(nAgg, [&](int a, std::vector<int>& out) {
+            out.clear();
+            for (int i : reach[a])
+                for (int b : reachedBy[i]) out.push_back(b);
+        }, colour);
+        std::vector<int32_t> colour32(colour.begin(), colour.end());
+        DevBuf<int32_t> dColour;
+        dColour.upload(be, colour32);
+        bool ok = true;
+        std::vector<int> owner(nAgg);
+        for (int k = 0; k < nColours && ok; k++)
+        {
+            be.launch(n, CoarseUnitColour{Cs.dAggOf.p, dColour.p, offP, nC, k, K.t2.p});
+            matVecDev(K.t2.p, K.t3.p);
+            coarseRestrict(K.t3.p);
+            nProbes++;
+            std::fill(owner.begin(), owner.end(), -1);
+            for (int a = 0; a < nAgg; a++)
+                if (colour[a] == k)
+                    for (int i : reach[a]) owner[i] = a;
+            double big = 0.0;
+            for (int i = 0; i < Kg; i++) big = std::max(big, std::fabs(Cs.hRc[i]));
+            for (int i = 0; i < Kg && ok; i++)
+            {
+                if (owner[i] >= 0) Cs.lu[(size_t)i * Kg + owner[i]] = Cs.hRc[i];
+                else if (std::fabs(Cs.hRc[i]) > 1e-12 * big) ok = false;
+            }
+        }
+        if (!ok)
+        {
+            if (printInfo) fprintf(stderr, "[dab200] coarse space: probing reach %d too short, falling back to one product per aggregate\n", coarseProbeReach);
+            std::fill(Cs.lu.begin(), Cs.lu.end(), 0.0);
+            nProbes = 0;
+        }
+        else if (printInfo)
+            fprintf(stderr, "[dab200] coarse space: %d aggregates probed with %d coloured products\n", nAgg, nProbes);
     }
+    if (nProbes == 0)
+        for (int j = 0; j < Kg; j++)
+        {
+            const int local = (j >= Cs.aggBase && j < Cs.aggBase + nAgg) ? j - Cs.aggBase : -1;
+            be.launch(n, CoarseUnit{Cs.dAggOf.p, offP, nC, local, K.t2.p});
+            matVecDev(K.t2.p, K.t3.p);
+            coarseRestrict(K.t3.p);
+            for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
+        }
     Cs.factor();
     Cs.valid = true;
     (void)offP;

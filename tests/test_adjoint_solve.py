@@ -144,3 +144,27 @@ def test_idrs_host_build():
 @pytest.mark.gpu
 def test_idrs_cuda():
     idrs_check(None)
+
+
+def test_coloured_probing_gives_the_same_coarse_operator(capfd):
+    """The coarse Galerkin operator probed with a few coloured products (coarseProbeReach, default 6) is the one probed with one
+    product per aggregate: same GMRES history, same solution; a reach that is too short is detected and falls back."""
+    out = {}
+    for reach in (0, 6, 1):
+        mesh, sol, W = adjoint_case(HOSTSIM, ni=96, nj=48)
+        sol.updateDAOption(dict(adjEqnOption=dict(coarseAggregates=100, coarseProbeReach=reach, gmresRelTol=1e-8, gmresMaxIters=900, gmresRestart=300, printInfo=1)))
+        n = sol.getNLocalAdjointStates()
+        b = np.zeros(n)
+        sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), b)
+        pc, ksp = Mat(), KSP()
+        sol.calcdRdWT(1, pc)
+        psi = np.zeros(n)
+        assert sol.solveLinearEqn(ksp, b, psi) == 0
+        out[reach] = (psi, ksp.stats.iterations, capfd.readouterr().err)
+    import re
+    for reach in (6, 1):
+        assert out[reach][1] == out[0][1], {k: v[1] for k, v in out.items()}
+        assert np.linalg.norm(out[reach][0] - out[0][0]) <= 1e-9 * np.linalg.norm(out[0][0])
+    m = re.search(r"coarse space: (\d+) aggregates probed with (\d+) coloured products", out[6][2])
+    assert m and int(m.group(1)) >= 100 and int(m.group(2)) < int(m.group(1)) // 2, out[6][2][-400:]
+    assert "too short, falling back" in out[1][2] and "coloured products" not in out[0][2]
