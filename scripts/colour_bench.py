@@ -26,7 +26,8 @@ out = []
 ksps = os.environ.get("CB_KSP", "gmres").split(",")  # e.g. "gmres,idrs:4,idrs:8"
 for r, ksp_name in [(int(x), kk) for x in os.environ.get("CB_RADII", "0,2,4").split(",") for kk in ksps]:
     kt, ks = (ksp_name.split(":") + ["4"])[:2]
-    sol.updateDAOption(dict(opts, adjEqnOption=dict(adj, pcColourRadius=r, kspType=kt, idrS=int(ks))))
+    sol.updateDAOption(dict(opts, adjEqnOption=dict(adj, pcColourRadius=r, kspType=kt, idrS=int(ks),
+                                                    gmresMaxIters=adj["gmresMaxIters"] * (3 if kt == "idrs" else 1))))
     pc, ksp = Mat(), KSP()
     t0 = time.time(); sol.calcdRdWT(1, pc); sol.createMLRKSPMatrixFree(pc, ksp); t_pc = time.time() - t0
     psi = np.zeros(n)
