@@ -478,6 +478,42 @@ struct Coarse
             }
         }
     }
+    // explicit inverse, transposed (invT[j*n + i] = (A^-1)[i][j]): applied on the device as a coalesced GEMV (CoarseApply), so a
+    // preconditioner application needs no host round trip.  Columns are independent: solved on host threads.
+    DevBuf<double> dInvT;
+    template <class ParallelFor>
+    void invertTransposed(std::vector<double>& invT, ParallelFor pfor) const
+    {
+        const int n = nAggGlobal;
+        invT.assign((size_t)n * n, 0.0);
+        pfor(n, [&](int, int b, int e) {
+            std::vector<double> x(n);
+            for (int j = b; j < e; j++)
+            {
+                std::fill(x.begin(), x.end(), 0.0);
+                x[j] = 1.0;
+                // P b, then L y = P b and U x = y with row-wise (contiguous) sweeps
+                for (int k = 0; k < n; k++) std::swap(x[k], x[piv[k]]);
+                int first = 0;
+                while (first < n && x[first] == 0.0) first++;
+                for (int i = first + 1; i < n; i++)
+                {
+                    const double* row = &lu[(size_t)i * n];
+                    double s2 = x[i];
+                    for (int k = first; k < i; k++) s2 -= row[k] * x[k];
+                    x[i] = s2;
+                }
+                for (int i = n - 1; i >= 0; i--)
+                {
+                    const double* row = &lu[(size_t)i * n];
+                    double s2 = x[i];
+                    for (int k = i + 1; k < n; k++) s2 -= row[k] * x[k];
+                    x[i] = s2 / row[i];
+                }
+                for (int i = 0; i < n; i++) invT[(size_t)j * n + i] = x[i]; // column j of A^-1 = row j of invT
+            }
+        });
+    }
     void solve(double* b) const
     {
         const int n = nAggGlobal;

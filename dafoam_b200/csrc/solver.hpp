@@ -2013,7 +2013,7 @@ struct Solver
     void applyPC(const double* v, double* z);
     void applyIlu(const double* v, double* z);
     void coarseSetup();
-    void coarseRestrict(const double* v);
+    void coarseRestrict(const double* v, bool toHost = true);
     int kspExtraMatvecs = 0;
     int solveLinearEqn(const double* rhs, double* sol, KspStats& st);
     int solveIdrs(const double* rhs, double* sol, KspStats& st);

@@ -632,12 +632,28 @@ inline void Solver::coarseSetup()
             for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
         }
     Cs.factor();
+    {
+        std::vector<double> invT;
+        Cs.invertTransposed(invT, [&](int nItems, auto fn) {
+            // small systems: one thread; the columns of the inverse are independent
+            const int nt = nItems >= 256 ? detail::hostThreads() : 1;
+            if (nt == 1) fn(0, 0, nItems);
+            else
+            {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nt; t++)
+                    th.emplace_back([&, t]() { fn(t, (int)((int64_t)nItems * t / nt), (int)((int64_t)nItems * (t + 1) / nt)); });
+                for (auto& x : th) x.join();
+            }
+        });
+        Cs.dInvT.upload(be, invT);
+    }
     Cs.valid = true;
     (void)offP;
 }
 
 // hRc = P^T v (global coarse vector on the host, summed over ranks)
-inline void Solver::coarseRestrict(const double* v)
+inline void Solver::coarseRestrict(const double* v, bool toHost)
 {
     Coarse& Cs = kry.coarse;
     const int offP = 3 * hm.nC;
@@ -645,7 +661,7 @@ inline void Solver::coarseRestrict(const double* v)
     be.zero(Cs.dRc.p, (size_t)Cs.nAggGlobal * sizeof(double));
     be.launch(Cs.nAggLocal, CoarseRestrict2{Cs.dPartial.p, Cs.dAggChunkOff.p, Cs.dRc.p + Cs.aggBase});
     comm.allreduceSum(be, Cs.dRc.p, Cs.nAggGlobal);
-    be.d2h(Cs.hRc.data(), Cs.dRc.p, (size_t)Cs.nAggGlobal * sizeof(double));
+    if (toHost) be.d2h(Cs.hRc.data(), Cs.dRc.p, (size_t)Cs.nAggGlobal * sizeof(double));
 }
 
 // z = M^{-1} v  (external layout in and out).  With the coarse space: multiplicative two-level,
@@ -657,9 +673,9 @@ inline void Solver::applyPC(const double* v, double* z)
     {
         Coarse& Cs = K.coarse;
         const int n = nDof();
-        coarseRestrict(v);
-        Cs.solve(Cs.hRc.data());
-        be.h2d(Cs.dYc.p, Cs.hRc.data(), (size_t)Cs.nAggGlobal * sizeof(double));
+        // coarse solve on the device: yc = Ac^-1 rc as a GEMV with the explicit (transposed) inverse -- no host round trip
+        coarseRestrict(v, false);
+        be.launch(Cs.nAggGlobal, CoarseApply{Cs.dInvT.p, Cs.dRc.p, Cs.nAggGlobal, Cs.dYc.p});
         be.launch(n, CoarseProlong{Cs.dYc.p, Cs.dAggOf.p, 3 * hm.nC, hm.nC, Cs.aggBase, K.t2.p}); // z1
         matVecDev(K.t2.p, K.t3.p);
         kspExtraMatvecs++;

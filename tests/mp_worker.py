@@ -156,6 +156,15 @@ def main():
     assert fs == 0 and fp == 0, (fs, fp, ks.stats.iterations, kp.stats.iterations)
     e4 = np.linalg.norm(xp[owned] - xs[idx][owned]) / np.linalg.norm(xs)
     assert e4 < (1e-3 if comp else 1e-6), e4  # compressible: both solves stop at rtol 1e-6 of an ill-scaled system
+    if not comp:
+        # two-level preconditioner (restriction all-reduced, coarse GEMV on every rank) with IDR(4) across the two ranks
+        par.updateDAOption(dict(adjEqnOption=dict(coarseAggregates=12, kspType="idrs", idrS=4, gmresMaxIters=3000)))
+        par.calcdRdWT(1, mp_)
+        xq = np.zeros(idx.size)
+        fq = par.solveLinearEqn(kp, dl, xq)
+        assert fq == 0, (fq, kp.stats.iterations)
+        e5 = np.linalg.norm(xq[owned] - xs[idx][owned]) / np.linalg.norm(xs)
+        assert e5 < 1e-5, e5
     print("rank %d ok: residual %.1e dRdWTPsi %.1e dFdW %.1e psi %.1e (its serial %d, 2 ranks %d)"
           % (rank, e1, e2, e3, e4, ks.stats.iterations, kp.stats.iterations), flush=True)
     dist.barrier()
