@@ -223,6 +223,160 @@ struct RevA
     }
 };
 
+// ---- lane-per-face pilot of RevA (DAB_LANES=1, one GPU) --------------------------------------------------------------------
+// Same arithmetic as RevA with a different thread mapping: 8 lanes per cell, lane k gathers face k (k, k+8, ... for polyhedra) and the
+// 14 per-cell accumulators are summed over the 8 lanes with a fixed xor-butterfly (__shfl_xor_sync 1, 2, 4), lane 0 finishing the cell.
+// Motivation: the cell-per-thread kernels are latency-bound at 18-35 % occupancy; this mapping puts 8x the
+// gathers of a cell in flight at once with a fraction of the live registers per thread.  The summation order differs from RevA
+// (butterfly instead of face order): results agree to rounding, and stay bitwise reproducible run to run.  The host build runs the
+// 8 lanes of a cell in sequence and reduces in the same butterfly order, so host and device give the same bits.
+constexpr int REV_LANES = 8;
+struct RevAAcc
+{
+    double v[14]; // HbA[3] | rAUb | pb | gPb[3] | Ub[3] | refb[3]
+};
+
+DAB_HD void revAFace(const MeshView& m, const Params& q, const StateView& s, const RecordView& r, const AdjView& a, const PsiView& x, int c,
+                     const FaceRef& fr, double psiPc, RevAAcc& A)
+{
+    const int nT = m.nCtot;
+    double* HbA = A.v;
+    double& rAUb = A.v[3];
+    double& pb = A.v[4];
+    double* gPb = A.v + 5;
+    double* Ub = A.v + 8;
+    double* refb = A.v + 11;
+    const int f = fr.f;
+    const double mS = m.magSf[f], dl = m.delta[f];
+    const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
+    const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
+    if (!fr.bnd)
+    {
+        const int n = fr.n;
+        const double psiPn = x.p[n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
+        const double Fb = cphi * x.phi[f] - fr.s * (psiPc - psiPn);
+        const double w = m.w[f];
+        const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
+        const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
+        double cg = 0.0;
+        for (int j = 0; j < 3; j++) cg += kv[j] * (wc * r.gP[(size_t)j * nT + c] + wn * r.gP[(size_t)j * nT + n]);
+        const double sn = fr.s * dl * (s.p[n] - s.p[c]) + cg;
+        const double gam = wc * r.rAU[c] + wn * r.rAU[n];
+        for (int j = 0; j < 3; j++)
+        {
+            HbA[j] += wc * Sv[j] * Fb;
+            gPb[j] -= gam * mS * wc * kv[j] * Fb;
+        }
+        rAUb -= wc * mS * sn * Fb;
+        pb += fr.s * gam * mS * dl * Fb;
+    }
+    else
+    {
+        const int b = f - m.nIF, pa = m.bPatch[b];
+        const double phib = s.phi[f];
+        const double Fb = cphi * x.phi[f] - psiPc;
+        const int kU = q.bcKind[F_U][pa];
+        const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
+        if (m.mrfType && m.mrfType[b] == 1)
+            ;
+        else if (q.constrainHbyA && !assignable)
+        {
+            const double im = 1.0 / mS;
+            const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+            const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
+            const double sngb[3] = {0.0, 0.0, 0.0};
+            bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
+            if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, phib, dl, valb, sngb, refb);
+        }
+        else
+            for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * Fb;
+        double pv, sn, frp;
+        bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, sn, frp);
+        rAUb -= mS * sn * Fb;
+        const double snb = -r.rAU[c] * mS * Fb;
+        pb -= frp * dl * snb;
+    }
+}
+
+struct RevALanes
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    PsiView x;
+    DAB_HD void lane(int c, int ln, double psiPc, RevAAcc& A) const
+    {
+        for (int i = 0; i < 14; i++) A.v[i] = 0.0;
+        for (int k = ln; k < m.maxCF; k += REV_LANES)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            revAFace(m, q, s, r, a, x, c, fr, psiPc, A);
+        }
+    }
+    DAB_HD void finish(int c, const RevAAcc& A) const
+    {
+        const int nT = m.nCtot, nC = m.nC;
+        const double* HbA = A.v;
+        const double V = m.V[c];
+        const double rAU = r.rAU[c];
+        const double cU = q.nrU ? 1.0 : V;
+        const double D0 = r.D0[c];
+        double rAUtot = A.v[3];
+        double Mbv[3];
+        for (int j = 0; j < 3; j++)
+        {
+            const double M = (s.U[3 * c + j] - r.HbyA[(size_t)j * nT + c]) / rAU;
+            const double psiU = cU * x.U[3 * c + j];
+            const double Mb = psiU - rAU * HbA[j];
+            Mbv[j] = Mb;
+            rAUtot -= M * HbA[j];
+            const double mt = Mb / V;
+            a.mt[(size_t)j * nT + c] = mt;
+            a.Udir[(size_t)j * nC + c] = A.v[8 + j] + HbA[j] + D0 * mt;
+            a.gPb[(size_t)j * nT + c] = A.v[5 + j] + psiU;
+        }
+        if (m.mrfCell && m.mrfCell[c])
+        {
+            const double* w = m.mrfOmega;
+            a.Udir[c] += Mbv[1] * w[2] - Mbv[2] * w[1];
+            a.Udir[(size_t)nC + c] += Mbv[2] * w[0] - Mbv[0] * w[2];
+            a.Udir[(size_t)2 * nC + c] += Mbv[0] * w[1] - Mbv[1] * w[0];
+        }
+        a.Dn[c] = -rAU * rAU * rAUtot / V;
+        a.pdir[c] = A.v[4];
+        if (a.bcRefb)
+            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] = A.v[11 + j];
+    }
+    DAB_HD void operator()(int t) const
+    {
+        const int c = t / REV_LANES, ln = t - c * REV_LANES;
+        const double psiPc = x.p[c] * (q.nrP ? 1.0 / m.V[c] : 1.0);
+#if defined(__CUDA_ARCH__)
+        RevAAcc A;
+        lane(c, ln, psiPc, A);
+        // groups of 8 lanes are entirely inside or outside the launch (n = 8 nC), so the active mask is made of whole groups
+        const unsigned mask = __activemask();
+        for (int off = 1; off < REV_LANES; off <<= 1)
+            for (int i = 0; i < 14; i++) A.v[i] += __shfl_xor_sync(mask, A.v[i], off);
+        if (ln == 0) finish(c, A);
+#else
+        if (ln != 0) return;
+        RevAAcc L[REV_LANES], T[REV_LANES];
+        for (int l = 0; l < REV_LANES; l++) lane(c, l, psiPc, L[l]);
+        for (int off = 1; off < REV_LANES; off <<= 1)
+        {
+            for (int l = 0; l < REV_LANES; l++)
+                for (int i = 0; i < 14; i++) T[l].v[i] = L[l].v[i] + L[l ^ off].v[i];
+            for (int l = 0; l < REV_LANES; l++) L[l] = T[l];
+        }
+        finish(c, L[0]);
+#endif
+    }
+};
+
 // FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in, bit 2 = adjoint of the
 // boundary reference values (patchVelocity input) compiled in (the common
 // configuration without them keeps its register budget)

@@ -1258,6 +1258,13 @@ struct Solver
     // y = diag(n) (dR/dW)^T x on device vectors (external layout)
     void launchRevA(const PsiView& pv)
     {
+        // DAB_LANES=1: lane-per-face pilot mapping of RevA (rev_kernels.hpp RevALanes); the default stays the measured cell-per-thread kernel
+        static const bool lanes = getenv("DAB_LANES") && atoi(getenv("DAB_LANES")) > 0;
+        if (lanes && hm.nC < (1 << 28))
+        {
+            be.launch(hm.nC * REV_LANES, RevALanes{mv, par, sv, rv, av, pv});
+            return;
+        }
         DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
     }
 

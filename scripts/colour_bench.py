@@ -1,5 +1,5 @@
 """Adjoint solve for several multicolour-ILU ordering radii (adjEqnOption.pcColourRadius) and Krylov methods (CB_KSP) on the bench O-grid.
-env: CB_CELLS, CB_RADII="0,2,4", CB_LIB (library path; default = the CUDA build), CB_AGG (coarse aggregates), CB_RESTART"""
+env: CB_SOLVER (DASimpleFoam | DARhoSimpleFoam), CB_CELLS, CB_RADII="0,2,4", CB_LIB (library path; default = the CUDA build), CB_AGG (coarse aggregates), CB_RESTART"""
 import json, os, sys, tempfile, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,15 +10,26 @@ cells = int(os.environ.get("CB_CELLS", 250000))
 nj = max(8, int(round((cells / 2.0) ** 0.5 / 2.0)) * 2)
 mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1)
 d = tempfile.mkdtemp(prefix="dab_cb_")
-cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
+comp = os.environ.get("CB_SOLVER", "DASimpleFoam") == "DARhoSimpleFoam"
+U0c = (100.0, 0.0, 0.0)
+thermo = cases.default_thermo() if comp else None
+if comp:
+    cases.write_case(d, mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c)), binary=True, thermo=thermo)
+else:
+    cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
 fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
 adj = dict(gmresRelTol=1e-6, gmresMaxIters=3000, gmresRestart=int(os.environ.get("CB_RESTART", 1500)), printInfo=0, pcConLevel=3,
            coarseAggregates=int(os.environ.get("CB_AGG", 1000)))
-opts = dict(normalizeStates=dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0), function=fn, adjEqnOption=adj)
-sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=os.environ.get("CB_LIB") or None)
+ns = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0)
+opts = dict(normalizeStates=ns, function=fn, adjEqnOption=adj)
+if comp:
+    opts["normalizeResiduals"] = ["URes", "pRes", "TRes", "nuTildaRes", "phiRes"]
+sol = pyDASolvers(("DARhoSimpleFoam" if comp else "DASimpleFoam") + " -python", opts, caseDir=d, _lib_path=os.environ.get("CB_LIB") or None)
 n = sol.getNLocalAdjointStates()
 y = np.zeros(sol.getNLocalCells()); sol.getOFField("yWall", "scalar", y)
-W = cases.boundary_layer_state(mesh, y, noise=0.001)
+W = cases.boundary_layer_state(mesh, y, U0=U0c, seed=1234, noise=0.001) if comp else cases.boundary_layer_state(mesh, y, noise=0.001)
+if comp:
+    W = cases.to_compressible_state(mesh, W, thermo)
 sol.updateOFFields(W)
 dFdW = np.zeros(n)
 sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)

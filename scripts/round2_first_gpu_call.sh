@@ -21,3 +21,7 @@ cat gpurun_out/${tag}_colour_bench.log
 # 4. config 3 (DARhoSimpleFoam, 2M cells): first timing of the compressible kernels
 timeout 300 python bench.py --solver DARhoSimpleFoam --cells 2000000 --no-cpu-baseline > gpurun_out/${tag}_bench_rhosimple_2m.json 2> gpurun_out/${tag}_bench_rhosimple_2m.err
 tail -c 1500 gpurun_out/${tag}_bench_rhosimple_2m.json
+# 5. lane-per-face pilot of RevA (8 lanes per cell + butterfly reduction) against the cell-per-thread kernel, and its parity on the device
+KB_QUIET=1 timeout 120 python scripts/kbench.py > gpurun_out/${tag}_kbench_cells.txt 2>&1; tail -1 gpurun_out/${tag}_kbench_cells.txt
+KB_QUIET=1 DAB_LANES=1 timeout 120 python scripts/kbench.py > gpurun_out/${tag}_kbench_lanes.txt 2>&1; tail -1 gpurun_out/${tag}_kbench_lanes.txt
+DAB_LANES=1 timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider 2>&1 | tail -2
