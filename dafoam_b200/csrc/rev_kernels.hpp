@@ -357,8 +357,11 @@ struct RevALanes
 #if defined(__CUDA_ARCH__)
         RevAAcc A;
         lane(c, ln, psiPc, A);
-        // groups of 8 lanes are entirely inside or outside the launch (n = 8 nC), so the active mask is made of whole groups
-        const unsigned mask = __activemask();
+        // the participating lanes are known a priori (the launch has n = 8 nC threads and 128-thread blocks, so a warp holds threads
+        // [t0, t0+32) with t0 a multiple of 32); naming them explicitly makes __shfl_xor_sync reconverge the warp after the
+        // divergent face loop -- __activemask() would not be safe under independent thread scheduling
+        const long long left = (long long)REV_LANES * m.nC - (long long)(t - (t & 31));
+        const unsigned mask = left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u);
         for (int off = 1; off < REV_LANES; off <<= 1)
             for (int i = 0; i < 14; i++) A.v[i] += __shfl_xor_sync(mask, A.v[i], off);
         if (ln == 0) finish(c, A);
