@@ -14,7 +14,9 @@
 #include "backend.hpp"
 #include "views.hpp"
 #include "comm.hpp"
+#include <atomic>
 #include <cmath>
+#include <thread>
 #include <cstdint>
 #include <vector>
 
@@ -454,10 +456,17 @@ struct Coarse
     std::vector<double> lu;   // dense LU of the Galerkin coarse operator (row-major, nAggGlobal^2)
     std::vector<int> piv;
     std::vector<double> hRc;
-    void factor()
+    // LU with partial pivoting; nThreads > 1: the row updates of every elimination step are shared by persistent host threads
+    // (spin barrier between steps) -- same arithmetic per entry as the serial loop, so the factors do not depend on the thread count
+    void factor(int nThreads = 1)
     {
         const int n = nAggGlobal;
         piv.resize(n);
+        if (nThreads > 1 && n >= 512)
+        {
+            factorThreaded(nThreads);
+            return;
+        }
         for (int k = 0; k < n; k++)
         {
             int p = k;
@@ -477,6 +486,58 @@ struct Coarse
                     for (int j = k + 1; j < n; j++) lu[(size_t)i * n + j] -= l * lu[(size_t)k * n + j];
             }
         }
+    }
+    void factorThreaded(int nThreads)
+    {
+        const int n = nAggGlobal;
+        std::atomic<int> arrived{0}, generation{0};
+        std::atomic<bool> singular{false};
+        auto barrier = [&]() {
+            const int g = generation.load(std::memory_order_acquire);
+            if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == nThreads)
+            {
+                arrived.store(0, std::memory_order_relaxed);
+                generation.store(g + 1, std::memory_order_release);
+            }
+            else
+                while (generation.load(std::memory_order_acquire) == g) std::this_thread::yield();
+        };
+        auto worker = [&](int t) {
+            for (int k = 0; k < n; k++)
+            {
+                if (t == 0)
+                {
+                    int p = k;
+                    double mx = std::fabs(lu[(size_t)k * n + k]);
+                    for (int i = k + 1; i < n; i++)
+                        if (std::fabs(lu[(size_t)i * n + k]) > mx) { mx = std::fabs(lu[(size_t)i * n + k]); p = i; }
+                    piv[k] = p;
+                    if (p != k)
+                        for (int j = 0; j < n; j++) std::swap(lu[(size_t)k * n + j], lu[(size_t)p * n + j]);
+                    if (lu[(size_t)k * n + k] == 0.0) singular.store(true);
+                }
+                barrier();
+                if (singular.load()) return;
+                const double d = lu[(size_t)k * n + k];
+                const int rows = n - (k + 1);
+                const int b = k + 1 + (int)((int64_t)rows * t / nThreads), e = k + 1 + (int)((int64_t)rows * (t + 1) / nThreads);
+                const double* rk = &lu[(size_t)k * n];
+                for (int i = b; i < e; i++)
+                {
+                    double* ri = &lu[(size_t)i * n];
+                    const double l = ri[k] / d;
+                    ri[k] = l;
+                    if (l != 0.0)
+                        for (int j = k + 1; j < n; j++) ri[j] -= l * rk[j];
+                }
+                barrier();
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nThreads; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& x : th) x.join();
+        if (singular.load()) throw Error("coarse operator is singular");
     }
     // explicit inverse, transposed (invT[j*n + i] = (A^-1)[i][j]): applied on the device as a coalesced GEMV (CoarseApply), so a
     // preconditioner application needs no host round trip.  Columns are independent: solved on host threads.

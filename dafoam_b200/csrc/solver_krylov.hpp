@@ -631,7 +631,7 @@ inline void Solver::coarseSetup()
             coarseRestrict(K.t3.p);
             for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
         }
-    Cs.factor();
+    Cs.factor(std::min(detail::hostThreads(), 32));
     {
         std::vector<double> invT;
         Cs.invertTransposed(invT, [&](int nItems, auto fn) {

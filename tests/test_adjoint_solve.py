@@ -168,3 +168,37 @@ def test_coloured_probing_gives_the_same_coarse_operator(capfd):
     m = re.search(r"coarse space: (\d+) aggregates probed with (\d+) coloured products", out[6][2])
     assert m and int(m.group(1)) >= 100 and int(m.group(2)) < int(m.group(1)) // 2, out[6][2][-400:]
     assert "too short, falling back" in out[1][2] and "coloured products" not in out[0][2]
+
+
+def test_host_threads_do_not_change_the_result():
+    """The host-threaded set-up (pattern rows, coarse LU and inverse: DAB_HOST_THREADS) gives the same preconditioner whatever the thread
+    count: identical GMRES history and solution bits with 1 and 4 threads (child processes: the count is read once)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, tempfile
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import pyDASolvers, Mat, KSP
+from tests.common import HOSTSIM, NORM_STATES
+mesh = cases.naca0012_ogrid(ni=128, nj=64, nk=1)
+d = tempfile.mkdtemp(); cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
+fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
+sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=NORM_STATES, function=fn,
+      adjEqnOption=dict(gmresRelTol=1e-8, gmresMaxIters=900, gmresRestart=300, coarseAggregates=520, pcConLevel=2)), caseDir=d, _lib_path=HOSTSIM)
+y = np.zeros(sol.getNLocalCells()); sol.getOFField("yWall", "scalar", y)
+W = cases.boundary_layer_state(mesh, y); sol.updateOFFields(W)
+n = sol.getNLocalAdjointStates(); b = np.zeros(n)
+sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), b)
+pc, ksp = Mat(), KSP(); sol.calcdRdWT(1, pc)
+psi = np.zeros(n); f = sol.solveLinearEqn(ksp, b, psi)
+print("RESULT", f, ksp.stats.iterations, float(np.abs(psi).sum()).hex())
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    for nt in ("1", "4"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, DAB_HOST_THREADS=nt, PYTHONPATH=root),
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(r.stdout.strip().split("RESULT")[-1].split())
+    assert out[0][0] == "0" and out[0] == out[1], out

@@ -53,7 +53,7 @@ def test_dot_product_identity_host_build():
 
 def test_lane_per_face_reva_pilot_matches():
     """DAB_LANES=1 (RevALanes: 8 lanes per cell, butterfly reduction) computes the same transpose product as the cell-per-thread RevA,
-    on hexahedral and on ragged (prism/poly) cells, with MRF and the patchVelocity boundary-reference adjoint.  The mapping is chosen
+    on hexahedral and on triangular-prism cells (5 faces: idle lanes).  The mapping is chosen
     once per process, so the check runs in a child process."""
     import os
     import subprocess
@@ -62,7 +62,7 @@ def test_lane_per_face_reva_pilot_matches():
 import numpy as np
 from tests.common import HOSTSIM, setup, rel_err
 worst = 0.0
-for kind, turb, nk in (("naca", True, 2), ("channel", True, 1), ("naca", False, 1)):
+for kind, turb, nk in (("naca", True, 2), ("channel", True, 1), ("naca", False, 1), ("prism", True, 1)):
     mesh, bcs, orc, sol, W, _ = setup(kind, turb, nk=nk, lib_path=HOSTSIM)
     sol.updateOFFields(W)
     orc.record(W)
