@@ -522,6 +522,29 @@ int dab_solve_primal(dab_solver* s, int* fail, dab_primal_stats* stats)
     DAB_CATCH
 }
 
+int dab_run_fp_adj(dab_solver* s, const double* dfdw, double* psi, int* fail, dab_ksp_stats* stats)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(dfdw, "dFdW");
+    need(psi, "psi");
+    KspStats st;
+    const int f = s->s.solveFixedPoint(dfdw, psi, st);
+    if (fail) *fail = f;
+    if (stats)
+    {
+        stats->iterations = st.iterations;
+        stats->converged_reason = st.reason;
+        stats->initial_residual = st.r0;
+        stats->final_residual = st.rn;
+        stats->solve_seconds = st.solveSec;
+        stats->pc_setup_seconds = st.pcSec;
+        stats->pc_assemblies = s->s.kry.pcAssemblies;
+        stats->n_matvec = st.nMatvec;
+    }
+    DAB_CATCH
+}
+
 int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats)
 {
     DAB_TRY

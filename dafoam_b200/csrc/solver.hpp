@@ -161,6 +161,8 @@ struct Solver
     std::string kspType = "gmres"; // adjEqnOption.kspType (extension): gmres (the reference's KSP) | idrs (IDR(s), short recurrences)
     int idrS = 4;
     int pcSymbolicOnly = 0;
+    int fpMaxIters = 1000;      // adjEqnOption fpMaxIters / fpRelTol / fpMinResTolDiff (reference pyDAFoam.py:540-542)
+    double fpRelTol = 1e-6, fpMinResTolDiff = 1e2, fpOmega = 0.5;
     int coarseProbeReach = 6; // cell levels a pressure perturbation reaches through the transposed Jacobian (coloured probing of the coarse operator; 0 = one product per aggregate)
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
@@ -592,6 +594,10 @@ struct Solver
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
             pcSymbolicOnly = (int)a->numOr("pcSymbolicOnly", pcSymbolicOnly);
+            fpMaxIters = (int)a->numOr("fpMaxIters", fpMaxIters);
+            fpRelTol = a->numOr("fpRelTol", fpRelTol);
+            fpMinResTolDiff = a->numOr("fpMinResTolDiff", fpMinResTolDiff);
+            fpOmega = a->numOr("fpOmega", fpOmega);
             {
                 const int pr = (int)a->numOr("coarseProbeReach", coarseProbeReach);
                 if (pr != coarseProbeReach) { coarseProbeReach = pr; kry.pcValid = false; }
@@ -2024,6 +2030,7 @@ struct Solver
     int kspExtraMatvecs = 0;
     int solveLinearEqn(const double* rhs, double* sol, KspStats& st);
     int solveIdrs(const double* rhs, double* sol, KspStats& st);
+    int solveFixedPoint(const double* rhs, double* sol, KspStats& st);
 };
 
 } // namespace dab

@@ -249,7 +249,7 @@ inline void Solver::pcSymbolic()
         std::vector<int> cellsBall, cols, faces, width;
         int64_t nnz = 0;
     };
-    const int nThreads = detail::hostThreads();
+    const int nThreads = std::max(1, detail::hostThreads() / std::max(1, nRanks)); // the ranks of a node share its cores
     std::vector<Work> work(nThreads);
     for (Work& w : work) w.width.assign(nG, 0);
     auto cellRowCols = [&](Work& w, int c) {
@@ -631,12 +631,12 @@ inline void Solver::coarseSetup()
             coarseRestrict(K.t3.p);
             for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
         }
-    Cs.factor(std::min(detail::hostThreads(), 32));
+    Cs.factor(std::min(std::max(1, detail::hostThreads() / std::max(1, nRanks)), 32));
     {
         std::vector<double> invT;
         Cs.invertTransposed(invT, [&](int nItems, auto fn) {
             // small systems: one thread; the columns of the inverse are independent
-            const int nt = nItems >= 256 ? detail::hostThreads() : 1;
+            const int nt = nItems >= 256 ? std::max(1, detail::hostThreads() / std::max(1, nRanks)) : 1;
             if (nt == 1) fn(0, 0, nItems);
             else
             {
@@ -1059,6 +1059,91 @@ inline int Solver::solveIdrs(const double* rhs, double* sol, KspStats& st)
     const double absRatio = rnorm / gmresAbsTol;
     const double relRatio = bnorm > 0 ? rnorm / bnorm / gmresRelTol : 0.0;
     return (relRatio > gmresTolDiff && absRatio > gmresTolDiff) ? 1 : 0;
+}
+
+// runFPAdj / solveAdjointFP (pyDASolvers.pyx:412-416; reference DASimpleFoam::runFPAdj, DASimpleFoam.C:189-909): a stationary
+// (fixed-point) adjoint iteration psi <- psi + omega M^-T (dFdW - J^T psi) with the reference's controls and termination rule --
+// zero start, adjEqnOption.fpMaxIters / fpRelTol / fpMinResTolDiff, the L2 norms of the adjoint residual per state block (U, p, [T],
+// [nuTilda], phi) normalised by their values after the first sweep, all below fpRelTol => 0, else the relaxed fpRelTol*fpMinResTolDiff
+// check => 0, else 1.  The approximate inverse M^-1 here is the engine's multicolour ILU(0) of the first-order Jacobian with the
+// damping adjEqnOption.fpOmega (default 0.5; 1.0 diverges), NOT the reference's transposed SIMPLE operators: it converges where that
+// splitting is convergent (small and medium cases; at 1M cells it is not) -- Krylov stays the production path.
+inline int Solver::solveFixedPoint(const double* rhs, double* sol, KspStats& st)
+{
+    Krylov& K = kry;
+    if (!K.pcValid && !(K.pcFactored && adjPCLag > 1 && K.symbolic)) calcPC();
+    ensureRecorded();
+    const int n = nDof(), nC = hm.nC;
+    if (K.w.n < (size_t)n)
+    {
+        K.w.alloc(be, n);
+        K.z.alloc(be, n);
+    }
+    K.xdev.alloc(be, n);
+    K.bdev.alloc(be, n);
+    K.ops.init(be, &comm, 34);
+    be.h2d(K.bdev.p, rhs, (size_t)n * sizeof(double));
+    // state blocks of the vector layout
+    std::vector<std::pair<int, int>> blocks{{0, 3 * nC}, {3 * nC, nC}};
+    int off = 4 * nC;
+    if (par.comp) { blocks.push_back({off, nC}); off += nC; }
+    if (par.turb) { blocks.push_back({off, nC}); off += nC; }
+    blocks.push_back({off, n - off});
+    const int nb = (int)blocks.size();
+    std::vector<double> init(nb, 0.0), nrm(nb, 0.0);
+    auto timer = be.timer();
+    be.sync();
+    timer.start();
+    st.nMatvec = 0;
+    kspExtraMatvecs = 0;
+    st.r0 = K.ops.norm2(K.bdev.p, n);
+    auto residual = [&]() {
+        matVecDev(K.xdev.p, K.w.p);
+        st.nMatvec++;
+        be.launch(n, SubVec{K.bdev.p, K.w.p});
+        for (int b = 0; b < nb; b++) nrm[b] = K.ops.norm2(K.w.p + blocks[b].first, blocks[b].second);
+    };
+    auto allBelow = [&](double tol) {
+        for (int b = 0; b < nb; b++)
+            if (init[b] > 0.0 && !(nrm[b] / init[b] < tol)) return false;
+        return true;
+    };
+    int conv = 1, cnt = 0;
+    for (; cnt < fpMaxIters; cnt++)
+    {
+        residual();
+        if (cnt >= 1)
+        {
+            if (cnt == 1) init = nrm;
+            if (printInfo && cnt % 50 == 0)
+            {
+                fprintf(stderr, "[dab200] fixed-point adjoint step %d, normalised residuals:", cnt);
+                for (int b = 0; b < nb; b++) fprintf(stderr, " %.3e", init[b] > 0 ? nrm[b] / init[b] : 0.0);
+                fprintf(stderr, "\n");
+            }
+            if (allBelow(fpRelTol)) { conv = 0; break; }
+            bool finite = true;
+            for (int b = 0; b < nb; b++) finite = finite && std::isfinite(nrm[b]);
+            if (!finite) break;
+        }
+        applyIlu(K.w.p, K.z.p); // ILU only: the multiplicative coarse correction is not a contraction as a stationary sweep (measured)
+        be.launch(n, AxpyVec{K.z.p, fpOmega, K.xdev.p});
+    }
+    if (conv == 1)
+    {
+        residual();
+        if (cnt >= 1 && allBelow(fpRelTol * fpMinResTolDiff)) conv = 0; // "Adjoint is still considered successful"
+    }
+    double tot = 0.0;
+    for (int b = 0; b < nb; b++) tot += nrm[b] * nrm[b];
+    st.solveSec = timer.stopMs() * 1e-3;
+    be.d2h(sol, K.xdev.p, (size_t)n * sizeof(double));
+    st.nMatvec += kspExtraMatvecs;
+    st.iterations = cnt;
+    st.reason = conv == 0 ? 2 : -3;
+    st.rn = std::sqrt(tot);
+    st.pcSec = K.pcSec;
+    return conv;
 }
 
 } // namespace dab

@@ -448,8 +448,17 @@ class pyDASolvers:
         return best
 
     def runFPAdj(self, dFdW, psi):
-        raise DAB200Error("runFPAdj: the fixed-point adjoint (reference DASimpleFoam.C:189-909) is not built; use adjEqnSolMethod Krylov "
-                          "(calcdRdWT + createMLRKSPMatrixFree + solveLinearEqn)")
+        """Fixed-point adjoint (reference pyDASolvers.pyx:412-413, DASimpleFoam::runFPAdj): stationary iteration from psi = 0 with
+        adjEqnOption fpMaxIters / fpRelTol / fpMinResTolDiff and the reference's termination rule; the approximate inverse is this
+        engine's preconditioner (include/dab200.h dab_run_fp_adj).  Returns 0 (converged, possibly by the relaxed rule) or 1."""
+        n = self.getNLocalAdjointStates()
+        _check_array(dFdW, n, "dFdW")
+        _check_array(psi, n, "psi")
+        fail = C.c_int(1)
+        st = KspStats()
+        self._raise(self._L.dab_run_fp_adj(self._h, _dp(dFdW), _dp(psi), C.byref(fail), C.byref(st)))
+        self.fpStats = st
+        return int(fail.value)
 
     def solveAdjointFP(self, dFdW, psi):
         return self.runFPAdj(dFdW, psi)

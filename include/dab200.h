@@ -175,6 +175,11 @@ int dab_pc_apply(dab_solver* s, const double* v, double* z);
  * success rule (relRatio > gmresTolDiff && absRatio > gmresTolDiff  =>  1). */
 int dab_solve_linear_eqn(dab_solver* s, const double* rhs, double* sol, int* fail, dab_ksp_stats* stats);
 
+/* runFPAdj(dFdW, psi) / solveAdjointFP (pyDASolvers.pyx:412-416; reference DASimpleFoam::runFPAdj, DASimpleFoam.C:189-909): stationary
+ * adjoint iteration from psi = 0 with adjEqnOption.fpMaxIters / fpRelTol / fpMinResTolDiff and the reference's per-block termination
+ * rule; the approximate inverse is this engine's preconditioner, not the reference's transposed SIMPLE operators.  *fail = 0/1. */
+int dab_run_fp_adj(dab_solver* s, const double* dfdw, double* psi, int* fail, dab_ksp_stats* stats);
+
 /* The assembled preconditioner matrix dRdWTPC of this rank as CSR (rows: states, columns: residuals, external numbering,
  * sorted columns) -- the matrix the reference writes with DAUtility::writeMatrixBinary(dRdWT, "dRdWTPC") when the
  * writeJacobians option lists it (DASolver.C:1080-1085, DAUtility.C:411-441).  Call with row_ptr == NULL to get the sizes,

@@ -202,3 +202,28 @@ print("RESULT", f, ksp.stats.iterations, float(np.abs(psi).sum()).hex())
         assert r.returncode == 0, r.stderr[-2000:]
         out.append(r.stdout.strip().split("RESULT")[-1].split())
     assert out[0][0] == "0" and out[0] == out[1], out
+
+
+def test_fixed_point_adjoint_host_build():
+    """runFPAdj / solveAdjointFP: the stationary iteration reaches the Krylov solution on a small case and follows the reference's
+    termination rule (strict, relaxed, failed)."""
+    mesh, sol, W = adjoint_case(HOSTSIM)
+    n = sol.getNLocalAdjointStates()
+    dFdW = np.zeros(n)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+    sol.updateDAOption(dict(adjEqnOption=dict(gmresRelTol=1e-10, gmresMaxIters=800, gmresRestart=400)))
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    psi_k = np.zeros(n)
+    assert sol.solveLinearEqn(ksp, dFdW, psi_k) == 0
+    sol.updateDAOption(dict(adjEqnOption=dict(fpMaxIters=3000, fpRelTol=1e-7, fpMinResTolDiff=1e2)))
+    psi = np.full(n, 7.0)  # the reference starts from zero whatever psi holds
+    assert sol.runFPAdj(dFdW, psi) == 0
+    its = sol.fpStats.iterations
+    assert 1 < its < 3000 and np.linalg.norm(psi - psi_k) <= 1e-4 * np.linalg.norm(psi_k), (its, np.linalg.norm(psi - psi_k) / np.linalg.norm(psi_k))
+    # too few sweeps for the strict tolerance, enough for the relaxed one -> still 0; far too few -> 1
+    sol.updateDAOption(dict(adjEqnOption=dict(fpMaxIters=max(3, its // 2), fpRelTol=1e-7, fpMinResTolDiff=1e6)))
+    assert sol.solveAdjointFP(dFdW, psi) == 0 and sol.fpStats.iterations == max(3, its // 2)
+    sol.updateDAOption(dict(adjEqnOption=dict(fpMaxIters=3, fpRelTol=1e-7, fpMinResTolDiff=1e1)))
+    assert sol.runFPAdj(dFdW, psi) == 1
