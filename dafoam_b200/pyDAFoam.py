@@ -170,13 +170,19 @@ class PYDAFOAM:
         W = self.getStates()
         dFdW = np.zeros(n)
         self.solver.calcJacTVecProduct("states", "stateVar", W, functionName, "function", np.array([1.0]), dFdW)
+        method = self.options.get("adjEqnSolMethod", "Krylov")
+        if method not in ("Krylov", "fixedPoint"):  # reference mphys_dafoam.py:562
+            raise RuntimeError("adjEqnSolMethod=%s not valid! Options are: Krylov or fixedPoint" % method)
         if self._pc is None or self._pcAge >= max(1, int(self.getOption("adjPCLag"))):
             self._pcAge = 0
             self._pc, self._ksp = Mat(), KSP()
             self.solver.calcdRdWT(1, self._pc)
             self.solver.createMLRKSPMatrixFree(self._pc, self._ksp)
         psi = np.zeros(n)
-        self.adjointFail = self.solver.solveLinearEqn(self._ksp, dFdW, psi)
+        if method == "fixedPoint":  # reference mphys_dafoam.py:549-557
+            self.adjointFail = self.solver.solveAdjointFP(dFdW, psi)
+        else:
+            self.adjointFail = self.solver.solveLinearEqn(self._ksp, dFdW, psi)
         self.nSolveAdjoints += 1
         self._psi[functionName] = psi
         return psi

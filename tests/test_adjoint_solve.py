@@ -227,3 +227,26 @@ def test_fixed_point_adjoint_host_build():
     assert sol.solveAdjointFP(dFdW, psi) == 0 and sol.fpStats.iterations == max(3, its // 2)
     sol.updateDAOption(dict(adjEqnOption=dict(fpMaxIters=3, fpRelTol=1e-7, fpMinResTolDiff=1e1)))
     assert sol.runFPAdj(dFdW, psi) == 1
+
+
+def test_pydafoam_adjoint_method_switch():
+    """PYDAFOAM.solveAdjoint follows adjEqnSolMethod like DAFoamSolver.solve_linear (reference mphys_dafoam.py:450-562)."""
+    import tempfile
+    from dafoam_b200.pyDAFoam import PYDAFOAM
+    mesh = cases.naca0012_ogrid(ni=24, nj=12, nk=1)
+    d = tempfile.mkdtemp(prefix="dab_pyd_")
+    cases.write_case(d, mesh, cases.default_bcs_naca())
+    opts = dict(solverName="DASimpleFoam", normalizeStates=NORM_STATES, function=FN,
+                adjEqnOption=dict(gmresRelTol=1e-9, gmresMaxIters=600, gmresRestart=300, fpMaxIters=4000, fpRelTol=1e-7))
+    DASolver = PYDAFOAM(options=opts, caseDir=d, _lib_path=HOSTSIM)
+    y = np.zeros(DASolver.solver.getNLocalCells())
+    DASolver.solver.getOFField("yWall", "scalar", y)
+    DASolver.setStates(cases.boundary_layer_state(mesh, y))
+    psi_k = DASolver.solveAdjoint("CD").copy()
+    assert DASolver.adjointFail == 0
+    DASolver.setOption("adjEqnSolMethod", "fixedPoint")
+    psi_f = DASolver.solveAdjoint("CD")
+    assert DASolver.adjointFail == 0 and np.linalg.norm(psi_f - psi_k) <= 1e-4 * np.linalg.norm(psi_k)
+    DASolver.setOption("adjEqnSolMethod", "cg")
+    with pytest.raises(RuntimeError, match="adjEqnSolMethod"):
+        DASolver.solveAdjoint("CD")
