@@ -396,6 +396,34 @@ class pyDASolvers:
         assert 0 <= pointI < self.getNLocalPoints() and 0 <= coordI < 3
         return getattr(self, "_xvOffset", 0) + 3 * pointI + coordI
 
+    def getOFFieldGlobal(self, fieldName, fieldType, field):
+        """globalField[globalCell] = localField[localCell] for this rank's cells (reference DASolver.C:4484-4517, scalar fields only);
+        the entries of other ranks are left untouched, as in the reference (the caller reduces)."""
+        if fieldType != "scalar":
+            raise DAB200Error("fieldType not valid")
+        assert len(field) == self.getNGlobalCells(), "invalid array size!"
+        loc = np.zeros(self.getNLocalCells())
+        self.getOFField(fieldName, fieldType, loc)
+        field[self.getLocalToGlobal("cells")] = loc
+
+    def setPrimalBoundaryConditions(self, printInfo=1):
+        """Re-apply the primalBC option (reference DASolver::setPrimalBoundaryConditions -> DAField::setPrimalBoundaryConditions)."""
+        pbc = self._options.get("primalBC", {})
+        if pbc:
+            self._raise(self._L.dab_update_options(self._h, json.dumps(dict(primalBC=pbc)).encode()))
+        if printInfo and pbc:
+            print("Setting primal boundary conditions: %s" % ", ".join(sorted(pbc)))
+
+    def getdFScaling(self, functionName, timeIdx=-1):
+        """Weight of a time instance in a time-averaged function (reference DASolver::getdFScaling): steady solvers have one
+        instance, weight 1."""
+        if functionName not in (self._options.get("function", {}) or {}):
+            raise DAB200Error("function %s not found in the function option" % functionName)
+        return 1.0
+
+    def meanStatesToStates(self):
+        raise DAB200Error("meanStatesToStates (option useMeanStates: step-averaged states of a limit-cycling primal) is not built")
+
     def hasVolCoordInput(self):
         """1 if any inputInfo entry is of type volCoord (reference DASolver::hasVolCoordInput)."""
         info = self._options.get("inputInfo", {}) or {}

@@ -180,6 +180,10 @@ def test_read_state_vars_mesh_points_and_sens_maps():
     want = np.array([sum(dF[pos[int(v)]] for v in f) / 3.0 for f in faces])
     assert np.allclose(got, want, rtol=1e-14, atol=0)
     assert sol.getElapsedClockTime() > 0 and sol.getElapsedCpuTime() > 0
+    g = np.full(sol.getNGlobalCells(), -1.0)
+    sol.getOFFieldGlobal("p", "scalar", g)
+    assert np.array_equal(g, W[3 * nC:4 * nC])
+    sol.setPrimalBoundaryConditions(0)
 
 
 def test_check_mesh():
