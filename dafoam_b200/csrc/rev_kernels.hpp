@@ -771,6 +771,115 @@ struct RevC
     }
 };
 
+// lane-per-face pilot of RevC (DAB_LANES=1, one GPU, product mode): 8 lanes per cell, 8 accumulators (Ub[3], pb, nb, refb[3])
+// reduced with the same xor-butterfly as RevALanes; lane 0 adds the cell's own terms and writes
+struct RevCLanes
+{
+    MeshView m;
+    Params q;
+    StateView s;
+    RecordView r;
+    AdjView a;
+    double* y;
+    DAB_HD void lane(int c, int ln, double* A) const
+    {
+        const int nT = m.nCtot;
+        for (int i = 0; i < 8; i++) A[i] = 0.0;
+        double* Ub = A;
+        double& pb = A[3];
+        double& nb = A[4];
+        double* refb = A + 5;
+        const double iVc = 1.0 / m.V[c];
+        double gUbc[9], gPbc[3], gNbc[3];
+        for (int i = 0; i < 9; i++) gUbc[i] = a.gUb[(size_t)i * nT + c] * iVc;
+        for (int i = 0; i < 3; i++)
+        {
+            gPbc[i] = a.gPb[(size_t)i * nT + c] * iVc;
+            gNbc[i] = q.turb ? a.gNtb[(size_t)i * nT + c] * iVc : 0.0;
+        }
+        for (int k = ln; k < m.maxCF; k += REV_LANES)
+        {
+            const FaceRef fr = faceOf(m, c, k);
+            if (fr.f < 0) break;
+            const int f = fr.f;
+            const double So[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]};
+            if (!fr.bnd)
+            {
+                const int n = fr.n;
+                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f];
+                const double iVn = 1.0 / m.V[n];
+                for (int j = 0; j < 3; j++)
+                {
+                    double t = 0.0;
+                    for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - a.gUb[(size_t)(j * 3 + i) * nT + n] * iVn);
+                    Ub[j] += wc * t;
+                }
+                double tp = 0.0, tn = 0.0;
+                for (int i = 0; i < 3; i++)
+                {
+                    tp += So[i] * (gPbc[i] - a.gPb[(size_t)i * nT + n] * iVn);
+                    if (q.turb) tn += So[i] * (gNbc[i] - a.gNtb[(size_t)i * nT + n] * iVn);
+                }
+                pb += wc * tp;
+                nb += wc * tn;
+            }
+            else
+            {
+                const int b = f - m.nIF, pa = m.bPatch[b];
+                const double phib = s.phi[f], dl = m.delta[f];
+                const double im = 1.0 / m.magSf[f];
+                const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
+                double valb[3];
+                const double sngb[3] = {0.0, 0.0, 0.0};
+                for (int j = 0; j < 3; j++) valb[j] = So[0] * gUbc[j * 3 + 0] + So[1] * gUbc[j * 3 + 1] + So[2] * gUbc[j * 3 + 2];
+                bcVectorAdj(q.bcKind[F_U][pa], phib, dl, nh, valb, sngb, Ub);
+                if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(q.bcKind[F_U][pa], phib, dl, valb, sngb, refb);
+                const double frp = bcFrac(q.bcKind[F_P][pa], phib);
+                pb += (1.0 - frp) * (So[0] * gPbc[0] + So[1] * gPbc[1] + So[2] * gPbc[2]);
+                if (q.turb)
+                {
+                    const double frn = bcFrac(q.bcKind[F_NUTILDA][pa], phib);
+                    nb += (1.0 - frn) * (So[0] * gNbc[0] + So[1] * gNbc[1] + So[2] * gNbc[2]);
+                }
+            }
+        }
+    }
+    DAB_HD void finish(int c, const double* A) const
+    {
+        const int nC = m.nC;
+        for (int j = 0; j < 3; j++) y[3 * c + j] = (a.Udir[(size_t)j * nC + c] + a.U2[(size_t)j * nC + c] + A[j]) * q.sU;
+        y[(size_t)3 * nC + c] = (a.pdir[c] + A[3]) * q.sP;
+        if (q.turb) y[(size_t)4 * nC + c] = (a.nt2[c] + a.nutb[c] * dnut_dnt(s.nt[c], q.nu) + A[4]) * q.sNut;
+        if (a.bcRefb)
+            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += A[5 + j];
+    }
+    DAB_HD void operator()(int t) const
+    {
+        const int c = t / REV_LANES, ln = t - c * REV_LANES;
+#if defined(__CUDA_ARCH__)
+        double A[8];
+        lane(c, ln, A);
+        const long long left = (long long)REV_LANES * m.nC - (long long)(t - (t & 31));
+        const unsigned mask = left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u);
+        for (int off = 1; off < REV_LANES; off <<= 1)
+            for (int i = 0; i < 8; i++) A[i] += __shfl_xor_sync(mask, A[i], off);
+        if (ln == 0) finish(c, A);
+#else
+        if (ln != 0) return;
+        double L[REV_LANES][8], T[REV_LANES][8];
+        for (int l = 0; l < REV_LANES; l++) lane(c, l, L[l]);
+        for (int off = 1; off < REV_LANES; off <<= 1)
+        {
+            for (int l = 0; l < REV_LANES; l++)
+                for (int i = 0; i < 8; i++) T[l][i] = L[l][i] + L[l ^ off][i];
+            for (int l = 0; l < REV_LANES; l++)
+                for (int i = 0; i < 8; i++) L[l][i] = T[l][i];
+        }
+        finish(c, L[0]);
+#endif
+    }
+};
+
 // ---- force function (DAFunctionForce.C:79-153) -------------------------------------------------------
 struct ForceSpec
 {

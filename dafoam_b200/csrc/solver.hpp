@@ -1345,7 +1345,9 @@ struct Solver
             const PsiView pv = psiView(x);
             launchRevA(pv);
             DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
-            DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
+            static const bool lanes = getenv("DAB_LANES") && atoi(getenv("DAB_LANES")) > 0;
+            if (lanes && hm.nC < (1 << 28)) be.launch(hm.nC * REV_LANES, RevCLanes{mv, par, sv, rv, av, y}); // pilot mapping (rev_kernels.hpp)
+            else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
             return;
         }
         // several ranks: every ghost exchange runs on the communication stream while the interior cells (no neighbour on
@@ -1416,7 +1418,12 @@ struct Solver
         }
         if (which == 0) launchRevA(pv);
         else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
-        else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
+        else
+        {
+            static const bool lanes = getenv("DAB_LANES") && atoi(getenv("DAB_LANES")) > 0;
+            if (lanes && hm.nC < (1 << 28)) be.launch(hm.nC * REV_LANES, RevCLanes{mv, par, sv, rv, av, dY2.p});
+            else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
+        }
     }
 
     void matVec(const double* x, double* y)
