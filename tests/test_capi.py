@@ -87,3 +87,32 @@ def test_output_and_statistics_helpers(capsys):
     v = np.zeros(1)
     sol.calcOutput(name, "function", v)
     assert v[0] == sol.calcFunction(name)
+
+
+def test_new_entry_points_reject_bad_arguments():
+    """NULL handles / pointers and impossible requests of the file, mesh-check and solver entry points return an error code with a
+    message (never a crash), through the raw C ABI."""
+    from dafoam_b200.pyDASolvers import DAB200Error
+    from tests.common import HOSTSIM
+    mesh, bcs, orc, sol, W, _ = setup("channel", True, nk=1, lib_path=HOSTSIM)
+    L, h = sol._L, sol._h
+    dp = ctypes.POINTER(ctypes.c_double)
+    ok = ctypes.c_int(0)
+    assert L.dab_check_mesh(None, ctypes.c_double(70), ctypes.c_double(4), ctypes.c_double(1000), 0, ctypes.byref(ok), None) != 0
+    assert L.dab_check_mesh(h, ctypes.c_double(70), ctypes.c_double(4), ctypes.c_double(1000), 0, None, None) != 0
+    assert L.dab_check_mesh(h, ctypes.c_double(70), ctypes.c_double(4), ctypes.c_double(1000), 0, ctypes.byref(ok), None) == 0 and ok.value == 1
+    assert L.dab_read_state_vars(h, ctypes.c_double(12345.0)) != 0 and b"does not exist" in L.dab_last_error()
+    assert L.dab_read_mesh_points(h, ctypes.c_double(12345.0)) != 0
+    assert L.dab_write_mesh_points(h, None, None) != 0
+    assert L.dab_write_sens_map_field(h, b"s", W.ctypes.data_as(dp), b"tensor", ctypes.c_double(1.0)) != 0
+    assert L.dab_write_sens_map_surface(h, b"s", None, None, 3, ctypes.c_double(1.0), None) != 0
+    assert L.dab_run_fp_adj(h, None, None, None, None) != 0
+    with pytest.raises(DAB200Error, match="old-time levels"):
+        sol.readStateVars(0.0, 1)
+    with pytest.raises(DAB200Error):
+        sol.getOFFieldGlobal("p", "vector", np.zeros(3))
+    with pytest.raises(DAB200Error, match="not found"):
+        sol.getdFScaling("CL")
+    # a surface map with no design points is refused
+    with pytest.raises(DAB200Error, match="empty surface"):
+        sol.writeSensMapSurface("s", np.zeros(0), np.zeros(0), 0, 1.0)
