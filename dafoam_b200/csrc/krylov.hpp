@@ -623,6 +623,7 @@ struct Krylov
     int vCap = 0;
     DevBuf<double> idr; // IDR(s) workspace: P(s) | G(s) | U(s) | r | t | v | z
     int idrS = 0;
+    bool idrShadowReady = false;
     VecOps ops;
     EllView view()
     {

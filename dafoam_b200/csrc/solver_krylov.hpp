@@ -915,6 +915,7 @@ inline int Solver::solveIdrs(const double* rhs, double* sol, KspStats& st)
         K.ops.init(be, &comm, std::max(gmresRestart, 32) + 2);
         K.vCap = 0; // the GMRES basis (if any) shares nothing with this workspace; hdev/ops were re-sized
         K.V.alloc(be, 1, false);
+        K.idrShadowReady = false;
     }
     double* P = K.idr.p;
     double* G = P + (size_t)s * n;
@@ -923,8 +924,10 @@ inline int Solver::solveIdrs(const double* rhs, double* sol, KspStats& st)
     double* t = r + n; // directly after r: dots(r, n, 2, t) = (r.t, t.t)
     double* v = t + n;
     double* z = v + n;
-    // shadow space: fixed pseudo-random vectors, orthonormalised (modified Gram-Schmidt)
+    // shadow space: fixed pseudo-random vectors, orthonormalised (modified Gram-Schmidt); kept between solves
+    if (!K.idrShadowReady)
     {
+        K.idrShadowReady = true;
         std::vector<double> h((size_t)n);
         for (int j = 0; j < s; j++)
         {
