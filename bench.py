@@ -408,6 +408,8 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         try:
             out["cpu_baseline"] = cpu_reference(os.cpu_count() or 1, reps=10)
+            # config 1 of BASELINE.json (the reference's own ~5k-cell case on ONE CPU rank): the same port on one core
+            out["cpu_baseline_1core"] = cpu_reference(1, reps=10)
         except Exception as e:
             out["cpu_baseline"] = {"error": str(e)}
     emit(out)
