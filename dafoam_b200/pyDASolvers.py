@@ -406,6 +406,24 @@ class pyDASolvers:
         self.getOFField(fieldName, fieldType, loc)
         field[self.getLocalToGlobal("cells")] = loc
 
+    def getInitStateVals(self, printInfo=0):
+        """Average of every cell state over the mesh (reference DASolver::getInitStateVals, DASolver.C:3637-3710): U0, U1, U2, p, [T],
+        [nuTilda] in self.initStateVals.  On several ranks each rank holds its own share sum(local)/nGlobalCells (the reference reduces
+        them with MPI; the caller owns the communicator here)."""
+        n, nC, nG = self.getNLocalAdjointStates(), self.getNLocalCells(), self.getNGlobalCells()
+        W = np.zeros(n)
+        self.getOFFields(W)
+        nCellStates = (n - self.getNLocalFaces()) // nC
+        comp = self._solverName != "DASimpleFoam"
+        names = ["p"] + (["T"] if comp else []) + (["nuTilda"] if nCellStates - 4 - int(comp) > 0 else [])
+        vals = {"U%d" % i: float(W[i:3 * nC:3].sum() / nG) for i in range(3)}
+        for k, name in enumerate(names):
+            vals[name] = float(W[(3 + k) * nC:(4 + k) * nC].sum() / nG)
+        self.initStateVals = vals
+        if printInfo:
+            print("initStateVals: %s" % vals)
+        return vals
+
     def setPrimalBoundaryConditions(self, printInfo=1):
         """Re-apply the primalBC option (reference DASolver::setPrimalBoundaryConditions -> DAField::setPrimalBoundaryConditions)."""
         pbc = self._options.get("primalBC", {})

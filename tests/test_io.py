@@ -184,6 +184,8 @@ def test_read_state_vars_mesh_points_and_sens_maps():
     sol.getOFFieldGlobal("p", "scalar", g)
     assert np.array_equal(g, W[3 * nC:4 * nC])
     sol.setPrimalBoundaryConditions(0)
+    iv = sol.getInitStateVals(0)
+    assert set(iv) == {"U0", "U1", "U2", "p", "nuTilda"} and abs(iv["U0"] - W[0:3 * nC:3].mean()) < 1e-12 and abs(iv["nuTilda"] - W[4 * nC:5 * nC].mean()) < 1e-15
 
 
 def test_check_mesh():
