@@ -45,6 +45,18 @@ __global__ void __launch_bounds__(DAB_BLOCK, LaunchTraits<F>::minBlocks) kernel1
     if (i < n) f(i);
 }
 
+// one CTA per tile (tile_kernels.hpp): the program's phases separated by block barriers, dynamic shared memory
+template <class P>
+__global__ void __launch_bounds__(P::THREADS) __maxnreg__(P::MAXREG) tileKernel(P p)
+{
+    extern __shared__ __align__(16) double dabTileSm[];
+    _Pragma("unroll") for (int ph = 0; ph < P::PHASES; ph++)
+    {
+        p.phase(ph, (int)blockIdx.x, (int)threadIdx.x, P::THREADS, dabTileSm);
+        if (ph + 1 < P::PHASES) __syncthreads();
+    }
+}
+
 struct Backend
 {
     cudaStream_t stream = nullptr;
@@ -85,6 +97,23 @@ struct Backend
         if (n <= 0) return;
         const int bs = DAB_BLOCK;
         kernel1d<F><<<(n + bs - 1) / bs, bs, 0, stream>>>(n, f);
+        DAB_CUDA_CHECK(cudaGetLastError()); // a launch-configuration failure is not sticky: catch it here, not as wrong numbers later
+        launches++;
+    }
+    template <class P>
+    void launchTiles(int nTiles, const P& p)
+    {
+        if (nTiles <= 0) return;
+        static bool configured = false; // per program type: opt in to > 48 KB of dynamic shared memory
+        const int bytes = P::SM_DOUBLES * (int)sizeof(double);
+        if (!configured)
+        {
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(tileKernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            DAB_CUDA_CHECK(cudaFuncSetAttribute(tileKernel<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            configured = true;
+        }
+        tileKernel<P><<<nTiles, P::THREADS, bytes, stream>>>(p);
+        DAB_CUDA_CHECK(cudaGetLastError());
         launches++;
     }
     // CUDA-event timer on the solver's stream
@@ -123,6 +152,15 @@ struct Backend
     void launch(int n, const F& f)
     {
         for (int i = 0; i < n; i++) f(i);
+        launches++;
+    }
+    // test-only emulation of a tile launch: tile by tile, phase by phase, one "thread" walking the whole CTA's work
+    template <class P>
+    void launchTiles(int nTiles, const P& p)
+    {
+        std::vector<double> sm((size_t)P::SM_DOUBLES, 0.0);
+        for (int t = 0; t < nTiles; t++)
+            for (int ph = 0; ph < P::PHASES; ph++) p.phase(ph, t, 0, 1, sm.data());
         launches++;
     }
     struct Timer

@@ -17,6 +17,7 @@
 // derivative at zero -- the same conventions as CoDiPack in the reference and as oracle/tape.hpp.
 #pragma once
 #include "views.hpp"
+#include "acc.hpp"
 #include "fwd_kernels.hpp"
 #include <cmath>
 
@@ -116,6 +117,130 @@ DAB_HD void boundaryGradAdj(const double* nh, const double* Gbb, double* gUb, do
     }
 }
 
+// ---- face iteration through an accessor: hexahedral meshes (NF = 6) load the cell's whole row of the two tables before the face loop
+// (all index loads in flight together; measured on B200: product 0.855 -> 0.763 ms), other meshes walk the ELL row
+DAB_HD FaceRef faceOfE2(int nIF, int e, int n)
+{
+    FaceRef r;
+    if (e < 0)
+    {
+        r.f = -1; r.n = -1; r.s = 0.0; r.bnd = false;
+        return r;
+    }
+    r.f = e >> 1;
+    r.s = (e & 1) ? -1.0 : 1.0;
+    r.bnd = r.f >= nIF;
+    r.n = n;
+    return r;
+}
+#define DAB_ACC_FACES(NF)                                        \
+    int e_[(NF) > 0 ? (NF) : 1], n_[(NF) > 0 ? (NF) : 1];        \
+    if constexpr ((NF) > 0) A.template faceRow<((NF) > 0 ? (NF) : 1)>(c, e_, n_);
+#define DAB_ACC_FACE(NF, k) ((NF) > 0 ? faceOfE2(A.nIF(), e_[(NF) > 0 ? (k) : 0], n_[(NF) > 0 ? (k) : 0]) : A.face(c, k))
+
+// RevA of one cell: adjoint of FwdC + cell-level adjoint of the momentum row
+template <int NF, class Acc>
+DAB_HD void revACell(const Acc& A, const Params& q, int c)
+{
+    const double Uc[3] = {A.U(c, 0), A.U(c, 1), A.U(c, 2)};
+    const double V = A.V(c);
+    const double psiPc = A.xp(c) * (q.nrP ? 1.0 / V : 1.0);
+    double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
+    double refb[3] = {0, 0, 0};
+    const double pc = A.p(c), rAUc = A.rAU(c);
+    const double gPc[3] = {A.gP(c, 0), A.gP(c, 1), A.gP(c, 2)};
+    DAB_ACC_FACES(NF)
+    _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : A.maxCF()); k++)
+    {
+        const FaceRef fr = DAB_ACC_FACE(NF, k);
+        if (fr.f < 0) break;
+        const int f = fr.f;
+        const double mS = A.magSf(f), dl = A.delta(f);
+        const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
+        double Sv[3];
+        A.Sf(f, Sv);
+        if (!fr.bnd)
+        {
+            const int n = fr.n;
+            const double psiPn = A.xp(n) * (q.nrP ? 1.0 / A.V(n) : 1.0);
+            // F_f enters pRes_own with -1, pRes_nei with +1, phiRes_f with +1
+            const double Fb = cphi * A.xphi(f) - fr.s * (psiPc - psiPn);
+            const double w = A.w(f);
+            const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
+            double kv[3];
+            A.kv(f, kv);
+            double cg = 0.0;
+            for (int j = 0; j < 3; j++) cg += kv[j] * (wc * gPc[j] + wn * A.gP(n, j));
+            const double sn = fr.s * dl * (A.p(n) - pc) + cg; // delta*(p_N - p_P) + corr
+            const double gam = wc * rAUc + wn * A.rAU(n);
+            for (int j = 0; j < 3; j++)
+            {
+                HbA[j] += wc * Sv[j] * Fb;
+                gPb[j] -= gam * mS * wc * kv[j] * Fb;
+            }
+            rAUb -= wc * mS * sn * Fb;
+            pb += fr.s * gam * mS * dl * Fb;
+        }
+        else
+        {
+            const int pa = A.patch(f);
+            const double phib = A.phi(f);
+            const double Fb = cphi * A.xphi(f) - psiPc;
+            const int kU = q.bcKind[F_U][pa];
+            const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
+            if (A.m.mrfType && A.m.mrfType[f - A.nIF()] == 1)
+                ; // rotating wall of the MRF zone: the relative phiHbyA is identically zero
+            else if (q.constrainHbyA && !assignable)
+            {
+                const double im = 1.0 / mS;
+                const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+                const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
+                const double sngb[3] = {0.0, 0.0, 0.0};
+                bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
+                if (A.bcRefOn(pa)) bcVectorRefAdj(kU, phib, dl, valb, sngb, refb);
+            }
+            else
+                for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * Fb;
+            double pv, sn, frp;
+            bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], pc, phib, dl, pv, sn, frp);
+            rAUb -= mS * sn * Fb;
+            const double snb = -rAUc * mS * Fb;
+            pb -= frp * dl * snb;
+        }
+    }
+    // cell-level adjoint of the momentum row: URes = cU*(M + grad p), HbyA = U - rAU*M, rAU = V/(Dn + icAvg)
+    const double rAU = rAUc;
+    const double cU = q.nrU ? 1.0 : V;
+    const double D0 = A.D0(c);
+    double rAUtot = rAUb;
+    double Mbv[3], Ud[3];
+    for (int j = 0; j < 3; j++)
+    {
+        const double M = (Uc[j] - A.HbyA(c, j)) / rAU;
+        const double psiU = cU * A.xU(c, j);
+        const double Mb = psiU - rAU * HbA[j];
+        Mbv[j] = Mb;
+        rAUtot -= M * HbA[j];
+        const double mt = Mb / V;
+        A.setMt(c, j, mt);
+        Ud[j] = Ub[j] + HbA[j] + D0 * mt;
+        A.setGPb(c, j, gPb[j] + psiU);
+    }
+    if (A.mrfCell(c))
+    {
+        // adjoint of the Coriolis term M += Omega x U: Ub += Mb x Omega
+        const double* w = A.m.mrfOmega;
+        Ud[0] += Mbv[1] * w[2] - Mbv[2] * w[1];
+        Ud[1] += Mbv[2] * w[0] - Mbv[0] * w[2];
+        Ud[2] += Mbv[0] * w[1] - Mbv[1] * w[0];
+    }
+    for (int j = 0; j < 3; j++) A.setUdir(c, j, Ud[j]);
+    A.setDn(c, -rAU * rAU * rAUtot / V);
+    A.setPdir(c, pb);
+    if (A.bcRefAny())
+        for (int j = 0; j < 3; j++) A.setBcRef(c, j, refb[j]);
+}
+
 template <int NF>
 struct RevA
 {
@@ -127,262 +252,303 @@ struct RevA
     PsiView x;
     DAB_HD void operator()(int c) const
     {
-        const int nT = m.nCtot, nC = m.nC;
-        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-        const double V = m.V[c];
-        const double psiPc = x.p[c] * (q.nrP ? 1.0 / V : 1.0);
-        double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
-        double refb[3] = {0, 0, 0};
-        DAB_FACE_PREFETCH(NF)
-        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
+        const GAcc A{m, s, r, a, x, nullptr, nullptr, nullptr, nullptr};
+        revACell<NF>(A, q, c);
+    }
+};
+
+// RevB of one cell.  FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in, bit 2 = adjoint of
+// the boundary reference values (patchVelocity input) compiled in (the common configuration without them keeps its register
+// budget).  gradOnly (tile kernels, halo ring): only the adjoints of grad(U) / grad(nuTilda) are stored.
+template <int NF, int FEAT, class Acc>
+DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
+{
+    const int schU = q.divU, schN = q.divNut;
+    const double Uc[3] = {A.U(c, 0), A.U(c, 1), A.U(c, 2)};
+    const double nutc = A.nut(c);
+    const double nuEc = nutc + q.nu;
+    double gUc[9], gNc[3];
+    for (int i = 0; i < 9; i++) gUc[i] = A.gU(c, i);
+    const double ntc = q.turb ? A.nt(c) : 0.0;
+    const double Gc = (ntc + q.nu) / SA::sigma;
+    for (int i = 0; i < 3; i++) gNc[i] = q.turb ? A.gNt(c, i) : 0.0;
+    const double trc = gUc[0] + gUc[4] + gUc[8];
+    const double V = A.V(c);
+    const double Cc[3] = {A.C(c, 0), A.C(c, 1), A.C(c, 2)};
+    // cell-level adjoints of row c
+    const double mtc[3] = {A.mt(c, 0), A.mt(c, 1), A.mt(c, 2)};
+    const double Dnc = A.Dn(c), flc = A.flag(c);
+    const double D2c = Dnc / q.alphaU;
+    const double D1c = flc != 0.0 ? flc * D2c : 0.0;
+    const double soc = flc != 0.0 ? 0.0 : D2c;
+    const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
+    const double psiN = q.turb ? A.xnt(c) : 0.0;
+    const double qc = psiN * (q.nrNut ? 1.0 / V : 1.0); // adjoint of NV
+    const double zc = psiN * (q.nrNut ? 1.0 : V);       // adjoint of the cell-local SA sources
+
+    double U2[3] = {0, 0, 0}, nt2 = 0.0, nuEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
+    double refb[3] = {0, 0, 0};
+    for (int i = 0; i < 9; i++) gUb[i] = 0.0;
+
+    DAB_ACC_FACES(NF)
+    _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : A.maxCF()); k++)
+    {
+        const FaceRef fr = DAB_ACC_FACE(NF, k);
+        if (fr.f < 0) break;
+        const int f = fr.f;
+        const double phi = A.phi(f);
+        const double mf = fr.s * phi;
+        double Sv[3];
+        A.Sf(f, Sv);
+        const double mS = A.magSf(f), dl = A.delta(f);
+        double phib_acc = 0.0; // adjoint of phi_f (only meaningful on the owner side)
+        if (!fr.bnd)
         {
-            const FaceRef fr = DAB_FACE(NF, k);
-            if (fr.f < 0) break;
-            const int f = fr.f;
-            const double mS = m.magSf[f], dl = m.delta[f];
-            const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
-            const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
-            if (!fr.bnd)
+            const int n = fr.n;
+            const double wf = A.w(f);
+            const double wc = fr.s > 0 ? wf : 1.0 - wf, wn = 1.0 - wc;
+            const bool pos0 = phi >= 0.0;
+            const double wupc = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
+            const double Un[3] = {A.U(n, 0), A.U(n, 1), A.U(n, 2)};
+            const double nuEn = A.nut(n) + q.nu;
+            const double mtn[3] = {A.mt(n, 0), A.mt(n, 1), A.mt(n, 2)};
+            const double Dnn = A.Dn(n), fln = A.flag(n);
+            const double D2n = Dnn / q.alphaU;
+            const double D1n = fln != 0.0 ? fln * D2n : 0.0;
+            const double son = fln != 0.0 ? 0.0 : D2n;
+            const double D0n = D1n + mtn[0] * Un[0] + mtn[1] * Un[1] + mtn[2] * Un[2];
+            const bool ownUp = phi > 0.0;
+            const bool cUp = fr.s > 0 ? ownUp : !ownUp;
+            double kv[3], Cfv[3];
+            A.kv(f, kv);
+            A.Cf(f, Cfv);
+            const double dC[3] = {Cfv[0] - Cc[0], Cfv[1] - Cc[1], Cfv[2] - Cc[2]};
+            // ---- momentum rows c and n
             {
-                const int n = fr.n;
-                const double psiPn = x.p[n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
-                // F_f enters pRes_own with -1, pRes_nei with +1, phiRes_f with +1
-                const double Fb = cphi * x.phi[f] - fr.s * (psiPc - psiPn);
-                const double w = m.w[f];
-                const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
-                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
-                double cg = 0.0;
-                for (int j = 0; j < 3; j++) cg += kv[j] * (wc * r.gP[(size_t)j * nT + c] + wn * r.gP[(size_t)j * nT + n]);
-                const double sn = fr.s * dl * (s.p[n] - s.p[c]) + cg; // delta*(p_N - p_P) + corr
-                const double gam = wc * r.rAU[c] + wn * r.rAU[n];
+                const double wpc = schU == DIV_LINEAR ? wc : wupc;
+                const double wpn = schU == DIV_LINEAR ? wn : 1.0 - wupc;
+                const double gf = (wc * nuEc + wn * nuEn) * mS;
+                const double g = gf * dl;
+                const double offc = mf - wpc * mf - g;
+                const double offn = -mf + wpn * mf - g;
+                const double offbc = mtc[0] * Un[0] + mtc[1] * Un[1] + mtc[2] * Un[2] + sgn(offc) * soc;
+                const double offbn = mtn[0] * Uc[0] + mtn[1] * Uc[1] + mtn[2] * Uc[2] + sgn(offn) * son;
+                for (int j = 0; j < 3; j++) U2[j] += offn * mtn[j];
+                const double abc = D0c - offbc, abn = D0n - offbn;
+                double gb = abc + abn;   // adjoint of g
+                double gfb = 0.0;        // adjoint of gf (non-orthogonal correction)
+                const double lam[3] = {fr.s * (mtc[0] - mtn[0]), fr.s * (mtc[1] - mtn[1]), fr.s * (mtc[2] - mtn[2])};
+                double gUn[9];
+                for (int i = 0; i < 9; i++) gUn[i] = A.gU(n, i);
+                if (fr.s > 0)
+                {
+                    const double mbc = -D0c + offbc + wpc * abc;
+                    const double mbn = -D0n + offbn + wpn * abn;
+                    phib_acc += mbc - mbn;
+                }
+                if (!(FEAT & 1))
+                {
+                    // plain linearUpwind (compact form: no limiter state)
+                    if (schU == DIV_LINEAR_UPWIND)
+                    {
+                        if (cUp)
+                            for (int j = 0; j < 3; j++)
+                                for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * phi * lam[j];
+                        if (fr.s > 0)
+                        {
+                            const double* gu = cUp ? gUc : gUn;
+                            double d[3];
+                            for (int i = 0; i < 3; i++) d[i] = cUp ? dC[i] : Cfv[i] - A.C(n, i);
+                            for (int j = 0; j < 3; j++)
+                                phib_acc += (d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2]) * lam[j];
+                        }
+                    }
+                }
+                else if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
+                {
+                    const double* gu = cUp ? gUc : gUn;
+                    double d[3];
+                    for (int i = 0; i < 3; i++) d[i] = cUp ? dC[i] : Cfv[i] - A.C(n, i);
+                    double corr[3], corrL[3], outb[3], corrb[3] = {0, 0, 0};
+                    for (int j = 0; j < 3; j++)
+                    {
+                        corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
+                        outb[j] = phi * lam[j]; // adjoint of the (limited) correction: +phi*corr into own row, -phi*corr into nei row
+                    }
+                    if ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V)
+                    {
+                        const double cf = ownUp ? (1.0 - wf) : -wf;
+                        double maxCorr[3], maxCorrb[3] = {0, 0, 0};
+                        for (int j = 0; j < 3; j++) maxCorr[j] = cf * fr.s * (Un[j] - Uc[j]);
+                        luvLimit(corr, maxCorr, corrL);
+                        luvLimitAdj(corr, maxCorr, outb, corrb, maxCorrb);
+                        for (int j = 0; j < 3; j++) U2[j] -= cf * fr.s * maxCorrb[j];
+                    }
+                    else
+                        for (int j = 0; j < 3; j++) { corrL[j] = corr[j]; corrb[j] = outb[j]; }
+                    if (cUp)
+                        for (int j = 0; j < 3; j++)
+                            for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * corrb[j];
+                    if (fr.s > 0)
+                        for (int j = 0; j < 3; j++) phib_acc += corrL[j] * lam[j];
+                }
+                // non-orthogonal correction: MV_own -= gf*cg_j, MV_nei += gf*cg_j
                 for (int j = 0; j < 3; j++)
                 {
-                    HbA[j] += wc * Sv[j] * Fb;
-                    gPb[j] -= gam * mS * wc * kv[j] * Fb;
+                    double cg = 0.0;
+                    for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gUc[j * 3 + i] + wn * gUn[j * 3 + i]);
+                    gfb -= cg * lam[j];
+                    const double cgb = -gf * lam[j];
+                    for (int i = 0; i < 3; i++) gUb[j * 3 + i] += wc * kv[i] * cgb;
                 }
-                rAUb -= wc * mS * sn * Fb;
-                pb += fr.s * gam * mS * dl * Fb;
-            }
-            else
-            {
-                const int b = f - m.nIF, pa = m.bPatch[b];
-                const double phib = s.phi[f];
-                const double Fb = cphi * x.phi[f] - psiPc;
-                const int kU = q.bcKind[F_U][pa];
-                const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
-                if (m.mrfType && m.mrfType[b] == 1)
-                    ; // rotating wall of the MRF zone: the relative phiHbyA is identically zero
-                else if (q.constrainHbyA && !assignable)
+                // dev2 term: MV_own -= fl_j, MV_nei += fl_j, fl = wc*tc + wn*tn
+                double trb = 0.0;
+                for (int j = 0; j < 3; j++)
                 {
-                    const double im = 1.0 / mS;
-                    const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
-                    const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
-                    const double sngb[3] = {0.0, 0.0, 0.0};
-                    bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
-                    if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, phib, dl, valb, sngb, refb);
+                    const double tcb = -wc * lam[j];
+                    const double tcj = Sv[0] * gUc[0 * 3 + j] + Sv[1] * gUc[1 * 3 + j] + Sv[2] * gUc[2 * 3 + j] - (2.0 / 3.0) * trc * Sv[j];
+                    nuEb += tcb * tcj;
+                    for (int i = 0; i < 3; i++) gUb[i * 3 + j] += nuEc * Sv[i] * tcb;
+                    trb -= (2.0 / 3.0) * nuEc * Sv[j] * tcb;
                 }
-                else
-                    for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * Fb;
-                double pv, sn, frp;
-                bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, sn, frp);
-                rAUb -= mS * sn * Fb;
-                const double snb = -r.rAU[c] * mS * Fb;
-                pb -= frp * dl * snb;
+                gUb[0] += trb; gUb[4] += trb; gUb[8] += trb;
+                nuEb += wc * mS * (dl * gb + gfb);
             }
-        }
-        // cell-level adjoint of the momentum row: URes = cU*(M + grad p), HbyA = U - rAU*M, rAU = V/(Dn + icAvg)
-        const double rAU = r.rAU[c];
-        const double cU = q.nrU ? 1.0 : V;
-        const double D0 = r.D0[c];
-        double rAUtot = rAUb;
-        double Mbv[3];
-        for (int j = 0; j < 3; j++)
-        {
-            const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) / rAU;
-            const double psiU = cU * x.U[3 * c + j];
-            const double Mb = psiU - rAU * HbA[j];
-            Mbv[j] = Mb;
-            rAUtot -= M * HbA[j];
-            const double mt = Mb / V;
-            a.mt[(size_t)j * nT + c] = mt;
-            a.Udir[(size_t)j * nC + c] = Ub[j] + HbA[j] + D0 * mt;
-            a.gPb[(size_t)j * nT + c] = gPb[j] + psiU;
-        }
-        if (m.mrfCell && m.mrfCell[c])
-        {
-            // adjoint of the Coriolis term M += Omega x U: Ub += Mb x Omega
-            const double* w = m.mrfOmega;
-            a.Udir[c] += Mbv[1] * w[2] - Mbv[2] * w[1];
-            a.Udir[(size_t)nC + c] += Mbv[2] * w[0] - Mbv[0] * w[2];
-            a.Udir[(size_t)2 * nC + c] += Mbv[0] * w[1] - Mbv[1] * w[0];
-        }
-        a.Dn[c] = -rAU * rAU * rAUtot / V;
-        a.pdir[c] = pb;
-        if (a.bcRefb)
-            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] = refb[j];
-    }
-};
-
-// ---- lane-per-face pilot of RevA (DAB_LANES=1, one GPU) --------------------------------------------------------------------
-// Same arithmetic as RevA with a different thread mapping: 8 lanes per cell, lane k gathers face k (k, k+8, ... for polyhedra) and the
-// 14 per-cell accumulators are summed over the 8 lanes with a fixed xor-butterfly (__shfl_xor_sync 1, 2, 4), lane 0 finishing the cell.
-// Motivation: the cell-per-thread kernels are latency-bound at 18-35 % occupancy; this mapping puts 8x the
-// gathers of a cell in flight at once with a fraction of the live registers per thread.  The summation order differs from RevA
-// (butterfly instead of face order): results agree to rounding, and stay bitwise reproducible run to run.  The host build runs the
-// 8 lanes of a cell in sequence and reduces in the same butterfly order, so host and device give the same bits.
-constexpr int REV_LANES = 8;
-struct RevAAcc
-{
-    double v[14]; // HbA[3] | rAUb | pb | gPb[3] | Ub[3] | refb[3]
-};
-
-DAB_HD void revAFace(const MeshView& m, const Params& q, const StateView& s, const RecordView& r, const AdjView& a, const PsiView& x, int c,
-                     const FaceRef& fr, double psiPc, RevAAcc& A)
-{
-    const int nT = m.nCtot;
-    double* HbA = A.v;
-    double& rAUb = A.v[3];
-    double& pb = A.v[4];
-    double* gPb = A.v + 5;
-    double* Ub = A.v + 8;
-    double* refb = A.v + 11;
-    const int f = fr.f;
-    const double mS = m.magSf[f], dl = m.delta[f];
-    const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
-    const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
-    if (!fr.bnd)
-    {
-        const int n = fr.n;
-        const double psiPn = x.p[n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
-        const double Fb = cphi * x.phi[f] - fr.s * (psiPc - psiPn);
-        const double w = m.w[f];
-        const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
-        const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
-        double cg = 0.0;
-        for (int j = 0; j < 3; j++) cg += kv[j] * (wc * r.gP[(size_t)j * nT + c] + wn * r.gP[(size_t)j * nT + n]);
-        const double sn = fr.s * dl * (s.p[n] - s.p[c]) + cg;
-        const double gam = wc * r.rAU[c] + wn * r.rAU[n];
-        for (int j = 0; j < 3; j++)
-        {
-            HbA[j] += wc * Sv[j] * Fb;
-            gPb[j] -= gam * mS * wc * kv[j] * Fb;
-        }
-        rAUb -= wc * mS * sn * Fb;
-        pb += fr.s * gam * mS * dl * Fb;
-    }
-    else
-    {
-        const int b = f - m.nIF, pa = m.bPatch[b];
-        const double phib = s.phi[f];
-        const double Fb = cphi * x.phi[f] - psiPc;
-        const int kU = q.bcKind[F_U][pa];
-        const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
-        if (m.mrfType && m.mrfType[b] == 1)
-            ;
-        else if (q.constrainHbyA && !assignable)
-        {
-            const double im = 1.0 / mS;
-            const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
-            const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
-            const double sngb[3] = {0.0, 0.0, 0.0};
-            bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
-            if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, phib, dl, valb, sngb, refb);
+            // ---- SA rows c and n
+            if (q.turb)
+            {
+                const double ntn = A.nt(n);
+                const double qn = A.xnt(n) * (q.nrNut ? 1.0 / A.V(n) : 1.0);
+                const double wpc = schN == DIV_LINEAR ? wc : wupc;
+                const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
+                const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
+                const double g = gf * dl;
+                nt2 += qc * (wpc * mf + g - mf) + qn * (-mf + wpn * mf - g);
+                const double gb = (qc - qn) * (ntc - ntn);
+                double gfb = 0.0;
+                const double lam = fr.s * (qc - qn);
+                if (fr.s > 0) phib_acc += qc * (1.0 - wpc) * (ntn - ntc) - qn * (1.0 - wpn) * (ntc - ntn);
+                if (schN == DIV_LINEAR_UPWIND)
+                {
+                    if (cUp)
+                        for (int i = 0; i < 3; i++) gNb[i] += dC[i] * phi * lam;
+                    if (fr.s > 0)
+                    {
+                        double corr = 0.0;
+                        for (int i = 0; i < 3; i++) corr += (cUp ? dC[i] * gNc[i] : (Cfv[i] - A.C(n, i)) * A.gNt(n, i));
+                        phib_acc += corr * lam;
+                    }
+                }
+                double cg = 0.0;
+                for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gNc[i] + wn * A.gNt(n, i));
+                gfb -= cg * lam;
+                const double cgb = -gf * lam;
+                for (int i = 0; i < 3; i++) gNb[i] += wc * kv[i] * cgb;
+                nt2 += wc * mS * (dl * gb + gfb) / SA::sigma;
+            }
         }
         else
-            for (int j = 0; j < 3; j++) HbA[j] += Sv[j] * Fb;
-        double pv, sn, frp;
-        bcScalar(q.bcKind[F_P][pa], q.bcVal[F_P][pa][0], s.p[c], phib, dl, pv, sn, frp);
-        rAUb -= mS * sn * Fb;
-        const double snb = -r.rAU[c] * mS * Fb;
-        pb -= frp * dl * snb;
+        {
+            const int pa = A.patch(f);
+            const double im = 1.0 / mS;
+            const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+            const int kU = q.bcKind[F_U][pa];
+            BCv bu;
+            double uw[3];
+            mrfWallRef(A.m, f, q.bcVal[F_U][pa], uw);
+            bcVector(kU, uw, Uc, mf, dl, nh, bu);
+            double ntb = 0.0, sngN = 0.0, frN = 0.0;
+            if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
+            double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
+            double nutb = 0.0;
+            if (q.turb)
+                nutb = (FEAT & 2) ? nutBoundary<true>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], nutc, ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn)
+                                  : nutBoundaryBasic(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], nutc, ntb, q.nu, dP, dNb);
+            const double nuEB = nutb + q.nu;
+            const double G = nuEB * mS;
+            // internalCoeffs and the argmax/argmin components used by relax()
+            double ic[3];
+            int kmax = 0, kmin = 0;
+            for (int j = 0; j < 3; j++)
+            {
+                ic[j] = mf * bu.vic[j] - G * bu.gic[j];
+                if (j > 0)
+                {
+                    if (fabs(ic[j]) > fabs(ic[kmax])) kmax = j;
+                    if (ic[j] < ic[kmin]) kmin = j;
+                }
+            }
+            double mb = -D0c, Gb_ = 0.0;
+            for (int j = 0; j < 3; j++)
+            {
+                double icb = Dnc / 3.0;
+                if (j == kmin) icb -= Dnc;
+                if (j == kmax) icb += D1c * sgn(ic[j]);
+                mb += bu.vic[j] * icb + mtc[j] * bu.val[j];
+                Gb_ += -bu.gic[j] * icb - mtc[j] * bu.sng[j];
+            }
+            double valb[3], sngb[3];
+            for (int j = 0; j < 3; j++) { valb[j] = mf * mtc[j]; sngb[j] = -G * mtc[j]; }
+            // dev2 boundary term: MV_j -= nuEB * X_j
+            double Gbd[9];
+            for (int j = 0; j < 3; j++)
+            {
+                const double nG = nh[0] * gUc[j * 3 + 0] + nh[1] * gUc[j * 3 + 1] + nh[2] * gUc[j * 3 + 2];
+                for (int i = 0; i < 3; i++) Gbd[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bu.sng[j] - nG);
+            }
+            const double trbv = Gbd[0] + Gbd[4] + Gbd[8];
+            double nuEBb = mS * Gb_;
+            double Gbb[9];
+            for (int i = 0; i < 9; i++) Gbb[i] = 0.0;
+            double trbb = 0.0;
+            for (int j = 0; j < 3; j++)
+            {
+                const double X = Sv[0] * Gbd[0 * 3 + j] + Sv[1] * Gbd[1 * 3 + j] + Sv[2] * Gbd[2 * 3 + j] - (2.0 / 3.0) * trbv * Sv[j];
+                nuEBb -= X * mtc[j];
+                const double Xb = -nuEB * mtc[j];
+                for (int i = 0; i < 3; i++) Gbb[i * 3 + j] += Sv[i] * Xb;
+                trbb -= (2.0 / 3.0) * Sv[j] * Xb;
+            }
+            Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
+            boundaryGradAdj(nh, Gbb, gUb, sngb);
+            bcVectorAdj(kU, mf, dl, nh, valb, sngb, U2);
+            if ((FEAT & 4) && A.bcRefOn(pa)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
+            // nut_b -> nut_c / nuTilda_b / U_c (wall function)
+            nuEb += dP * nuEBb;
+            if (FEAT & 2)
+                for (int j = 0; j < 3; j++) U2[j] += dUn[j] * nuEBb;
+            double ntbb = dNb * nuEBb;
+            if (q.turb)
+            {
+                const double Gs = (ntb + q.nu) / SA::sigma * mS;
+                mb += qc * (ntb - ntc);
+                ntbb += qc * mf - qc * sngN * mS / SA::sigma;
+                const double sngNb = -qc * Gs;
+                nt2 += -qc * mf + (1.0 - frN) * ntbb - frN * dl * sngNb;
+            }
+            phib_acc += mb;
+        }
+        if (!gradOnly)
+        {
+            if (fr.s > 0)
+                A.setYPhi(f, (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * A.xphi(f)) * q.sPhi * mS);
+            else if (A.ghost(fr.n))
+                A.setYPhi(f, 0.0); // cut face whose phi belongs to the neighbouring rank
+        }
     }
+    if (q.turb) saSourceAdj(ntc, q.nu, A.yWall(c), gUc, gNc, zc, nt2, gUb, gNb, q.saFv3);
+    if (!gradOnly)
+    {
+        for (int j = 0; j < 3; j++) A.setU2(c, j, U2[j]);
+        if ((FEAT & 4) && A.bcRefAny())
+            for (int j = 0; j < 3; j++) A.addBcRef(c, j, refb[j]);
+        A.setNt2(c, nt2);
+        A.setNutb(c, nuEb);
+    }
+    for (int i = 0; i < 9; i++) A.setGUb(c, i, gUb[i]);
+    for (int i = 0; i < 3; i++) A.setGNtb(c, i, gNb[i]);
 }
 
-struct RevALanes
-{
-    MeshView m;
-    Params q;
-    StateView s;
-    RecordView r;
-    AdjView a;
-    PsiView x;
-    DAB_HD void lane(int c, int ln, double psiPc, RevAAcc& A) const
-    {
-        for (int i = 0; i < 14; i++) A.v[i] = 0.0;
-        for (int k = ln; k < m.maxCF; k += REV_LANES)
-        {
-            const FaceRef fr = faceOf(m, c, k);
-            if (fr.f < 0) break;
-            revAFace(m, q, s, r, a, x, c, fr, psiPc, A);
-        }
-    }
-    DAB_HD void finish(int c, const RevAAcc& A) const
-    {
-        const int nT = m.nCtot, nC = m.nC;
-        const double* HbA = A.v;
-        const double V = m.V[c];
-        const double rAU = r.rAU[c];
-        const double cU = q.nrU ? 1.0 : V;
-        const double D0 = r.D0[c];
-        double rAUtot = A.v[3];
-        double Mbv[3];
-        for (int j = 0; j < 3; j++)
-        {
-            const double M = (s.U[3 * c + j] - r.HbyA[(size_t)j * nT + c]) / rAU;
-            const double psiU = cU * x.U[3 * c + j];
-            const double Mb = psiU - rAU * HbA[j];
-            Mbv[j] = Mb;
-            rAUtot -= M * HbA[j];
-            const double mt = Mb / V;
-            a.mt[(size_t)j * nT + c] = mt;
-            a.Udir[(size_t)j * nC + c] = A.v[8 + j] + HbA[j] + D0 * mt;
-            a.gPb[(size_t)j * nT + c] = A.v[5 + j] + psiU;
-        }
-        if (m.mrfCell && m.mrfCell[c])
-        {
-            const double* w = m.mrfOmega;
-            a.Udir[c] += Mbv[1] * w[2] - Mbv[2] * w[1];
-            a.Udir[(size_t)nC + c] += Mbv[2] * w[0] - Mbv[0] * w[2];
-            a.Udir[(size_t)2 * nC + c] += Mbv[0] * w[1] - Mbv[1] * w[0];
-        }
-        a.Dn[c] = -rAU * rAU * rAUtot / V;
-        a.pdir[c] = A.v[4];
-        if (a.bcRefb)
-            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] = A.v[11 + j];
-    }
-    DAB_HD void operator()(int t) const
-    {
-        const int c = t / REV_LANES, ln = t - c * REV_LANES;
-        const double psiPc = x.p[c] * (q.nrP ? 1.0 / m.V[c] : 1.0);
-#if defined(__CUDA_ARCH__)
-        RevAAcc A;
-        lane(c, ln, psiPc, A);
-        // the participating lanes are known a priori (the launch has n = 8 nC threads and 128-thread blocks, so a warp holds threads
-        // [t0, t0+32) with t0 a multiple of 32); naming them explicitly makes __shfl_xor_sync reconverge the warp after the
-        // divergent face loop -- __activemask() would not be safe under independent thread scheduling
-        const long long left = (long long)REV_LANES * m.nC - (long long)(t - (t & 31));
-        const unsigned mask = left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u);
-        for (int off = 1; off < REV_LANES; off <<= 1)
-            for (int i = 0; i < 14; i++) A.v[i] += __shfl_xor_sync(mask, A.v[i], off);
-        if (ln == 0) finish(c, A);
-#else
-        if (ln != 0) return;
-        RevAAcc L[REV_LANES], T[REV_LANES];
-        for (int l = 0; l < REV_LANES; l++) lane(c, l, psiPc, L[l]);
-        for (int off = 1; off < REV_LANES; off <<= 1)
-        {
-            for (int l = 0; l < REV_LANES; l++)
-                for (int i = 0; i < 14; i++) T[l].v[i] = L[l].v[i] + L[l ^ off].v[i];
-            for (int l = 0; l < REV_LANES; l++) L[l] = T[l];
-        }
-        finish(c, L[0]);
-#endif
-    }
-};
-
-// FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in, bit 2 = adjoint of the
-// boundary reference values (patchVelocity input) compiled in (the common
-// configuration without them keeps its register budget)
 template <int NF, int FEAT>
 struct RevB
 {
@@ -395,285 +561,93 @@ struct RevB
     double* y;
     DAB_HD void operator()(int c) const
     {
-        const int nT = m.nCtot, nC = m.nC;
-        const size_t offPhi = (size_t)(q.turb ? 5 : 4) * nC;
-        const int schU = q.divU, schN = q.divNut;
-        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-        const double nuEc = r.nut[c] + q.nu;
-        double gUc[9], gNc[3];
-        for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
-        const double ntc = q.turb ? s.nt[c] : 0.0;
-        const double Gc = (ntc + q.nu) / SA::sigma;
-        for (int i = 0; i < 3; i++) gNc[i] = q.turb ? r.gNt[(size_t)i * nT + c] : 0.0;
-        const double trc = gUc[0] + gUc[4] + gUc[8];
-        const double V = m.V[c];
-        // cell-level adjoints of row c
-        const double mtc[3] = {a.mt[c], a.mt[(size_t)nT + c], a.mt[(size_t)2 * nT + c]};
-        const double Dnc = a.Dn[c], flc = r.flag[c];
-        const double D2c = Dnc / q.alphaU;
-        const double D1c = flc != 0.0 ? flc * D2c : 0.0;
-        const double soc = flc != 0.0 ? 0.0 : D2c;
-        const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
-        const double psiN = q.turb ? x.nt[c] : 0.0;
-        const double qc = psiN * (q.nrNut ? 1.0 / V : 1.0); // adjoint of NV
-        const double zc = psiN * (q.nrNut ? 1.0 : V);       // adjoint of the cell-local SA sources
-
-        double U2[3] = {0, 0, 0}, nt2 = 0.0, nuEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
-        double refb[3] = {0, 0, 0};
-        for (int i = 0; i < 9; i++) gUb[i] = 0.0;
-
-        DAB_FACE_PREFETCH(NF)
-        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
-        {
-            const FaceRef fr = DAB_FACE(NF, k);
-            if (fr.f < 0) break;
-            const int f = fr.f;
-            const double phi = s.phi[f];
-            const double mf = fr.s * phi;
-            const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
-            const double mS = m.magSf[f], dl = m.delta[f];
-            double phib_acc = 0.0; // adjoint of phi_f (only meaningful on the owner side)
-            if (!fr.bnd)
-            {
-                const int n = fr.n;
-                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f], wn = 1.0 - wc;
-                const bool pos0 = phi >= 0.0;
-                const double wupc = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
-                const double Un[3] = {s.U[3 * n], s.U[3 * n + 1], s.U[3 * n + 2]};
-                const double nuEn = r.nut[n] + q.nu;
-                const double mtn[3] = {a.mt[n], a.mt[(size_t)nT + n], a.mt[(size_t)2 * nT + n]};
-                const double Dnn = a.Dn[n], fln = r.flag[n];
-                const double D2n = Dnn / q.alphaU;
-                const double D1n = fln != 0.0 ? fln * D2n : 0.0;
-                const double son = fln != 0.0 ? 0.0 : D2n;
-                const double D0n = D1n + mtn[0] * Un[0] + mtn[1] * Un[1] + mtn[2] * Un[2];
-                const bool ownUp = phi > 0.0;
-                const bool cUp = fr.s > 0 ? ownUp : !ownUp;
-                const double kv[3] = {m.kx[f], m.ky[f], m.kz[f]};
-                const double dC[3] = {m.Cfx[f] - m.Cx[c], m.Cfy[f] - m.Cy[c], m.Cfz[f] - m.Cz[c]};
-                // ---- momentum rows c and n
-                {
-                    const double wpc = schU == DIV_LINEAR ? wc : wupc;
-                    const double wpn = schU == DIV_LINEAR ? wn : 1.0 - wupc;
-                    const double gf = (wc * nuEc + wn * nuEn) * mS;
-                    const double g = gf * dl;
-                    const double offc = mf - wpc * mf - g;
-                    const double offn = -mf + wpn * mf - g;
-                    const double offbc = mtc[0] * Un[0] + mtc[1] * Un[1] + mtc[2] * Un[2] + sgn(offc) * soc;
-                    const double offbn = mtn[0] * Uc[0] + mtn[1] * Uc[1] + mtn[2] * Uc[2] + sgn(offn) * son;
-                    for (int j = 0; j < 3; j++) U2[j] += offn * mtn[j];
-                    const double abc = D0c - offbc, abn = D0n - offbn;
-                    double gb = abc + abn;   // adjoint of g
-                    double gfb = 0.0;        // adjoint of gf (non-orthogonal correction)
-                    const double lam[3] = {fr.s * (mtc[0] - mtn[0]), fr.s * (mtc[1] - mtn[1]), fr.s * (mtc[2] - mtn[2])};
-                    double gUn[9];
-                    for (int i = 0; i < 9; i++) gUn[i] = r.gU[(size_t)i * nT + n];
-                    if (fr.s > 0)
-                    {
-                        const double mbc = -D0c + offbc + wpc * abc;
-                        const double mbn = -D0n + offbn + wpn * abn;
-                        phib_acc += mbc - mbn;
-                    }
-                    if (!(FEAT & 1))
-                    {
-                        // plain linearUpwind (compact form: no limiter state)
-                        if (schU == DIV_LINEAR_UPWIND)
-                        {
-                            if (cUp)
-                                for (int j = 0; j < 3; j++)
-                                    for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * phi * lam[j];
-                            if (fr.s > 0)
-                            {
-                                const double* gu = cUp ? gUc : gUn;
-                                const int u = cUp ? c : n;
-                                const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
-                                for (int j = 0; j < 3; j++)
-                                    phib_acc += (d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2]) * lam[j];
-                            }
-                        }
-                    }
-                    else if (schU == DIV_LINEAR_UPWIND || schU == DIV_LINEAR_UPWIND_V)
-                    {
-                        const double* gu = cUp ? gUc : gUn;
-                        const int u = cUp ? c : n;
-                        const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
-                        double corr[3], corrL[3], outb[3], corrb[3] = {0, 0, 0};
-                        for (int j = 0; j < 3; j++)
-                        {
-                            corr[j] = d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2];
-                            outb[j] = phi * lam[j]; // adjoint of the (limited) correction: +phi*corr into own row, -phi*corr into nei row
-                        }
-                        if ((FEAT & 1) && schU == DIV_LINEAR_UPWIND_V)
-                        {
-                            const double wo_ = m.w[f];
-                            const double cf = ownUp ? (1.0 - wo_) : -wo_;
-                            double maxCorr[3], maxCorrb[3] = {0, 0, 0};
-                            for (int j = 0; j < 3; j++) maxCorr[j] = cf * fr.s * (Un[j] - Uc[j]);
-                            luvLimit(corr, maxCorr, corrL);
-                            luvLimitAdj(corr, maxCorr, outb, corrb, maxCorrb);
-                            for (int j = 0; j < 3; j++) U2[j] -= cf * fr.s * maxCorrb[j];
-                        }
-                        else
-                            for (int j = 0; j < 3; j++) { corrL[j] = corr[j]; corrb[j] = outb[j]; }
-                        if (cUp)
-                            for (int j = 0; j < 3; j++)
-                                for (int i = 0; i < 3; i++) gUb[j * 3 + i] += dC[i] * corrb[j];
-                        if (fr.s > 0)
-                            for (int j = 0; j < 3; j++) phib_acc += corrL[j] * lam[j];
-                    }
-                    // non-orthogonal correction: MV_own -= gf*cg_j, MV_nei += gf*cg_j
-                    for (int j = 0; j < 3; j++)
-                    {
-                        double cg = 0.0;
-                        for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gUc[j * 3 + i] + wn * gUn[j * 3 + i]);
-                        gfb -= cg * lam[j];
-                        const double cgb = -gf * lam[j];
-                        for (int i = 0; i < 3; i++) gUb[j * 3 + i] += wc * kv[i] * cgb;
-                    }
-                    // dev2 term: MV_own -= fl_j, MV_nei += fl_j, fl = wc*tc + wn*tn
-                    double trb = 0.0;
-                    for (int j = 0; j < 3; j++)
-                    {
-                        const double tcb = -wc * lam[j];
-                        const double tcj = Sv[0] * gUc[0 * 3 + j] + Sv[1] * gUc[1 * 3 + j] + Sv[2] * gUc[2 * 3 + j] - (2.0 / 3.0) * trc * Sv[j];
-                        nuEb += tcb * tcj;
-                        for (int i = 0; i < 3; i++) gUb[i * 3 + j] += nuEc * Sv[i] * tcb;
-                        trb -= (2.0 / 3.0) * nuEc * Sv[j] * tcb;
-                    }
-                    gUb[0] += trb; gUb[4] += trb; gUb[8] += trb;
-                    nuEb += wc * mS * (dl * gb + gfb);
-                }
-                // ---- SA rows c and n
-                if (q.turb)
-                {
-                    const double ntn = s.nt[n];
-                    const double qn = x.nt[n] * (q.nrNut ? 1.0 / m.V[n] : 1.0);
-                    const double wpc = schN == DIV_LINEAR ? wc : wupc;
-                    const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
-                    const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
-                    const double g = gf * dl;
-                    nt2 += qc * (wpc * mf + g - mf) + qn * (-mf + wpn * mf - g);
-                    const double gb = (qc - qn) * (ntc - ntn);
-                    double gfb = 0.0;
-                    const double lam = fr.s * (qc - qn);
-                    if (fr.s > 0) phib_acc += qc * (1.0 - wpc) * (ntn - ntc) - qn * (1.0 - wpn) * (ntc - ntn);
-                    if (schN == DIV_LINEAR_UPWIND)
-                    {
-                        if (cUp)
-                            for (int i = 0; i < 3; i++) gNb[i] += dC[i] * phi * lam;
-                        if (fr.s > 0)
-                        {
-                            const int u = cUp ? c : n;
-                            const double d[3] = {m.Cfx[f] - m.Cx[u], m.Cfy[f] - m.Cy[u], m.Cfz[f] - m.Cz[u]};
-                            double corr = 0.0;
-                            for (int i = 0; i < 3; i++) corr += d[i] * r.gNt[(size_t)i * nT + u];
-                            phib_acc += corr * lam;
-                        }
-                    }
-                    double cg = 0.0;
-                    for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gNc[i] + wn * r.gNt[(size_t)i * nT + n]);
-                    gfb -= cg * lam;
-                    const double cgb = -gf * lam;
-                    for (int i = 0; i < 3; i++) gNb[i] += wc * kv[i] * cgb;
-                    nt2 += wc * mS * (dl * gb + gfb) / SA::sigma;
-                }
-            }
-            else
-            {
-                const int b = f - m.nIF, pa = m.bPatch[b];
-                const double im = 1.0 / mS;
-                const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
-                const int kU = q.bcKind[F_U][pa];
-                BCv bu;
-                double uw[3];
-                mrfWallRef(m, f, q.bcVal[F_U][pa], uw);
-                bcVector(kU, uw, Uc, mf, dl, nh, bu);
-                double ntb = 0.0, sngN = 0.0, frN = 0.0;
-                if (q.turb) bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
-                double dP = 0.0, dNb = 0.0, dUn[3] = {0.0, 0.0, 0.0};
-                double nutb = 0.0;
-                if (q.turb)
-                    nutb = (FEAT & 2) ? nutBoundary<true>(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, Uc, bu.val, dl, dP, dNb, dUn)
-                                      : nutBoundaryBasic(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], ntb, q.nu, dP, dNb);
-                const double nuEB = nutb + q.nu;
-                const double G = nuEB * mS;
-                // internalCoeffs and the argmax/argmin components used by relax()
-                double ic[3];
-                int kmax = 0, kmin = 0;
-                for (int j = 0; j < 3; j++)
-                {
-                    ic[j] = mf * bu.vic[j] - G * bu.gic[j];
-                    if (j > 0)
-                    {
-                        if (fabs(ic[j]) > fabs(ic[kmax])) kmax = j;
-                        if (ic[j] < ic[kmin]) kmin = j;
-                    }
-                }
-                double mb = -D0c, Gb_ = 0.0;
-                for (int j = 0; j < 3; j++)
-                {
-                    double icb = Dnc / 3.0;
-                    if (j == kmin) icb -= Dnc;
-                    if (j == kmax) icb += D1c * sgn(ic[j]);
-                    mb += bu.vic[j] * icb + mtc[j] * bu.val[j];
-                    Gb_ += -bu.gic[j] * icb - mtc[j] * bu.sng[j];
-                }
-                double valb[3], sngb[3];
-                for (int j = 0; j < 3; j++) { valb[j] = mf * mtc[j]; sngb[j] = -G * mtc[j]; }
-                // dev2 boundary term: MV_j -= nuEB * X_j
-                double Gbd[9];
-                for (int j = 0; j < 3; j++)
-                {
-                    const double nG = nh[0] * gUc[j * 3 + 0] + nh[1] * gUc[j * 3 + 1] + nh[2] * gUc[j * 3 + 2];
-                    for (int i = 0; i < 3; i++) Gbd[j * 3 + i] = gUc[j * 3 + i] + nh[i] * (bu.sng[j] - nG);
-                }
-                const double trbv = Gbd[0] + Gbd[4] + Gbd[8];
-                double nuEBb = mS * Gb_;
-                double Gbb[9];
-                for (int i = 0; i < 9; i++) Gbb[i] = 0.0;
-                double trbb = 0.0;
-                for (int j = 0; j < 3; j++)
-                {
-                    const double X = Sv[0] * Gbd[0 * 3 + j] + Sv[1] * Gbd[1 * 3 + j] + Sv[2] * Gbd[2 * 3 + j] - (2.0 / 3.0) * trbv * Sv[j];
-                    nuEBb -= X * mtc[j];
-                    const double Xb = -nuEB * mtc[j];
-                    for (int i = 0; i < 3; i++) Gbb[i * 3 + j] += Sv[i] * Xb;
-                    trbb -= (2.0 / 3.0) * Sv[j] * Xb;
-                }
-                Gbb[0] += trbb; Gbb[4] += trbb; Gbb[8] += trbb;
-                boundaryGradAdj(nh, Gbb, gUb, sngb);
-                bcVectorAdj(kU, mf, dl, nh, valb, sngb, U2);
-                if ((FEAT & 4) && a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(kU, mf, dl, valb, sngb, refb);
-                // nut_b -> nut_c / nuTilda_b / U_c (wall function)
-                nuEb += dP * nuEBb;
-                if (FEAT & 2)
-                    for (int j = 0; j < 3; j++) U2[j] += dUn[j] * nuEBb;
-                double ntbb = dNb * nuEBb;
-                if (q.turb)
-                {
-                    const double Gs = (ntb + q.nu) / SA::sigma * mS;
-                    mb += qc * (ntb - ntc);
-                    ntbb += qc * mf - qc * sngN * mS / SA::sigma;
-                    const double sngNb = -qc * Gs;
-                    nt2 += -qc * mf + (1.0 - frN) * ntbb - frN * dl * sngNb;
-                }
-                phib_acc += mb;
-            }
-            if (fr.s > 0)
-                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x.phi[f]) * q.sPhi * mS;
-            else if (fr.n >= nC)
-                y[offPhi + f] = 0.0; // cut face whose phi belongs to the neighbouring rank
-        }
-        if (q.turb) saSourceAdj(ntc, q.nu, m.yWall[c], gUc, gNc, zc, nt2, gUb, gNb, q.saFv3);
-        for (int j = 0; j < 3; j++) a.U2[(size_t)j * nC + c] = U2[j];
-        if ((FEAT & 4) && a.bcRefb)
-            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += refb[j];
-        a.nt2[c] = nt2;
-        a.nutb[c] = nuEb;
-        for (int i = 0; i < 9; i++) a.gUb[(size_t)i * nT + c] = gUb[i];
-        for (int i = 0; i < 3; i++) a.gNtb[(size_t)i * nT + c] = gNb[i];
+        const GAcc A{m, s, r, a, x, nullptr, nullptr, nullptr, y + (size_t)(q.turb ? 5 : 4) * m.nC};
+        revBCell<NF, FEAT>(A, q, c, false);
     }
 };
+
+// RevC of one cell: adjoint of FwdA (Gauss-gradient transpose, nut(nuTilda), BC adjoints) + final sum and state scaling
+template <int NF, class Acc>
+DAB_HD void revCCell(const Acc& A, const Params& q, int c, int functionMode)
+{
+    const double iVc = 1.0 / A.V(c);
+    double Ub[3], pb = A.pdir(c), nb = 0.0;
+    for (int j = 0; j < 3; j++) Ub[j] = A.Udir(c, j) + A.U2(c, j);
+    double gUbc[9], gPbc[3], gNbc[3];
+    for (int i = 0; i < 9; i++) gUbc[i] = A.gUb(c, i) * iVc;
+    for (int i = 0; i < 3; i++)
+    {
+        gPbc[i] = A.gPb(c, i) * iVc;
+        gNbc[i] = q.turb ? A.gNtb(c, i) * iVc : 0.0;
+    }
+    if (q.turb) nb = A.nt2(c) + A.nutb(c) * dnut_dnt(A.nt(c), q.nu);
+    double refb[3] = {0, 0, 0};
+    DAB_ACC_FACES(NF)
+    _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : A.maxCF()); k++)
+    {
+        const FaceRef fr = DAB_ACC_FACE(NF, k);
+        if (fr.f < 0) break;
+        const int f = fr.f;
+        double Sv[3];
+        A.Sf(f, Sv);
+        const double So[3] = {fr.s * Sv[0], fr.s * Sv[1], fr.s * Sv[2]}; // outward
+        if (!fr.bnd)
+        {
+            const int n = fr.n;
+            const double wf = A.w(f);
+            const double wc = fr.s > 0 ? wf : 1.0 - wf;
+            const double iVn = 1.0 / A.V(n);
+            for (int j = 0; j < 3; j++)
+            {
+                double t = 0.0;
+                for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - A.gUb(n, j * 3 + i) * iVn);
+                Ub[j] += wc * t;
+            }
+            double tp = 0.0, tn = 0.0;
+            for (int i = 0; i < 3; i++)
+            {
+                tp += So[i] * (gPbc[i] - A.gPb(n, i) * iVn);
+                if (q.turb) tn += So[i] * (gNbc[i] - A.gNtb(n, i) * iVn);
+            }
+            pb += wc * tp;
+            nb += wc * tn;
+        }
+        else
+        {
+            const int pa = A.patch(f);
+            const double phib = A.phi(f), dl = A.delta(f);
+            const double im = 1.0 / A.magSf(f);
+            const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+            double valb[3];
+            const double sngb[3] = {0.0, 0.0, 0.0};
+            for (int j = 0; j < 3; j++) valb[j] = So[0] * gUbc[j * 3 + 0] + So[1] * gUbc[j * 3 + 1] + So[2] * gUbc[j * 3 + 2];
+            bcVectorAdj(q.bcKind[F_U][pa], phib, dl, nh, valb, sngb, Ub);
+            if (A.bcRefOn(pa)) bcVectorRefAdj(q.bcKind[F_U][pa], phib, dl, valb, sngb, refb);
+            const double frp = bcFrac(q.bcKind[F_P][pa], phib);
+            pb += (1.0 - frp) * (So[0] * gPbc[0] + So[1] * gPbc[1] + So[2] * gPbc[2]);
+            if (q.turb)
+            {
+                const double frn = bcFrac(q.bcKind[F_NUTILDA][pa], phib);
+                nb += (1.0 - frn) * (So[0] * gNbc[0] + So[1] * gNbc[1] + So[2] * gNbc[2]);
+            }
+        }
+    }
+    if (A.bcRefAny())
+        for (int j = 0; j < 3; j++) A.addBcRef(c, j, refb[j]);
+    for (int j = 0; j < 3; j++) A.setYU(c, j, Ub[j] * q.sU);
+    A.setYP(c, pb * q.sP);
+    if (q.turb) A.setYN(c, nb * q.sNut);
+    if (functionMode)
+    {
+        // phi adjoint of a function: no face-flux dependence for the force function
+        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : A.maxCF()); k++)
+        {
+            const FaceRef fr = DAB_ACC_FACE(NF, k);
+            if (fr.f < 0) break;
+            if (fr.s > 0 || A.ghost(fr.n)) A.setYPhi(fr.f, 0.0);
+        }
+    }
+}
 
 template <int NF>
 struct RevC
@@ -687,196 +661,9 @@ struct RevC
     int functionMode;
     DAB_HD void operator()(int c) const
     {
-        const int nT = m.nCtot, nC = m.nC;
-        const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-        const double iVc = 1.0 / m.V[c];
-        double Ub[3], pb = a.pdir[c], nb = 0.0;
-        for (int j = 0; j < 3; j++) Ub[j] = a.Udir[(size_t)j * nC + c] + a.U2[(size_t)j * nC + c];
-        double gUbc[9], gPbc[3], gNbc[3];
-        for (int i = 0; i < 9; i++) gUbc[i] = a.gUb[(size_t)i * nT + c] * iVc;
-        for (int i = 0; i < 3; i++)
-        {
-            gPbc[i] = a.gPb[(size_t)i * nT + c] * iVc;
-            gNbc[i] = q.turb ? a.gNtb[(size_t)i * nT + c] * iVc : 0.0;
-        }
-        if (q.turb) nb = a.nt2[c] + a.nutb[c] * dnut_dnt(s.nt[c], q.nu);
-        DAB_FACE_PREFETCH(NF)
-        _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
-        {
-            const FaceRef fr = DAB_FACE(NF, k);
-            if (fr.f < 0) break;
-            const int f = fr.f;
-            const double So[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]}; // outward
-            if (!fr.bnd)
-            {
-                const int n = fr.n;
-                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f];
-                const double iVn = 1.0 / m.V[n];
-                for (int j = 0; j < 3; j++)
-                {
-                    double t = 0.0;
-                    for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - a.gUb[(size_t)(j * 3 + i) * nT + n] * iVn);
-                    Ub[j] += wc * t;
-                }
-                double tp = 0.0, tn = 0.0;
-                for (int i = 0; i < 3; i++)
-                {
-                    tp += So[i] * (gPbc[i] - a.gPb[(size_t)i * nT + n] * iVn);
-                    if (q.turb) tn += So[i] * (gNbc[i] - a.gNtb[(size_t)i * nT + n] * iVn);
-                }
-                pb += wc * tp;
-                nb += wc * tn;
-            }
-            else
-            {
-                const int b = f - m.nIF, pa = m.bPatch[b];
-                const double phib = s.phi[f], dl = m.delta[f];
-                const double im = 1.0 / m.magSf[f];
-                const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
-                double valb[3];
-                const double sngb[3] = {0.0, 0.0, 0.0};
-                for (int j = 0; j < 3; j++) valb[j] = So[0] * gUbc[j * 3 + 0] + So[1] * gUbc[j * 3 + 1] + So[2] * gUbc[j * 3 + 2];
-                bcVectorAdj(q.bcKind[F_U][pa], phib, dl, nh, valb, sngb, Ub);
-                if (a.bcRefb && ((a.bcMask >> pa) & 1u))
-                {
-                    double refb[3] = {0, 0, 0};
-                    bcVectorRefAdj(q.bcKind[F_U][pa], phib, dl, valb, sngb, refb);
-                    for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += refb[j];
-                }
-                const double frp = bcFrac(q.bcKind[F_P][pa], phib);
-                pb += (1.0 - frp) * (So[0] * gPbc[0] + So[1] * gPbc[1] + So[2] * gPbc[2]);
-                if (q.turb)
-                {
-                    const double frn = bcFrac(q.bcKind[F_NUTILDA][pa], phib);
-                    nb += (1.0 - frn) * (So[0] * gNbc[0] + So[1] * gNbc[1] + So[2] * gNbc[2]);
-                }
-            }
-        }
-        (void)Uc;
-        for (int j = 0; j < 3; j++) y[3 * c + j] = Ub[j] * q.sU;
-        y[(size_t)3 * nC + c] = pb * q.sP;
-        if (q.turb) y[(size_t)4 * nC + c] = nb * q.sNut;
-        if (functionMode)
-        {
-            // phi adjoint of a function: no face-flux dependence for the force function
-            const size_t offPhi = (size_t)(q.turb ? 5 : 4) * nC;
-            DAB_FACE_PREFETCH(NF)
-            _Pragma("unroll") for (int k = 0; k < (NF > 0 ? NF : m.maxCF); k++)
-            {
-                const FaceRef fr = DAB_FACE(NF, k);
-                if (fr.f < 0) break;
-                if (fr.s > 0 || fr.n >= nC) y[offPhi + fr.f] = 0.0;
-            }
-        }
-    }
-};
-
-// lane-per-face pilot of RevC (DAB_LANES=1, one GPU, product mode): 8 lanes per cell, 8 accumulators (Ub[3], pb, nb, refb[3])
-// reduced with the same xor-butterfly as RevALanes; lane 0 adds the cell's own terms and writes
-struct RevCLanes
-{
-    MeshView m;
-    Params q;
-    StateView s;
-    RecordView r;
-    AdjView a;
-    double* y;
-    DAB_HD void lane(int c, int ln, double* A) const
-    {
-        const int nT = m.nCtot;
-        for (int i = 0; i < 8; i++) A[i] = 0.0;
-        double* Ub = A;
-        double& pb = A[3];
-        double& nb = A[4];
-        double* refb = A + 5;
-        const double iVc = 1.0 / m.V[c];
-        double gUbc[9], gPbc[3], gNbc[3];
-        for (int i = 0; i < 9; i++) gUbc[i] = a.gUb[(size_t)i * nT + c] * iVc;
-        for (int i = 0; i < 3; i++)
-        {
-            gPbc[i] = a.gPb[(size_t)i * nT + c] * iVc;
-            gNbc[i] = q.turb ? a.gNtb[(size_t)i * nT + c] * iVc : 0.0;
-        }
-        for (int k = ln; k < m.maxCF; k += REV_LANES)
-        {
-            const FaceRef fr = faceOf(m, c, k);
-            if (fr.f < 0) break;
-            const int f = fr.f;
-            const double So[3] = {fr.s * m.Sx[f], fr.s * m.Sy[f], fr.s * m.Sz[f]};
-            if (!fr.bnd)
-            {
-                const int n = fr.n;
-                const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f];
-                const double iVn = 1.0 / m.V[n];
-                for (int j = 0; j < 3; j++)
-                {
-                    double t = 0.0;
-                    for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - a.gUb[(size_t)(j * 3 + i) * nT + n] * iVn);
-                    Ub[j] += wc * t;
-                }
-                double tp = 0.0, tn = 0.0;
-                for (int i = 0; i < 3; i++)
-                {
-                    tp += So[i] * (gPbc[i] - a.gPb[(size_t)i * nT + n] * iVn);
-                    if (q.turb) tn += So[i] * (gNbc[i] - a.gNtb[(size_t)i * nT + n] * iVn);
-                }
-                pb += wc * tp;
-                nb += wc * tn;
-            }
-            else
-            {
-                const int b = f - m.nIF, pa = m.bPatch[b];
-                const double phib = s.phi[f], dl = m.delta[f];
-                const double im = 1.0 / m.magSf[f];
-                const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
-                double valb[3];
-                const double sngb[3] = {0.0, 0.0, 0.0};
-                for (int j = 0; j < 3; j++) valb[j] = So[0] * gUbc[j * 3 + 0] + So[1] * gUbc[j * 3 + 1] + So[2] * gUbc[j * 3 + 2];
-                bcVectorAdj(q.bcKind[F_U][pa], phib, dl, nh, valb, sngb, Ub);
-                if (a.bcRefb && ((a.bcMask >> pa) & 1u)) bcVectorRefAdj(q.bcKind[F_U][pa], phib, dl, valb, sngb, refb);
-                const double frp = bcFrac(q.bcKind[F_P][pa], phib);
-                pb += (1.0 - frp) * (So[0] * gPbc[0] + So[1] * gPbc[1] + So[2] * gPbc[2]);
-                if (q.turb)
-                {
-                    const double frn = bcFrac(q.bcKind[F_NUTILDA][pa], phib);
-                    nb += (1.0 - frn) * (So[0] * gNbc[0] + So[1] * gNbc[1] + So[2] * gNbc[2]);
-                }
-            }
-        }
-    }
-    DAB_HD void finish(int c, const double* A) const
-    {
-        const int nC = m.nC;
-        for (int j = 0; j < 3; j++) y[3 * c + j] = (a.Udir[(size_t)j * nC + c] + a.U2[(size_t)j * nC + c] + A[j]) * q.sU;
-        y[(size_t)3 * nC + c] = (a.pdir[c] + A[3]) * q.sP;
-        if (q.turb) y[(size_t)4 * nC + c] = (a.nt2[c] + a.nutb[c] * dnut_dnt(s.nt[c], q.nu) + A[4]) * q.sNut;
-        if (a.bcRefb)
-            for (int j = 0; j < 3; j++) a.bcRefb[(size_t)j * nC + c] += A[5 + j];
-    }
-    DAB_HD void operator()(int t) const
-    {
-        const int c = t / REV_LANES, ln = t - c * REV_LANES;
-#if defined(__CUDA_ARCH__)
-        double A[8];
-        lane(c, ln, A);
-        const long long left = (long long)REV_LANES * m.nC - (long long)(t - (t & 31));
-        const unsigned mask = left >= 32 ? 0xffffffffu : ((1u << (int)left) - 1u);
-        for (int off = 1; off < REV_LANES; off <<= 1)
-            for (int i = 0; i < 8; i++) A[i] += __shfl_xor_sync(mask, A[i], off);
-        if (ln == 0) finish(c, A);
-#else
-        if (ln != 0) return;
-        double L[REV_LANES][8], T[REV_LANES][8];
-        for (int l = 0; l < REV_LANES; l++) lane(c, l, L[l]);
-        for (int off = 1; off < REV_LANES; off <<= 1)
-        {
-            for (int l = 0; l < REV_LANES; l++)
-                for (int i = 0; i < 8; i++) T[l][i] = L[l][i] + L[l ^ off][i];
-            for (int l = 0; l < REV_LANES; l++)
-                for (int i = 0; i < 8; i++) L[l][i] = T[l][i];
-        }
-        finish(c, L[0]);
-#endif
+        const size_t nC = m.nC;
+        const GAcc A{m, s, r, a, PsiView{}, y, y + 3 * nC, y + 4 * nC, y + (size_t)(q.turb ? 5 : 4) * nC};
+        revCCell<NF>(A, q, c, functionMode);
     }
 };
 

@@ -13,6 +13,7 @@
 #include "views.hpp"
 #include "fwd_kernels.hpp"
 #include "rev_kernels.hpp"
+#include "tile_kernels.hpp"
 #include "comp_kernels.hpp"
 #include "comp_rev_kernels.hpp"
 #include "krylov.hpp"
@@ -218,6 +219,13 @@ struct Solver
     Halo halo;
     Partition part;
     DevBuf<double> psiP, psiN, psiPhi, psiT; // working copies of the input vector with ghost slots (multi-rank only)
+
+    // CTA-resident product kernels (tile_kernels.hpp): one GPU, DASimpleFoam without an MRF zone
+    TileMap tiles;
+    DevBuf<int32_t> dTileCum, dTileGid, dTileTf, dTileTn;
+    TileView tvw{};
+    bool tilesOn = false;
+    int tileCellsHint = 0; // adjEqnOption.tileCells (extension): cells per tile of a tile-major numbered mesh; 0 = search
 
     bool fvSourceDirty = false;
     bool hex6 = false; // every owned cell has exactly 6 faces: the kernels with fully unrolled, break-free face loops apply
@@ -598,6 +606,7 @@ struct Solver
             fpRelTol = a->numOr("fpRelTol", fpRelTol);
             fpMinResTolDiff = a->numOr("fpMinResTolDiff", fpMinResTolDiff);
             fpOmega = a->numOr("fpOmega", fpOmega);
+            tileCellsHint = (int)a->numOr("tileCells", tileCellsHint);
             {
                 const int pr = (int)a->numOr("coarseProbeReach", coarseProbeReach);
                 if (pr != coarseProbeReach) { coarseProbeReach = pr; kry.pcValid = false; }
@@ -908,7 +917,7 @@ struct Solver
         dOwn.upload(be, hm.own);
         dNei.upload(be, hm.nei);
         dCellFaces.upload(be, hm.cellFaces);
-        hex6 = hm.maxCF == 6;
+        hex6 = hm.maxCF == 6 && !(getenv("DAB_NOHEX6") && atoi(getenv("DAB_NOHEX6")) > 0); // DAB_NOHEX6: measurement hook (rolled face loops)
         for (size_t i = 0; i < hm.cellFaces.size() && hex6; i++)
             if (hm.cellFaces[i] < 0) hex6 = false;
         hm.buildCellNbr();
@@ -979,6 +988,69 @@ struct Solver
             av.cHe = aCHe.p; av.cEk = aCEk.p;
         }
         dR.alloc(be, nd); dX.alloc(be, nd); dY2.alloc(be, nd);
+        setupTiles();
+    }
+
+    // choose a tile size whose tiles (with two halo rings) fit the capacities compiled into tile_kernels.hpp and build the tile map
+    void setupTiles()
+    {
+        tilesOn = false;
+        const char* env = getenv("DAB_TILE");
+        if (env && atoi(env) == 0) return;
+        if (nRanks > 1 || par.comp || mrf.on || hm.nC < 64) return;
+        std::vector<int> cand;
+        if (tileCellsHint > 0) cand.push_back(tileCellsHint);
+        for (int t : {224, 196, 192, 168, 160, 144, 128, 112, 96, 80, 64, 48, 32}) cand.push_back(t);
+        int best = 0;
+        double bestRatio = 1e30;
+        for (int T : cand)
+        {
+            if (T > TILE_TMAX || T < 1) continue;
+            int maxRun, maxAll;
+            long sumAll;
+            TileMap::measure(hm, T, 2, maxRun, maxAll, sumAll);
+            if (maxRun > TILE_EXT1 || maxAll > TILE_EXT2) continue;
+            const double ratio = (double)sumAll / hm.nC;
+            if (ratio < bestRatio)
+            {
+                bestRatio = ratio;
+                best = T;
+            }
+            if (T == tileCellsHint && ratio < 1.8) break; // the caller's hint fits and is compact
+        }
+        if (!best) return;
+        tiles.build(hm, best, 2);
+        dTileCum.upload(be, tiles.cum);
+        dTileGid.upload(be, tiles.gid);
+        dTileTf.upload(be, tiles.tf);
+        dTileTn.upload(be, tiles.tn);
+        tvw.T = tiles.T; tvw.nTiles = tiles.nTiles; tvw.R = tiles.R; tvw.maxCF = tiles.maxCF; tvw.ln = tiles.ln; tvw.ls = tiles.ls;
+        tvw.cum = dTileCum.p; tvw.gid = dTileGid.p; tvw.tf = dTileTf.p; tvw.tn = dTileTn.p;
+        tilesOn = true;
+        if (printInfo || getenv("DAB_TILE_INFO"))
+            fprintf(stderr, "[dab200] tiles: %d cells per tile, %d tiles, local cells per owned cell %.3f (ring 1: %.3f), max %d / %d\n", tiles.T,
+                    tiles.nTiles, bestRatio, (double)tiles.sumRun / hm.nC, tiles.maxRun, tiles.maxAll);
+    }
+
+    bool tileProduct() const { return tilesOn && av.bcRefb == nullptr; }
+    void launchTileA(const PsiView& pv)
+    {
+        if (hex6) be.launchTiles(tvw.nTiles, ProdTileA<6>{mv, par, sv, rv, av, pv, tvw});
+        else be.launchTiles(tvw.nTiles, ProdTileA<0>{mv, par, sv, rv, av, pv, tvw});
+    }
+    void launchTileBC(const PsiView& pv, double* y)
+    {
+        if (hex6)
+        {
+            switch (featureMask())
+            {
+            case 0: be.launchTiles(tvw.nTiles, ProdTileBC<6, 0>{mv, par, sv, rv, av, pv, y, tvw}); break;
+            case 1: be.launchTiles(tvw.nTiles, ProdTileBC<6, 1>{mv, par, sv, rv, av, pv, y, tvw}); break;
+            case 2: be.launchTiles(tvw.nTiles, ProdTileBC<6, 2>{mv, par, sv, rv, av, pv, y, tvw}); break;
+            default: be.launchTiles(tvw.nTiles, ProdTileBC<6, 3>{mv, par, sv, rv, av, pv, y, tvw}); break;
+            }
+        }
+        else be.launchTiles(tvw.nTiles, ProdTileBC<0, 3>{mv, par, sv, rv, av, pv, y, tvw});
     }
 
     // initial states from the 0/ files (DASimpleFoam::initSolver createFieldsSimple.H role); phi = linear-interpolated U . Sf
@@ -1262,17 +1334,7 @@ struct Solver
     }
 
     // y = diag(n) (dR/dW)^T x on device vectors (external layout)
-    void launchRevA(const PsiView& pv)
-    {
-        // DAB_LANES=1: lane-per-face pilot mapping of RevA (rev_kernels.hpp RevALanes); the default stays the measured cell-per-thread kernel
-        static const bool lanes = getenv("DAB_LANES") && atoi(getenv("DAB_LANES")) > 0;
-        if (lanes && hm.nC < (1 << 28))
-        {
-            be.launch(hm.nC * REV_LANES, RevALanes{mv, par, sv, rv, av, pv});
-            return;
-        }
-        DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv);
-    }
+    void launchRevA(const PsiView& pv) { DAB_LAUNCH_NF(hm.nC, RevA, mv, par, sv, rv, av, pv); }
 
     PsiView psiView(const double* x)
     {
@@ -1343,11 +1405,15 @@ struct Solver
         if (!comm.active())
         {
             const PsiView pv = psiView(x);
+            if (tileProduct())
+            {
+                launchTileA(pv);
+                launchTileBC(pv, y);
+                return;
+            }
             launchRevA(pv);
             DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
-            static const bool lanes = getenv("DAB_LANES") && atoi(getenv("DAB_LANES")) > 0;
-            if (lanes && hm.nC < (1 << 28)) be.launch(hm.nC * REV_LANES, RevCLanes{mv, par, sv, rv, av, y}); // pilot mapping (rev_kernels.hpp)
-            else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
+            DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
             return;
         }
         // several ranks: every ghost exchange runs on the communication stream while the interior cells (no neighbour on
@@ -1416,14 +1482,16 @@ struct Solver
             }
             return;
         }
+        if (tileProduct())
+        {
+            // tile kernels: 0 = RevA tile, 1 = fused RevB+RevC tile (there is no separate RevC)
+            if (which == 0) launchTileA(pv);
+            else if (which == 1) launchTileBC(pv, dY2.p);
+            return;
+        }
         if (which == 0) launchRevA(pv);
         else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
-        else
-        {
-            static const bool lanes = getenv("DAB_LANES") && atoi(getenv("DAB_LANES")) > 0;
-            if (lanes && hm.nC < (1 << 28)) be.launch(hm.nC * REV_LANES, RevCLanes{mv, par, sv, rv, av, dY2.p});
-            else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
-        }
+        else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
     }
 
     void matVec(const double* x, double* y)

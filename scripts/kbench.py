@@ -17,7 +17,10 @@ mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=nk, span=1.0 if nk > 1 else 0.1
 d = tempfile.mkdtemp(prefix="dab_kb_")
 cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
 for lib in libs:
-    sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0)), caseDir=d, _lib_path=lib)
+    opts = dict(normalizeStates=dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0))
+    if tile:
+        opts["adjEqnOption"] = dict(tileCells=int(np.prod([int(v) for v in tile.split("x")])))
+    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib)
     n = sol.getNLocalAdjointStates()
     y = np.zeros(sol.getNLocalCells()); sol.getOFField("yWall", "scalar", y)
     sol.updateOFFields(cases.boundary_layer_state(mesh, y, noise=0.001))
