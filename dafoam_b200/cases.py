@@ -67,7 +67,7 @@ def _naca0012_y(x):
     return 0.6 * (0.2969 * np.sqrt(np.maximum(x, 0.0)) - 0.1260 * x - 0.3516 * x**2 + 0.2843 * x**3 - 0.1036 * x**4)
 
 
-def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_centres, family_major=None):
+def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_centres, family_major=None, bface_by_owner=False):
     """Orient faces (normal owner->neighbour / outward), sort, and build a PolyMesh.
 
     quads: (n,4) point ids; cell_a: (n,) one adjacent cell; cell_b: (n,) other cell or -1;
@@ -99,7 +99,9 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     else:
         order_i = ii[np.lexsort((nei[ii], own[ii]))]
     bi = np.nonzero(~internal)[0]
-    order_b = bi[np.lexsort((np.arange(bi.size), patch_of_bface[bi]))]
+    # boundary faces patch by patch, inside a patch by owner cell (the order OpenFOAM's renumberMesh leaves): the boundary
+    # faces of consecutive cells are consecutive in memory
+    order_b = bi[np.lexsort((own[bi], patch_of_bface[bi]))] if bface_by_owner else bi[np.lexsort((np.arange(bi.size), patch_of_bface[bi]))]
     order = np.concatenate([order_i, order_b])
     faces = quads[order]
     owner = own[order]
@@ -114,7 +116,7 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     return PolyMesh(points, faces, owner, neighbour, patches)
 
 
-def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None, family_major=False):
+def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None, family_major=False, bface_by_owner=None):
     """NACA0012 O-grid: ni cells around the airfoil, nj cells radially (geometric stretching
     from `first_dy` chord at the wall to the farfield circle of `radius` chords), nk cells in z.
     Patches: wing (wall), inout (patch), sym1/sym2 (symmetry)."""
@@ -226,7 +228,9 @@ def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, 
     pf = np.concatenate(pf)
     defs = [("wing", "wall"), ("inout", "patch"), ("sym1", "symmetry"), ("sym2", "symmetry")]
     fam = np.concatenate([np.full(q.shape[0], i) for i, q in enumerate(quads_list)]) if family_major else None
-    return _assemble(points, quads, ca, cb, pf, defs, cc, family_major=fam)
+    # tile-major cell numbering comes with boundary faces ordered by owner cell (the order OpenFOAM's renumberMesh leaves)
+    return _assemble(points, quads, ca, cb, pf, defs, cc, family_major=fam,
+                     bface_by_owner=(tile is not None) if bface_by_owner is None else bface_by_owner)
 
 
 def channel(nx=20, ny=10, nz=1, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.15):

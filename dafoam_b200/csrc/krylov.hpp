@@ -328,10 +328,13 @@ struct VecOps
     Comm* comm = nullptr; // dot products are summed over the ranks (the MPI_Allreduce of the reference's KSP)
     DevBuf<double> partial, dOut;
     std::vector<double> hOut;
+    int cap = 0; // vectors one dots() call may take; init() only ever grows it (GMRES, IDR(s) and the fixed-point solver share the object)
     void init(Backend& b, Comm* c, int maxK)
     {
         be = &b;
         comm = c;
+        if (maxK <= cap) return;
+        cap = maxK;
 #ifndef DAB_HOSTSIM
         partial.alloc(b, (size_t)DOT_BLOCKS * (maxK + 2));
 #endif
@@ -341,6 +344,7 @@ struct VecOps
     // out[j] = V_j . w, j < k  (host result)
     const double* dots(const double* V, int64_t ld, int k, const double* w, int n)
     {
+        if (k > cap) throw Error("VecOps::dots: more vectors than the workspace was initialised for");
 #ifndef DAB_HOSTSIM
         multiDotPartial<<<DOT_BLOCKS, DOT_THREADS, 0, be->stream>>>(V, ld, k, w, n, partial.p);
         multiDotFinal<<<(k + 63) / 64, 64, 0, be->stream>>>(partial.p, DOT_BLOCKS, k, dOut.p);
@@ -367,6 +371,7 @@ struct VecOps
     // out[j] = V_j . w left on the device (no host synchronisation); summed over the ranks
     void dotsDev(const double* V, int64_t ld, int k, const double* w, int n, double* out)
     {
+        if (k > cap) throw Error("VecOps::dotsDev: more vectors than the workspace was initialised for");
 #ifndef DAB_HOSTSIM
         multiDotPartial<<<DOT_BLOCKS, DOT_THREADS, 0, be->stream>>>(V, ld, k, w, n, partial.p);
         multiDotFinal<<<(k + 63) / 64, 64, 0, be->stream>>>(partial.p, DOT_BLOCKS, k, out);

@@ -270,7 +270,8 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
     double gUc[9], gNc[3];
     for (int i = 0; i < 9; i++) gUc[i] = A.gU(c, i);
     const double ntc = q.turb ? A.nt(c) : 0.0;
-    const double Gc = (ntc + q.nu) / SA::sigma;
+    const double rsig = 1.0 / SA::sigma, rAl = 1.0 / q.alphaU; // one division per cell instead of one per face
+    const double Gc = (ntc + q.nu) * rsig;
     for (int i = 0; i < 3; i++) gNc[i] = q.turb ? A.gNt(c, i) : 0.0;
     const double trc = gUc[0] + gUc[4] + gUc[8];
     const double V = A.V(c);
@@ -278,7 +279,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
     // cell-level adjoints of row c
     const double mtc[3] = {A.mt(c, 0), A.mt(c, 1), A.mt(c, 2)};
     const double Dnc = A.Dn(c), flc = A.flag(c);
-    const double D2c = Dnc / q.alphaU;
+    const double D2c = Dnc * rAl;
     const double D1c = flc != 0.0 ? flc * D2c : 0.0;
     const double soc = flc != 0.0 ? 0.0 : D2c;
     const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
@@ -313,7 +314,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
             const double nuEn = A.nut(n) + q.nu;
             const double mtn[3] = {A.mt(n, 0), A.mt(n, 1), A.mt(n, 2)};
             const double Dnn = A.Dn(n), fln = A.flag(n);
-            const double D2n = Dnn / q.alphaU;
+            const double D2n = Dnn * rAl;
             const double D1n = fln != 0.0 ? fln * D2n : 0.0;
             const double son = fln != 0.0 ? 0.0 : D2n;
             const double D0n = D1n + mtn[0] * Un[0] + mtn[1] * Un[1] + mtn[2] * Un[2];
@@ -421,7 +422,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
                 const double qn = A.xnt(n) * (q.nrNut ? 1.0 / A.V(n) : 1.0);
                 const double wpc = schN == DIV_LINEAR ? wc : wupc;
                 const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
-                const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
+                const double gf = (wc * Gc + wn * (ntn + q.nu) * rsig) * mS;
                 const double g = gf * dl;
                 nt2 += qc * (wpc * mf + g - mf) + qn * (-mf + wpn * mf - g);
                 const double gb = (qc - qn) * (ntc - ntn);
@@ -444,7 +445,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
                 gfb -= cg * lam;
                 const double cgb = -gf * lam;
                 for (int i = 0; i < 3; i++) gNb[i] += wc * kv[i] * cgb;
-                nt2 += wc * mS * (dl * gb + gfb) / SA::sigma;
+                nt2 += wc * mS * (dl * gb + gfb) * rsig;
             }
         }
         else
@@ -520,9 +521,9 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
             double ntbb = dNb * nuEBb;
             if (q.turb)
             {
-                const double Gs = (ntb + q.nu) / SA::sigma * mS;
+                const double Gs = (ntb + q.nu) * rsig * mS;
                 mb += qc * (ntb - ntc);
-                ntbb += qc * mf - qc * sngN * mS / SA::sigma;
+                ntbb += qc * mf - qc * sngN * mS * rsig;
                 const double sngNb = -qc * Gs;
                 nt2 += -qc * mf + (1.0 - frN) * ntbb - frN * dl * sngNb;
             }

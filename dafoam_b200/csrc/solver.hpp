@@ -107,6 +107,30 @@ template <int NF> struct LaunchTraits<cFwdC<NF>> { static constexpr int minBlock
         else be.launch(n, F<0>{__VA_ARGS__});                     \
     } while (0)
 
+// the same with an L2 prefetch plan (backend.hpp PfPlan)
+#define DAB_LAUNCH_NF_PF(pl, n, F, ...)                           \
+    do                                                            \
+    {                                                             \
+        if (hex6) be.launchPf(n, F<6>{__VA_ARGS__}, pl);          \
+        else be.launchPf(n, F<0>{__VA_ARGS__}, pl);               \
+    } while (0)
+#define DAB_LAUNCH_NFF_PF(pl, n, F, ...)                                  \
+    do                                                                    \
+    {                                                                     \
+        if (hex6)                                                         \
+        {                                                                 \
+            switch (featureMask())                                        \
+            {                                                             \
+            case 0: be.launchPf(n, F<6, 0>{__VA_ARGS__}, pl); break;      \
+            case 1: be.launchPf(n, F<6, 1>{__VA_ARGS__}, pl); break;      \
+            case 2: be.launchPf(n, F<6, 2>{__VA_ARGS__}, pl); break;      \
+            case 3: be.launchPf(n, F<6, 3>{__VA_ARGS__}, pl); break;      \
+            default: be.launchPf(n, F<6, 7>{__VA_ARGS__}, pl); break;     \
+            }                                                             \
+        }                                                                 \
+        else be.launchPf(n, F<0, 7>{__VA_ARGS__}, pl);                    \
+    } while (0)
+
 // DAInputPatchVelocity (reference src/adjoint/DAInput/DAInputPatchVelocity.C): input = (|U|, angle of attack in degrees)
 struct PatchVelocityDef
 {
@@ -166,6 +190,7 @@ struct Solver
     double fpRelTol = 1e-6, fpMinResTolDiff = 1e2, fpOmega = 0.5;
     int coarseProbeReach = 6; // cell levels a pressure perturbation reaches through the transposed Jacobian (coloured probing of the coarse operator; 0 = one product per aggregate)
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
+    int pcBlockCells = 0;          // > 0: block-Jacobi ILU with the natural cell order inside blocks of that many consecutive cells (PCASM overlap 0 + natural-order PCILU), level-scheduled
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
     double richardsonOmega = 1.0;
@@ -226,6 +251,11 @@ struct Solver
     TileView tvw{};
     bool tilesOn = false;
     int tileCellsHint = 0; // adjEqnOption.tileCells (extension): cells per tile of a tile-major numbered mesh; 0 = search
+
+    // L2 prefetch plans of the cell-per-thread product kernels (backend.hpp PfPlan)
+    DevBuf<int32_t> dPfRanges;
+    int pfChunks = 0;
+    bool pfOn = false;
 
     bool fvSourceDirty = false;
     bool hex6 = false; // every owned cell has exactly 6 faces: the kernels with fully unrolled, break-free face loops apply
@@ -617,6 +647,10 @@ struct Solver
             if (idrS < 1 || idrS > 16) throw Error("adjEqnOption.idrS: 1..16");
             globalPCIters = (int)a->numOr("globalPCIters", globalPCIters);
             {
+                const int bc = (int)a->numOr("pcBlockCells", pcBlockCells);
+                if (bc != pcBlockCells) { pcBlockCells = bc; kry.symbolic = false; kry.pcValid = false; }
+            }
+            {
                 const int cr = (int)a->numOr("pcColourRadius", pcExtraColourRadius);
                 if (cr != pcExtraColourRadius) { pcExtraColourRadius = cr; kry.symbolic = false; kry.pcValid = false; }
             }
@@ -989,18 +1023,21 @@ struct Solver
         }
         dR.alloc(be, nd); dX.alloc(be, nd); dY2.alloc(be, nd);
         setupTiles();
+        setupPrefetch();
     }
 
     // choose a tile size whose tiles (with two halo rings) fit the capacities compiled into tile_kernels.hpp and build the tile map
     void setupTiles()
     {
         tilesOn = false;
+        // measured on B200 (profiles/r02_tile_kernels.md): the tile kernels are slower than the cell-per-thread kernels (face data
+        // still comes from global memory, one or two CTAs per SM) -- they stay a tested option (DAB_TILE=1), not the default
         const char* env = getenv("DAB_TILE");
-        if (env && atoi(env) == 0) return;
+        if (!env || atoi(env) == 0) return;
         if (nRanks > 1 || par.comp || mrf.on || hm.nC < 64) return;
         std::vector<int> cand;
         if (tileCellsHint > 0) cand.push_back(tileCellsHint);
-        for (int t : {224, 196, 192, 168, 160, 144, 128, 112, 96, 80, 64, 48, 32}) cand.push_back(t);
+        for (int t : {192, 176, 168, 160, 144, 128, 112, 96, 80, 64, 48, 32}) cand.push_back(t);
         int best = 0;
         double bestRatio = 1e30;
         for (int T : cand)
@@ -1030,6 +1067,117 @@ struct Solver
         if (printInfo || getenv("DAB_TILE_INFO"))
             fprintf(stderr, "[dab200] tiles: %d cells per tile, %d tiles, local cells per owned cell %.3f (ring 1: %.3f), max %d / %d\n", tiles.T,
                     tiles.nTiles, bestRatio, (double)tiles.sumRun / hm.nC, tiles.maxRun, tiles.maxAll);
+    }
+
+    // face ranges owned by each chunk of DAB_BLOCK consecutive cells: OpenFOAM orders internal faces by owner, so the faces a
+    // chunk owns are one contiguous range; boundary faces are contiguous per patch when the patch is ordered by owner cell
+    void setupPrefetch()
+    {
+        pfOn = false;
+#ifndef DAB_HOSTSIM
+        const char* env = getenv("DAB_PREFETCH_L2");
+        if (env && atoi(env) == 0) return;
+        const int nC = hm.nC, nIF = hm.nIF;
+        for (int f = 1; f < nIF; f++)
+            if (hm.own[f] < hm.own[f - 1]) return; // not in upper-triangular order: no plan
+        const int bs = DAB_BLOCK;
+        pfChunks = (nC + bs - 1) / bs;
+        std::vector<int32_t> rg((size_t)pfChunks * 2 * PF_MAXR, 0);
+        // patches whose faces are sorted by owner
+        std::vector<int> sortedPatch;
+        for (size_t p = 0; p < hm.patches.size(); p++)
+        {
+            bool ok = hm.patches[p].size > 0;
+            for (int i = 1; i < hm.patches[p].size && ok; i++)
+                if (hm.own[hm.patches[p].start + i] < hm.own[hm.patches[p].start + i - 1]) ok = false;
+            if (ok) sortedPatch.push_back((int)p);
+        }
+        auto lower = [&](int a, int b, int c) { return (int)(std::lower_bound(hm.own.begin() + a, hm.own.begin() + b, c) - hm.own.begin()); };
+        for (int k = 0; k < pfChunks; k++)
+        {
+            const int c0 = k * bs, c1 = std::min(nC, c0 + bs);
+            int nr = 0;
+            int32_t* r = &rg[(size_t)k * 2 * PF_MAXR];
+            r[0] = lower(0, nIF, c0);
+            r[1] = lower(0, nIF, c1);
+            nr = 1;
+            for (int p : sortedPatch)
+            {
+                if (nr >= PF_MAXR) break;
+                const int a = hm.patches[p].start, b = a + hm.patches[p].size;
+                const int f0 = lower(a, b, c0), f1 = lower(a, b, c1);
+                if (f1 > f0)
+                {
+                    r[2 * nr] = f0;
+                    r[2 * nr + 1] = f1;
+                    nr++;
+                }
+            }
+        }
+        dPfRanges.upload(be, rg);
+        pfOn = true;
+#endif
+    }
+    PfPlan pfBase() const
+    {
+        PfPlan pl;
+        if (!pfOn) return pl;
+        pl.nC = hm.nC;
+        pl.nChunks = pfChunks;
+        pl.ranges = dPfRanges.p;
+        static const int ahead = getenv("DAB_PF_AHEAD") ? atoi(getenv("DAB_PF_AHEAD")) : 0;
+        pl.ahead = ahead;
+        const size_t nC = hm.nC;
+        for (int k = 0; k < hm.maxCF && k < 6; k++)
+        {
+            pl.cell(mv.cellFaces + (size_t)k * nC, 4);
+            pl.cell(mv.cellNbr + (size_t)k * nC, 4);
+        }
+        return pl;
+    }
+    PfPlan pfRevA(const PsiView& pv) const
+    {
+        PfPlan pl = pfBase();
+        if (!pfOn) return pl;
+        const size_t nT = hm.nCtot;
+        pl.cell(sv.U, 24); pl.cell(pv.U, 24); pl.cell(pv.p, 8); pl.cell(mv.V, 8); pl.cell(sv.p, 8); pl.cell(rv.rAU, 8); pl.cell(rv.D0, 8);
+        for (int j = 0; j < 3; j++) { pl.cell(rv.gP + j * nT, 8); pl.cell(rv.HbyA + j * nT, 8); }
+        pl.face(mv.magSf, 8); pl.face(mv.delta, 8); pl.face(mv.Sx, 8); pl.face(mv.Sy, 8); pl.face(mv.Sz, 8); pl.face(pv.phi, 8);
+        pl.face(mv.w, 8); pl.face(mv.kx, 8); pl.face(mv.ky, 8); pl.face(mv.kz, 8); pl.face(sv.phi, 8);
+        return pl;
+    }
+    PfPlan pfRevB(const PsiView& pv) const
+    {
+        PfPlan pl = pfBase();
+        if (!pfOn) return pl;
+        const size_t nT = hm.nCtot;
+        pl.cell(sv.U, 24); pl.cell(rv.nut, 8); pl.cell(mv.V, 8); pl.cell(av.Dn, 8); pl.cell(rv.flag, 8);
+        for (int i = 0; i < 9; i++) pl.cell(rv.gU + i * nT, 8);
+        for (int j = 0; j < 3; j++) { pl.cell(av.mt + j * nT, 8); pl.cell((j == 0 ? mv.Cx : (j == 1 ? mv.Cy : mv.Cz)), 8); }
+        if (par.turb)
+        {
+            pl.cell(sv.nt, 8); pl.cell(pv.nt, 8); pl.cell(mv.yWall, 8);
+            for (int j = 0; j < 3; j++) pl.cell(rv.gNt + j * nT, 8);
+        }
+        pl.face(sv.phi, 8); pl.face(mv.Sx, 8); pl.face(mv.Sy, 8); pl.face(mv.Sz, 8); pl.face(mv.magSf, 8); pl.face(mv.delta, 8); pl.face(mv.w, 8);
+        pl.face(mv.kx, 8); pl.face(mv.ky, 8); pl.face(mv.kz, 8); pl.face(mv.Cfx, 8); pl.face(mv.Cfy, 8); pl.face(mv.Cfz, 8); pl.face(pv.phi, 8);
+        return pl;
+    }
+    PfPlan pfRevC() const
+    {
+        PfPlan pl = pfBase();
+        if (!pfOn) return pl;
+        const size_t nT = hm.nCtot, nC = hm.nC;
+        pl.cell(av.pdir, 8); pl.cell(mv.V, 8);
+        for (int j = 0; j < 3; j++) { pl.cell(av.Udir + j * nC, 8); pl.cell(av.U2 + j * nC, 8); pl.cell(av.gPb + j * nT, 8); }
+        for (int i = 0; i < 9; i++) pl.cell(av.gUb + i * nT, 8);
+        if (par.turb)
+        {
+            pl.cell(av.nt2, 8); pl.cell(av.nutb, 8); pl.cell(sv.nt, 8);
+            for (int j = 0; j < 3; j++) pl.cell(av.gNtb + j * nT, 8);
+        }
+        pl.face(mv.Sx, 8); pl.face(mv.Sy, 8); pl.face(mv.Sz, 8); pl.face(mv.w, 8); pl.face(sv.phi, 8); pl.face(mv.delta, 8); pl.face(mv.magSf, 8);
+        return pl;
     }
 
     bool tileProduct() const { return tilesOn && av.bcRefb == nullptr; }
@@ -1411,9 +1559,9 @@ struct Solver
                 launchTileBC(pv, y);
                 return;
             }
-            launchRevA(pv);
-            DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, y);
-            DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, y, 0);
+            DAB_LAUNCH_NF_PF(pfRevA(pv), hm.nC, RevA, mv, par, sv, rv, av, pv);
+            DAB_LAUNCH_NFF_PF(pfRevB(pv), hm.nC, RevB, mv, par, sv, rv, av, pv, y);
+            DAB_LAUNCH_NF_PF(pfRevC(), hm.nC, RevC, mv, par, sv, rv, av, y, 0);
             return;
         }
         // several ranks: every ghost exchange runs on the communication stream while the interior cells (no neighbour on
@@ -1489,9 +1637,16 @@ struct Solver
             else if (which == 1) launchTileBC(pv, dY2.p);
             return;
         }
-        if (which == 0) launchRevA(pv);
-        else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
-        else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
+        if (comm.active())
+        {
+            if (which == 0) launchRevA(pv);
+            else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
+            else DAB_LAUNCH_NF(hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
+            return;
+        }
+        if (which == 0) DAB_LAUNCH_NF_PF(pfRevA(pv), hm.nC, RevA, mv, par, sv, rv, av, pv);
+        else if (which == 1) DAB_LAUNCH_NFF_PF(pfRevB(pv), hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
+        else DAB_LAUNCH_NF_PF(pfRevC(), hm.nC, RevC, mv, par, sv, rv, av, dY2.p, 0);
     }
 
     void matVec(const double* x, double* y)

@@ -184,7 +184,29 @@ inline void Solver::pcSymbolic()
     // natural one (better ILU) at the price of more, smaller launches per application (adjEqnOption.pcColourRadius, extension)
     const int rho = std::max(std::max(Lcc, Lfc + 1), Lcf + 1) + pcExtraColourRadius;
     std::vector<int> colour;
-    const int nCol = detail::greedyColour(nC, [&](int c, std::vector<int>& out) { G.ball(&c, 1, rho, out); }, colour);
+    int nCol;
+    const int blk = pcBlockCells;
+    if (blk > 0)
+    {
+        // block-Jacobi ILU(0) with the natural (given) cell order inside blocks of `blk` consecutive cells -- the reference's
+        // PCASM (overlap 0) + PCILU with natural ordering per block (DALinearEqn.C:212-216, 283-291), scheduled by dependency level:
+        // level(c) = 1 + max level of the earlier cells of the same block coupled to c.  Cells of one level (over all blocks) are
+        // mutually independent and form one "colour" of the kernels; couplings across blocks are dropped from the pattern below.
+        colour.assign(nC, 0);
+        std::vector<int> ballCells;
+        nCol = 0;
+        for (int c = 0; c < nC; c++)
+        {
+            G.ball(&c, 1, rho, ballCells);
+            int lvl = 0;
+            for (int x : ballCells)
+                if (x < c && x / blk == c / blk) lvl = std::max(lvl, colour[x] + 1);
+            colour[c] = lvl;
+            nCol = std::max(nCol, lvl + 1);
+        }
+    }
+    else
+        nCol = detail::greedyColour(nC, [&](int c, std::vector<int>& out) { G.ball(&c, 1, rho, out); }, colour);
     std::vector<std::vector<int>> cellsOf(nCol);
     for (int c = 0; c < nC; c++) cellsOf[colour[c]].push_back(c);
     K.perm.assign(K.n, -1);
@@ -258,6 +280,7 @@ inline void Solver::pcSymbolic()
         G.ball(&c, 1, Lcc, w.cellsBall, w.sc);
         for (int x : w.cellsBall)
         {
+            if (blk > 0 && x / blk != c / blk) continue; // block-Jacobi: couplings across blocks are dropped
             for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
             for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
         }
@@ -266,7 +289,8 @@ inline void Solver::pcSymbolic()
         for (int x : w.cellsBall) facesOf(x, w.faces);
         std::sort(w.faces.begin(), w.faces.end());
         w.faces.erase(std::unique(w.faces.begin(), w.faces.end()), w.faces.end());
-        for (int f : w.faces) cols.push_back(K.iperm[offPhi + f]);
+        for (int f : w.faces)
+            if (!(blk > 0 && blockCell(f) / blk != c / blk)) cols.push_back(K.iperm[offPhi + f]);
         std::sort(cols.begin(), cols.end());
     };
     auto faceRowCols = [&](Work& w, int f) {
@@ -282,6 +306,7 @@ inline void Solver::pcSymbolic()
         G.ball(seeds, nSeeds, Lcf, w.cellsBall, w.sc);
         for (int x : w.cellsBall)
         {
+            if (blk > 0 && x / blk != blockCell(f) / blk) continue;
             for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
             for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
         }
@@ -727,6 +752,7 @@ inline int Solver::solveLinearEqn(const double* rhs, double* sol, KspStats& st)
     if (kspType == "idrs") return solveIdrs(rhs, sol, st);
     const int n = nDof();
     const int m = std::max(1, std::min(gmresRestart, gmresMaxIters));
+    K.ops.init(be, &comm, m + 2); // grow-only: a no-op when another solver already sized it larger
     if (K.vCap < m + 1 || K.V.n < (size_t)(m + 1) * n)
     {
         K.V.alloc(be, (size_t)(m + 1) * n, false);

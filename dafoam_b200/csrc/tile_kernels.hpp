@@ -19,7 +19,7 @@ namespace dab
 {
 
 // capacities compiled into the tile kernels (doubles per array are EXT*, shared memory is static per program)
-constexpr int TILE_TMAX = 224; // cells per tile (<= threads per CTA)
+constexpr int TILE_TMAX = 192; // cells per tile (= threads per CTA: 6 warps)
 constexpr int TILE_EXT1 = 256; // tile + ring 1
 constexpr int TILE_EXT2 = 320; // tile + rings 1, 2   (ProdTileBC: 110.8 KB of shared memory -> 2 CTAs per SM)
 
@@ -184,7 +184,7 @@ template <int NF, int FEAT>
 struct ProdTileBC
 {
     static constexpr int THREADS = TILE_TMAX;
-    static constexpr int MAXREG = 144; // 2 CTAs x 7 warps x 144 registers = 63 K of the SM's 64 K
+    static constexpr int MAXREG = 168; // 2 CTAs x 6 warps x 168 registers = 63 K of the SM's 64 K
     static constexpr int PHASES = 3;
     static constexpr int SM_DOUBLES = TAccBC::SM_DOUBLES;
     MeshView m;

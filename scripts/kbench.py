@@ -10,10 +10,11 @@ from dafoam_b200.pyDASolvers import pyDASolvers
 libs = sys.argv[1:] or [None]
 cells = int(os.environ.get("KB_CELLS", "980000"))
 nk = int(os.environ.get("KB_NK", "1"))
-nj = max(8, int(round((cells / nk / 2.0) ** 0.5 / 2.0)) * 2)
+nj = int(os.environ["KB_NJ"]) if os.environ.get("KB_NJ") else max(8, int(round((cells / nk / 2.0) ** 0.5 / 2.0)) * 2)
 tile = os.environ.get("KB_TILE")
 mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=nk, span=1.0 if nk > 1 else 0.1, tile=tuple(int(v) for v in tile.split("x")) if tile else None,
-                            family_major=bool(int(os.environ.get("KB_FAMILY", "0"))))
+                            family_major=bool(int(os.environ.get("KB_FAMILY", "0"))),
+                            bface_by_owner=bool(int(os.environ["KB_BFO"])) if os.environ.get("KB_BFO") else None)
 d = tempfile.mkdtemp(prefix="dab_kb_")
 cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
 for lib in libs:
