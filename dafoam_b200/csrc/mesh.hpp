@@ -253,8 +253,10 @@ struct HostMesh
                 st.push_back({mid + 1, r.hi, r.depth + 1});
             }
         }
+        // the queries are independent: host threads (the set-up of a 10M-cell mesh is otherwise minutes of one core)
+        detail::parallelFor(nC, detail::hostThreads(), [&](int, int cb, int ce) {
         std::vector<Range> stack;
-        for (int c = 0; c < nC; c++)
+        for (int c = cb; c < ce; c++)
         {
             const double q[3] = {C[0][c], C[1][c], C[2][c]};
             double best = 1e300;
@@ -278,6 +280,7 @@ struct HostMesh
             }
             yWall[c] = std::sqrt(best);
         }
+        });
     }
     // Mesh quality report of DACheckMesh::run (reference src/adjoint/DACheckMesh/DACheckMesh.C:45-79, DACheckGeometry.C:256-478;
     // OpenFOAM primitiveMeshCheck semantics): the checks that count as failures there - open boundary, open cells /

@@ -144,7 +144,8 @@ DAB_HD void revACell(const Acc& A, const Params& q, int c)
 {
     const double Uc[3] = {A.U(c, 0), A.U(c, 1), A.U(c, 2)};
     const double V = A.V(c);
-    const double psiPc = A.xp(c) * (q.nrP ? 1.0 / V : 1.0);
+    const double rV = frcp(V);
+    const double psiPc = A.xp(c) * (q.nrP ? rV : 1.0);
     double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0};
     double refb[3] = {0, 0, 0};
     const double pc = A.p(c), rAUc = A.rAU(c);
@@ -155,24 +156,29 @@ DAB_HD void revACell(const Acc& A, const Params& q, int c)
         const FaceRef fr = DAB_ACC_FACE(NF, k);
         if (fr.f < 0) break;
         const int f = fr.f;
-        const double mS = A.magSf(f), dl = A.delta(f);
-        const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
-        double Sv[3];
+        // ---- load block: everything either branch reads, issued back to back with no control flow in between (a boundary face
+        // "neighbour" is the cell itself: valid addresses, values unused).  The kernels are latency-bound; what limits them is
+        // how many loads a thread has in flight, and a branch (or the slow-path CALL of an fp64 division) ends the region the
+        // scheduler can batch loads in.
+        const int n = fr.bnd ? c : fr.n;
+        const double mS = A.magSf(f), dl = A.delta(f), xphif = A.xphi(f), w = A.w(f);
+        double Sv[3], kv[3];
         A.Sf(f, Sv);
+        A.kv(f, kv);
+        const double xpn = A.xp(n), Vn = A.V(n), pn = A.p(n), rAUn = A.rAU(n);
+        const double gPn[3] = {A.gP(n, 0), A.gP(n, 1), A.gP(n, 2)};
+        const double rmS = frcp(mS);
+        const double cphi = q.nrPhi ? rmS : 1.0;
         if (!fr.bnd)
         {
-            const int n = fr.n;
-            const double psiPn = A.xp(n) * (q.nrP ? 1.0 / A.V(n) : 1.0);
+            const double psiPn = xpn * (q.nrP ? frcp(Vn) : 1.0);
             // F_f enters pRes_own with -1, pRes_nei with +1, phiRes_f with +1
-            const double Fb = cphi * A.xphi(f) - fr.s * (psiPc - psiPn);
-            const double w = A.w(f);
+            const double Fb = cphi * xphif - fr.s * (psiPc - psiPn);
             const double wc = fr.s > 0 ? w : 1.0 - w, wn = 1.0 - wc;
-            double kv[3];
-            A.kv(f, kv);
             double cg = 0.0;
-            for (int j = 0; j < 3; j++) cg += kv[j] * (wc * gPc[j] + wn * A.gP(n, j));
-            const double sn = fr.s * dl * (A.p(n) - pc) + cg; // delta*(p_N - p_P) + corr
-            const double gam = wc * rAUc + wn * A.rAU(n);
+            for (int j = 0; j < 3; j++) cg += kv[j] * (wc * gPc[j] + wn * gPn[j]);
+            const double sn = fr.s * dl * (pn - pc) + cg; // delta*(p_N - p_P) + corr
+            const double gam = wc * rAUc + wn * rAUn;
             for (int j = 0; j < 3; j++)
             {
                 HbA[j] += wc * Sv[j] * Fb;
@@ -185,15 +191,14 @@ DAB_HD void revACell(const Acc& A, const Params& q, int c)
         {
             const int pa = A.patch(f);
             const double phib = A.phi(f);
-            const double Fb = cphi * A.xphi(f) - psiPc;
+            const double Fb = cphi * xphif - psiPc;
             const int kU = q.bcKind[F_U][pa];
             const bool assignable = (kU == BC_INLET_OUTLET || kU == BC_OUTLET_INLET || kU == BC_ZERO_GRADIENT);
             if (A.m.mrfType && A.m.mrfType[f - A.nIF()] == 1)
                 ; // rotating wall of the MRF zone: the relative phiHbyA is identically zero
             else if (q.constrainHbyA && !assignable)
             {
-                const double im = 1.0 / mS;
-                const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+                const double nh[3] = {Sv[0] * rmS, Sv[1] * rmS, Sv[2] * rmS};
                 const double valb[3] = {Sv[0] * Fb, Sv[1] * Fb, Sv[2] * Fb};
                 const double sngb[3] = {0.0, 0.0, 0.0};
                 bcVectorAdj(kU, phib, dl, nh, valb, sngb, Ub);
@@ -210,18 +215,19 @@ DAB_HD void revACell(const Acc& A, const Params& q, int c)
     }
     // cell-level adjoint of the momentum row: URes = cU*(M + grad p), HbyA = U - rAU*M, rAU = V/(Dn + icAvg)
     const double rAU = rAUc;
+    const double rrAU = frcp(rAU);
     const double cU = q.nrU ? 1.0 : V;
     const double D0 = A.D0(c);
     double rAUtot = rAUb;
     double Mbv[3], Ud[3];
     for (int j = 0; j < 3; j++)
     {
-        const double M = (Uc[j] - A.HbyA(c, j)) / rAU;
+        const double M = (Uc[j] - A.HbyA(c, j)) * rrAU;
         const double psiU = cU * A.xU(c, j);
         const double Mb = psiU - rAU * HbA[j];
         Mbv[j] = Mb;
         rAUtot -= M * HbA[j];
-        const double mt = Mb / V;
+        const double mt = Mb * rV;
         A.setMt(c, j, mt);
         Ud[j] = Ub[j] + HbA[j] + D0 * mt;
         A.setGPb(c, j, gPb[j] + psiU);
@@ -235,7 +241,7 @@ DAB_HD void revACell(const Acc& A, const Params& q, int c)
         Ud[2] += Mbv[0] * w[1] - Mbv[1] * w[0];
     }
     for (int j = 0; j < 3; j++) A.setUdir(c, j, Ud[j]);
-    A.setDn(c, -rAU * rAU * rAUtot / V);
+    A.setDn(c, -rAU * rAU * rAUtot * rV);
     A.setPdir(c, pb);
     if (A.bcRefAny())
         for (int j = 0; j < 3; j++) A.setBcRef(c, j, refb[j]);
@@ -571,7 +577,7 @@ struct RevB
 template <int NF, class Acc>
 DAB_HD void revCCell(const Acc& A, const Params& q, int c, int functionMode)
 {
-    const double iVc = 1.0 / A.V(c);
+    const double iVc = frcp(A.V(c));
     double Ub[3], pb = A.pdir(c), nb = 0.0;
     for (int j = 0; j < 3; j++) Ub[j] = A.Udir(c, j) + A.U2(c, j);
     double gUbc[9], gPbc[3], gNbc[3];
@@ -589,26 +595,34 @@ DAB_HD void revCCell(const Acc& A, const Params& q, int c, int functionMode)
         const FaceRef fr = DAB_ACC_FACE(NF, k);
         if (fr.f < 0) break;
         const int f = fr.f;
+        // load block (see revACell): the neighbour's gradient adjoints of an internal face, the cell's own for a boundary face
+        const int n = fr.bnd ? c : fr.n;
         double Sv[3];
         A.Sf(f, Sv);
+        const double wf = A.w(f), Vn = A.V(n);
+        double gUbn[9], gPbn[3], gNbn[3];
+        for (int i = 0; i < 9; i++) gUbn[i] = A.gUb(n, i);
+        for (int i = 0; i < 3; i++)
+        {
+            gPbn[i] = A.gPb(n, i);
+            gNbn[i] = q.turb ? A.gNtb(n, i) : 0.0;
+        }
         const double So[3] = {fr.s * Sv[0], fr.s * Sv[1], fr.s * Sv[2]}; // outward
         if (!fr.bnd)
         {
-            const int n = fr.n;
-            const double wf = A.w(f);
             const double wc = fr.s > 0 ? wf : 1.0 - wf;
-            const double iVn = 1.0 / A.V(n);
+            const double iVn = frcp(Vn);
             for (int j = 0; j < 3; j++)
             {
                 double t = 0.0;
-                for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - A.gUb(n, j * 3 + i) * iVn);
+                for (int i = 0; i < 3; i++) t += So[i] * (gUbc[j * 3 + i] - gUbn[j * 3 + i] * iVn);
                 Ub[j] += wc * t;
             }
             double tp = 0.0, tn = 0.0;
             for (int i = 0; i < 3; i++)
             {
-                tp += So[i] * (gPbc[i] - A.gPb(n, i) * iVn);
-                if (q.turb) tn += So[i] * (gNbc[i] - A.gNtb(n, i) * iVn);
+                tp += So[i] * (gPbc[i] - gPbn[i] * iVn);
+                if (q.turb) tn += So[i] * (gNbc[i] - gNbn[i] * iVn);
             }
             pb += wc * tp;
             nb += wc * tn;
@@ -617,7 +631,7 @@ DAB_HD void revCCell(const Acc& A, const Params& q, int c, int functionMode)
         {
             const int pa = A.patch(f);
             const double phib = A.phi(f), dl = A.delta(f);
-            const double im = 1.0 / A.magSf(f);
+            const double im = frcp(A.magSf(f));
             const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
             double valb[3];
             const double sngb[3] = {0.0, 0.0, 0.0};

@@ -22,6 +22,7 @@
 #include "comp_primal_kernels.hpp"
 #include "partition.hpp"
 #include "comm.hpp"
+#include <chrono>
 #include <cstdlib>
 #include <cstdio>
 #include <fstream>
@@ -291,11 +292,21 @@ struct Solver
         if (solverName != "DASimpleFoam" && solverName != "DARhoSimpleFoam" && solverName != "DATurboFoam" && solverName != "DARhoSimpleCFoam")
             throw Error("solver " + solverName + " is not supported (DASimpleFoam, DARhoSimpleFoam, DARhoSimpleCFoam, DATurboFoam)");
         be.init(device);
+        auto tPrev = std::chrono::steady_clock::now();
+        const bool setupInfo = getenv("DAB_SETUP_INFO") != nullptr;
+        auto lap = [&](const char* what) {
+            const auto now = std::chrono::steady_clock::now();
+            if (setupInfo) fprintf(stderr, "[dab200] setup %-28s %.3f s (rank %d)\n", what, std::chrono::duration<double>(now - tPrev).count(), rank);
+            tPrev = now;
+        };
         if (nRanks == 1)
         {
             hm.read(caseDir);
+            lap("read polyMesh");
             hm.computeGeometry();
+            lap("geometry");
             hm.computeWallDistance();
+            lap("wall distance");
             part.nGlobalCells = hm.nC;
         }
         else
@@ -303,13 +314,19 @@ struct Solver
             // every rank reads the whole case, partitions it identically (RCB) and keeps its own sub-mesh
             HostMesh g;
             g.read(caseDir);
+            lap("read polyMesh (global)");
             g.computeGeometry();
+            lap("geometry (global)");
             g.computeWallDistance();
+            lap("wall distance (global)");
             std::vector<int> cellPart;
             rcbPartition(g, nRanks, cellPart);
+            lap("RCB partition");
             extractLocalMesh(g, cellPart, rank, nRanks, hm, part);
+            lap("local sub-mesh");
             comm.initNccl(be, rank, nRanks, ncclUid);
             halo.build(be, comm, part.halo);
+            lap("NCCL + halo plans");
         }
         if ((int)hm.patches.size() > MAXP) throw Error("too many patches");
         readCase(caseDir);
@@ -319,9 +336,12 @@ struct Solver
                 if (mrf.type[b] == 1 && par.bcKind[F_U][hm.bPatch[b]] != BC_FIXED_VALUE)
                     throw Error("MRF: patch " + hm.patches[hm.bPatch[b]].name
                                 + " rotates with the zone and needs a fixedValue U (list it in nonRotatingPatches otherwise)");
+        lap("dictionaries");
         applyOptions(optionsJson, true);
         upload();
+        lap("upload + tile/prefetch maps");
         initialStates(caseDir);
+        lap("initial states");
     }
 
     static int bcKindOf(const std::string& t, const std::string& where)

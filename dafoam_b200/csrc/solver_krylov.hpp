@@ -86,36 +86,6 @@ struct CellGraph
     }
 };
 
-// host threads for the set-up loops whose iterations are independent (DAB_HOST_THREADS overrides; default: the hardware
-// concurrency, at most 64).  fn(threadIndex, begin, end); exceptions are re-thrown on the calling thread.
-inline int hostThreads()
-{
-    if (const char* e = getenv("DAB_HOST_THREADS")) return std::max(1, atoi(e));
-    const unsigned h = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(h ? h : 1u, 64u));
-}
-template <class Fn>
-void parallelFor(int n, int nThreads, Fn fn)
-{
-    nThreads = std::max(1, std::min(nThreads, n / 4096 + 1));
-    if (nThreads == 1)
-    {
-        fn(0, 0, n);
-        return;
-    }
-    std::vector<std::thread> th;
-    std::vector<std::string> err(nThreads);
-    for (int t = 0; t < nThreads; t++)
-        th.emplace_back([&, t]() {
-            const int b = (int)((int64_t)n * t / nThreads), e = (int)((int64_t)n * (t + 1) / nThreads);
-            try { fn(t, b, e); }
-            catch (const std::exception& ex) { err[t] = ex.what(); if (err[t].empty()) err[t] = "error"; }
-        });
-    for (auto& x : th) x.join();
-    for (auto& m : err)
-        if (!m.empty()) throw Error(m);
-}
-
 // greedy colouring: item i conflicts with the items listed by neighbours(i, out)
 template <class NbrFn>
 int greedyColour(int n, NbrFn nbr, std::vector<int>& colour)

@@ -13,6 +13,23 @@
 namespace dab
 {
 
+// Reciprocal without the slow-path branch of an IEEE fp64 division.  `a / b` compiles to MUFU.RCP64H + Newton steps + a
+// conditional CALL for denormal / huge operands; that branch ends the scheduling region, so the loads of a face stay serialised
+// behind it (the kernels are latency-bound: profiles/r02_latency_analysis.md).  For the operands it is used on (cell volumes,
+// face areas: normal, positive) two Newton steps on rcp.approx give the correctly rounded result to within 1 ulp.
+DAB_HD double frcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
 constexpr int MAXP = 16; // max patches per rank
 enum { F_U = 0, F_P = 1, F_NUTILDA = 2, F_NUT = 3, N_FIELDS = 4 };
 enum { BC_FIXED_VALUE = 0, BC_ZERO_GRADIENT = 1, BC_INLET_OUTLET = 2, BC_OUTLET_INLET = 3, BC_SYMMETRY = 4, BC_CALCULATED = 5, BC_NUT_LOW_RE = 6, BC_NUT_SPALDING = 7 };

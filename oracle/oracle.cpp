@@ -1830,6 +1830,22 @@ void orc_residual(void* h, const double* W, int isPC, double* R)
     std::copy(r.begin(), r.end(), R);
 }
 
+// J v by forward-mode dual numbers (one tangent direction): the exact counterpart of orc_jtvec, used by the tests to check the
+// tape to rounding instead of to finite-difference accuracy
+void orc_jvec(void* h, const double* W, const double* v, int isPC, double* out)
+{
+    Case* cs = (Case*)h;
+    const int n = cs->nDof();
+    std::vector<Dual> w(n), r;
+    for (int i = 0; i < n; i++) w[i] = Dual(W[i], v[i]);
+    Geom<Dual> g;
+    std::vector<V3<Dual>> P(cs->t.nP);
+    for (int i = 0; i < cs->t.nP; i++) P[i] = V3<Dual>(Dual(cs->pts[3 * i]), Dual(cs->pts[3 * i + 1]), Dual(cs->pts[3 * i + 2]));
+    computeGeometry(cs->t, P, g);
+    residual<Dual>(*cs, g, w, isPC, r);
+    for (int i = 0; i < n; i++) out[i] = r[i].d;
+}
+
 // state scaling of a product vector: DASolver::normalizeGradientVec (DASolver.C:2356-2455)
 static void scaleStates(const Case* cs, double* y)
 {

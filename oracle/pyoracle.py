@@ -147,6 +147,12 @@ class Oracle:
         W = np.ascontiguousarray(W, dtype=np.float64)
         return lib().orc_record(self.h, _p(W), C.c_int(isPC))
 
+    def jvec(self, W, v, isPC=0):
+        """J v by forward-mode dual numbers (exact tangent; the independent check of the tape)."""
+        out = np.zeros(self.ndof)
+        lib().orc_jvec(self.h, _p(np.ascontiguousarray(W, dtype=np.float64)), _p(np.ascontiguousarray(v, dtype=np.float64)), C.c_int(isPC), _p(out))
+        return out
+
     def jtvec(self, psi, normalize=True):
         psi = np.ascontiguousarray(psi, dtype=np.float64)
         out = np.zeros(self.ndof)

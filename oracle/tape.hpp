@@ -131,4 +131,57 @@ inline double pow(double a, double e) { return std::pow(a, e); }
 inline double max(double a, double b) { return a > b ? a : b; }
 inline double min(double a, double b) { return a < b ? a : b; }
 
+// ---- forward-mode dual number (tangent of ONE direction): the independent check of the reverse tape.  psi^T (J v) from the
+// dual instantiation of the residual must equal v^T (J^T psi) from the tape to rounding (1e-12), where central finite differences
+// only give 1e-7 (tests/test_oracle.py).  Same conventions as the tape for the non-smooth intrinsics (active branch; sqrt'(0) = 0).
+struct Dual
+{
+    double v, d;
+    Dual() : v(0.0), d(0.0) {}
+    Dual(double x) : v(x), d(0.0) {}
+    Dual(double x, double t) : v(x), d(t) {}
+};
+inline double val(const Dual& x) { return x.v; }
+inline Dual operator+(const Dual& a, const Dual& b) { return Dual(a.v + b.v, a.d + b.d); }
+inline Dual operator-(const Dual& a, const Dual& b) { return Dual(a.v - b.v, a.d - b.d); }
+inline Dual operator*(const Dual& a, const Dual& b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+inline Dual operator/(const Dual& a, const Dual& b) { return Dual(a.v / b.v, a.d / b.v - a.v * b.d / (b.v * b.v)); }
+inline Dual operator+(const Dual& a, double b) { return Dual(a.v + b, a.d); }
+inline Dual operator-(const Dual& a, double b) { return Dual(a.v - b, a.d); }
+inline Dual operator*(const Dual& a, double b) { return Dual(a.v * b, a.d * b); }
+inline Dual operator/(const Dual& a, double b) { return Dual(a.v / b, a.d / b); }
+inline Dual operator+(double a, const Dual& b) { return Dual(a + b.v, b.d); }
+inline Dual operator-(double a, const Dual& b) { return Dual(a - b.v, -b.d); }
+inline Dual operator*(double a, const Dual& b) { return Dual(a * b.v, a * b.d); }
+inline Dual operator/(double a, const Dual& b) { return Dual(a / b.v, -a * b.d / (b.v * b.v)); }
+inline Dual operator-(const Dual& a) { return Dual(-a.v, -a.d); }
+inline Dual& operator+=(Dual& a, const Dual& b) { a = a + b; return a; }
+inline Dual& operator-=(Dual& a, const Dual& b) { a = a - b; return a; }
+inline Dual& operator*=(Dual& a, const Dual& b) { a = a * b; return a; }
+inline Dual& operator/=(Dual& a, const Dual& b) { a = a / b; return a; }
+inline Dual& operator+=(Dual& a, double b) { a = a + b; return a; }
+inline Dual& operator-=(Dual& a, double b) { a = a - b; return a; }
+inline Dual& operator*=(Dual& a, double b) { a = a * b; return a; }
+inline Dual& operator/=(Dual& a, double b) { a = a / b; return a; }
+inline Dual sqrt(const Dual& a)
+{
+    const double r = std::sqrt(a.v);
+    return Dual(r, r != 0.0 ? 0.5 / r * a.d : 0.0);
+}
+inline Dual fabs(const Dual& a) { return Dual(std::fabs(a.v), a.v < 0.0 ? -a.d : a.d); }
+inline Dual pow(const Dual& a, double e)
+{
+    const double r = std::pow(a.v, e);
+    return Dual(r, a.v != 0.0 ? e * r / a.v * a.d : 0.0);
+}
+inline Dual exp(const Dual& a)
+{
+    const double r = std::exp(a.v);
+    return Dual(r, r * a.d);
+}
+inline Dual max(const Dual& a, const Dual& b) { return a.v > b.v ? a : b; }
+inline Dual min(const Dual& a, const Dual& b) { return a.v < b.v ? a : b; }
+inline Dual max(const Dual& a, double b) { return a.v > b ? a : Dual(b); }
+inline Dual min(const Dual& a, double b) { return a.v < b ? a : Dual(b); }
+
 } // namespace orc
