@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- the adjoint hot path on B200: dRdW^T*psi throughput (GCells/s) and adjoint-solve wall time.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C] [--scaling weak|strong]
 
-A "step" is one matrix-free product y = diag(n) (dR/dW)^T psi over the whole mesh (the body of the
-reference's GMRES shell-matrix callback, DASolver.C:1364-1409).  Workload: BASELINE.json configs[1],
-"DASimpleFoam NACA0012 SA turbulence 1M cells" (synthetic O-grid 1400x700x1 = 980k cells, analytic state
-+ 1 % seeded noise; the reference ships no mesh).  One JSON line on stdout (rank 0).
+A "step" is one matrix-free product y = diag(n) (dR/dW)^T psi over the whole mesh (the body of the reference's GMRES
+shell-matrix callback, DASolver.C:1364-1409).  Workload: BASELINE.json configs[1], "DASimpleFoam NACA0012 SA turbulence
+1M cells": a synthetic O-grid 1440x720x1 = 1 036 800 cells (the reference ships no mesh), tile-major cell numbering
+(16x12 tiles, the order a bandwidth-reducing renumbering leaves), analytic boundary-layer state + 0.1 % seeded noise.
+With N GPUs: weak scaling (default; N x cells, RCB partitions) or strong scaling (--scaling strong; the same mesh).
+The adjoint solve (preconditioner assembly + Krylov solve of [dRdW]^T psi = dFdW) runs at every N.
+One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -23,21 +26,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 NORM_STATES = dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0)
+TILE = (16, 12)  # cells per tile of the generator's tile-major numbering (ni % 16 == 0, nj % 12 == 0)
 
 
 def grid_for(cells):
-    nj = max(8, int(round((cells / 2.0) ** 0.5 / 2.0)) * 2)
-    ni = 2 * nj
-    return ni, nj
-
-
-def smooth_state(sol, mesh, seed=1234, noise=0.001):
-    """Smooth analytic boundary-layer state (+0.1 % seeded noise) -- SURVEY.md section 8d; the reference
-    would supply a converged primal here, which needs the (out-of-scope) primal solver."""
-    from dafoam_b200 import cases
-    y = np.zeros(sol.getNLocalCells())
-    sol.getOFField("yWall", "scalar", y)
-    return cases.boundary_layer_state(mesh, y, seed=seed, noise=noise)
+    """O-grid ni x nj = 2 nj x nj closest to `cells` with nj a multiple of 24 (whole 16x12 tiles)."""
+    nj = max(24, int(round((cells / 2.0) ** 0.5 / 24.0)) * 24)
+    return 2 * nj, nj
 
 
 class ClockSampler:
@@ -82,77 +77,153 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU reference arm: the oracle port of the reference algorithm (tape record once, evaluate per product)
+# CPU arms.  "port": the oracle restatement of the reference's algorithm (tape recorded once, evaluated per product =
+# CoDiPack's tape.evaluate()).  "handcoded": the engine's own hand-derived reverse sweep compiled for the host
+# (tests/hostsim) -- the strong CPU baseline.  One process per usable core, each on a partition-sized O-grid of the same
+# physics: cells_total / P cells per process, as an MPI run of the reference on the bench mesh would have.
 # ---------------------------------------------------------------------------------------------------
 _WORKER = r"""
 import sys, time, json
 sys.path.insert(0, %(root)r)
 import numpy as np
 from dafoam_b200 import cases
-from oracle.pyoracle import Oracle, synthetic_state
-ni, nj, reps = %(ni)d, %(nj)d, %(reps)d
+ni, nj, engine = %(ni)d, %(nj)d, %(engine)r
 m = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1)
-o = Oracle(m, cases.default_bcs_naca(), normalizeStates=%(ns)r)
-W = synthetic_state(m, o.geometry("C"), o.geometry("Sf"))
-t0 = time.time(); o.record(W); trec = time.time() - t0
-psi = np.random.default_rng(4321).uniform(-1, 1, o.ndof)
-o.jtvec(psi)
-print("READY", flush=True)
-sys.stdin.readline()
-t0 = time.time()
-for _ in range(reps):
-    o.jtvec(psi)
-dt = time.time() - t0
-print(json.dumps(dict(cells=m.n_cells, reps=reps, seconds=dt, record_seconds=trec)), flush=True)
+if engine == "port":
+    from oracle.pyoracle import Oracle, synthetic_state
+    o = Oracle(m, cases.default_bcs_naca(), normalizeStates=%(ns)r)
+    W = synthetic_state(m, o.geometry("C"), o.geometry("Sf"))
+    t0 = time.time(); o.record(W); trec = time.time() - t0
+    psi = np.random.default_rng(4321).uniform(-1, 1, o.ndof)
+    def product(): o.jtvec(psi)
+else:
+    import tempfile
+    from dafoam_b200.pyDASolvers import pyDASolvers
+    from oracle.pyoracle import synthetic_state
+    d = tempfile.mkdtemp(prefix="dab_cpu_")
+    cases.write_case(d, m, cases.default_bcs_naca(), binary=True)
+    sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=%(ns)r), caseDir=d, _lib_path=%(hostsim)r)
+    n = sol.getNLocalAdjointStates()
+    yv = np.zeros(m.n_cells); sol.getOFField("yWall", "scalar", yv)
+    W = cases.boundary_layer_state(m, yv, noise=0.001)
+    t0 = time.time(); sol.updateOFFields(W); R = np.zeros(n); sol.getResiduals(R); trec = time.time() - t0
+    psi = np.random.default_rng(4321).uniform(-1, 1, n); y = np.zeros(n)
+    def product(): sol.calcdRdWTPsiAD(psi, y)
+product()
+print("READY %%d %%.4f" %% (m.n_cells, trec), flush=True)
+for line in sys.stdin:
+    reps = int(line.split()[1])
+    t0 = time.time()
+    for _ in range(reps):
+        product()
+    print(json.dumps(dict(seconds=time.time() - t0, reps=reps)), flush=True)
 """
 
 
-def cpu_reference(cores, cells_per_proc=6000, reps=20):
-    """All `cores` host cores, one process per core (the reference runs one MPI rank per core), each
-    evaluating the recorded tape of a `cells_per_proc`-cell partition `reps` times."""
-    ni, nj = grid_for(cells_per_proc)
-    code = _WORKER % dict(root=ROOT, ni=ni, nj=nj, reps=reps, ns=NORM_STATES)
-    procs = [subprocess.Popen([sys.executable, "-c", code], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
-             for _ in range(cores)]
-    for p in procs:
-        assert p.stdout.readline().strip() == "READY"
-    t0 = time.time()
-    for p in procs:
-        p.stdin.write("go\n")
-        p.stdin.flush()
-    res = [json.loads(p.stdout.readline()) for p in procs]
-    wall = time.time() - t0
-    for p in procs:
-        p.wait()
-    cells = sum(r["cells"] for r in res)
-    reps_ = res[0]["reps"]
-    return dict(value=cells * reps_ / wall / 1e9, unit="GCells/s", cores=cores, kind="port",
-                sample="%d processes x %d-cell NACA0012 partition x %d tape evaluations (oracle port of the reference's "
-                       "CoDiPack tape-evaluate matvec; wall %.2f s)" % (cores, res[0]["cells"], reps_, wall),
-                seconds_per_product_per_partition=wall / reps_, tape_record_seconds=res[0]["record_seconds"])
+def usable_cores():
+    """Cores this process may really use: CPU affinity, the cgroup quota, and physical (not hyper-threaded) cores."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    src = "affinity %d" % n
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            quota = max(1, int(float(q[0]) / float(q[1])))
+            if quota < n:
+                n, src = quota, src + ", cgroup quota %d" % quota
+    except Exception:
+        pass
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys and phys < n:
+            n, src = phys, src + ", physical cores %d" % phys
+    except Exception:
+        pass
+    return max(1, n), src
+
+
+class CpuArm:
+    """P persistent worker processes; every run() is one bounded sample: `reps` products on each partition."""
+
+    def __init__(self, cells_total, engine="port", procs=None):
+        self.cores, self.cores_src = usable_cores()
+        self.P = procs or self.cores
+        self.engine = engine
+        nj = max(8, int(round((cells_total / self.P / 2.0) ** 0.5 / 2.0)) * 2)
+        self.ni, self.nj = 2 * nj, nj
+        code = _WORKER % dict(root=ROOT, ni=self.ni, nj=self.nj, engine=engine, ns=NORM_STATES,
+                              hostsim=os.path.join(ROOT, "tests", "hostsim", "libdab200_hostsim.so"))
+        self.procs = [subprocess.Popen([sys.executable, "-c", code], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True)
+                      for _ in range(self.P)]
+        self.cells, self.trec = 0, 0.0
+        for p in self.procs:
+            tok = p.stdout.readline().split()
+            assert tok and tok[0] == "READY", "CPU worker failed to start"
+            self.cells += int(tok[1])
+            self.trec = max(self.trec, float(tok[2]))
+        self.solo = None
+
+    def _go(self, procs, reps):
+        t0 = time.time()
+        for p in procs:
+            p.stdin.write("go %d\n" % reps)
+            p.stdin.flush()
+        res = [json.loads(p.stdout.readline()) for p in procs]
+        return time.time() - t0, res
+
+    def run(self, reps):
+        if self.solo is None:  # one process alone: the undisturbed per-product time
+            _, r = self._go(self.procs[:1], max(2, reps // 2))
+            self.solo = r[0]["seconds"] / r[0]["reps"]
+        wall, res = self._go(self.procs, reps)
+        per = max(r["seconds"] for r in res) / reps
+        slow = per / self.solo if self.solo > 0 else None
+        if slow and slow > 3.0:
+            sys.stderr.write("[bench] WARNING: CPU arm: a product takes %.1fx longer with %d processes running than alone "
+                             "(memory-bound tape / oversubscribed cores)\n" % (slow, self.P))
+        kind = "port" if self.engine == "port" else "port-handcoded"
+        what = ("oracle port of the reference's CoDiPack tape-evaluate matvec" if self.engine == "port"
+                else "the engine's hand-derived reverse sweep compiled for the host (tests/hostsim)")
+        return dict(value=self.cells * reps / wall / 1e9, unit="GCells/s", cores=self.P, kind=kind, cores_source=self.cores_src,
+                    sample="%d processes x %d-cell O-grid partition (%dx%d) x %d products (%s; wall %.2f s)"
+                           % (self.P, self.cells // self.P, self.ni, self.nj, reps, what, wall),
+                    cells_total=self.cells, seconds_per_product=wall / reps, seconds_per_product_one_process_alone=self.solo,
+                    slowdown_all_vs_alone=slow, oversubscribed=bool(slow and slow > 3.0), record_seconds=self.trec)
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.close()
+            except Exception:
+                pass
+        for p in self.procs:
+            p.wait()
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's algorithm for this path on the host cores (oracle port; the reference itself needs
+    OpenFOAM + CoDiPack + PETSc).  Rank 0 only; the other ranks exit without work."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     ni, nj = grid_for(args.cells)
-    steps = max(1, args.steps)
-    t_all = []
-    base = None
-    for i in range(args.warmup + steps):
-        base = cpu_reference(cores, reps=5)
+    arm = CpuArm(ni * nj, "port")
+    reps = 5
+    vals, last = [], None
+    for i in range(args.warmup + max(1, args.steps)):
+        last = arm.run(reps)
         if i >= args.warmup:
-            t_all.append(base["value"])
-        if i >= args.warmup + 2:  # bounded: the CPU arm is slow
+            vals.append(last["value"])
+        if i >= args.warmup + 2:  # bounded: three timed samples
             break
-    v = float(np.mean(t_all))
-    base["value"] = v
+    arm.close()
+    v = float(np.mean(vals))
+    last["value"] = v
     out = {"impl": "reference", "metric": "dRdWTPsi_GCells_per_s", "value": v, "unit": "GCells/s", "n_gpus": args.gpus,
-           "steps": len(t_all), "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": args.solver + " NACA0012 SA %dx%dx1 O-grid (CPU arm: bounded sample of partitions)" % (ni, nj)},
-           "cpu_baseline": base,
+           "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * last["seconds_per_product"], "higher_is_better": True,
+           "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "%s NACA0012 SA %dx%dx1 O-grid, %d cells as %d partitions of %d cells on %d host cores"
+                                  % (args.solver, ni, nj, ni * nj, last["cores"], last["cells_total"] // last["cores"], last["cores"])},
+           "cpu_baseline": last,
            "e2e": {"value": v, "unit": "GCells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
@@ -172,6 +243,27 @@ def emit(obj):
         os.write(_REAL_STDOUT, line)
 
 
+def global_state(mesh, comp, U0c, thermo):
+    """Smooth analytic boundary-layer state (+0.1 % seeded noise) on the global mesh -- SURVEY.md section 8d."""
+    from scipy.spatial import cKDTree
+    from dafoam_b200 import cases
+    Sf, Cf = cases.quad_face_geometry(mesh)
+    wall = [p for p in mesh.patches if p["type"] == "wall"][0]
+    nIF = mesh.n_internal_faces
+    Cc = np.zeros((mesh.n_cells, 3))
+    cnt = np.zeros(mesh.n_cells)
+    np.add.at(Cc, mesh.owner, Cf)
+    np.add.at(cnt, mesh.owner, 1.0)
+    np.add.at(Cc, mesh.neighbour, Cf[:nIF])
+    np.add.at(cnt, mesh.neighbour, 1.0)
+    Cc /= cnt[:, None]
+    yw = cKDTree(Cf[wall["start"]:wall["start"] + wall["size"]]).query(Cc, workers=-1)[0]
+    Wg = cases.boundary_layer_state(mesh, yw, U0=U0c if comp else (10.0, 0.0, 0.0), seed=1234, noise=0.001)
+    if comp:
+        Wg = cases.to_compressible_state(mesh, Wg, thermo)
+    return Wg
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -182,17 +274,21 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cells", type=int, default=980000)
+    ap.add_argument("--cells", type=int, default=1036800)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N x cells (fixed work per GPU, default), strong = the same mesh on every N")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
-    ap.add_argument("--no-idrs", action="store_true", help="skip the IDR(s) leg of the adjoint solve")
-    ap.add_argument("--solve-multi", action="store_true")
+    ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES leg of the adjoint solve (the reference's KSP)")
     ap.add_argument("--restart", type=int, default=1500)
-    ap.add_argument("--pc-level", type=int, default=3)
+    ap.add_argument("--pc-level", type=int, default=2)
+    ap.add_argument("--pc-block", type=int, default=TILE[0] * TILE[1],
+                    help="adjEqnOption.pcBlockCells: block-Jacobi ILU(0) with natural order inside blocks of that many cells (0: multicolour)")
     ap.add_argument("--coarse", type=int, default=1000)
+    ap.add_argument("--idr-s", type=int, default=8)
     ap.add_argument("--max-iters", type=int, default=3000)
     ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam"],
-                    help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000); single GPU")
+                    help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000)")
     ap.add_argument("--primal-iters", type=int, default=0,
                     help="run that many SIMPLE iterations (solvePrimal on the GPU) from the synthetic state before the adjoint legs (1 GPU)")
     args = ap.parse_args()
@@ -212,61 +308,52 @@ def main():
     from dafoam_b200 import cases
     from dafoam_b200.pyDASolvers import pyDASolvers
 
-    # weak scaling: the global mesh has world x args.cells cells and is split into `world` sub-domains (RCB)
-    ni, nj = grid_for(args.cells * world)
+    ni, nj = grid_for(args.cells * (world if args.scaling == "weak" else 1))
     t_setup = time.time()
-    mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1)
-    shared = [None]
     comp = args.solver == "DARhoSimpleFoam"
     U0c = (100.0, 0.0, 0.0)  # M ~ 0.29 at 300 K
     thermo = cases.default_thermo() if comp else None
+    # rank 0 generates the mesh, writes the case (binary polyMesh) and, on several GPUs, the global state; the other ranks
+    # only read: their own engine reads the polyMesh and keeps its partition, the state slice comes from the shared file
+    mesh = None
+    info = [None, None, 0, 0]
     if rank == 0:
-        shared[0] = tempfile.mkdtemp(prefix="dab_bench_")
+        mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1, tile=TILE)
+        case_dir = tempfile.mkdtemp(prefix="dab_bench_")
         if comp:
-            cases.write_case(shared[0], mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c)), binary=True, thermo=thermo)
+            cases.write_case(case_dir, mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c)), binary=True, thermo=thermo)
         else:
-            cases.write_case(shared[0], mesh, cases.default_bcs_naca(), binary=True)
-    uid = None
+            cases.write_case(case_dir, mesh, cases.default_bcs_naca(), binary=True)
+        info = [case_dir, None, mesh.n_cells, mesh.n_faces]
+        if world > 1:
+            from dafoam_b200.pyDASolvers import nccl_unique_id
+            info[1] = nccl_unique_id()
+            np.save(os.path.join(case_dir, "W_global.npy"), global_state(mesh, comp, U0c, thermo))
     if world > 1:
-        from dafoam_b200.pyDASolvers import nccl_unique_id
-        box = [shared[0], nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        shared[0], uid = box
-    case_dir = shared[0]
+        dist.broadcast_object_list(info, src=0)
+    case_dir, uid, n_cells_g, n_faces_g = info
+    t_mesh = time.time() - t_setup
     fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     ns_opt = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else NORM_STATES
+    adj_opt = dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level,
+                   coarseAggregates=args.coarse, pcBlockCells=args.pc_block, tileCells=TILE[0] * TILE[1])
     opts = dict(normalizeStates=ns_opt, function=fn, primalMaxIters=max(args.primal_iters, 1), primalMinResTol=1e-8, printInterval=100,
-                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level, coarseAggregates=args.coarse))
+                adjEqnOption=adj_opt)
     sol = pyDASolvers(args.solver + " -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()
     if world == 1:
+        y_ = np.zeros(nC)
+        sol.getOFField("yWall", "scalar", y_)
+        W = cases.boundary_layer_state(mesh, y_, U0=U0c if comp else (10.0, 0.0, 0.0), seed=1234, noise=0.001)
         if comp:
-            y_ = np.zeros(sol.getNLocalCells())
-            sol.getOFField("yWall", "scalar", y_)
-            W = cases.to_compressible_state(mesh, cases.boundary_layer_state(mesh, y_, U0=U0c, seed=1234, noise=0.001), thermo)
-        else:
-            W = smooth_state(sol, mesh)
+            W = cases.to_compressible_state(mesh, W, thermo)
     else:
-        # global analytic state (wall distance by a KD-tree on the wall-face centres), then this rank's slice
-        from scipy.spatial import cKDTree
-        Sf, Cf = cases.quad_face_geometry(mesh)
-        wall = [p for p in mesh.patches if p["type"] == "wall"][0]
-        nIF = mesh.n_internal_faces
-        Cc = np.zeros((mesh.n_cells, 3))
-        cnt = np.zeros(mesh.n_cells)
-        np.add.at(Cc, mesh.owner, Cf)
-        np.add.at(cnt, mesh.owner, 1.0)
-        np.add.at(Cc, mesh.neighbour, Cf[:nIF])
-        np.add.at(cnt, mesh.neighbour, 1.0)
-        Cc /= cnt[:, None]
-        yw = cKDTree(Cf[wall["start"]:wall["start"] + wall["size"]]).query(Cc)[0]
-        Wg = cases.boundary_layer_state(mesh, yw, U0=U0c if comp else (10.0, 0.0, 0.0), seed=1234, noise=0.001)
-        if comp:
-            Wg = cases.to_compressible_state(mesh, Wg, thermo)
-        W = np.ascontiguousarray(Wg[sol.localStateIndex(mesh.n_cells, mesh.n_faces, compressible=comp)])
+        Wg = np.load(os.path.join(case_dir, "W_global.npy"), mmap_mode="r")
+        W = np.ascontiguousarray(Wg[sol.localStateIndex(n_cells_g, n_faces_g, compressible=comp)])
         del Wg
+    del mesh
     sol.updateOFFields(W)
     t_setup = time.time() - t_setup
     primal = None
@@ -320,45 +407,59 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max = float(tt[0]), float(tt[1])
 
+    # ---- adjoint solve at every N: dRdWTPC assembly + factorisation, then [dRdW]^T psi = dFdW to 1e-6.  Two Krylov legs on the
+    # same preconditioner: IDR(s) (adjEqnOption.kspType idrs, an extension: short recurrences, no orthogonalisation against the whole
+    # basis) and GMRES, the reference's KSP (its restart bounded by the basis that fits next to the preconditioner in HBM)
     adjoint = None
-    if not args.no_solve and (world == 1 or args.solve_multi):
+    if not args.no_solve:
         try:
             from dafoam_b200.pyDASolvers import Mat, KSP
+            barrier()
             t0 = time.perf_counter()
             pc = Mat()
             sol.calcdRdWT(1, pc)
             ksp = KSP()
             sol.createMLRKSPMatrixFree(pc, ksp)
+            barrier()
             t_pc = time.perf_counter() - t0
             dFdW = np.zeros(n)
             sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
-            psi_sol = np.zeros(n)
-            t0 = time.perf_counter()
-            fail = sol.solveLinearEqn(ksp, dFdW, psi_sol)
-            t_solve = time.perf_counter() - t0
-            st = ksp.stats
-            adjoint = {"wall_s": t_pc + t_solve, "pc_s": t_pc, "solve_s": t_solve, "fail": fail, "iterations": st.iterations,
-                       "rel_residual": st.final_residual / st.initial_residual if st.initial_residual else None,
-                       "n_matvec": st.n_matvec, "gmres_device_s": st.solve_seconds, "method": "GMRES(%d), the reference's KSP" % args.restart}
-            # the same system with IDR(s) on the same preconditioner (adjEqnOption.kspType idrs, an extension: short recurrences,
-            # no orthogonalisation against the whole basis); reported beside the GMRES number, never instead of it
-            if not args.no_idrs:
+            adjoint = {"pc_s": t_pc, "tolerance": 1e-6}
+
+            def leg(name, ksp_opts):
+                sol.updateDAOption(dict(adjEqnOption=ksp_opts))
+                x = np.zeros(n)
+                barrier()
+                t1 = time.perf_counter()
+                fail = sol.solveLinearEqn(ksp, dFdW, x)
+                barrier()
+                dt = time.perf_counter() - t1
+                tm = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                st = ksp.stats
+                return x, {"method": name, "wall_s": t_pc + float(tm[0]), "solve_s": float(tm[0]), "fail": fail, "iterations": st.iterations,
+                           "rel_residual": st.final_residual / st.initial_residual if st.initial_residual else None,
+                           "n_matvec": st.n_matvec, "device_s": st.solve_seconds}
+
+            psi_i, adjoint["idrs"] = leg("IDR(%d)" % args.idr_s, dict(kspType="idrs", idrS=args.idr_s, gmresMaxIters=3 * args.max_iters))
+            best = adjoint["idrs"]
+            if not args.no_gmres:
+                free_b = torch.cuda.mem_get_info()[0]
+                m_fit = int(0.8 * free_b / (8.0 * n)) - 8
+                restart = max(30, min(args.restart, m_fit))
                 try:
-                    sol.updateDAOption(dict(adjEqnOption=dict(kspType="idrs", idrS=4, gmresMaxIters=3 * args.max_iters)))
-                    psi2 = np.zeros(n)
-                    t0 = time.perf_counter()
-                    fail2 = sol.solveLinearEqn(ksp, dFdW, psi2)
-                    t2 = time.perf_counter() - t0
-                    st = ksp.stats
-                    dn = float(np.linalg.norm(psi_sol))
-                    adjoint["idrs"] = {"method": "IDR(4)", "wall_s": t_pc + t2, "solve_s": t2, "fail": fail2, "operator_applications": st.iterations,
-                                       "rel_residual": st.final_residual / st.initial_residual if st.initial_residual else None,
-                                       "n_matvec": st.n_matvec, "device_s": st.solve_seconds,
-                                       "psi_rel_diff_vs_gmres": float(np.linalg.norm(psi2 - psi_sol)) / dn if dn > 0 else None}
+                    psi_g, adjoint["gmres"] = leg("GMRES(%d), the reference's KSP" % restart,
+                                                  dict(kspType="gmres", gmresRestart=restart, gmresMaxIters=args.max_iters))
+                    dn = float(np.linalg.norm(psi_g))
+                    adjoint["idrs"]["psi_rel_diff_vs_gmres"] = float(np.linalg.norm(psi_i - psi_g)) / dn if dn > 0 else None
+                    if adjoint["gmres"]["fail"] == 0 and (best["fail"] or adjoint["gmres"]["wall_s"] < best["wall_s"]):
+                        best = adjoint["gmres"]
                 except Exception as e:
-                    adjoint["idrs"] = {"error": str(e)}
-                finally:
-                    sol.updateDAOption(dict(adjEqnOption=dict(kspType="gmres", gmresMaxIters=args.max_iters)))
+                    adjoint["gmres"] = {"error": str(e)}
+            # headline fields = the faster converged leg
+            for k in ("method", "wall_s", "solve_s", "fail", "iterations", "rel_residual", "n_matvec"):
+                adjoint[k] = best[k]
         except Exception as e:  # reported, never hidden
             adjoint = {"error": str(e)}
 
@@ -374,25 +475,25 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     traffic, traffic_src = None, None
-    if comp:
-        args.no_cpu_baseline = True  # the CPU port leg times the incompressible oracle; not comparable
-    tf = os.path.join(ROOT, "profiles", "r01d_ncu_kernels_dram.json")
-    if os.path.exists(tf) and world == 1 and args.cells == 980000 and not comp:
+    tf = os.path.join(ROOT, "profiles", "r02_ncu_kernels_dram.json")
+    if os.path.exists(tf) and world == 1 and not comp:
         tj = json.load(open(tf))
-        traffic = sum(tj[k]["dram__bytes_read.sum"] + tj[k]["dram__bytes_write.sum"] for k in ("RevA", "RevB", "RevC"))
-        traffic_src = "profiles/r01d_ncu_kernels_dram.json (ncu dram__bytes_read+write of RevA+RevB+RevC, same workload)"
+        if tj.get("cells") == n_cells_g:
+            traffic = sum(tj[k]["dram__bytes_read.sum"] + tj[k]["dram__bytes_write.sum"] for k in ("RevA", "RevB", "RevC"))
+            traffic_src = "profiles/r02_ncu_kernels_dram.json (ncu dram__bytes_read+write of RevA+RevB+RevC, same workload, commit %s)" % tj.get("commit")
     alg = sol.algorithmicBytes(0)
     achieved = alg / (ms_max * 1e-3) / 1e9
     nC_global = sol.getNGlobalCells()
     value = nC_global / (ms_max * 1e-3) / 1e9
     out = {
         "metric": "dRdWTPsi_GCells_per_s", "value": value, "unit": "GCells/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "DASimpleFoam NACA0012 SA %dx%dx1 O-grid, %d cells, %d DOF per GPU; adjoint matvec "
-                               "dRdW^T*psi; working set per product ~%.0f MB >> 126 MB L2 (no explicit flush)"
-                               % (ni, nj, nC, n, (alg + 60 * 8 * nC) / 1e6),
-                   "parallelism": ("domain decomposition (RCB) over %d GPUs, NCCL ghost-cell exchange" % world) if world > 1 else "single GPU", "setup_s": t_setup},
+        "config": {"workload": "%s NACA0012 SA %dx%dx1 O-grid (tile-major cell numbering, %dx%d tiles), %d cells global, %d cells / %d DOF "
+                               "on this GPU; adjoint matvec dRdW^T*psi; working set per product ~%.0f MB >> 126 MB L2 (no explicit flush)"
+                               % (args.solver, ni, nj, TILE[0], TILE[1], nC_global, nC, n, (alg + 60 * 8 * nC) / 1e6),
+                   "parallelism": ("domain decomposition (RCB) over %d GPUs, NCCL ghost-cell exchange" % world) if world > 1 else "single GPU",
+                   "setup_s": t_setup, "setup_mesh_generation_s": t_mesh},
         "gpu_launches": launches,
         "e2e": {"value": nC_global / (e2e_ms_max * 1e-3) / 1e9, "unit": "GCells/s", "ms_per_step": e2e_ms_max,
                 "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
@@ -405,11 +506,21 @@ def main():
         "primal_solve": primal,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not comp:
         try:
-            out["cpu_baseline"] = cpu_reference(os.cpu_count() or 1, reps=10)
+            arm = CpuArm(nC_global, "port")
+            out["cpu_baseline"] = arm.run(10)
+            arm.close()
+            # perfectly scaled bound: every core as fast as one process alone (the ratio to quote beside the measured one)
+            cb = out["cpu_baseline"]
+            cb["value_if_perfectly_scaled"] = cb["cells_total"] / cb["seconds_per_product_one_process_alone"] / 1e9
+            arm = CpuArm(nC_global, "handcoded")
+            out["cpu_baseline_handcoded"] = arm.run(10)
+            arm.close()
             # config 1 of BASELINE.json (the reference's own ~5k-cell case on ONE CPU rank): the same port on one core
-            out["cpu_baseline_1core"] = cpu_reference(1, reps=10)
+            arm = CpuArm(5832, "port", procs=1)
+            out["cpu_baseline_1core"] = arm.run(10)
+            arm.close()
         except Exception as e:
             out["cpu_baseline"] = {"error": str(e)}
     emit(out)

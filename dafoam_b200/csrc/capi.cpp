@@ -443,6 +443,29 @@ int dab_get_pc_matrix(dab_solver* s, int64_t* n_rows, int64_t* nnz, int64_t* row
     DAB_CATCH
 }
 
+int dab_calc_pc_mat_fvmatrix(dab_solver* s, int turb_only, int64_t* nnz, int32_t* rows, int32_t* cols, double* vals)
+{
+    DAB_TRY
+    need(s, "solver");
+    need(nnz, "nnz");
+    std::vector<int32_t> r, c;
+    std::vector<double> v;
+    s->s.calcPCMatWithFvMatrix(turb_only, r, c, v);
+    if (!rows)
+    {
+        *nnz = (int64_t)v.size();
+        return 0;
+    }
+    need(cols, "cols");
+    need(vals, "vals");
+    if ((int64_t)v.size() > *nnz) throw Error("dab_calc_pc_mat_fvmatrix: the buffers are too small");
+    *nnz = (int64_t)v.size();
+    std::copy(r.begin(), r.end(), rows);
+    std::copy(c.begin(), c.end(), cols);
+    std::copy(v.begin(), v.end(), vals);
+    DAB_CATCH
+}
+
 int dab_pc_apply(dab_solver* s, const double* v, double* z)
 {
     DAB_TRY

@@ -290,7 +290,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
     const double soc = flc != 0.0 ? 0.0 : D2c;
     const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
     const double psiN = q.turb ? A.xnt(c) : 0.0;
-    const double qc = psiN * (q.nrNut ? 1.0 / V : 1.0); // adjoint of NV
+    const double qc = psiN * (q.nrNut ? frcp(V) : 1.0); // adjoint of NV
     const double zc = psiN * (q.nrNut ? 1.0 : V);       // adjoint of the cell-local SA sources
 
     double U2[3] = {0, 0, 0}, nt2 = 0.0, nuEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
@@ -303,32 +303,38 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
         const FaceRef fr = DAB_ACC_FACE(NF, k);
         if (fr.f < 0) break;
         const int f = fr.f;
-        const double phi = A.phi(f);
-        const double mf = fr.s * phi;
-        double Sv[3];
+        // ---- load block (see revACell): the face's geometry and flux and the neighbour's record, issued with no control flow in
+        // between; a boundary face reads the cell itself in place of a neighbour (valid addresses, values unused)
+        const int n = fr.bnd ? c : fr.n;
+        const double phi = A.phi(f), xphif = A.xphi(f);
+        double Sv[3], kv[3], Cfv[3];
         A.Sf(f, Sv);
-        const double mS = A.magSf(f), dl = A.delta(f);
+        A.kv(f, kv);
+        A.Cf(f, Cfv);
+        const double mS = A.magSf(f), dl = A.delta(f), wf = A.w(f);
+        const double Un[3] = {A.U(n, 0), A.U(n, 1), A.U(n, 2)};
+        const double nutn = A.nut(n), Dnn = A.Dn(n), fln = A.flag(n), Vn = A.V(n);
+        const double mtn[3] = {A.mt(n, 0), A.mt(n, 1), A.mt(n, 2)};
+        const double Cn[3] = {A.C(n, 0), A.C(n, 1), A.C(n, 2)};
+        double gUn[9], gNn[3];
+        for (int i = 0; i < 9; i++) gUn[i] = A.gU(n, i);
+        const double ntn = q.turb ? A.nt(n) : 0.0, xntn = q.turb ? A.xnt(n) : 0.0;
+        for (int i = 0; i < 3; i++) gNn[i] = q.turb ? A.gNt(n, i) : 0.0;
+        const double mf = fr.s * phi;
+        const double rmS = frcp(mS);
         double phib_acc = 0.0; // adjoint of phi_f (only meaningful on the owner side)
         if (!fr.bnd)
         {
-            const int n = fr.n;
-            const double wf = A.w(f);
             const double wc = fr.s > 0 ? wf : 1.0 - wf, wn = 1.0 - wc;
             const bool pos0 = phi >= 0.0;
             const double wupc = fr.s > 0 ? (pos0 ? 1.0 : 0.0) : (pos0 ? 0.0 : 1.0);
-            const double Un[3] = {A.U(n, 0), A.U(n, 1), A.U(n, 2)};
-            const double nuEn = A.nut(n) + q.nu;
-            const double mtn[3] = {A.mt(n, 0), A.mt(n, 1), A.mt(n, 2)};
-            const double Dnn = A.Dn(n), fln = A.flag(n);
+            const double nuEn = nutn + q.nu;
             const double D2n = Dnn * rAl;
             const double D1n = fln != 0.0 ? fln * D2n : 0.0;
             const double son = fln != 0.0 ? 0.0 : D2n;
             const double D0n = D1n + mtn[0] * Un[0] + mtn[1] * Un[1] + mtn[2] * Un[2];
             const bool ownUp = phi > 0.0;
             const bool cUp = fr.s > 0 ? ownUp : !ownUp;
-            double kv[3], Cfv[3];
-            A.kv(f, kv);
-            A.Cf(f, Cfv);
             const double dC[3] = {Cfv[0] - Cc[0], Cfv[1] - Cc[1], Cfv[2] - Cc[2]};
             // ---- momentum rows c and n
             {
@@ -345,8 +351,6 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
                 double gb = abc + abn;   // adjoint of g
                 double gfb = 0.0;        // adjoint of gf (non-orthogonal correction)
                 const double lam[3] = {fr.s * (mtc[0] - mtn[0]), fr.s * (mtc[1] - mtn[1]), fr.s * (mtc[2] - mtn[2])};
-                double gUn[9];
-                for (int i = 0; i < 9; i++) gUn[i] = A.gU(n, i);
                 if (fr.s > 0)
                 {
                     const double mbc = -D0c + offbc + wpc * abc;
@@ -365,7 +369,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
                         {
                             const double* gu = cUp ? gUc : gUn;
                             double d[3];
-                            for (int i = 0; i < 3; i++) d[i] = cUp ? dC[i] : Cfv[i] - A.C(n, i);
+                            for (int i = 0; i < 3; i++) d[i] = cUp ? dC[i] : Cfv[i] - Cn[i];
                             for (int j = 0; j < 3; j++)
                                 phib_acc += (d[0] * gu[j * 3 + 0] + d[1] * gu[j * 3 + 1] + d[2] * gu[j * 3 + 2]) * lam[j];
                         }
@@ -375,7 +379,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
                 {
                     const double* gu = cUp ? gUc : gUn;
                     double d[3];
-                    for (int i = 0; i < 3; i++) d[i] = cUp ? dC[i] : Cfv[i] - A.C(n, i);
+                    for (int i = 0; i < 3; i++) d[i] = cUp ? dC[i] : Cfv[i] - Cn[i];
                     double corr[3], corrL[3], outb[3], corrb[3] = {0, 0, 0};
                     for (int j = 0; j < 3; j++)
                     {
@@ -424,8 +428,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
             // ---- SA rows c and n
             if (q.turb)
             {
-                const double ntn = A.nt(n);
-                const double qn = A.xnt(n) * (q.nrNut ? 1.0 / A.V(n) : 1.0);
+                const double qn = xntn * (q.nrNut ? frcp(Vn) : 1.0);
                 const double wpc = schN == DIV_LINEAR ? wc : wupc;
                 const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
                 const double gf = (wc * Gc + wn * (ntn + q.nu) * rsig) * mS;
@@ -442,12 +445,12 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
                     if (fr.s > 0)
                     {
                         double corr = 0.0;
-                        for (int i = 0; i < 3; i++) corr += (cUp ? dC[i] * gNc[i] : (Cfv[i] - A.C(n, i)) * A.gNt(n, i));
+                        for (int i = 0; i < 3; i++) corr += (cUp ? dC[i] * gNc[i] : (Cfv[i] - Cn[i]) * gNn[i]);
                         phib_acc += corr * lam;
                     }
                 }
                 double cg = 0.0;
-                for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gNc[i] + wn * A.gNt(n, i));
+                for (int i = 0; i < 3; i++) cg += kv[i] * (wc * gNc[i] + wn * gNn[i]);
                 gfb -= cg * lam;
                 const double cgb = -gf * lam;
                 for (int i = 0; i < 3; i++) gNb[i] += wc * kv[i] * cgb;
@@ -457,8 +460,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
         else
         {
             const int pa = A.patch(f);
-            const double im = 1.0 / mS;
-            const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
+            const double nh[3] = {Sv[0] * rmS, Sv[1] * rmS, Sv[2] * rmS};
             const int kU = q.bcKind[F_U][pa];
             BCv bu;
             double uw[3];
@@ -538,7 +540,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
         if (!gradOnly)
         {
             if (fr.s > 0)
-                A.setYPhi(f, (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * A.xphi(f)) * q.sPhi * mS);
+                A.setYPhi(f, (phib_acc - (q.nrPhi ? rmS : 1.0) * xphif) * q.sPhi * mS);
             else if (A.ghost(fr.n))
                 A.setYPhi(f, 0.0); // cut face whose phi belongs to the neighbouring rank
         }

@@ -1200,6 +1200,57 @@ struct Solver
         return pl;
     }
 
+    // DASolver::calcPCMatWithFvMatrix(PCMat, turbOnly = 1) (reference DASolver.C:2888-2988 + DASpalartAllmaras::getFvMatrixFields,
+    // DASpalartAllmaras.C:490-529): the block-diagonal entries dR_nuTilda/d nuTilda taken straight from the relaxed nuTilda fvMatrix
+    // assembled with the `div(pc)` (upwind) convection scheme -- D() on the diagonal, lower()/upper() on the internal faces --
+    // scaled by normalizeStates.nuTilda / (V when nuTildaRes is listed in normalizeResiduals), written TRANSPOSED like the
+    // reference does (MatSetValues(PCMat, col, row)).  Returned as COO triplets in the local state numbering.  The non-turbulence
+    // part (turbOnly = 0) aborts in the reference for the SIMPLE family (DAResidual::calcPCMatWithFvMatrix, DAResidual.C:295-300).
+    void calcPCMatWithFvMatrix(int turbOnly, std::vector<int32_t>& rows, std::vector<int32_t>& cols, std::vector<double>& vals)
+    {
+        if (!turbOnly)
+            throw Error("calcPCMatWithFvMatrix: only turbOnly = 1 is available for " + solverName
+                        + " (the reference's DAResidual::calcPCMatWithFvMatrix aborts for the SIMPLE solver family)");
+        rows.clear(); cols.clear(); vals.clear();
+        if (!par.turb) return;
+        if (par.comp) throw Error("calcPCMatWithFvMatrix: the compressible nuTilda matrix export is not built (DASimpleFoam only)");
+        ensureRecorded();
+        const int nC = hm.nC, nIF = hm.nIF, mcf = hm.maxCF;
+        DevBuf<double> off, diag, b;
+        off.alloc(be, (size_t)mcf * nC);
+        diag.alloc(be, nC);
+        b.alloc(be, nC);
+        EqnView e{nC, mcf, 1, off.p, diag.p, b.p, mv.cellNbr};
+        Params pq = par;
+        pq.divNut = DIV_UPWIND; // "div(pc)"
+        DAB_LAUNCH_NF(nC, NutEqnAssemble, mv, pq, sv, rv, e, primal.alphaN);
+        std::vector<double> hOff((size_t)mcf * nC), hD(nC);
+        be.d2h(hOff.data(), off.p, hOff.size() * sizeof(double));
+        be.d2h(hD.data(), diag.p, hD.size() * sizeof(double));
+        const int base = (par.comp ? 5 : 4) * nC; // local adjoint state index of nuTilda_c (state ordering)
+        auto resScale = [&](int c) { return par.nrNut ? hm.V[c] : 1.0; };
+        for (int c = 0; c < nC; c++)
+        {
+            rows.push_back(base + c);
+            cols.push_back(base + c);
+            vals.push_back(hD[c] * par.sNut / resScale(c));
+        }
+        for (int c = 0; c < nC; c++)
+            for (int k = 0; k < mcf; k++)
+            {
+                const int en = hm.cellFaces[(size_t)k * nC + c];
+                if (en < 0) break;
+                const int f = en >> 1;
+                if (f >= nIF) continue;
+                const int n = hm.cellNbr[(size_t)k * nC + c];
+                if (n < 0 || n >= nC) continue; // cut face: the other cell belongs to another rank
+                // A[c][n] (upper when c owns the face, lower otherwise), stored at the transposed position (row n, column c)
+                rows.push_back(base + n);
+                cols.push_back(base + c);
+                vals.push_back(hOff[(size_t)k * nC + c] * par.sNut / resScale(c));
+            }
+    }
+
     bool tileProduct() const { return tilesOn && av.bcRefb == nullptr; }
     void launchTileA(const PsiView& pv)
     {

@@ -99,10 +99,24 @@ def set_comm_callbacks(exchange, allreduce, lib_path):
 
 
 class Mat:
-    """Stand-in for the PETSc Mat handle of the reference's calcdRdWT(isPC, dRdWT)."""
+    """Stand-in for the PETSc Mat handle of the reference's calcdRdWT(isPC, dRdWT) / calcPCMatWithFvMatrix(PCMat, turbOnly)."""
 
     def __init__(self):
         self.assembled = False
+        self.rows = self.cols = self.vals = None  # COO triplets inserted by calcPCMatWithFvMatrix (INSERT_VALUES)
+
+    def zeroEntries(self):
+        self.rows = self.cols = self.vals = None
+
+    def norm(self):
+        """Frobenius norm (petsc4py Mat.norm() default, as the reference's unit test reads it)."""
+        return 0.0 if self.vals is None else float(np.sqrt(np.sum(self.vals * self.vals)))
+
+    def toDense(self, n):
+        a = np.zeros((n, n))
+        if self.vals is not None:
+            a[self.rows, self.cols] = self.vals
+        return a
 
 
 class KSP:
@@ -528,6 +542,26 @@ class pyDASolvers:
             rp, cl, vl = self.getPCMatrix()
             name = "dRdWTPC.bin" if self._nRanks == 1 else "dRdWTPC_rank%d.bin" % self._rank
             petsc_io.write_mat(os.path.join(self._caseDir, name), rp, cl, vl)
+
+    def calcPCMatWithFvMatrix(self, PCMat, turbOnly=0):
+        """Reference pyDASolvers.pyx calcPCMatWithFvMatrix -> DASolver::calcPCMatWithFvMatrix (DASolver.C:2888-2988): the turbulence
+        block of the preconditioner from the relaxed nuTilda fvMatrix; entries land in PCMat (INSERT_VALUES semantics)."""
+        nnz = C.c_int64()
+        self._raise(self._L.dab_calc_pc_mat_fvmatrix(self._h, C.c_int(int(turbOnly)), C.byref(nnz), None, None, None))
+        rows, cols, vals = np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value)
+        if nnz.value:
+            self._raise(self._L.dab_calc_pc_mat_fvmatrix(self._h, C.c_int(int(turbOnly)), C.byref(nnz), rows.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                         cols.ctypes.data_as(C.POINTER(C.c_int32)), _dp(vals)))
+        if PCMat.vals is None:
+            PCMat.rows, PCMat.cols, PCMat.vals = rows, cols, vals
+        else:  # INSERT_VALUES over what is there: new entries replace old ones at the same position
+            key_old = PCMat.rows.astype(np.int64) << 32 | PCMat.cols.astype(np.int64)
+            key_new = rows.astype(np.int64) << 32 | cols.astype(np.int64)
+            keep = ~np.isin(key_old, key_new)
+            PCMat.rows = np.concatenate([PCMat.rows[keep], rows])
+            PCMat.cols = np.concatenate([PCMat.cols[keep], cols])
+            PCMat.vals = np.concatenate([PCMat.vals[keep], vals])
+        PCMat.assembled = True
 
     def getPCMatrix(self):
         """(row_ptr, cols, vals) of the assembled dRdWTPC (CSR, external numbering); needs "dRdWTPC" in writeJacobians."""

@@ -187,6 +187,13 @@ int dab_run_fp_adj(dab_solver* s, const double* dfdw, double* psi, int* fail, da
  * dab_calc_drdwt_pc, otherwise only the factorisation is kept. */
 int dab_get_pc_matrix(dab_solver* s, int64_t* n_rows, int64_t* nnz, int64_t* row_ptr, int32_t* cols, double* vals);
 
+/* calcPCMatWithFvMatrix(PCMat, turbOnly) (reference pyDASolvers.pyx:99-114 list, DASolver.C:2888-2988): the turbulence block of
+ * the preconditioner taken from the relaxed nuTilda fvMatrix (diag / lower / upper, `div(pc)` convection, DASpalartAllmaras.C:
+ * 490-529), scaled and transposed like the reference, as COO triplets (row, column, value) in the local state numbering -- what the
+ * reference inserts into the PETSc Mat.  rows == NULL: only *nnz is returned.  turb_only == 0 is an error, as in the reference
+ * (DAResidual::calcPCMatWithFvMatrix aborts for the SIMPLE solver family, DAResidual.C:295-300). */
+int dab_calc_pc_mat_fvmatrix(dab_solver* s, int turb_only, int64_t* nnz, int32_t* rows, int32_t* cols, double* vals);
+
 /* setSolverInput(inputName, inputType, inputSize, inputs, seeds): assign an input to the solver's fields before
  * solvePrimal / calcFunction (reference pyDASolvers.pyx:164-182, DASolver::setSolverInput -> DAInput::run;
  * DAInputPatchVelocity.C, DAInputStateVar.C).  Types: "patchVelocity" (|U|, angle of attack [deg]) and "stateVar".

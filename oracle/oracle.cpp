@@ -685,6 +685,10 @@ struct Work
     std::vector<T> muEB; // compressible: rho_b*nuEff_b on the boundary faces
     std::vector<T> rhoB; // compressible: boundary density
     std::vector<T> TB;   // compressible: boundary temperature
+    // capture of the relaxed nuTilda fvMatrix (calcPCMatWithFvMatrix, turbOnly): D(), upper(), lower()
+    bool captureNut = false;
+    double nutAlpha = 0.7;
+    std::vector<T> nutD, nutUpper, nutLower;
 };
 
 // DAFvSourceActuatorDisk::calcFvSource, source = cylinderAnnulusSmooth (reference DAFvSourceActuatorDisk.C:205-407), adjustThrust 0;
@@ -1045,6 +1049,18 @@ void residual(const Case& cs, const Geom<T>& g, const std::vector<T>& W, int isP
             nEqn.diag[c] += g.V[c] * (Cw1 * fw * nt[c] / (cs.yWall[c] * cs.yWall[c]));
         }
         // relax() does not change (M & x) evaluated at x; omitted.
+        if (wk && wk->captureNut)
+        {
+            // DASpalartAllmaras::getFvMatrixFields (DASpalartAllmaras.C:490-529): D(), upper(), lower() of the RELAXED matrix;
+            // fvMatrix::D() = diag + (component-averaged) boundary internalCoeffs
+            Mat<T> mr = nEqn;
+            relax(mr, t, wk->nutAlpha, nt);
+            wk->nutD.assign(nC, T(0.0));
+            for (int c = 0; c < nC; c++) wk->nutD[c] = mr.diag[c];
+            for (int b = 0; b < nBF; b++) wk->nutD[t.own[t.nIF + b]] += mr.ic[b];
+            wk->nutUpper = mr.upper;
+            wk->nutLower = mr.lower;
+        }
         matResidual(nEqn, t, g, nt, ntRes);
         if (!par.nrNut)
             for (int c = 0; c < nC; c++) ntRes[c] *= g.V[c];
@@ -1828,6 +1844,20 @@ void orc_residual(void* h, const double* W, int isPC, double* R)
     std::vector<double> w(W, W + cs->nDof()), r;
     residual<double>(*cs, cs->gd, w, isPC, r);
     std::copy(r.begin(), r.end(), R);
+}
+
+// DASpalartAllmaras::getFvMatrixFields with the `div(pc)` scheme (isPC = 1): D [nC], upper [nIF], lower [nIF] of the relaxed matrix
+void orc_nut_fvmatrix(void* h, const double* W, double alpha, double* D, double* upper, double* lower)
+{
+    Case* cs = (Case*)h;
+    std::vector<double> w(W, W + cs->nDof()), r;
+    Work<double> wk;
+    wk.captureNut = true;
+    wk.nutAlpha = alpha;
+    residual<double>(*cs, cs->gd, w, 1, r, &wk);
+    std::copy(wk.nutD.begin(), wk.nutD.end(), D);
+    std::copy(wk.nutUpper.begin(), wk.nutUpper.end(), upper);
+    std::copy(wk.nutLower.begin(), wk.nutLower.end(), lower);
 }
 
 // J v by forward-mode dual numbers (one tangent direction): the exact counterpart of orc_jtvec, used by the tests to check the

@@ -147,6 +147,12 @@ class Oracle:
         W = np.ascontiguousarray(W, dtype=np.float64)
         return lib().orc_record(self.h, _p(W), C.c_int(isPC))
 
+    def nut_fvmatrix(self, W, alpha=0.7):
+        """(D, upper, lower) of the relaxed nuTilda fvMatrix with the div(pc) scheme (DASpalartAllmaras::getFvMatrixFields)."""
+        D, up, lo = np.zeros(self.ncells), np.zeros(self.mesh.n_internal_faces), np.zeros(self.mesh.n_internal_faces)
+        lib().orc_nut_fvmatrix(self.h, _p(np.ascontiguousarray(W, dtype=np.float64)), C.c_double(alpha), _p(D), _p(up), _p(lo))
+        return D, up, lo
+
     def jvec(self, W, v, isPC=0):
         """J v by forward-mode dual numbers (exact tangent; the independent check of the tape)."""
         out = np.zeros(self.ndof)
