@@ -281,8 +281,8 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES leg of the adjoint solve (the reference's KSP)")
     ap.add_argument("--restart", type=int, default=1500)
-    ap.add_argument("--pc-level", type=int, default=2)
-    ap.add_argument("--pc-block", type=int, default=TILE[0] * TILE[1],
+    ap.add_argument("--pc-level", type=int, default=3)
+    ap.add_argument("--pc-block", type=int, default=0,
                     help="adjEqnOption.pcBlockCells: block-Jacobi ILU(0) with natural order inside blocks of that many cells (0: multicolour)")
     ap.add_argument("--coarse", type=int, default=1000)
     ap.add_argument("--idr-s", type=int, default=8)

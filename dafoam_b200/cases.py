@@ -116,10 +116,14 @@ def _assemble(points, quads, cell_a, cell_b, patch_of_bface, patch_defs, cell_ce
     return PolyMesh(points, faces, owner, neighbour, patches)
 
 
-def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None, family_major=False, bface_by_owner=None):
+def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, tile=None, family_major=False, bface_by_owner=None,
+                   sweep=0.0, taper=1.0):
     """NACA0012 O-grid: ni cells around the airfoil, nj cells radially (geometric stretching
     from `first_dy` chord at the wall to the farfield circle of `radius` chords), nk cells in z.
-    Patches: wing (wall), inout (patch), sym1/sym2 (symmetry)."""
+    Patches: wing (wall), inout (patch), sym1/sym2 (symmetry).
+    sweep / taper (nk > 1): a swept, tapered wing between the two symmetry planes -- the section at span station z is the root
+    section scaled about its leading edge by 1 + (taper - 1) z/span and shifted downstream by sweep*z (fully 3-D hexahedra:
+    no face is aligned with a coordinate plane except the symmetry planes).  tile may be (ti, tj) or (ti, tj, tk)."""
     assert ni % 2 == 0
     th = 2.0 * np.pi * np.arange(ni) / ni
     xa = 0.5 * (1.0 + np.cos(th))
@@ -153,8 +157,11 @@ def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, 
     npl = ni * (nj + 1)
     points = np.empty(((nk + 1) * npl, 3))
     for k in range(nk + 1):
-        points[k * npl:(k + 1) * npl, 0] = X.ravel()
-        points[k * npl:(k + 1) * npl, 1] = Y.ravel()
+        sc = 1.0 + (taper - 1.0) * z[k] / span
+        # the far field stays the root's circle: only the near-wall part of the grid follows the local chord
+        blend = (1.0 - s)[:, None] if (taper != 1.0 or sweep != 0.0) else 0.0
+        points[k * npl:(k + 1) * npl, 0] = (X + blend * ((sc - 1.0) * X + sweep * z[k])).ravel()
+        points[k * npl:(k + 1) * npl, 1] = (Y + blend * (sc - 1.0) * Y).ravel()
         points[k * npl:(k + 1) * npl, 2] = z[k]
 
     def pid(i, j, k):
@@ -167,16 +174,30 @@ def naca0012_ogrid(ni=100, nj=50, nk=1, radius=20.0, span=0.1, first_dy=2.0e-3, 
         cid = cid_lex
     else:
         # tile-major cell numbering (ti x tj cells per tile): neighbouring cells get nearby indices in both directions
-        ti, tj = tile
-        ii, jj = np.meshgrid(np.arange(ni), np.arange(nj), indexing="ij")
-        key = ((jj // tj) * ((ni + ti - 1) // ti) + (ii // ti)) * (ti * tj) + (jj % tj) * ti + (ii % ti)
-        order = np.argsort(key.ravel(), kind="stable")  # positions in lexicographic (i,j) raveled as i*nj + j
-        rank2d = np.empty(ni * nj, dtype=np.int64)
-        rank2d[order] = np.arange(ni * nj)
-        rank2d = rank2d.reshape(ni, nj)
+        ti, tj = tile[0], tile[1]
+        tk = tile[2] if len(tile) > 2 else 1
+        nti, ntj = (ni + ti - 1) // ti, (nj + tj - 1) // tj
+        if tk <= 1:
+            ii, jj = np.meshgrid(np.arange(ni), np.arange(nj), indexing="ij")
+            key = ((jj // tj) * nti + (ii // ti)) * (ti * tj) + (jj % tj) * ti + (ii % ti)
+            order = np.argsort(key.ravel(), kind="stable")  # positions in lexicographic (i,j) raveled as i*nj + j
+            rank2d = np.empty(ni * nj, dtype=np.int64)
+            rank2d[order] = np.arange(ni * nj)
+            rank2d = rank2d.reshape(ni, nj)
 
-        def cid(i, j, k):
-            return rank2d[i % ni, j] + ni * nj * k
+            def cid(i, j, k):
+                return rank2d[i % ni, j] + ni * nj * k
+        else:
+            # 3-D bricks of ti x tj x tk cells, numbered brick by brick, i fastest inside a brick
+            ii, jj, kk = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing="ij")
+            key = (((kk // tk) * ntj + (jj // tj)) * nti + (ii // ti)) * (ti * tj * tk) + ((kk % tk) * tj + (jj % tj)) * ti + (ii % ti)
+            order = np.argsort(key.ravel(), kind="stable")
+            rank3d = np.empty(ni * nj * nk, dtype=np.int64)
+            rank3d[order] = np.arange(ni * nj * nk)
+            rank3d = rank3d.reshape(ni, nj, nk)
+
+            def cid(i, j, k):
+                return rank3d[i % ni, j, k]
 
     I, J, K = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing="ij")
     I, J, K = I.ravel(), J.ravel(), K.ravel()

@@ -41,6 +41,9 @@ namespace dab
 #define DAB_FWDB_MINBLOCKS 3
 #endif
 template <int NF, int FEAT> struct LaunchTraits<RevB<NF, FEAT>> { static constexpr int minBlocks = DAB_REVB_MINBLOCKS; };
+// measured with the hoisted load blocks (profiles/r02_kernel_experiments.md): RevA 96 registers / 5 CTAs per SM, RevC 128 / 4
+template <int NF> struct LaunchTraits<RevA<NF>> { static constexpr int minBlocks = 5; };
+template <int NF> struct LaunchTraits<RevC<NF>> { static constexpr int minBlocks = 4; };
 template <int NF, int FEAT> struct LaunchTraits<FwdB<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 template <int NF, int FEAT> struct LaunchTraits<UEqnAssemble<NF, FEAT>> { static constexpr int minBlocks = DAB_FWDB_MINBLOCKS; };
 template <int NF> struct LaunchTraits<NutEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
@@ -1095,8 +1098,10 @@ struct Solver
     {
         pfOn = false;
 #ifndef DAB_HOSTSIM
+        // measured on B200 (profiles/r02_kernel_experiments.md, #5): 2-17 % SLOWER at every prefetch distance -- the plans stay an
+        // opt-in measurement hook (DAB_PREFETCH_L2=1), not the default
         const char* env = getenv("DAB_PREFETCH_L2");
-        if (env && atoi(env) == 0) return;
+        if (!env || atoi(env) == 0) return;
         const int nC = hm.nC, nIF = hm.nIF;
         for (int f = 1; f < nIF; f++)
             if (hm.own[f] < hm.own[f - 1]) return; // not in upper-triangular order: no plan
@@ -1685,10 +1690,17 @@ struct Solver
         return v;
     }
 
-    // one reverse kernel alone on the bench vectors (dab_bench_device selectors 2-4)
+    // one reverse kernel alone on the bench vectors (dab_bench_device selectors 2-4).  On several ranks the kernel runs over all owned
+    // cells on the ghost values the last full product left behind: no copy, no exchange inside the timed launches
     void benchKernel(int which)
     {
-        const PsiView pv = psiView(dX.p);
+        PsiView pv;
+        if (comm.active() && psiP.n >= (size_t)hm.nCtot)
+        {
+            pv.U = dX.p; pv.p = psiP.p; pv.nt = psiN.p; pv.phi = psiPhi.p; pv.T = psiT.n ? psiT.p : nullptr;
+        }
+        else
+            pv = psiView(dX.p);
         if (par.comp)
         {
             // DARhoSimpleFoam: 0 cRevA, 1 cRevB, 2 cRevE + cRevC
