@@ -29,10 +29,20 @@ NORM_STATES = dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0)
 TILE = (16, 12)  # cells per tile of the generator's tile-major numbering (ni % 16 == 0, nj % 12 == 0)
 
 
+TILE3 = (8, 6, 4)  # bricks of the 3-D wing mesh (BASELINE config 4)
+
+
 def grid_for(cells):
     """O-grid ni x nj = 2 nj x nj closest to `cells` with nj a multiple of 24 (whole 16x12 tiles)."""
     nj = max(24, int(round((cells / 2.0) ** 0.5 / 24.0)) * 24)
     return 2 * nj, nj
+
+
+def grid3_for(cells):
+    """Swept tapered wing (BASELINE config 4): ni x nj x nk = 2 nj x nj x nk hexahedra, nk ~ 1.1 nj, whole 8x6x4 bricks."""
+    nj = max(12, int(round((cells / 2.2) ** (1.0 / 3.0) / 12.0)) * 12)
+    nk = max(4, int(round(cells / (2.0 * nj * nj) / 4.0)) * 4)
+    return 2 * nj, nj, nk
 
 
 class ClockSampler:
@@ -287,6 +297,8 @@ def main():
     ap.add_argument("--coarse", type=int, default=1000)
     ap.add_argument("--idr-s", type=int, default=8)
     ap.add_argument("--max-iters", type=int, default=3000)
+    ap.add_argument("--mesh", default="ogrid2d", choices=["ogrid2d", "wing3d"],
+                    help="wing3d: BASELINE config 4, a swept tapered NACA0012 wing between two symmetry planes, fully 3-D hexahedra (use --cells 5000000 --gpus 4)")
     ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam"],
                     help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000)")
     ap.add_argument("--primal-iters", type=int, default=0,
@@ -308,7 +320,14 @@ def main():
     from dafoam_b200 import cases
     from dafoam_b200.pyDASolvers import pyDASolvers
 
-    ni, nj = grid_for(args.cells * (world if args.scaling == "weak" else 1))
+    ncell_target = args.cells * (world if args.scaling == "weak" else 1)
+    wing = args.mesh == "wing3d"
+    if wing:
+        ni, nj, nk = grid3_for(ncell_target)
+        tile = TILE3
+    else:
+        (ni, nj), nk = grid_for(ncell_target), 1
+        tile = TILE
     t_setup = time.time()
     comp = args.solver == "DARhoSimpleFoam"
     U0c = (100.0, 0.0, 0.0)  # M ~ 0.29 at 300 K
@@ -318,7 +337,10 @@ def main():
     mesh = None
     info = [None, None, 0, 0]
     if rank == 0:
-        mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1, tile=TILE)
+        if wing:
+            mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=nk, span=3.0, sweep=0.5, taper=0.5, radius=15.0, tile=tile)
+        else:
+            mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1, tile=tile)
         case_dir = tempfile.mkdtemp(prefix="dab_bench_")
         if comp:
             cases.write_case(case_dir, mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c)), binary=True, thermo=thermo)
@@ -337,7 +359,7 @@ def main():
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     ns_opt = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else NORM_STATES
     adj_opt = dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level,
-                   coarseAggregates=args.coarse, pcBlockCells=args.pc_block, tileCells=TILE[0] * TILE[1])
+                   coarseAggregates=args.coarse, pcBlockCells=args.pc_block, tileCells=int(np.prod(tile)))
     opts = dict(normalizeStates=ns_opt, function=fn, primalMaxIters=max(args.primal_iters, 1), primalMinResTol=1e-8, printInterval=100,
                 adjEqnOption=adj_opt)
     sol = pyDASolvers(args.solver + " -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
@@ -489,9 +511,10 @@ def main():
         "metric": "dRdWTPsi_GCells_per_s", "value": value, "unit": "GCells/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s NACA0012 SA %dx%dx1 O-grid (tile-major cell numbering, %dx%d tiles), %d cells global, %d cells / %d DOF "
+        "config": {"workload": "%s NACA0012 SA %s %dx%dx%d (tile-major cell numbering, %s tiles), %d cells global, %d cells / %d DOF "
                                "on this GPU; adjoint matvec dRdW^T*psi; working set per product ~%.0f MB >> 126 MB L2 (no explicit flush)"
-                               % (args.solver, ni, nj, TILE[0], TILE[1], nC_global, nC, n, (alg + 60 * 8 * nC) / 1e6),
+                               % (args.solver, "swept tapered wing, 3-D O-grid" if wing else "O-grid", ni, nj, nk, "x".join(str(t) for t in tile),
+                                  nC_global, nC, n, (alg + 60 * 8 * nC) / 1e6),
                    "parallelism": ("domain decomposition (RCB) over %d GPUs, NCCL ghost-cell exchange" % world) if world > 1 else "single GPU",
                    "setup_s": t_setup, "setup_mesh_generation_s": t_mesh},
         "gpu_launches": launches,
@@ -506,7 +529,7 @@ def main():
         "primal_solve": primal,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1 and not comp:
+    if not args.no_cpu_baseline and world == 1 and not comp and not wing:
         try:
             arm = CpuArm(nC_global, "port")
             out["cpu_baseline"] = arm.run(10)

@@ -175,6 +175,84 @@ struct HaloUnpack
     }
 };
 
+// ---- peer-memory ghost exchange (CUDA build, one process per GPU on one NVLink/NVSwitch node) ---------------------------------------
+// Instead of pack -> grouped ncclSend/ncclRecv -> unpack, the pack kernel of the sending rank writes its values STRAIGHT INTO the
+// receiving rank's window over NVLink (the window is cudaMalloc'ed by the receiver and mapped here through CUDA IPC), a one-warp
+// kernel then publishes an epoch flag per peer (system-scope release), and the receiver's unpack kernel spins on its own flags
+// (system-scope acquire) before it scatters the window into the ghost slots: the transfer is part of the producing kernel, no
+// collective call and no NCCL launch latency on the path of a product (4 exchanges per product: 8 launches instead of ~20).
+// Two parities of the window alternate, so a sender may run one exchange ahead of the receiver; every rank issues the same
+// sequence of exchanges (SPMD), which is what makes the epoch counters agree.  NCCL stays for the all-reduces and as the fallback
+// when IPC mapping is not available (DAB_P2P=0 forces it).
+constexpr int P2P_MAXPEER = 32, P2P_CAP = 32, P2P_MAXITEMS = 8;
+struct P2pItems
+{
+    int n, sumComp;
+    double* arr[P2P_MAXITEMS];
+    int cellStride[P2P_MAXITEMS], compStride[P2P_MAXITEMS], ncomp[P2P_MAXITEMS], compBase[P2P_MAXITEMS];
+};
+struct P2pDst
+{
+    double* base[P2P_MAXPEER];      // per peer: start of my segment in the peer's window (this set, this parity)
+    long long* flag[P2P_MAXPEER];   // per peer: my flag slot in the peer's window
+};
+#if !defined(DAB_HOSTSIM)
+struct P2pPack
+{
+    P2pItems it;
+    P2pDst dst;
+    const int32_t *idx, *segOff, *segCnt, *peerOf; // [nSend]
+    int nSend;
+    __device__ void operator()(int t) const
+    {
+        const int kk = t / nSend, j = t - kk * nSend;
+        int a = 0;
+        while (a + 1 < it.n && kk >= it.compBase[a + 1]) a++;
+        const int k = kk - it.compBase[a];
+        const double v = it.arr[a][(int64_t)idx[j] * it.cellStride[a] + (int64_t)k * it.compStride[a]];
+        dst.base[peerOf[j]][(int64_t)kk * segCnt[j] + (j - segOff[j])] = v;
+    }
+};
+__global__ void p2pSignal(P2pDst dst, int nPeers, long long epoch)
+{
+    const int p = (int)threadIdx.x;
+    if (p < nPeers)
+    {
+        __threadfence_system(); // the pack kernel before this one in the stream has completed: publish after its stores
+        *(volatile long long*)dst.flag[p] = epoch;
+        __threadfence_system();
+    }
+}
+struct P2pUnpackArgs
+{
+    P2pItems it;
+    const double* win;           // my window, this set, this parity
+    const long long* flags;      // my flag slots [nPeers]
+    const int32_t *idx, *segOff, *segCnt; // [nRecv]
+    int nRecv, nPeers;
+    long long epoch;
+};
+__global__ void __launch_bounds__(128) p2pUnpack(P2pUnpackArgs a, int n)
+{
+    // every block first waits until all peers have published this epoch (flags live in local memory: cheap to poll)
+    if ((int)threadIdx.x < a.nPeers)
+    {
+        const volatile long long* f = a.flags + threadIdx.x;
+        while (*f < a.epoch) { }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int kk = t / a.nRecv, j = t - kk * a.nRecv;
+    int q = 0;
+    while (q + 1 < a.it.n && kk >= a.it.compBase[q + 1]) q++;
+    const int k = kk - a.it.compBase[q];
+    const double v = a.win[(int64_t)a.segOff[j] * a.it.sumComp + (int64_t)kk * a.segCnt[j] + (j - a.segOff[j])];
+    a.it.arr[q][(int64_t)a.idx[j] * a.it.cellStride[q] + (int64_t)k * a.it.compStride[q]] = v;
+}
+#endif
+
 // one index set (cells or faces) exchanged with every peer
 struct HaloSet
 {
@@ -182,6 +260,8 @@ struct HaloSet
     std::vector<int> sendOffPeer, sendCntPeer, recvOffPeer, recvCntPeer; // per peer
     DevBuf<int32_t> dSendIdx, dSendSegOff, dSendSegCnt, dRecvIdx, dRecvSegOff, dRecvSegCnt;
     DevBuf<double> sendBuf, recvBuf;
+    DevBuf<int32_t> dSendPeer; // [nSend] index of the element's peer
+    long long epoch = 0;       // peer-memory path: exchanges done on this set (parity = epoch & 1)
     int capComp = 0;
 #ifndef DAB_HOSTSIM
     cudaEvent_t evPack = nullptr, evDone = nullptr;
@@ -190,13 +270,14 @@ struct HaloSet
 
     void build(Backend& be, const std::vector<std::vector<int32_t>>& send, const std::vector<std::vector<int32_t>>& recv)
     {
-        std::vector<int32_t> si, so, sc, ri, ro, rc;
+        std::vector<int32_t> si, so, sc, ri, ro, rc, sp;
         for (size_t p = 0; p < send.size(); p++)
         {
             sendOffPeer.push_back((int)si.size());
             sendCntPeer.push_back((int)send[p].size());
             for (int32_t c : send[p])
             {
+                sp.push_back((int32_t)p);
                 si.push_back(c);
                 so.push_back(sendOffPeer.back());
                 sc.push_back((int32_t)send[p].size());
@@ -212,7 +293,7 @@ struct HaloSet
         }
         nSend = (int)si.size();
         nRecv = (int)ri.size();
-        dSendIdx.upload(be, si); dSendSegOff.upload(be, so); dSendSegCnt.upload(be, sc);
+        dSendIdx.upload(be, si); dSendSegOff.upload(be, so); dSendSegCnt.upload(be, sc); dSendPeer.upload(be, sp);
         dRecvIdx.upload(be, ri); dRecvSegOff.upload(be, ro); dRecvSegCnt.upload(be, rc);
     }
     void reserve(Backend& be, int sumComp)
@@ -237,6 +318,163 @@ struct Halo
     std::vector<int> peers;
     HaloSet cells, faces;
     long exchanges = 0;
+    // peer-memory windows (see P2pPack): p2p == false -> NCCL send/recv
+    bool p2p = false;
+    double* win = nullptr;               // my window (cudaMalloc)
+    std::vector<double*> peerWin;        // per peer: the peer's window mapped through CUDA IPC
+    size_t myData[2][2] = {{0, 0}, {0, 0}}, myFlag[2][2] = {{0, 0}, {0, 0}};     // [set][parity] offsets (doubles) in my window
+    std::vector<size_t> peerData[2][2], peerFlag[2][2];                         // the same offsets in each peer's window
+    std::vector<int> peerRecvOff[2];     // [set][peer]: where my segment starts in the peer's receive list
+    std::vector<int> myIdxInPeer;        // my index in the peer's peer list (flag slot)
+
+    static size_t windowLayout(size_t nRecvCells, size_t nRecvFaces, size_t data[2][2], size_t flag[2][2])
+    {
+        size_t off = 0;
+        const size_t nr[2] = {nRecvCells, nRecvFaces};
+        for (int st = 0; st < 2; st++)
+            for (int q = 0; q < 2; q++)
+            {
+                data[st][q] = off;
+                off += nr[st] * P2P_CAP;
+            }
+        for (int st = 0; st < 2; st++)
+            for (int q = 0; q < 2; q++)
+            {
+                flag[st][q] = off;
+                off += P2P_MAXPEER;
+            }
+        return off;
+    }
+
+    void setupP2P()
+    {
+        p2p = false;
+#if !defined(DAB_HOSTSIM) && defined(DAB_WITH_NCCL)
+        if (!comm || !comm->active()) return;
+        if (const char* e = getenv("DAB_P2P"))
+            if (atoi(e) == 0) return;
+        const int nP = (int)peers.size(), R = comm->size, me = comm->rank;
+        // every decision below must be the same on all ranks: problems are summed over the ranks before anybody acts on them
+        double bad = (nP > P2P_MAXPEER) ? 1.0 : 0.0;
+        // 1. table of everybody's receive layout: row r = [nPeers, nRecvCells, nRecvFaces, (peerRank, recvOffCells, recvOffFaces) x nPeers]
+        const int RW = 4 + 3 * P2P_MAXPEER;
+        std::vector<double> tab((size_t)R * RW, 0.0);
+        if (bad == 0.0)
+        {
+            double* row = &tab[(size_t)me * RW];
+            row[0] = nP; row[1] = cells.nRecv; row[2] = faces.nRecv;
+            for (int p = 0; p < nP; p++)
+            {
+                row[4 + 3 * p] = peers[p];
+                row[5 + 3 * p] = cells.recvOffPeer[p];
+                row[6 + 3 * p] = faces.recvOffPeer[p];
+            }
+        }
+        // 2. my window + its IPC handle (one byte per double: exact through a sum with zeros)
+        size_t nW = windowLayout(cells.nRecv, faces.nRecv, myData, myFlag);
+        cudaIpcMemHandle_t hnd;
+        memset(&hnd, 0, sizeof(hnd));
+        if (cudaMalloc((void**)&win, (nW + 2) * sizeof(double)) != cudaSuccess) { bad = 1.0; win = nullptr; cudaGetLastError(); }
+        if (win)
+        {
+            cudaMemset(win, 0, (nW + 2) * sizeof(double));
+            cudaDeviceSynchronize();
+            if (cudaIpcGetMemHandle(&hnd, win) != cudaSuccess) { bad = 1.0; cudaGetLastError(); }
+        }
+        const int HB = (int)sizeof(cudaIpcMemHandle_t);
+        std::vector<double> hv((size_t)R * HB + 1, 0.0);
+        for (int i = 0; i < HB; i++) hv[(size_t)me * HB + i] = (double)((const unsigned char*)&hnd)[i];
+        hv[(size_t)R * HB] = bad;
+        DevBuf<double> dTab, dH;
+        dTab.upload(*be, tab);
+        dH.upload(*be, hv);
+        comm->allreduceSum(*be, dTab.p, (int)tab.size());
+        comm->allreduceSum(*be, dH.p, (int)hv.size());
+        be->d2h(tab.data(), dTab.p, tab.size() * sizeof(double));
+        be->d2h(hv.data(), dH.p, hv.size() * sizeof(double));
+        bool ok = hv[(size_t)R * HB] == 0.0;
+        // 3. map the peers' windows, find my segment in their layout
+        peerWin.assign(nP, nullptr);
+        myIdxInPeer.assign(nP, -1);
+        for (int st = 0; st < 2; st++)
+        {
+            peerRecvOff[st].assign(nP, 0);
+            for (int q = 0; q < 2; q++) { peerData[st][q].assign(nP, 0); peerFlag[st][q].assign(nP, 0); }
+        }
+        double bad2 = 0.0;
+        if (ok)
+            for (int p = 0; p < nP; p++)
+            {
+                const int r = peers[p];
+                const double* row = &tab[(size_t)r * RW];
+                const int rp = (int)row[0];
+                for (int i = 0; i < rp; i++)
+                    if ((int)row[4 + 3 * i] == me)
+                    {
+                        myIdxInPeer[p] = i;
+                        peerRecvOff[0][p] = (int)row[5 + 3 * i];
+                        peerRecvOff[1][p] = (int)row[6 + 3 * i];
+                    }
+                if (myIdxInPeer[p] < 0) bad2 = 1.0;
+                size_t d[2][2], f[2][2];
+                windowLayout((size_t)row[1], (size_t)row[2], d, f);
+                for (int st = 0; st < 2; st++)
+                    for (int q = 0; q < 2; q++) { peerData[st][q][p] = d[st][q]; peerFlag[st][q][p] = f[st][q]; }
+                cudaIpcMemHandle_t ph;
+                for (int i = 0; i < HB; i++) ((unsigned char*)&ph)[i] = (unsigned char)hv[(size_t)r * HB + i];
+                void* mapped = nullptr;
+                if (cudaIpcOpenMemHandle(&mapped, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { bad2 = 1.0; cudaGetLastError(); }
+                peerWin[p] = (double*)mapped;
+            }
+        else
+            bad2 = 1.0;
+        DevBuf<double> dB;
+        std::vector<double> b1(1, bad2);
+        dB.upload(*be, b1);
+        comm->allreduceSum(*be, dB.p, 1);
+        be->d2h(b1.data(), dB.p, sizeof(double));
+        p2p = b1[0] == 0.0;
+        if (getenv("DAB_SETUP_INFO"))
+            fprintf(stderr, "[dab200] halo exchange: %s (rank %d, %d peers)\n", p2p ? "peer-memory windows over NVLink (CUDA IPC)" : "NCCL send/recv", me, nP);
+#endif
+    }
+
+#if !defined(DAB_HOSTSIM) && defined(DAB_WITH_NCCL)
+    // one exchange through the peer windows on the backend's current stream: pack into the peers, publish, wait + unpack
+    void runP2P(HaloSet& hs, int st, const std::vector<HaloItem>& items, int sumComp)
+    {
+        hs.epoch++;
+        const int q = (int)(hs.epoch & 1), nP = (int)peers.size();
+        P2pItems it;
+        it.n = (int)items.size();
+        it.sumComp = sumComp;
+        int base = 0;
+        for (int i = 0; i < it.n; i++)
+        {
+            it.arr[i] = items[i].arr; it.cellStride[i] = items[i].cellStride; it.compStride[i] = items[i].compStride;
+            it.ncomp[i] = items[i].ncomp; it.compBase[i] = base;
+            base += items[i].ncomp;
+        }
+        P2pDst dst;
+        for (int p = 0; p < nP; p++)
+        {
+            dst.base[p] = peerWin[p] + peerData[st][q][p] + (size_t)peerRecvOff[st][p] * sumComp;
+            dst.flag[p] = (long long*)(peerWin[p] + peerFlag[st][q][p]) + myIdxInPeer[p];
+        }
+        if (hs.nSend > 0) be->launch(hs.nSend * sumComp, P2pPack{it, dst, hs.dSendIdx.p, hs.dSendSegOff.p, hs.dSendSegCnt.p, hs.dSendPeer.p, hs.nSend});
+        p2pSignal<<<1, 32, 0, be->stream>>>(dst, nP, hs.epoch);
+        const int n = hs.nRecv * sumComp;
+        if (n > 0)
+        {
+            P2pUnpackArgs a{it, win + myData[st][q], (const long long*)(win + myFlag[st][q]), hs.dRecvIdx.p, hs.dRecvSegOff.p, hs.dRecvSegCnt.p,
+                            hs.nRecv, nP, hs.epoch};
+            p2pUnpack<<<(n + 127) / 128, 128, 0, be->stream>>>(a, n);
+        }
+        DAB_CUDA_CHECK(cudaGetLastError());
+        be->launches += 2;
+    }
+    bool useP2P(const std::vector<HaloItem>& items, int sumComp) const { return p2p && sumComp <= P2P_CAP && (int)items.size() <= P2P_MAXITEMS; }
+#endif
 
     void build(Backend& b, Comm& c, const HaloPlan& plan)
     {
@@ -248,6 +486,7 @@ struct Halo
             for (int i = 0; i < plan.recvCellCount[p]; i++) recvCells[p].push_back(plan.recvCellStart[p] + i);
         cells.build(b, plan.sendCells, recvCells);
         faces.build(b, plan.sendFaces, plan.recvFaces);
+        setupP2P();
     }
 
     void run(HaloSet& hs, const std::vector<HaloItem>& items)
@@ -255,6 +494,14 @@ struct Halo
         if (!comm || !comm->active()) return;
         int sumComp = 0;
         for (const auto& it : items) sumComp += it.ncomp;
+#if !defined(DAB_HOSTSIM) && defined(DAB_WITH_NCCL)
+        if (useP2P(items, sumComp))
+        {
+            runP2P(hs, &hs == &faces ? 1 : 0, items, sumComp);
+            exchanges++;
+            return;
+        }
+#endif
         hs.reserve(*be, sumComp);
         int base = 0;
         for (const auto& it : items)
@@ -301,6 +548,20 @@ struct Halo
         }
         int sumComp = 0;
         for (const auto& it : items) sumComp += it.ncomp;
+        if (useP2P(items, sumComp))
+        {
+            // everything of this exchange goes to the communication stream (after what the compute stream has produced so far): the
+            // interior kernels of the next stage overlap the NVLink stores and the wait for the peers
+            cudaEventRecord(hs.evPack, be->stream);
+            std::swap(be->stream, be->stream2);
+            cudaStreamWaitEvent(be->stream, hs.evPack, 0);
+            runP2P(hs, &hs == &faces ? 1 : 0, items, sumComp);
+            cudaEventRecord(hs.evDone, be->stream);
+            std::swap(be->stream, be->stream2);
+            hs.pending = true;
+            exchanges++;
+            return;
+        }
         hs.reserve(*be, sumComp);
         int base = 0;
         for (const auto& it : items)

@@ -40,6 +40,7 @@ struct EllView
     const int32_t* diag;     // [n] entry index of the diagonal
     const int32_t* col;      // ELL columns (new numbering), -1 padding
     double* val;
+    const float* valF = nullptr; // fp32 copy of the FACTORS (adjEqnOption.pcStorage "fp32"): what the triangular solves read
 };
 
 // one colour of the ordering: `nCells` cells, slot s occupies rows [slotStart[s], slotStart[s]+slotCount[s])
@@ -188,7 +189,10 @@ struct TriLowerColour // y = L^{-1} y (unit lower), in place
             const int64_t bi = A.rowBase[i], si = A.rowStride[i];
             const int di = A.diag[i];
             double acc = y[i];
-            for (int e = 0; e < di; e++) acc -= A.val[bi + e * si] * y[A.col[bi + e * si]];
+            if (A.valF)
+                for (int e = 0; e < di; e++) acc -= (double)A.valF[bi + e * si] * y[A.col[bi + e * si]];
+            else
+                for (int e = 0; e < di; e++) acc -= A.val[bi + e * si] * y[A.col[bi + e * si]];
             y[i] = acc;
         }
     }
@@ -208,10 +212,25 @@ struct TriUpperColour // x = U^{-1} x, in place
             const int64_t bi = A.rowBase[i], si = A.rowStride[i];
             const int di = A.diag[i], len = A.rowLen[i];
             double acc = x[i];
-            for (int e = di + 1; e < len; e++) acc -= A.val[bi + e * si] * x[A.col[bi + e * si]];
-            x[i] = acc / A.val[bi + di * si];
+            if (A.valF)
+            {
+                for (int e = di + 1; e < len; e++) acc -= (double)A.valF[bi + e * si] * x[A.col[bi + e * si]];
+                x[i] = acc / (double)A.valF[bi + di * si];
+            }
+            else
+            {
+                for (int e = di + 1; e < len; e++) acc -= A.val[bi + e * si] * x[A.col[bi + e * si]];
+                x[i] = acc / A.val[bi + di * si];
+            }
         }
     }
+};
+
+struct CvtToFloat // fp32 copy of the factors
+{
+    const double* src;
+    float* dst;
+    DAB_HD void operator()(int i) const { dst[i] = (float)src[i]; }
 };
 
 struct GatherVec // dst[i] = src[idx[i]]
@@ -615,6 +634,8 @@ struct Krylov
     DevBuf<int64_t> dRowBase;
     DevBuf<int32_t> dRowStride, dRowLen, dDiag, dCol;
     DevBuf<double> dVal, dDinv;
+    DevBuf<float> dValF; // fp32 copy of the ILU factors (pcStorage fp32): halves the value traffic of every application
+    bool useF32 = false;
     std::vector<double> hValAssembled; // host copy of the assembled (unfactorised) values when writeJacobians asks for dRdWTPC
     int64_t nnz = 0, ellSize = 0;
     // FD colours
@@ -635,6 +656,7 @@ struct Krylov
         EllView e;
         e.n = n; e.rowBase = dRowBase.p; e.rowStride = dRowStride.p; e.rowLen = dRowLen.p; e.diag = dDiag.p;
         e.col = dCol.p; e.val = dVal.p;
+        e.valF = useF32 && dValF.n ? dValF.p : nullptr;
         return e;
     }
 };

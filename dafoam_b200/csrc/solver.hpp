@@ -200,6 +200,7 @@ struct Solver
     double richardsonOmega = 1.0;
     double gmresRelTol = 1e-6, gmresAbsTol = 1e-14, gmresTolDiff = 1e2, fdStep = 1e-6;
     std::string pcType = "ilu";
+    std::string pcStorage = "fp64"; // adjEqnOption.pcStorage (extension): "fp32" keeps an fp32 copy of the ILU factors for the applications
     int coarseAggregates = 0; // > 0: two-level preconditioner with that many pressure aggregates (global)
     int pcConLevel = 2; // cell-to-cell connectivity level of dRdWTPC (maxResConLv4JacPCMat role)
     std::vector<FunctionDef> functions;
@@ -654,6 +655,11 @@ struct Solver
             pcFillLevel = (int)a->numOr("pcFillLevel", pcFillLevel);
             printInfo = (int)a->numOr("printInfo", printInfo);
             pcType = a->strOr("pcType", pcType);
+            {
+                const std::string ps = a->strOr("pcStorage", pcStorage);
+                if (ps != "fp64" && ps != "fp32") throw Error("adjEqnOption.pcStorage " + ps + ": fp64 or fp32");
+                if (ps != pcStorage) { pcStorage = ps; kry.pcValid = false; }
+            }
             pcSymbolicOnly = (int)a->numOr("pcSymbolicOnly", pcSymbolicOnly);
             fpMaxIters = (int)a->numOr("fpMaxIters", fpMaxIters);
             fpRelTol = a->numOr("fpRelTol", fpRelTol);

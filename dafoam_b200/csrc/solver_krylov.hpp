@@ -461,6 +461,15 @@ inline void Solver::calcPC()
     }
     // ILU(0), one kernel per colour
     for (const ColourView& cv : K.colours) be.launch(cv.nCells, IluFactorColour{A, cv, 1e-10});
+    // adjEqnOption.pcStorage "fp32" (extension): the triangular solves read an fp32 copy of the factors -- the preconditioner is an
+    // approximation anyway, the Krylov operator and all vectors stay fp64; 12 -> 8 bytes per nonzero per application
+    K.useF32 = pcStorage == "fp32";
+    if (K.useF32)
+    {
+        if (K.dValF.n < (size_t)K.ellSize) K.dValF.alloc(be, (size_t)K.ellSize, false);
+        for (int64_t o = 0; o < K.ellSize; o += (int64_t)1 << 30)
+            be.launch((int)std::min<int64_t>((int64_t)1 << 30, K.ellSize - o), CvtToFloat{K.dVal.p + o, K.dValF.p + o});
+    }
     be.sync();
     K.pcValid = true;
     K.pcFactored = true;
@@ -993,16 +1002,32 @@ inline int Solver::solveIdrs(const double* rhs, double* sol, KspStats& st)
                 matVecDev(Uk, Gk);
                 st.nMatvec++;
                 its++;
-                // bi-orthogonalise against P_0..P_{k-1}
-                for (int i = 0; i < k; i++)
+                // bi-orthogonalise against P_0..P_{k-1}.  The textbook loop (alpha_i = p_i.g / mu_ii; g -= alpha_i g_i; u -= alpha_i u_i, one
+                // dot product and host round trip per i) is a forward substitution in disguise: P^T G is lower triangular (= M), so with
+                // d = P^T g taken ONCE from the unmodified g, alpha solves M[0:k,0:k] alpha = d[0:k] and the dots of the updated g with
+                // the remaining shadow vectors are d_i - sum_j alpha_j M_ij.  One multi-dot + two multi-axpys per application instead of
+                // k dots + 2k axpys + k synchronisations; identical in exact arithmetic.
                 {
-                    const double al = K.ops.dots(P + (size_t)i * n, n, 1, Gk, n)[0] / M[(size_t)i * s + i];
-                    be.launch(n, AxpyVec{G + (size_t)i * n, -al, Gk});
-                    be.launch(n, AxpyVec{U + (size_t)i * n, -al, Uk});
-                }
-                {
-                    const double* d = K.ops.dots(P + (size_t)k * n, n, s - k, Gk, n);
-                    for (int i = k; i < s; i++) M[(size_t)i * s + k] = d[i - k];
+                    const double* d = K.ops.dots(P, n, s, Gk, n);
+                    std::vector<double> dd(d, d + s), al(k > 0 ? k : 1, 0.0);
+                    for (int i = 0; i < k; i++)
+                    {
+                        double a = dd[i];
+                        for (int j = 0; j < i; j++) a -= M[(size_t)i * s + j] * al[j];
+                        al[i] = a / M[(size_t)i * s + i];
+                    }
+                    if (k > 0)
+                    {
+                        be.h2d(K.hdev.p, al.data(), (size_t)k * sizeof(double));
+                        be.launch(n, MultiAxpy{G, n, k, K.hdev.p, Gk, 0}); // Gk -= sum_i al_i G_i
+                        be.launch(n, MultiAxpy{U, n, k, K.hdev.p, Uk, 0}); // Uk -= sum_i al_i U_i
+                    }
+                    for (int i = k; i < s; i++)
+                    {
+                        double a = dd[i];
+                        for (int j = 0; j < k; j++) a -= M[(size_t)i * s + j] * al[j];
+                        M[(size_t)i * s + k] = a;
+                    }
                 }
                 const double mkk = M[(size_t)k * s + k];
                 if (!(std::fabs(mkk) > 1e-300) || !std::isfinite(mkk)) { breakdown = true; break; }

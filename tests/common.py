@@ -17,6 +17,8 @@ ALL_RES = ("URes", "pRes", "nuTildaRes", "phiRes")
 def make_mesh(kind, nk=2, scale=1):
     if kind in ("naca", "nacawf"):
         return cases.naca0012_ogrid(ni=40 * scale, nj=20 * scale, nk=nk)
+    if kind == "wing":  # swept tapered 3-D wing section (BASELINE config 4 topology): no face aligned with the axes but the symmetry planes
+        return cases.naca0012_ogrid(ni=16 * scale, nj=8 * scale, nk=max(nk, 3), span=1.5, sweep=0.5, taper=0.5, radius=8.0, tile=(4, 4, 3))
     if kind == "prism":
         return cases.prism_channel(nx=10 * scale, ny=6 * scale)
     return cases.channel(nx=12 * scale, ny=8 * scale, nz=nk)
@@ -25,7 +27,7 @@ def make_mesh(kind, nk=2, scale=1):
 def make_bcs(kind, turbulent):
     if kind == "nacawf":  # nutUSpaldingWallFunction on the wing (useWallFunction True in the reference's NACA0012 cases)
         return cases.default_bcs_naca(turbulent=turbulent, wall_function=True)
-    return cases.default_bcs_naca(turbulent=turbulent) if kind == "naca" else cases.default_bcs_channel(turbulent=turbulent)
+    return cases.default_bcs_naca(turbulent=turbulent) if kind in ("naca", "wing") else cases.default_bcs_channel(turbulent=turbulent)
 
 
 def setup(kind="naca", turbulent=True, divU="linearUpwind", nk=2, nres=ALL_RES, lib_path=None, scale=1, binary=False,
@@ -75,6 +77,7 @@ CONFIGS = [
     ("naca", True, "linearUpwindV", 1, ALL_RES, "SpalartAllmarasFv3"),  # fv3 production term (the reference's compressible tests use it)
     ("channel", True, "linearUpwind", 2, ALL_RES, "SpalartAllmarasFv3"),
     ("prism", True, "linearUpwind", 1, ALL_RES),    # triangular prisms: 5 faces per cell, triangles + quads
+    ("wing", True, "linearUpwindV", 3, ALL_RES),    # swept tapered wing, brick-major numbering: skewed fully 3-D hexahedra
 ]
 
 

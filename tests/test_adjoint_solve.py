@@ -250,3 +250,55 @@ def test_pydafoam_adjoint_method_switch():
     DASolver.setOption("adjEqnSolMethod", "cg")
     with pytest.raises(RuntimeError, match="adjEqnSolMethod"):
         DASolver.solveAdjoint("CD")
+
+
+def _solve_with(sol, W, extra):
+    n = sol.getNLocalAdjointStates()
+    sol.updateDAOption(dict(adjEqnOption=dict(gmresRelTol=1e-9, gmresMaxIters=600, gmresRestart=300, **extra)))
+    dFdW = np.zeros(n)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    psi = np.zeros(n)
+    fail = sol.solveLinearEqn(ksp, dFdW, psi)
+    r = np.zeros(n)
+    sol.calcdRdWTPsiAD(psi, r)
+    assert fail == 0 and np.linalg.norm(r - dFdW) <= 2e-9 * np.linalg.norm(dFdW)
+    return psi, ksp.stats.iterations
+
+
+def test_preconditioner_variants_reach_the_same_adjoint():
+    """Ordering / storage variants of the preconditioner (adjEqnOption.pcBlockCells: block-Jacobi ILU(0) with the natural cell order
+    inside blocks, level-scheduled -- the reference's PCASM overlap 0 + natural-order PCILU; adjEqnOption.pcStorage fp32: fp32 copy
+    of the factors) change the iteration count, never the converged adjoint."""
+    mesh, sol, W = adjoint_case(HOSTSIM, ni=32, nj=16)
+    psi0, it0 = _solve_with(sol, W, dict(pcBlockCells=0, pcStorage="fp64"))
+    for extra in (dict(pcBlockCells=64, pcStorage="fp64"), dict(pcBlockCells=0, pcStorage="fp32"), dict(pcBlockCells=128, pcStorage="fp32")):
+        psi, it = _solve_with(sol, W, extra)
+        assert np.linalg.norm(psi - psi0) <= 1e-6 * np.linalg.norm(psi0), extra
+        assert it < 600
+    with pytest.raises(Exception):
+        sol.updateDAOption(dict(adjEqnOption=dict(pcStorage="fp16")))
+
+
+def test_fixed_point_then_gmres_on_the_same_handle():
+    """runFPAdj re-initialised the dot-product workspace to 34 vectors; a later GMRES with more than 34 iterations on
+    the same handle then wrote past it.  The workspace now only grows."""
+    mesh, sol, W = adjoint_case(HOSTSIM, ni=32, nj=16, restart=300, maxit=600)
+    n = sol.getNLocalAdjointStates()
+    dFdW = np.zeros(n)
+    sol.calcJacTVecProduct("states", "stateVar", W, "CD", "function", np.array([1.0]), dFdW)
+    psi_fp = np.zeros(n)
+    sol.updateDAOption(dict(adjEqnOption=dict(fpMaxIters=5)))
+    sol.runFPAdj(dFdW, psi_fp)  # not expected to converge in 5 sweeps: only its workspace matters here
+    sol.updateDAOption(dict(adjEqnOption=dict(gmresRelTol=1e-9, gmresMaxIters=600, gmresRestart=300)))
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    sol.createMLRKSPMatrixFree(pc, ksp)
+    psi = np.zeros(n)
+    fail = sol.solveLinearEqn(ksp, dFdW, psi)
+    assert fail == 0 and ksp.stats.iterations > 40
+    r = np.zeros(n)
+    sol.calcdRdWTPsiAD(psi, r)
+    assert np.linalg.norm(r - dFdW) <= 2e-9 * np.linalg.norm(dFdW)
