@@ -294,7 +294,9 @@ def main():
     ap.add_argument("--pc-level", type=int, default=3)
     ap.add_argument("--pc-block", type=int, default=0,
                     help="adjEqnOption.pcBlockCells: block-Jacobi ILU(0) with natural order inside blocks of that many cells (0: multicolour)")
-    ap.add_argument("--coarse", type=int, default=1000)
+    ap.add_argument("--coarse", type=int, default=2000)
+    ap.add_argument("--pc-storage", default="fp32", choices=["fp32", "fp64"],
+                    help="adjEqnOption.pcStorage: fp32 copy of the ILU factors for the triangular solves (operator and vectors stay fp64)")
     ap.add_argument("--idr-s", type=int, default=8)
     ap.add_argument("--max-iters", type=int, default=3000)
     ap.add_argument("--mesh", default="ogrid2d", choices=["ogrid2d", "wing3d"],
@@ -359,7 +361,7 @@ def main():
                  "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
     ns_opt = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else NORM_STATES
     adj_opt = dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level,
-                   coarseAggregates=args.coarse, pcBlockCells=args.pc_block, tileCells=int(np.prod(tile)))
+                   coarseAggregates=args.coarse, pcBlockCells=args.pc_block, pcStorage=args.pc_storage, tileCells=int(np.prod(tile)))
     opts = dict(normalizeStates=ns_opt, function=fn, primalMaxIters=max(args.primal_iters, 1), primalMinResTol=1e-8, printInterval=100,
                 adjEqnOption=adj_opt)
     sol = pyDASolvers(args.solver + " -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)

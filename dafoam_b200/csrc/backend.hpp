@@ -119,8 +119,11 @@ struct Backend
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr; // communication stream (halo exchange overlapped with interior cells)
     long launches = 0;
+    int device_ = 0;
+    void makeCurrent() { if (stream) cudaSetDevice(device_); }
     void init(int device)
     {
+        device_ = device;
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0)
@@ -221,6 +224,7 @@ struct Backend
 struct Backend
 {
     long launches = 0;
+    void makeCurrent() {}
     void init(int) {}
     void destroy() {}
     void* alloc(size_t bytes) { return std::malloc(bytes ? bytes : 8); }

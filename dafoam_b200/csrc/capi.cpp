@@ -36,6 +36,13 @@ static void need(const void* p, const char* what)
 {
     if (!p) throw Error(std::string("null pointer: ") + what);
 }
+// every entry point that takes a solver makes the solver's device current first: another library (torch, a second engine handle)
+// may have changed the calling thread's current device since dab_create
+static void need(dab_solver* s, const char* what)
+{
+    if (!s) throw Error(std::string("null pointer: ") + what);
+    s->s.be.makeCurrent();
+}
 
 extern "C"
 {

@@ -88,7 +88,14 @@ struct Comm
         NcclApi& N = NcclApi::get();
         ncclResult_t r = N.CommInitRank(&nccl, size, id, rank);
         if (r != ncclSuccess) throw Error(std::string("ncclCommInitRank: ") + N.GetErrorString(r));
-        (void)be;
+        {
+            // NCCL builds its channels lazily on the first collective: pay that second here, not inside the first timed solve
+            double* w = (double*)be.alloc(8 * sizeof(double));
+            be.zero(w, 8 * sizeof(double));
+            N.AllReduce(w, w, 8, ncclDouble, ncclSum, nccl, be.stream);
+            be.sync();
+            be.free(w);
+        }
 #else
         (void)be;
         (void)uid;

@@ -511,7 +511,7 @@ struct cRevB
                 phib_acc += mb;
             }
             if (fr.s > 0)
-                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x.phi[f]) * q.sPhi * mS;
+                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x.phi[f]) * phiRowScale(q, mS);
             else if (fr.n >= nC)
                 y[offPhi + f] = 0.0;
         }
@@ -663,7 +663,7 @@ struct cRevE
                 }
                 boundaryPointAdj<true>(m, q, s, r, f, c, bp, ba, Ub, pb, Tb, ntb, nutPb);
             }
-            if (fr.s > 0) y[offPhi + f] += phib_acc * q.sPhi * mS;
+            if (fr.s > 0) y[offPhi + f] += phib_acc * phiRowScale(q, mS);
         }
         if (q.turboH)
         {

@@ -50,6 +50,7 @@ struct ColourView
     int nCells, nSlots;
     int slotStart[MAXSLOT];
     int slotCount[MAXSLOT];
+    long long slotBase[MAXSLOT]; // ELL offset of entry 0 of the slot's first row (the slot's rows are contiguous; entry stride = slotCount)
 };
 
 // ---- FD assembly -----------------------------------------------------------------------------------------
@@ -59,6 +60,7 @@ struct StatePtrs
     int nC, turb;
     const double* magSf;
     double sU, sP, sNut, sPhi;
+    int phiNorm = 1; // "phi" listed in normalizeStates: the FD perturbation of a face flux is scaled by |Sf| (DAPartDeriv.C:284-310), else by 1
     double* T = nullptr; // compressible: [U | p | T | nuTilda | phi]
     double sT = 1.0;
     DAB_HD double* at(int ext, double& scale) const
@@ -77,7 +79,7 @@ struct StatePtrs
             if (ext < nC) { scale = sNut; return nt + ext; }
             ext -= nC;
         }
-        scale = sPhi * magSf[ext];
+        scale = phiNorm ? sPhi * magSf[ext] : 1.0;
         return phi + ext;
     }
 };
@@ -175,54 +177,109 @@ struct IluFactorColour
     }
 };
 
-struct TriLowerColour // y = L^{-1} y (unit lower), in place
+// Triangular solves, one launch per colour.  LANES threads share a cell: the cell's rows (slots) are walked in order -- later rows
+// of the cell read what its earlier rows produced -- and the entries of a row are dealt round-robin to the lanes, the partial sums
+// combined with a shuffle butterfly.  Measured at 1M cells (profiles/r02_adjoint_solve_profile.md): with the multicolour ordering
+// (74k cells per launch) LANES = 1 is FASTER (99 / 76 us per launch against 106 / 105 with 4 lanes): the kernels are bound by the
+// x[col] gathers, which coalesce across the consecutive cells of a warp, and splitting a row over lanes divides that coalescing by
+// LANES.  With the block-natural ordering (40 levels of ~5k cells) 4 lanes win (14.9 -> 11.0 s per solve): there the launches are
+// too small to fill the device.  The ordering picks the variant.
+
+template <int TRI_LANES>
+DAB_HD double triRowDot(const EllView& A, int64_t bi, int64_t si, int e0, int e1, int lane, const double* y)
+{
+    // (a 4-way unrolled version with independent partial sums was measured: lower solve -5 %, upper solve +20 % -- not kept)
+    double acc = 0.0;
+    if (A.valF)
+        for (int e = e0 + lane; e < e1; e += TRI_LANES) acc += (double)A.valF[bi + e * si] * y[A.col[bi + e * si]];
+    else
+        for (int e = e0 + lane; e < e1; e += TRI_LANES) acc += A.val[bi + e * si] * y[A.col[bi + e * si]];
+    return acc;
+}
+
+template <int TRI_LANES>
+struct TriLowerColour // y = L^{-1} y (unit lower), in place; launched over nCells * TRI_LANES threads
 {
     EllView A;
     ColourView cv;
     double* y;
-    DAB_HD void operator()(int t) const
+    DAB_HD void operator()(int tt) const
     {
+#if defined(__CUDA_ARCH__)
+        // the launch is padded to whole warps and no thread leaves early: every lane of the warp takes part in every shuffle
+        const int t = tt / TRI_LANES, lane = tt - t * TRI_LANES;
+        for (int s = 0; s < cv.nSlots; s++)
+        {
+            const bool on = t < cv.slotCount[s];
+            const int i = cv.slotStart[s] + t;
+            double acc = 0.0;
+            if (on) acc = triRowDot<TRI_LANES>(A, cv.slotBase[s] + t, cv.slotCount[s], 0, A.diag[i], lane, y);
+            for (int o = 1; o < TRI_LANES; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TRI_LANES);
+            if (on && lane == 0) y[i] -= acc;
+            __syncwarp(); // the next row of this cell may read y[i]
+        }
+#else
+        if (tt % TRI_LANES) return;
+        const int t = tt / TRI_LANES;
         for (int s = 0; s < cv.nSlots; s++)
         {
             if (t >= cv.slotCount[s]) break;
             const int i = cv.slotStart[s] + t;
             const int64_t bi = A.rowBase[i], si = A.rowStride[i];
-            const int di = A.diag[i];
-            double acc = y[i];
-            if (A.valF)
-                for (int e = 0; e < di; e++) acc -= (double)A.valF[bi + e * si] * y[A.col[bi + e * si]];
-            else
-                for (int e = 0; e < di; e++) acc -= A.val[bi + e * si] * y[A.col[bi + e * si]];
-            y[i] = acc;
+            double part[TRI_LANES];
+            for (int l = 0; l < TRI_LANES; l++) part[l] = triRowDot<TRI_LANES>(A, bi, si, 0, A.diag[i], l, y);
+            for (int o = 1; o < TRI_LANES; o <<= 1)
+                for (int l = 0; l < TRI_LANES; l++)
+                    if (!(l & o)) part[l] += part[l | o]; // same pairing as the device butterfly (lane 0's sum)
+            y[i] -= part[0];
         }
+#endif
     }
 };
 
-struct TriUpperColour // x = U^{-1} x, in place
+template <int TRI_LANES>
+struct TriUpperColour // x = U^{-1} x, in place; launched over nCells * TRI_LANES threads
 {
     EllView A;
     ColourView cv;
     double* x;
-    DAB_HD void operator()(int t) const
+    DAB_HD void operator()(int tt) const
     {
+#if defined(__CUDA_ARCH__)
+        const int t = tt / TRI_LANES, lane = tt - t * TRI_LANES;
+        for (int s = cv.nSlots - 1; s >= 0; s--)
+        {
+            const bool on = t < cv.slotCount[s];
+            const int i = cv.slotStart[s] + t;
+            int64_t bi = 0, si = 0;
+            int di = 0;
+            double acc = 0.0;
+            if (on)
+            {
+                bi = cv.slotBase[s] + t; si = cv.slotCount[s]; di = A.diag[i];
+                acc = triRowDot<TRI_LANES>(A, bi, si, di + 1, A.rowLen[i], lane, x);
+            }
+            for (int o = 1; o < TRI_LANES; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TRI_LANES);
+            if (on && lane == 0) x[i] = (x[i] - acc) / (A.valF ? (double)A.valF[bi + di * si] : A.val[bi + di * si]);
+            __syncwarp();
+        }
+#else
+        if (tt % TRI_LANES) return;
+        const int t = tt / TRI_LANES;
         for (int s = cv.nSlots - 1; s >= 0; s--)
         {
             if (t >= cv.slotCount[s]) continue;
             const int i = cv.slotStart[s] + t;
             const int64_t bi = A.rowBase[i], si = A.rowStride[i];
-            const int di = A.diag[i], len = A.rowLen[i];
-            double acc = x[i];
-            if (A.valF)
-            {
-                for (int e = di + 1; e < len; e++) acc -= (double)A.valF[bi + e * si] * x[A.col[bi + e * si]];
-                x[i] = acc / (double)A.valF[bi + di * si];
-            }
-            else
-            {
-                for (int e = di + 1; e < len; e++) acc -= A.val[bi + e * si] * x[A.col[bi + e * si]];
-                x[i] = acc / A.val[bi + di * si];
-            }
+            const int di = A.diag[i];
+            double part[TRI_LANES];
+            for (int l = 0; l < TRI_LANES; l++) part[l] = triRowDot<TRI_LANES>(A, bi, si, di + 1, A.rowLen[i], l, x);
+            for (int o = 1; o < TRI_LANES; o <<= 1)
+                for (int l = 0; l < TRI_LANES; l++)
+                    if (!(l & o)) part[l] += part[l | o];
+            x[i] = (x[i] - part[0]) / (A.valF ? (double)A.valF[bi + di * si] : A.val[bi + di * si]);
         }
+#endif
     }
 };
 
@@ -471,9 +528,74 @@ struct CoarseUnitColour // x = indicator of the pressure DOFs of every local agg
     }
 };
 
+// ---- sparse A*P: the product of the operator with a coarse-space vector, without a matrix-free product ------------------------------
+// The multiplicative two-level step needs t = v - A z1 with z1 = P yc (piecewise-constant pressure per aggregate).  A (P e_a) is zero
+// except within a few cells of the boundary of aggregate a (a constant pressure has no gradient inside), and the probing of the
+// Galerkin operator computes exactly these columns: they are kept (COO while probing, CSR by row afterwards) and t = v - (AP) yc
+// becomes one short sparse product per application instead of a full RevA+RevB+RevC (17 % of an IDR(s) application at 1M cells).
+struct ApExtract
+{
+    const double* t;        // response A * (sum of unit aggregates of this probe)
+    int nC, nCellStates, offPhi;
+    const int32_t* aggOf;   // [nC] local aggregate of a cell
+    const int32_t *own, *nei;
+    const int32_t* srcOfAgg; // coloured probe: global index of the source aggregate whose reach contains local aggregate i (-1: none); or null
+    int constSrc;            // one-aggregate probe: its global index
+    unsigned long long* counter;
+    long long cap;
+    int32_t *outRow, *outAgg;
+    double* outVal;
+    DAB_HD void operator()(int r) const
+    {
+        const double v = t[r];
+        if (v == 0.0) return;
+        int c;
+        if (r < 3 * nC) c = r / 3;
+        else if (r < offPhi) c = (r - 3 * nC) % nC;
+        else
+        {
+            const int f = r - offPhi;
+            c = own[f] < nC ? own[f] : nei[f];
+        }
+        const int src = srcOfAgg ? srcOfAgg[aggOf[c]] : constSrc;
+#if defined(__CUDA_ARCH__)
+        const unsigned long long k = atomicAdd(counter, 1ull);
+#else
+        const unsigned long long k = (*counter)++;
+#endif
+        if ((long long)k < cap)
+        {
+            outRow[k] = r;
+            outAgg[k] = src;
+            outVal[k] = v;
+        }
+    }
+};
+struct ApApply // out = v - (A P) yc, rows in CSR
+{
+    const int32_t* ptr;
+    const int32_t* agg;
+    const double* val;
+    const double* yc;
+    const double* v;
+    double* out;
+    DAB_HD void operator()(int r) const
+    {
+        double s = 0.0;
+        for (int e = ptr[r]; e < ptr[r + 1]; e++) s += val[e] * yc[agg[e]];
+        out[r] = v[r] - s;
+    }
+};
+
 struct Coarse
 {
     bool enabled = false, valid = false;
+    // sparse A*P (see ApExtract)
+    bool apValid = false;
+    long long apCap = 0;
+    DevBuf<unsigned long long> dApCount;
+    DevBuf<int32_t> dApRow, dApAgg, dApPtr, dApAggSorted;
+    DevBuf<double> dApVal, dApValSorted;
     int nAggLocal = 0, nAggGlobal = 0, aggBase = 0, nChunks = 0;
     DevBuf<int32_t> dAggOf, dCells, dChunkStart, dAggChunkOff;
     DevBuf<double> dPartial, dRc, dYc;

@@ -540,7 +540,7 @@ DAB_HD void revBCell(const Acc& A, const Params& q, int c, bool gradOnly)
         if (!gradOnly)
         {
             if (fr.s > 0)
-                A.setYPhi(f, (phib_acc - (q.nrPhi ? rmS : 1.0) * xphif) * q.sPhi * mS);
+                A.setYPhi(f, (phib_acc - (q.nrPhi ? rmS : 1.0) * xphif) * phiRowScale(q, mS));
             else if (A.ghost(fr.n))
                 A.setYPhi(f, 0.0); // cut face whose phi belongs to the neighbouring rank
         }

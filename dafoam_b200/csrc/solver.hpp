@@ -192,6 +192,7 @@ struct Solver
     int pcSymbolicOnly = 0;
     int fpMaxIters = 1000;      // adjEqnOption fpMaxIters / fpRelTol / fpMinResTolDiff (reference pyDAFoam.py:540-542)
     double fpRelTol = 1e-6, fpMinResTolDiff = 1e2, fpOmega = 0.5;
+    int coarseSparseAP = 1;   // keep the columns A*(P e_a) the probing computes and apply v - A P yc as a sparse product (0: matrix-free product per application)
     int coarseProbeReach = 6; // cell levels a pressure perturbation reaches through the transposed Jacobian (coloured probing of the coarse operator; 0 = one product per aggregate)
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
     int pcBlockCells = 0;          // > 0: block-Jacobi ILU with the natural cell order inside blocks of that many consecutive cells (PCASM overlap 0 + natural-order PCILU), level-scheduled
@@ -610,6 +611,7 @@ struct Solver
         }
         // defaults of the reference's DAOPTION (dafoam/pyDAFoam.py:526-563)
         par.sU = par.sP = par.sNut = par.sPhi = 1.0;
+        par.phiNorm = 0; // normalizeStates is empty by default: no state is scaled
         par.nrU = par.nrP = par.nrNut = par.nrPhi = 1;
         par.constrainHbyA = 1;
     }
@@ -625,6 +627,7 @@ struct Solver
             par.sP = ns->numOr("p", par.sP);
             par.sNut = ns->numOr("nuTilda", par.sNut);
             par.sPhi = ns->numOr("phi", par.sPhi);
+            par.phiNorm = ns->get("phi") ? 1 : 0;
             par.sT = ns->numOr("T", par.sT);
         }
         if (const JVal* nr = o.get("normalizeResiduals"))
@@ -666,6 +669,10 @@ struct Solver
             fpMinResTolDiff = a->numOr("fpMinResTolDiff", fpMinResTolDiff);
             fpOmega = a->numOr("fpOmega", fpOmega);
             tileCellsHint = (int)a->numOr("tileCells", tileCellsHint);
+            {
+                const int sa = (int)a->numOr("coarseSparseAP", coarseSparseAP);
+                if (sa != coarseSparseAP) { coarseSparseAP = sa; kry.pcValid = false; }
+            }
             {
                 const int pr = (int)a->numOr("coarseProbeReach", coarseProbeReach);
                 if (pr != coarseProbeReach) { coarseProbeReach = pr; kry.pcValid = false; }

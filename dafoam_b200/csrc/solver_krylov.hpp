@@ -312,6 +312,11 @@ inline void Solver::pcSymbolic()
     std::vector<int64_t> gOff(nG + 1, 0);
     for (int g = 0; g < nG; g++) gOff[g + 1] = gOff[g] + (int64_t)width[g] * groupRows[g];
     K.ellSize = gOff[nG];
+    {
+        int g = 0; // groups were pushed colour by colour, slot by slot
+        for (ColourView& cv : K.colours)
+            for (int sl = 0; sl < cv.nSlots; sl++) cv.slotBase[sl] = gOff[g++];
+    }
     K.rowBase.resize(K.n);
     K.rowStride.resize(K.n);
     K.diag.assign(K.n, -1);
@@ -415,7 +420,7 @@ inline void Solver::calcPC()
     if (!K.symbolic) pcSymbolic();
     if (pcSymbolicOnly) return; // profiling hook (adjEqnOption.pcSymbolicOnly): host set-up only, nothing assembled
     be.zero(K.dVal.p, (size_t)K.ellSize * sizeof(double));
-    StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi};
+    StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi, par.phiNorm};
     if (par.comp)
     {
         sp.T = dT.p;
@@ -557,6 +562,23 @@ inline void Solver::coarseSetup()
     Cs.dYc.alloc(be, Cs.nAggGlobal + 1);
     Cs.hRc.assign(Cs.nAggGlobal, 0.0);
     K.t3.alloc(be, n);
+    // sparse A*P collected while probing (adjEqnOption.coarseSparseAP, default 1; 0: one extra matrix-free product per application)
+    Cs.apValid = false;
+    const bool wantAp = coarseSparseAP != 0;
+    if (wantAp)
+    {
+        Cs.apCap = (long long)3 * n;
+        Cs.dApRow.alloc(be, (size_t)Cs.apCap, false);
+        Cs.dApAgg.alloc(be, (size_t)Cs.apCap, false);
+        Cs.dApVal.alloc(be, (size_t)Cs.apCap, false);
+        Cs.dApCount.alloc(be, 1);
+    }
+    const int offPhiAp = nCellStates() * nC;
+    auto extractAp = [&](const int32_t* dSrcOfAgg, int constSrc) {
+        if (!wantAp) return;
+        be.launch(n, ApExtract{K.t3.p, nC, nCellStates(), offPhiAp, Cs.dAggOf.p, mv.own, mv.nei, dSrcOfAgg, constSrc, Cs.dApCount.p, Cs.apCap,
+                               Cs.dApRow.p, Cs.dApAgg.p, Cs.dApVal.p});
+    };
     // Galerkin operator, column by column
     const int Kg = Cs.nAggGlobal;
     Cs.lu.assign((size_t)Kg * Kg, 0.0);
@@ -609,6 +631,14 @@ inline void Solver::coarseSetup()
             for (int a = 0; a < nAgg; a++)
                 if (colour[a] == k)
                     for (int i : reach[a]) owner[i] = a;
+            if (wantAp)
+            {
+                std::vector<int32_t> o32(owner.begin(), owner.end());
+                DevBuf<int32_t> dOwner;
+                dOwner.upload(be, o32);
+                extractAp(dOwner.p, -1);
+                be.sync(); // dOwner goes out of scope
+            }
             double big = 0.0;
             for (int i = 0; i < Kg; i++) big = std::max(big, std::fabs(Cs.hRc[i]));
             for (int i = 0; i < Kg && ok; i++)
@@ -622,6 +652,7 @@ inline void Solver::coarseSetup()
             if (printInfo) fprintf(stderr, "[dab200] coarse space: probing reach %d too short, falling back to one product per aggregate\n", coarseProbeReach);
             std::fill(Cs.lu.begin(), Cs.lu.end(), 0.0);
             nProbes = 0;
+            if (wantAp) be.zero(Cs.dApCount.p, sizeof(unsigned long long));
         }
         else if (printInfo)
             fprintf(stderr, "[dab200] coarse space: %d aggregates probed with %d coloured products\n", nAgg, nProbes);
@@ -634,7 +665,61 @@ inline void Solver::coarseSetup()
             matVecDev(K.t2.p, K.t3.p);
             coarseRestrict(K.t3.p);
             for (int i = 0; i < Kg; i++) Cs.lu[(size_t)i * Kg + j] = Cs.hRc[i];
+            extractAp(nullptr, j);
         }
+    if (wantAp)
+    {
+        // COO -> CSR by row, entries of a row ordered by aggregate (the atomics fill the COO in no particular order: fix it)
+        unsigned long long cnt = 0;
+        be.d2h(&cnt, Cs.dApCount.p, sizeof(cnt));
+        bool bad = (long long)cnt > Cs.apCap;
+        std::vector<int32_t> row, agg;
+        std::vector<double> val;
+        if (!bad)
+        {
+            row.resize(cnt); agg.resize(cnt); val.resize(cnt);
+            if (cnt)
+            {
+                be.d2h(row.data(), Cs.dApRow.p, cnt * sizeof(int32_t));
+                be.d2h(agg.data(), Cs.dApAgg.p, cnt * sizeof(int32_t));
+                be.d2h(val.data(), Cs.dApVal.p, cnt * sizeof(double));
+            }
+            for (size_t e = 0; e < cnt && !bad; e++)
+                if (agg[e] < 0 || agg[e] >= Kg) bad = true; // a response outside every reach set: keep the exact product path
+        }
+        if (!bad)
+        {
+            std::vector<int32_t> ptr((size_t)n + 1, 0);
+            for (size_t e = 0; e < cnt; e++) ptr[row[e] + 1]++;
+            for (int r = 0; r < n; r++) ptr[r + 1] += ptr[r];
+            std::vector<int32_t> pos(ptr.begin(), ptr.end() - 1), sAgg(cnt);
+            std::vector<double> sVal(cnt);
+            for (size_t e = 0; e < cnt; e++)
+            {
+                const int32_t q = pos[row[e]]++;
+                sAgg[q] = agg[e];
+                sVal[q] = val[e];
+            }
+            std::vector<std::pair<int32_t, double>> tmp;
+            for (int r = 0; r < n; r++)
+            {
+                const int a = ptr[r], b = ptr[r + 1];
+                if (b - a < 2) continue;
+                tmp.clear();
+                for (int e = a; e < b; e++) tmp.emplace_back(sAgg[e], sVal[e]);
+                std::sort(tmp.begin(), tmp.end());
+                for (int e = a; e < b; e++) { sAgg[e] = tmp[e - a].first; sVal[e] = tmp[e - a].second; }
+            }
+            Cs.dApPtr.upload(be, ptr);
+            Cs.dApAggSorted.upload(be, sAgg);
+            Cs.dApValSorted.upload(be, sVal);
+            Cs.apValid = true;
+            if (printInfo) fprintf(stderr, "[dab200] coarse space: sparse A*P with %llu entries (%.2f per row)\n", cnt, (double)cnt / n);
+        }
+        else if (printInfo)
+            fprintf(stderr, "[dab200] coarse space: sparse A*P not usable (overflow or response outside the reach sets): matrix-free product kept\n");
+        Cs.dApRow.release(); Cs.dApAgg.release(); Cs.dApVal.release();
+    }
     Cs.factor(std::min(std::max(1, detail::hostThreads() / std::max(1, nRanks)), 32));
     {
         std::vector<double> invT;
@@ -681,9 +766,14 @@ inline void Solver::applyPC(const double* v, double* z)
         coarseRestrict(v, false);
         be.launch(Cs.nAggGlobal, CoarseApply{Cs.dInvT.p, Cs.dRc.p, Cs.nAggGlobal, Cs.dYc.p});
         be.launch(n, CoarseProlong{Cs.dYc.p, Cs.dAggOf.p, 3 * hm.nC, hm.nC, Cs.aggBase, K.t2.p}); // z1
-        matVecDev(K.t2.p, K.t3.p);
-        kspExtraMatvecs++;
-        be.launch(n, SubVec{v, K.t3.p}); // t3 = v - A z1
+        if (Cs.apValid)
+            be.launch(n, ApApply{Cs.dApPtr.p, Cs.dApAggSorted.p, Cs.dApValSorted.p, Cs.dYc.p, v, K.t3.p}); // t3 = v - (A P) yc
+        else
+        {
+            matVecDev(K.t2.p, K.t3.p);
+            kspExtraMatvecs++;
+            be.launch(n, SubVec{v, K.t3.p}); // t3 = v - A z1
+        }
         applyIlu(K.t3.p, z);
         be.launch(n, AxpyVec{K.t2.p, 1.0, z});
     }
@@ -715,8 +805,18 @@ inline void Solver::applyIlu(const double* v, double* z)
     Krylov& K = kry;
     EllView A = K.view();
     be.launch(K.n, GatherVec{v, K.dPerm.p, K.t1.p});
-    for (size_t k = 0; k < K.colours.size(); k++) be.launch(K.colours[k].nCells, TriLowerColour{A, K.colours[k], K.t1.p});
-    for (size_t k = K.colours.size(); k-- > 0;) be.launch(K.colours[k].nCells, TriUpperColour{A, K.colours[k], K.t1.p});
+    auto padded = [](int nCells, int lanes) { return (nCells * lanes + 31) / 32 * 32; }; // whole warps: see TriLowerColour
+    if (pcBlockCells > 0)
+    {
+        // many small levels: four lanes per cell
+        for (size_t k = 0; k < K.colours.size(); k++) be.launch(padded(K.colours[k].nCells, 4), TriLowerColour<4>{A, K.colours[k], K.t1.p});
+        for (size_t k = K.colours.size(); k-- > 0;) be.launch(padded(K.colours[k].nCells, 4), TriUpperColour<4>{A, K.colours[k], K.t1.p});
+    }
+    else
+    {
+        for (size_t k = 0; k < K.colours.size(); k++) be.launch(padded(K.colours[k].nCells, 1), TriLowerColour<1>{A, K.colours[k], K.t1.p});
+        for (size_t k = K.colours.size(); k-- > 0;) be.launch(padded(K.colours[k].nCells, 1), TriUpperColour<1>{A, K.colours[k], K.t1.p});
+    }
     be.launch(K.n, ScatterVec{K.t1.p, K.dPerm.p, z});
 }
 

@@ -163,6 +163,7 @@ struct Params
 {
     double nu, alphaU;
     double sU, sP, sNut, sPhi;           // normalizeStates
+    int phiNorm;                         // "phi" is listed in normalizeStates: only then the phi rows get sPhi*|Sf| (DASolver.C:2431-2452)
     int turb, divU, divNut;              // turb: 0 laminar (dummyTurbulenceModel), 1 SpalartAllmaras
     int saFv3;                           // 1: SpalartAllmarasFv3 production term (DASpalartAllmarasFv3.C:158-175, 452-456)
     int nrU, nrP, nrNut, nrPhi;          // residual listed in normalizeResiduals
@@ -327,6 +328,11 @@ DAB_HD double dnut_dnt(double nt, double nu)
     const double fv1 = c3 / den, dfv1 = 3.0 * chi * chi * SA::Cv1c / (den * den);
     return fv1 + chi * dfv1;
 }
+
+// scaling of a phi row of a product (DASolver::normalizeGradientVec, DASolver.C:2431-2452): normalizeStates.phi * |Sf| when "phi" is
+// listed in normalizeStates, otherwise the row is left alone
+template <class P>
+DAB_HD double phiRowScale(const P& q, double magSf) { return q.phiNorm ? q.sPhi * magSf : 1.0; }
 
 // mixed-BC value fraction (fixedValue 1, zeroGradient 0, inletOutlet 1-pos0(phi), outletInlet pos0(phi))
 DAB_HD double bcFrac(int kind, double phib)

@@ -98,6 +98,7 @@ struct Params
     int turb;         // 0: dummyTurbulenceModel (laminar, no nuTilda state), 1: SpalartAllmaras, 2: SpalartAllmarasFv3
     int divU, divNut; // DivScheme for div(phi,U), div(phi,nuTilda)
     double sU, sP, sNut, sPhi; // normalizeStates
+    int phiNorm = 1;           // "phi" listed in normalizeStates (DASolver.C:2431-2452: the phi rows are scaled only then)
     int nrU, nrP, nrNut, nrPhi; // 1 = residual name listed in normalizeResiduals
     int constrainHbyA;
 };
@@ -1727,6 +1728,7 @@ void* orc_create(int nP, const double* points, int nF, const int* fOff, const in
     q.nu = dpar[0]; q.alphaU = dpar[1]; q.sU = dpar[2]; q.sP = dpar[3]; q.sNut = dpar[4]; q.sPhi = dpar[5];
     q.turb = ipar[0]; q.divU = ipar[1]; q.divNut = ipar[2];
     q.nrU = ipar[3]; q.nrP = ipar[4]; q.nrNut = ipar[5]; q.nrPhi = ipar[6]; q.constrainHbyA = ipar[7];
+    q.phiNorm = ipar[8];
     cs->pts.assign(points, points + 3 * (size_t)nP);
     std::vector<V3<double>> P(nP);
     for (int i = 0; i < nP; i++) P[i] = V3<double>(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
@@ -1896,7 +1898,8 @@ static void scaleStates(const Case* cs, double* y)
         for (int i = 0; i < t.nC; i++) y[off + i] *= q.sNut;
         off += t.nC;
     }
-    for (int f = 0; f < t.nF; f++) y[off + f] *= q.sPhi * cs->gd.magSf[f];
+    if (q.phiNorm)
+        for (int f = 0; f < t.nF; f++) y[off + f] *= q.sPhi * cs->gd.magSf[f];
 }
 
 // DASolver::initializeGlobalADTape4dRdWT: record R(W) once on the global tape

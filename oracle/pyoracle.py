@@ -87,11 +87,11 @@ class Oracle:
         pstart = np.array([p["start"] for p in mesh.patches], dtype=np.int32)
         psize = np.array([p["size"] for p in mesh.patches], dtype=np.int32)
         pgeom = np.array([GEOM_KIND.get(p["type"], 0) for p in mesh.patches], dtype=np.int32)
-        dpar = np.array([nu, alphaU, ns["U"], ns["p"], ns["nuTilda"], ns["phi"]], dtype=np.float64)
+        dpar = np.array([nu, alphaU, ns["U"], ns["p"], ns["nuTilda"], ns.get("phi", 1.0)], dtype=np.float64)
         ipar = np.array([int(self.turb) * (2 if rasModel == "SpalartAllmarasFv3" else 1), DIV_SCHEME[divU], DIV_SCHEME[divNut],
                          int("URes" in normalizeResiduals), int("pRes" in normalizeResiduals),
                          int("nuTildaRes" in normalizeResiduals), int("phiRes" in normalizeResiduals),
-                         int(constrainHbyA)], dtype=np.int32)
+                         int(constrainHbyA), int("phi" in (normalizeStates or {"phi": 1.0}))], dtype=np.int32)
         yw = None if yWall is None else _p(np.ascontiguousarray(yWall, dtype=np.float64))
         self._keep = (foff, flab, pstart, psize, pgeom, kind, value, dpar, ipar)
         self.h = C.c_void_p(L.orc_create(

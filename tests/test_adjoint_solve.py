@@ -302,3 +302,17 @@ def test_fixed_point_then_gmres_on_the_same_handle():
     r = np.zeros(n)
     sol.calcdRdWTPsiAD(psi, r)
     assert np.linalg.norm(r - dFdW) <= 2e-9 * np.linalg.norm(dFdW)
+
+
+def test_sparse_coarse_columns_equal_the_matrix_free_product():
+    """adjEqnOption.coarseSparseAP: the multiplicative two-level step t = v - A P yc through the columns A (P e_a) kept from the probing
+    of the coarse operator (a short sparse product) gives the same preconditioner as the matrix-free product it replaces: same GMRES
+    history, same adjoint; coloured probing (> 64 aggregates) and one-product-per-aggregate probing."""
+    for nagg in (100, 12):
+        mesh, sol, W = adjoint_case(HOSTSIM, ni=48, nj=24, restart=300, maxit=600)
+        res = {}
+        for sparse in (1, 0):
+            psi, it = _solve_with(sol, W, dict(coarseAggregates=nagg, coarseSparseAP=sparse))
+            res[sparse] = (psi, it)
+        assert res[1][1] == res[0][1], (nagg, res[1][1], res[0][1])
+        assert np.linalg.norm(res[1][0] - res[0][0]) <= 1e-9 * np.linalg.norm(res[0][0])

@@ -55,3 +55,71 @@ def test_full_size_linearity_and_determinism_cuda():
     assert np.array_equal(ya, ya2)  # gather kernels: bitwise reproducible
     assert rel_err(yab, 2.0 * ya - 3.0 * yb) < 1e-12
     assert np.isfinite(ya).all() and np.linalg.norm(ya) > 0
+
+
+def _medium_case(ni, nj, lib=None, extra=None):
+    import tempfile
+    from dafoam_b200 import cases
+    from dafoam_b200.pyDASolvers import pyDASolvers
+    from oracle.pyoracle import Oracle
+    from tests.common import NORM_STATES
+    mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1, tile=(16, 12))
+    bcs = cases.default_bcs_naca(wall_function=True)
+    d = tempfile.mkdtemp(prefix="dab_mid_")
+    cases.write_case(d, mesh, bcs, binary=True, div_u="bounded Gauss linearUpwindV grad(U)")
+    opts = dict(normalizeStates=NORM_STATES)
+    opts.update(extra or {})
+    sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib)
+    orc = Oracle(mesh, bcs, normalizeStates=NORM_STATES, divU="linearUpwindV")
+    yw = np.zeros(mesh.n_cells)
+    sol.getOFField("yWall", "scalar", yw)
+    W = cases.boundary_layer_state(mesh, yw, noise=0.01)
+    return mesh, orc, sol, W
+
+
+def test_values_match_the_oracle_on_a_34k_cell_mesh_cuda():
+    """the value comparisons ran on <= 1600 cells.  33 792 cells (256x132 O-grid, tile-major numbering, the NACA
+    tutorial's linearUpwindV + wall-function variant of the kernels): R(W) and dRdW^T psi against the oracle -- thousands of CTAs,
+    every occupancy-dependent code path, int32 offsets two orders of magnitude larger."""
+    mesh, orc, sol, W = _medium_case(256, 132)
+    assert mesh.n_cells == 33792
+    sol.updateOFFields(W)
+    R = np.zeros(orc.ndof)
+    sol.getResiduals(R)
+    assert rel_err(R, orc.residual(W)) < 1e-10
+    orc.record(W)
+    psi = np.random.default_rng(4321).uniform(-1, 1, orc.ndof)
+    y = np.zeros(orc.ndof)
+    sol.calcdRdWTPsiAD(psi, y)
+    yo = orc.jtvec(psi)
+    nC = mesh.n_cells
+    for a, b in ((0, 3 * nC), (3 * nC, 4 * nC), (4 * nC, 5 * nC), (5 * nC, orc.ndof)):
+        assert rel_err(y[a:b], yo[a:b]) < 1e-10
+
+
+def test_tile_kernels_match_the_default_kernels_cuda():
+    """DAB_TILE=1 (CTA-resident tile kernels, chosen once per process: child processes) computes the same product as the default
+    cell-per-thread kernels on a tile-major numbered mesh with real halos."""
+    import os, subprocess, sys
+    code = r'''
+import numpy as np, sys
+from tests.test_gpu_parity import _medium_case
+mesh, orc, sol, W = _medium_case(160, 96, extra=dict(adjEqnOption=dict(tileCells=192)))
+sol.updateOFFields(W)
+psi = np.random.default_rng(7).uniform(-1, 1, orc.ndof)
+y = np.zeros(orc.ndof)
+sol.calcdRdWTPsiAD(psi, y)
+np.save(sys.argv[1], y)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    import tempfile
+    for tile in ("0", "1"):
+        f = os.path.join(tempfile.mkdtemp(), "y.npy")
+        r = subprocess.run([sys.executable, "-c", code, f], cwd=root, env=dict(os.environ, DAB_TILE=tile, PYTHONPATH=root, DAB_TILE_INFO="1"),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        if tile == "1":
+            assert "tiles: 192 cells per tile" in r.stderr
+        out[tile] = np.load(f)
+    assert rel_err(out["1"], out["0"]) < 1e-12

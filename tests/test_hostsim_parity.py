@@ -49,3 +49,61 @@ def test_dot_product_identity_host_build():
     sol.getResiduals(Rm)
     Jv = (Rp - Rm) / (2 * eps)
     assert abs(psi @ Jv - v @ y) <= 1e-6 * abs(v @ y)
+
+
+def test_phi_rows_are_scaled_only_when_phi_is_listed_in_normalize_states():
+    """DASolver::normalizeGradientVec (DASolver.C:2431-2452) multiplies the phi rows of a product by normalizeStates.phi * |Sf| only if
+    "phi" is a key of normalizeStates; otherwise they are left alone."""
+    ns = dict(U=10.0, p=50.0, nuTilda=1e-3)  # no phi
+    from oracle.pyoracle import Oracle
+    mesh, bcs, orc, sol, W, _ = setup("channel", True, nk=1, lib_path=HOSTSIM, extra_options=dict(normalizeStates=ns))
+    orc2 = Oracle(mesh, bcs, normalizeStates=ns, divU="linearUpwind")
+    sol.updateOFFields(W)
+    orc2.record(W)
+    psi = np.random.default_rng(9).uniform(-1, 1, orc2.ndof)
+    y = np.zeros(orc2.ndof)
+    sol.calcdRdWTPsiAD(psi, y)
+    yo = orc2.jtvec(psi)
+    assert rel_err(y, yo) < 1e-10
+    # and it differs from the listed case by exactly |Sf| on the phi rows
+    orc.record(W)
+    y1 = orc.jtvec(psi)
+    nF = mesh.n_faces
+    assert rel_err(y1[-nF:], yo[-nF:] * orc.geometry("magSf")) < 1e-12
+
+
+def test_tile_kernels_match_the_default_kernels_host_build():
+    """The CTA-resident tile kernels (DAB_TILE=1; tile_kernels.hpp: RevA tile + fused RevB/RevC tile with two halo rings) against the
+    cell-per-thread kernels and the oracle, on a tile-major numbered mesh (192-cell tiles with real halos) and on meshes whose tiles
+    are whatever fits (prisms, 3-D bricks).  The variant is chosen once per process: child processes."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np
+from tests.common import HOSTSIM, setup, rel_err
+from tests.test_gpu_parity import _medium_case
+worst = 0.0
+mesh, orc, sol, W = _medium_case(64, 48, lib=HOSTSIM, extra=dict(adjEqnOption=dict(tileCells=192)))
+sol.updateOFFields(W); orc.record(W)
+psi = np.random.default_rng(3).uniform(-1, 1, orc.ndof); y = np.zeros(orc.ndof)
+sol.calcdRdWTPsiAD(psi, y)
+worst = max(worst, rel_err(y, orc.jtvec(psi)))
+for kind, turb, nk in (("wing", True, 3), ("prism", True, 1), ("channel", False, 1)):
+    mesh, bcs, orc, sol, W, _ = setup(kind, turb, nk=nk, lib_path=HOSTSIM)
+    sol.updateOFFields(W); orc.record(W)
+    psi = np.random.default_rng(3).uniform(-1, 1, orc.ndof); y = np.zeros(orc.ndof)
+    sol.calcdRdWTPsiAD(psi, y)
+    worst = max(worst, rel_err(y, orc.jtvec(psi)))
+print("WORST %.3e" % worst)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for tile in ("0", "1"):
+        env = dict(os.environ, DAB_TILE=tile, PYTHONPATH=root, DAB_TILE_INFO="1")
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[tile] = float(r.stdout.strip().split("WORST")[-1])
+        if tile == "1":
+            assert "tiles: 192 cells per tile" in r.stderr
+    assert out["0"] < 1e-10 and out["1"] < 1e-10, out
