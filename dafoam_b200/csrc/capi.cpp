@@ -363,7 +363,7 @@ int dab_calc_jac_t_vec_product(dab_solver* s, const char* input_name, const char
     }
     if (it != "stateVar") throw Error("calcJacTVecProduct: inputType " + it + " is not supported (stateVar, patchVelocity, patchVar, volCoord)");
     // daInput->run(inputList): assign the input to the OpenFOAM fields (DAInputStateVar.C:35-140)
-    if (input) S.updateOFFields(input);
+    if (input && !S.statesAreResident(input)) S.updateOFFields(input);
     if (ot == "residual") S.matVec(seed, product);
     else if (ot == "function")
     {

@@ -283,6 +283,11 @@ struct TriUpperColour // x = U^{-1} x, in place; launched over nCells * TRI_LANE
     }
 };
 
+// (Measured and removed: solving a colour in two steps -- one thread per ROW for the other colours' contributions, then one thread per
+// cell for the in-cell substitution -- is slower, 163 + 44 us per colour against 101: the ~10 rows of a cell gather the same x entries,
+// which the per-cell thread re-reads from L1; spread over ten warps they come from L2 ten times.  profiles/r02_adjoint_solve_profile.md)
+DAB_HD double ellVal(const EllView& A, int64_t o) { return A.valF ? (double)A.valF[o] : A.val[o]; }
+
 struct CvtToFloat // fp32 copy of the factors
 {
     const double* src;

@@ -1408,9 +1408,20 @@ struct Solver
     }
 
     // ------------------------------------------------------------------------------------------
+    // host mirror of the states last assigned through updateOFFields: calcJacTVecProduct(stateVar, ...) re-assigns the states on every
+    // call (DAInputStateVar::run); when they are the resident ones the record and the preconditioner stay valid (computing
+    // dFdW after calcdRdWT used to force a second assembly inside the next solveLinearEqn)
+    std::vector<double> hWMirror;
+    bool hWMirrorValid = false;
+    bool statesAreResident(const double* W) const
+    {
+        return hWMirrorValid && hWMirror.size() == (size_t)nDof() && std::memcmp(hWMirror.data(), W, hWMirror.size() * sizeof(double)) == 0;
+    }
     void updateOFFields(const double* W)
     {
         const size_t nC = hm.nC;
+        hWMirror.assign(W, W + nDof());
+        hWMirrorValid = true;
         be.h2d(dWext.p, W, (size_t)nDof() * sizeof(double));
         be.d2d(dU.p, dWext.p, 3 * nC * sizeof(double));
         be.d2d(dP.p, dWext.p + 3 * nC, nC * sizeof(double));

@@ -432,6 +432,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
     // mirror the new state into the external layout (getOFFields) and invalidate what depended on the old one
     {
         const size_t n = nC;
+        hWMirrorValid = false; // the states changed on the device
         be.d2d(dWext.p, dU.p, 3 * n * sizeof(double));
         be.d2d(dWext.p + 3 * n, dP.p, n * sizeof(double));
         size_t off = 4 * n;

@@ -11,7 +11,7 @@ mesh = cases.naca0012_ogrid(ni=2 * nj, nj=nj, nk=1, tile=(16, 12))
 d = tempfile.mkdtemp(prefix="dab_ip_")
 cases.write_case(d, mesh, cases.default_bcs_naca(), binary=True)
 fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection", "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
-adj = dict(gmresRelTol=1e-6, gmresMaxIters=int(os.environ.get("IP_ITERS", 40)), gmresRestart=100, printInfo=0, pcConLevel=3, coarseAggregates=1000,
+adj = dict(gmresRelTol=1e-6, gmresMaxIters=int(os.environ.get("IP_ITERS", 40)), gmresRestart=100, printInfo=0, pcConLevel=3, coarseAggregates=2000,
            kspType="idrs", idrS=8, pcStorage=os.environ.get("IP_STORAGE", "fp32"))
 sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=dict(U=10.0, p=50.0, nuTilda=1e-3, phi=1.0), function=fn, adjEqnOption=adj), caseDir=d)
 n = sol.getNLocalAdjointStates()
