@@ -260,13 +260,11 @@ def global_state(mesh, comp, U0c, thermo):
     Sf, Cf = cases.quad_face_geometry(mesh)
     wall = [p for p in mesh.patches if p["type"] == "wall"][0]
     nIF = mesh.n_internal_faces
-    Cc = np.zeros((mesh.n_cells, 3))
-    cnt = np.zeros(mesh.n_cells)
-    np.add.at(Cc, mesh.owner, Cf)
-    np.add.at(cnt, mesh.owner, 1.0)
-    np.add.at(Cc, mesh.neighbour, Cf[:nIF])
-    np.add.at(cnt, mesh.neighbour, 1.0)
-    Cc /= cnt[:, None]
+    # cell centres as the mean of the face centres (bincount: np.add.at is ~50x slower at 10^7 faces)
+    nC = mesh.n_cells
+    cnt = np.bincount(mesh.owner, minlength=nC) + np.bincount(mesh.neighbour, minlength=nC)
+    Cc = np.stack([np.bincount(mesh.owner, weights=Cf[:, k], minlength=nC) + np.bincount(mesh.neighbour, weights=Cf[:nIF, k], minlength=nC)
+                   for k in range(3)], axis=1) / cnt[:, None]
     yw = cKDTree(Cf[wall["start"]:wall["start"] + wall["size"]]).query(Cc, workers=-1)[0]
     Wg = cases.boundary_layer_state(mesh, yw, U0=U0c if comp else (10.0, 0.0, 0.0), seed=1234, noise=0.001)
     if comp:

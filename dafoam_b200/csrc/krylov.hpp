@@ -288,6 +288,9 @@ struct TriUpperColour // x = U^{-1} x, in place; launched over nCells * TRI_LANE
 // which the per-cell thread re-reads from L1; spread over ten warps they come from L2 ten times.  profiles/r02_adjoint_solve_profile.md)
 DAB_HD double ellVal(const EllView& A, int64_t o) { return A.valF ? (double)A.valF[o] : A.val[o]; }
 
+// (Also measured and removed: accumulating the other-colour sums of ALL rows of a cell in lock step before the in-cell substitution --
+// ~10 independent load chains per thread on paper; 16-slot accumulator/bound arrays spill at the 80-register budget and the solve takes
+// 23.4 s instead of 7.6 s.  The plain row-after-row loop below is the fastest of the five variants tried.)
 struct CvtToFloat // fp32 copy of the factors
 {
     const double* src;

@@ -322,11 +322,22 @@ struct Solver
             lap("read polyMesh (global)");
             g.computeGeometry();
             lap("geometry (global)");
-            g.computeWallDistance();
-            lap("wall distance (global)");
             std::vector<int> cellPart;
             rcbPartition(g, nRanks, cellPart);
             lap("RCB partition");
+            {
+                // wall distance of this rank's cells and their face neighbours (the ghosts) against ALL wall faces of the global mesh
+                std::vector<uint8_t> mine(g.nC, 0);
+                for (int c = 0; c < g.nC; c++) mine[c] = cellPart[c] == rank;
+                for (int f = 0; f < g.nIF; f++)
+                {
+                    const int a = g.own[f], b = g.nei[f];
+                    if (cellPart[a] == rank) mine[b] = 1;
+                    if (cellPart[b] == rank) mine[a] = 1;
+                }
+                g.computeWallDistance(&mine);
+            }
+            lap("wall distance (own cells)");
             extractLocalMesh(g, cellPart, rank, nRanks, hm, part);
             lap("local sub-mesh");
             comm.initNccl(be, rank, nRanks, ncclUid);

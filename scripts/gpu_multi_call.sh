@@ -21,8 +21,10 @@ except Exception as e:
 PY
   grep -E "halo exchange|Error|error|Traceback" gpurun_out/${tag}_$1.err | sort | uniq -c | tail -5
 }
-run n${N}_weak_nccl DAB_P2P=0 "--scaling weak --no-solve"
-run n${N}_weak_p2p DAB_P2P=1 "--scaling weak --no-solve"
+if [ "$N" = "2" ]; then
+  run n${N}_weak_nccl DAB_P2P=0 "--scaling weak --no-solve"
+  run n${N}_weak_p2p DAB_P2P=1 "--scaling weak --no-solve"
+fi
 if [ "$SOLVE" = "solve" ]; then
   run n${N}_weak DAB_P2P=1 "--scaling weak"
   run n${N}_strong DAB_P2P=1 "--scaling strong"
