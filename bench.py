@@ -289,7 +289,7 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES leg of the adjoint solve (the reference's KSP)")
     ap.add_argument("--restart", type=int, default=1500)
-    ap.add_argument("--pc-level", type=int, default=3)
+    ap.add_argument("--pc-level", type=int, default=None, help="pcConLevel of dRdWTPC (default 3 on the 2-D O-grid, 2 on the 3-D wing: a level-3 ball holds 63 hexahedra)")
     ap.add_argument("--pc-block", type=int, default=0,
                     help="adjEqnOption.pcBlockCells: block-Jacobi ILU(0) with natural order inside blocks of that many cells (0: multicolour)")
     ap.add_argument("--coarse", type=int, default=2000)
@@ -322,6 +322,8 @@ def main():
 
     ncell_target = args.cells * (world if args.scaling == "weak" else 1)
     wing = args.mesh == "wing3d"
+    if args.pc_level is None:
+        args.pc_level = 2 if wing else 3
     if wing:
         ni, nj, nk = grid3_for(ncell_target)
         tile = TILE3
