@@ -288,6 +288,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES leg of the adjoint solve (the reference's KSP)")
+    ap.add_argument("--gmres-multi", action="store_true", help="run the GMRES leg on several GPUs too")
     ap.add_argument("--restart", type=int, default=1500)
     ap.add_argument("--pc-level", type=int, default=None, help="pcConLevel of dRdWTPC (default 3 on the 2-D O-grid, 2 on the 3-D wing: a level-3 ball holds 63 hexahedra)")
     ap.add_argument("--pc-block", type=int, default=0,
@@ -386,6 +387,7 @@ def main():
         pfail = sol.solvePrimal()
         ps = sol.primalStats
         sol.getOFFields(W)
+        sol.updateOFFields(W)  # the states the adjoint legs pass to calcJacTVecProduct are then the resident ones (no second assembly)
         primal = {"iterations": ps.iterations, "seconds": ps.seconds, "max_residual": ps.max_residual, "converged": int(ps.converged),
                   "fail": pfail, "p_iterations": ps.p_iterations, "ms_per_iteration": 1e3 * ps.seconds / max(ps.iterations, 1),
                   "CD": sol.calcFunction("CD")}
@@ -468,7 +470,7 @@ def main():
 
             psi_i, adjoint["idrs"] = leg("IDR(%d)" % args.idr_s, dict(kspType="idrs", idrS=args.idr_s, gmresMaxIters=3 * args.max_iters))
             best = adjoint["idrs"]
-            if not args.no_gmres:
+            if not args.no_gmres and (world == 1 or args.gmres_multi):  # the GMRES leg (25 s and a 110 GB basis at 1M cells) runs on one GPU only by default
                 free_b = torch.cuda.mem_get_info()[0]
                 m_fit = int(0.8 * free_b / (8.0 * n)) - 8
                 restart = max(30, min(args.restart, m_fit))
