@@ -327,6 +327,101 @@ def channel(nx=20, ny=10, nz=1, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.
                      np.concatenate(pf), defs, cc)
 
 
+def annular_passage(nr=4, nt=4, nz=6, r0=0.2, r1=0.35, lz=0.3, n_sectors=5, sectors=1, stagger=0.35, lean=0.15, bulge=0.08):
+    """Annular duct about the z axis, flow in +z: the shape of a turbomachinery passage (BASELINE config 5: DATurboFoam rotor,
+    `cyclic` sides, MRF).  One passage spans 2*pi/n_sectors; `sectors` consecutive passages are generated.
+
+    sectors < n_sectors: the two theta-sides are the patches `per_lo` / `per_hi`, type cyclic, transform rotational about z, face i of
+    one coupled to face i of the other (the OpenFOAM convention).  sectors == n_sectors: the closed ring, no cyclic patches -- the
+    periodic problem written out, which the parity tests use as the known answer for the cyclic mesh.
+    The grid lines are staggered in theta along z (`stagger`, blade-passage like), lean with the radius (`lean`) and bulge inside a
+    passage (`bulge`), the same way in every passage, so the mesh is non-orthogonal and skewed but exactly periodic.
+    Cells are numbered passage-major: cell = s * (nr*nt*nz) + (ir + nr * (it + nt * iz))."""
+    closed = sectors == n_sectors
+    if sectors > n_sectors:
+        raise ValueError("sectors > n_sectors")
+    dth = 2.0 * np.pi / n_sectors
+    NT = nt * sectors
+    ntp = NT if closed else NT + 1  # point columns in theta
+
+    def pid(i, j, k):
+        return i + (nr + 1) * ((j % ntp if closed else j) + ntp * k)
+
+    def cid(i, j, k):
+        s_, jl = j // nt, j % nt
+        return s_ * (nr * nt * nz) + i + nr * (jl + nt * k)
+
+    rr = np.linspace(0.0, 1.0, nr + 1)
+    zz = np.linspace(0.0, 1.0, nz + 1)
+    points = np.empty(((nr + 1) * ntp * (nz + 1), 3))
+    Ip, Jp, Kp = np.meshgrid(np.arange(nr + 1), np.arange(ntp), np.arange(nz + 1), indexing="ij")
+    Ip, Jp, Kp = Ip.ravel(), Jp.ravel(), Kp.ravel()
+    frac = (Jp % nt) / nt  # position inside the passage
+    th = (Jp // nt) * dth + frac * dth + stagger * dth * np.sin(0.5 * np.pi * zz[Kp]) + lean * dth * rr[Ip] \
+        + bulge * dth * np.sin(2.0 * np.pi * frac) * np.sin(np.pi * zz[Kp])
+    rad = r0 + (r1 - r0) * (rr[Ip] + 0.06 * np.sin(np.pi * rr[Ip]) * np.cos(2.0 * np.pi * frac))
+    zc = lz * (zz[Kp] + 0.05 * np.sin(np.pi * zz[Kp]) * np.sin(2.0 * np.pi * frac) * rr[Ip])
+    idx = pid(Ip, Jp, Kp)
+    points[idx, 0] = rad * np.cos(th)
+    points[idx, 1] = rad * np.sin(th)
+    points[idx, 2] = zc
+
+    I, J, K = np.meshgrid(np.arange(nr), np.arange(NT), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    corners = [pid(I + a, J + b, K + c) for a in (0, 1) for b in (0, 1) for c in (0, 1)]
+    cc = np.zeros((nr * NT * nz, 3))
+    cc[cid(I, J, K)] = sum(points[c] for c in corners) / 8.0
+
+    quads, ca, cb, pf = [], [], [], []
+
+    def add(q, a, b, patch):
+        quads.append(np.stack(q, axis=1))
+        ca.append(a)
+        cb.append(b)
+        pf.append(np.full(a.shape, patch, dtype=np.int64))
+
+    def rface(i, j, k):
+        return [pid(i, j, k), pid(i, j + 1, k), pid(i, j + 1, k + 1), pid(i, j, k + 1)]
+
+    def tface(i, j, k):
+        return [pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j, k + 1), pid(i, j, k + 1)]
+
+    def zface(i, j, k):
+        return [pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)]
+
+    none = lambda m: np.full(int(m.sum()), -1)
+    m = I >= 1
+    add(rface(I[m], J[m], K[m]), cid(I[m] - 1, J[m], K[m]), cid(I[m], J[m], K[m]), -1)
+    m = (J >= 1) | closed
+    add(tface(I[m], J[m], K[m]), cid(I[m], (J[m] - 1) % NT, K[m]), cid(I[m], J[m], K[m]), -1)
+    m = K >= 1
+    add(zface(I[m], J[m], K[m]), cid(I[m], J[m], K[m] - 1), cid(I[m], J[m], K[m]), -1)
+    m = K == 0
+    add(zface(I[m], J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 0)
+    m = K == nz - 1
+    add(zface(I[m], J[m], K[m] + 1), cid(I[m], J[m], K[m]), none(m), 1)
+    m = I == 0
+    add(rface(I[m], J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 2)
+    m = I == nr - 1
+    add(rface(I[m] + 1, J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 3)
+    defs = [("inlet", "patch"), ("outlet", "patch"), ("hub", "wall"), ("shroud", "wall")]
+    if not closed:
+        m = J == 0
+        add(tface(I[m], J[m], K[m]), cid(I[m], J[m], K[m]), none(m), 4)
+        m = J == NT - 1
+        add(tface(I[m], J[m] + 1, K[m]), cid(I[m], J[m], K[m]), none(m), 5)
+        defs += [("per_lo", "cyclic"), ("per_hi", "cyclic")]
+    quads = np.concatenate(quads).astype(np.int32)
+    mesh = _assemble(points, quads, np.concatenate(ca).astype(np.int64), np.concatenate(cb).astype(np.int64), np.concatenate(pf), defs, cc)
+    for pd in mesh.patches:
+        if pd["type"] == "cyclic":
+            pd.update(neighbourPatch="per_hi" if pd["name"] == "per_lo" else "per_lo", transform="rotational",
+                      rotationAxis=(0.0, 0.0, 1.0), rotationCentre=(0.0, 0.0, 0.0))
+    mesh.sector_angle = dth
+    mesh.cells_per_sector = nr * nt * nz
+    return mesh
+
+
 def prism_channel(nx=10, ny=6, lx=2.0, ly=0.5, lz=0.1, contraction=0.3, skew=0.15):
     """The convergent channel meshed with triangular prisms (every quad column split along its diagonal): cells with
     5 faces, triangular and quadrilateral faces -- exercises the general polyhedral paths of the engine."""
@@ -457,6 +552,15 @@ def write_polymesh(case_dir, mesh: PolyMesh, binary=False):
             f.write("    %s\n    {\n        type            %s;\n" % (p["name"], p["type"]))
             if p["type"] == "wall":
                 f.write("        inGroups        1(wall);\n")
+            if p["type"] == "cyclic":
+                f.write("        inGroups        1(cyclic);\n        neighbourPatch  %s;\n" % p["neighbourPatch"])
+                if p.get("transform"):
+                    f.write("        transform       %s;\n" % p["transform"])
+                if "rotationAxis" in p:
+                    f.write("        rotationAxis    (%.17g %.17g %.17g);\n" % tuple(p["rotationAxis"]))
+                    f.write("        rotationCentre  (%.17g %.17g %.17g);\n" % tuple(p.get("rotationCentre", (0.0, 0.0, 0.0))))
+                if "separationVector" in p:
+                    f.write("        separationVector (%.17g %.17g %.17g);\n" % tuple(p["separationVector"]))
             f.write("        nFaces          %d;\n        startFace       %d;\n    }\n" % (p["size"], p["start"]))
         f.write(")\n")
 
@@ -593,6 +697,29 @@ def default_bcs_channel(U0=(10.0, 0.0, 0.0), nuTilda0=4.5e-5, turbulent=True):
     return bcs
 
 
+def default_bcs_passage(Uin=(0.0, 0.0, 10.0), nuTilda0=4.5e-5, turbulent=True, cyclic=True):
+    """Annular passage (annular_passage): axial inflow, fixed-pressure outflow, hub and shroud walls, cyclic sides."""
+    Uin = tuple(float(x) for x in Uin)
+    cyc = {"per_lo": dict(type="cyclic"), "per_hi": dict(type="cyclic")} if cyclic else {}
+    wall0 = dict(type="fixedValue", value=(0.0, 0.0, 0.0))
+    bcs = {
+        "U": ("volVectorField", "[0 1 -1 0 0 0 0]", Uin, dict(
+            inlet=dict(type="fixedValue", value=Uin), outlet=dict(type="inletOutlet", inletValue=(0.0, 0.0, 0.0), value=Uin),
+            hub=dict(wall0), shroud=dict(wall0), **cyc)),
+        "p": ("volScalarField", "[0 2 -2 0 0 0 0]", 0.0, dict(
+            inlet=dict(type="zeroGradient"), outlet=dict(type="fixedValue", value=0.0),
+            hub=dict(type="zeroGradient"), shroud=dict(type="zeroGradient"), **cyc)),
+    }
+    if turbulent:
+        bcs["nuTilda"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, dict(
+            inlet=dict(type="fixedValue", value=nuTilda0), outlet=dict(type="zeroGradient"),
+            hub=dict(type="fixedValue", value=0.0), shroud=dict(type="fixedValue", value=0.0), **cyc))
+        bcs["nut"] = ("volScalarField", "[0 2 -1 0 0 0 0]", nuTilda0, dict(
+            inlet=dict(type="calculated", value=0.0), outlet=dict(type="calculated", value=0.0),
+            hub=dict(type="nutLowReWallFunction", value=0.0), shroud=dict(type="nutLowReWallFunction", value=0.0), **cyc))
+    return bcs
+
+
 def default_thermo(energy="sensibleInternalEnergy", transport="const", mu=1.8e-5, Pr=0.7, Prt=1.0, Cp=1005.0, molWeight=28.96,
                    divE="upwind", divEkp="upwind"):
     """thermophysicalProperties of the reference's DARhoSimpleFoam cases: hePsiThermo, pureMixture, perfectGas, hConst,
@@ -616,6 +743,8 @@ def compressible_bcs(bcs, U0mag=None, p0=101325.0, T0=300.0):
         ty = ub["type"]
         if ty == "symmetry":
             tb[pn] = dict(type="symmetry")
+        elif ty == "cyclic":
+            tb[pn] = dict(type="cyclic")
         elif ty == "inletOutlet":
             tb[pn] = dict(type="inletOutlet", inletValue=T0, value=T0)
         elif ty == "fixedValue" and any(abs(x) > 0 for x in ub["value"]):

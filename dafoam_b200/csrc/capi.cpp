@@ -413,11 +413,11 @@ int dab_get_local_to_global(dab_solver* s, int what, int64_t* out)
     need(out, "out");
     Solver& S = s->s;
     if (what == 0)
-        for (int c = 0; c < S.hm.nC; c++) out[c] = S.nRanks > 1 ? S.part.cellGlobal[c] : c;
+        for (int c = 0; c < S.hm.nC; c++) out[c] = S.partitioned ? S.part.cellGlobal[c] : c;
     else if (what == 1)
-        for (int f = 0; f < S.hm.nF; f++) out[f] = S.nRanks > 1 ? S.part.faceGlobal[f] : f;
+        for (int f = 0; f < S.hm.nF; f++) out[f] = S.partitioned ? S.part.faceGlobal[f] : f;
     else if (what == 2)
-        for (int f = 0; f < S.hm.nF; f++) out[f] = S.nRanks > 1 ? S.part.faceOwned[f] : 1;
+        for (int f = 0; f < S.hm.nF; f++) out[f] = S.partitioned ? S.part.faceOwned[f] : 1;
     else throw Error("dab_get_local_to_global: what must be 0 (cells), 1 (faces) or 2 (face ownership)");
     DAB_CATCH
 }

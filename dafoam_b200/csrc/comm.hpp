@@ -149,6 +149,31 @@ struct Comm
 };
 
 // ---- pack / unpack kernels ---------------------------------------------------------------------------------
+// component k of an exchanged item at `cell`, as the receiver must see it.  xs != 0: the value crosses a cyclic patch pair whose
+// transform is R = Rtab[|xs| - 1] (xs < 0: the inverse, R^T): 3-component items are vectors (v' = R v), 9-component items rank-2
+// tensors (T' = R T R^T; gradients and their adjoints), everything else is a scalar.  Role of OpenFOAM's
+// cyclicFvPatchField::patchNeighbourField -> transform(forwardT(), pnf).
+DAB_HD double haloValue(const double* arr, int64_t cell, int cellStride, int compStride, int ncomp, int k, int xs, const double* Rtab)
+{
+    const double* a = arr + cell * cellStride;
+    if (xs == 0 || (ncomp != 3 && ncomp != 9)) return a[(int64_t)k * compStride];
+    const double* M = Rtab + 9 * ((xs < 0 ? -xs : xs) - 1);
+    const bool inv = xs < 0;
+    if (ncomp == 3)
+    {
+        double v = 0.0;
+        for (int m = 0; m < 3; m++) v += (inv ? M[3 * m + k] : M[3 * k + m]) * a[(int64_t)m * compStride];
+        return v;
+    }
+    const int r = k / 3, c = k - 3 * r;
+    double v = 0.0;
+    for (int i = 0; i < 3; i++)
+    {
+        const double mri = inv ? M[3 * i + r] : M[3 * r + i];
+        for (int j = 0; j < 3; j++) v += mri * (inv ? M[3 * j + c] : M[3 * c + j]) * a[(int64_t)(3 * i + j) * compStride];
+    }
+    return v;
+}
 struct HaloPack
 {
     const double* arr;
@@ -158,11 +183,27 @@ struct HaloPack
     const int32_t* segCnt;  // [nSend] size of the element's peer segment
     int nSend, sumComp, compBase;
     double* buf;
+    const int32_t* xf = nullptr; // [nSend] signed cyclic transform of the element (nullptr: none anywhere)
+    const double* Rtab = nullptr;
     DAB_HD void operator()(int i) const
     {
         const int k = i / nSend, j = i - k * nSend;
         const int64_t o = (int64_t)segOff[j] * sumComp + (int64_t)(compBase + k) * segCnt[j] + (j - segOff[j]);
-        buf[o] = arr[(int64_t)idx[j] * cellStride + (int64_t)k * compStride];
+        buf[o] = haloValue(arr, idx[j], cellStride, compStride, ncomp, k, xf ? xf[j] : 0, Rtab);
+    }
+};
+// couplings of a rank with itself (cyclic patch pair inside one sub-mesh): ghost slot <- transformed value of the local cell
+struct SelfCopy
+{
+    double* arr;
+    int cellStride, compStride, ncomp;
+    const int32_t *src, *dst, *xf; // [n]; xf may be nullptr (faces)
+    int n;
+    const double* Rtab;
+    DAB_HD void operator()(int i) const
+    {
+        const int k = i / n, j = i - k * n;
+        arr[(int64_t)dst[j] * cellStride + (int64_t)k * compStride] = haloValue(arr, src[j], cellStride, compStride, ncomp, k, xf ? xf[j] : 0, Rtab);
     }
 };
 struct HaloUnpack
@@ -210,13 +251,15 @@ struct P2pPack
     P2pDst dst;
     const int32_t *idx, *segOff, *segCnt, *peerOf; // [nSend]
     int nSend;
+    const int32_t* xf;  // [nSend] signed cyclic transform (nullptr: none anywhere)
+    const double* Rtab;
     __device__ void operator()(int t) const
     {
         const int kk = t / nSend, j = t - kk * nSend;
         int a = 0;
         while (a + 1 < it.n && kk >= it.compBase[a + 1]) a++;
         const int k = kk - it.compBase[a];
-        const double v = it.arr[a][(int64_t)idx[j] * it.cellStride[a] + (int64_t)k * it.compStride[a]];
+        const double v = haloValue(it.arr[a], idx[j], it.cellStride[a], it.compStride[a], it.ncomp[a], k, xf ? xf[j] : 0, Rtab);
         dst.base[peerOf[j]][(int64_t)kk * segCnt[j] + (j - segOff[j])] = v;
     }
 };
@@ -268,6 +311,11 @@ struct HaloSet
     DevBuf<int32_t> dSendIdx, dSendSegOff, dSendSegCnt, dRecvIdx, dRecvSegOff, dRecvSegCnt;
     DevBuf<double> sendBuf, recvBuf;
     DevBuf<int32_t> dSendPeer; // [nSend] index of the element's peer
+    DevBuf<int32_t> dSendXf;   // [nSend] signed cyclic transform, allocated only when some element has one
+    const int32_t* xfPtr() const { return dSendXf.n ? dSendXf.p : nullptr; }
+    // couplings of the rank with itself (cyclic pairs inside the sub-mesh)
+    int nSelf = 0;
+    DevBuf<int32_t> dSelfSrc, dSelfDst, dSelfXf;
     long long epoch = 0;       // peer-memory path: exchanges done on this set (parity = epoch & 1)
     int capComp = 0;
 #ifndef DAB_HOSTSIM
@@ -275,8 +323,26 @@ struct HaloSet
 #endif
     bool pending = false;
 
-    void build(Backend& be, const std::vector<std::vector<int32_t>>& send, const std::vector<std::vector<int32_t>>& recv)
+    void buildSelf(Backend& be, const std::vector<int32_t>& src, const std::vector<int32_t>& dst, const std::vector<int32_t>& xf)
     {
+        if (src.size() != dst.size()) throw Error("cyclic self-coupling: send / receive lists differ in size");
+        nSelf = (int)src.size();
+        if (!nSelf) return;
+        dSelfSrc.upload(be, src);
+        dSelfDst.upload(be, dst);
+        if (!xf.empty()) dSelfXf.upload(be, xf);
+    }
+    void build(Backend& be, const std::vector<std::vector<int32_t>>& send, const std::vector<std::vector<int32_t>>& recv,
+               const std::vector<std::vector<int32_t>>* sendXf = nullptr)
+    {
+        if (sendXf)
+        {
+            std::vector<int32_t> sx;
+            bool any = false;
+            for (const auto& v : *sendXf)
+                for (int32_t x : v) { sx.push_back(x); any = any || x != 0; }
+            if (any) dSendXf.upload(be, sx);
+        }
         std::vector<int32_t> si, so, sc, ri, ro, rc, sp;
         for (size_t p = 0; p < send.size(); p++)
         {
@@ -468,7 +534,7 @@ struct Halo
             dst.base[p] = peerWin[p] + peerData[st][q][p] + (size_t)peerRecvOff[st][p] * sumComp;
             dst.flag[p] = (long long*)(peerWin[p] + peerFlag[st][q][p]) + myIdxInPeer[p];
         }
-        if (hs.nSend > 0) be->launch(hs.nSend * sumComp, P2pPack{it, dst, hs.dSendIdx.p, hs.dSendSegOff.p, hs.dSendSegCnt.p, hs.dSendPeer.p, hs.nSend});
+        if (hs.nSend > 0) be->launch(hs.nSend * sumComp, P2pPack{it, dst, hs.dSendIdx.p, hs.dSendSegOff.p, hs.dSendSegCnt.p, hs.dSendPeer.p, hs.nSend, hs.xfPtr(), dRtab.p});
         p2pSignal<<<1, 32, 0, be->stream>>>(dst, nP, hs.epoch);
         const int n = hs.nRecv * sumComp;
         if (n > 0)
@@ -483,22 +549,44 @@ struct Halo
     bool useP2P(const std::vector<HaloItem>& items, int sumComp) const { return p2p && sumComp <= P2P_CAP && (int)items.size() <= P2P_MAXITEMS; }
 #endif
 
-    void build(Backend& b, Comm& c, const HaloPlan& plan)
+    DevBuf<double> dRtab; // rotation matrices of the cyclic transforms, 9 doubles each
+    bool remote() const { return comm && comm->active(); }
+    bool any() const { return remote() || cells.nSelf > 0 || faces.nSelf > 0; }
+
+    void build(Backend& b, Comm& c, const HaloPlan& plan, const std::vector<HostMesh::CycXf>& xforms)
     {
         be = &b;
         comm = &c;
         peers = plan.peers;
+        std::vector<double> R(9 * xforms.size() + 1, 0.0);
+        for (size_t k = 0; k < xforms.size(); k++)
+            for (int a = 0; a < 9; a++) R[9 * k + a] = xforms[k].R[a];
+        dRtab.upload(b, R);
         std::vector<std::vector<int32_t>> recvCells(plan.peers.size());
         for (size_t p = 0; p < plan.peers.size(); p++)
             for (int i = 0; i < plan.recvCellCount[p]; i++) recvCells[p].push_back(plan.recvCellStart[p] + i);
-        cells.build(b, plan.sendCells, recvCells);
+        cells.build(b, plan.sendCells, recvCells, &plan.sendXf);
         faces.build(b, plan.sendFaces, plan.recvFaces);
+        std::vector<int32_t> selfDst;
+        for (int i = 0; i < plan.selfRecvCount; i++) selfDst.push_back(plan.selfRecvStart + i);
+        cells.buildSelf(b, plan.selfSendCells, selfDst, plan.selfSendXf);
+        faces.buildSelf(b, plan.selfSendFaces, plan.selfRecvFaces, {});
         setupP2P();
+    }
+
+    // ghost slots of the rank's own cyclic images: on the launching stream, in order with the producers of the values
+    void runSelf(HaloSet& hs, const std::vector<HaloItem>& items)
+    {
+        if (hs.nSelf == 0) return;
+        for (const auto& it : items)
+            be->launch(hs.nSelf * it.ncomp, SelfCopy{it.arr, it.cellStride, it.compStride, it.ncomp, hs.dSelfSrc.p, hs.dSelfDst.p,
+                                                     hs.dSelfXf.n ? hs.dSelfXf.p : nullptr, hs.nSelf, dRtab.p});
     }
 
     void run(HaloSet& hs, const std::vector<HaloItem>& items)
     {
-        if (!comm || !comm->active()) return;
+        runSelf(hs, items);
+        if (!remote()) return;
         int sumComp = 0;
         for (const auto& it : items) sumComp += it.ncomp;
 #if !defined(DAB_HOSTSIM) && defined(DAB_WITH_NCCL)
@@ -514,7 +602,7 @@ struct Halo
         for (const auto& it : items)
         {
             be->launch(hs.nSend * it.ncomp, HaloPack{it.arr, it.cellStride, it.compStride, it.ncomp, hs.dSendIdx.p, hs.dSendSegOff.p,
-                                                     hs.dSendSegCnt.p, hs.nSend, sumComp, base, hs.sendBuf.p});
+                                                     hs.dSendSegCnt.p, hs.nSend, sumComp, base, hs.sendBuf.p, hs.xfPtr(), dRtab.p});
             base += it.ncomp;
         }
         std::vector<const double*> sb;
@@ -544,10 +632,11 @@ struct Halo
     // launches work that does not touch ghost slots in between and calls finish() before the work that does
     void start(HaloSet& hs, const std::vector<HaloItem>& items)
     {
-        if (!comm || !comm->active()) return;
 #ifdef DAB_HOSTSIM
         run(hs, items);
 #else
+        runSelf(hs, items);
+        if (!remote()) return;
         if (!hs.evPack)
         {
             cudaEventCreateWithFlags(&hs.evPack, cudaEventDisableTiming);
@@ -574,7 +663,7 @@ struct Halo
         for (const auto& it : items)
         {
             be->launch(hs.nSend * it.ncomp, HaloPack{it.arr, it.cellStride, it.compStride, it.ncomp, hs.dSendIdx.p, hs.dSendSegOff.p,
-                                                     hs.dSendSegCnt.p, hs.nSend, sumComp, base, hs.sendBuf.p});
+                                                     hs.dSendSegCnt.p, hs.nSend, sumComp, base, hs.sendBuf.p, hs.xfPtr(), dRtab.p});
             base += it.ncomp;
         }
         cudaEventRecord(hs.evPack, be->stream);

@@ -407,6 +407,10 @@ struct PatchDef
 {
     std::string name, type;
     int start, size;
+    // cyclic patches (OpenFOAM cyclicPolyPatch entries of constant/polyMesh/boundary)
+    std::string neighbourPatch, transform; // transform: rotational | translational | (empty / unknown / noOrdering: from the geometry)
+    double rotationAxis[3] = {0, 0, 0}, rotationCentre[3] = {0, 0, 0}, separationVector[3] = {0, 0, 0};
+    bool hasAxis = false, hasSeparation = false;
 };
 
 inline std::vector<PatchDef> readBoundary(const std::string& path)
@@ -430,6 +434,14 @@ inline std::vector<PatchDef> readBoundary(const std::string& path)
         pd.type = p.word("type");
         pd.start = atoi(p.word("startFace").c_str());
         pd.size = atoi(p.word("nFaces").c_str());
+        if (pd.type == "cyclic")
+        {
+            pd.neighbourPatch = p.word("neighbourPatch");
+            pd.transform = p.wordOr("transform", "");
+            if (p.has("rotationAxis")) { p.uniform("rotationAxis", pd.rotationAxis); pd.hasAxis = true; }
+            if (p.has("rotationCentre")) p.uniform("rotationCentre", pd.rotationCentre);
+            if (p.has("separationVector")) { p.uniform("separationVector", pd.separationVector); pd.hasSeparation = true; }
+        }
         out.push_back(pd);
     }
     return out;

@@ -29,6 +29,29 @@ struct HostMesh
     int maxCF = 0;
     std::vector<int32_t> cellFaces;      // ELL: [k*nC + c] = (f<<1)|isNeighbour, -1 padding
     std::vector<int32_t> cellNbr;        // ELL: the cell across that face, -1 on boundary faces / padding
+    // cyclic (periodic) patch pairs are merged into internal faces when the mesh is read (mergeCyclics): the owner is the cell on the
+    // first patch of the pair, the neighbour the cell on the second one, and cyc[f] = k > 0 names the transform that maps the
+    // neighbour's side into the owner's frame (positions x' = R x + t, vectors v' = R v).  The local mesh of a rank holds such a
+    // neighbour as a ghost cell whose copies are transformed on the way (partition.hpp, comm.hpp), so no kernel knows about it.
+    struct CycXf { double R[9]; double t[3]; };
+    std::vector<int32_t> cyc;            // per internal face (global mesh only); empty = no cyclic faces
+    std::vector<CycXf> xforms;           // transform k is xforms[k - 1]
+    bool hasCyclic() const { return !xforms.empty(); }
+    static void xfPoint(const CycXf& X, bool inverse, const double* x, double* y)
+    {
+        if (!inverse)
+            for (int a = 0; a < 3; a++) y[a] = X.R[3 * a] * x[0] + X.R[3 * a + 1] * x[1] + X.R[3 * a + 2] * x[2] + X.t[a];
+        else
+        {
+            const double d[3] = {x[0] - X.t[0], x[1] - X.t[1], x[2] - X.t[2]};
+            for (int a = 0; a < 3; a++) y[a] = X.R[a] * d[0] + X.R[3 + a] * d[1] + X.R[6 + a] * d[2];
+        }
+    }
+    static void xfVector(const CycXf& X, bool inverse, const double* v, double* y)
+    {
+        for (int a = 0; a < 3; a++)
+            y[a] = inverse ? X.R[a] * v[0] + X.R[3 + a] * v[1] + X.R[6 + a] * v[2] : X.R[3 * a] * v[0] + X.R[3 * a + 1] * v[1] + X.R[3 * a + 2] * v[2];
+    }
     // geometry (SoA)
     std::vector<double> Sf[3], Cf[3], corr[3]; // per face
     std::vector<double> magSf, w, delta;       // per face (w = 1 on boundary faces)
@@ -42,7 +65,183 @@ struct HostMesh
         readLabelList(pm + "owner", own);
         readLabelList(pm + "neighbour", nei);
         patches = readBoundary(pm + "boundary");
+        mergeCyclics();
         finalizeTopology();
+    }
+
+    // centre and area vector of face f from its points (OpenFOAM primitiveMeshFaceCentresAndAreas)
+    void faceGeom(int f, double* cf, double* sf) const
+    {
+        const double* P = points.data();
+        const int n = fOff[f + 1] - fOff[f];
+        const int32_t* l = &fLab[fOff[f]];
+        if (n == 3)
+        {
+            for (int k = 0; k < 3; k++) cf[k] = (P[3 * l[0] + k] + P[3 * l[1] + k] + P[3 * l[2] + k]) / 3.0;
+            double a[3], b[3];
+            for (int k = 0; k < 3; k++) { a[k] = P[3 * l[1] + k] - P[3 * l[0] + k]; b[k] = P[3 * l[2] + k] - P[3 * l[0] + k]; }
+            sf[0] = 0.5 * (a[1] * b[2] - a[2] * b[1]); sf[1] = 0.5 * (a[2] * b[0] - a[0] * b[2]); sf[2] = 0.5 * (a[0] * b[1] - a[1] * b[0]);
+            return;
+        }
+        double est[3] = {0, 0, 0};
+        for (int i = 0; i < n; i++)
+            for (int k = 0; k < 3; k++) est[k] += P[3 * l[i] + k];
+        for (int k = 0; k < 3; k++) est[k] /= n;
+        double sumN[3] = {0, 0, 0}, sumAc[3] = {0, 0, 0}, sumA = 0.0;
+        for (int i = 0; i < n; i++)
+        {
+            const double* p0 = &P[3 * l[i]];
+            const double* p1 = &P[3 * l[(i + 1) % n]];
+            double a[3], b[3], nn[3], c[3];
+            for (int k = 0; k < 3; k++) { a[k] = p1[k] - p0[k]; b[k] = est[k] - p0[k]; c[k] = p0[k] + p1[k] + est[k]; }
+            nn[0] = a[1] * b[2] - a[2] * b[1]; nn[1] = a[2] * b[0] - a[0] * b[2]; nn[2] = a[0] * b[1] - a[1] * b[0];
+            double an = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+            for (int k = 0; k < 3; k++) { sumN[k] += nn[k]; sumAc[k] += an * c[k]; }
+            sumA += an;
+        }
+        for (int k = 0; k < 3; k++) { cf[k] = (1.0 / 3.0) / sumA * sumAc[k]; sf[k] = 0.5 * sumN[k]; }
+    }
+
+    // Cyclic patch pairs -> internal faces (OpenFOAM cyclicPolyPatch: face i of a patch is coupled to face i of its neighbourPatch;
+    // DAFoam counts both sides as coupled boundary faces with a phi state each, reference src/adjoint/DAIndex/DAIndex.C:151-167 --
+    // here a pair shares ONE face and one phi state, like the cut faces between ranks).  The transform is taken from the geometry of
+    // the two patches (translation: mean offset of the face centres; rotation: angle about rotationAxis / rotationCentre that maps
+    // the second patch onto the first) and checked on every face pair.
+    void mergeCyclics()
+    {
+        std::vector<int> isCyc(patches.size(), 0);
+        bool any = false;
+        for (size_t p = 0; p < patches.size(); p++)
+            if (patches[p].type == "cyclic") { isCyc[p] = 1; any = true; }
+        if (!any) return;
+        const int nF0 = (int)own.size(), nIF0 = (int)nei.size();
+        auto patchIndex = [&](const std::string& n) {
+            for (size_t p = 0; p < patches.size(); p++)
+                if (patches[p].name == n) return (int)p;
+            throw Error("polyMesh: cyclic neighbourPatch " + n + " not found");
+        };
+        std::vector<int32_t> newOwn(own.begin(), own.begin() + nIF0), newNei(nei), newCyc(nIF0, 0);
+        std::vector<int> faceOrder(nIF0);
+        for (int f = 0; f < nIF0; f++) faceOrder[f] = f;
+        double scale = 0.0;
+        for (size_t i = 0; i < points.size(); i++) scale = std::max(scale, std::fabs(points[i]));
+        for (size_t p = 0; p < patches.size(); p++)
+        {
+            if (!isCyc[p]) continue;
+            const int q = patchIndex(patches[p].neighbourPatch);
+            if (!isCyc[q] || patches[q].neighbourPatch != patches[p].name) throw Error("polyMesh: cyclic patches " + patches[p].name + " / " + patches[q].name + " do not name each other");
+            if ((int)p > q) continue; // handled with its partner
+            if ((int)p == q) throw Error("polyMesh: cyclic patch " + patches[p].name + " is its own neighbour");
+            const PatchDef &A = patches[p], &B = patches[q];
+            if (A.size != B.size) throw Error("polyMesh: cyclic patches " + A.name + " / " + B.name + " differ in size");
+            const int n = A.size;
+            std::vector<double> cA((size_t)3 * n), sA((size_t)3 * n), cB((size_t)3 * n), sB((size_t)3 * n);
+            for (int i = 0; i < n; i++)
+            {
+                faceGeom(A.start + i, &cA[3 * (size_t)i], &sA[3 * (size_t)i]);
+                faceGeom(B.start + i, &cB[3 * (size_t)i], &sB[3 * (size_t)i]);
+            }
+            CycXf X;
+            for (int a = 0; a < 9; a++) X.R[a] = (a % 4 == 0) ? 1.0 : 0.0;
+            for (int a = 0; a < 3; a++) X.t[a] = 0.0;
+            bool rotational = A.transform == "rotational";
+            if (A.transform != "rotational" && A.transform != "translational" && A.hasAxis && n > 0)
+            {
+                // unknown / noOrdering: coupled faces of a translation have opposite area vectors
+                double dev = 0.0, mag = 0.0;
+                for (int i = 0; i < 3 * n; i++) { dev = std::max(dev, std::fabs(sA[i] + sB[i])); mag = std::max(mag, std::fabs(sA[i])); }
+                rotational = dev > 1e-6 * mag;
+            }
+            if (rotational)
+            {
+                if (!A.hasAxis) throw Error("polyMesh: rotational cyclic patch " + A.name + " without rotationAxis");
+                double ax[3] = {A.rotationAxis[0], A.rotationAxis[1], A.rotationAxis[2]};
+                const double an = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+                if (!(an > 0.0)) throw Error("polyMesh: zero rotationAxis on " + A.name);
+                for (int a = 0; a < 3; a++) ax[a] /= an;
+                const double* c0 = A.rotationCentre;
+                // angle that takes the second patch onto the first: area-weighted mean over the face pairs
+                double sumW = 0.0, sumTh = 0.0;
+                for (int i = 0; i < n; i++)
+                {
+                    double rA[3], rB[3], dA = 0.0, dB = 0.0;
+                    for (int a = 0; a < 3; a++) { rA[a] = cA[3 * (size_t)i + a] - c0[a]; rB[a] = cB[3 * (size_t)i + a] - c0[a]; dA += rA[a] * ax[a]; dB += rB[a] * ax[a]; }
+                    for (int a = 0; a < 3; a++) { rA[a] -= dA * ax[a]; rB[a] -= dB * ax[a]; }
+                    const double cr[3] = {rB[1] * rA[2] - rB[2] * rA[1], rB[2] * rA[0] - rB[0] * rA[2], rB[0] * rA[1] - rB[1] * rA[0]};
+                    const double sn = cr[0] * ax[0] + cr[1] * ax[1] + cr[2] * ax[2], cs = rA[0] * rB[0] + rA[1] * rB[1] + rA[2] * rB[2];
+                    const double wgt = std::sqrt(rA[0] * rA[0] + rA[1] * rA[1] + rA[2] * rA[2]) * std::sqrt(rB[0] * rB[0] + rB[1] * rB[1] + rB[2] * rB[2]);
+                    if (!(wgt > 0.0)) continue;
+                    sumW += wgt;
+                    sumTh += wgt * std::atan2(sn, cs);
+                }
+                if (!(sumW > 0.0)) throw Error("polyMesh: cannot determine the rotation angle of cyclic patch " + A.name);
+                const double th = sumTh / sumW, c = std::cos(th), s1 = std::sin(th), C1 = 1.0 - c;
+                const double x = ax[0], y = ax[1], z = ax[2];
+                const double R[9] = {c + x * x * C1, x * y * C1 - z * s1, x * z * C1 + y * s1,
+                                     y * x * C1 + z * s1, c + y * y * C1, y * z * C1 - x * s1,
+                                     z * x * C1 - y * s1, z * y * C1 + x * s1, c + z * z * C1};
+                for (int a = 0; a < 9; a++) X.R[a] = R[a];
+                for (int a = 0; a < 3; a++) X.t[a] = c0[a] - (R[3 * a] * c0[0] + R[3 * a + 1] * c0[1] + R[3 * a + 2] * c0[2]);
+            }
+            else
+            {
+                double t[3] = {0, 0, 0};
+                for (int i = 0; i < n; i++)
+                    for (int a = 0; a < 3; a++) t[a] += cA[3 * (size_t)i + a] - cB[3 * (size_t)i + a];
+                for (int a = 0; a < 3; a++) X.t[a] = n ? t[a] / n : 0.0;
+            }
+            // every coupled pair must map onto each other: centres coincide, area vectors are opposite
+            for (int i = 0; i < n; i++)
+            {
+                double y[3], v[3];
+                xfPoint(X, false, &cB[3 * (size_t)i], y);
+                xfVector(X, false, &sB[3 * (size_t)i], v);
+                double mA = 0.0;
+                for (int a = 0; a < 3; a++) mA = std::max(mA, std::fabs(sA[3 * (size_t)i + a]));
+                for (int a = 0; a < 3; a++)
+                    if (std::fabs(y[a] - cA[3 * (size_t)i + a]) > 1e-6 * scale || std::fabs(v[a] + sA[3 * (size_t)i + a]) > 1e-6 * mA)
+                        throw Error("polyMesh: faces " + std::to_string(i) + " of cyclic patches " + A.name + " / " + B.name
+                                    + " do not match under the patch transform (ordering or transform entry)");
+            }
+            xforms.push_back(X);
+            const int k = (int)xforms.size();
+            for (int i = 0; i < n; i++)
+            {
+                newOwn.push_back(own[A.start + i]);
+                newNei.push_back(own[B.start + i]);
+                newCyc.push_back(k);
+                faceOrder.push_back(A.start + i);
+            }
+        }
+        const int nIF1 = (int)newNei.size();
+        std::vector<PatchDef> newPatches;
+        for (size_t p = 0; p < patches.size(); p++)
+        {
+            if (isCyc[p]) continue;
+            PatchDef pd = patches[p];
+            pd.start = (int)faceOrder.size();
+            for (int i = 0; i < patches[p].size; i++)
+            {
+                faceOrder.push_back(patches[p].start + i);
+                newOwn.push_back(own[patches[p].start + i]);
+            }
+            newPatches.push_back(pd);
+        }
+        (void)nF0;
+        std::vector<int32_t> nOff(1, 0), nLab;
+        nLab.reserve(fLab.size());
+        for (int f : faceOrder)
+        {
+            for (int i = fOff[f]; i < fOff[f + 1]; i++) nLab.push_back(fLab[i]);
+            nOff.push_back((int32_t)nLab.size());
+        }
+        fOff.swap(nOff);
+        fLab.swap(nLab);
+        own.swap(newOwn);
+        nei.swap(newNei);
+        cyc.swap(newCyc);
+        patches.swap(newPatches);
+        (void)nIF1;
     }
 
     void finalizeTopology()
@@ -109,54 +308,35 @@ struct HostMesh
             Sf[k].assign(nF, 0.0); Cf[k].assign(nF, 0.0); corr[k].assign(nF, 0.0); C[k].assign(nC, 0.0);
         }
         magSf.assign(nF, 0.0); w.assign(nF, 1.0); delta.assign(nF, 0.0); V.assign(nC, 0.0);
-        const double* P = points.data();
         for (int f = 0; f < nF; f++)
         {
-            const int n = fOff[f + 1] - fOff[f];
-            const int32_t* l = &fLab[fOff[f]];
             double cf[3], sf[3];
-            if (n == 3)
-            {
-                for (int k = 0; k < 3; k++) cf[k] = (P[3 * l[0] + k] + P[3 * l[1] + k] + P[3 * l[2] + k]) / 3.0;
-                double a[3], b[3];
-                for (int k = 0; k < 3; k++) { a[k] = P[3 * l[1] + k] - P[3 * l[0] + k]; b[k] = P[3 * l[2] + k] - P[3 * l[0] + k]; }
-                sf[0] = 0.5 * (a[1] * b[2] - a[2] * b[1]); sf[1] = 0.5 * (a[2] * b[0] - a[0] * b[2]); sf[2] = 0.5 * (a[0] * b[1] - a[1] * b[0]);
-            }
-            else
-            {
-                double est[3] = {0, 0, 0};
-                for (int i = 0; i < n; i++)
-                    for (int k = 0; k < 3; k++) est[k] += P[3 * l[i] + k];
-                for (int k = 0; k < 3; k++) est[k] /= n;
-                double sumN[3] = {0, 0, 0}, sumAc[3] = {0, 0, 0}, sumA = 0.0;
-                for (int i = 0; i < n; i++)
-                {
-                    const double* p0 = &P[3 * l[i]];
-                    const double* p1 = &P[3 * l[(i + 1) % n]];
-                    double a[3], b[3], nn[3], c[3];
-                    for (int k = 0; k < 3; k++) { a[k] = p1[k] - p0[k]; b[k] = est[k] - p0[k]; c[k] = p0[k] + p1[k] + est[k]; }
-                    nn[0] = a[1] * b[2] - a[2] * b[1]; nn[1] = a[2] * b[0] - a[0] * b[2]; nn[2] = a[0] * b[1] - a[1] * b[0];
-                    double an = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-                    for (int k = 0; k < 3; k++) { sumN[k] += nn[k]; sumAc[k] += an * c[k]; }
-                    sumA += an;
-                }
-                for (int k = 0; k < 3; k++) { cf[k] = (1.0 / 3.0) / sumA * sumAc[k]; sf[k] = 0.5 * sumN[k]; }
-            }
+            faceGeom(f, cf, sf);
             for (int k = 0; k < 3; k++) { Cf[k][f] = cf[k]; Sf[k][f] = sf[k]; }
             magSf[f] = std::sqrt(sf[0] * sf[0] + sf[1] * sf[1] + sf[2] * sf[2]);
         }
+        // face centre / area vector as the cell on `side` sees them: the neighbour of a cyclic face lives in its own frame
+        auto sideGeom = [&](int f, int side, double* cf, double* sf) {
+            for (int k = 0; k < 3; k++) { cf[k] = Cf[k][f]; sf[k] = Sf[k][f]; }
+            if (side == 1 && f < (int)cyc.size() && cyc[f] > 0)
+            {
+                const CycXf& X = xforms[cyc[f] - 1];
+                double c0[3] = {cf[0], cf[1], cf[2]}, s0[3] = {sf[0], sf[1], sf[2]};
+                xfPoint(X, true, c0, cf);
+                xfVector(X, true, s0, sf);
+            }
+        };
         std::vector<double> est((size_t)3 * nC, 0.0);
         std::vector<int> cnt(nC, 0);
         for (int f = 0; f < nF; f++)
-        {
-            for (int k = 0; k < 3; k++) est[3 * (size_t)own[f] + k] += Cf[k][f];
-            cnt[own[f]]++;
-            if (f < nIF)
+            for (int side = 0; side < (f < nIF ? 2 : 1); side++)
             {
-                for (int k = 0; k < 3; k++) est[3 * (size_t)nei[f] + k] += Cf[k][f];
-                cnt[nei[f]]++;
+                const int c = side == 0 ? own[f] : nei[f];
+                double cf[3], sf[3];
+                sideGeom(f, side, cf, sf);
+                for (int k = 0; k < 3; k++) est[3 * (size_t)c + k] += cf[k];
+                cnt[c]++;
             }
-        }
         for (int c = 0; c < nC; c++)
             for (int k = 0; k < 3; k++) est[3 * (size_t)c + k] /= cnt[c];
         for (int f = 0; f < nF; f++)
@@ -164,10 +344,12 @@ struct HostMesh
             for (int side = 0; side < (f < nIF ? 2 : 1); side++)
             {
                 const int c = side == 0 ? own[f] : nei[f];
+                double cf[3], sf[3];
+                sideGeom(f, side, cf, sf);
                 double pyr3 = 0.0;
                 for (int k = 0; k < 3; k++)
-                    pyr3 += Sf[k][f] * (side == 0 ? (Cf[k][f] - est[3 * (size_t)c + k]) : (est[3 * (size_t)c + k] - Cf[k][f]));
-                for (int k = 0; k < 3; k++) C[k][c] += pyr3 * (0.75 * Cf[k][f] + 0.25 * est[3 * (size_t)c + k]);
+                    pyr3 += sf[k] * (side == 0 ? (cf[k] - est[3 * (size_t)c + k]) : (est[3 * (size_t)c + k] - cf[k]));
+                for (int k = 0; k < 3; k++) C[k][c] += pyr3 * (0.75 * cf[k] + 0.25 * est[3 * (size_t)c + k]);
                 V[c] += pyr3;
             }
         }
@@ -183,12 +365,18 @@ struct HostMesh
             if (f < nIF)
             {
                 const int o = own[f], n = nei[f];
+                double Cn[3] = {C[0][n], C[1][n], C[2][n]};
+                if (f < (int)cyc.size() && cyc[f] > 0)
+                {
+                    const double c0[3] = {Cn[0], Cn[1], Cn[2]};
+                    xfPoint(xforms[cyc[f] - 1], false, c0, Cn); // the neighbour's centre in the owner's frame
+                }
                 double dO = 0.0, dN = 0.0, d[3], nd = 0.0, md = 0.0;
                 for (int k = 0; k < 3; k++)
                 {
                     dO += Sf[k][f] * (Cf[k][f] - C[k][o]);
-                    dN += Sf[k][f] * (C[k][n] - Cf[k][f]);
-                    d[k] = C[k][n] - C[k][o];
+                    dN += Sf[k][f] * (Cn[k] - Cf[k][f]);
+                    d[k] = Cn[k] - C[k][o];
                     nd += nh[k] * d[k];
                     md += d[k] * d[k];
                 }
@@ -222,10 +410,20 @@ struct HostMesh
             if (patchGeom[bPatch[b]] == PG_WALL) wf.push_back(nIF + b);
         if (wf.empty()) return;
         // k-d tree over the wall-face centres (median splits, implicit layout), exact nearest-neighbour query
-        const int nw = (int)wf.size();
+        // cyclic patches: the nearest wall face may be the periodic image of one (one layer of images on either side of every pair)
+        const int nImg = 1 + 2 * (int)xforms.size();
+        const int nw = (int)wf.size() * nImg;
         std::vector<double> pts((size_t)3 * nw);
-        for (int i = 0; i < nw; i++)
-            for (int k = 0; k < 3; k++) pts[3 * (size_t)i + k] = Cf[k][wf[i]];
+        for (size_t i = 0; i < wf.size(); i++)
+        {
+            const double c0[3] = {Cf[0][wf[i]], Cf[1][wf[i]], Cf[2][wf[i]]};
+            for (int k = 0; k < 3; k++) pts[3 * (nImg * i) + k] = c0[k];
+            for (size_t x = 0; x < xforms.size(); x++)
+            {
+                xfPoint(xforms[x], false, c0, &pts[3 * (nImg * i + 1 + 2 * x)]);
+                xfPoint(xforms[x], true, c0, &pts[3 * (nImg * i + 2 + 2 * x)]);
+            }
+        }
         std::vector<int> idx(nw), axisOf(nw, 0);
         for (int i = 0; i < nw; i++) idx[i] = i;
         struct Range { int lo, hi, depth; };

@@ -8,6 +8,7 @@
 #include "mesh.hpp"
 #include <algorithm>
 #include <numeric>
+#include <cstdlib>
 
 namespace dab
 {
@@ -19,6 +20,12 @@ struct HaloPlan
     std::vector<int> recvCellStart, recvCellCount; // per peer: contiguous ghost slots [start, start+count)
     std::vector<std::vector<int32_t>> sendFaces; // per peer: local faces whose phi this rank owns and the peer needs
     std::vector<std::vector<int32_t>> recvFaces; // per peer: local (foreign) faces filled from the peer
+    // cyclic patches: per peer and send cell, the signed transform the value undergoes on the way (0: none; +k: R_k v; -k: R_k^T v)
+    std::vector<std::vector<int32_t>> sendXf;
+    // couplings of this rank with itself (both cells of a cyclic face pair owned here): plain local copies, same ordering rules
+    std::vector<int32_t> selfSendCells, selfSendXf, selfSendFaces, selfRecvFaces;
+    int selfRecvStart = 0, selfRecvCount = 0;
+    bool hasSelf() const { return selfRecvCount > 0 || !selfRecvFaces.empty(); }
 };
 
 struct Partition
@@ -68,17 +75,25 @@ inline void rcbPartition(const HostMesh& g, int nParts, std::vector<int>& part)
 }
 
 // build the local mesh of `rank` from the global mesh (geometry and wall distance already computed)
+//
+// Cyclic faces (g.cyc[f] = k > 0, mesh.hpp) are cut faces as well, also when both cells belong to this rank: the owner-side cell sees
+// the neighbour as a ghost holding the neighbour's values transformed by +k, the neighbour-side cell sees the owner as a ghost
+// transformed by -k, and the face appears twice in the local mesh -- once with the owner's geometry and the phi state (type B), once
+// in the neighbour's frame as a foreign face filled by the face exchange (type D).  Reference role: cyclicFvPatchField::
+// patchNeighbourField + the `transform()` of coupled patches inside every fvc:: operator; coupled-face indexing DAIndex.C:151-167.
 inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, int rank, int nRanks, HostMesh& l, Partition& P)
 {
     P.rank = rank;
     P.nRanks = nRanks;
     P.nGlobalCells = g.nC;
+    const bool anyCyc = g.hasCyclic();
+    auto cycOf = [&](int f) { return anyCyc ? g.cyc[f] : 0; };
     std::vector<int32_t> g2l(g.nC, -1);
-    // owned cells: first the interior ones (no neighbour on another rank), then the ones along the cuts, each group
+    // owned cells: first the interior ones (no ghost neighbour), then the ones along the cuts, each group
     // in global order -- kernels can then run the interior range while the ghost exchange is in flight
     std::vector<uint8_t> onCut(g.nC, 0);
     for (int f = 0; f < g.nIF; f++)
-        if (part[g.own[f]] != part[g.nei[f]])
+        if (part[g.own[f]] != part[g.nei[f]] || cycOf(f) != 0)
         {
             onCut[g.own[f]] = 1;
             onCut[g.nei[f]] = 1;
@@ -94,54 +109,90 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
             }
         if (pass == 0) l.nInterior = nC;
     }
-    // ghost cells grouped by owning rank, then global id
-    std::vector<std::pair<int, int>> ghosts; // (rank, global)
+    // ghost cells: (source rank, transform, global id); grouped by rank (this rank's own cyclic images last), then transform, then id
+    struct Key
+    {
+        int q, xs, c;
+        bool operator<(const Key& o) const { return q != o.q ? q < o.q : (xs != o.xs ? xs < o.xs : c < o.c); }
+        bool operator==(const Key& o) const { return q == o.q && xs == o.xs && c == o.c; }
+    };
+    auto rankKey = [&](int q) { return q == rank ? nRanks : q; }; // self sorts after every peer
+    std::vector<Key> ghosts, sends; // sends: (destination rank, transform at the receiver, my global cell)
     for (int f = 0; f < g.nIF; f++)
     {
-        const int a = g.own[f], b = g.nei[f];
-        if (part[a] == rank && part[b] != rank) ghosts.emplace_back(part[b], b);
-        if (part[b] == rank && part[a] != rank) ghosts.emplace_back(part[a], a);
+        const int a = g.own[f], b = g.nei[f], k = cycOf(f);
+        if (k == 0)
+        {
+            if (part[a] == rank && part[b] != rank) { ghosts.push_back({rankKey(part[b]), 0, b}); sends.push_back({rankKey(part[b]), 0, a}); }
+            if (part[b] == rank && part[a] != rank) { ghosts.push_back({rankKey(part[a]), 0, a}); sends.push_back({rankKey(part[a]), 0, b}); }
+        }
+        else
+        {
+            if (part[a] == rank) { ghosts.push_back({rankKey(part[b]), +k, b}); sends.push_back({rankKey(part[b]), -k, a}); }
+            if (part[b] == rank) { ghosts.push_back({rankKey(part[a]), -k, a}); sends.push_back({rankKey(part[a]), +k, b}); }
+        }
     }
     std::sort(ghosts.begin(), ghosts.end());
     ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+    std::sort(sends.begin(), sends.end());
+    sends.erase(std::unique(sends.begin(), sends.end()), sends.end());
     int nT = nC;
-    for (auto& pr : ghosts)
+    std::vector<int> ghostXs; // per ghost (index - nC)
+    auto ghostSlot = [&](int q, int xs, int c) {
+        const Key key{rankKey(q), xs, c};
+        return nC + (int)(std::lower_bound(ghosts.begin(), ghosts.end(), key) - ghosts.begin());
+    };
+    P.halo.selfRecvStart = nC;
+    for (const Key& gk : ghosts)
     {
-        if (P.halo.peers.empty() || P.halo.peers.back() != pr.first)
+        if (gk.q == nRanks)
         {
-            P.halo.peers.push_back(pr.first);
-            P.halo.recvCellStart.push_back(nT);
-            P.halo.recvCellCount.push_back(0);
+            if (P.halo.selfRecvCount == 0) P.halo.selfRecvStart = nT;
+            P.halo.selfRecvCount++;
         }
-        g2l[pr.second] = nT++;
-        P.cellGlobal.push_back(pr.second);
-        P.halo.recvCellCount.back()++;
+        else
+        {
+            if (P.halo.peers.empty() || P.halo.peers.back() != gk.q)
+            {
+                P.halo.peers.push_back(gk.q);
+                P.halo.recvCellStart.push_back(nT);
+                P.halo.recvCellCount.push_back(0);
+            }
+            P.halo.recvCellCount.back()++;
+        }
+        nT++;
+        P.cellGlobal.push_back(gk.c);
+        ghostXs.push_back(gk.xs);
     }
     const int nPeers = (int)P.halo.peers.size();
     auto peerIndex = [&](int q) { return (int)(std::lower_bound(P.halo.peers.begin(), P.halo.peers.end(), q) - P.halo.peers.begin()); };
-    // cells to send: owned cells adjacent to a cell of peer q (sorted by global id = local order)
+    // cells to send, in the order the receiver lists its ghosts (transform, then global id)
     P.halo.sendCells.assign(nPeers, {});
+    P.halo.sendXf.assign(nPeers, {});
+    for (const Key& sk : sends)
     {
-        std::vector<std::pair<int, int>> snd; // (peer, local cell)
-        for (int f = 0; f < g.nIF; f++)
+        if (sk.q == nRanks)
         {
-            const int a = g.own[f], b = g.nei[f];
-            if (part[a] == rank && part[b] != rank) snd.emplace_back(part[b], g2l[a]);
-            if (part[b] == rank && part[a] != rank) snd.emplace_back(part[a], g2l[b]);
+            P.halo.selfSendCells.push_back(g2l[sk.c]);
+            P.halo.selfSendXf.push_back(sk.xs);
         }
-        // the peer lists its ghosts by global id: send in the same order
-        std::sort(snd.begin(), snd.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
-            return a.first != b.first ? a.first < b.first : P.cellGlobal[a.second] < P.cellGlobal[b.second];
-        });
-        snd.erase(std::unique(snd.begin(), snd.end()), snd.end());
-        for (auto& pr : snd) P.halo.sendCells[peerIndex(pr.first)].push_back(pr.second);
+        else
+        {
+            P.halo.sendCells[peerIndex(sk.q)].push_back(g2l[sk.c]);
+            P.halo.sendXf[peerIndex(sk.q)].push_back(sk.xs);
+        }
     }
-    // faces: A (both owned), B (owner mine, neighbour ghost), D (owner ghost, neighbour mine), then boundary by patch
+    // faces: A (both owned, not cyclic), B (owner mine, neighbour ghost), D (owner ghost, neighbour mine), then boundary by patch
     std::vector<int> fa, fb, fd;
     for (int f = 0; f < g.nIF; f++)
     {
         const bool oa = part[g.own[f]] == rank, ob = part[g.nei[f]] == rank;
-        if (oa && ob) fa.push_back(f);
+        if (cycOf(f) != 0)
+        {
+            if (oa) fb.push_back(f);
+            if (ob) fd.push_back(f);
+        }
+        else if (oa && ob) fa.push_back(f);
         else if (oa) fb.push_back(f);
         else if (ob) fd.push_back(f);
     }
@@ -149,6 +200,7 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
     lf.insert(lf.end(), fb.begin(), fb.end());
     lf.insert(lf.end(), fd.begin(), fd.end());
     const int nIF = (int)lf.size();
+    const int nA = (int)fa.size(), nB = (int)fb.size();
     l.patches.clear();
     for (size_t p = 0; p < g.patches.size(); p++)
     {
@@ -168,15 +220,22 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
     P.faceOwned.assign(nF, 1);
     P.halo.sendFaces.assign(nPeers, {});
     P.halo.recvFaces.assign(nPeers, {});
-    for (int i = 0; i < nIF; i++)
+    for (int i = nA; i < nIF; i++)
     {
         const int f = lf[i];
         const int ra = part[g.own[f]], rb = part[g.nei[f]];
-        if (ra == rank && rb != rank) P.halo.sendFaces[peerIndex(rb)].push_back(i); // B: ascending global id
-        if (ra != rank && rb == rank)
+        if (i < nA + nB)
         {
+            // B: ascending global id
+            if (rb == rank) P.halo.selfSendFaces.push_back(i);
+            else P.halo.sendFaces[peerIndex(rb)].push_back(i);
+        }
+        else
+        {
+            // D: ascending global id
             P.faceOwned[i] = 0;
-            P.halo.recvFaces[peerIndex(ra)].push_back(i); // D: ascending global id
+            if (ra == rank) P.halo.selfRecvFaces.push_back(i);
+            else P.halo.recvFaces[peerIndex(ra)].push_back(i);
         }
     }
     // topology
@@ -190,11 +249,26 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
     for (int i = 0; i < nF; i++)
     {
         const int f = lf[i];
-        l.own[i] = g2l[g.own[f]];
-        if (i < nIF) l.nei[i] = g2l[g.nei[f]];
+        const int k = i < nIF ? cycOf(f) : 0;
+        if (i < nA || i >= nIF)
+        {
+            l.own[i] = g2l[g.own[f]];
+            if (i < nIF) l.nei[i] = g2l[g.nei[f]];
+        }
+        else if (i < nA + nB)
+        {
+            l.own[i] = g2l[g.own[f]];
+            l.nei[i] = ghostSlot(part[g.nei[f]], k, g.nei[f]);
+        }
+        else
+        {
+            l.own[i] = ghostSlot(part[g.own[f]], -k, g.own[f]);
+            l.nei[i] = g2l[g.nei[f]];
+        }
         for (int q = g.fOff[f]; q < g.fOff[f + 1]; q++) l.fLab.push_back(g.fLab[q]);
         l.fOff.push_back((int32_t)l.fLab.size());
     }
+    l.xforms = g.xforms;
     l.patchGeom = g.patchGeom;
     l.bPatch.assign(l.nBF, -1);
     for (size_t p = 0; p < l.patches.size(); p++)
@@ -223,13 +297,31 @@ inline void extractLocalMesh(const HostMesh& g, const std::vector<int>& part, in
     for (int i = 0; i < nF; i++)
     {
         const int f = lf[i];
-        for (int k = 0; k < 3; k++) { l.Sf[k][i] = g.Sf[k][f]; l.Cf[k][i] = g.Cf[k][f]; l.corr[k][i] = g.corr[k][f]; }
+        double sf[3] = {g.Sf[0][f], g.Sf[1][f], g.Sf[2][f]}, cf[3] = {g.Cf[0][f], g.Cf[1][f], g.Cf[2][f]};
+        double co[3] = {g.corr[0][f], g.corr[1][f], g.corr[2][f]};
+        if (i >= nA + nB && i < nIF && cycOf(f) != 0)
+        {
+            // the neighbour-side copy of a cyclic face: geometry in the neighbour's frame
+            const HostMesh::CycXf& X = g.xforms[cycOf(f) - 1];
+            const double s0[3] = {sf[0], sf[1], sf[2]}, c0[3] = {cf[0], cf[1], cf[2]}, o0[3] = {co[0], co[1], co[2]};
+            HostMesh::xfVector(X, true, s0, sf);
+            HostMesh::xfPoint(X, true, c0, cf);
+            HostMesh::xfVector(X, true, o0, co);
+        }
+        for (int k = 0; k < 3; k++) { l.Sf[k][i] = sf[k]; l.Cf[k][i] = cf[k]; l.corr[k][i] = co[k]; }
         l.magSf[i] = g.magSf[f]; l.w[i] = g.w[f]; l.delta[i] = g.delta[f];
     }
     for (int c = 0; c < nT; c++)
     {
         const int gc = P.cellGlobal[c];
-        for (int k = 0; k < 3; k++) l.C[k][c] = g.C[k][gc];
+        double cc[3] = {g.C[0][gc], g.C[1][gc], g.C[2][gc]};
+        const int xs = c >= nC ? ghostXs[c - nC] : 0;
+        if (xs != 0)
+        {
+            const double c0[3] = {cc[0], cc[1], cc[2]};
+            HostMesh::xfPoint(g.xforms[std::abs(xs) - 1], xs < 0, c0, cc);
+        }
+        for (int k = 0; k < 3; k++) l.C[k][c] = cc[k];
         l.V[c] = g.V[gc];
         l.yWall[c] = g.yWall[gc];
     }

@@ -185,6 +185,8 @@ struct Solver
     Params par;
     std::string solverName, caseDirectory;
     int rank = 0, nRanks = 1;
+    bool partitioned = false; // the local mesh has ghost cells: several ranks, or cyclic patches (whose images are ghosts even on one rank)
+    bool ghosted() const { return partitioned; }
     // options
     int gmresRestart = 1000, gmresMaxIters = 1000, useMGSO = 0, pcFillLevel = 0, printInfo = 0;
     std::string kspType = "gmres"; // adjEqnOption.kspType (extension): gmres (the reference's KSP) | idrs (IDR(s), short recurrences)
@@ -304,10 +306,11 @@ struct Solver
             if (setupInfo) fprintf(stderr, "[dab200] setup %-28s %.3f s (rank %d)\n", what, std::chrono::duration<double>(now - tPrev).count(), rank);
             tPrev = now;
         };
-        if (nRanks == 1)
+        hm.read(caseDir);
+        lap("read polyMesh");
+        partitioned = nRanks > 1 || hm.hasCyclic();
+        if (!partitioned)
         {
-            hm.read(caseDir);
-            lap("read polyMesh");
             hm.computeGeometry();
             lap("geometry");
             hm.computeWallDistance();
@@ -316,10 +319,10 @@ struct Solver
         }
         else
         {
-            // every rank reads the whole case, partitions it identically (RCB) and keeps its own sub-mesh
+            // every rank reads the whole case, partitions it identically (RCB) and keeps its own sub-mesh; a mesh with cyclic patches
+            // takes this route on one rank too (the periodic images of its cells are ghost cells, partition.hpp)
             HostMesh g;
-            g.read(caseDir);
-            lap("read polyMesh (global)");
+            std::swap(g, hm);
             g.computeGeometry();
             lap("geometry (global)");
             std::vector<int> cellPart;
@@ -340,8 +343,8 @@ struct Solver
             lap("wall distance (own cells)");
             extractLocalMesh(g, cellPart, rank, nRanks, hm, part);
             lap("local sub-mesh");
-            comm.initNccl(be, rank, nRanks, ncclUid);
-            halo.build(be, comm, part.halo);
+            if (nRanks > 1) comm.initNccl(be, rank, nRanks, ncclUid);
+            halo.build(be, comm, part.halo, hm.xforms);
             lap("NCCL + halo plans");
         }
         if ((int)hm.patches.size() > MAXP) throw Error("too many patches");
@@ -428,7 +431,7 @@ struct Solver
         if (!found) throw Error("cannot find MRF cellZone " + mrf.zone);
         const int nT = hm.nCtot, nIF = hm.nIF;
         mrf.cell.assign(nT, 0);
-        for (int c = 0; c < nT; c++) mrf.cell[c] = gmask[nRanks > 1 ? (size_t)part.cellGlobal[c] : (size_t)c];
+        for (int c = 0; c < nT; c++) mrf.cell[c] = gmask[partitioned ? (size_t)part.cellGlobal[c] : (size_t)c];
         mrf.type.assign(hm.nBF, 0);
         mrf.faceIn.assign(hm.nF, 0);
         for (int f = 0; f < nIF; f++)
@@ -1081,7 +1084,7 @@ struct Solver
         // still comes from global memory, one or two CTAs per SM) -- they stay a tested option (DAB_TILE=1), not the default
         const char* env = getenv("DAB_TILE");
         if (!env || atoi(env) == 0) return;
-        if (nRanks > 1 || par.comp || mrf.on || hm.nC < 64) return;
+        if (partitioned || par.comp || mrf.on || hm.nC < 64) return;
         std::vector<int> cand;
         if (tileCellsHint > 0) cand.push_back(tileCellsHint);
         for (int t : {192, 176, 168, 160, 144, 128, 112, 96, 80, 64, 48, 32}) cand.push_back(t);
@@ -1341,7 +1344,7 @@ struct Solver
                 if (vals.size() < (size_t)nc * part.nGlobalCells) throw Error("internalField of " + name + " has the wrong size");
                 for (int c = 0; c < nT; c++)
                 {
-                    const size_t gc = nRanks > 1 ? (size_t)part.cellGlobal[c] : (size_t)c;
+                    const size_t gc = partitioned ? (size_t)part.cellGlobal[c] : (size_t)c;
                     for (int k = 0; k < nc; k++) out[(size_t)nc * c + k] = vals[(size_t)nc * gc + k];
                 }
             }
@@ -1388,7 +1391,7 @@ struct Solver
             }
         }
         // a flux field written by a previous run (writeFields / OpenFOAM's own phi) takes precedence over the interpolated one
-        if (nRanks == 1 && fileExists(caseDirectory + "/" + timeName + "/phi"))
+        if (!partitioned && fileExists(caseDirectory + "/" + timeName + "/phi"))
         {
             Dict d = readDict(caseDirectory + "/" + timeName + "/phi");
             auto listOf = [&](const std::vector<std::string>& t, size_t n, std::vector<double>& out) {
@@ -1456,7 +1459,7 @@ struct Solver
     // ghost cells <- owners (U, p, nuTilda) and foreign cut faces <- owners (phi)
     void exchangeStates()
     {
-        if (!comm.active()) return;
+        if (!ghosted()) return;
         const int nT = hm.nCtot;
         std::vector<HaloItem> it{{dU.p, 3, 3, 1}, {dP.p, 1, 1, nT}};
         if (par.turb) it.push_back({dNt.p, 1, 1, nT});
@@ -1546,7 +1549,7 @@ struct Solver
         {
             // DARhoSimpleFoam: closures + gradients, momentum/SA rows, energy row, pressure/flux rows (comp_kernels.hpp)
             DAB_LAUNCH_NF(hm.nCtot, cFwdA, mv, par, sv, rv); // closures of the ghost cells come from their exchanged states
-            if (exchange && comm.active())
+            if (exchange && ghosted())
             {
                 std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}, {rv.gHe, 3, 1, nT}};
                 if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
@@ -1554,7 +1557,7 @@ struct Solver
             }
             DAB_LAUNCH_NF(hm.nC, cFwdB, mv, par, sv, rv, isPC, Rdev);
             DAB_LAUNCH_NF(hm.nC, cFwdE, mv, par, sv, rv, isPC, Rdev);
-            if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
+            if (exchange && ghosted()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
             if (isPC && par.transonic)
             {
                 Params pq = par; // div(pc) scheme and transonicPCOption for the preconditioner residual
@@ -1567,14 +1570,14 @@ struct Solver
             return;
         }
         DAB_LAUNCH_NF(hm.nCtot, FwdA, mv, par, sv, rv);
-        if (exchange && comm.active())
+        if (exchange && ghosted())
         {
             std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};
             if (par.turb) it.push_back({rv.gNt, 3, 1, nT});
             halo.exchangeCells(it);
         }
         DAB_LAUNCH_NFF(hm.nC, FwdB, mv, par, sv, rv, isPC, Rdev);
-        if (exchange && comm.active()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
+        if (exchange && ghosted()) halo.exchangeCells({{rv.rAU, 1, 1, nT}, {rv.HbyA, 3, 1, nT}, {rv.flag, 1, 1, nT}});
         DAB_LAUNCH_NF(hm.nC, FwdC, mv, par, sv, rv, Rdev);
     }
 
@@ -1601,7 +1604,7 @@ struct Solver
         PsiView v;
         v.U = x;
         v.T = nullptr;
-        if (!comm.active())
+        if (!ghosted())
         {
             v.p = x + 3 * nC;
             v.T = par.comp ? x + 4 * nC : nullptr;
@@ -1648,10 +1651,10 @@ struct Solver
             const PsiView pv = psiView(x);
             const int nTc = hm.nCtot;
             DAB_LAUNCH_NF(hm.nC, cRevA, mv, par, sv, rv, av, pv);
-            if (comm.active()) halo.exchangeCells({{av.mt, 3, 1, nTc}, {av.Dn, 1, 1, nTc}, {av.gPb, 3, 1, nTc}});
+            if (ghosted()) halo.exchangeCells({{av.mt, 3, 1, nTc}, {av.Dn, 1, 1, nTc}, {av.gPb, 3, 1, nTc}});
             DAB_LAUNCH_NF(hm.nC, cRevB, mv, par, sv, rv, av, pv, y);
             DAB_LAUNCH_NF(hm.nC, cRevE, mv, par, sv, rv, av, pv, y);
-            if (comm.active())
+            if (ghosted())
             {
                 std::vector<HaloItem> it{{av.gUb, 9, 1, nTc}, {av.gHeb, 3, 1, nTc}};
                 if (par.turb) it.push_back({av.gNtb, 3, 1, nTc});
@@ -1661,7 +1664,7 @@ struct Solver
             return;
         }
         const int nT = hm.nCtot;
-        if (!comm.active())
+        if (!ghosted())
         {
             const PsiView pv = psiView(x);
             if (tileProduct())
@@ -1730,7 +1733,7 @@ struct Solver
     void benchKernel(int which)
     {
         PsiView pv;
-        if (comm.active() && psiP.n >= (size_t)hm.nCtot)
+        if (ghosted() && psiP.n >= (size_t)hm.nCtot)
         {
             pv.U = dX.p; pv.p = psiP.p; pv.nt = psiN.p; pv.phi = psiPhi.p; pv.T = psiT.n ? psiT.p : nullptr;
         }
@@ -1755,7 +1758,7 @@ struct Solver
             else if (which == 1) launchTileBC(pv, dY2.p);
             return;
         }
-        if (comm.active())
+        if (ghosted())
         {
             if (which == 0) launchRevA(pv);
             else if (which == 1) DAB_LAUNCH_NFF(hm.nC, RevB, mv, par, sv, rv, av, pv, dY2.p);
@@ -1854,7 +1857,7 @@ struct Solver
             {
                 double sdot = 0.0;
                 for (size_t i = 0; i < n; i++) sdot += psi[i] * (Rp[i] - Rm[i]);
-                if (comm.active())
+                if (ghosted())
                 {
                     be.h2d(dY2.p, &sdot, sizeof(double));
                     comm.allreduceSum(be, dY2.p, 1);
@@ -1911,7 +1914,7 @@ struct Solver
         double refb[3] = {0, 0, 0};
         for (int k = 0; k < 3; k++)
             for (size_t c = 0; c < nC; c++) refb[k] += part[k * nC + c];
-        if (comm.active())
+        if (ghosted())
         {
             be.h2d(aBcRefb.p, refb, 3 * sizeof(double));
             comm.allreduceSum(be, aBcRefb.p, 3);
@@ -1946,7 +1949,7 @@ struct Solver
             double a = 0.0;
             for (int p : f.patches)
                 for (int i = 0; i < hm.patches[p].size; i++) a += hm.magSf[hm.patches[p].start + i];
-            if (comm.active())
+            if (ghosted())
             {
                 Solver* self = const_cast<Solver*>(this);
                 if (self->dFacePart.n < 1) self->dFacePart.alloc(self->be, hm.nBF + 1);
@@ -2039,7 +2042,7 @@ struct Solver
         be.d2h(facePart.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
         double s = 0.0;
         for (int b = 0; b < hm.nBF; b++) s += facePart[b];
-        if (comm.active())
+        if (ghosted())
         {
             be.h2d(dFacePart.p, &s, sizeof(double));
             comm.allreduceSum(be, dFacePart.p, 1);
@@ -2084,7 +2087,7 @@ struct Solver
         // deterministic host summation in face order (the all-reduce of the reference, DAFunctionForce.C:146)
         double s = 0.0;
         for (int b = 0; b < hm.nBF; b++) s += facePart[b];
-        if (comm.active())
+        if (ghosted())
         {
             be.h2d(dFacePart.p, &s, sizeof(double));
             comm.allreduceSum(be, dFacePart.p, 1);
@@ -2107,7 +2110,7 @@ struct Solver
         be.d2h(facePart.data(), dFacePart.p, (size_t)hm.nBF * sizeof(double));
         double s = 0.0;
         for (int b = 0; b < hm.nBF; b++) s += facePart[b];
-        if (comm.active())
+        if (ghosted())
         {
             be.h2d(dFacePart.p, &s, sizeof(double));
             comm.allreduceSum(be, dFacePart.p, 1);
@@ -2133,7 +2136,7 @@ struct Solver
                 be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
                 be.zero(av.gHeb, (size_t)3 * hm.nCtot * sizeof(double));
                 DAB_LAUNCH_NF(hm.nC, cForceRevA, mv, par, sv, rv, av, specs[g], seed);
-                if (comm.active()) halo.exchangeCells({{av.gUb, 9, 1, hm.nCtot}});
+                if (ghosted()) halo.exchangeCells({{av.gUb, 9, 1, hm.nCtot}});
                 DAB_LAUNCH_NF(hm.nC, cRevC, mv, par, sv, rv, av, dY2.p);
                 be.zero(dY2.p + (size_t)nCellStates() * hm.nC, (size_t)hm.nF * sizeof(double)); // no face-flux dependence
                 if (g == 0)
@@ -2152,7 +2155,7 @@ struct Solver
         be.zero(av.gPb, (size_t)3 * hm.nCtot * sizeof(double));
         be.zero(av.gNtb, (size_t)3 * hm.nCtot * sizeof(double));
         DAB_LAUNCH_NF(hm.nC, ForceRevA, mv, par, sv, rv, av, forceSpec(f), seed);
-        if (comm.active())
+        if (ghosted())
         {
             std::vector<HaloItem> it{{av.gUb, 9, 1, hm.nCtot}};
             halo.exchangeCells(it);
@@ -2165,7 +2168,7 @@ struct Solver
     // ASCII vol/surface fields of a state-layout vector under <case>/<timeName>/<prefix><state>; one GPU
     void writeStateVector(const std::string& timeName, const std::string& prefix, const double* W) const
     {
-        if (comm.active()) throw Error("field output runs on one GPU in this build");
+        if (ghosted()) throw Error("field output needs an undecomposed mesh without cyclic patches in this build");
         const std::string dir = caseDirectory + "/" + timeName;
         ::mkdir(dir.c_str(), 0755);
         const int nC = hm.nC, nIF = hm.nIF;
@@ -2237,7 +2240,7 @@ struct Solver
     // boundary patches fixedValue zero
     void writeSensMapField(const std::string& name, const double* v, bool vector, const std::string& timeName) const
     {
-        if (comm.active()) throw Error("field output runs on one GPU in this build");
+        if (ghosted()) throw Error("field output needs an undecomposed mesh without cyclic patches in this build");
         const std::string dir = caseDirectory + "/" + timeName;
         ::mkdir(dir.c_str(), 0755);
         FILE* f = fopen((dir + "/" + name).c_str(), "w");
@@ -2262,7 +2265,7 @@ struct Solver
     // Returns the norm of the closest distances the reference prints.
     double writeSensMapSurface(const std::string& name, const double* dFdXs, const double* Xs, int size, const std::string& timeName) const
     {
-        if (comm.active()) throw Error("field output runs on one GPU in this build");
+        if (ghosted()) throw Error("field output needs an undecomposed mesh without cyclic patches in this build");
         const int nS = (int)std::lround(size / 3.0);
         if (nS <= 0) throw Error("writeSensMapSurface: empty surface");
         std::vector<double> sens((size_t)3 * hm.nBF, 0.0);
@@ -2325,7 +2328,7 @@ struct Solver
     // writeMeshPoints (pyDASolvers.pyx:388-392) / writeCurrentMeshPointsToConstant / writeFailedMesh: <case>/<dirName>/polyMesh/points
     void writeMeshPoints(const double* pts, const std::string& dirName) const
     {
-        if (comm.active()) throw Error("mesh output runs on one GPU in this build");
+        if (ghosted()) throw Error("mesh output needs an undecomposed mesh without cyclic patches in this build");
         const std::string d1 = caseDirectory + "/" + dirName, d2 = d1 + "/polyMesh";
         ::mkdir(d1.c_str(), 0755);
         ::mkdir(d2.c_str(), 0755);

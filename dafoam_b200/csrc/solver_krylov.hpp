@@ -597,7 +597,7 @@ inline void Solver::coarseSetup()
     Cs.lu.assign((size_t)Kg * Kg, 0.0);
     ensureRecorded();
     int nProbes = 0;
-    if (nRanks == 1 && coarseProbeReach > 0 && nAgg > 64)
+    if (!partitioned && coarseProbeReach > 0 && nAgg > 64)
     {
         // Coloured probing (one GPU): the transposed Jacobian couples a pressure DOF to residual rows at most `coarseProbeReach` cell
         // levels away, far less than an aggregate's diameter, so aggregates whose reach sets N(a) (the aggregates within that many

@@ -72,8 +72,8 @@ inline const double* Solver::primalSums(int k) { return primal.ops->dots(primal.
 inline void Solver::primalResidual(const EqnView& e, const double* x, const double* g, double* res)
 {
     const int nC = hm.nC;
-    const double nG = comm.active() ? (double)part.nGlobalCells : (double)nC;
-    if (comm.active()) halo.exchangeCells({{const_cast<double*>(x), e.nc, e.nc == 3 ? 3 : 1, e.nc == 3 ? 1 : hm.nCtot}});
+    const double nG = ghosted() ? (double)part.nGlobalCells : (double)nC;
+    if (ghosted()) halo.exchangeCells({{const_cast<double*>(x), e.nc, e.nc == 3 ? 3 : 1, e.nc == 3 ? 1 : hm.nCtot}});
     be.launch(nC, StridedCopy{x, e.nc, e.nc, nC, primal.red.p});
     const double* s = primalSums(e.nc);
     if (e.nc == 3)
@@ -108,16 +108,16 @@ inline void Solver::primalJacobi(const EqnView& e, double* x, double* tmp, const
             if (e.nc == 3)
             {
                 be.launch(nC, JacobiSweep<3>{e, x, tmp, g, mv.V, hm.nCtot});
-                if (comm.active()) halo.exchangeCells({{tmp, 3, 3, 1}});
+                if (ghosted()) halo.exchangeCells({{tmp, 3, 3, 1}});
                 be.launch(nC, JacobiSweep<3>{e, tmp, x, g, mv.V, hm.nCtot});
-                if (comm.active()) halo.exchangeCells({{x, 3, 3, 1}});
+                if (ghosted()) halo.exchangeCells({{x, 3, 3, 1}});
             }
             else
             {
                 be.launch(nC, JacobiSweep<1>{e, x, tmp, g, mv.V, hm.nCtot});
-                if (comm.active()) halo.exchangeCells({{tmp, 1, 1, hm.nCtot}});
+                if (ghosted()) halo.exchangeCells({{tmp, 1, 1, hm.nCtot}});
                 be.launch(nC, JacobiSweep<1>{e, tmp, x, g, mv.V, hm.nCtot});
-                if (comm.active()) halo.exchangeCells({{x, 1, 1, hm.nCtot}});
+                if (ghosted()) halo.exchangeCells({{x, 1, 1, hm.nCtot}});
             }
         }
         primalResidual(e, x, g, res);
@@ -215,7 +215,7 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
     res0 = r1[0];
     if (res0 < ctl.tol) return 0;
     // norm factor once (OpenFOAM keeps it fixed during the solve)
-    if (comm.active()) halo.exchangeCells({{x, 1, 1, hm.nCtot}});
+    if (ghosted()) halo.exchangeCells({{x, 1, 1, hm.nCtot}});
     be.launch(nC, SpmvEll{e, x, P.q.p});
     be.launch(nC, ResidualOf{e.b, P.q.p, P.r.p});
     be.launch(nC, PcgProducts{P.r.p, P.r.p, P.r.p, P.red.p, P.red.p + nC});
@@ -231,7 +231,7 @@ inline int Solver::primalPcg(const EqnView& e, double* x, const SegControl& ctl,
         P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 0);
         be.launch(1, PcgScalarBeta{S, it == 0 ? 1 : 0});
         be.launch(nC, PcgUpdate2{S, P.z.p, P.d.p});
-        if (comm.active()) halo.exchangeCells({{P.d.p, 1, 1, hm.nCtot}});
+        if (ghosted()) halo.exchangeCells({{P.d.p, 1, 1, hm.nCtot}});
         be.launch(nC, SpmvEllProd{e, P.d.p, P.q.p, P.red.p});
         P.ops->dotsDev(P.red.p, nC, 1, P.ones.p, nC, S + 2);
         be.launch(1, PcgScalarAlpha{S});
@@ -267,7 +267,7 @@ inline int Solver::solvePrimal(PrimalStats& st)
     double maxRes = 0.0;
     int it = 0;
     EqnView eE{nC, hm.maxCF, 1, P.eOff.p, P.eDiag.p, P.eB.p, mv.cellNbr};
-    const bool mr = comm.active();
+    const bool mr = ghosted();
     auto exGrad = [&]() {
         if (!mr) return;
         std::vector<HaloItem> it{{rv.gU, 9, 1, nT}, {rv.gP, 3, 1, nT}};

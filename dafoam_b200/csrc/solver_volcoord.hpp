@@ -29,7 +29,7 @@ inline void Solver::uploadGeometry()
 // new point coordinates (the wall distance stays frozen: meshWaveFrozen)
 inline void Solver::updateMesh(const double* pts)
 {
-    if (comm.active()) throw Error("updateOFMesh runs on one GPU in this build");
+    if (ghosted()) throw Error("updateOFMesh runs on one GPU in this build");
     std::copy(pts, pts + hm.points.size(), hm.points.begin());
     hm.computeGeometry();
     uploadGeometry();
@@ -41,7 +41,7 @@ inline void Solver::volCoordSetup()
 {
     VolCoord& Vc = volc;
     if (Vc.ready) return;
-    if (comm.active()) throw Error("the volCoord input runs on one GPU in this build");
+    if (ghosted()) throw Error("the volCoord input runs on one GPU in this build");
     const int nC = hm.nC, nF = hm.nF, nP = hm.nP;
     // cells around each point
     std::vector<int> pcOff(nP + 1, 0), pcList;

@@ -1,0 +1,264 @@
+"""Cyclic (periodic) patch pairs: one passage of an annular duct with `cyclic` sides against the closed ring of n passages.
+
+The reference couples the two patches of a pair through cyclicFvPatchField (neighbour values rotated by the patch transform inside
+every fvc:: operator) and counts the coupled faces as states (reference src/adjoint/DAIndex/DAIndex.C:151-167); BASELINE config 5
+(DATurboFoam rotor passage) needs them.  Known answer: the periodic problem written out -- the same passage repeated n times around
+the axis, closed into a ring, NO cyclic patch anywhere, evaluated by the oracle.  With a state that repeats from passage to passage
+(vectors rotated by the passage angle), the residual rows of passage 0 and the rows of [dR/dW]^T psi of passage 0 must be the ones
+the engine computes on the single passage with cyclic sides.
+"""
+import tempfile
+
+import numpy as np
+import pytest
+
+from dafoam_b200 import cases
+from dafoam_b200.pyDASolvers import pyDASolvers
+from oracle.pyoracle import Oracle
+from tests.common import HOSTSIM, NORM_STATES, ALL_RES, rel_err
+
+N_SECTORS = 5
+
+
+def merged_faces(mesh):
+    """Face numbering of the engine on a mesh with cyclic patches (mesh.hpp mergeCyclics): internal faces, one face per coupled
+    pair (owner = the cell on the first patch of the pair), the remaining boundary faces patch by patch.
+    Returns owner, neighbour (-1: boundary), patch name per face ('' for internal)."""
+    nIF = mesh.n_internal_faces
+    own, nei, pname = list(mesh.owner[:nIF]), list(mesh.neighbour), [""] * nIF
+    names = [p["name"] for p in mesh.patches]
+    for pi, p in enumerate(mesh.patches):
+        if p["type"] != "cyclic":
+            continue
+        qi = names.index(p["neighbourPatch"])
+        if qi < pi:
+            continue
+        q = mesh.patches[qi]
+        for i in range(p["size"]):
+            own.append(mesh.owner[p["start"] + i])
+            nei.append(mesh.owner[q["start"] + i])
+            pname.append("")
+    for p in mesh.patches:
+        if p["type"] == "cyclic":
+            continue
+        for i in range(p["size"]):
+            own.append(mesh.owner[p["start"] + i])
+            nei.append(-1)
+            pname.append(p["name"])
+    return np.array(own), np.array(nei), pname
+
+
+def rotz(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+
+
+class Pair:
+    """One passage with cyclic sides (engine) and the ring of N_SECTORS passages (oracle), with the maps between them."""
+
+    def __init__(self, turbulent=True, divU="linearUpwind", lib_path=HOSTSIM, dims=(4, 4, 6), mrf_omega=None, extra=None):
+        nr, nt, nz = dims
+        self.turb = turbulent
+        self.sec = cases.annular_passage(nr=nr, nt=nt, nz=nz, n_sectors=N_SECTORS, sectors=1)
+        self.full = cases.annular_passage(nr=nr, nt=nt, nz=nz, n_sectors=N_SECTORS, sectors=N_SECTORS)
+        self.nCs = self.sec.n_cells
+        bs = cases.default_bcs_passage(turbulent=turbulent, cyclic=True)
+        bf = cases.default_bcs_passage(turbulent=turbulent, cyclic=False)
+        div_u = "bounded Gauss %s%s" % (divU, " grad(U)" if divU.startswith("linearUpwind") else "")
+        d = tempfile.mkdtemp(prefix="dab_cyc_")
+        kw = {}
+        self.mrf_s = self.mrf_f = None
+        if mrf_omega is not None:
+            self.mrf_s = dict(cellZone="rotor", cells=np.arange(self.nCs), origin=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), omega=mrf_omega,
+                              nonRotatingPatches=["inlet", "outlet", "shroud"])
+            self.mrf_f = dict(self.mrf_s, cells=np.arange(self.full.n_cells))
+            kw["mrf"] = self.mrf_s
+        cases.write_case(d, self.sec, bs, div_u=div_u, **kw)
+        opts = dict(normalizeStates=NORM_STATES, normalizeResiduals=list(ALL_RES))
+        opts.update(extra or {})
+        self.sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib_path)
+        self.orc = Oracle(self.full, bf, normalizeStates=NORM_STATES, divU=divU, normalizeResiduals=ALL_RES)
+        if self.mrf_f is not None:
+            self.orc.set_mrf(self.full, self.mrf_f)
+        self.case_dir = d
+        # faces of the ring -> merged faces of the passage, by the pair of passage-local cells (boundary: cell + patch)
+        so, sn, sp = merged_faces(self.sec)
+        self.nFs = so.size
+        key = {}
+        for g in range(self.nFs):
+            k = (min(so[g], sn[g]), max(so[g], sn[g])) if sn[g] >= 0 else (so[g], sp[g])
+            assert k not in key
+            key[k] = g
+        nF, nIF = self.full.n_faces, self.full.n_internal_faces
+        pn = [""] * nF
+        for p in self.full.patches:
+            for i in range(p["size"]):
+                pn[p["start"] + i] = p["name"]
+        self.f2s = np.zeros(nF, dtype=np.int64)
+        self.fsign = np.ones(nF)
+        self.s2f = -np.ones(self.nFs, dtype=np.int64)  # the ring face that is the passage-0 instance of a merged face
+        for f in range(nF):
+            o = self.full.owner[f]
+            if f < nIF:
+                n = self.full.neighbour[f]
+                ol, nl = o % self.nCs, n % self.nCs
+                g = key[(min(ol, nl), max(ol, nl))]
+                same = ol == so[g]
+                self.fsign[f] = 1.0 if same else -1.0
+                owner_cell = o if same else n  # the ring cell playing the owner of the merged face
+            else:
+                g = key[(o % self.nCs, pn[f])]
+                owner_cell = o
+            self.f2s[f] = g
+            if owner_cell < self.nCs:
+                self.s2f[g] = f
+        assert (self.s2f >= 0).all()
+        # local (engine) layout -> merged numbering
+        self.idx = self.sol.localStateIndex(self.nCs, self.nFs, turbulent=turbulent)
+        self.owned = np.concatenate([np.ones((5 if turbulent else 4) * self.sol.getNLocalCells(), dtype=bool),
+                                     self.sol.getLocalToGlobal("faceOwned").astype(bool)])
+        assert self.sol.getNLocalCells() == self.nCs
+
+    # ---- vectors in the merged (passage) numbering <-> ring numbering
+    def n_sec(self):
+        return (5 if self.turb else 4) * self.nCs + self.nFs
+
+    def to_ring(self, v):
+        nCs, nCf = self.nCs, self.full.n_cells
+        ns = 5 if self.turb else 4
+        out = np.zeros(ns * nCf + self.full.n_faces)
+        U = v[:3 * nCs].reshape(nCs, 3)
+        for s in range(N_SECTORS):
+            out[3 * s * nCs:3 * (s + 1) * nCs] = (U @ rotz(s * self.sec.sector_angle).T).ravel()
+            for k in range(ns - 3):
+                out[(3 + k) * nCf + s * nCs:(3 + k) * nCf + (s + 1) * nCs] = v[(3 + k) * nCs:(4 + k) * nCs]
+        out[ns * nCf:] = self.fsign * v[ns * nCs + self.f2s]
+        return out
+
+    def from_ring(self, w):
+        """rows of passage 0"""
+        nCs, nCf = self.nCs, self.full.n_cells
+        ns = 5 if self.turb else 4
+        out = np.zeros(self.n_sec())
+        out[:3 * nCs] = w[:3 * nCs]
+        for k in range(ns - 3):
+            out[(3 + k) * nCs:(4 + k) * nCs] = w[(3 + k) * nCf:(3 + k) * nCf + nCs]
+        out[ns * nCs:] = self.fsign[self.s2f] * w[ns * nCf + self.s2f]
+        return out
+
+    def state(self, seed=7):
+        """a flow through the passage: axial velocity with swirl and a boundary-layer-like profile, passage-periodic"""
+        rng = np.random.default_rng(seed)
+        nCs = self.nCs
+        C = np.asarray(self.orc.geometry("C")).reshape(-1, 3)[:nCs]
+        r = np.hypot(C[:, 0], C[:, 1])
+        th = np.arctan2(C[:, 1], C[:, 0])
+        z = C[:, 2]
+        eta = (r - 0.2) / 0.15
+        prof = 4.0 * eta * (1.0 - eta) + 0.2
+        ur = 0.4 * np.sin(N_SECTORS * th) * np.sin(np.pi * eta)
+        ut = 3.0 * prof * (1.0 + 0.2 * np.cos(N_SECTORS * th)) + 1.0 * z
+        uz = 10.0 * prof * (1.0 + 0.1 * np.sin(N_SECTORS * th + 3.0 * z))
+        U = np.stack([ur * np.cos(th) - ut * np.sin(th), ur * np.sin(th) + ut * np.cos(th), uz], axis=1)
+        U *= 1.0 + 0.01 * rng.uniform(-1, 1, U.shape)
+        p = 20.0 * (1.0 - z / 0.3) + 5.0 * np.cos(N_SECTORS * th) * eta + 0.2 * rng.uniform(-1, 1, nCs)
+        parts = [U.ravel(), p]
+        if self.turb:
+            parts.append(4.5e-5 * (1.0 + 3.0 * prof) * (1.0 + 0.01 * rng.uniform(-1, 1, nCs)))
+        so, sn, _ = merged_faces(self.sec)
+        # flux through the merged faces from the ring geometry of their passage-0 instances
+        S = np.asarray(self.orc.geometry("Sf")).reshape(-1, 3)[self.s2f] * self.fsign[self.s2f][:, None]
+        ring_o = np.where(self.fsign[self.s2f] > 0, self.full.owner[self.s2f], 0)
+        Uo = U[so]
+        # the neighbour's velocity in the owner's frame: across the coupled pair it is the rotated image
+        Un = np.where((sn >= 0)[:, None], U[np.maximum(sn, 0)], Uo)
+        nIF = self.sec.n_internal_faces
+        nCyc = sum(p["size"] for p in self.sec.patches if p["type"] == "cyclic") // 2
+        Rm = rotz(-self.sec.sector_angle)  # per_hi cells seen from per_lo: one passage back
+        Un[nIF:nIF + nCyc] = Un[nIF:nIF + nCyc] @ Rm.T
+        del ring_o
+        phi = np.einsum("ij,ij->i", 0.5 * (Uo + Un), S) * (1.0 + 0.01 * rng.uniform(-1, 1, self.nFs))
+        _, _, pname = merged_faces(self.sec)
+        for g in range(self.nFs):
+            if pname[g] in ("hub", "shroud"):
+                phi[g] = 0.0
+        parts.append(phi)
+        return np.concatenate(parts)
+
+    def local(self, v):
+        return np.ascontiguousarray(v[self.idx])
+
+    def merged(self, vloc):
+        out = np.zeros(self.n_sec())
+        out[self.idx[self.owned]] = vloc[self.owned]
+        return out
+
+    def segments(self):
+        nC = self.nCs
+        segs = [("U", 0, 3 * nC), ("p", 3 * nC, 4 * nC)]
+        if self.turb:
+            segs.append(("nuTilda", 4 * nC, 5 * nC))
+        segs.append(("phi", (5 if self.turb else 4) * nC, self.n_sec()))
+        return segs
+
+
+def check_pair(P, tol=1e-9):
+    W = P.state()
+    Wr = P.to_ring(W)
+    # the ring state repeats: its passage-0 rows are the passage state
+    assert np.array_equal(P.from_ring(Wr), W)
+    P.sol.updateOFFields(P.local(W))
+    worst = 0.0
+    for isPC in (0, 1):
+        R = np.zeros(P.idx.size)
+        P.sol.getResiduals(R, isPC)
+        Rs, Ro = P.merged(R), P.from_ring(P.orc.residual(Wr, isPC))
+        for name, a, b in P.segments():
+            e = rel_err(Rs[a:b], Ro[a:b])
+            worst = max(worst, e)
+            assert e < tol, ("residual", isPC, name, e)
+    P.orc.record(Wr)
+    rng = np.random.default_rng(99)
+    for trial in range(2):
+        psi = rng.uniform(-1, 1, P.n_sec()) if trial == 0 else np.full(P.n_sec(), 1e-3)
+        if trial == 1:
+            psi[:3 * P.nCs] = (np.array([0.3e-3, -0.7e-3, 1e-3])[None, :] * np.ones((P.nCs, 1))).ravel()
+        y = np.zeros(P.idx.size)
+        P.sol.calcdRdWTPsiAD(P.local(psi), y)
+        ys, yo = P.merged(y), P.from_ring(P.orc.jtvec(P.to_ring(psi)))
+        for name, a, b in P.segments():
+            e = rel_err(ys[a:b], yo[a:b])
+            worst = max(worst, e)
+            assert e < tol, ("jtvec", trial, name, e)
+    return worst
+
+
+def test_passage_generator_is_periodic():
+    sec = cases.annular_passage(n_sectors=N_SECTORS)
+    lo = next(p for p in sec.patches if p["name"] == "per_lo")
+    hi = next(p for p in sec.patches if p["name"] == "per_hi")
+    assert lo["size"] == hi["size"] > 0
+    R = rotz(sec.sector_angle)
+    for i in range(lo["size"]):
+        a = sec.points[sec.faces[lo["start"] + i]].mean(axis=0)
+        b = sec.points[sec.faces[hi["start"] + i]].mean(axis=0)
+        assert np.allclose(R @ a, b, atol=1e-13)
+
+
+@pytest.mark.parametrize("turbulent,divU", [(True, "linearUpwind"), (False, "upwind"), (True, "linearUpwindV")])
+def test_cyclic_passage_equals_ring_host_build(turbulent, divU):
+    worst = check_pair(Pair(turbulent, divU))
+    assert worst < 1e-9
+
+
+def test_cyclic_passage_with_mrf_host_build():
+    worst = check_pair(Pair(True, "linearUpwind", mrf_omega=30.0))
+    assert worst < 1e-9
+
+
+@pytest.mark.gpu
+def test_cyclic_passage_equals_ring_cuda():
+    worst = check_pair(Pair(True, "linearUpwindV", lib_path=None))
+    assert worst < 1e-9
+    worst = check_pair(Pair(True, "linearUpwind", lib_path=None, mrf_omega=30.0))
+    assert worst < 1e-9
