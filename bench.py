@@ -298,10 +298,11 @@ def main():
                     help="adjEqnOption.pcStorage: fp32 copy of the ILU factors for the triangular solves (operator and vectors stay fp64)")
     ap.add_argument("--idr-s", type=int, default=8)
     ap.add_argument("--max-iters", type=int, default=3000)
-    ap.add_argument("--mesh", default="ogrid2d", choices=["ogrid2d", "wing3d"],
-                    help="wing3d: BASELINE config 4, a swept tapered NACA0012 wing between two symmetry planes, fully 3-D hexahedra (use --cells 5000000 --gpus 4)")
-    ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam"],
-                    help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000)")
+    ap.add_argument("--mesh", default="ogrid2d", choices=["ogrid2d", "wing3d", "passage"],
+                    help="wing3d: BASELINE config 4, a swept tapered NACA0012 wing between two symmetry planes, fully 3-D hexahedra (use --cells 5000000 --gpus 4); "
+                         "passage: BASELINE config 5's shape, one passage of an annular rotor row with cyclic sides and an MRF zone (use --solver DATurboFoam)")
+    ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam", "DATurboFoam"],
+                    help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000); DATurboFoam: config 5 (with --mesh passage)")
     ap.add_argument("--primal-iters", type=int, default=0,
                     help="run that many SIMPLE iterations (solvePrimal on the GPU) from the synthetic state before the adjoint legs (1 GPU)")
     args = ap.parse_args()
@@ -323,23 +324,47 @@ def main():
 
     ncell_target = args.cells * (world if args.scaling == "weak" else 1)
     wing = args.mesh == "wing3d"
+    passage = args.mesh == "passage"
     if args.pc_level is None:
-        args.pc_level = 2 if wing else 3
-    if wing:
+        args.pc_level = 2 if (wing or passage) else 3
+    if passage:
+        # 36 passages (10 degree pitch); radial : pitchwise : axial cell counts 1 : 1 : 2
+        nj = ni = max(4, int(round((ncell_target / 2.0) ** (1.0 / 3.0))))
+        nk = max(4, int(round(ncell_target / float(ni * nj))))
+        tile = (1, 1, 1)
+    elif wing:
         ni, nj, nk = grid3_for(ncell_target)
         tile = TILE3
     else:
         (ni, nj), nk = grid_for(ncell_target), 1
         tile = TILE
     t_setup = time.time()
-    comp = args.solver == "DARhoSimpleFoam"
+    comp = args.solver in ("DARhoSimpleFoam", "DATurboFoam")
     U0c = (100.0, 0.0, 0.0)  # M ~ 0.29 at 300 K
-    thermo = cases.default_thermo() if comp else None
+    thermo = cases.default_thermo(energy="sensibleEnthalpy" if args.solver == "DATurboFoam" else "sensibleInternalEnergy") if comp else None
+    partitioned = world > 1 or passage  # the engine's state vector is then a local one (ghost / image slots), filled from a global state
     # rank 0 generates the mesh, writes the case (binary polyMesh) and, on several GPUs, the global state; the other ranks
     # only read: their own engine reads the polyMesh and keeps its partition, the state slice comes from the shared file
     mesh = None
     info = [None, None, 0, 0]
-    if rank == 0:
+    if rank == 0 and passage:
+        mesh = cases.annular_passage(nr=ni, nt=nj, nz=nk, r0=0.2, r1=0.35, lz=0.3, n_sectors=36)
+        case_dir = tempfile.mkdtemp(prefix="dab_bench_")
+        Uax = 100.0 if comp else 10.0
+        bcs = cases.default_bcs_passage(Uin=(0.0, 0.0, Uax))
+        mrf = dict(cellZone="rotor", cells=np.arange(mesh.n_cells), origin=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), omega=300.0 if comp else 30.0,
+                   nonRotatingPatches=["inlet", "outlet", "shroud"])
+        if comp:
+            cases.write_case(case_dir, mesh, cases.compressible_bcs(bcs), binary=True, thermo=thermo, mrf=mrf)
+        else:
+            cases.write_case(case_dir, mesh, bcs, binary=True, mrf=mrf)
+        n_merged = cases.merged_face_order(mesh).size
+        info = [case_dir, None, mesh.n_cells, n_merged]
+        if world > 1:
+            from dafoam_b200.pyDASolvers import nccl_unique_id
+            info[1] = nccl_unique_id()
+        np.save(os.path.join(case_dir, "W_global.npy"), cases.passage_state(mesh, Uax=Uax, thermo=thermo, n_sectors=36))
+    elif rank == 0:
         if wing:
             mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=nk, span=3.0, sweep=0.5, taper=0.5, radius=15.0, tile=tile)
         else:
@@ -358,8 +383,8 @@ def main():
         dist.broadcast_object_list(info, src=0)
     case_dir, uid, n_cells_g, n_faces_g = info
     t_mesh = time.time() - t_setup
-    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["wing"], "directionMode": "fixedDirection",
-                 "direction": [1.0, 0.0, 0.0], "scale": 1.0}}
+    fn = {"CD": {"type": "force", "source": "patchToFace", "patches": ["hub" if passage else "wing"], "directionMode": "fixedDirection",
+                 "direction": [0.0, 0.0, 1.0] if passage else [1.0, 0.0, 0.0], "scale": 1.0}}
     ns_opt = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else NORM_STATES
     adj_opt = dict(gmresRelTol=1e-6, gmresMaxIters=args.max_iters, gmresRestart=args.restart, printInfo=1, pcConLevel=args.pc_level,
                    coarseAggregates=args.coarse, pcBlockCells=args.pc_block, pcStorage=args.pc_storage, tileCells=int(np.prod(tile)))
@@ -368,7 +393,7 @@ def main():
     sol = pyDASolvers(args.solver + " -python", opts, caseDir=case_dir, device=local_rank, rank=rank, nRanks=world, ncclUniqueId=uid)
     n = sol.getNLocalAdjointStates()
     nC = sol.getNLocalCells()
-    if world == 1:
+    if not partitioned:
         y_ = np.zeros(nC)
         sol.getOFField("yWall", "scalar", y_)
         W = cases.boundary_layer_state(mesh, y_, U0=U0c if comp else (10.0, 0.0, 0.0), seed=1234, noise=0.001)
@@ -382,7 +407,7 @@ def main():
     sol.updateOFFields(W)
     t_setup = time.time() - t_setup
     primal = None
-    if args.primal_iters > 0 and world == 1:
+    if args.primal_iters > 0 and (world == 1 or passage):
         # the step before the path (solve_nonlinear): SIMPLE iterations on the device, then the adjoint at that state
         pfail = sol.solvePrimal()
         ps = sol.primalStats
@@ -515,9 +540,11 @@ def main():
         "metric": "dRdWTPsi_GCells_per_s", "value": value, "unit": "GCells/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s NACA0012 SA %s %dx%dx%d (tile-major cell numbering, %s tiles), %d cells global, %d cells / %d DOF "
+        "config": {"workload": "%s %s SA %s %dx%dx%d (%s tiles), %d cells global, %d cells / %d DOF "
                                "on this GPU; adjoint matvec dRdW^T*psi; working set per product ~%.0f MB >> 126 MB L2 (no explicit flush)"
-                               % (args.solver, "swept tapered wing, 3-D O-grid" if wing else "O-grid", ni, nj, nk, "x".join(str(t) for t in tile),
+                               % (args.solver, "annular rotor passage (36 per row), cyclic sides + MRF zone," if passage else "NACA0012",
+                                  "radial x pitchwise x axial" if passage else ("swept tapered wing, 3-D O-grid" if wing else "O-grid, tile-major cell numbering"),
+                                  ni, nj, nk, "x".join(str(t) for t in tile),
                                   nC_global, nC, n, (alg + 60 * 8 * nC) / 1e6),
                    "parallelism": ("domain decomposition (RCB) over %d GPUs, NCCL ghost-cell exchange" % world) if world > 1 else "single GPU",
                    "setup_s": t_setup, "setup_mesh_generation_s": t_mesh},
@@ -533,7 +560,7 @@ def main():
         "primal_solve": primal,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1 and not comp and not wing:
+    if not args.no_cpu_baseline and world == 1 and not comp and not wing and not passage:
         try:
             arm = CpuArm(nC_global, "port")
             out["cpu_baseline"] = arm.run(10)

@@ -899,3 +899,62 @@ def boundary_layer_state(mesh: PolyMesh, yWall, U0=(10.0, 0.0, 0.0), nuTilda0=4.
         parts.append(nt)
     parts.append(phi)
     return np.concatenate(parts)
+
+
+def merged_face_order(mesh: PolyMesh):
+    """Face numbering of the engine on a mesh with cyclic patches (csrc/mesh.hpp mergeCyclics): the internal faces, then ONE face per
+    coupled pair (the face of the first patch of the pair: owner = its cell, neighbour = the cell on the partner patch), then the
+    faces of the other patches.  Returns the polyMesh face index of every engine face; phi of a coupled face is the flux out of the
+    first patch.  Meshes without cyclic patches: the identity."""
+    names = [p["name"] for p in mesh.patches]
+    parts = [np.arange(mesh.n_internal_faces)]
+    for pi, p in enumerate(mesh.patches):
+        if p["type"] == "cyclic" and names.index(p["neighbourPatch"]) > pi:
+            parts.append(np.arange(p["start"], p["start"] + p["size"]))
+    for p in mesh.patches:
+        if p["type"] != "cyclic":
+            parts.append(np.arange(p["start"], p["start"] + p["size"]))
+    return np.concatenate(parts)
+
+
+def passage_state(mesh: PolyMesh, Uax=10.0, nuTilda0=4.5e-5, thermo=None, p0=101325.0, T0=300.0, seed=1234, noise=0.001, r0=0.2, r1=0.35,
+                  n_sectors=None):
+    """Synthetic flow through annular_passage(): axial velocity with a hub-to-shroud profile, swirl, passage-periodic pressure
+    and temperature fields (+ seeded noise), flux = rho_f U_f . Sf.  Returned in the ENGINE's ordering ([U | p | (T) | nuTilda | phi],
+    phi over merged_face_order(mesh)); the state of a periodic image is the rotated state, so the field repeats by construction."""
+    rng = np.random.default_rng(seed)
+    Sf, Cf = quad_face_geometry(mesh)
+    nC, nIF = mesh.n_cells, mesh.n_internal_faces
+    cnt = np.bincount(mesh.owner, minlength=nC) + np.bincount(mesh.neighbour, minlength=nC)
+    C = np.stack([np.bincount(mesh.owner, weights=Cf[:, k], minlength=nC) + np.bincount(mesh.neighbour, weights=Cf[:nIF, k], minlength=nC)
+                  for k in range(3)], axis=1) / cnt[:, None]
+    ns_ = n_sectors if n_sectors is not None else int(round(2.0 * np.pi / mesh.sector_angle))
+    r, th, z = np.hypot(C[:, 0], C[:, 1]), np.arctan2(C[:, 1], C[:, 0]), C[:, 2]
+    eta = np.clip((r - r0) / (r1 - r0), 0.0, 1.0)
+    prof = 4.0 * eta * (1.0 - eta) + 0.05
+    ur = 0.02 * Uax * np.sin(ns_ * th) * np.sin(np.pi * eta)
+    ut = 0.3 * Uax * prof * (1.0 + 0.1 * np.cos(ns_ * th))
+    uz = Uax * prof * (1.0 + 0.05 * np.sin(ns_ * th + 3.0 * z))
+    U = np.stack([ur * np.cos(th) - ut * np.sin(th), ur * np.sin(th) + ut * np.cos(th), uz], axis=1)
+    U *= 1.0 + noise * rng.uniform(-1, 1, U.shape)
+    zl = z / max(z.max(), 1e-300)
+    p = 0.5 * Uax**2 * ((1.0 - zl) + 0.1 * np.cos(ns_ * th) * eta) * (1.0 + noise * rng.uniform(-1, 1, nC))
+    nt = nuTilda0 * (1.0 + 3.0 * prof) * (1.0 + noise * rng.uniform(-1, 1, nC))
+    rho = np.ones(nC)
+    parts = [U.ravel()]
+    if thermo is not None:
+        p = p0 + p
+        T = T0 * (1.0 + 0.02 * np.sin(ns_ * th) * np.cos(9.0 * z)) * (1.0 + 0.1 * noise * rng.uniform(-1, 1, nC))
+        rho = p / (8314.4700665 / thermo["molWeight"] * T)
+        parts += [p, T]
+    else:
+        parts.append(p)
+    parts.append(nt)
+    nei = np.concatenate([mesh.neighbour, mesh.owner[nIF:]])
+    phi = 0.5 * (rho[mesh.owner] + rho[nei]) * np.einsum("ij,ij->i", 0.5 * (U[mesh.owner] + U[nei]), Sf)
+    phi *= 1.0 + noise * rng.uniform(-1, 1, phi.size)
+    for pch in mesh.patches:
+        if pch["type"] == "wall":
+            phi[pch["start"]:pch["start"] + pch["size"]] = 0.0
+    parts.append(phi[merged_face_order(mesh)])
+    return np.concatenate(parts)

@@ -56,14 +56,25 @@ def rotz(a):
 class Pair:
     """One passage with cyclic sides (engine) and the ring of N_SECTORS passages (oracle), with the maps between them."""
 
-    def __init__(self, turbulent=True, divU="linearUpwind", lib_path=HOSTSIM, dims=(4, 4, 6), mrf_omega=None, extra=None):
+    def __init__(self, turbulent=True, divU="linearUpwind", lib_path=HOSTSIM, dims=(4, 4, 6), mrf_omega=None, extra=None, solver="DASimpleFoam",
+                 energy="sensibleEnthalpy"):
         nr, nt, nz = dims
         self.turb = turbulent
+        self.comp = solver != "DASimpleFoam"
+        self.ns = 4 + int(turbulent) + int(self.comp)
+        self.Uax = 60.0 if self.comp else 10.0
         self.sec = cases.annular_passage(nr=nr, nt=nt, nz=nz, n_sectors=N_SECTORS, sectors=1)
         self.full = cases.annular_passage(nr=nr, nt=nt, nz=nz, n_sectors=N_SECTORS, sectors=N_SECTORS)
         self.nCs = self.sec.n_cells
-        bs = cases.default_bcs_passage(turbulent=turbulent, cyclic=True)
-        bf = cases.default_bcs_passage(turbulent=turbulent, cyclic=False)
+        bs = cases.default_bcs_passage(Uin=(0.0, 0.0, self.Uax), turbulent=turbulent, cyclic=True)
+        bf = cases.default_bcs_passage(Uin=(0.0, 0.0, self.Uax), turbulent=turbulent, cyclic=False)
+        self.thermo = None
+        ns_, nres_ = NORM_STATES, ALL_RES
+        if self.comp:
+            bs, bf = cases.compressible_bcs(bs), cases.compressible_bcs(bf)
+            self.thermo = cases.default_thermo(energy=energy)
+            ns_ = dict(U=50.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0)
+            nres_ = ("URes", "pRes", "TRes", "nuTildaRes", "phiRes")
         div_u = "bounded Gauss %s%s" % (divU, " grad(U)" if divU.startswith("linearUpwind") else "")
         d = tempfile.mkdtemp(prefix="dab_cyc_")
         kw = {}
@@ -73,11 +84,16 @@ class Pair:
                               nonRotatingPatches=["inlet", "outlet", "shroud"])
             self.mrf_f = dict(self.mrf_s, cells=np.arange(self.full.n_cells))
             kw["mrf"] = self.mrf_s
+        if self.thermo is not None:
+            kw["thermo"] = self.thermo
         cases.write_case(d, self.sec, bs, div_u=div_u, **kw)
-        opts = dict(normalizeStates=NORM_STATES, normalizeResiduals=list(ALL_RES))
+        opts = dict(normalizeStates=ns_, normalizeResiduals=list(nres_))
         opts.update(extra or {})
-        self.sol = pyDASolvers("DASimpleFoam -python", opts, caseDir=d, _lib_path=lib_path)
-        self.orc = Oracle(self.full, bf, normalizeStates=NORM_STATES, divU=divU, normalizeResiduals=ALL_RES)
+        self.sol = pyDASolvers(solver + " -python", opts, caseDir=d, _lib_path=lib_path)
+        okw = dict(thermo=self.thermo) if self.comp else {}
+        self.orc = Oracle(self.full, bf, normalizeStates=ns_, divU=divU, normalizeResiduals=nres_, **okw)
+        if self.comp:
+            self.orc.set_turbo(solver == "DATurboFoam")
         if self.mrf_f is not None:
             self.orc.set_mrf(self.full, self.mrf_f)
         self.case_dir = d
@@ -114,18 +130,18 @@ class Pair:
                 self.s2f[g] = f
         assert (self.s2f >= 0).all()
         # local (engine) layout -> merged numbering
-        self.idx = self.sol.localStateIndex(self.nCs, self.nFs, turbulent=turbulent)
-        self.owned = np.concatenate([np.ones((5 if turbulent else 4) * self.sol.getNLocalCells(), dtype=bool),
+        self.idx = self.sol.localStateIndex(self.nCs, self.nFs, turbulent=turbulent, compressible=self.comp)
+        self.owned = np.concatenate([np.ones(self.ns * self.sol.getNLocalCells(), dtype=bool),
                                      self.sol.getLocalToGlobal("faceOwned").astype(bool)])
         assert self.sol.getNLocalCells() == self.nCs
 
     # ---- vectors in the merged (passage) numbering <-> ring numbering
     def n_sec(self):
-        return (5 if self.turb else 4) * self.nCs + self.nFs
+        return self.ns * self.nCs + self.nFs
 
     def to_ring(self, v):
         nCs, nCf = self.nCs, self.full.n_cells
-        ns = 5 if self.turb else 4
+        ns = self.ns
         out = np.zeros(ns * nCf + self.full.n_faces)
         U = v[:3 * nCs].reshape(nCs, 3)
         for s in range(N_SECTORS):
@@ -138,7 +154,7 @@ class Pair:
     def from_ring(self, w):
         """rows of passage 0"""
         nCs, nCf = self.nCs, self.full.n_cells
-        ns = 5 if self.turb else 4
+        ns = self.ns
         out = np.zeros(self.n_sec())
         out[:3 * nCs] = w[:3 * nCs]
         for k in range(ns - 3):
@@ -157,12 +173,19 @@ class Pair:
         eta = (r - 0.2) / 0.15
         prof = 4.0 * eta * (1.0 - eta) + 0.2
         ur = 0.4 * np.sin(N_SECTORS * th) * np.sin(np.pi * eta)
-        ut = 3.0 * prof * (1.0 + 0.2 * np.cos(N_SECTORS * th)) + 1.0 * z
-        uz = 10.0 * prof * (1.0 + 0.1 * np.sin(N_SECTORS * th + 3.0 * z))
+        ut = 0.3 * self.Uax * prof * (1.0 + 0.2 * np.cos(N_SECTORS * th)) + 0.1 * self.Uax * z
+        uz = self.Uax * prof * (1.0 + 0.1 * np.sin(N_SECTORS * th + 3.0 * z))
         U = np.stack([ur * np.cos(th) - ut * np.sin(th), ur * np.sin(th) + ut * np.cos(th), uz], axis=1)
         U *= 1.0 + 0.01 * rng.uniform(-1, 1, U.shape)
         p = 20.0 * (1.0 - z / 0.3) + 5.0 * np.cos(N_SECTORS * th) * eta + 0.2 * rng.uniform(-1, 1, nCs)
+        rho = np.ones(nCs)
+        if self.comp:
+            p = 101325.0 + 40.0 * p
+            T = 300.0 * (1.0 + 0.02 * np.sin(N_SECTORS * th) * np.cos(9.0 * z)) * (1.0 + 0.001 * rng.uniform(-1, 1, nCs))
+            rho = p / (8314.4700665 / self.thermo["molWeight"] * T)
         parts = [U.ravel(), p]
+        if self.comp:
+            parts.append(T)
         if self.turb:
             parts.append(4.5e-5 * (1.0 + 3.0 * prof) * (1.0 + 0.01 * rng.uniform(-1, 1, nCs)))
         so, sn, _ = merged_faces(self.sec)
@@ -177,7 +200,8 @@ class Pair:
         Rm = rotz(-self.sec.sector_angle)  # per_hi cells seen from per_lo: one passage back
         Un[nIF:nIF + nCyc] = Un[nIF:nIF + nCyc] @ Rm.T
         del ring_o
-        phi = np.einsum("ij,ij->i", 0.5 * (Uo + Un), S) * (1.0 + 0.01 * rng.uniform(-1, 1, self.nFs))
+        rf = 0.5 * (rho[so] + np.where(sn >= 0, rho[np.maximum(sn, 0)], rho[so]))
+        phi = rf * np.einsum("ij,ij->i", 0.5 * (Uo + Un), S) * (1.0 + 0.01 * rng.uniform(-1, 1, self.nFs))
         _, _, pname = merged_faces(self.sec)
         for g in range(self.nFs):
             if pname[g] in ("hub", "shroud"):
@@ -196,9 +220,14 @@ class Pair:
     def segments(self):
         nC = self.nCs
         segs = [("U", 0, 3 * nC), ("p", 3 * nC, 4 * nC)]
+        k = 4
+        if self.comp:
+            segs.append(("T", k * nC, (k + 1) * nC))
+            k += 1
         if self.turb:
-            segs.append(("nuTilda", 4 * nC, 5 * nC))
-        segs.append(("phi", (5 if self.turb else 4) * nC, self.n_sec()))
+            segs.append(("nuTilda", k * nC, (k + 1) * nC))
+            k += 1
+        segs.append(("phi", k * nC, self.n_sec()))
         return segs
 
 
@@ -254,6 +283,70 @@ def test_cyclic_passage_equals_ring_host_build(turbulent, divU):
 def test_cyclic_passage_with_mrf_host_build():
     worst = check_pair(Pair(True, "linearUpwind", mrf_omega=30.0))
     assert worst < 1e-9
+
+
+@pytest.mark.parametrize("solver,energy,omega", [("DARhoSimpleFoam", "sensibleInternalEnergy", None), ("DATurboFoam", "sensibleEnthalpy", 300.0),
+                                                 ("DATurboFoam", "sensibleInternalEnergy", 300.0)])
+def test_cyclic_compressible_passage_host_build(solver, energy, omega):
+    """BASELINE config 5's combination: DATurboFoam + SA + MRF rotor zone + cyclic sides"""
+    worst = check_pair(Pair(True, "linearUpwindV", solver=solver, energy=energy, mrf_omega=omega))
+    assert worst < 1e-9
+
+
+def solve_on_passage(lib_path, solver="DATurboFoam", dims=(6, 6, 12)):
+    """the bench's config-5 workload in small: state from cases.passage_state, dRdWTPC + GMRES, the solution checked with the product"""
+    from dafoam_b200.pyDASolvers import KSP, Mat
+    comp = solver != "DASimpleFoam"
+    mesh = cases.annular_passage(nr=dims[0], nt=dims[1], nz=dims[2], n_sectors=36)
+    Uax = 100.0 if comp else 10.0
+    bcs = cases.default_bcs_passage(Uin=(0.0, 0.0, Uax))
+    th = cases.default_thermo(energy="sensibleEnthalpy") if comp else None
+    mrf = dict(cellZone="rotor", cells=np.arange(mesh.n_cells), origin=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), omega=300.0 if comp else 30.0,
+               nonRotatingPatches=["inlet", "outlet", "shroud"])
+    d = tempfile.mkdtemp(prefix="dab_cyc_")
+    kw = dict(thermo=th) if comp else {}
+    cases.write_case(d, mesh, cases.compressible_bcs(bcs) if comp else bcs, mrf=mrf, **kw)
+    fn = {"FZ": {"type": "force", "source": "patchToFace", "patches": ["hub"], "directionMode": "fixedDirection", "direction": [0.0, 0.0, 1.0],
+                 "scale": 1.0}}
+    ns = dict(U=100.0, p=101325.0, T=300.0, nuTilda=1e-3, phi=1.0) if comp else NORM_STATES
+    sol = pyDASolvers(solver + " -python", dict(normalizeStates=ns, function=fn,
+                                                adjEqnOption=dict(gmresRelTol=1e-8, gmresMaxIters=1500, gmresRestart=1500, pcConLevel=2)),
+                      caseDir=d, _lib_path=lib_path)
+    Wg = cases.passage_state(mesh, Uax=Uax, thermo=th, n_sectors=36)
+    nFg = cases.merged_face_order(mesh).size
+    idx = sol.localStateIndex(mesh.n_cells, nFg, compressible=comp)
+    owned = np.concatenate([np.ones((6 if comp else 5) * mesh.n_cells, dtype=bool), sol.getLocalToGlobal("faceOwned").astype(bool)])
+    assert idx.size == sol.getNLocalAdjointStates() and int(owned.sum()) == Wg.size
+    W = np.ascontiguousarray(Wg[idx])
+    sol.updateOFFields(W)
+    R = np.zeros(idx.size)
+    sol.getResiduals(R)
+    assert np.all(np.isfinite(R)) and np.all(R[~owned] == 0.0)
+    b = np.zeros(idx.size)
+    sol.calcJacTVecProduct("s", "stateVar", W, "FZ", "function", np.array([1.0]), b)
+    assert np.linalg.norm(b) > 0
+    pc, ksp = Mat(), KSP()
+    sol.calcdRdWT(1, pc)
+    x = np.zeros(idx.size)
+    fail = sol.solveLinearEqn(ksp, b, x)
+    assert fail == 0, (fail, ksp.stats.iterations, ksp.stats.final_residual / ksp.stats.initial_residual)
+    y = np.zeros(idx.size)
+    sol.calcdRdWTPsiAD(x, y)
+    res = np.linalg.norm((y - b)[owned]) / np.linalg.norm(b[owned])
+    assert res < 1e-6, res
+    return ksp.stats.iterations, res
+
+
+@pytest.mark.parametrize("solver", ["DASimpleFoam", "DATurboFoam"])
+def test_adjoint_solve_on_passage_host_build(solver):
+    its, res = solve_on_passage(HOSTSIM, solver)
+    assert its > 0
+
+
+@pytest.mark.gpu
+def test_adjoint_solve_on_passage_cuda():
+    its, res = solve_on_passage(None, "DATurboFoam", dims=(12, 12, 24))
+    assert its > 0
 
 
 @pytest.mark.gpu

@@ -56,3 +56,23 @@ def test_two_ranks_match_one_rank(kind):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok: ") == 2, r.stdout
+
+
+@pytest.mark.parametrize("kind,port", [("passage", 29751), ("passageturbo", 29753), ("passageprimal", 29755)])
+def test_cyclic_passage_on_two_ranks(kind, port):
+    """cyclic patch pairs across a partition cut (tests/mp_worker.py passage): images rotated inside the pack kernels"""
+    d = tempfile.mkdtemp(prefix="dab_mp_")
+    mesh = cases.annular_passage(nr=5, nt=6, nz=8, n_sectors=7)
+    bcs = cases.default_bcs_passage(Uin=(0.0, 0.0, 60.0 if "turbo" in kind else 10.0))
+    kw = {}
+    if "turbo" in kind:
+        bcs = cases.compressible_bcs(bcs)
+        kw = dict(thermo=cases.default_thermo(energy="sensibleEnthalpy"),
+                  mrf=dict(cellZone="rotor", cells=list(range(mesh.n_cells)), origin=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), omega=200.0,
+                           nonRotatingPatches=["inlet", "outlet", "shroud"]))
+    cases.write_case(d, mesh, bcs, **kw)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok: ") == 2, r.stdout
