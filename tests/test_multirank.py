@@ -11,9 +11,23 @@ from dafoam_b200 import cases
 from tests.common import ROOT
 
 
+def _write_passage(d, kind):
+    mesh = cases.annular_passage(nr=5, nt=6, nz=8, n_sectors=7)
+    bcs = cases.default_bcs_passage(Uin=(0.0, 0.0, 60.0 if "turbo" in kind else 10.0))
+    kw = {}
+    if "turbo" in kind:
+        bcs = cases.compressible_bcs(bcs)
+        kw = dict(thermo=cases.default_thermo(energy="sensibleEnthalpy"),
+                  mrf=dict(cellZone="rotor", cells=list(range(mesh.n_cells)), origin=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), omega=200.0,
+                           nonRotatingPatches=["inlet", "outlet", "shroud"]))
+    cases.write_case(d, mesh, bcs, **kw)
+
+
 def _run(kind, extra, port):
     d = tempfile.mkdtemp(prefix="dab_mp_")
-    if kind == "naca":
+    if kind.startswith("passage"):
+        _write_passage(d, kind)
+    elif kind == "naca":
         cases.write_case(d, cases.naca0012_ogrid(ni=32, nj=16, nk=2), cases.default_bcs_naca())
     else:
         cases.write_case(d, cases.channel(nx=12, ny=8, nz=2), cases.default_bcs_channel())
@@ -25,7 +39,7 @@ def _run(kind, extra, port):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,port", [("naca", 29735), ("channelprimal", 29741)])
+@pytest.mark.parametrize("kind,port", [("naca", 29735), ("channelprimal", 29741), ("passageturbo", 29757)])
 def test_two_gpus_match_one_gpu_nccl(kind, port):
     import torch
     if torch.cuda.device_count() < 2:
@@ -62,15 +76,7 @@ def test_two_ranks_match_one_rank(kind):
 def test_cyclic_passage_on_two_ranks(kind, port):
     """cyclic patch pairs across a partition cut (tests/mp_worker.py passage): images rotated inside the pack kernels"""
     d = tempfile.mkdtemp(prefix="dab_mp_")
-    mesh = cases.annular_passage(nr=5, nt=6, nz=8, n_sectors=7)
-    bcs = cases.default_bcs_passage(Uin=(0.0, 0.0, 60.0 if "turbo" in kind else 10.0))
-    kw = {}
-    if "turbo" in kind:
-        bcs = cases.compressible_bcs(bcs)
-        kw = dict(thermo=cases.default_thermo(energy="sensibleEnthalpy"),
-                  mrf=dict(cellZone="rotor", cells=list(range(mesh.n_cells)), origin=(0.0, 0.0, 0.0), axis=(0.0, 0.0, 1.0), omega=200.0,
-                           nonRotatingPatches=["inlet", "outlet", "shroud"]))
-    cases.write_case(d, mesh, bcs, **kw)
+    _write_passage(d, kind)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=ROOT)
