@@ -303,7 +303,7 @@ def main():
                          "passage: BASELINE config 5's shape, one passage of an annular rotor row with cyclic sides and an MRF zone (use --solver DATurboFoam)")
     ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam", "DATurboFoam"],
                     help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000); DATurboFoam: config 5 (with --mesh passage)")
-    ap.add_argument("--primal-iters", type=int, default=0,
+    ap.add_argument("--primal-iters", type=int, default=None,
                     help="run that many SIMPLE iterations (solvePrimal on the GPU) from the synthetic state before the adjoint legs (1 GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -327,6 +327,10 @@ def main():
     passage = args.mesh == "passage"
     if args.pc_level is None:
         args.pc_level = 2 if (wing or passage) else 3
+    if args.primal_iters is None:
+        # the synthetic passage state (a profile with slip at a hub that rotates under it) is far from any flow: ILU(0) of its Jacobian
+        # is unstable (GMRES stagnates, IDR diverges at 65k cells on the host build); after 300 SIMPLE iterations it is a flow
+        args.primal_iters = 300 if passage else 0
     if passage:
         # 36 passages (10 degree pitch); radial : pitchwise : axial cell counts 1 : 1 : 2
         nj = ni = max(4, int(round((ncell_target / 2.0) ** (1.0 / 3.0))))

@@ -20,24 +20,31 @@ struct CellGraph
     int nC;
     std::vector<int> off, adj, stamp, queue;
     int tick = 0;
-    void build(const HostMesh& m)
+    // alias != nullptr: ghost cell g (>= nC) stands for the owned cell (*alias)[g - nC] (-1: a cell of another rank) -- the periodic
+    // images of a rank's own cells; the graph then holds the true (periodic) adjacency instead of stopping at the coupled patches
+    void build(const HostMesh& m, const std::vector<int>* alias = nullptr)
     {
         nC = m.nC;
+        auto cellOf = [&](int c) { return c < nC ? c : (alias ? (*alias)[c - nC] : -1); };
         off.assign(nC + 1, 0);
         for (int f = 0; f < m.nIF; f++)
         {
-            if (m.own[f] >= nC || m.nei[f] >= nC) continue; // cut face: the other cell is a ghost (block-Jacobi over ranks)
-            off[m.own[f] + 1]++;
-            off[m.nei[f] + 1]++;
+            const int a = cellOf(m.own[f]), b = cellOf(m.nei[f]);
+            if (a < 0 || b < 0) continue; // cut face: the other cell is a ghost (block-Jacobi over ranks)
+            if (alias && m.own[f] >= nC) continue; // the second local copy of a coupled face
+            off[a + 1]++;
+            off[b + 1]++;
         }
         for (int c = 0; c < nC; c++) off[c + 1] += off[c];
         adj.resize(off[nC]);
         std::vector<int> pos(off.begin(), off.end() - 1);
         for (int f = 0; f < m.nIF; f++)
         {
-            if (m.own[f] >= nC || m.nei[f] >= nC) continue;
-            adj[pos[m.own[f]]++] = m.nei[f];
-            adj[pos[m.nei[f]]++] = m.own[f];
+            const int a = cellOf(m.own[f]), b = cellOf(m.nei[f]);
+            if (a < 0 || b < 0) continue;
+            if (alias && m.own[f] >= nC) continue;
+            adj[pos[a]++] = b;
+            adj[pos[b]++] = a;
         }
         stamp.assign(nC, 0);
     }
@@ -508,8 +515,9 @@ inline void Solver::coarseSetup()
     Krylov& K = kry;
     Coarse& Cs = K.coarse;
     const int nC = hm.nC, n = nDof(), offP = 3 * nC;
-    detail::CellGraph G;
-    G.build(hm);
+    detail::CellGraph Gagg;
+    Gagg.build(hm);
+    detail::CellGraph& G = Gagg;
     const int target = std::max(1, nC / std::max(1, coarseAggregates / std::max(1, nRanks)));
     std::vector<int32_t> aggOf(nC, -1);
     int nAgg = 0;
@@ -597,8 +605,17 @@ inline void Solver::coarseSetup()
     Cs.lu.assign((size_t)Kg * Kg, 0.0);
     ensureRecorded();
     int nProbes = 0;
-    if (!partitioned && coarseProbeReach > 0 && nAgg > 64)
+    if (nRanks == 1 && coarseProbeReach > 0 && nAgg > 64)
     {
+        // cyclic patches: the reach sets follow the periodic adjacency (an image stands for its source cell)
+        detail::CellGraph Gp;
+        if (partitioned)
+        {
+            std::vector<int> alias(hm.nCtot - nC, -1);
+            for (int i = 0; i < part.halo.selfRecvCount; i++) alias[part.halo.selfRecvStart - nC + i] = part.halo.selfSendCells[i];
+            Gp.build(hm, &alias);
+        }
+        detail::CellGraph& G = partitioned ? Gp : Gagg;
         // Coloured probing (one GPU): the transposed Jacobian couples a pressure DOF to residual rows at most `coarseProbeReach` cell
         // levels away, far less than an aggregate's diameter, so aggregates whose reach sets N(a) (the aggregates within that many
         // levels of a's cells) are disjoint share one probing vector; entry (i, a) is read from the restricted response at the only
