@@ -32,23 +32,23 @@ struct BoundaryAdj
 
 DAB_HD double dmuSutherland(const Params& q, double T)
 {
-    const double sT = sqrt(T), den = 1.0 + q.Ts / T;
-    return q.As * (0.5 / sT) / den + q.As * sT * (q.Ts / (T * T)) / (den * den);
+    const double sT = sqrt(T), den = 1.0 + q.Ts * frcp(T);
+    return q.As * (0.5 * frcp(sT)) * frcp(den) + q.As * sT * (q.Ts * frcp(T * T)) * frcp(den * den);
 }
 
 // adjoint of the thermo point rho(p,T), mu(T), alpha(T), nu = mu/rho given adjoints of rho, nu and alpha
 DAB_HD void thermoAdj(const Params& q, double p, double T, const ThermoPoint& th, double rhob, double nub, double alphab, double& pb, double& Tb)
 {
-    double mub = nub / th.rho;
-    rhob -= nub * th.mu / (th.rho * th.rho);
+    double mub = nub * frcp(th.rho);
+    rhob -= nub * th.mu * frcp(th.rho * th.rho);
     if (q.sutherland)
     {
         const double Cv = q.Cp - q.Rg;
-        mub += alphab * Cv * (1.32 + 1.77 * q.Rg / Cv) / q.Cp;
+        mub += alphab * Cv * (1.32 + 1.77 * q.Rg * frcp(Cv)) * frcp(q.Cp);
         Tb += mub * dmuSutherland(q, T);
     }
-    pb += rhob / (q.Rg * T);
-    Tb -= rhob * th.rho / T;
+    pb += rhob * frcp(q.Rg * T);
+    Tb -= rhob * th.rho * frcp(T);
     (void)p;
 }
 
@@ -58,20 +58,20 @@ DAB_HD void boundaryPointAdj(const MeshView& m, const Params& q, const StateView
                              BoundaryAdj a, double* Ub, double& pb, double& Tb, double& ntb, double& nutPb)
 {
     const int pa = m.bPatch[f - m.nIF];
-    const double phib = s.phi[f], dl = m.delta[f], im = 1.0 / m.magSf[f];
+    const double phib = s.phi[f], dl = m.delta[f], im = frcp(m.magSf[f]);
     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
     // Ek_b = 0.5|U_b|^2 (+ p_b/rho_b)
     for (int j = 0; j < 3; j++) a.val[j] += a.Ek * b.bu.val[j];
     if (q.heIsE)
     {
-        a.p += a.Ek / b.th.rho;
-        a.rho -= a.Ek * b.p / (b.th.rho * b.th.rho);
+        a.p += a.Ek * frcp(b.th.rho);
+        a.rho -= a.Ek * b.p * frcp(b.th.rho * b.th.rho);
     }
     // aE_b = CpByCpv (alpha_b + rho_b nut_b / Prt), muE_b = rho_b (nu_b + nut_b)
     const double kc = cpByCpv(q);
     double alphab = kc * a.aE;
-    a.rho += kc * a.aE * b.nut / q.Prt + a.muE * (b.th.nu + b.nut);
-    a.nut += kc * a.aE * b.th.rho / q.Prt + a.muE * b.th.rho;
+    a.rho += kc * a.aE * b.nut * frcp(q.Prt) + a.muE * (b.th.nu + b.nut);
+    a.nut += kc * a.aE * b.th.rho * frcp(q.Prt) + a.muE * b.th.rho;
     a.nu += a.muE * b.th.rho;
     // nut_b by BC kind
     if (q.turb && a.nut != 0.0)
@@ -79,8 +79,8 @@ DAB_HD void boundaryPointAdj(const MeshView& m, const Params& q, const StateView
         const int kind = q.bcKind[F_NUT][pa];
         if (kind == BC_CALCULATED)
         {
-            const double chi = b.nt / b.th.nu, c3 = chi * chi * chi, den = c3 + SA::Cv1c;
-            const double fv1 = c3 / den, dfv1 = 3.0 * chi * chi * SA::Cv1c / (den * den);
+            const double chi = b.nt * frcp(b.th.nu), c3 = chi * chi * chi, den = c3 + SA::Cv1c;
+            const double fv1 = c3 * frcp(den), dfv1 = 3.0 * chi * chi * SA::Cv1c * frcp(den * den);
             a.nt += a.nut * (fv1 + chi * dfv1);
             a.nu -= a.nut * chi * chi * dfv1;
         }
@@ -95,8 +95,8 @@ DAB_HD void boundaryPointAdj(const MeshView& m, const Params& q, const StateView
                 if (magUp > 0.0)
                     for (int j = 0; j < 3; j++)
                     {
-                        Ub[j] += a.nut * dM * d[j] / magUp;
-                        a.val[j] -= a.nut * dM * d[j] / magUp;
+                        Ub[j] += a.nut * dM * d[j] * frcp(magUp);
+                        a.val[j] -= a.nut * dM * d[j] * frcp(magUp);
                     }
                 a.nu += a.nut * dNu;
             }
@@ -126,7 +126,7 @@ struct cRevA
         const int nT = m.nCtot, nC = m.nC;
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
         const double V = m.V[c];
-        const double psiPc = x.p[c] * (q.nrP ? 1.0 / V : 1.0);
+        const double psiPc = x.p[c] * (q.nrP ? frcp(V) : 1.0);
         const double rhoc = r.rho[c], rAUc = r.rAU[c];
         double HbA[3] = {0, 0, 0}, rAUb = 0.0, pb = 0.0, Tb = 0.0, ntb = 0.0, nutPb = 0.0, gPb[3] = {0, 0, 0}, Ub[3] = {0, 0, 0}, rhob = 0.0;
         DAB_FACE_PREFETCH(NF)
@@ -136,12 +136,12 @@ struct cRevA
             if (fr.f < 0) break;
             const int f = fr.f;
             const double mS = m.magSf[f], dl = m.delta[f];
-            const double cphi = q.nrPhi ? 1.0 / mS : 1.0;
+            const double cphi = q.nrPhi ? frcp(mS) : 1.0;
             const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
             if (!fr.bnd)
             {
                 const int n = fr.n;
-                const double psiPn = x.p[n] * (q.nrP ? 1.0 / m.V[n] : 1.0);
+                const double psiPn = x.p[n] * (q.nrP ? frcp(m.V[n]) : 1.0);
                 // F_f enters pRes_own with +1, pRes_nei with -1, phiRes_f with +1
                 const double Fb = cphi * x.phi[f] + fr.s * (psiPc - psiPn);
                 const double w = m.w[f];
@@ -163,7 +163,7 @@ struct cRevA
                     // F = phid p_f - gam |S| sn, phid = psi_f ph, p_f = wf p_own + (1 - wf) p_nei (cFaceF); this cell's share
                     const int o = fr.s > 0 ? c : n, nn = fr.s > 0 ? n : c;
                     const double Tc = s.T[c];
-                    const double psif = wc / (q.Rg * Tc) + wn / (q.Rg * s.T[n]);
+                    const double psif = wc * frcp(q.Rg * Tc) + wn * frcp(q.Rg * s.T[n]);
                     const double phid = psif * ph;
                     const double up = phid >= 0.0 ? 1.0 : 0.0;
                     double wf = up, dLimDr = 0.0, gradf = 1.0, gradcf = 0.0;
@@ -176,7 +176,7 @@ struct cRevA
                     }
                     const double pS = wf * s.p[o] + (1.0 - wf) * s.p[nn];
                     for (int j = 0; j < 3; j++) HbA[j] += wc * Sv[j] * psif * pS * Fb;
-                    Tb -= wc / (q.Rg * Tc * Tc) * ph * pS * Fb;
+                    Tb -= wc * frcp(q.Rg * Tc * Tc) * ph * pS * Fb;
                     pb += (fr.s > 0 ? wf : 1.0 - wf) * phid * Fb;
                     if (dLimDr != 0.0)
                     {
@@ -237,12 +237,12 @@ struct cRevA
         double Mbv[3];
         for (int j = 0; j < 3; j++)
         {
-            const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) / rAUc;
+            const double M = (Uc[j] - r.HbyA[(size_t)j * nT + c]) * frcp(rAUc);
             const double psiU = cU * x.U[3 * c + j];
             const double Mb = psiU - rAUc * HbA[j];
             Mbv[j] = Mb;
             rAUtot -= M * HbA[j];
-            const double mt = Mb / V;
+            const double mt = Mb * frcp(V);
             a.mt[(size_t)j * nT + c] = mt;
             a.Udir[(size_t)j * nC + c] = Ub[j] + HbA[j] + D0 * mt;
             a.gPb[(size_t)j * nT + c] = gPb[j] + psiU;
@@ -256,7 +256,7 @@ struct cRevA
             a.Udir[(size_t)2 * nC + c] += rhoc * (Mbv[0] * w[1] - Mbv[1] * w[0]);
             rhob += Mbv[0] * (w[1] * Uc[2] - w[2] * Uc[1]) + Mbv[1] * (w[2] * Uc[0] - w[0] * Uc[2]) + Mbv[2] * (w[0] * Uc[1] - w[1] * Uc[0]);
         }
-        a.Dn[c] = -rAUc * rAUc * rAUtot / V;
+        a.Dn[c] = -rAUc * rAUc * rAUtot * frcp(V);
         a.pdir[c] = pb;
         a.Tdir[c] = Tb;
         a.cRho[c] = rhob;
@@ -285,18 +285,18 @@ struct cRevB
         double gUc[9], gNc[3];
         for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
         const double ntc = q.turb ? s.nt[c] : 0.0;
-        const double Gc = rhoc * (ntc + nuc) / SA::sigma;
+        const double Gc = rhoc * (ntc + nuc) * (1.0 / SA::sigma);
         for (int i = 0; i < 3; i++) gNc[i] = q.turb ? r.gNt[(size_t)i * nT + c] : 0.0;
         const double trc = gUc[0] + gUc[4] + gUc[8];
         const double V = m.V[c];
         const double mtc[3] = {a.mt[c], a.mt[(size_t)nT + c], a.mt[(size_t)2 * nT + c]};
         const double Dnc = a.Dn[c], flc = r.flag[c];
-        const double D2c = Dnc / q.alphaU;
+        const double D2c = Dnc * frcp(q.alphaU);
         const double D1c = flc != 0.0 ? flc * D2c : 0.0;
         const double soc = flc != 0.0 ? 0.0 : D2c;
         const double D0c = D1c + mtc[0] * Uc[0] + mtc[1] * Uc[1] + mtc[2] * Uc[2];
         const double psiN = q.turb ? x.nt[c] : 0.0;
-        const double qc = psiN * (q.nrNut ? 1.0 / V : 1.0);
+        const double qc = psiN * (q.nrNut ? frcp(V) : 1.0);
         const double zc = psiN * (q.nrNut ? 1.0 : V);
 
         double U2[3] = {0, 0, 0}, nt2 = 0.0, muEb = 0.0, gUb[9], gNb[3] = {0, 0, 0};
@@ -324,7 +324,7 @@ struct cRevB
                 const double muEn = r.muE[n];
                 const double mtn[3] = {a.mt[n], a.mt[(size_t)nT + n], a.mt[(size_t)2 * nT + n]};
                 const double Dnn = a.Dn[n], fln = r.flag[n];
-                const double D2n = Dnn / q.alphaU;
+                const double D2n = Dnn * frcp(q.alphaU);
                 const double D1n = fln != 0.0 ? fln * D2n : 0.0;
                 const double son = fln != 0.0 ? 0.0 : D2n;
                 const double D0n = D1n + mtn[0] * Un[0] + mtn[1] * Un[1] + mtn[2] * Un[2];
@@ -406,10 +406,10 @@ struct cRevB
                 if (q.turb)
                 {
                     const double ntn = s.nt[n];
-                    const double qn = x.nt[n] * (q.nrNut ? 1.0 / m.V[n] : 1.0);
+                    const double qn = x.nt[n] * (q.nrNut ? frcp(m.V[n]) : 1.0);
                     const double wpc = schN == DIV_LINEAR ? wc : wupc;
                     const double wpn = schN == DIV_LINEAR ? wn : 1.0 - wupc;
-                    const double Gn = r.rho[n] * (ntn + r.nuL[n]) / SA::sigma;
+                    const double Gn = r.rho[n] * (ntn + r.nuL[n]) * (1.0 / SA::sigma);
                     const double gf = (wc * Gc + wn * Gn) * mS;
                     const double g = gf * dl;
                     nt2 += qc * (wpc * mf + g - mf) + qn * (-mf + wpn * mf - g);
@@ -437,16 +437,16 @@ struct cRevB
                     for (int i = 0; i < 3; i++) gNb[i] += wc * kv[i] * cgb;
                     // adjoint of G_c = rho_c (nuTilda_c + nu_c) / sigma
                     const double Gcb = wc * mS * (dl * gb + gfb);
-                    nt2 += Gcb * rhoc / SA::sigma;
-                    nub += Gcb * rhoc / SA::sigma;
-                    rhob += Gcb * (ntc + nuc) / SA::sigma;
+                    nt2 += Gcb * rhoc * (1.0 / SA::sigma);
+                    nub += Gcb * rhoc * (1.0 / SA::sigma);
+                    rhob += Gcb * (ntc + nuc) * (1.0 / SA::sigma);
                 }
             }
             else
             {
                 BoundaryPoint bp;
                 boundaryPoint<true>(m, q, s, r, f, c, bp);
-                const double im = 1.0 / mS;
+                const double im = frcp(mS);
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 const double G = bp.muE * mS;
                 BoundaryAdj ba;
@@ -497,21 +497,21 @@ struct cRevB
                 if (q.turb)
                 {
                     // SA boundary part: NV += mf*nt_b - Gs*sngN - mf*nt_c, Gs = rho_b (nt_b + nu_b)/sigma |S|
-                    const double Gs = bp.th.rho * (bp.nt + bp.th.nu) / SA::sigma * mS;
+                    const double Gs = bp.th.rho * (bp.nt + bp.th.nu) * (1.0 / SA::sigma) * mS;
                     mb += qc * (bp.nt - ntc);
                     ba.nt += qc * mf;
                     ba.sngN -= qc * Gs;
                     const double Gsb = -qc * bp.sngN;
-                    ba.rho += Gsb * (bp.nt + bp.th.nu) / SA::sigma * mS;
-                    ba.nt += Gsb * bp.th.rho / SA::sigma * mS;
-                    ba.nu += Gsb * bp.th.rho / SA::sigma * mS;
+                    ba.rho += Gsb * (bp.nt + bp.th.nu) * (1.0 / SA::sigma) * mS;
+                    ba.nt += Gsb * bp.th.rho * (1.0 / SA::sigma) * mS;
+                    ba.nu += Gsb * bp.th.rho * (1.0 / SA::sigma) * mS;
                     nt2 -= qc * mf;
                 }
                 boundaryPointAdj<true>(m, q, s, r, f, c, bp, ba, U2, pb, Tb, nt2, nutPb);
                 phib_acc += mb;
             }
             if (fr.s > 0)
-                y[offPhi + f] = (phib_acc - (q.nrPhi ? 1.0 / mS : 1.0) * x.phi[f]) * phiRowScale(q, mS);
+                y[offPhi + f] = (phib_acc - (q.nrPhi ? frcp(mS) : 1.0) * x.phi[f]) * phiRowScale(q, mS);
             else if (fr.n >= nC)
                 y[offPhi + f] = 0.0;
         }
@@ -553,7 +553,7 @@ struct cRevE
         const double hec = r.he[c], aEc = r.aE[c], Ekc = r.Ek[c];
         double gHc[3];
         for (int i = 0; i < 3; i++) gHc[i] = r.gHe[(size_t)i * nT + c];
-        const double qc = x.T[c] * (q.nrT ? 1.0 / m.V[c] : 1.0);
+        const double qc = x.T[c] * (q.nrT ? frcp(m.V[c]) : 1.0);
         double he2 = 0.0, aEb = 0.0, Ekb = 0.0, gHb[3] = {0, 0, 0};
         double Ub[3] = {0, 0, 0}, pb = 0.0, Tb = 0.0, ntb = 0.0, nutPb = 0.0;
         double twb[3] = {0.0, 0.0, 0.0}, gUt[9], gUtb[9]; // turboH: adjoint of this cell's work vector, grad(U) and its adjoint
@@ -582,7 +582,7 @@ struct cRevE
                 const bool ownUp = phi > 0.0;
                 const bool cUp = fr.s > 0 ? ownUp : !ownUp;
                 const double hen = r.he[n];
-                const double qn = x.T[n] * (q.nrT ? 1.0 / m.V[n] : 1.0);
+                const double qn = x.T[n] * (q.nrT ? frcp(m.V[n]) : 1.0);
                 const double wpc = schE == DIV_LINEAR ? wc : wupc;
                 const double wpn = schE == DIV_LINEAR ? wn : 1.0 - wupc;
                 const double gf = (wc * aEc + wn * r.aE[n]) * mS;
@@ -643,7 +643,7 @@ struct cRevE
                 phib_acc += qc * (bp.th.he - hec + bp.Ek - Ekc);
                 if (q.turboH)
                 {
-                    const double im = 1.0 / mS;
+                    const double im = frcp(mS);
                     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                     double Gb[9], Gbb[9], vr[3];
                     for (int j = 0; j < 3; j++)
@@ -703,7 +703,7 @@ struct cRevC
         const int nT = m.nCtot, nC = m.nC;
         const double heA = q.heIsE ? (q.Cp - q.Rg) : q.Cp;
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-        const double iVc = 1.0 / m.V[c];
+        const double iVc = frcp(m.V[c]);
         double Ub[3], pb = a.pdir[c], Tb = a.Tdir[c], nb = q.turb ? a.nt2[c] : 0.0, heb = a.cHe[c];
         for (int j = 0; j < 3; j++) Ub[j] = a.Udir[(size_t)j * nC + c] + a.U2[(size_t)j * nC + c];
         double gUbc[9], gPbc[3], gNbc[3], gHbc[3];
@@ -725,7 +725,7 @@ struct cRevC
             {
                 const int n = fr.n;
                 const double wc = fr.s > 0 ? m.w[f] : 1.0 - m.w[f];
-                const double iVn = 1.0 / m.V[n];
+                const double iVn = frcp(m.V[n]);
                 for (int j = 0; j < 3; j++)
                 {
                     double t = 0.0;
@@ -747,7 +747,7 @@ struct cRevC
             {
                 const int pa = m.bPatch[f - m.nIF];
                 const double phib = s.phi[f], dl = m.delta[f];
-                const double im = 1.0 / m.magSf[f];
+                const double im = frcp(m.magSf[f]);
                 const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                 double valb[3];
                 const double sngb[3] = {0.0, 0.0, 0.0};
@@ -777,18 +777,18 @@ struct cRevC
             for (int j = 0; j < 3; j++) Ub[j] += Ekb * Uc[j];
             if (q.heIsE)
             {
-                pb += Ekb / th.rho;
-                rhob -= Ekb * pc / (th.rho * th.rho);
+                pb += Ekb * frcp(th.rho);
+                rhob -= Ekb * pc * frcp(th.rho * th.rho);
             }
             Tb += heA * heb;
             const double alphab = kc * aEb;
-            rhob += kc * aEb * nut / q.Prt + muEb * (th.nu + nut);
-            nutb += kc * aEb * th.rho / q.Prt + muEb * th.rho;
+            rhob += kc * aEb * nut * frcp(q.Prt) + muEb * (th.nu + nut);
+            nutb += kc * aEb * th.rho * frcp(q.Prt) + muEb * th.rho;
             nub += muEb * th.rho;
             if (q.turb)
             {
-                const double chi = ntc / th.nu, c3 = chi * chi * chi, den = c3 + SA::Cv1c;
-                const double fv1 = c3 / den, dfv1 = 3.0 * chi * chi * SA::Cv1c / (den * den);
+                const double chi = ntc * frcp(th.nu), c3 = chi * chi * chi, den = c3 + SA::Cv1c;
+                const double fv1 = c3 * frcp(den), dfv1 = 3.0 * chi * chi * SA::Cv1c * frcp(den * den);
                 nb += nutb * (fv1 + chi * dfv1);
                 nub -= nutb * chi * chi * dfv1;
             }
@@ -808,7 +808,7 @@ DAB_HD double cForceFace(const MeshView& m, const Params& q, const StateView& s,
     const int nT = m.nCtot;
     const double mS = m.magSf[f];
     const double Sv[3] = {m.Sx[f], m.Sy[f], m.Sz[f]};
-    const double im = 1.0 / mS;
+    const double im = frcp(mS);
     const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
     double gUc[9];
     for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
@@ -817,21 +817,21 @@ DAB_HD double cForceFace(const MeshView& m, const Params& q, const StateView& s,
     if (fs.mode >= 2)
     {
         const double U2 = bp.bu.val[0] * bp.bu.val[0] + bp.bu.val[1] * bp.bu.val[1] + bp.bu.val[2] * bp.bu.val[2];
-        const double wA = mS / fs.areaSum;
+        const double wA = mS * frcp(fs.areaSum);
         const double SU = Sv[0] * bp.bu.val[0] + Sv[1] * bp.bu.val[1] + Sv[2] * bp.bu.val[2];
         double F, pTp = 0.0, pTT = 0.0, pTU = 0.0; // mode 4: d(pT)/dp, /dT, /d(|U|^2)
         if (fs.mode == 4)
         {
             // p (1 + (gamma-1)/2 Ma^2)^(gamma/(gamma-1)), Ma^2 = |U|^2/(gamma R T), R = Cp - Cp/gamma (DAFunctionTotalPressureRatio.C:96-125)
-            const double gam = fs.gamma, Rg = q.Cp - q.Cp / gam, ex = gam / (gam - 1.0);
-            const double Ma2 = U2 / (gam * Rg * bp.T);
+            const double gam = fs.gamma, Rg = q.Cp - q.Cp * frcp(gam), ex = gam * frcp(gam - 1.0);
+            const double Ma2 = U2 * frcp(gam * Rg * bp.T);
             const double base = 1.0 + 0.5 * (gam - 1.0) * Ma2;
             const double pw = pow(base, ex);
-            const double dMa = bp.p * ex * pw / base * 0.5 * (gam - 1.0); // d(pT)/d(Ma2)
+            const double dMa = bp.p * ex * pw * frcp(base) * 0.5 * (gam - 1.0); // d(pT)/d(Ma2)
             F = fs.scale * (bp.p * pw - fs.shift) * wA;
             pTp = pw;
-            pTU = dMa / (gam * Rg * bp.T);
-            pTT = -dMa * Ma2 / bp.T;
+            pTU = dMa * frcp(gam * Rg * bp.T);
+            pTT = -dMa * Ma2 * frcp(bp.T);
         }
         else
             F = fs.scale * (fs.mode == 2 ? (bp.p + 0.5 * bp.th.rho * U2 - fs.shift) * wA : bp.th.rho * SU);

@@ -3,8 +3,8 @@
 tag=${1:-r02y}
 cells=${2:-1000000}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_cyclic.py -m gpu -x -q > gpurun_out/${tag}_cyclic_tests.log 2>&1
-tail -3 gpurun_out/${tag}_cyclic_tests.log
+[ -z "$SKIP_TESTS" ] && timeout 600 python -m pytest tests/test_cyclic.py -m gpu -x -q > gpurun_out/${tag}_cyclic_tests.log 2>&1
+[ -z "$SKIP_TESTS" ] && tail -3 gpurun_out/${tag}_cyclic_tests.log
 DAB_SETUP_INFO=1 timeout 900 python bench.py --steps 30 --warmup 5 --mesh passage --solver DATurboFoam --cells $cells --no-gmres --no-cpu-baseline \
   > gpurun_out/${tag}_bench_cfg5_n1.json 2> gpurun_out/${tag}_bench_cfg5_n1.err
 python - <<PY
@@ -13,7 +13,7 @@ try:
     d = json.loads(open("gpurun_out/${tag}_bench_cfg5_n1.json").read().strip().splitlines()[-1])
     a = d.get("adjoint_solve") or {}
     print({k: d[k] for k in ("value", "ms_per_step", "n_gpus")}, d["roofline"]["frac"], d["roofline"]["kernels_ms"], d["config"]["workload"][:160], "setup %.1f" % d["config"]["setup_s"],
-          {k: a.get(k) for k in ("pc_s", "wall_s", "solve_s", "iterations", "n_matvec", "fail", "error")})
+          {k: a.get(k) for k in ("pc_s", "wall_s", "solve_s", "iterations", "n_matvec", "fail", "error")}, d.get("primal_solve"))
 except Exception as e:
     print("failed", e)
 PY
