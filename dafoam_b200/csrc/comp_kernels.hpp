@@ -31,24 +31,24 @@ DAB_HD double heOfT(const Params& q, double T) { return (q.heIsE ? (q.Cp - q.Rg)
 DAB_HD ThermoPoint thermoOf(const Params& q, double p, double T)
 {
     ThermoPoint t;
-    t.rho = p / (q.Rg * T);
+    t.rho = p * frcp(q.Rg * T);
     if (q.sutherland)
     {
         const double Cv = q.Cp - q.Rg;
-        t.mu = q.As * sqrt(T) / (1.0 + q.Ts / T);
-        t.alpha = t.mu * Cv * (1.32 + 1.77 * q.Rg / Cv) / q.Cp;
+        t.mu = q.As * sqrt(T) * frcp(1.0 + q.Ts * frcp(T));
+        t.alpha = t.mu * Cv * (1.32 + 1.77 * q.Rg * frcp(Cv)) * frcp(q.Cp);
     }
     else
     {
         t.mu = q.muC;
-        t.alpha = t.mu / q.Pr;
+        t.alpha = t.mu * frcp(q.Pr);
     }
-    t.nu = t.mu / t.rho;
+    t.nu = t.mu * frcp(t.rho);
     t.he = heOfT(q, T);
     return t;
 }
 
-DAB_HD double cpByCpv(const Params& q) { return q.heIsE ? q.Cp / (q.Cp - q.Rg) : 1.0; }
+DAB_HD double cpByCpv(const Params& q) { return q.heIsE ? q.Cp * frcp(q.Cp - q.Rg) : 1.0; }
 
 // boundary-face values and closures of one boundary face (from the cell values through the BCs)
 struct BoundaryPoint
@@ -65,7 +65,7 @@ template <bool WF>
 DAB_HD void boundaryPoint(const MeshView& m, const Params& q, const StateView& s, const RecordView& r, int f, int c, BoundaryPoint& b)
 {
     const int pa = m.bPatch[f - m.nIF];
-    const double phib = s.phi[f], dl = m.delta[f], im = 1.0 / m.magSf[f];
+    const double phib = s.phi[f], dl = m.delta[f], im = frcp(m.magSf[f]);
     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
     const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
     double uw[3];
@@ -77,8 +77,8 @@ DAB_HD void boundaryPoint(const MeshView& m, const Params& q, const StateView& s
     if (q.rhoFrozen)
     {
         // SIMPLE iterations: the boundary density follows the stored (relaxed) cell density; equal to psi_b*p_b at the fixed point
-        b.th.rho = r.rho[c] * (b.p * s.T[c]) / (s.p[c] * b.T);
-        b.th.nu = b.th.mu / b.th.rho;
+        b.th.rho = r.rho[c] * (b.p * s.T[c]) * frcp(s.p[c] * b.T);
+        b.th.nu = b.th.mu * frcp(b.th.rho);
     }
     b.nt = 0.0; b.sngN = 0.0; b.frN = 0.0; b.nut = 0.0;
     if (q.turb)
@@ -89,9 +89,9 @@ DAB_HD void boundaryPoint(const MeshView& m, const Params& q, const StateView& s
                    : nutBoundaryBasic(q.bcKind[F_NUT][pa], q.bcVal[F_NUT][pa][0], r.nut[c], b.nt, b.th.nu, dP, dNb);
     }
     b.muE = b.th.rho * (b.th.nu + b.nut);
-    b.aE = cpByCpv(q) * (b.th.alpha + b.th.rho * b.nut / q.Prt);
+    b.aE = cpByCpv(q) * (b.th.alpha + b.th.rho * b.nut * frcp(q.Prt));
     b.Ek = 0.5 * (b.bu.val[0] * b.bu.val[0] + b.bu.val[1] * b.bu.val[1] + b.bu.val[2] * b.bu.val[2]);
-    if (q.heIsE) b.Ek += b.p / b.th.rho;
+    if (q.heIsE) b.Ek += b.p * frcp(b.th.rho);
 }
 
 template <int NF>
@@ -113,16 +113,16 @@ struct cFwdA
         {
             // SIMPLE iterations: rho is the relaxed field of the previous iteration (reference pEqnRhoSimple.H rho.relax())
             th.rho = r.rho[c];
-            th.nu = th.mu / th.rho;
+            th.nu = th.mu * frcp(th.rho);
         }
-        const double nut = q.turb ? ntc * fv1f(ntc / th.nu) : 0.0;
+        const double nut = q.turb ? ntc * fv1f(ntc * frcp(th.nu)) : 0.0;
         r.rho[c] = th.rho;
         r.nuL[c] = th.nu;
         r.nut[c] = nut;
         r.muE[c] = th.rho * (th.nu + nut);
-        r.aE[c] = cpByCpv(q) * (th.alpha + th.rho * nut / q.Prt);
+        r.aE[c] = cpByCpv(q) * (th.alpha + th.rho * nut * frcp(q.Prt));
         r.he[c] = th.he;
-        r.Ek[c] = 0.5 * (Uc[0] * Uc[0] + Uc[1] * Uc[1] + Uc[2] * Uc[2]) + (q.heIsE ? pc / th.rho : 0.0);
+        r.Ek[c] = 0.5 * (Uc[0] * Uc[0] + Uc[1] * Uc[1] + Uc[2] * Uc[2]) + (q.heIsE ? pc * frcp(th.rho) : 0.0);
         if (c >= m.nC) return;
         double gU[9], gP[3], gN[3], gH[3];
         for (int i = 0; i < 9; i++) gU[i] = 0.0;
@@ -147,7 +147,7 @@ struct cFwdA
             else
             {
                 const int pa = m.bPatch[f - m.nIF];
-                const double phib = s.phi[f], dl = m.delta[f], im = 1.0 / m.magSf[f];
+                const double phib = s.phi[f], dl = m.delta[f], im = frcp(m.magSf[f]);
                 const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                 BCv bu;
                 double uw[3];
@@ -164,7 +164,7 @@ struct cFwdA
                 for (int i = 0; i < 3; i++) gU[j * 3 + i] += S[i] * Uf[j];
             for (int i = 0; i < 3; i++) { gP[i] += S[i] * pf; gN[i] += S[i] * nf; gH[i] += S[i] * hf; }
         }
-        const double iV = 1.0 / m.V[c];
+        const double iV = frcp(m.V[c]);
         for (int i = 0; i < 9; i++) r.gU[(size_t)i * nT + c] = gU[i] * iV;
         for (int i = 0; i < 3; i++)
         {
@@ -195,7 +195,7 @@ struct cFwdB
         double gUc[9], gNc[3];
         for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
         const double ntc = q.turb ? s.nt[c] : 0.0;
-        const double Gc = rhoc * (ntc + nuc) / SA::sigma;
+        const double Gc = rhoc * (ntc + nuc) * (1.0 / SA::sigma);
         for (int i = 0; i < 3; i++) gNc[i] = q.turb ? r.gNt[(size_t)i * nT + c] : 0.0;
         const double trc = gUc[0] + gUc[4] + gUc[8];
         double D0 = 0.0, sumOff = 0.0, MV[3] = {0.0, 0.0, 0.0};
@@ -271,7 +271,7 @@ struct cFwdB
                     const double ntn = s.nt[n];
                     const double wp = schN == DIV_LINEAR ? wc : wup;
                     const double a = wp * mf;
-                    const double Gn = r.rho[n] * (ntn + r.nuL[n]) / SA::sigma;
+                    const double Gn = r.rho[n] * (ntn + r.nuL[n]) * (1.0 / SA::sigma);
                     const double gf = (wc * Gc + wn * Gn) * mS;
                     const double g = gf * dl;
                     NV += (a + g - mf) * ntc + (mf - a - g) * ntn;
@@ -295,7 +295,7 @@ struct cFwdB
             {
                 BoundaryPoint bp;
                 boundaryPoint<true>(m, q, s, r, f, c, bp);
-                const double im = 1.0 / mS;
+                const double im = frcp(mS);
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 const double G = bp.muE * mS;
                 D0 -= mf;
@@ -309,7 +309,7 @@ struct cFwdB
                     av += ic;
                     MV[j] += mf * bp.bu.val[j] - G * bp.bu.sng[j] - mf * Uc[j];
                 }
-                icMax += mx; icMin += mn; icAvg += av / 3.0;
+                icMax += mx; icMin += mn; icAvg += av * (1.0 / 3.0);
                 double Gb[9];
                 for (int j = 0; j < 3; j++)
                 {
@@ -324,20 +324,20 @@ struct cFwdB
                 }
                 if (q.turb)
                 {
-                    const double Gs = bp.th.rho * (bp.nt + bp.th.nu) / SA::sigma * mS;
+                    const double Gs = bp.th.rho * (bp.nt + bp.th.nu) * (1.0 / SA::sigma) * mS;
                     NV += mf * bp.nt - Gs * bp.sngN - mf * ntc;
                 }
             }
         }
-        const double V = m.V[c], iV = 1.0 / V;
+        const double V = m.V[c], iV = frcp(V);
         const double D1 = D0 + icMax;
         const double aD1 = fabs(D1);
         double D2, flag;
         if (aD1 > sumOff) { D2 = aD1; flag = D1 < 0.0 ? -1.0 : 1.0; }
         else { D2 = sumOff; flag = 0.0; }
-        const double Dn = D2 / q.alphaU - icMin;
+        const double Dn = D2 * frcp(q.alphaU) - icMin;
         const double A = (Dn + icAvg) * iV;
-        const double rAU = 1.0 / A;
+        const double rAU = frcp(A);
         r.rAU[c] = rAU;
         r.D0[c] = D0;
         r.flag[c] = flag;
@@ -499,7 +499,7 @@ struct cFwdE
                 EV += mf * (bp.Ek - Ekc);
                 if (q.turboH)
                 {
-                    const double im = 1.0 / mS;
+                    const double im = frcp(mS);
                     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                     double Gb[9], twb[3], vr[3];
                     for (int j = 0; j < 3; j++)
@@ -516,7 +516,7 @@ struct cFwdE
         }
         if (m.fvS) // - fvSourceEnergy = -(fvSource & U)
             EV -= m.V[c] * (m.fvS[c] * s.U[3 * c] + m.fvS[(size_t)nC + c] * s.U[3 * c + 1] + m.fvS[(size_t)2 * nC + c] * s.U[3 * c + 2]);
-        R[4 * (size_t)nC + c] = EV * (q.nrT ? 1.0 / m.V[c] : 1.0);
+        R[4 * (size_t)nC + c] = EV * (q.nrT ? frcp(m.V[c]) : 1.0);
     }
 };
 
@@ -560,7 +560,7 @@ DAB_HD double cFaceF(const MeshView& m, const Params& q, const StateView& s, con
     if (q.transonic)
     {
         if (q.transonic == 2) return -gam * mS * sn; // preconditioner residual without div(phid,p)
-        const double phid = (w / (q.Rg * s.T[o]) + (1.0 - w) / (q.Rg * s.T[n])) * ph;
+        const double phid = (w * frcp(q.Rg * s.T[o]) + (1.0 - w) * frcp(q.Rg * s.T[n])) * ph;
         double wf;
         if (q.divPhidP == DIV_LINEAR) wf = w;
         else if (q.divPhidP == DIV_LIMITED_LINEAR)
@@ -619,11 +619,11 @@ struct cFwdC
                 F = bp.th.rho * ph - bp.th.rho * r.rAU[c] * m.magSf[f] * bp.sngP;
             }
             div += fr.s * F;
-            if (q.transonic == 3 && fr.s > 0) R[offPhi + f] = s.phi[f] * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0); // transonicPCOption 2
-            else if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0);
+            if (q.transonic == 3 && fr.s > 0) R[offPhi + f] = s.phi[f] * (q.nrPhi ? frcp(m.magSf[f]) : 1.0); // transonicPCOption 2
+            else if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? frcp(m.magSf[f]) : 1.0);
             else if (fr.n >= nC) R[offPhi + f] = 0.0;
         }
-        R[offP + c] = div * (q.nrP ? 1.0 / m.V[c] : 1.0);
+        R[offP + c] = div * (q.nrP ? frcp(m.V[c]) : 1.0);
     }
 };
 

@@ -102,7 +102,7 @@ struct cUEqnAssemble
                 e.off[(size_t)k * nC + c] = 0.0;
                 BoundaryPoint bp;
                 boundaryPoint<true>(m, q, s, r, f, c, bp);
-                const double im = 1.0 / mS;
+                const double im = frcp(mS);
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 const double G = bp.muE * mS;
                 D0 -= mf;
@@ -136,8 +136,8 @@ struct cUEqnAssemble
         const double D1 = D0 + icMax;
         const double aD1 = fabs(D1);
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
-        const double Dn = D2 / q.alphaU - icMin;
-        r.rAU[c] = V / (Dn + icAvg);
+        const double Dn = D2 * frcp(q.alphaU) - icMin;
+        r.rAU[c] = V * frcp(Dn + icAvg);
         double cor[3] = {0.0, 0.0, 0.0}; // MRF.DDt(rho, U), explicit
         if (m.mrfCell && m.mrfCell[c])
         {
@@ -251,7 +251,7 @@ struct cEEqnAssemble
                 X += mf * (bp.Ek - Ekc);
                 if (q.turboH)
                 {
-                    const double im = 1.0 / mS;
+                    const double im = frcp(mS);
                     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                     double Gb[9], twb[3], vr[3];
                     for (int j = 0; j < 3; j++)
@@ -270,7 +270,7 @@ struct cEEqnAssemble
         const double D1 = D0 + aic;
         const double aD1 = fabs(D1);
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
-        const double Dn = D2 / alphaE - ic;
+        const double Dn = D2 * frcp(alphaE) - ic;
         e.diag[c] = Dn + ic;
         e.b[c] = -X + (Dn - D0) * hec;
         (void)NF;
@@ -285,7 +285,7 @@ struct RhoRelax // rho <- rho + alpha (psi p - rho)   (rho = thermo.rho(); rho.r
     double alpha;
     DAB_HD void operator()(int c) const
     {
-        const double rn = s.p[c] / (q.Rg * s.T[c]);
+        const double rn = s.p[c] * frcp(q.Rg * s.T[c]);
         rho[c] += alpha * (rn - rho[c]);
     }
 };
@@ -298,7 +298,7 @@ struct TFromHe // T = (he - heB)/heA on the owned cells
     DAB_HD void operator()(int c) const
     {
         const double heA = q.heIsE ? (q.Cp - q.Rg) : q.Cp;
-        T[c] = (he[c] + q.Cp * q.TRef) / heA;
+        T[c] = (he[c] + q.Cp * q.TRef) * frcp(heA);
     }
 };
 
@@ -465,7 +465,7 @@ struct cNutEqnAssemble
         const int nT = m.nCtot, nC = m.nC;
         const int schN = q.divNut;
         const double ntc = s.nt[c], rhoc = r.rho[c], nuc = r.nuL[c];
-        const double Gc = rhoc * (ntc + nuc) / SA::sigma;
+        const double Gc = rhoc * (ntc + nuc) * (1.0 / SA::sigma);
         double gUc[9], gNc[3];
         for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
         for (int i = 0; i < 3; i++) gNc[i] = r.gNt[(size_t)i * nT + c];
@@ -490,7 +490,7 @@ struct cNutEqnAssemble
                 const double ntn = s.nt[n];
                 const double wp = schN == DIV_LINEAR ? wc : wup;
                 const double a = wp * mf;
-                const double gf = (wc * Gc + wn * r.rho[n] * (ntn + r.nuL[n]) / SA::sigma) * mS;
+                const double gf = (wc * Gc + wn * r.rho[n] * (ntn + r.nuL[n]) * (1.0 / SA::sigma)) * mS;
                 const double g = gf * dl;
                 const double off = mf - a - g;
                 e.off[(size_t)k * nC + c] = off;
@@ -516,7 +516,7 @@ struct cNutEqnAssemble
                 e.off[(size_t)k * nC + c] = 0.0;
                 BoundaryPoint bp;
                 boundaryPoint<true>(m, q, s, r, f, c, bp);
-                const double Gs = bp.th.rho * (bp.nt + bp.th.nu) / SA::sigma * mS;
+                const double Gs = bp.th.rho * (bp.nt + bp.th.nu) * (1.0 / SA::sigma) * mS;
                 const double icf = mf * (1.0 - bp.frN) + Gs * bp.frN * dl;
                 ic += icf;
                 aic += fabs(icf);
@@ -528,14 +528,14 @@ struct cNutEqnAssemble
         const double P = saSource(ntc, nuc, y, gUc, gNc, q.saFv3);
         const double St = saStilda(ntc, nuc, y, gUc, q.saFv3);
         const double mg2 = gNc[0] * gNc[0] + gNc[1] * gNc[1] + gNc[2] * gNc[2];
-        const double expl = -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * ntc;
+        const double expl = -(SA::Cb2 * (1.0 / SA::sigma)) * mg2 - SA::Cb1 * St * ntc;
         const double sp = ntc != 0.0 ? (P - expl) / ntc : 0.0;
         D0 += V * rhoc * sp;
         X += V * rhoc * expl;
         const double D1 = D0 + aic;
         const double aD1 = fabs(D1);
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
-        const double Dn = D2 / alphaN - ic;
+        const double Dn = D2 * frcp(alphaN) - ic;
         e.diag[c] = Dn + ic;
         e.b[c] = -X + (Dn - D0) * ntc;
         (void)NF;

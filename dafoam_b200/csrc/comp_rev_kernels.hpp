@@ -465,7 +465,7 @@ struct cRevB
                 double mb = -D0c, Gb_ = 0.0;
                 for (int j = 0; j < 3; j++)
                 {
-                    double icb = Dnc / 3.0;
+                    double icb = Dnc * (1.0 / 3.0);
                     if (j == kmin) icb -= Dnc;
                     if (j == kmax) icb += D1c * sgn(ic[j]);
                     mb += bp.bu.vic[j] * icb + mtc[j] * bp.bu.val[j];

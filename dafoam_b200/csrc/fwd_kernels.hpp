@@ -28,7 +28,7 @@ struct FwdA
     DAB_HD void operator()(int c) const
     {
         const int nT = m.nCtot;
-        if (q.turb) r.nut[c] = s.nt[c] * fv1f(s.nt[c] / q.nu);
+        if (q.turb) r.nut[c] = s.nt[c] * fv1f(s.nt[c] * frcp(q.nu));
         else r.nut[c] = 0.0;
         if (c >= m.nC) return;
         double gU[9], gP[3], gN[3];
@@ -58,7 +58,7 @@ struct FwdA
             {
                 const int b = f - m.nIF, pa = m.bPatch[b];
                 const double phib = s.phi[f], dl = m.delta[f];
-                const double im = 1.0 / m.magSf[f];
+                const double im = frcp(m.magSf[f]);
                 const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                 BCv bu;
                 double uw[3];
@@ -73,7 +73,7 @@ struct FwdA
                 for (int i = 0; i < 3; i++) gU[j * 3 + i] += S[i] * Uf[j];
             for (int i = 0; i < 3; i++) { gP[i] += S[i] * pf; gN[i] += S[i] * nf; }
         }
-        const double iV = 1.0 / m.V[c];
+        const double iV = frcp(m.V[c]);
         for (int i = 0; i < 9; i++) r.gU[(size_t)i * nT + c] = gU[i] * iV;
         for (int i = 0; i < 3; i++)
         {
@@ -88,7 +88,7 @@ struct FwdA
 // with fv2 = (1 + chi/Cv2)^-3, fv3 = (1 + chi fv1)(1/Cv2)(3(1 + chi/Cv2) + (chi/Cv2)^2)/(1 + chi/Cv2)^3, no clip.
 DAB_HD double saStilda(double nt, double nu, double y, const double* gU, int fv3)
 {
-    const double chi = nt / nu;
+    const double chi = nt * frcp(nu);
     const double fv1 = fv1f(chi);
     const double w01 = 0.5 * (gU[1 * 3 + 0] - gU[0 * 3 + 1]);
     const double w02 = 0.5 * (gU[2 * 3 + 0] - gU[0 * 3 + 2]);
@@ -97,13 +97,13 @@ DAB_HD double saStilda(double nt, double nu, double y, const double* gU, int fv3
     const double ky2 = (SA::kappa * y) * (SA::kappa * y);
     if (fv3)
     {
-        const double t = 1.0 + chi / SA::Cv2, t3 = t * t * t;
-        const double fv2 = 1.0 / t3;
-        const double f3 = (1.0 + chi * fv1) * (1.0 / SA::Cv2) * (3.0 * t + (chi / SA::Cv2) * (chi / SA::Cv2)) / t3;
-        return f3 * Omega + fv2 * nt / ky2;
+        const double t = 1.0 + chi * (1.0 / SA::Cv2), t3 = t * t * t;
+        const double fv2 = frcp(t3);
+        const double f3 = (1.0 + chi * fv1) * ((1.0 / SA::Cv2)) * (3.0 * t + (chi * (1.0 / SA::Cv2)) * (chi * (1.0 / SA::Cv2))) * frcp(t3);
+        return f3 * Omega + fv2 * nt * frcp(ky2);
     }
-    const double fv2 = 1.0 - chi / (1.0 + chi * fv1);
-    const double S1 = Omega + fv2 * nt / ky2, S2 = SA::Cs * Omega;
+    const double fv2 = 1.0 - chi * frcp(1.0 + chi * fv1);
+    const double S1 = Omega + fv2 * nt * frcp(ky2), S2 = SA::Cs * Omega;
     return S1 > S2 ? S1 : S2;
 }
 
@@ -114,14 +114,14 @@ DAB_HD double saSource(double nt, double nu, double y, const double* gU, const d
     const double St = saStilda(nt, nu, y, gU, fv3);
     const double ky2 = (SA::kappa * y) * (SA::kappa * y);
     const double Sm = St > 1e-15 ? St : 1e-15;
-    double rr = nt / (Sm * ky2);
+    double rr = nt * frcp(Sm * ky2);
     rr = rr < 10.0 ? rr : 10.0;
     const double r2 = rr * rr;
     const double g = rr + SA::Cw2 * (r2 * r2 * r2 - rr);
     const double g2 = g * g;
-    const double fw = g * pow((1.0 + SA::Cw3p6) / (g2 * g2 * g2 + SA::Cw3p6), 1.0 / 6.0);
+    const double fw = g * cbrt(sqrt((1.0 + SA::Cw3p6) * frcp(g2 * g2 * g2 + SA::Cw3p6))); // x^(1/6)
     const double mg2 = gN[0] * gN[0] + gN[1] * gN[1] + gN[2] * gN[2];
-    return -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * nt + SA::Cw1 * fw * nt * nt / (y * y);
+    return -(SA::Cb2 * (1.0 / SA::sigma)) * mg2 - SA::Cb1 * St * nt + SA::Cw1 * fw * nt * nt * frcp(y * y);
 }
 
 // FEAT: bit 0 = linearUpwindV limiter compiled in, bit 1 = wall-function nut BC compiled in (the common
@@ -145,7 +145,7 @@ struct FwdB
         double gUc[9], gNc[3];
         for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
         const double ntc = q.turb ? s.nt[c] : 0.0;
-        const double Gc = (ntc + q.nu) / SA::sigma;
+        const double Gc = (ntc + q.nu) * (1.0 / SA::sigma);
         for (int i = 0; i < 3; i++) gNc[i] = q.turb ? r.gNt[(size_t)i * nT + c] : 0.0;
         const double trc = gUc[0] + gUc[4] + gUc[8];
 
@@ -227,7 +227,7 @@ struct FwdB
                     const double ntn = s.nt[n];
                     const double wp = schN == DIV_LINEAR ? wc : wup;
                     const double a = wp * mf;
-                    const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
+                    const double gf = (wc * Gc + wn * (ntn + q.nu) * (1.0 / SA::sigma)) * mS;
                     const double g = gf * dl;
                     NV += (a + g - mf) * ntc + (mf - a - g) * ntn;
                     if (schN == DIV_LINEAR_UPWIND)
@@ -253,7 +253,7 @@ struct FwdB
             else
             {
                 const int b = f - m.nIF, pa = m.bPatch[b];
-                const double im = 1.0 / mS;
+                const double im = frcp(mS);
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 BCv bu;
                 double uw[3];
@@ -278,7 +278,7 @@ struct FwdB
                     av += ic;
                     MV[j] += mf * bu.val[j] - G * bu.sng[j] - mf * Uc[j];
                 }
-                icMax += mx; icMin += mn; icAvg += av / 3.0;
+                icMax += mx; icMin += mn; icAvg += av * (1.0 / 3.0);
                 // dev2 boundary term: boundary grad(U) = cell value with the normal component replaced by snGrad
                 double Gb[9]; // Gb[j*3+i] = d_i U_j at the face
                 for (int j = 0; j < 3; j++)
@@ -294,21 +294,21 @@ struct FwdB
                 }
                 if (q.turb)
                 {
-                    const double Gs = (ntb + q.nu) / SA::sigma * mS;
+                    const double Gs = (ntb + q.nu) * (1.0 / SA::sigma) * mS;
                     NV += mf * ntb - Gs * sngN - mf * ntc;
                 }
             }
         }
-        const double V = m.V[c], iV = 1.0 / V;
+        const double V = m.V[c], iV = frcp(V);
         // relax (fvMatrix::relax, OpenFOAM-v1812)
         const double D1 = D0 + icMax;
         const double aD1 = fabs(D1);
         double D2, flag;
         if (aD1 > sumOff) { D2 = aD1; flag = D1 < 0.0 ? -1.0 : 1.0; }
         else { D2 = sumOff; flag = 0.0; }
-        const double Dn = D2 / q.alphaU - icMin;
+        const double Dn = D2 * frcp(q.alphaU) - icMin;
         const double A = (Dn + icAvg) * iV;
-        const double rAU = 1.0 / A;
+        const double rAU = frcp(A);
         r.rAU[c] = rAU;
         r.D0[c] = D0;
         r.flag[c] = flag;
@@ -389,7 +389,7 @@ struct FwdC
                 if (q.constrainHbyA && !assignable)
                 {
                     const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-                    const double im = 1.0 / mS;
+                    const double im = frcp(mS);
                     const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
                     BCv bu;
                     double uw[3];
@@ -405,10 +405,10 @@ struct FwdC
                 F = ph - r.rAU[c] * mS * sn;
             }
             div += fr.s * F;
-            if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? 1.0 / m.magSf[f] : 1.0);
+            if (fr.s > 0) R[offPhi + f] = (F - s.phi[f]) * (q.nrPhi ? frcp(m.magSf[f]) : 1.0);
             else if (fr.n >= nC) R[offPhi + f] = 0.0; // cut face whose phi belongs to the neighbouring rank
         }
-        R[offP + c] = -div * (q.nrP ? 1.0 / m.V[c] : 1.0);
+        R[offP + c] = -div * (q.nrP ? frcp(m.V[c]) : 1.0);
     }
 };
 

@@ -117,7 +117,7 @@ struct UEqnAssemble
             {
                 e.off[(size_t)k * nC + c] = 0.0;
                 const int b = f - m.nIF, pa = m.bPatch[b];
-                const double im = 1.0 / mS;
+                const double im = frcp(mS);
                 const double nh[3] = {Sv[0] * im, Sv[1] * im, Sv[2] * im};
                 BCv bu;
                 double uw[3];
@@ -164,8 +164,8 @@ struct UEqnAssemble
         const double D1 = D0 + icMax;
         const double aD1 = fabs(D1);
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
-        const double Dn = D2 / q.alphaU - icMin;
-        r.rAU[c] = V / (Dn + icAvg);
+        const double Dn = D2 * frcp(q.alphaU) - icMin;
+        r.rAU[c] = V * frcp(Dn + icAvg);
         double cor[3] = {0.0, 0.0, 0.0}; // MRF.DDt(U), explicit
         if (m.mrfCell && m.mrfCell[c])
         {
@@ -208,7 +208,7 @@ struct JacobiSweep
         {
             double rhs = e.b[(size_t)j * nC + c];
             if (g) rhs -= V[c] * g[(size_t)j * nT + c];
-            xn[(size_t)NC * c + j] = (rhs - acc[j]) / e.diag[(size_t)j * nC + c];
+            xn[(size_t)NC * c + j] = (rhs - acc[j]) * frcp(e.diag[(size_t)j * nC + c]);
         }
     }
 };
@@ -283,7 +283,7 @@ struct RAtKernel
     {
         double h1 = 0.0;
         for (int k = 0; k < e.maxCF; k++) h1 -= e.off[(size_t)k * e.nC + c];
-        rAt[c] = 1.0 / (1.0 / rAU[c] - h1 / V[c]);
+        rAt[c] = frcp(1.0 / rAU[c] - h1 / V[c]);
     }
 };
 
@@ -305,7 +305,7 @@ struct HbyAKernel
             const double o = e.off[(size_t)k * nC + c];
             for (int j = 0; j < 3; j++) acc[j] += o * s.U[3 * n + j];
         }
-        const double rAU = r.rAU[c], iV = 1.0 / V[c];
+        const double rAU = r.rAU[c], iV = frcp(V[c]);
         for (int j = 0; j < 3; j++)
         {
             const double M = (e.diag[(size_t)j * nC + c] * s.U[3 * c + j] + acc[j] - e.b[(size_t)j * nC + c]) * iV;
@@ -324,7 +324,7 @@ DAB_HD double phiHbyABoundary(const MeshView& m, const Params& q, const StateVie
     if (q.constrainHbyA && !assignable)
     {
         const double Uc[3] = {s.U[3 * c], s.U[3 * c + 1], s.U[3 * c + 2]};
-        const double im = 1.0 / m.magSf[f];
+        const double im = frcp(m.magSf[f]);
         const double nh[3] = {m.Sx[f] * im, m.Sy[f] * im, m.Sz[f] * im};
         BCv bu;
         double uw[3];
@@ -512,7 +512,7 @@ struct NutEqnAssemble
         const int nT = m.nCtot, nC = m.nC;
         const int schN = q.divNut;
         const double ntc = s.nt[c];
-        const double Gc = (ntc + q.nu) / SA::sigma;
+        const double Gc = (ntc + q.nu) * (1.0 / SA::sigma);
         double gUc[9], gNc[3];
         for (int i = 0; i < 9; i++) gUc[i] = r.gU[(size_t)i * nT + c];
         for (int i = 0; i < 3; i++) gNc[i] = r.gNt[(size_t)i * nT + c];
@@ -538,7 +538,7 @@ struct NutEqnAssemble
                 const double ntn = s.nt[n];
                 const double wp = schN == DIV_LINEAR ? wc : wup;
                 const double a = wp * mf;
-                const double gf = (wc * Gc + wn * (ntn + q.nu) / SA::sigma) * mS;
+                const double gf = (wc * Gc + wn * (ntn + q.nu) * (1.0 / SA::sigma)) * mS;
                 const double g = gf * dl;
                 const double off = mf - a - g;
                 e.off[(size_t)k * nC + c] = off;
@@ -565,7 +565,7 @@ struct NutEqnAssemble
                 const int b = f - m.nIF, pa = m.bPatch[b];
                 double ntb, sngN, frN;
                 bcScalar(q.bcKind[F_NUTILDA][pa], q.bcVal[F_NUTILDA][pa][0], ntc, mf, dl, ntb, sngN, frN);
-                const double Gs = (ntb + q.nu) / SA::sigma * mS;
+                const double Gs = (ntb + q.nu) * (1.0 / SA::sigma) * mS;
                 const double icf = mf * (1.0 - frN) + Gs * frN * dl;
                 ic += icf;
                 aic += fabs(icf);
@@ -578,7 +578,7 @@ struct NutEqnAssemble
         const double P = saSource(ntc, q.nu, y, gUc, gNc, q.saFv3); // -Cb2/sigma|grad nt|^2 - Cb1 St nt + Cw1 fw nt^2/y^2
         const double St = saStilda(ntc, q.nu, y, gUc, q.saFv3);
         const double mg2 = gNc[0] * gNc[0] + gNc[1] * gNc[1] + gNc[2] * gNc[2];
-        const double expl = -(SA::Cb2 / SA::sigma) * mg2 - SA::Cb1 * St * ntc; // explicit part of P
+        const double expl = -(SA::Cb2 * (1.0 / SA::sigma)) * mg2 - SA::Cb1 * St * ntc; // explicit part of P
         const double sp = ntc != 0.0 ? (P - expl) / ntc : 0.0;                  // Cw1 fw nt / y^2
         D0 += V * sp;
         X += V * expl;
@@ -586,7 +586,7 @@ struct NutEqnAssemble
         const double D1 = D0 + aic;
         const double aD1 = fabs(D1);
         const double D2 = aD1 > sumOff ? aD1 : sumOff;
-        const double Dn = D2 / alphaN - ic;
+        const double Dn = D2 * frcp(alphaN) - ic;
         e.diag[c] = Dn + ic;
         e.b[c] = -X + (Dn - D0) * ntc;
     }
@@ -642,8 +642,8 @@ struct SgsColour
             const int cn = colourOf[n];
             if (backward ? cn > colour : cn < colour) acc += e.off[(size_t)k * nC + c] * z[n];
         }
-        if (backward) z[c] -= acc / e.diag[c];
-        else z[c] = (rhs[c] - acc) / e.diag[c];
+        if (backward) z[c] -= acc * frcp(e.diag[c]);
+        else z[c] = (rhs[c] - acc) * frcp(e.diag[c]);
     }
 };
 

@@ -319,13 +319,13 @@ struct SA
 DAB_HD double fv1f(double chi)
 {
     const double c3 = chi * chi * chi;
-    return c3 / (c3 + SA::Cv1c);
+    return c3 * frcp(c3 + SA::Cv1c);
 }
 // d(nuTilda*fv1(nuTilda/nu))/d nuTilda
 DAB_HD double dnut_dnt(double nt, double nu)
 {
-    const double chi = nt / nu, c3 = chi * chi * chi, den = c3 + SA::Cv1c;
-    const double fv1 = c3 / den, dfv1 = 3.0 * chi * chi * SA::Cv1c / (den * den);
+    const double chi = nt * frcp(nu), c3 = chi * chi * chi, den = c3 + SA::Cv1c, iden = frcp(den);
+    const double fv1 = c3 * iden, dfv1 = 3.0 * chi * chi * SA::Cv1c * iden * iden;
     return fv1 + chi * dfv1;
 }
 
