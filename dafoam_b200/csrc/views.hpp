@@ -422,7 +422,7 @@ DAB_HD void luvLimit(const double* corr, const double* maxCorr, double* out)
     if (s > 0.0)
     {
         if (mm < 0.0) ratio = 0.0;
-        else if (s > mm) ratio = mm / (s + 1e-300);
+        else if (s > mm) ratio = mm * frcp(s + 1e-300);
     }
     for (int j = 0; j < 3; j++) out[j] = ratio * corr[j];
 }
@@ -434,9 +434,9 @@ DAB_HD void luvLimitAdj(const double* corr, const double* maxCorr, const double*
     if (s > 0.0 && mm < 0.0) return;
     if (s > 0.0 && s > mm)
     {
-        const double den = s + 1e-300, r = mm / den;
+        const double iden = frcp(s + 1e-300), r = mm * iden;
         const double g = outb[0] * corr[0] + outb[1] * corr[1] + outb[2] * corr[2];
-        const double mb = g / den, sb = -g * mm / (den * den);
+        const double mb = g * iden, sb = -g * mm * iden * iden;
         for (int j = 0; j < 3; j++)
         {
             corrb[j] += r * outb[j] + mb * maxCorr[j] + 2.0 * sb * corr[j];
