@@ -160,7 +160,7 @@ struct IluFactorColour
                 const int k = A.col[bi + e * si];
                 const int64_t bk = A.rowBase[k], sk = A.rowStride[k];
                 const int dk = A.diag[k], lk = A.rowLen[k];
-                const double lik = A.val[bi + e * si] / A.val[bk + dk * sk];
+                const double lik = A.val[bi + e * si] * A.val[bk + dk * sk]; // finished rows hold 1 / u_kk
                 A.val[bi + e * si] = lik;
                 if (lik == 0.0) continue;
                 // both rows are sorted by column: one merge pass over (upper part of row k, row i right of entry e) instead of a binary
@@ -175,7 +175,9 @@ struct IluFactorColour
             }
             double d = A.val[bi + di * si];
             if (!(fabs(d) > shift * rowMax)) d = (d < 0.0 ? -1.0 : 1.0) * (rowMax > 0.0 ? shift * rowMax : 1.0);
-            A.val[bi + di * si] = d;
+            // the reciprocal is what gets stored: the eliminations above and the back substitution multiply instead of dividing (an
+            // IEEE fp64 division per row sits in the dependency chain of the ~10 rows a thread solves one after the other)
+            A.val[bi + di * si] = 1.0 / d;
         }
     }
 };
@@ -263,7 +265,7 @@ struct TriUpperColour // x = U^{-1} x, in place; launched over nCells * TRI_LANE
                 acc = triRowDot<TRI_LANES>(A, bi, si, di + 1, A.rowLen[i], lane, x);
             }
             for (int o = 1; o < TRI_LANES; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, TRI_LANES);
-            if (on && lane == 0) x[i] = (x[i] - acc) / (A.valF ? (double)A.valF[bi + di * si] : A.val[bi + di * si]);
+            if (on && lane == 0) x[i] = (x[i] - acc) * (A.valF ? (double)A.valF[bi + di * si] : A.val[bi + di * si]); // the factor stores 1 / u_ii
             __syncwarp();
         }
 #else
@@ -280,7 +282,7 @@ struct TriUpperColour // x = U^{-1} x, in place; launched over nCells * TRI_LANE
             for (int o = 1; o < TRI_LANES; o <<= 1)
                 for (int l = 0; l < TRI_LANES; l++)
                     if (!(l & o)) part[l] += part[l | o];
-            x[i] = (x[i] - part[0]) / (A.valF ? (double)A.valF[bi + di * si] : A.val[bi + di * si]);
+            x[i] = (x[i] - part[0]) * (A.valF ? (double)A.valF[bi + di * si] : A.val[bi + di * si]);
         }
 #endif
     }

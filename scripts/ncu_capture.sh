@@ -13,5 +13,6 @@ ncu --set full --clock-control none --import-source on --kernel-name-base demang
 for r in rev fwd; do
   ncu -i gpurun_out/${tag}_${r}.ncu-rep --page raw --csv > gpurun_out/${tag}_${r}_raw.csv 2>/dev/null
 done
+rm -f gpurun_out/${tag}_*.ncu-rep  # the reports are 35 MB each: gpurun_out/ travels back only below 64 MiB
 tail -1 gpurun_out/${tag}_rev.log
 ls -la gpurun_out | tail -6

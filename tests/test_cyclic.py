@@ -293,6 +293,91 @@ def test_cyclic_compressible_passage_host_build(solver, energy, omega):
     assert worst < 1e-9
 
 
+def _channel_pair(lib_path, nz=3):
+    """the convergent channel once with its two z-planes as a translational cyclic pair, once as symmetry planes"""
+    out = []
+    for cyc in (True, False):
+        mesh = cases.channel(nx=12, ny=8, nz=nz)
+        bcs = cases.default_bcs_channel()
+        if cyc:
+            for p in mesh.patches:
+                if p["name"] in ("sym1", "sym2"):
+                    p.update(type="cyclic", neighbourPatch="sym2" if p["name"] == "sym1" else "sym1", transform="translational",
+                             separationVector=(0.0, 0.0, 0.1 if p["name"] == "sym1" else -0.1))
+            for f in bcs.values():
+                f[3]["sym1"] = dict(type="cyclic")
+                f[3]["sym2"] = dict(type="cyclic")
+        d = tempfile.mkdtemp(prefix="dab_cyc_")
+        cases.write_case(d, mesh, bcs)
+        sol = pyDASolvers("DASimpleFoam -python", dict(normalizeStates=NORM_STATES, normalizeResiduals=list(ALL_RES)), caseDir=d, _lib_path=lib_path)
+        out.append((mesh, sol))
+    return out
+
+
+def test_translational_cyclic_host_build():
+    """A flow that does not vary along z and has no z-velocity sees a translational cyclic pair exactly like two symmetry planes
+    (momentum and nuTilda rows of the residual); and the transposed product of the cyclic mesh passes the dot-product test against central
+    differences of its own residual."""
+    (mc, sc), (ms, ss) = _channel_pair(HOSTSIM)
+    nC, nz = mc.n_cells, 3
+    nxy = nC // nz
+    rng = np.random.default_rng(3)
+    # z-invariant state on the symmetric mesh (its state vector is the polyMesh one)
+    Ws = np.zeros(ss.getNLocalAdjointStates())
+    ss.getOFFields(Ws)
+    U = Ws[:3 * nC].reshape(nC, 3).copy()
+    col = np.arange(nC) % nxy  # cells are numbered i + nx*(j + ny*k)
+    U2 = (np.array([10.0, 0.4, 0.0])[None, :] * (1.0 + 0.05 * rng.uniform(-1, 1, (nxy, 3))))[col]
+    U2[:, 2] = 0.0
+    p2 = (3.0 * rng.uniform(-1, 1, nxy))[col]
+    nt2 = (4.5e-5 * (1.0 + 0.3 * rng.uniform(0, 1, nxy)))[col]
+    Sf, Cf = cases.quad_face_geometry(ms)
+    nIF = ms.n_internal_faces
+    nei = np.concatenate([ms.neighbour, ms.owner[nIF:]])
+    phi = np.einsum("ij,ij->i", 0.5 * (U2[ms.owner] + U2[nei]), Sf)
+    for pch in ms.patches:
+        if pch["type"] in ("wall", "symmetry"):
+            phi[pch["start"]:pch["start"] + pch["size"]] = 0.0
+    Wsym = np.concatenate([U2.ravel(), p2, nt2, phi])
+    ss.updateOFFields(Wsym)
+    Rs = np.zeros(Wsym.size)
+    ss.getResiduals(Rs)
+    # the same state on the cyclic mesh: merged numbering = polyMesh faces with the pair merged (phi through the pair is zero: U_z = 0)
+    order = cases.merged_face_order(mc)
+    Wm = np.concatenate([U2.ravel(), p2, nt2, phi[order]])
+    idx = sc.localStateIndex(nC, order.size)
+    owned = np.concatenate([np.ones(5 * nC, dtype=bool), sc.getLocalToGlobal("faceOwned").astype(bool)])
+    sc.updateOFFields(np.ascontiguousarray(Wm[idx]))
+    Rc = np.zeros(idx.size)
+    sc.getResiduals(Rc)
+    Rm = np.zeros(Wm.size)
+    Rm[idx[owned]] = Rc[owned]
+    # (not the pressure rows: rAU carries the component-averaged boundary diagonal of the momentum matrix, to which a symmetry plane
+    # contributes through its normal component and a cyclic pair does not)
+    for a, b in ((0, 3 * nC), (4 * nC, 5 * nC)):
+        assert rel_err(Rm[a:b], Rs[a:b]) < 1e-11, (a, b)
+    # dot-product test of the cyclic operator: psi^T (R(W + h v) - R(W - h v)) / 2h = v^T (J^T psi)
+    psi = rng.uniform(-1, 1, idx.size) * owned
+    v = rng.uniform(-1, 1, idx.size) * owned
+    v[5 * nC:] = 0.0  # cell states (every row of psi, the phi rows included, still takes part)
+    y = np.zeros(idx.size)
+    W0 = np.ascontiguousarray(Wm[idx])
+    sc.calcdRdWTPsiAD(psi, y)
+    # the product is y_j = s_j (J^T psi)_j with s_j the state scaling (normalizeStates; phi rows also carry the face area): perturb by s_j v_j
+    fa = np.linalg.norm(Sf, axis=1)[order][sc.getLocalToGlobal("faces")]
+    scale = np.concatenate([np.full(3 * nC, NORM_STATES["U"]), np.full(nC, NORM_STATES["p"]), np.full(nC, NORM_STATES["nuTilda"]),
+                            NORM_STATES["phi"] * fa])
+    h = 1e-5
+    Rp, Rn = np.zeros(idx.size), np.zeros(idx.size)
+    sc.updateOFFields(W0 + h * v * scale)
+    sc.getResiduals(Rp)
+    sc.updateOFFields(W0 - h * v * scale)
+    sc.getResiduals(Rn)
+    lhs = float(psi @ (Rp - Rn)) / (2.0 * h)
+    rhs = float(v @ y)
+    assert abs(lhs - rhs) < 1e-6 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
 def solve_on_passage(lib_path, solver="DATurboFoam", dims=(6, 6, 12)):
     """the bench's config-5 workload in small: state from cases.passage_state, dRdWTPC + GMRES, the solution checked with the product"""
     from dafoam_b200.pyDASolvers import KSP, Mat
