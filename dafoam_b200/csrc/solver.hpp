@@ -53,9 +53,21 @@ template <int NF> struct LaunchTraits<cEEqnAssemble<NF>> { static constexpr int 
 template <int NF> struct LaunchTraits<cNutEqnAssemble<NF>> { static constexpr int minBlocks = 3; };
 template <int NF> struct LaunchTraits<cPEqnAssemble<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cPhiUpdate<NF>> { static constexpr int minBlocks = 4; };
-template <int NF> struct LaunchTraits<cRevB<NF>> { static constexpr int minBlocks = 2; };
-template <int NF> struct LaunchTraits<cRevA<NF>> { static constexpr int minBlocks = 3; };
-template <int NF> struct LaunchTraits<cRevE<NF>> { static constexpr int minBlocks = 3; };
+// resident CTAs per SM of the compressible reverse kernels, measured on the 1M-cell DATurboFoam passage (profiles/r02_kernel_experiments.md):
+// cRevA 2 / 3 / 4 CTAs: 0.233 / 0.233 / 0.192 ms; cRevB 2 / 3: 0.581 / 0.551 (168 registers, 1.3 KB of spills, still faster);
+// cRevE (+cRevC) 2 / 3 / 4: 0.823 / 0.639 / 0.592 -- these kernels wait on gathers: more warps beat fewer spills
+#ifndef DAB_CREVA_MINBLOCKS
+#define DAB_CREVA_MINBLOCKS 4
+#endif
+#ifndef DAB_CREVB_MINBLOCKS
+#define DAB_CREVB_MINBLOCKS 3
+#endif
+#ifndef DAB_CREVE_MINBLOCKS
+#define DAB_CREVE_MINBLOCKS 4
+#endif
+template <int NF> struct LaunchTraits<cRevB<NF>> { static constexpr int minBlocks = DAB_CREVB_MINBLOCKS; };
+template <int NF> struct LaunchTraits<cRevA<NF>> { static constexpr int minBlocks = DAB_CREVA_MINBLOCKS; };
+template <int NF> struct LaunchTraits<cRevE<NF>> { static constexpr int minBlocks = DAB_CREVE_MINBLOCKS; };
 template <int NF> struct LaunchTraits<cRevC<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cFwdE<NF>> { static constexpr int minBlocks = 4; };
 template <int NF> struct LaunchTraits<cFwdC<NF>> { static constexpr int minBlocks = 4; };
