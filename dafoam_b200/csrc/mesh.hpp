@@ -398,6 +398,111 @@ struct HostMesh
         }
     }
 
+    // ---- exact distance to the wall faces for the cells next to a wall (OpenFOAM wallDist `correctWalls true`: patchWave ->
+    // cellDistFuncs::correctBoundaryFaceCells / correctBoundaryPointCells; face::nearestPointClassify decomposes a face into the
+    // triangles (p_i, p_i+1, face centre) and takes the closest point over them).  Opt-in (option wallDistCorrectWalls): the
+    // default keeps the centre distance everywhere, which is what the oracle and the committed golden vectors use.
+    static double distToTriangle(const double* a, const double* b, const double* c, const double* p)
+    {
+        // closest point on a triangle to p (Ericson, Real-Time Collision Detection 5.1.5), returned as a distance
+        double ab[3], ac[3], ap[3];
+        for (int k = 0; k < 3; k++) { ab[k] = b[k] - a[k]; ac[k] = c[k] - a[k]; ap[k] = p[k] - a[k]; }
+        auto dot = [](const double* x, const double* y) { return x[0] * y[0] + x[1] * y[1] + x[2] * y[2]; };
+        auto dist = [&](const double* q) { return std::sqrt((p[0] - q[0]) * (p[0] - q[0]) + (p[1] - q[1]) * (p[1] - q[1]) + (p[2] - q[2]) * (p[2] - q[2])); };
+        const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+        if (d1 <= 0.0 && d2 <= 0.0) return dist(a);
+        double bp[3];
+        for (int k = 0; k < 3; k++) bp[k] = p[k] - b[k];
+        const double d3 = dot(ab, bp), d4 = dot(ac, bp);
+        if (d3 >= 0.0 && d4 <= d3) return dist(b);
+        const double vc = d1 * d4 - d3 * d2;
+        double q[3];
+        if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0)
+        {
+            const double v = d1 / (d1 - d3);
+            for (int k = 0; k < 3; k++) q[k] = a[k] + v * ab[k];
+            return dist(q);
+        }
+        double cp[3];
+        for (int k = 0; k < 3; k++) cp[k] = p[k] - c[k];
+        const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+        if (d6 >= 0.0 && d5 <= d6) return dist(c);
+        const double vb = d5 * d2 - d1 * d6;
+        if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0)
+        {
+            const double w = d2 / (d2 - d6);
+            for (int k = 0; k < 3; k++) q[k] = a[k] + w * ac[k];
+            return dist(q);
+        }
+        const double va = d3 * d6 - d5 * d4;
+        if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0)
+        {
+            const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+            for (int k = 0; k < 3; k++) q[k] = b[k] + w * (c[k] - b[k]);
+            return dist(q);
+        }
+        const double den = 1.0 / (va + vb + vc), v = vb * den, w = vc * den;
+        for (int k = 0; k < 3; k++) q[k] = a[k] + ab[k] * v + ac[k] * w;
+        return dist(q);
+    }
+    double distToFace(int f, const double* p) const
+    {
+        const int n = fOff[f + 1] - fOff[f];
+        const int32_t* l = &fLab[fOff[f]];
+        const double* P = points.data();
+        if (n == 3) return distToTriangle(&P[3 * l[0]], &P[3 * l[1]], &P[3 * l[2]], p);
+        const double ctr[3] = {Cf[0][f], Cf[1][f], Cf[2][f]};
+        double best = 1e300;
+        for (int i = 0; i < n; i++) best = std::min(best, distToTriangle(&P[3 * l[i]], &P[3 * l[(i + 1) % n]], ctr, p));
+        return best;
+    }
+    void correctWallDistance(const std::vector<uint8_t>* only = nullptr)
+    {
+        // wall faces around every wall point
+        std::vector<std::vector<int>> pointWallFaces(nP);
+        std::vector<uint8_t> wallPoint(nP, 0);
+        for (int b = 0; b < nBF; b++)
+        {
+            if (patchGeom[bPatch[b]] != PG_WALL) continue;
+            const int f = nIF + b;
+            for (int q = fOff[f]; q < fOff[f + 1]; q++)
+            {
+                pointWallFaces[fLab[q]].push_back(f);
+                wallPoint[fLab[q]] = 1;
+            }
+        }
+        std::vector<double> corrected(nC, -1.0);
+        auto consider = [&](int c, int f) {
+            if (only && !(*only)[c]) return;
+            const double p[3] = {C[0][c], C[1][c], C[2][c]};
+            const double d = distToFace(f, p);
+            corrected[c] = corrected[c] < 0.0 ? d : std::min(corrected[c], d);
+        };
+        // cells that own a wall face: that face and the wall faces sharing a point with it
+        for (int b = 0; b < nBF; b++)
+        {
+            if (patchGeom[bPatch[b]] != PG_WALL) continue;
+            const int f = nIF + b, c = own[f];
+            for (int q = fOff[f]; q < fOff[f + 1]; q++)
+                for (int g : pointWallFaces[fLab[q]]) consider(c, g);
+        }
+        // cells that only touch the wall with a point (or an edge): the wall faces around that point
+        std::vector<uint8_t> faceCell(nC, 0);
+        for (int c = 0; c < nC; c++) faceCell[c] = corrected[c] >= 0.0;
+        for (int f = 0; f < nF; f++)
+            for (int side = 0; side < (f < nIF ? 2 : 1); side++)
+            {
+                if (side == 1 && f < (int)cyc.size() && cyc[f] > 0) continue; // the points of a coupled face are the owner side's
+                const int c = side == 0 ? own[f] : nei[f];
+                if (faceCell[c]) continue;
+                for (int q = fOff[f]; q < fOff[f + 1]; q++)
+                    if (wallPoint[fLab[q]])
+                        for (int g : pointWallFaces[fLab[q]]) consider(c, g);
+            }
+        for (int c = 0; c < nC; c++)
+            if (corrected[c] >= 0.0) yWall[c] = corrected[c];
+    }
+
     // frozen wall distance (meshWaveFrozen role, reference src/adjoint/DAMisc/meshWaveFrozen): distance
     // from the cell centre to the nearest wall-face centre, evaluated once
     // only != nullptr: wall distance of the flagged cells only (a rank of a decomposed run needs its own cells, not all of the global

@@ -320,12 +320,19 @@ struct Solver
         };
         hm.read(caseDir);
         lap("read polyMesh");
+        bool correctWalls = false; // option wallDistCorrectWalls (OpenFOAM wallDist correctWalls): needed before the other options are applied
+        if (!optionsJson.empty())
+        {
+            const JVal o = parseJson(optionsJson);
+            if (o.kind == JVal::Obj) correctWalls = o.numOr("wallDistCorrectWalls", 0.0) != 0.0;
+        }
         partitioned = nRanks > 1 || hm.hasCyclic();
         if (!partitioned)
         {
             hm.computeGeometry();
             lap("geometry");
             hm.computeWallDistance();
+            if (correctWalls) hm.correctWallDistance();
             lap("wall distance");
             part.nGlobalCells = hm.nC;
         }
@@ -351,6 +358,7 @@ struct Solver
                     if (cellPart[b] == rank) mine[a] = 1;
                 }
                 g.computeWallDistance(&mine);
+                if (correctWalls) g.correctWallDistance(&mine);
             }
             lap("wall distance (own cells)");
             extractLocalMesh(g, cellPart, rank, nRanks, hm, part);
