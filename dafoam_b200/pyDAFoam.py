@@ -66,7 +66,12 @@ class PYDAFOAM:
         self._pc = None
         self._ksp = None
         self._psi = {}
-        self._pcAge = 0  # primal solutions since the preconditioner was assembled (adjPCLag)
+        # adjPCLag bookkeeping of DAFoamSolver.solve_linear (reference mphys_dafoam.py:481-514): `solution_counter` advances once per
+        # design iteration IN WHICH DERIVATIVES ARE ASKED FOR (the first adjoint after a new primal solution, `renamed`), not per primal
+        # solution -- line-search primals do not age the preconditioner; it is re-assembled when (solution_counter - 1) % adjPCLag == 0
+        self.solution_counter = 1
+        self._renamed = True  # a primal solution not yet followed by an adjoint
+        self.nPCAssemblies = 0
 
     # ---- options -----------------------------------------------------------------------------------------
     def getOption(self, name):
@@ -88,7 +93,7 @@ class PYDAFOAM:
         """Solve the primal (reference pyDAFoam.py:800-821)."""
         self.primalFail = self.solver.solvePrimal()
         self.nSolvePrimals += 1
-        self._pcAge += 1  # the preconditioner now belongs to an earlier design: refreshed every adjPCLag (below)
+        self._renamed = True  # the next adjoint opens a new derivative iteration (adjPCLag counts those)
         self._psi = {}
 
     def solve_nonlinear(self, inputs=None):
@@ -138,6 +143,7 @@ class PYDAFOAM:
         self.solver.updateOFFields(np.ascontiguousarray(states, dtype=np.float64))
         self._pc = None
         self._psi = {}
+        self._renamed = True
 
     def getVolCoords(self):
         xv = np.zeros(3 * self.solver.getNLocalPoints(), self.dtype)
@@ -173,8 +179,13 @@ class PYDAFOAM:
         method = self.options.get("adjEqnSolMethod", "Krylov")
         if method not in ("Krylov", "fixedPoint"):  # reference mphys_dafoam.py:562
             raise RuntimeError("adjEqnSolMethod=%s not valid! Options are: Krylov or fixedPoint" % method)
-        if self._pc is None or self._pcAge >= max(1, int(self.getOption("adjPCLag"))):
-            self._pcAge = 0
+        renamed = self._renamed
+        if renamed:
+            self.solution_counter += 1
+            self._renamed = False
+        adjPCLag = max(1, int(self.getOption("adjPCLag")))
+        if self._pc is None or (renamed and (self.solution_counter - 1) % adjPCLag == 0):
+            self.nPCAssemblies += 1
             self._pc, self._ksp = Mat(), KSP()
             self.solver.calcdRdWT(1, self._pc)
             self.solver.createMLRKSPMatrixFree(self._pc, self._ksp)

@@ -252,6 +252,35 @@ def test_pydafoam_adjoint_method_switch():
         DASolver.solveAdjoint("CD")
 
 
+def test_pydafoam_pc_lag_counts_derivative_iterations():
+    """adjPCLag as in DAFoamSolver.solve_linear (reference mphys_dafoam.py:481-514): the counter advances with the first adjoint after
+    a new primal solution; primal solutions without derivatives (line searches) and further functions of the same iteration do not
+    age the preconditioner."""
+    import tempfile
+    from dafoam_b200.pyDAFoam import PYDAFOAM
+    mesh = cases.naca0012_ogrid(ni=24, nj=12, nk=1)
+    d = tempfile.mkdtemp(prefix="dab_pyd_")
+    cases.write_case(d, mesh, cases.default_bcs_naca())
+    fn = dict(FN, CL=dict(FN["CD"], direction=[0.0, 1.0, 0.0]))
+    opts = dict(solverName="DASimpleFoam", normalizeStates=NORM_STATES, function=fn, adjPCLag=2, primalMaxIters=5,
+                adjEqnOption=dict(gmresRelTol=1e-6, gmresMaxIters=600, gmresRestart=300))
+    DASolver = PYDAFOAM(options=opts, caseDir=d, _lib_path=HOSTSIM)
+    y = np.zeros(DASolver.solver.getNLocalCells())
+    DASolver.solver.getOFField("yWall", "scalar", y)
+    DASolver.setStates(cases.boundary_layer_state(mesh, y))
+    DASolver.solveAdjoint("CD")          # iteration 1: nothing assembled yet -> assembly 1
+    DASolver.solveAdjoint("CL")          # same iteration, second function: kept
+    assert DASolver.nPCAssemblies == 1 and DASolver.solution_counter == 2
+    DASolver()
+    DASolver()                           # a line-search primal: no derivatives asked for
+    DASolver.solveAdjoint("CD")          # iteration 2: (3 - 1) % 2 == 0 -> assembly 2
+    assert DASolver.nPCAssemblies == 2 and DASolver.solution_counter == 3
+    DASolver()
+    DASolver.solveAdjoint("CD")          # iteration 3: (4 - 1) % 2 != 0 -> kept
+    DASolver.solveAdjoint("CL")
+    assert DASolver.nPCAssemblies == 2 and DASolver.solution_counter == 4 and DASolver.adjointFail == 0
+
+
 def _solve_with(sol, W, extra):
     n = sol.getNLocalAdjointStates()
     sol.updateDAOption(dict(adjEqnOption=dict(gmresRelTol=1e-9, gmresMaxIters=600, gmresRestart=300, **extra)))
