@@ -191,6 +191,7 @@ def run_pydafoam_api(lib_path):
     DASolver.setOption("adjPCLag", 2)
     DASolver.updateDAOption()
     counts, totals = [], []
+    c0 = DASolver.solution_counter
     for k in range(3):
         xk = x + np.array([0.2 * (k + 1), 0.1 * (k + 1)])
         DASolver.set_solver_input({"patchV": xk})
@@ -198,7 +199,9 @@ def run_pydafoam_api(lib_path):
         totals.append(DASolver.calcTotalDeriv("CD", "patchV", xk))
         assert DASolver.adjointFail == 0
         counts.append(DASolver._ksp.stats.pc_assemblies - n0)
-    assert counts == [1, 1, 2], counts  # assembled for the 1st and 3rd design, reused for the 2nd
+    # re-assembled in the derivative iterations with (solution_counter - 1) % adjPCLag == 0, kept in between
+    expected = [int(v) for v in np.cumsum([1 if (c0 + k) % 2 == 0 else 0 for k in range(3)])]
+    assert counts == expected and counts[-1] in (1, 2), (counts, expected)
     DASolver.setOption("adjPCLag", 1)
     DASolver.updateDAOption()
     DASolver.set_solver_input({"patchV": x + np.array([0.4, 0.2])})
