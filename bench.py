@@ -303,6 +303,9 @@ def main():
                          "passage: BASELINE config 5's shape, one passage of an annular rotor row with cyclic sides and an MRF zone (use --solver DATurboFoam)")
     ap.add_argument("--solver", default="DASimpleFoam", choices=["DASimpleFoam", "DARhoSimpleFoam", "DATurboFoam"],
                     help="DARhoSimpleFoam: BASELINE config 3 (compressible airfoil; use --cells 2000000); DATurboFoam: config 5 (with --mesh passage)")
+    ap.add_argument("--reference-schemes", action="store_true",
+                    help="the schemes the reference's NACA0012 cases select: div(phi,U) linearUpwindV and nutUSpaldingWallFunction on the wing "
+                         "(the RevB<6,7> / FwdB<6,7> kernel variants instead of the light <6,0> ones); not the default workload")
     ap.add_argument("--primal-iters", type=int, default=None,
                     help="run that many SIMPLE iterations (solvePrimal on the GPU) from the synthetic state before the adjoint legs (1 GPU)")
     args = ap.parse_args()
@@ -351,6 +354,7 @@ def main():
     # only read: their own engine reads the polyMesh and keeps its partition, the state slice comes from the shared file
     mesh = None
     info = [None, None, 0, 0]
+    ref_kw = dict(div_u="bounded Gauss linearUpwindV grad(U)") if args.reference_schemes else {}
     if rank == 0 and passage:
         mesh = cases.annular_passage(nr=ni, nt=nj, nz=nk, r0=0.2, r1=0.35, lz=0.3, n_sectors=36)
         case_dir = tempfile.mkdtemp(prefix="dab_bench_")
@@ -375,9 +379,10 @@ def main():
             mesh = cases.naca0012_ogrid(ni=ni, nj=nj, nk=1, tile=tile)
         case_dir = tempfile.mkdtemp(prefix="dab_bench_")
         if comp:
-            cases.write_case(case_dir, mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c)), binary=True, thermo=thermo)
+            cases.write_case(case_dir, mesh, cases.compressible_bcs(cases.default_bcs_naca(U0=U0c, wall_function=args.reference_schemes)), binary=True,
+                             thermo=thermo, **ref_kw)
         else:
-            cases.write_case(case_dir, mesh, cases.default_bcs_naca(), binary=True)
+            cases.write_case(case_dir, mesh, cases.default_bcs_naca(wall_function=args.reference_schemes), binary=True, **ref_kw)
         info = [case_dir, None, mesh.n_cells, mesh.n_faces]
         if world > 1:
             from dafoam_b200.pyDASolvers import nccl_unique_id
@@ -546,7 +551,8 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s %s SA %s %dx%dx%d (%s tiles), %d cells global, %d cells / %d DOF "
                                "on this GPU; adjoint matvec dRdW^T*psi; working set per product ~%.0f MB >> 126 MB L2 (no explicit flush)"
-                               % (args.solver, "annular rotor passage (36 per row), cyclic sides + MRF zone," if passage else "NACA0012",
+                               % (args.solver, "annular rotor passage (36 per row), cyclic sides + MRF zone," if passage else
+                                  ("NACA0012 (linearUpwindV + Spalding wall function)" if args.reference_schemes else "NACA0012"),
                                   "radial x pitchwise x axial" if passage else ("swept tapered wing, 3-D O-grid" if wing else "O-grid, tile-major cell numbering"),
                                   ni, nj, nk, "x".join(str(t) for t in tile),
                                   nC_global, nC, n, (alg + 60 * 8 * nC) / 1e6),
