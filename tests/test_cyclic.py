@@ -434,6 +434,33 @@ def test_adjoint_solve_on_passage_cuda():
     assert its > 0
 
 
+def check_golden(lib_path, tol=1e-10):
+    """the committed vectors of tests/golden/make_golden_cyclic.py (oracle on the ring of passages): DATurboFoam + SA + MRF, cyclic sides"""
+    import os
+    from tests.golden.make_golden_cyclic import SPEC
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "passage_turbo_cyclic_4x4x6.npz"))
+    P = Pair(SPEC["turbulent"], SPEC["divU"], lib_path=lib_path, solver=SPEC["solver"], energy=SPEC["energy"], mrf_omega=SPEC["mrf_omega"])
+    assert np.allclose(P.state(), g["W"], rtol=1e-12, atol=0.0)  # the generator of the state has not drifted either (libm may differ in the last bit)
+    P.sol.updateOFFields(P.local(g["W"]))
+    R = np.zeros(P.idx.size)
+    P.sol.getResiduals(R)
+    y = np.zeros(P.idx.size)
+    P.sol.calcdRdWTPsiAD(P.local(g["psi"]), y)
+    Rm, ym = P.merged(R), P.merged(y)
+    for name, a, b in P.segments():
+        assert rel_err(Rm[a:b], g["R"][a:b]) < tol, ("R", name)
+        assert rel_err(ym[a:b], g["y"][a:b]) < tol, ("JTpsi", name)
+
+
+def test_cyclic_golden_host_build():
+    check_golden(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_cyclic_golden_cuda():
+    check_golden(None)
+
+
 @pytest.mark.gpu
 def test_cyclic_passage_equals_ring_cuda():
     worst = check_pair(Pair(True, "linearUpwindV", lib_path=None))
