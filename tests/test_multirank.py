@@ -12,7 +12,12 @@ from tests.common import ROOT
 
 
 def _write_passage(d, kind):
-    mesh = cases.annular_passage(nr=5, nt=6, nz=8, n_sectors=7)
+    if "axial" in kind:
+        # a long passage: the RCB cut is axial, so each rank holds parts of BOTH coupled patches (images copied inside the rank) next
+        # to an ordinary cut (ghosts from the other rank)
+        mesh = cases.annular_passage(nr=4, nt=4, nz=16, lz=0.9, n_sectors=7)
+    else:
+        mesh = cases.annular_passage(nr=5, nt=6, nz=8, n_sectors=7)
     bcs = cases.default_bcs_passage(Uin=(0.0, 0.0, 60.0 if "turbo" in kind else 10.0))
     kw = {}
     if "turbo" in kind:
@@ -72,7 +77,7 @@ def test_two_ranks_match_one_rank(kind):
     assert r.stdout.count(" ok: ") == 2, r.stdout
 
 
-@pytest.mark.parametrize("kind,port", [("passage", 29751), ("passageturbo", 29753), ("passageprimal", 29755)])
+@pytest.mark.parametrize("kind,port", [("passage", 29751), ("passageturbo", 29753), ("passageprimal", 29755), ("passageaxial", 29759)])
 def test_cyclic_passage_on_two_ranks(kind, port):
     """cyclic patch pairs across a partition cut (tests/mp_worker.py passage): images rotated inside the pack kernels"""
     d = tempfile.mkdtemp(prefix="dab_mp_")
