@@ -77,13 +77,15 @@ def test_two_ranks_match_one_rank(kind):
     assert r.stdout.count(" ok: ") == 2, r.stdout
 
 
-@pytest.mark.parametrize("kind,port", [("passage", 29751), ("passageturbo", 29753), ("passageprimal", 29755), ("passageaxial", 29759)])
-def test_cyclic_passage_on_two_ranks(kind, port):
-    """cyclic patch pairs across a partition cut (tests/mp_worker.py passage): images rotated inside the pack kernels"""
+@pytest.mark.parametrize("kind,port,nproc", [("passage", 29751, 2), ("passageturbo", 29753, 2), ("passageprimal", 29755, 2),
+                                             ("passageaxial", 29759, 3), ("passageturbo", 29761, 4)])
+def test_cyclic_passage_on_two_ranks(kind, port, nproc):
+    """cyclic patch pairs across partition cuts (tests/mp_worker.py passage): images rotated inside the pack kernels; 2, 3 and 4 ranks
+    (BASELINE config 5 runs on 8)"""
     d = tempfile.mkdtemp(prefix="dab_mp_")
     _write_passage(d, kind)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), d, kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, OMP_NUM_THREADS="1"), cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count(" ok: ") == 2, r.stdout
+    assert r.stdout.count(" ok: ") == nproc, r.stdout
