@@ -209,6 +209,10 @@ struct Solver
     int coarseSparseAP = 1;   // keep the columns A*(P e_a) the probing computes and apply v - A P yc as a sparse product (0: matrix-free product per application)
     int coarseProbeReach = 6; // cell levels a pressure perturbation reaches through the transposed Jacobian (coloured probing of the coarse operator; 0 = one product per aggregate)
     int transonicPCOption = -1; // reference pyDAFoam.py:394-396 (-1 none, 1 no div(phid,p) in the PC residual, 2 phiRes = phi there)
+    // adjEqnOption.pcPattern (extension): "uniform" = every state of a cell is coupled to every cell residual within pcConLevel cell levels
+    // and to the phi residuals of its own faces; "stateInfo" = the reference's per-(residual, state) connectivity levels
+    // (DAStateInfoSimpleFoam.C:75-99, DASpalartAllmaras.C:364-373, capped by maxResConLv4JacPCMat, pyDAFoam.py:568-582) -- DASimpleFoam only
+    std::string pcPattern = "uniform";
     int pcBlockCells = 0;          // > 0: block-Jacobi ILU with the natural cell order inside blocks of that many consecutive cells (PCASM overlap 0 + natural-order PCILU), level-scheduled
     int pcExtraColourRadius = 0;   // extra colouring radius of the ILU ordering (0: the minimum that keeps same-colour rows independent)
     int globalPCIters = 0;         // Richardson sweeps wrapped around the preconditioner (reference adjEqnOption.globalPCIters)
@@ -717,6 +721,9 @@ struct Solver
             if (idrS < 1 || idrS > 16) throw Error("adjEqnOption.idrS: 1..16");
             globalPCIters = (int)a->numOr("globalPCIters", globalPCIters);
             {
+                const std::string pp = a->strOr("pcPattern", pcPattern);
+                if (pp != "uniform" && pp != "stateInfo") throw Error("adjEqnOption.pcPattern " + pp + ": uniform or stateInfo");
+                if (pp != pcPattern) { pcPattern = pp; kry.symbolic = false; kry.pcValid = false; }
                 const int bc = (int)a->numOr("pcBlockCells", pcBlockCells);
                 if (bc != pcBlockCells) { pcBlockCells = bc; kry.symbolic = false; kry.pcValid = false; }
             }

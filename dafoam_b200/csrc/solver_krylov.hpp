@@ -61,8 +61,16 @@ struct CellGraph
         ballWith(seeds, nSeeds, radius, out, sc.stamp, sc.tick);
     }
     // cells within `radius` hops of the seeds (seeds included), appended to out (cleared first)
-    void ballWith(const int* seeds, int nSeeds, int radius, std::vector<int>& out, std::vector<int>& stamp, int& tick) const
+    // levelEnd != nullptr: (*levelEnd)[k] = number of cells within k hops (the list is in breadth-first order), k = 0..radius
+    void ball(const int* seeds, int nSeeds, int radius, std::vector<int>& out, Scratch& sc, std::vector<int>* levelEnd) const
     {
+        if ((int)sc.stamp.size() != nC) sc.stamp.assign(nC, 0);
+        ballWith(seeds, nSeeds, radius, out, sc.stamp, sc.tick, levelEnd);
+    }
+    void ballWith(const int* seeds, int nSeeds, int radius, std::vector<int>& out, std::vector<int>& stamp, int& tick,
+                  std::vector<int>* levelEnd = nullptr) const
+    {
+        if (levelEnd) levelEnd->clear();
         out.clear();
         tick++;
         for (int i = 0; i < nSeeds; i++)
@@ -72,6 +80,7 @@ struct CellGraph
                 out.push_back(seeds[i]);
             }
         size_t lo = 0;
+        if (levelEnd) levelEnd->push_back((int)out.size());
         for (int r = 0; r < radius; r++)
         {
             const size_t hi = out.size();
@@ -89,6 +98,7 @@ struct CellGraph
                 }
             }
             lo = hi;
+            if (levelEnd) levelEnd->push_back((int)out.size());
         }
     }
 };
@@ -136,7 +146,43 @@ inline void Solver::pcSymbolic()
     CellGraph G;
     G.build(hm);
     lap("cell graph");
-    const int Lcc = pcConLevel, Lfc = 0, Lcf = 0;
+    // connectivity levels of the pattern.  Row = a state, columns = the residuals that see it.
+    //   lvCell[s][r]  cell residual r (0 URes, 1 pRes, 2 nuTildaRes) of the cells within that many levels of the state's cell, s = 0 U, 1 p, 2 nuTilda
+    //   lvPhiRes[s]   phiRes of the faces of the cells within that many levels of the state's cell
+    //   lvOfPhi[r]    cell residual r of the cells within that many levels of the two cells of a phi state's face
+    //   phiPhi        a phi state is seen by phiRes of the faces of its two cells (0: of its own face only)
+    const bool stateInfo = pcPattern == "stateInfo" && !par.comp;
+    int lvCell[3][3], lvPhiRes[3], lvOfPhi[3], phiPhi = 0;
+    if (stateInfo)
+    {
+        // URes {U,p,nut,phi | U,p,nut | U}; pRes {U,p,nut,phi | U,p,nut,phi | U,p,nut | U} capped at 2; phiRes {U,p,nut,phi | U,p,nut | U} capped
+        // at 1; nuTildaRes {U,nuTilda,phi | U,nuTilda | nuTilda}  (nut -> nuTilda: DASpalartAllmaras::correctStateResidualModelCon)
+        const int cell[3][3] = {{2, 2, 1}, {1, 2, -1}, {1, 2, 2}}; // [state U,p,nt][residual U,p,nt]
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) lvCell[a][b] = std::min(cell[a][b], pcConLevel);
+        for (int a = 0; a < 3; a++) lvPhiRes[a] = 1;
+        lvOfPhi[0] = 0; lvOfPhi[1] = 1; lvOfPhi[2] = 0;
+        phiPhi = 1;
+    }
+    else
+    {
+        for (int a = 0; a < 3; a++)
+        {
+            for (int b = 0; b < 3; b++) lvCell[a][b] = pcConLevel;
+            lvPhiRes[a] = 0;
+            lvOfPhi[a] = 0;
+        }
+        // (measured on the host build, 18k cells: adding the flux couplings of the reference's table to the uniform pattern -- phiRes one
+        // level away, pRes-phi one level away, phiRes-phi of the two cells' faces -- costs 21 % more entries for 3.6 % fewer applications)
+    }
+    int Lcc = 0, Lfc = 0, Lcf = 0; // the largest levels: cell-cell, cell state -> phiRes, phi state -> cell residual
+    for (int a = 0; a < 3; a++)
+    {
+        for (int b = 0; b < 3; b++) Lcc = std::max(Lcc, lvCell[a][b]);
+        Lfc = std::max(Lfc, lvPhiRes[a]);
+        Lcf = std::max(Lcf, lvOfPhi[a]);
+    }
+    if (phiPhi) Lcf = std::max(Lcf, 1);
     // owned faces per cell (a face belongs to the block of its owner cell)
     // (a cut face whose owner is a ghost sits in the block of its local cell; its row is a trivial identity row)
     auto blockCell = [&](int f) { return hm.own[f] < nC ? hm.own[f] : hm.nei[f]; };
@@ -245,25 +291,34 @@ inline void Solver::pcSymbolic()
     struct Work
     {
         CellGraph::Scratch sc;
-        std::vector<int> cellsBall, cols, faces, width;
+        std::vector<int> cellsBall, cols, faces, width, levelEnd;
         int64_t nnz = 0;
     };
     const int nThreads = std::max(1, detail::hostThreads() / std::max(1, nRanks)); // the ranks of a node share its cores
     std::vector<Work> work(nThreads);
     for (Work& w : work) w.width.assign(nG, 0);
-    auto cellRowCols = [&](Work& w, int c) {
+    // state kind of cell state s (0 U, 1 p, 2 nuTilda; the compressible T follows p) and residual kind of cell-residual slot s
+    auto kindOf = [&](int s) { return s < 3 ? 0 : (s == ns - 1 && par.turb ? 2 : 1); };
+    // the ball of the cell is gathered once (cellBall) and shared by the rows of its states
+    auto cellBall = [&](Work& w, int c) { G.ball(&c, 1, std::max(Lcc, Lfc), w.cellsBall, w.sc, &w.levelEnd); };
+    auto cellRowCols = [&](Work& w, int c, int s) {
         std::vector<int>& cols = w.cols;
         cols.clear();
-        G.ball(&c, 1, Lcc, w.cellsBall, w.sc);
-        for (int x : w.cellsBall)
+        const int ks = kindOf(s);
+        auto within = [&](int lv) { return lv < 0 ? 0 : w.levelEnd[std::min(lv, (int)w.levelEnd.size() - 1)]; };
+        for (int r = 0; r < ns; r++)
         {
-            if (blk > 0 && x / blk != c / blk) continue; // block-Jacobi: couplings across blocks are dropped
-            for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
-            for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
+            const int nIn = within(lvCell[ks][kindOf(r)]);
+            for (int q = 0; q < nIn; q++)
+            {
+                const int x = w.cellsBall[q];
+                if (blk > 0 && x / blk != c / blk) continue; // block-Jacobi: couplings across blocks are dropped
+                cols.push_back(K.iperm[r < 3 ? 3 * x + r : r * nC + x]);
+            }
         }
-        G.ball(&c, 1, Lfc, w.cellsBall, w.sc);
         w.faces.clear();
-        for (int x : w.cellsBall) facesOf(x, w.faces);
+        const int nIn = within(lvPhiRes[ks]);
+        for (int q = 0; q < nIn; q++) facesOf(w.cellsBall[q], w.faces);
         std::sort(w.faces.begin(), w.faces.end());
         w.faces.erase(std::unique(w.faces.begin(), w.faces.end()), w.faces.end());
         for (int f : w.faces)
@@ -280,23 +335,40 @@ inline void Solver::pcSymbolic()
         }
         int seeds[2];
         const int nSeeds = faceSeeds(f, seeds);
-        G.ball(seeds, nSeeds, Lcf, w.cellsBall, w.sc);
-        for (int x : w.cellsBall)
+        G.ball(seeds, nSeeds, Lcf, w.cellsBall, w.sc, &w.levelEnd);
+        for (int r = 0; r < ns; r++)
         {
-            if (blk > 0 && x / blk != blockCell(f) / blk) continue;
-            for (int s = 0; s < 3; s++) cols.push_back(K.iperm[3 * x + s]);
-            for (int s = 3; s < ns; s++) cols.push_back(K.iperm[s * nC + x]);
+            const int lv = lvOfPhi[kindOf(r)];
+            const int nIn = lv < 0 ? 0 : w.levelEnd[std::min(lv, (int)w.levelEnd.size() - 1)];
+            for (int q = 0; q < nIn; q++)
+            {
+                const int x = w.cellsBall[q];
+                if (blk > 0 && x / blk != blockCell(f) / blk) continue;
+                cols.push_back(K.iperm[r < 3 ? 3 * x + r : r * nC + x]);
+            }
         }
-        cols.push_back(K.iperm[offPhi + f]);
+        if (phiPhi)
+        {
+            w.faces.clear();
+            for (int q = 0; q < nSeeds; q++) facesOf(seeds[q], w.faces);
+            w.faces.push_back(f);
+            std::sort(w.faces.begin(), w.faces.end());
+            w.faces.erase(std::unique(w.faces.begin(), w.faces.end()), w.faces.end());
+            for (int g : w.faces)
+                if (g == f || !(blk > 0 && blockCell(g) / blk != blockCell(f) / blk)) cols.push_back(K.iperm[offPhi + g]);
+        }
+        else
+            cols.push_back(K.iperm[offPhi + f]);
         std::sort(cols.begin(), cols.end());
     };
     detail::parallelFor(nC, nThreads, [&](int t, int b, int e) {
         Work& w = work[t];
         for (int c = b; c < e; c++)
         {
-            cellRowCols(w, c);
+            cellBall(w, c);
             for (int s = 0; s < ns; s++)
             {
+                if (s == 0 || s >= 3) cellRowCols(w, c, s); // the three components of U share their columns
                 const int i = K.iperm[s < 3 ? 3 * c + s : s * nC + c];
                 K.rowLen[i] = (int)w.cols.size();
                 w.width[groupOfRow[i]] = std::max(w.width[groupOfRow[i]], (int)w.cols.size());
@@ -355,8 +427,12 @@ inline void Solver::pcSymbolic()
         Work& w = work[t];
         for (int c = b; c < e; c++)
         {
-            cellRowCols(w, c);
-            for (int s = 0; s < ns; s++) putRow(w, K.iperm[s < 3 ? 3 * c + s : s * nC + c]);
+            cellBall(w, c);
+            for (int s = 0; s < ns; s++)
+            {
+                if (s == 0 || s >= 3) cellRowCols(w, c, s);
+                putRow(w, K.iperm[s < 3 ? 3 * c + s : s * nC + c]);
+            }
         }
     });
     detail::parallelFor(nF, nThreads, [&](int t, int b, int e) {

@@ -563,6 +563,12 @@ class pyDASolvers:
             PCMat.vals = np.concatenate([PCMat.vals[keep], vals])
         PCMat.assembled = True
 
+    def getPCMatrixSize(self):
+        """(rows, stored entries) of the dRdWTPC pattern of the last calcdRdWT(1, ...)."""
+        n, nnz = C.c_int64(), C.c_int64()
+        self._raise(self._L.dab_get_pc_matrix(self._h, C.byref(n), C.byref(nnz), None, None, None))
+        return int(n.value), int(nnz.value)
+
     def getPCMatrix(self):
         """(row_ptr, cols, vals) of the assembled dRdWTPC (CSR, external numbering); needs "dRdWTPC" in writeJacobians."""
         n, nnz = C.c_int64(), C.c_int64()

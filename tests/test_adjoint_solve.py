@@ -309,6 +309,19 @@ def test_preconditioner_variants_reach_the_same_adjoint():
         assert it < 600
     with pytest.raises(Exception):
         sol.updateDAOption(dict(adjEqnOption=dict(pcStorage="fp16")))
+    # adjEqnOption.pcPattern "stateInfo": the reference's per-(residual, state) connectivity levels (DAStateInfoSimpleFoam.C:75-99,
+    # DASpalartAllmaras.C:364-373, capped by maxResConLv4JacPCMat) -- a sparser matrix, the same adjoint
+    pc = Mat()
+    sol.updateDAOption(dict(adjEqnOption=dict(pcBlockCells=0, pcStorage="fp64", pcPattern="uniform", pcConLevel=3)))
+    sol.calcdRdWT(1, pc)
+    nnz_uniform = sol.getPCMatrixSize()[1]
+    psi, it = _solve_with(sol, W, dict(pcBlockCells=0, pcStorage="fp64", pcPattern="stateInfo", pcConLevel=3))
+    assert np.linalg.norm(psi - psi0) <= 1e-6 * np.linalg.norm(psi0) and it < 600
+    sol.calcdRdWT(1, pc)
+    assert sol.getPCMatrixSize()[1] < 0.8 * nnz_uniform, (sol.getPCMatrixSize(), nnz_uniform)
+    sol.updateDAOption(dict(adjEqnOption=dict(pcPattern="uniform", pcConLevel=2)))
+    with pytest.raises(Exception):
+        sol.updateDAOption(dict(adjEqnOption=dict(pcPattern="dense")))
 
 
 def test_fixed_point_then_gmres_on_the_same_handle():
